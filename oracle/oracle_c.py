@@ -1,0 +1,241 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of the C oracle (oracle/orb_oracle.c).
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs only; never by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "liborb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("d", C.c_double * 4), ("width", C.c_int), ("height", C.c_int)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "orb_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B" if force else "-s"], stdout=subprocess.DEVNULL)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        vp, ci, cf, cd = C.c_void_p, C.c_int, C.c_float, C.c_double
+        L.orc_extractor_create.restype = vp
+        L.orc_extractor_create.argtypes = [ci, cf, ci, ci, ci]
+        L.orc_extractor_destroy.argtypes = [vp]
+        L.orc_extractor_tables.argtypes = [vp] + [vp] * 6
+        L.orc_level_size.argtypes = [vp, ci, ci, ci, vp, vp]
+        L.orc_extract.restype = ci
+        L.orc_extract.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci]
+        for f in ("orc_get_level", "orc_get_blur", "orc_get_score"):
+            getattr(L, f).restype = ci
+            getattr(L, f).argtypes = [vp, ci, vp]
+        for f in ("orc_get_candidates", "orc_get_distributed"):
+            getattr(L, f).restype = ci
+            getattr(L, f).argtypes = [vp, ci, vp, ci]
+        L.orc_resize_linear_u8.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci]
+        L.orc_gaussian7_s2_u8.argtypes = [vp, ci, ci, ci, vp, ci]
+        L.orc_fast_score_u8.argtypes = [vp, ci, ci, ci, vp]
+        L.orc_fast_nms.restype = ci
+        L.orc_fast_nms.argtypes = [vp, ci, ci, ci, ci, vp, ci]
+        L.orc_fast_atan2.restype = cf
+        L.orc_fast_atan2.argtypes = [cf, cf]
+        L.orc_distribute.restype = ci
+        L.orc_distribute.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, ci]
+        L.orc_hamming256.restype = ci
+        L.orc_hamming256.argtypes = [vp, vp]
+        L.orc_stereo_match.argtypes = [vp, vp, ci, vp, vp, ci, cd, cd, cd, vp, vp]
+        L.orc_projection_match.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, cd, vp, vp]
+        L.orc_knn2.argtypes = [vp, ci, vp, C.c_int64, C.c_int64, vp]
+        L.orc_stereo_frames.restype = C.c_int64
+        L.orc_stereo_frames.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Extractor:
+    def __init__(self, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.L = lib()
+        self.h = self.L.orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        if not self.h:
+            raise ValueError("bad extractor parameters")
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_extractor_destroy(self.h)
+            self.h = None
+
+    def tables(self):
+        n = self.nlevels
+        sc, isc, s2, is2 = (np.zeros(n, np.float32) for _ in range(4))
+        per = np.zeros(n, np.int32)
+        umax = np.zeros(16, np.int32)
+        self.L.orc_extractor_tables(self.h, _p(sc), _p(isc), _p(s2), _p(is2), _p(per), _p(umax))
+        return dict(scale=sc, inv_scale=isc, sigma2=s2, inv_sigma2=is2, per_level=per, umax=umax)
+
+    def level_size(self, w, h, level):
+        lw, lh = C.c_int(), C.c_int()
+        self.L.orc_level_size(self.h, w, h, level, C.byref(lw), C.byref(lh))
+        return lw.value, lh.value
+
+    def extract(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape if img.ndim == 2 else (0, 0)
+        cap = self.nfeatures + 4 * self.nlevels + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = self.L.orc_extract(self.h, _p(img) if img.size else None, w, h, w, _p(kps), _p(desc), cap)
+        if n < 0:
+            raise RuntimeError(f"orc_extract failed: {n}")
+        self._wh = (w, h)
+        return kps[:n].copy(), desc[:n].copy()
+
+    def _plane(self, fn, level):
+        lw, lh = self.level_size(*self._wh, level)
+        out = np.zeros((lh, lw), np.uint8)
+        if fn(self.h, level, _p(out)) != 0:
+            return None
+        return out
+
+    def level(self, l):
+        return self._plane(self.L.orc_get_level, l)
+
+    def blur(self, l):
+        return self._plane(self.L.orc_get_blur, l)
+
+    def score(self, l):
+        return self._plane(self.L.orc_get_score, l)
+
+    def candidates(self, l, cap=1 << 16):
+        out = np.zeros((cap, 3), np.float32)
+        n = self.L.orc_get_candidates(self.h, l, _p(out), cap)
+        return out[:n].copy()
+
+    def distributed(self, l, cap=1 << 16):
+        out = np.zeros((cap, 3), np.float32)
+        n = self.L.orc_get_distributed(self.h, l, _p(out), cap)
+        return out[:n].copy()
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def gaussian7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.zeros_like(src)
+    lib().orc_gaussian7_s2_u8(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), src.shape[1])
+    return dst
+
+
+def fast_score(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().orc_fast_score_u8(_p(img), img.shape[1], img.shape[0], img.shape[1], _p(out))
+    return out
+
+
+def fast_nms(img, threshold, cap=1 << 16):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((cap, 3), np.float32)
+    n = lib().orc_fast_nms(_p(img), img.shape[1], img.shape[0], img.shape[1], threshold, _p(out), cap)
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return np.float32(lib().orc_fast_atan2(float(y), float(x)))
+
+
+def distribute(xyr, min_x, max_x, min_y, max_y, n_want):
+    xyr = np.ascontiguousarray(xyr, np.float32)
+    out = np.zeros((max(len(xyr), 1), 3), np.float32)
+    n = lib().orc_distribute(_p(xyr), len(xyr), min_x, max_x, min_y, max_y, n_want, _p(out), len(out))
+    if n < 0:
+        raise ValueError("distribute failed")
+    return out[:n].copy()
+
+
+def hamming256(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming256(_p(a), _p(b))
+
+
+def stereo_match(kl, dl, kr, dr, y_thr=3.0, max_dx=100.0, ratio=0.5):
+    kl, kr = np.ascontiguousarray(kl), np.ascontiguousarray(kr)
+    dl, dr = np.ascontiguousarray(dl, np.uint8), np.ascontiguousarray(dr, np.uint8)
+    idx = np.full(len(kl), -1, np.int32)
+    dist = np.full(len(kl), -1, np.int32)
+    lib().orc_stereo_match(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), y_thr, max_dx, ratio,
+                           _p(idx), _p(dist))
+    return idx, dist
+
+
+def make_camera(fx, fy, cx, cy, d, width, height):
+    cam = Camera()
+    cam.fx, cam.fy, cam.cx, cam.cy = fx, fy, cx, cy
+    for i in range(4):
+        cam.d[i] = d[i]
+    cam.width, cam.height = width, height
+    return cam
+
+
+def projection_match(xw, mp_desc, skip, rt, cam, kps, kp_desc, radius, ratio=0.5):
+    xw = np.ascontiguousarray(xw, np.float64)
+    mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+    skip = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+    rt = np.ascontiguousarray(rt, np.float64).reshape(12)
+    kps = np.ascontiguousarray(kps)
+    kp_desc = np.ascontiguousarray(kp_desc, np.uint8)
+    m = len(kps)
+    to_q = np.full(m, -1, np.int32)
+    dist = np.full(m, -1, np.int32)
+    lib().orc_projection_match(_p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), C.byref(cam), _p(kps),
+                               _p(kp_desc), m, radius, ratio, _p(to_q), _p(dist))
+    return to_q, dist
+
+
+def knn2(queries, db, idx_base=0):
+    queries = np.ascontiguousarray(queries, np.uint8)
+    db = np.ascontiguousarray(db, np.uint8)
+    out = np.zeros((len(queries), 4), np.int32)
+    lib().orc_knn2(_p(queries), len(queries), _p(db), len(db), idx_base, _p(out))
+    return out
+
+
+def stereo_frames(left, right, nthreads, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    count, h, w = left.shape
+    tot = C.c_int64()
+    m = lib().orc_stereo_frames(_p(left), _p(right), count, w, h, nthreads, nfeatures, scale_factor,
+                                nlevels, ini_th, min_th, C.byref(tot))
+    return int(m), int(tot.value)

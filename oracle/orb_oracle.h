@@ -1,0 +1,93 @@
+/* TEST INFRASTRUCTURE ONLY -- the CPU oracle.  Never linked, imported or called by
+ * the product path (slam-toolkit_b200/); only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may use it, and only as the
+ * checker / reported baseline.
+ *
+ * Dependency-free C restatement of the reference's ORB front end:
+ *   src/orb_extractor.cpp:72-147,410-853,1034-1132, include/orb_extractor.h:87-103,
+ *   src/matcher.cpp:54-209, src/camera.cpp:26-36,50-79 (paths in geonuklee/slam-toolkit).
+ * The OpenCV 3.4 primitives the reference delegates to (cv::FAST, cv::resize,
+ * cv::GaussianBlur, cv::fastAtan2, cvRound) are replaced by closed-form integer /
+ * float32 models that are pinned bit-for-bit against cv2 4.13 by
+ * tests/test_oracle_vs_cv2.py and the fixtures in tests/golden/.
+ *
+ * Parity status: the reference ships no tests / golden vectors, and its own
+ * keypoint order depends on heap addresses (src/orb_extractor.cpp:684), so parity
+ * is defined against THIS canonical oracle with the declared tie rules T1-T4
+ * (SURVEY.md §8c).  "Parity unpinned by the reference's own tests."
+ */
+#ifndef ORB_ORACLE_H_
+#define ORB_ORACLE_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* byte-identical to cv::KeyPoint (28 B) */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orc_keypoint;
+
+typedef struct orc_extractor orc_extractor;
+
+orc_extractor *orc_extractor_create(int nfeatures, float scale_factor, int nlevels,
+                                    int ini_th_fast, int min_th_fast);
+void orc_extractor_destroy(orc_extractor *ex);
+/* tables: out arrays of nlevels entries each (any may be NULL) */
+void orc_extractor_tables(const orc_extractor *ex, float *scale, float *inv_scale, float *sigma2,
+                          float *inv_sigma2, int *features_per_level, int *umax16);
+void orc_level_size(const orc_extractor *ex, int w, int h, int level, int *lw, int *lh);
+
+/* full extraction; returns keypoint count (<= cap) or <0 on error */
+int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, int stride,
+                orc_keypoint *kps, uint8_t *desc, int cap);
+
+/* stage taps, valid after orc_extract on the same handle */
+int orc_get_level(const orc_extractor *ex, int level, uint8_t *out /* lw*lh */);
+int orc_get_blur(const orc_extractor *ex, int level, uint8_t *out /* lw*lh */);
+int orc_get_score(const orc_extractor *ex, int level, uint8_t *out /* lw*lh, FAST best map */);
+int orc_get_candidates(const orc_extractor *ex, int level, float *xyr /* cap*3 */, int cap);
+int orc_get_distributed(const orc_extractor *ex, int level, float *xyr /* cap*3 */, int cap);
+
+/* primitive models (pinned to cv2) */
+void orc_resize_linear_u8(const uint8_t *src, int sw, int sh, int sstride,
+                          uint8_t *dst, int dw, int dh, int dstride);
+void orc_gaussian7_s2_u8(const uint8_t *src, int w, int h, int sstride, uint8_t *dst, int dstride);
+void orc_fast_score_u8(const uint8_t *img, int w, int h, int stride, uint8_t *score /* w*h */);
+int orc_fast_nms(const uint8_t *img, int w, int h, int stride, int threshold,
+                 float *xyr /* cap*3 */, int cap);
+float orc_fast_atan2(float y, float x);
+int orc_distribute(const float *xyr, int n, int min_x, int max_x, int min_y, int max_y,
+                   int n_want, float *out_xyr, int cap);
+
+/* matching */
+int orc_hamming256(const void *a, const void *b);
+void orc_stereo_match(const orc_keypoint *kl, const uint8_t *dl, int nl,
+                      const orc_keypoint *kr, const uint8_t *dr, int nr,
+                      double y_thr, double max_dx, double ratio, int *out_idx, int *out_dist);
+typedef struct {
+    double fx, fy, cx, cy;
+    double d[4];
+    int width, height;
+} orc_camera;
+/* kp_to_query[m] = winning map-point index or -1; kp_dist[m] = its distance */
+void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                          const double rt[12], const orc_camera *cam,
+                          const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                          double ratio, int *kp_to_query, int *kp_dist);
+/* out[q*4] = {idx0, dist0, idx1, dist1}; lexicographic (dist, idx) top-2 */
+void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base,
+              int32_t *out);
+
+/* CPU baseline helper: extract L + extract R + stereo match for `count` stereo
+ * frames with `nthreads` worker threads (one frame per thread at a time).
+ * left/right: count contiguous w*h images.  Returns total matches. */
+int64_t orc_stereo_frames(const uint8_t *left, const uint8_t *right, int count, int w, int h,
+                          int nthreads, int nfeatures, float scale_factor, int nlevels,
+                          int ini_th, int min_th, int64_t *total_kps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

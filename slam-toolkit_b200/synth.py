@@ -1,0 +1,118 @@
+"""Seeded synthetic KITTI-shaped inputs.  numpy only, frozen.
+
+KITTI itself is not available offline; the reference's workload shape is
+1241x376 8-bit gray stereo (reference src/dataset.cpp:103-104).  Every generator
+here is a pure function of its seed so CPU oracle, CUDA path and golden fixtures
+provably see identical bytes (tests/golden/synth_sha256.json pins seeds 0-7).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+KITTI_W, KITTI_H = 1241, 376
+DISPARITY = 24
+_EXTRA = 128
+# KITTI seq-00 intrinsics / baseline as hard-coded by reference src/dataset.cpp:87-101
+KITTI_FX = 7.188560000000e+02
+KITTI_FY = 7.188560000000e+02
+KITTI_CX = 6.071928e+02
+KITTI_CY = 1.852157000000e+02
+KITTI_BASELINE = 3.861448000000e+02 / 7.188560000000e+02
+
+
+def _blur_sigma08(a: np.ndarray) -> np.ndarray:
+    """Separable Gaussian, sigma 0.8, radius 3, edge-replicated (float32)."""
+    r = 3
+    x = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-(x * x) / (2 * 0.8 * 0.8))
+    k = (k / k.sum()).astype(np.float32)
+    p = np.pad(a, ((0, 0), (r, r)), mode="edge")
+    h = np.zeros_like(a)
+    for i in range(2 * r + 1):
+        h += k[i] * p[:, i:i + a.shape[1]]
+    p = np.pad(h, ((r, r), (0, 0)), mode="edge")
+    v = np.zeros_like(a)
+    for i in range(2 * r + 1):
+        v += k[i] * p[i:i + a.shape[0], :]
+    return v
+
+
+def canvas(seed: int, width: int = KITTI_W, height: int = KITTI_H) -> np.ndarray:
+    """u8 canvas height x (width+128); stereo views are column windows of it."""
+    rng = np.random.default_rng(seed)
+    cw = width + _EXTRA
+    xs = np.arange(cw, dtype=np.float32)[None, :]
+    ys = np.arange(height, dtype=np.float32)[:, None]
+    c = (96.0 + 48.0 * np.sin(xs / 97.0) + 32.0 * np.cos(ys / 53.0)).astype(np.float32)
+    n_rect = max(1, int(round(900 * (cw * height) / float((KITTI_W + _EXTRA) * KITTI_H))))
+    for _ in range(n_rect):
+        x = int(rng.integers(0, cw - 8))
+        y = int(rng.integers(0, max(1, height - 8)))
+        w = int(rng.integers(6, 70))
+        h = int(rng.integers(6, 50))
+        val = float(rng.integers(0, 256))
+        c[y:y + h, x:x + w] = val
+    c = _blur_sigma08(c)
+    c = c + rng.normal(0.0, 2.0, c.shape).astype(np.float32)
+    return np.clip(np.rint(c), 0, 255).astype(np.uint8)
+
+
+def stereo_pair(seed: int, width: int = KITTI_W, height: int = KITTI_H):
+    """(left, right) contiguous u8 images; right = left shifted by 24 px
+    (uniform disparity so every true match has dy=0, 0<=dx<=100; cf. the
+    filter at reference src/matcher.cpp:103-110)."""
+    c = canvas(seed, width, height)
+    left = np.ascontiguousarray(c[:, :width])
+    right = np.ascontiguousarray(c[:, DISPARITY:DISPARITY + width])
+    return left, right
+
+
+def knn_database(m: int, seed: int = 1234) -> np.ndarray:
+    """m x 32 u8 random descriptors (BASELINE config 4)."""
+    return np.random.default_rng(seed).integers(0, 256, (m, 32), dtype=np.uint8)
+
+
+def knn_queries(db: np.ndarray, q: int, seed: int = 5678, max_flips: int = 40):
+    """q rows picked from db with 0..max_flips random bit flips each, so the
+    ratio test of reference src/matcher.cpp:125 both passes and fails."""
+    rng = np.random.default_rng(seed)
+    rows = rng.choice(db.shape[0], q, replace=db.shape[0] < q)
+    out = db[rows].copy()
+    for i in range(q):
+        nf = int(rng.integers(0, max_flips + 1))
+        bits = rng.integers(0, 256, nf)
+        for b in bits:
+            out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    return out, rows
+
+
+def projection_scene(kps_xy: np.ndarray, desc: np.ndarray, n_points: int, seed: int = 99,
+                     width: int = KITTI_W, height: int = KITTI_H):
+    """Map points for BASELINE config 5: Xw uniform in the KITTI frustum
+    (z~U[2,80] m, back-projected from uniform pixels), descriptors = 10 % noisy
+    copies of frame descriptors placed within 20 px of that keypoint, 90 % random.
+    Returns (Xw float64 n x 3, desc u8 n x 32).  Pose is identity."""
+    rng = np.random.default_rng(seed)
+    n_kp = kps_xy.shape[0]
+    u = rng.uniform(0, width, n_points)
+    v = rng.uniform(0, height, n_points)
+    z = rng.uniform(2.0, 80.0, n_points)
+    d = rng.integers(0, 256, (n_points, 32), dtype=np.uint8)
+    if n_kp > 0:
+        n_copy = n_points // 10
+        sel = rng.choice(n_points, n_copy, replace=False)
+        src = rng.integers(0, n_kp, n_copy)
+        ang = rng.uniform(0, 2 * np.pi, n_copy)
+        rad = rng.uniform(0, 20.0, n_copy)
+        u[sel] = kps_xy[src, 0] + rad * np.cos(ang)
+        v[sel] = kps_xy[src, 1] + rad * np.sin(ang)
+        d[sel] = desc[src]
+        nflip = rng.integers(0, 31, n_copy)
+        for i in range(n_copy):
+            for b in rng.integers(0, 256, int(nflip[i])):
+                d[sel[i], b >> 3] ^= np.uint8(1 << (b & 7))
+    X = np.empty((n_points, 3), dtype=np.float64)
+    X[:, 0] = (u - KITTI_CX) / KITTI_FX * z
+    X[:, 1] = (v - KITTI_CY) / KITTI_FY * z
+    X[:, 2] = z
+    return X, np.ascontiguousarray(d)
