@@ -1,0 +1,208 @@
+/* sfe.h -- C ABI of the B200-native ORB front end ("slam front end", sfe).
+ *
+ * Drop-in boundary for the one data-parallel hot path of geonuklee/slam-toolkit:
+ *   ORBextractor::extract            include/orb_extractor.h:51-59, src/orb_extractor.cpp:1043-1105
+ *   ORBextractor::DescriptorDistance include/orb_extractor.h:87-103
+ *   StereoMatch                      include/matcher.h:33,  src/matcher.cpp:54-132
+ *   ProjectionMatch                  include/matcher.h:35-38, src/matcher.cpp:134-209
+ *   (+ the brute-force top-2 kNN that BASELINE config 4 defines over the same inner loop)
+ * The reference has no FFI layer (it is one C++ library); a maintainer binds these
+ * symbols through include/sfe_adapter.hpp, which keeps the reference's own class and
+ * function signatures.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; every call returns an int status.
+ *   - the library never allocates caller-visible memory: the caller passes capacity, gets counts.
+ *   - "host" entry points take host pointers and copy to/from the device inside the call;
+ *     "_dev" entry points take device pointers of the handle's device (resident data).
+ *   - a handle owns one CUDA device + stream + its buffers and is NOT re-entrant (the reference's
+ *     extract() is not either: it mutates mvImagePyramid, src/orb_extractor.cpp:1115);
+ *     use one handle per thread / per GPU.
+ *   - there is no CPU fallback: without a usable CUDA device every compute call fails with
+ *     SFE_ERR_NO_DEVICE / SFE_ERR_CUDA.
+ */
+#ifndef SFE_H_
+#define SFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFE_ABI_VERSION 1
+
+enum {
+    SFE_OK = 0,
+    SFE_ERR_BAD_ARG = 1,     /* null pointer, non-positive size, unsupported geometry */
+    SFE_ERR_CAPACITY = 2,    /* caller capacity or an internal candidate buffer too small */
+    SFE_ERR_CUDA = 3,        /* a CUDA runtime call failed; see sfe_last_error() */
+    SFE_ERR_NO_DEVICE = 4,   /* no CUDA device (there is no CPU fallback) */
+    SFE_ERR_UNSUPPORTED = 5  /* parameters outside what the kernels were built for */
+};
+
+/* byte-identical to cv::KeyPoint (28 B: pt.x, pt.y, size, angle, response, octave, class_id),
+ * so the C++ adapter fills std::vector<cv::KeyPoint> with one memcpy. */
+typedef struct sfe_keypoint {
+    float x, y;      /* level-0 pixel coordinates (pt *= scale, src/orb_extractor.cpp:1095-1101) */
+    float size;      /* (int)(31 * scale[octave]), :837-847 */
+    float angle;     /* degrees in [0,360), IC_Angle + fastAtan2, :77-104 */
+    float response;  /* FAST score, cv::FAST cornerScore */
+    int32_t octave;
+    int32_t class_id; /* always -1 */
+} sfe_keypoint;
+
+/* the five ORBextractor constructor arguments, include/orb_extractor.h:51 */
+typedef struct sfe_extractor_params {
+    int32_t nfeatures;    /* 2000 in the reference pipeline (src/pipeline.cpp:46-50) */
+    float scale_factor;   /* 1.2f */
+    int32_t nlevels;      /* 8 */
+    int32_t ini_th_fast;  /* 20 */
+    int32_t min_th_fast;  /* 7 */
+} sfe_extractor_params;
+
+/* StereoMatch constants, src/matcher.cpp:60,68-70 */
+typedef struct sfe_stereo_params {
+    double y_threshold;      /* 3.0 */
+    double max_dx;           /* 100.0 */
+    double best12_threshold; /* 0.5 */
+} sfe_stereo_params;
+
+/* Camera, src/camera.cpp:26-79: pinhole + 4-coefficient radial-tangential distortion */
+typedef struct sfe_camera {
+    double fx, fy, cx, cy;
+    double d[4];
+    int32_t width, height;
+} sfe_camera;
+
+typedef struct sfe_extractor sfe_extractor;
+typedef struct sfe_matcher sfe_matcher;
+typedef struct sfe_db sfe_db;
+typedef struct sfe_event sfe_event;
+
+/* ---- general -------------------------------------------------------------------------- */
+int sfe_abi_version(void);
+const char *sfe_status_string(int status);
+const char *sfe_last_error(void); /* thread-local detail of the last failure */
+int sfe_device_count(int *count);
+int sfe_host_alloc(void **ptr, size_t bytes); /* pinned host memory for the host entry points */
+int sfe_host_free(void *ptr);
+int sfe_device_alloc(int device, void **ptr, size_t bytes);
+int sfe_device_free(int device, void *ptr);
+int sfe_copy_to_device(int device, void *dst_dev, const void *src_host, size_t bytes);
+int sfe_copy_to_host(int device, void *dst_host, const void *src_dev, size_t bytes);
+/* CUDA events on a handle's own stream (bench timing must be taken on the launching stream) */
+int sfe_event_create(int device, sfe_event **ev);
+int sfe_event_destroy(sfe_event *ev);
+int sfe_event_record_extractor(sfe_event *ev, sfe_extractor *ex);
+int sfe_event_record_matcher(sfe_event *ev, sfe_matcher *m);
+int sfe_event_elapsed_ms(sfe_event *start, sfe_event *stop, float *ms); /* synchronises on stop */
+
+/* ---- ORBextractor (include/orb_extractor.h:45-133) -------------------------------------- */
+/* max_images: how many images one batched call may carry (device buffers are sized for it). */
+int sfe_extractor_create(const sfe_extractor_params *params, int device, int max_images,
+                         sfe_extractor **out);
+int sfe_extractor_destroy(sfe_extractor *ex);
+/* GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares
+ * (:63-83) + the per-level quotas; each out array has nlevels entries, any may be NULL. */
+int sfe_extractor_tables(const sfe_extractor *ex, float *scale, float *inv_scale, float *sigma2,
+                         float *inv_sigma2, int32_t *features_per_level);
+int sfe_extractor_level_size(const sfe_extractor *ex, int w, int h, int level, int *lw, int *lh);
+/* upper bound of keypoints one image can return (nfeatures + 3 per level + slack) */
+int sfe_extractor_max_keypoints(const sfe_extractor *ex, int *cap);
+
+/* extract(): one 8-bit gray image in, keypoints + 256-bit descriptors out (row i <-> keypoint i).
+ * An empty image (w==0 || h==0) is a silent success with *n_out = 0 (:1046-1047). */
+int sfe_extract(sfe_extractor *ex, const uint8_t *image, int w, int h, int stride,
+                sfe_keypoint *kps, uint8_t *desc /* cap*32 */, int cap, int *n_out);
+/* count images of identical geometry, image i at images + i*image_stride bytes; outputs for image i
+ * at kps + i*cap, desc + i*cap*32, n_out[i]. */
+int sfe_extract_batch(sfe_extractor *ex, const uint8_t *images, size_t image_stride, int count,
+                      int w, int h, int stride, sfe_keypoint *kps, uint8_t *desc, int cap,
+                      int32_t *n_out);
+int sfe_extract_batch_dev(sfe_extractor *ex, const uint8_t *images_dev, size_t image_stride,
+                          int count, int w, int h, int stride, sfe_keypoint *kps_dev,
+                          uint8_t *desc_dev, int cap, int32_t *n_out_dev);
+
+/* Keyframe path of the reference pipeline in one call (src/pipeline.cpp:243-249,
+ * src/frame.cpp:47,388): extract(left), extract(right), StereoMatch, for `frames` stereo pairs.
+ * stereo_idx[f*cap + i] = right keypoint index or -1 (SetStereoCorrespond, src/matcher.cpp:130);
+ * stereo_dist (optional, may be NULL) = accepted Hamming distance or -1. */
+int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *right,
+                      size_t image_stride, int frames, int w, int h, int stride,
+                      const sfe_stereo_params *sp, sfe_keypoint *kps_l, uint8_t *desc_l,
+                      int32_t *n_l, sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r,
+                      int32_t *stereo_idx, int32_t *stereo_dist, int cap);
+int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev,
+                          size_t image_stride, int frames, int w, int h, int stride,
+                          const sfe_stereo_params *sp, sfe_keypoint *kps_l_dev, uint8_t *desc_l_dev,
+                          int32_t *n_l_dev, sfe_keypoint *kps_r_dev, uint8_t *desc_r_dev,
+                          int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
+                          int cap);
+
+/* stage taps for parity tests (valid for the images of the last call on this handle) */
+int sfe_debug_level(sfe_extractor *ex, int image, int level, uint8_t *out /* lw*lh */);
+int sfe_debug_blur(sfe_extractor *ex, int image, int level, uint8_t *out /* lw*lh */);
+/* FAST candidates in the reference's vToDistributeKeys order (x, y window-relative, response) */
+int sfe_debug_candidates(sfe_extractor *ex, int image, int level, float *xyr, int cap, int *n);
+/* quadtree survivors in DistributeOctTree's list order */
+int sfe_debug_distributed(sfe_extractor *ex, int image, int level, float *xyr, int cap, int *n);
+/* number of kernel launches the handle issued since creation (bench's gpu_launches) */
+int sfe_extractor_launches(const sfe_extractor *ex, int64_t *launches);
+/* per-stage device time from CUDA events recorded on the handle's own stream between the stage
+ * kernels (no extra synchronisation).  Stages: 0 pyramid, 1 FAST cells, 2 quadtree, 3 blur,
+ * 4 orientation+rBRIEF, 5 stereo match.  ms[i] accumulates over `calls` batched calls. */
+int sfe_extractor_set_profiling(sfe_extractor *ex, int enable);
+int sfe_extractor_stage_ms(const sfe_extractor *ex, double *ms, int n, int64_t *calls);
+
+/* ---- matcher (include/matcher.h, DescriptorDistance) ------------------------------------- */
+int sfe_hamming256(const void *a, const void *b); /* DescriptorDistance of two 32-byte rows */
+
+int sfe_matcher_create(int device, sfe_matcher **out);
+int sfe_matcher_destroy(sfe_matcher *m);
+int sfe_matcher_launches(const sfe_matcher *m, int64_t *launches);
+
+/* StereoMatch on one frame's keypoints (host buffers) */
+int sfe_stereo_match(sfe_matcher *m, const sfe_keypoint *kps_l, const uint8_t *desc_l, int n_l,
+                     const sfe_keypoint *kps_r, const uint8_t *desc_r, int n_r,
+                     const sfe_stereo_params *sp, int32_t *out_idx /* n_l */,
+                     int32_t *out_dist /* n_l, optional */);
+
+/* ProjectionMatch: n map points (world xyz double[3], 32-B descriptor, optional skip byte = the
+ * host-side prefilter curr_frame->GetIndex(mp) >= 0, src/matcher.cpp:144) against a frame's m
+ * keypoints.  rt = row-major 3x4 [R|t] of predicted_Tcw.  Map points are visited in array order
+ * (the reference iterates a std::set<Mappoint*>, i.e. pointer order).
+ * kp_to_query[j] = index of the map point matched to keypoint j or -1 (the reference's
+ * std::map<int, Mappoint*>), kp_dist[j] = its Hamming distance or -1. */
+int sfe_projection_match(sfe_matcher *m, const double *xw, const uint8_t *mp_desc,
+                         const uint8_t *skip, int n, const double rt[12], const sfe_camera *cam,
+                         const sfe_keypoint *kps, const uint8_t *kp_desc, int m_kps, double radius,
+                         double best12_threshold, int32_t *kp_to_query, int32_t *kp_dist);
+int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev,
+                             const uint8_t *skip_dev, int n, const double rt[12],
+                             const sfe_camera *cam, const sfe_keypoint *kps_dev,
+                             const uint8_t *kp_desc_dev, int m_kps, double radius,
+                             double best12_threshold, int32_t *kp_to_query_dev,
+                             int32_t *kp_dist_dev);
+
+/* Brute-force top-2 over a resident descriptor database shard.
+ * idx_base = global index of the shard's first row (multi-GPU sharding). */
+int sfe_db_create(sfe_matcher *m, const uint8_t *desc_host, int64_t rows, int64_t idx_base,
+                  sfe_db **out);
+int sfe_db_destroy(sfe_db *db);
+/* out[q*4] = {idx0, dist0, idx1, dist1}: lexicographic (dist, idx) smallest two; -1/999999999
+ * when the shard holds fewer rows.  The ratio test is (2*dist0 < dist1) on the caller's side. */
+int sfe_knn2(sfe_matcher *m, const sfe_db *db, const uint8_t *queries, int q, int32_t *out);
+/* resident variant: keys_dev[q*2 + r] = (uint64)dist << 32 | global idx (r-th best);
+ * this is what one rank contributes to the all-gather. */
+int sfe_knn2_dev(sfe_matcher *m, const sfe_db *db, const uint8_t *queries_dev, int q,
+                 uint64_t *keys_dev);
+/* merge `shards` gathered key arrays (shards x q x 2) into out_dev[q*4] */
+int sfe_knn2_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int q,
+                       int32_t *out_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFE_H_ */

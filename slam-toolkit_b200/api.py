@@ -1,0 +1,478 @@
+"""Python binding of the sfe C ABI (include/sfe.h) with the reference's call surface.
+
+The reference's host code is C++ (its adapter is include/sfe_adapter.hpp); this module is the
+same surface for Python callers, tests and bench.py: ``ORBextractor.extract`` (reference
+include/orb_extractor.h:51-59), ``StereoMatch`` / ``ProjectionMatch`` (include/matcher.h:33-38)
+and the brute-force top-2 kNN.  Everything computes on the GPU through ``libsfe.so``; there is
+no CPU fallback -- a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfe.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28  # == sizeof(cv::KeyPoint)
+
+SFE_OK, SFE_ERR_BAD_ARG, SFE_ERR_CAPACITY, SFE_ERR_CUDA, SFE_ERR_NO_DEVICE, SFE_ERR_UNSUPPORTED = range(6)
+
+
+class SfeError(RuntimeError):
+    def __init__(self, status, detail):
+        super().__init__(f"sfe status {status}: {detail}")
+        self.status = status
+
+
+class ExtractorParams(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+class StereoParams(C.Structure):
+    _fields_ = [("y_threshold", C.c_double), ("max_dx", C.c_double), ("best12_threshold", C.c_double)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("d", C.c_double * 4), ("width", C.c_int32), ("height", C.c_int32)]
+
+    @staticmethod
+    def make(fx, fy, cx, cy, d, width, height):
+        c = Camera()
+        c.fx, c.fy, c.cx, c.cy, c.width, c.height = fx, fy, cx, cy, width, height
+        for i in range(4):
+            c.d[i] = d[i]
+        return c
+
+
+# every symbol include/sfe.h declares: name -> (restype, argtypes)
+_vp, _i, _sz, _d, _i64 = C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.c_int64
+_pp = C.POINTER(C.c_void_p)
+SIGNATURES = {
+    "sfe_abi_version": (_i, []),
+    "sfe_status_string": (C.c_char_p, [_i]),
+    "sfe_last_error": (C.c_char_p, []),
+    "sfe_device_count": (_i, [C.POINTER(_i)]),
+    "sfe_host_alloc": (_i, [_pp, _sz]),
+    "sfe_host_free": (_i, [_vp]),
+    "sfe_device_alloc": (_i, [_i, _pp, _sz]),
+    "sfe_device_free": (_i, [_i, _vp]),
+    "sfe_copy_to_device": (_i, [_i, _vp, _vp, _sz]),
+    "sfe_copy_to_host": (_i, [_i, _vp, _vp, _sz]),
+    "sfe_event_create": (_i, [_i, _pp]),
+    "sfe_event_destroy": (_i, [_vp]),
+    "sfe_event_record_extractor": (_i, [_vp, _vp]),
+    "sfe_event_record_matcher": (_i, [_vp, _vp]),
+    "sfe_event_elapsed_ms": (_i, [_vp, _vp, C.POINTER(C.c_float)]),
+    "sfe_extractor_create": (_i, [C.POINTER(ExtractorParams), _i, _i, _pp]),
+    "sfe_extractor_destroy": (_i, [_vp]),
+    "sfe_extractor_tables": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "sfe_extractor_level_size": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "sfe_extractor_max_keypoints": (_i, [_vp, C.POINTER(_i)]),
+    "sfe_extract": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
+    "sfe_extract_batch": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sfe_extract_batch_dev": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "sfe_stereo_frames": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
+    "sfe_stereo_frames_dev": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
+    "sfe_debug_level": (_i, [_vp, _i, _i, _vp]),
+    "sfe_debug_blur": (_i, [_vp, _i, _i, _vp]),
+    "sfe_debug_candidates": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
+    "sfe_debug_distributed": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
+    "sfe_extractor_launches": (_i, [_vp, C.POINTER(_i64)]),
+    "sfe_extractor_set_profiling": (_i, [_vp, _i]),
+    "sfe_extractor_stage_ms": (_i, [_vp, _vp, _i, C.POINTER(_i64)]),
+    "sfe_hamming256": (_i, [_vp, _vp]),
+    "sfe_matcher_create": (_i, [_i, _pp]),
+    "sfe_matcher_destroy": (_i, [_vp]),
+    "sfe_matcher_launches": (_i, [_vp, C.POINTER(_i64)]),
+    "sfe_stereo_match": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(StereoParams), _vp, _vp]),
+    "sfe_projection_match": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
+    "sfe_projection_match_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
+    "sfe_db_create": (_i, [_vp, _vp, _i64, _i64, _pp]),
+    "sfe_db_destroy": (_i, [_vp]),
+    "sfe_knn2": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "sfe_knn2_dev": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "sfe_knn2_merge_dev": (_i, [_vp, _vp, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libsfe.so (built in-tree by __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SfeError(SFE_ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                         "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.sfe_abi_version() != 1:
+            raise SfeError(SFE_ERR_UNSUPPORTED, "libsfe.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def _check(status):
+    if status != SFE_OK:
+        raise SfeError(status, lib().sfe_last_error().decode() or lib().sfe_status_string(status).decode())
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    lib().sfe_device_count(C.byref(n))
+    return n.value
+
+
+def hamming256(a, b) -> int:
+    """ORBextractor::DescriptorDistance (reference include/orb_extractor.h:87-103)."""
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().sfe_hamming256(_p(a), _p(b))
+
+
+class PinnedArray:
+    """numpy view of pinned host memory (cudaHostAlloc) for the host entry points."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.nbytes = max(int(np.prod(self.shape)) * self.dtype.itemsize, 1)
+        ptr = C.c_void_p()
+        _check(lib().sfe_host_alloc(C.byref(ptr), self.nbytes))
+        self.ptr = ptr.value
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().sfe_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceBuffer:
+    """Raw device allocation on `device` (resident inputs / outputs of the _dev entry points)."""
+
+    def __init__(self, nbytes, device=0):
+        self.device, self.nbytes = device, max(int(nbytes), 1)
+        ptr = C.c_void_p()
+        _check(lib().sfe_device_alloc(device, C.byref(ptr), self.nbytes))
+        self.ptr = ptr.value
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        _check(lib().sfe_copy_to_device(self.device, C.c_void_p(self.ptr), _p(arr), arr.nbytes))
+        return self
+
+    def download(self, shape, dtype):
+        out = np.empty(shape, dtype)
+        assert out.nbytes <= self.nbytes
+        _check(lib().sfe_copy_to_host(self.device, _p(out), C.c_void_p(self.ptr), out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            lib().sfe_device_free(self.device, C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Event:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().sfe_event_create(device, C.byref(h)))
+        self.h = h
+
+    def record(self, handle):
+        if isinstance(handle, ORBextractor):
+            _check(lib().sfe_event_record_extractor(self.h, handle.h))
+        else:
+            _check(lib().sfe_event_record_matcher(self.h, handle.h))
+
+    def elapsed_ms(self, stop: "Event") -> float:
+        ms = C.c_float()
+        _check(lib().sfe_event_elapsed_ms(self.h, stop.h, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        try:
+            lib().sfe_event_destroy(self.h)
+        except Exception:
+            pass
+
+
+class ORBextractor:
+    """ORB_SLAM2::ORBextractor (reference include/orb_extractor.h:45-133)."""
+
+    def __init__(self, nfeatures=2000, scaleFactor=1.2, nlevels=8, iniThFAST=20, minThFAST=7, device=0, max_images=2):
+        self.params = ExtractorParams(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
+        self.device, self.max_images, self.nlevels = device, max_images, nlevels
+        h = C.c_void_p()
+        _check(lib().sfe_extractor_create(C.byref(self.params), device, max_images, C.byref(h)))
+        self.h = h
+        cap = C.c_int()
+        _check(lib().sfe_extractor_max_keypoints(self.h, C.byref(cap)))
+        self.cap = cap.value
+        self._wh = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sfe_extractor_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # getters: include/orb_extractor.h:63-83
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return self.params.scale_factor
+
+    def _tables(self):
+        n = self.nlevels
+        t = [np.zeros(n, np.float32) for _ in range(4)] + [np.zeros(n, np.int32)]
+        _check(lib().sfe_extractor_tables(self.h, *[_p(a) for a in t]))
+        return t
+
+    def GetScaleFactors(self):
+        return self._tables()[0]
+
+    def GetInverseScaleFactors(self):
+        return self._tables()[1]
+
+    def GetScaleSigmaSquares(self):
+        return self._tables()[2]
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._tables()[3]
+
+    def features_per_level(self):
+        return self._tables()[4]
+
+    def level_size(self, w, h, level):
+        lw, lh = C.c_int(), C.c_int()
+        _check(lib().sfe_extractor_level_size(self.h, w, h, level, C.byref(lw), C.byref(lh)))
+        return lw.value, lh.value
+
+    def extract(self, image):
+        """extract(image, mask ignored) -> (keypoints[KP_DTYPE], descriptors n x 32 u8)."""
+        image = np.ascontiguousarray(image, np.uint8)
+        if image.size == 0:
+            return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
+        assert image.ndim == 2, "CV_8UC1 expected (reference asserts the same, src/orb_extractor.cpp:1050)"
+        h, w = image.shape
+        kps = np.zeros(self.cap, KP_DTYPE)
+        desc = np.zeros((self.cap, 32), np.uint8)
+        n = C.c_int()
+        _check(lib().sfe_extract(self.h, _p(image), w, h, w, _p(kps), _p(desc), self.cap, C.byref(n)))
+        self._wh = (w, h)
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
+    def extract_batch(self, images, out=None):
+        """images: count x h x w u8 (numpy or PinnedArray.array).  Returns (kps[count, cap], desc[count, cap, 32], n[count])."""
+        images = np.ascontiguousarray(images, np.uint8)
+        count, h, w = images.shape
+        if out is None:
+            out = (np.zeros((count, self.cap), KP_DTYPE), np.zeros((count, self.cap, 32), np.uint8), np.zeros(count, np.int32))
+        kps, desc, n = out
+        _check(lib().sfe_extract_batch(self.h, _p(images), w * h, count, w, h, w, _p(kps), _p(desc), self.cap, _p(n)))
+        self._wh = (w, h)
+        return kps, desc, n
+
+    def extract_batch_dev(self, images_ptr, count, w, h, kps_ptr, desc_ptr, n_ptr):
+        _check(lib().sfe_extract_batch_dev(self.h, _p(images_ptr), w * h, count, w, h, w, _p(kps_ptr), _p(desc_ptr), self.cap,
+                                           _p(n_ptr)))
+        self._wh = (w, h)
+
+    def stereo_frames(self, left, right, out=None, stereo_params=None):
+        """Keyframe path (src/pipeline.cpp:243-249): extract(left), extract(right), StereoMatch for
+        `frames` pairs in one call.  left/right: frames x h x w u8."""
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        f, h, w = left.shape
+        assert right.shape == left.shape
+        if out is None:
+            out = self.alloc_stereo_out(f)
+        sp = C.byref(stereo_params) if stereo_params is not None else None
+        _check(lib().sfe_stereo_frames(self.h, _p(left), _p(right), w * h, f, w, h, w, sp, _p(out["kps_l"]), _p(out["desc_l"]),
+                                       _p(out["n_l"]), _p(out["kps_r"]), _p(out["desc_r"]), _p(out["n_r"]),
+                                       _p(out["stereo_idx"]), _p(out["stereo_dist"]), self.cap))
+        self._wh = (w, h)
+        return out
+
+    def alloc_stereo_out(self, frames, pinned=False):
+        spec = {"kps_l": ((frames, self.cap), KP_DTYPE), "desc_l": ((frames, self.cap, 32), np.uint8),
+                "n_l": ((frames,), np.int32), "kps_r": ((frames, self.cap), KP_DTYPE),
+                "desc_r": ((frames, self.cap, 32), np.uint8), "n_r": ((frames,), np.int32),
+                "stereo_idx": ((frames, self.cap), np.int32), "stereo_dist": ((frames, self.cap), np.int32)}
+        if not pinned:
+            return {k: np.zeros(s, d) for k, (s, d) in spec.items()}
+        self._pinned_out = {k: PinnedArray(s, d) for k, (s, d) in spec.items()}
+        return {k: v.array for k, v in self._pinned_out.items()}
+
+    def stereo_frames_dev(self, left_ptr, right_ptr, frames, w, h, ptrs, stereo_params=None):
+        sp = C.byref(stereo_params) if stereo_params is not None else None
+        _check(lib().sfe_stereo_frames_dev(self.h, _p(left_ptr), _p(right_ptr), w * h, frames, w, h, w, sp,
+                                           _p(ptrs["kps_l"]), _p(ptrs["desc_l"]), _p(ptrs["n_l"]), _p(ptrs["kps_r"]),
+                                           _p(ptrs["desc_r"]), _p(ptrs["n_r"]), _p(ptrs["stereo_idx"]),
+                                           _p(ptrs["stereo_dist"]), self.cap))
+        self._wh = (w, h)
+
+    def launches(self) -> int:
+        n = C.c_int64()
+        _check(lib().sfe_extractor_launches(self.h, C.byref(n)))
+        return n.value
+
+    STAGES = ("pyramid", "fast_cells", "quadtree", "blur", "orient_describe", "stereo_match")
+
+    def set_profiling(self, enable=True):
+        _check(lib().sfe_extractor_set_profiling(self.h, int(enable)))
+
+    def stage_ms(self):
+        """-> ({stage: accumulated ms}, calls) from CUDA events on the handle's stream."""
+        ms = np.zeros(len(self.STAGES), np.float64)
+        calls = C.c_int64()
+        _check(lib().sfe_extractor_stage_ms(self.h, _p(ms), len(ms), C.byref(calls)))
+        return dict(zip(self.STAGES, ms.tolist())), calls.value
+
+    # stage taps (parity tests)
+    def debug_level(self, image, level, blur=False):
+        lw, lh = self.level_size(*self._wh, level)
+        out = np.zeros((lh, lw), np.uint8)
+        fn = lib().sfe_debug_blur if blur else lib().sfe_debug_level
+        _check(fn(self.h, image, level, _p(out)))
+        return out
+
+    def debug_points(self, image, level, distributed=False, cap=1 << 15):
+        out = np.zeros((cap, 3), np.float32)
+        n = C.c_int()
+        fn = lib().sfe_debug_distributed if distributed else lib().sfe_debug_candidates
+        _check(fn(self.h, image, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+
+class Matcher:
+    """StereoMatch / ProjectionMatch (reference include/matcher.h) + brute-force top-2."""
+
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().sfe_matcher_create(device, C.byref(h)))
+        self.h, self.device = h, device
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sfe_matcher_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launches(self) -> int:
+        n = C.c_int64()
+        _check(lib().sfe_matcher_launches(self.h, C.byref(n)))
+        return n.value
+
+    def StereoMatch(self, kps_l, desc_l, kps_r, desc_r, params=None):
+        """-> (stereo_indices, distances): right index or -1 per left keypoint (src/matcher.cpp:54-132)."""
+        kps_l, kps_r = np.ascontiguousarray(kps_l, KP_DTYPE), np.ascontiguousarray(kps_r, KP_DTYPE)
+        desc_l, desc_r = np.ascontiguousarray(desc_l, np.uint8), np.ascontiguousarray(desc_r, np.uint8)
+        idx = np.full(len(kps_l), -1, np.int32)
+        dist = np.full(len(kps_l), -1, np.int32)
+        sp = C.byref(params) if params is not None else None
+        _check(lib().sfe_stereo_match(self.h, _p(kps_l), _p(desc_l), len(kps_l), _p(kps_r), _p(desc_r), len(kps_r), sp,
+                                      _p(idx), _p(dist)))
+        return idx, dist
+
+    def ProjectionMatch(self, xw, mp_desc, skip, Tcw, camera, kps, kp_desc, search_radius, best12=0.5):
+        """-> (kp_to_query, kp_dist): for every frame keypoint the matched map-point index or -1
+        (the reference's std::map<int, Mappoint*>, src/matcher.cpp:134-209).  Tcw: 3x4 [R|t]."""
+        xw = np.ascontiguousarray(xw, np.float64)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        skip = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        kps = np.ascontiguousarray(kps, KP_DTYPE)
+        kp_desc = np.ascontiguousarray(kp_desc, np.uint8)
+        to_q = np.full(len(kps), -1, np.int32)
+        dist = np.full(len(kps), -1, np.int32)
+        _check(lib().sfe_projection_match(self.h, _p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), C.byref(camera), _p(kps),
+                                          _p(kp_desc), len(kps), search_radius, best12, _p(to_q), _p(dist)))
+        return to_q, dist
+
+    def projection_match_dev(self, xw_ptr, mp_desc_ptr, skip_ptr, n, Tcw, camera, kps_ptr, kp_desc_ptr, m, radius,
+                             to_q_ptr, dist_ptr, best12=0.5):
+        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        _check(lib().sfe_projection_match_dev(self.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n, _p(rt), C.byref(camera),
+                                              _p(kps_ptr), _p(kp_desc_ptr), m, radius, best12, _p(to_q_ptr), _p(dist_ptr)))
+
+    def create_db(self, desc, idx_base=0):
+        return DescriptorDB(self, desc, idx_base)
+
+    def knn2(self, db, queries):
+        """-> int32 q x 4 {idx0, dist0, idx1, dist1}, lexicographic (dist, idx) top-2."""
+        queries = np.ascontiguousarray(queries, np.uint8)
+        out = np.zeros((len(queries), 4), np.int32)
+        _check(lib().sfe_knn2(self.h, db.h, _p(queries), len(queries), _p(out)))
+        return out
+
+    def knn2_dev(self, db, queries_ptr, q, keys_ptr):
+        _check(lib().sfe_knn2_dev(self.h, db.h, _p(queries_ptr), q, _p(keys_ptr)))
+
+    def knn2_merge_dev(self, keys_ptr, shards, q, out_ptr):
+        _check(lib().sfe_knn2_merge_dev(self.h, _p(keys_ptr), shards, q, _p(out_ptr)))
+
+
+class DescriptorDB:
+    def __init__(self, matcher: Matcher, desc, idx_base=0):
+        desc = np.ascontiguousarray(desc, np.uint8)
+        assert desc.ndim == 2 and desc.shape[1] == 32
+        h = C.c_void_p()
+        _check(lib().sfe_db_create(matcher.h, _p(desc), len(desc), idx_base, C.byref(h)))
+        self.h, self.rows, self.idx_base = h, len(desc), idx_base
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sfe_db_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

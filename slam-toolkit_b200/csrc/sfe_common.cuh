@@ -1,0 +1,86 @@
+// Shared host-side plumbing for the sfe C ABI (error reporting, CUDA checks, handles).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sfe.h"
+
+namespace sfe {
+
+void set_error(const char *fmt, ...);
+
+#define SFE_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            ::sfe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? SFE_ERR_NO_DEVICE \
+                                                                                  : SFE_ERR_CUDA; \
+        }                                                                                     \
+    } while (0)
+
+#define SFE_REQUIRE(cond, status, msg)                           \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            ::sfe::set_error("%s: %s", __func__, msg);           \
+            return status;                                       \
+        }                                                        \
+    } while (0)
+
+// RAII device-scope guard: every ABI call runs on its handle's device and restores the caller's.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; return; }
+        ok = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc((void **)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+}  // namespace sfe
+
+struct sfe_event {
+    int device;
+    cudaEvent_t ev;
+};
+
+// Device-side 256-bit Hamming distance of two descriptors held as 8 words.
+__device__ __forceinline__ int hamming8(const uint32_t a[8], const uint32_t b[8]) {
+    int d = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
+    return d;
+}

@@ -1,0 +1,1291 @@
+// ORB extraction for sm_100a: pyramid -> per-cell FAST -> quadtree distribution ->
+// IC_Angle -> 7x7 Gaussian -> rBRIEF.  From-scratch CUDA behind the sfe C ABI; reproduces
+// reference src/orb_extractor.cpp:410-853,1034-1132 bit-for-bit under the canonical rules of
+// oracle/orb_oracle.h.  Compiled with -fmad=false: every float op is individually rounded, as
+// in the reference build (no -march => no FMA, CMakeLists.txt:54-55).
+#include <algorithm>
+#include <cmath>
+
+#include "sfe_extract.cuh"
+
+namespace sfe {
+
+// ---------------------------------------------------------------------------------------------
+// pyramid: cv::resize(INTER_LINEAR) fixed-point model, level l from level l-1 (:1120)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, int l, const uint2 *__restrict__ xtab,
+                                                         const uint2 *__restrict__ ytab) {
+    const LevelPlan &L = S.lv[l];
+    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, img = blockIdx.z;
+    if (x >= L.w || y >= L.h) return;
+    int sp;
+    const uint8_t *src = level_pixels(S, l - 1, img, sp);
+    const int sw = S.lv[l - 1].w;
+    const uint2 xt = __ldg(&xtab[L.xtab_off + x]), yt = __ldg(&ytab[L.ytab_off + y]);
+    const int sx = xt.x, sx1 = min(sx + 1, sw - 1);
+    const int w0 = xt.y & 0xFFFF, w1 = xt.y >> 16;
+    const int y0 = yt.x & 0xFFFF, y1 = yt.x >> 16;
+    const int b0 = yt.y & 0xFFFF, b1 = yt.y >> 16;
+    const uint8_t *r0 = src + (size_t)y0 * sp, *r1 = src + (size_t)y1 * sp;
+    const int t0 = r0[sx] * w0 + r0[sx1] * w1;
+    const int t1 = r1[sx] * w0 + r1[sx1] * w1;
+    const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+    uint8_t *dst = S.pyr + (size_t)img * S.pyr_stride + L.plane_off;
+    dst[(size_t)y * L.pitch + x] = (uint8_t)min(max(v, 0), 255);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FAST-9-16, one CTA per reference cv::FAST call (one 30-px grid cell, :789-816)
+// ---------------------------------------------------------------------------------------------
+constexpr int kTilePitch = 72;   // >= kMaxSub, multiple of 4
+constexpr int kScorePitch = 64;  // >= kMaxSub - 6 + 2
+
+__device__ __forceinline__ bool has_arc9(uint32_t m) {
+    m |= m << 16;
+    uint32_t r = m & (m >> 1);
+    r &= r >> 2;
+    r &= r >> 4;
+    r &= m >> 8;
+    return (r & 0xFFFFu) != 0;
+}
+
+// d[k] = I(p) - I(p + o_k) on the 16-pixel Bresenham circle, k clockwise from (0, +3)
+__device__ __forceinline__ void circle_diffs(const uint8_t *c, int d[16]) {
+    const int v = c[0];
+    d[0] = v - c[3 * kTilePitch + 0];
+    d[1] = v - c[3 * kTilePitch + 1];
+    d[2] = v - c[2 * kTilePitch + 2];
+    d[3] = v - c[1 * kTilePitch + 3];
+    d[4] = v - c[3];
+    d[5] = v - c[-1 * kTilePitch + 3];
+    d[6] = v - c[-2 * kTilePitch + 2];
+    d[7] = v - c[-3 * kTilePitch + 1];
+    d[8] = v - c[-3 * kTilePitch + 0];
+    d[9] = v - c[-3 * kTilePitch - 1];
+    d[10] = v - c[-2 * kTilePitch - 2];
+    d[11] = v - c[-1 * kTilePitch - 3];
+    d[12] = v - c[-3];
+    d[13] = v - c[1 * kTilePitch - 3];
+    d[14] = v - c[2 * kTilePitch - 2];
+    d[15] = v - c[3 * kTilePitch - 1];
+}
+
+// best(p) = max over the 16 arcs of 9 consecutive k of max(min d_k, min -d_k)   (cv::FAST score + 1)
+__device__ __forceinline__ int fast_best(const int d[16]) {
+    int lo2[16], hi2[16], lo4[16], hi4[16];
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        lo2[s] = min(d[s], d[(s + 1) & 15]);
+        hi2[s] = max(d[s], d[(s + 1) & 15]);
+    }
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        lo4[s] = min(lo2[s], lo2[(s + 2) & 15]);
+        hi4[s] = max(hi2[s], hi2[(s + 2) & 15]);
+    }
+    int a = -256, b = 256;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+        const int lo9 = min(min(lo4[s], lo4[(s + 4) & 15]), d[(s + 8) & 15]);
+        const int hi9 = max(max(hi4[s], hi4[(s + 4) & 15]), d[(s + 8) & 15]);
+        a = max(a, lo9);
+        b = min(b, hi9);
+    }
+    return max(a, -b);
+}
+
+__global__ void __launch_bounds__(256) fast_cells_kernel(ImgSet S, const CellPlan *__restrict__ cells,
+                                                         int ini_th, int min_th) {
+    __shared__ uint8_t tile[kMaxSub * kTilePitch];
+    __shared__ uint8_t score[(kMaxSub - 4) * kScorePitch];
+    __shared__ uint16_t det[(kMaxSub - 6) * (kMaxSub - 6)];
+    __shared__ uint16_t surv[(kMaxSub - 6) * (kMaxSub - 6) / 2 + 64];
+    __shared__ int n_det, n_surv, out_base;
+
+    const CellPlan C = cells[blockIdx.x];
+    const int img = blockIdx.y, tid = threadIdx.x;
+    const LevelPlan &L = S.lv[C.level];
+    int pitch;
+    const uint8_t *src = level_pixels(S, C.level, img, pitch);
+    src += (size_t)C.ini_y * pitch + C.ini_x;
+    const int sw = C.sub_w, sh = C.sub_h;
+    for (int i = tid; i < sw * sh; i += 256) {
+        const int r = i / sw, c = i - r * sw;
+        tile[r * kTilePitch + c] = __ldg(src + (size_t)r * pitch + c);
+    }
+    const int tw = sw - 6, th = sh - 6;  // tested pixels: 3-px margin inside the sub-image
+    int t = ini_th;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        for (int i = tid; i < (th + 2) * kScorePitch; i += 256) score[i] = 0;
+        if (tid == 0) { n_det = 0; n_surv = 0; }
+        __syncthreads();
+        // phase A: segment test at threshold t on every tested pixel, branch-free
+        for (int i = tid; i < tw * th; i += 256) {
+            const int y = i / tw, x = i - y * tw;
+            int d[16];
+            circle_diffs(&tile[(y + 3) * kTilePitch + x + 3], d);
+            uint32_t dark = 0, bright = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                dark |= (uint32_t)(d[k] > t) << k;
+                bright |= (uint32_t)(d[k] < -t) << k;
+            }
+            if (has_arc9(dark) || has_arc9(bright)) det[atomicAdd(&n_det, 1)] = (uint16_t)i;
+        }
+        __syncthreads();
+        // phase B: exact score for the (few) corners, all lanes busy
+        const int nd = n_det;
+        for (int e = tid; e < nd; e += 256) {
+            const int i = det[e], y = i / tw, x = i - y * tw;
+            int d[16];
+            circle_diffs(&tile[(y + 3) * kTilePitch + x + 3], d);
+            score[(y + 1) * kScorePitch + x + 1] = (uint8_t)fast_best(d);
+        }
+        __syncthreads();
+        // non-max suppression inside this cell only: strict > over 8 neighbours, outside = 0
+        for (int e = tid; e < nd; e += 256) {
+            const int i = det[e], y = i / tw, x = i - y * tw;
+            const uint8_t *sc = &score[(y + 1) * kScorePitch + x + 1];
+            const int s = sc[0];
+            const bool keep = s > sc[-1] && s > sc[1] && s > sc[-kScorePitch - 1] && s > sc[-kScorePitch] &&
+                              s > sc[-kScorePitch + 1] && s > sc[kScorePitch - 1] && s > sc[kScorePitch] &&
+                              s > sc[kScorePitch + 1];
+            if (keep) surv[atomicAdd(&n_surv, 1)] = (uint16_t)i;
+        }
+        __syncthreads();
+        if (n_surv > 0 || min_th >= t) break;  // :811-816: retry with minThFAST only when nothing survived
+        t = min_th;
+        __syncthreads();
+    }
+    const int ns = n_surv;
+    if (ns == 0) return;
+    int *cnt = &S.cand_count[img * S.nlevels + C.level];
+    if (tid == 0) out_base = atomicAdd(cnt, ns);
+    __syncthreads();
+    uint32_t *out = S.cand + (size_t)img * S.cand_stride + L.cand_off;
+    for (int e = tid; e < ns; e += 256) {
+        const int i = surv[e], y = i / tw, x = i - y * tw;
+        const int slot = out_base + e;
+        if (slot >= L.cand_cap) {
+            atomicOr(&S.flags[img], kFlagCandOverflow);
+            continue;
+        }
+        const uint32_t resp = score[(y + 1) * kScorePitch + x + 1] - 1;  // cv::FAST response = best - 1
+        const uint32_t xw = C.ini_x - kBorder + x + 3, yw = C.ini_y - kBorder + y + 3;
+        out[slot] = resp << 24 | yw << 12 | xw;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// DistributeOctTree (:539-763) as arrays + prefix sums; one CTA per (level, image).
+// Transcribes tools/octree_model.py, which tests/test_octree_model.py checks against the literal
+// std::list emulation of the oracle.  Candidate order is irrelevant here: membership is a pure
+// function of coordinates, and the only order-dependent step (first max response wins, :742-760)
+// uses the explicit order key of the reference's cell-major / raster candidate list.
+// ---------------------------------------------------------------------------------------------
+struct ONode {
+    short x0, x1, y0, y1;
+    unsigned short start, cnt;
+};
+
+struct OctSmem {
+    uint32_t *pk[2];       // packed candidates, grouped by node
+    uint16_t *own[2];      // list index of the node owning each position
+    uint16_t *qs;          // quadrant << 14 | slot within the child
+    ONode *nd[2];
+    uint16_t *eidx[2];     // creation order among expandable nodes (tie rule T1)
+    uint32_t *child;       // [node][4]: child counts, then child start positions
+    uint16_t *childpos;    // [node][4]: list index of each child in the next list
+    int *tord;             // processing order of a split node, -1 = not split
+    int *arr_a, *arr_b;    // scan scratch
+    int *warp_sums;
+};
+
+__device__ int block_excl_scan(int *a, int n, int *warp_sums) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + tid;
+        const int v = i < n ? a[i] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) warp_sums[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < nwarps ? warp_sums[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_sums[lane] = w;
+        }
+        __syncthreads();
+        const int woff = warp > 0 ? warp_sums[warp - 1] : 0;
+        if (i < n) a[i] = carry + woff + inc - v;
+        const int chunk = warp_sums[nwarps - 1];
+        __syncthreads();
+        carry += chunk;
+    }
+    return carry;
+}
+
+// One pass over the node list.  careful == false: split every expandable node in list order
+// (:594-665).  careful == true: split expandable nodes in descending (count, creation order)
+// until the list reaches n_want (:673-738).  Returns new list size; *n_expand = new |E|.
+__device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool careful, int *n_expand,
+                           int *sh_misc) {
+    const int tid = threadIdx.x, T = blockDim.x, nxt = cur ^ 1;
+    const ONode *nd = M.nd[cur];
+    for (int i = tid; i < nL * 4; i += T) M.child[i] = 0;
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const int i = M.own[cur][p];
+        const ONode o = nd[i];
+        if (o.cnt > 1) {
+            const uint32_t v = M.pk[cur][p];
+            const int x = v & 0xFFF, y = (v >> 12) & 0xFFF;
+            const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
+            const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);
+            const int s = atomicAdd(&M.child[i * 4 + q], 1u);
+            M.qs[p] = (uint16_t)(q << 14 | s);
+        }
+    }
+    __syncthreads();
+    // processing order of expandable nodes
+    int n_split;
+    if (!careful) {
+        for (int i = tid; i < nL; i += T) M.arr_a[i] = nd[i].cnt > 1 ? 1 : 0;
+        __syncthreads();
+        n_split = block_excl_scan(M.arr_a, nL, M.warp_sums);
+        for (int i = tid; i < nL; i += T) M.tord[i] = nd[i].cnt > 1 ? M.arr_a[i] : -1;
+        __syncthreads();
+    } else {
+        for (int i = tid; i < nL; i += T)
+            M.arr_a[i] = nd[i].cnt > 1 ? (int)((uint32_t)nd[i].cnt << 16 | M.eidx[cur][i]) : 0;
+        __syncthreads();
+        int n_e_local = 0;
+        for (int i = tid; i < nL; i += T) {
+            const int key = M.arr_a[i];
+            int rank = -1;
+            if (key > 0) {
+                rank = 0;
+                for (int j = 0; j < nL; j++) rank += M.arr_a[j] > key;
+                n_e_local++;
+            }
+            M.tord[i] = rank;
+        }
+        if (tid == 0) { sh_misc[0] = 0; sh_misc[1] = 0x7fffffff; }
+        __syncthreads();
+        if (n_e_local) atomicAdd(&sh_misc[0], n_e_local);
+        // growth of the list per split, in processing order
+        for (int i = tid; i < nL; i += T) {
+            const int t = M.tord[i];
+            if (t >= 0) {
+                const uint32_t *c = &M.child[i * 4];
+                M.arr_b[t] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
+            }
+        }
+        __syncthreads();
+        const int n_e = sh_misc[0];
+        block_excl_scan(M.arr_b, n_e, M.warp_sums);  // exclusive; inclusive = excl + own growth
+        for (int i = tid; i < nL; i += T) {
+            const int t = M.tord[i];
+            if (t >= 0) {
+                const uint32_t *c = &M.child[i * 4];
+                const int g = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
+                if (nL + M.arr_b[t] + g >= n_want) atomicMin(&sh_misc[1], t + 1);  // break after this split (:730)
+            }
+        }
+        __syncthreads();
+        n_split = min(sh_misc[1], n_e);
+        __syncthreads();
+        for (int i = tid; i < nL; i += T)
+            if (M.tord[i] >= n_split) M.tord[i] = -1;
+        __syncthreads();
+    }
+    // per split node, in processing order: non-empty children | children with > 1 points << 16
+    for (int i = tid; i < nL; i += T) {
+        const int t = M.tord[i];
+        if (t >= 0) {
+            const uint32_t *c = &M.child[i * 4];
+            const int nz = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+            const int ne = (c[0] > 1) + (c[1] > 1) + (c[2] > 1) + (c[3] > 1);
+            M.arr_b[t] = nz | ne << 16;
+        }
+        M.arr_a[i] = t < 0 ? 1 : 0;  // unsplit nodes keep their relative order behind the children
+    }
+    __syncthreads();
+    const int tot = block_excl_scan(M.arr_b, n_split, M.warp_sums);
+    const int n_unsplit = block_excl_scan(M.arr_a, nL, M.warp_sums);
+    const int C = tot & 0xFFFF;
+    *n_expand = tot >> 16;
+    for (int i = tid; i < nL; i += T) {
+        const int t = M.tord[i];
+        const ONode o = nd[i];
+        if (t >= 0) {
+            const int pp = M.arr_b[t] & 0xFFFF, ep = M.arr_b[t] >> 16;
+            const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
+            uint32_t cc[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) cc[q] = M.child[i * 4 + q];
+            int k = 0, ke = 0, off = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                M.child[i * 4 + q] = o.start + off;  // from now on: start position of child q
+                if (cc[q] > 0) {
+                    const int pos = C - 1 - (pp + k);  // push_front order reversed (:606-662)
+                    ONode c;
+                    c.x0 = (q & 1) ? mx : o.x0;
+                    c.x1 = (q & 1) ? o.x1 : mx;
+                    c.y0 = (q & 2) ? my : o.y0;
+                    c.y1 = (q & 2) ? o.y1 : my;
+                    c.start = (unsigned short)(o.start + off);
+                    c.cnt = (unsigned short)cc[q];
+                    M.nd[nxt][pos] = c;
+                    M.eidx[nxt][pos] = (uint16_t)(cc[q] > 1 ? ep + ke : 0);
+                    M.childpos[i * 4 + q] = (uint16_t)pos;
+                    k++;
+                    ke += cc[q] > 1;
+                }
+                off += cc[q];
+            }
+        } else {
+            const int pos = C + M.arr_a[i];
+            M.nd[nxt][pos] = o;
+            M.eidx[nxt][pos] = M.eidx[cur][i];
+            M.childpos[i * 4] = (uint16_t)pos;
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const int i = M.own[cur][p];
+        if (M.tord[i] >= 0) {
+            const int q = M.qs[p] >> 14, s = M.qs[p] & 0x3FFF;
+            const int np = M.child[i * 4 + q] + s;
+            M.pk[nxt][np] = M.pk[cur][p];
+            M.own[nxt][np] = M.childpos[i * 4 + q];
+        } else {
+            M.pk[nxt][p] = M.pk[cur][p];
+            M.own[nxt][p] = M.childpos[i * 4];
+        }
+    }
+    __syncthreads();
+    return C + n_unsplit;
+}
+
+__global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int max_cand, int max_nodes) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int sh_misc[4];
+    const int l = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+    const LevelPlan &L = S.lv[l];
+    int *kp_count = &S.kp_count[img * S.nlevels + l];
+    const int n = min(S.cand_count[img * S.nlevels + l], L.cand_cap);
+    if (n <= 0) {
+        if (tid == 0) *kp_count = 0;
+        return;
+    }
+    OctSmem M;
+    {
+        uint8_t *p = smem_raw;
+        M.pk[0] = (uint32_t *)p; p += sizeof(uint32_t) * max_cand;
+        M.pk[1] = (uint32_t *)p; p += sizeof(uint32_t) * max_cand;
+        M.child = (uint32_t *)p; p += sizeof(uint32_t) * 4 * max_nodes;
+        M.tord = (int *)p; p += sizeof(int) * max_nodes;
+        M.arr_a = (int *)p; p += sizeof(int) * max_nodes;
+        M.arr_b = (int *)p; p += sizeof(int) * max_nodes;
+        M.warp_sums = (int *)p; p += sizeof(int) * 32;
+        M.nd[0] = (ONode *)p; p += sizeof(ONode) * max_nodes;
+        M.nd[1] = (ONode *)p; p += sizeof(ONode) * max_nodes;
+        M.own[0] = (uint16_t *)p; p += sizeof(uint16_t) * max_cand;
+        M.own[1] = (uint16_t *)p; p += sizeof(uint16_t) * max_cand;
+        M.qs = (uint16_t *)p; p += sizeof(uint16_t) * max_cand;
+        M.eidx[0] = (uint16_t *)p; p += sizeof(uint16_t) * max_nodes;
+        M.eidx[1] = (uint16_t *)p; p += sizeof(uint16_t) * max_nodes;
+        M.childpos = (uint16_t *)p; p += sizeof(uint16_t) * 4 * max_nodes;
+    }
+    const uint32_t *cand = S.cand + (size_t)img * S.cand_stride + L.cand_off;
+    const int n_ini = L.n_ini, n_want = L.quota;
+    const float hx = L.hx;
+    // roots (:543-585): point -> root (int)(x / hX); empty roots are dropped
+    for (int i = tid; i < n_ini; i += T) M.child[i] = 0;
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const uint32_t v = cand[p];
+        int r = (int)__fdiv_rn((float)(v & 0xFFF), hx);
+        r = min(r, n_ini - 1);
+        M.own[1][p] = (uint16_t)r;
+        M.qs[p] = (uint16_t)atomicAdd(&M.child[r], 1u);
+    }
+    __syncthreads();
+    for (int i = tid; i < n_ini; i += T) {
+        M.arr_a[i] = M.child[i];
+        M.arr_b[i] = M.child[i] > 0;
+    }
+    __syncthreads();
+    block_excl_scan(M.arr_a, n_ini, M.warp_sums);
+    int nL = block_excl_scan(M.arr_b, n_ini, M.warp_sums);
+    for (int i = tid; i < n_ini; i += T) {
+        const int c = M.child[i];
+        if (c > 0) {
+            ONode o;
+            o.x0 = (short)(int)__fmul_rn(hx, (float)i);
+            o.x1 = (short)(int)__fmul_rn(hx, (float)(i + 1));
+            o.y0 = 0;
+            o.y1 = (short)L.win_h;
+            o.start = (unsigned short)M.arr_a[i];
+            o.cnt = (unsigned short)c;
+            M.nd[0][M.arr_b[i]] = o;
+            M.eidx[0][M.arr_b[i]] = 0;
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const int r = M.own[1][p];
+        const int np = M.arr_a[r] + M.qs[p];
+        M.pk[0][np] = cand[p];
+        M.own[0][np] = (uint16_t)M.arr_b[r];
+    }
+    __syncthreads();
+    // main loop (:587-739)
+    int cur = 0;
+    const bool overflow = false;
+    for (;;) {
+        // a full pass is only entered with nL <= n_ini or nL + 3 * nExpand <= quota, so the next
+        // list always fits max_nodes >= max(quota + 8, 4 * n_ini + 5)
+        const int prev = nL;
+        int n_expand;
+        nL = octree_pass(M, cur, n, nL, n_want, false, &n_expand, sh_misc);
+        cur ^= 1;
+        if (nL >= n_want || nL == prev) break;
+        if (nL + 3 * n_expand > n_want) {
+            for (;;) {
+                const int prev2 = nL;
+                nL = octree_pass(M, cur, n, nL, n_want, true, &n_expand, sh_misc);
+                cur ^= 1;
+                if (nL >= n_want || nL == prev2) break;
+            }
+            break;
+        }
+    }
+    if (overflow || nL > L.kp_cap) {
+        if (tid == 0) {
+            atomicOr(&S.flags[img], kFlagNodeOverflow);
+            *kp_count = 0;
+        }
+        return;
+    }
+    // retain the best point of every node (:742-760): max response, earliest in the reference's
+    // candidate order (cell-row-major, raster inside the cell) on ties
+    uint32_t *out = S.kpst + (size_t)img * S.kpst_stride + L.kp_off;
+    for (int i = tid; i < nL; i += T) {
+        const ONode o = M.nd[cur][i];
+        uint32_t best = 0;
+        unsigned long long best_key = 0;
+        for (int p = o.start; p < o.start + o.cnt; p++) {
+            const uint32_t v = M.pk[cur][p];
+            const uint32_t x = v & 0xFFF, y = (v >> 12) & 0xFFF, r = v >> 24;
+            const uint32_t ci = (y - 3) / L.h_cell, cj = (x - 3) / L.w_cell;
+            const unsigned long long ord = (((unsigned long long)ci * 4096 + cj) * 4096 + y) * 4096 + x;
+            const unsigned long long key = (unsigned long long)r << 48 | (0xFFFFFFFFFFFFull - ord);
+            if (p == o.start || key > best_key) { best_key = key; best = v; }
+        }
+        out[i] = best;
+    }
+    if (tid == 0) *kp_count = nL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) fixed-point model (:1085-1086)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);  // only reached by halo pixels of outputs outside the image
+}
+
+__global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__restrict__ tiles) {
+    constexpr int IW = kBlurTileW + 6, IH = kBlurTileH + 6, IP = kBlurTileW + 8;
+    __shared__ uint8_t in[IH * IP];
+    __shared__ uint16_t hb[IH * kBlurTileW];
+    const TilePlan t = tiles[blockIdx.x];
+    const int img = blockIdx.y, tid = threadIdx.x, l = t.level;
+    if (S.kp_count[img * S.nlevels + l] == 0) return;  // the reference blurs only levels with keypoints
+    const LevelPlan &L = S.lv[l];
+    int pitch;
+    const uint8_t *src = level_pixels(S, l, img, pitch);
+    for (int i = tid; i < IH * IW; i += 256) {
+        const int r = i / IW, c = i - r * IW;
+        const int gy = reflect101(t.y0 + r - 3, L.h), gx = reflect101(t.x0 + c - 3, L.w);
+        in[r * IP + c] = __ldg(src + (size_t)gy * pitch + gx);
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * kBlurTileW; i += 256) {
+        const int r = i / kBlurTileW, c = i - r * kBlurTileW;
+        const uint8_t *p = &in[r * IP + c];
+        hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    uint8_t *dst = S.blur + (size_t)img * S.blur_stride + L.blur_off;
+    for (int i = tid; i < kBlurTileH * kBlurTileW; i += 256) {
+        const int r = i / kBlurTileW, c = i - r * kBlurTileW;
+        const int gx = t.x0 + c, gy = t.y0 + r;
+        if (gx >= L.w || gy >= L.h) continue;
+        const uint16_t *p = &hb[r * kBlurTileW + c];
+        const uint32_t v = 18u * (p[0] + p[6 * kBlurTileW]) + 34u * (p[kBlurTileW] + p[5 * kBlurTileW]) +
+                           48u * (p[2 * kBlurTileW] + p[4 * kBlurTileW]) + 56u * p[3 * kBlurTileW];
+        dst[(size_t)gy * L.blur_pitch + gx] = (uint8_t)((v + 32768u) >> 16);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// IC_Angle (:77-104) + rBRIEF (:107-147), one warp per keypoint; also the final keypoint record
+// ---------------------------------------------------------------------------------------------
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // :452-469
+__device__ const signed char g_pattern[1024] = {
+#include "orb_pattern_data.inc"
+};
+
+// cv::fastAtan2 (degree-7 polynomial, float32)
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    // OpenCV: atan2_pN = <coef>f * (float)(180 / CV_PI), folded at compile time in float
+    constexpr float s = (float)(180.0 / 3.1415926535897932384626433832795);
+    constexpr float p1 = 0.9997878412794807f * s, p3 = -0.3258083974640975f * s, p5 = 0.1555786518463281f * s,
+                    p7 = -0.04432655554792128f * s;
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float eps = 2.220446049250313e-16f;
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O) {
+    __shared__ char2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane`
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y;
+    for (int i = tid; i < 512; i += 256) {
+        const int byte = i >> 4, s = i & 15;
+        pat[s * 32 + byte] = make_char2(g_pattern[2 * i], g_pattern[2 * i + 1]);
+    }
+    __syncthreads();
+    // locate keypoint g: levels are concatenated 0..L-1 (:1076-1104)
+    const int g = blockIdx.x * 8 + warp;
+    int l = -1, local = 0, total = 0;
+    for (int k = 0; k < S.nlevels; k++) {
+        const int c = min(S.kp_count[img * S.nlevels + k], S.lv[k].kp_cap);
+        if (l < 0 && g < total + c) { l = k; local = g - total; }
+        total += c;
+    }
+    const bool set_a = img < S.split;
+    const int oi = set_a ? img : img - S.split;
+    if (g == 0 && lane == 0) {
+        (set_a ? O.n_a : O.n_b)[oi] = min(total, O.cap);
+        if (total > O.cap) atomicOr(&S.flags[img], kFlagOutOverflow);
+    }
+    if (l < 0 || g >= O.cap) return;
+    const LevelPlan &L = S.lv[l];
+    const uint32_t v = S.kpst[(size_t)img * S.kpst_stride + L.kp_off + local];
+    const int x = (v & 0xFFF) + kBorder, y = ((v >> 12) & 0xFFF) + kBorder;
+    int pitch;
+    const uint8_t *lvl = level_pixels(S, l, img, pitch);
+    // intensity centroid over the 31-px disc on the UNBLURRED level; lane = column u
+    int m01 = 0, m10 = 0;
+    if (lane < 31) {
+        const int u = lane - kHalfPatch, au = abs(u);
+        const uint8_t *c = lvl + (size_t)y * pitch + x + u;
+#pragma unroll 1
+        for (int dv = -kHalfPatch; dv <= kHalfPatch; dv++) {
+            if (au <= c_umax[abs(dv)]) {
+                const int val = __ldg(c + dv * pitch);
+                m10 += u * val;
+                m01 += dv * val;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    }
+    const float angle = fast_atan2_deg((float)m01, (float)m10);
+    // rotated pattern lookups on the blurred level; float ops rounded one by one (T2)
+    float a = 0.f, b = 0.f;
+    if (lane == 0) {
+        const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.0);
+        const float rad = __fmul_rn(angle, factor_pi);
+        a = (float)cos((double)rad);
+        b = (float)sin((double)rad);
+    }
+    a = __shfl_sync(0xffffffffu, a, 0);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    const uint8_t *bl = S.blur + (size_t)img * S.blur_stride + L.blur_off + (size_t)y * L.blur_pitch + x;
+    uint32_t byte = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int tv[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            const char2 pp = pat[(2 * k + s) * 32 + lane];
+            const float px = (float)pp.x, py = (float)pp.y;
+            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            tv[s] = __ldg(bl + ry * L.blur_pitch + rx);
+        }
+        byte |= (uint32_t)(tv[0] < tv[1]) << k;
+    }
+    uint8_t *desc = (set_a ? O.desc_a : O.desc_b) + ((size_t)oi * O.cap + g) * 32;
+    desc[lane] = (uint8_t)byte;
+    if (lane == 0) {
+        sfe_keypoint kp;
+        kp.x = (float)x;
+        kp.y = (float)y;
+        if (l != 0) {  // :1095-1101
+            kp.x = __fmul_rn(kp.x, L.scale);
+            kp.y = __fmul_rn(kp.y, L.scale);
+        }
+        kp.size = L.size;
+        kp.angle = angle;
+        kp.response = (float)(v >> 24);
+        kp.octave = l;
+        kp.class_id = -1;
+        (set_a ? O.kps_a : O.kps_b)[(size_t)oi * O.cap + g] = kp;
+    }
+}
+
+}  // namespace sfe
+
+// =============================================================================================
+// host side: the extractor handle
+// =============================================================================================
+using namespace sfe;
+
+enum { kStagePyramid, kStageFast, kStageQuadtree, kStageBlur, kStageDescribe, kStageStereo, kNumStages };
+
+struct sfe_extractor {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    sfe_extractor_params prm{};
+    float scale[kMaxLevels], inv_scale[kMaxLevels], sigma2[kMaxLevels], inv_sigma2[kMaxLevels];
+    int quota[kMaxLevels];
+    int max_images = 0;
+    // geometry-dependent plan
+    int w = 0, h = 0;
+    LevelPlan lv[kMaxLevels];
+    std::vector<CellPlan> cells;
+    std::vector<TilePlan> tiles;
+    size_t pyr_stride = 0, blur_stride = 0;
+    int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0, out_cap = 0;
+    size_t octree_smem = 0;
+    DevBuf<uint8_t> d_pyr, d_blur, d_in, d_desc;
+    DevBuf<uint32_t> d_cand, d_kpst;
+    DevBuf<int> d_counts;  // cand_count | kp_count | flags
+    DevBuf<LevelPlan> d_lv;
+    DevBuf<CellPlan> d_cells;
+    DevBuf<TilePlan> d_tiles;
+    DevBuf<uint2> d_xtab, d_ytab;
+    DevBuf<sfe_keypoint> d_kps;
+    DevBuf<int32_t> d_nout, d_sidx, d_sdist;
+    std::vector<int> h_flags;
+    int64_t launches = 0;
+    // optional per-stage CUDA-event timing on the handle's own stream (bench roofline)
+    bool profiling = false;
+    cudaEvent_t prof_ev[kNumStages + 1] = {};
+    bool prof_pending = false, prof_has_stereo = false;
+    double stage_ms[kNumStages] = {};
+    int64_t stage_calls = 0;
+    // what the last call processed (stage taps)
+    ImgSet last{};
+    int last_count = 0;
+};
+
+static inline int cv_round_f(float v) { return (int)nearbyintf(v); }
+
+static inline void prof_mark(sfe_extractor *ex, int i) {
+    if (ex->profiling) cudaEventRecord(ex->prof_ev[i], ex->stream);
+}
+
+// ctor tables, reference src/orb_extractor.cpp:410-446
+static void build_tables(sfe_extractor *ex) {
+    const int nl = ex->prm.nlevels;
+    const double sf = (double)ex->prm.scale_factor;  // the member is a double initialised from float
+    ex->scale[0] = 1.0f;
+    ex->sigma2[0] = 1.0f;
+    for (int i = 1; i < nl; i++) {
+        ex->scale[i] = (float)((double)ex->scale[i - 1] * sf);
+        ex->sigma2[i] = ex->scale[i] * ex->scale[i];
+    }
+    for (int i = 0; i < nl; i++) {
+        ex->inv_scale[i] = 1.0f / ex->scale[i];
+        ex->inv_sigma2[i] = 1.0f / ex->sigma2[i];
+    }
+    const float factor = (float)(1.0 / sf);
+    const float denom = 1 - (float)pow((double)factor, (double)nl);
+    float want = (float)ex->prm.nfeatures * (1 - factor) / denom;
+    int sum = 0;
+    for (int l = 0; l < nl - 1; l++) {
+        ex->quota[l] = cv_round_f(want);
+        sum += ex->quota[l];
+        want *= factor;
+    }
+    ex->quota[nl - 1] = std::max(ex->prm.nfeatures - sum, 0);
+}
+
+// geometry plan for a w x h input: level sizes (:1111-1112), FAST cells (:771-806), quadtree roots
+// (:543-545), buffer layout, resize tables (cv::resize INTER_LINEAR coefficient tables)
+static int build_plan(sfe_extractor *ex, int w, int h) {
+    const int nl = ex->prm.nlevels;
+    std::vector<uint2> xtab, ytab;
+    ex->cells.clear();
+    ex->tiles.clear();
+    size_t pyr_off = 0, blur_off = 0;
+    int cand_off = 0, kp_off = 0, max_cand = 0, max_nodes = 8;
+    for (int l = 0; l < nl; l++) {
+        LevelPlan &L = ex->lv[l];
+        memset(&L, 0, sizeof(L));
+        L.w = cv_round_f((float)w * ex->inv_scale[l]);
+        L.h = cv_round_f((float)h * ex->inv_scale[l]);
+        SFE_REQUIRE(L.w >= 1 && L.h >= 1, SFE_ERR_UNSUPPORTED, "pyramid level collapses to zero size");
+        SFE_REQUIRE(L.w <= 4096 + 2 * kBorder && L.h <= 4096 + 2 * kBorder, SFE_ERR_UNSUPPORTED,
+                    "image larger than 4128 px per side");
+        L.pitch = (int)align_up((size_t)L.w, 16);
+        L.blur_pitch = L.pitch;
+        if (l > 0) {
+            L.plane_off = (int)pyr_off;
+            pyr_off += align_up((size_t)L.pitch * L.h, 128);
+        }
+        L.blur_off = (int)blur_off;
+        blur_off += align_up((size_t)L.blur_pitch * L.h, 128);
+        L.scale = ex->scale[l];
+        L.size = (float)(int)(31 * ex->scale[l]);
+        L.quota = ex->quota[l];
+        // FAST window and cells
+        const int max_bx = L.w - kBorder, max_by = L.h - kBorder;
+        L.win_w = max_bx - kBorder;
+        L.win_h = max_by - kBorder;
+        const float width = (float)L.win_w, height = (float)L.win_h;
+        L.n_cols = L.win_w > 0 ? (int)(width / 30.f) : 0;
+        L.n_rows = L.win_h > 0 ? (int)(height / 30.f) : 0;
+        L.w_cell = L.h_cell = 1;
+        int tested = 0;
+        if (L.n_cols >= 1 && L.n_rows >= 1) {  // else: reference divides by zero; canonical = no keypoints (T5)
+            L.w_cell = (int)ceilf(width / L.n_cols);
+            L.h_cell = (int)ceilf(height / L.n_rows);
+            for (int i = 0; i < L.n_rows; i++) {
+                const int ini_y = kBorder + i * L.h_cell;
+                int max_y = ini_y + L.h_cell + 6;
+                if (ini_y >= max_by - 3) continue;
+                if (max_y > max_by) max_y = max_by;
+                for (int j = 0; j < L.n_cols; j++) {
+                    const int ini_x = kBorder + j * L.w_cell;
+                    int max_x = ini_x + L.w_cell + 6;
+                    if (ini_x >= max_bx - 6) continue;
+                    if (max_x > max_bx) max_x = max_bx;
+                    const int sw = max_x - ini_x, sh = max_y - ini_y;
+                    if (sw < 7 || sh < 7) continue;  // cv::FAST tests nothing on such a sub-image
+                    SFE_REQUIRE(sw <= kMaxSub && sh <= kMaxSub, SFE_ERR_UNSUPPORTED, "FAST cell larger than 66 px");
+                    CellPlan c{(short)l, (short)ini_x, (short)ini_y, (short)sw, (short)sh, 0};
+                    ex->cells.push_back(c);
+                    tested += (sw - 6) * (sh - 6);
+                }
+            }
+        }
+        // quadtree roots
+        L.n_ini = 1;
+        L.hx = 1.f;
+        if (tested > 0) {
+            L.n_ini = (int)roundf((float)L.win_w / (float)L.win_h);
+            SFE_REQUIRE(L.n_ini >= 1, SFE_ERR_UNSUPPORTED,
+                        "portrait level (W/H < 0.5): the reference divides by nIni == 0");
+            L.hx = (float)L.win_w / (float)L.n_ini;
+        }
+        L.cand_cap = tested > 0 ? std::min(std::max(tested / 64, 512), kMaxCandCap) : 0;
+        L.cand_off = cand_off;
+        cand_off += L.cand_cap;
+        L.kp_cap = tested > 0 ? std::max(L.quota + 3, 4 * L.n_ini) + 1 : 0;
+        L.kp_off = kp_off;
+        kp_off += L.kp_cap;
+        max_cand = std::max(max_cand, L.cand_cap);
+        max_nodes = std::max(max_nodes, std::max(L.kp_cap + 4, L.n_ini));
+        if (tested > 0)
+            for (int y0 = 0; y0 < L.h; y0 += kBlurTileH)
+                for (int x0 = 0; x0 < L.w; x0 += kBlurTileW) ex->tiles.push_back(TilePlan{(short)l, (short)x0, (short)y0, 0});
+        // resize coefficient tables producing level l from level l-1
+        if (l > 0) {
+            const int sw = ex->lv[l - 1].w, sh = ex->lv[l - 1].h;
+            L.xtab_off = (int)xtab.size();
+            L.ytab_off = (int)ytab.size();
+            const double scale_x = 1.0 / ((double)L.w / sw), scale_y = 1.0 / ((double)L.h / sh);
+            for (int dx = 0; dx < L.w; dx++) {
+                float fx = (float)((dx + 0.5) * scale_x - 0.5);
+                int sx = (int)floorf(fx);
+                fx -= sx;
+                if (sx < 0) { fx = 0; sx = 0; }
+                if (sx >= sw - 1) { fx = 0; sx = sw - 1; }
+                const int w0 = cv_round_f((1.f - fx) * 2048), w1 = cv_round_f(fx * 2048);
+                xtab.push_back(make_uint2((unsigned)sx, (unsigned)w0 | (unsigned)w1 << 16));
+            }
+            for (int dy = 0; dy < L.h; dy++) {
+                float fy = (float)((dy + 0.5) * scale_y - 0.5);
+                int sy = (int)floorf(fy);
+                fy -= sy;
+                const int b0 = cv_round_f((1.f - fy) * 2048), b1 = cv_round_f(fy * 2048);
+                const int y0 = std::min(std::max(sy, 0), sh - 1), y1 = std::min(std::max(sy + 1, 0), sh - 1);
+                ytab.push_back(make_uint2((unsigned)y0 | (unsigned)y1 << 16, (unsigned)b0 | (unsigned)b1 << 16));
+            }
+        }
+    }
+    ex->pyr_stride = std::max<size_t>(pyr_off, 128);
+    ex->blur_stride = std::max<size_t>(blur_off, 128);
+    ex->cand_stride = std::max(cand_off, 1);
+    ex->kpst_stride = std::max(kp_off, 1);
+    ex->max_cand = std::max(max_cand, 1);
+    ex->max_nodes = max_nodes;
+    ex->octree_smem = (size_t)ex->max_cand * (2 * 4 + 3 * 2) + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
+    SFE_REQUIRE(ex->octree_smem <= 227 * 1024, SFE_ERR_UNSUPPORTED, "quadtree working set exceeds shared memory");
+    const int n = ex->max_images;
+    SFE_CUDA(ex->d_pyr.ensure(ex->pyr_stride * n));
+    SFE_CUDA(ex->d_blur.ensure(ex->blur_stride * n));
+    SFE_CUDA(ex->d_cand.ensure((size_t)ex->cand_stride * n));
+    SFE_CUDA(ex->d_kpst.ensure((size_t)ex->kpst_stride * n));
+    SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1)));
+    SFE_CUDA(ex->d_lv.ensure(kMaxLevels));
+    SFE_CUDA(ex->d_cells.ensure(std::max<size_t>(ex->cells.size(), 1)));
+    SFE_CUDA(ex->d_tiles.ensure(std::max<size_t>(ex->tiles.size(), 1)));
+    SFE_CUDA(ex->d_xtab.ensure(std::max<size_t>(xtab.size(), 1)));
+    SFE_CUDA(ex->d_ytab.ensure(std::max<size_t>(ytab.size(), 1)));
+    SFE_CUDA(cudaMemcpyAsync(ex->d_lv.p, ex->lv, sizeof(LevelPlan) * nl, cudaMemcpyHostToDevice, ex->stream));
+    if (!ex->cells.empty())
+        SFE_CUDA(cudaMemcpyAsync(ex->d_cells.p, ex->cells.data(), sizeof(CellPlan) * ex->cells.size(), cudaMemcpyHostToDevice, ex->stream));
+    if (!ex->tiles.empty())
+        SFE_CUDA(cudaMemcpyAsync(ex->d_tiles.p, ex->tiles.data(), sizeof(TilePlan) * ex->tiles.size(), cudaMemcpyHostToDevice, ex->stream));
+    if (!xtab.empty()) {
+        SFE_CUDA(cudaMemcpyAsync(ex->d_xtab.p, xtab.data(), sizeof(uint2) * xtab.size(), cudaMemcpyHostToDevice, ex->stream));
+        SFE_CUDA(cudaMemcpyAsync(ex->d_ytab.p, ytab.data(), sizeof(uint2) * ytab.size(), cudaMemcpyHostToDevice, ex->stream));
+    }
+    SFE_CUDA(cudaStreamSynchronize(ex->stream));  // the std::vectors above die at return
+    SFE_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
+    ex->w = w;
+    ex->h = h;
+    return SFE_OK;
+}
+
+// enqueue the whole extraction of `count` images on the handle's stream
+static int enqueue_extract(sfe_extractor *ex, const uint8_t *in_a, const uint8_t *in_b, int split, size_t in_stride,
+                           int in_pitch, int count, const OutSet &O) {
+    const int nl = ex->prm.nlevels;
+    ImgSet S{};
+    S.in_a = in_a;
+    S.in_b = in_b;
+    S.split = split;
+    S.in_stride = in_stride;
+    S.in_pitch = in_pitch;
+    S.pyr = ex->d_pyr.p;
+    S.pyr_stride = ex->pyr_stride;
+    S.blur = ex->d_blur.p;
+    S.blur_stride = ex->blur_stride;
+    S.lv = ex->d_lv.p;
+    S.nlevels = nl;
+    S.cand = ex->d_cand.p;
+    S.cand_stride = ex->cand_stride;
+    S.kpst = ex->d_kpst.p;
+    S.kpst_stride = ex->kpst_stride;
+    S.cand_count = ex->d_counts.p;
+    S.kp_count = ex->d_counts.p + (size_t)ex->max_images * nl;
+    S.flags = ex->d_counts.p + (size_t)ex->max_images * nl * 2;
+    cudaStream_t st = ex->stream;
+    SFE_CUDA(cudaMemsetAsync(ex->d_counts.p, 0, sizeof(int) * (size_t)ex->max_images * (2 * nl + 1), st));
+    prof_mark(ex, 0);
+    for (int l = 1; l < nl; l++) {
+        dim3 grid(div_up(ex->lv[l].w, 64), div_up(ex->lv[l].h, 4), count);
+        pyr_resize_kernel<<<grid, dim3(64, 4), 0, st>>>(S, l, ex->d_xtab.p, ex->d_ytab.p);
+        ex->launches++;
+    }
+    prof_mark(ex, 1);
+    if (!ex->cells.empty()) {
+        fast_cells_kernel<<<dim3((unsigned)ex->cells.size(), count), 256, 0, st>>>(S, ex->d_cells.p, ex->prm.ini_th_fast,
+                                                                                   ex->prm.min_th_fast);
+        prof_mark(ex, 2);
+        octree_kernel<<<dim3(nl, count), 256, ex->octree_smem, st>>>(S, ex->max_cand, ex->max_nodes);
+        prof_mark(ex, 3);
+        blur_kernel<<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p);
+        prof_mark(ex, 4);
+        ex->launches += 3;
+    } else {
+        prof_mark(ex, 2); prof_mark(ex, 3); prof_mark(ex, 4);
+    }
+    orient_describe_kernel<<<dim3(div_up(O.cap, 8), count), 256, 0, st>>>(S, O);
+    prof_mark(ex, 5);
+    ex->prof_pending = ex->profiling;
+    ex->prof_has_stereo = false;
+    ex->launches++;
+    SFE_CUDA(cudaGetLastError());
+    ex->last = S;
+    ex->last_count = count;
+    return SFE_OK;
+}
+
+static int check_flags(sfe_extractor *ex, int count) {
+    ex->h_flags.resize(count);
+    SFE_CUDA(cudaMemcpyAsync(ex->h_flags.data(), ex->last.flags, sizeof(int) * count, cudaMemcpyDeviceToHost, ex->stream));
+    SFE_CUDA(cudaStreamSynchronize(ex->stream));
+    if (ex->prof_pending) {
+        const int ns = ex->prof_has_stereo ? kNumStages : kNumStages - 1;
+        for (int i = 0; i < ns; i++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ex->prof_ev[i], ex->prof_ev[i + 1]) == cudaSuccess) ex->stage_ms[i] += ms;
+        }
+        ex->stage_calls++;
+        ex->prof_pending = false;
+    }
+    for (int i = 0; i < count; i++) {
+        if (ex->h_flags[i] & kFlagCandOverflow) { set_error("image %d: FAST candidate buffer overflow", i); return SFE_ERR_CAPACITY; }
+        if (ex->h_flags[i] & kFlagNodeOverflow) { set_error("image %d: quadtree node buffer overflow", i); return SFE_ERR_CAPACITY; }
+        if (ex->h_flags[i] & kFlagOutOverflow) { set_error("image %d: more keypoints than the caller's capacity", i); return SFE_ERR_CAPACITY; }
+    }
+    return SFE_OK;
+}
+
+static int prepare(sfe_extractor *ex, int count, int w, int h, int stride, int cap) {
+    SFE_REQUIRE(ex != nullptr, SFE_ERR_BAD_ARG, "null handle");
+    SFE_REQUIRE(count >= 1 && count <= ex->max_images, SFE_ERR_BAD_ARG, "count outside [1, max_images]");
+    SFE_REQUIRE(w > 0 && h > 0 && stride >= w, SFE_ERR_BAD_ARG, "bad image geometry");
+    SFE_REQUIRE(cap >= 1 && cap < 65536, SFE_ERR_BAD_ARG, "capacity must be in [1, 65535]");
+    if (w != ex->w || h != ex->h) {
+        int rc = build_plan(ex, w, h);
+        if (rc != SFE_OK) { ex->w = ex->h = 0; return rc; }
+    }
+    return SFE_OK;
+}
+
+// upload `count` host images into the tight staging buffer at slot `first`
+static int upload_images(sfe_extractor *ex, const uint8_t *images, size_t image_stride, int count, int w, int h, int stride,
+                         int first) {
+    uint8_t *dst = ex->d_in.p + (size_t)first * w * h;
+    if (stride == w && image_stride == (size_t)w * h) {
+        SFE_CUDA(cudaMemcpyAsync(dst, images, (size_t)count * w * h, cudaMemcpyHostToDevice, ex->stream));
+    } else {
+        for (int i = 0; i < count; i++)
+            SFE_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * w * h, w, images + (size_t)i * image_stride, stride, w, h,
+                                       cudaMemcpyHostToDevice, ex->stream));
+    }
+    return SFE_OK;
+}
+
+extern "C" {
+
+int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_images, sfe_extractor **out) {
+    SFE_REQUIRE(p && out, SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(p->nlevels >= 1 && p->nlevels <= kMaxLevels, SFE_ERR_BAD_ARG, "nlevels outside [1,16]");
+    SFE_REQUIRE(p->nfeatures >= 1 && p->nfeatures <= 60000, SFE_ERR_BAD_ARG, "nfeatures outside [1,60000]");
+    SFE_REQUIRE(p->scale_factor > 1.0f, SFE_ERR_BAD_ARG, "scale_factor must be > 1");
+    SFE_REQUIRE(p->ini_th_fast >= 1 && p->min_th_fast >= 1 && p->ini_th_fast < 255 && p->min_th_fast < 255, SFE_ERR_BAD_ARG,
+                "FAST thresholds outside [1,254]");
+    SFE_REQUIRE(max_images >= 1 && max_images <= 65535, SFE_ERR_BAD_ARG, "max_images outside [1,65535]");
+    int ndev = 0;
+    SFE_CUDA(cudaGetDeviceCount(&ndev));
+    SFE_REQUIRE(ndev > 0, SFE_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    SFE_REQUIRE(device >= 0 && device < ndev, SFE_ERR_BAD_ARG, "device index out of range");
+    DeviceGuard g(device);
+    sfe_extractor *ex = new sfe_extractor();
+    ex->device = device;
+    ex->prm = *p;
+    ex->max_images = max_images;
+    cudaError_t e = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+        delete ex;
+        return SFE_ERR_CUDA;
+    }
+    build_tables(ex);
+    int cap = p->nfeatures;
+    for (int l = 0; l < p->nlevels; l++) cap += 4;
+    ex->out_cap = cap;
+    *out = ex;
+    return SFE_OK;
+}
+
+int sfe_extractor_destroy(sfe_extractor *ex) {
+    if (!ex) return SFE_OK;
+    DeviceGuard g(ex->device);
+    cudaStreamSynchronize(ex->stream);
+    ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_desc.release();
+    ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release(); ex->d_lv.release();
+    ex->d_cells.release(); ex->d_tiles.release(); ex->d_xtab.release(); ex->d_ytab.release();
+    ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
+    for (int i = 0; i <= kNumStages; i++)
+        if (ex->prof_ev[i]) cudaEventDestroy(ex->prof_ev[i]);
+    cudaStreamDestroy(ex->stream);
+    delete ex;
+    return SFE_OK;
+}
+
+int sfe_extractor_tables(const sfe_extractor *ex, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2,
+                         int32_t *per_level) {
+    SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
+    for (int i = 0; i < ex->prm.nlevels; i++) {
+        if (scale) scale[i] = ex->scale[i];
+        if (inv_scale) inv_scale[i] = ex->inv_scale[i];
+        if (sigma2) sigma2[i] = ex->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = ex->inv_sigma2[i];
+        if (per_level) per_level[i] = ex->quota[i];
+    }
+    return SFE_OK;
+}
+
+int sfe_extractor_level_size(const sfe_extractor *ex, int w, int h, int level, int *lw, int *lh) {
+    SFE_REQUIRE(ex && lw && lh && level >= 0 && level < ex->prm.nlevels, SFE_ERR_BAD_ARG, "bad argument");
+    *lw = cv_round_f((float)w * ex->inv_scale[level]);
+    *lh = cv_round_f((float)h * ex->inv_scale[level]);
+    return SFE_OK;
+}
+
+int sfe_extractor_max_keypoints(const sfe_extractor *ex, int *cap) {
+    SFE_REQUIRE(ex && cap, SFE_ERR_BAD_ARG, "null argument");
+    *cap = ex->out_cap;
+    return SFE_OK;
+}
+
+int sfe_extractor_launches(const sfe_extractor *ex, int64_t *launches) {
+    SFE_REQUIRE(ex && launches, SFE_ERR_BAD_ARG, "null argument");
+    *launches = ex->launches;
+    return SFE_OK;
+}
+
+int sfe_extract_batch_dev(sfe_extractor *ex, const uint8_t *images_dev, size_t image_stride, int count, int w, int h,
+                          int stride, sfe_keypoint *kps_dev, uint8_t *desc_dev, int cap, int32_t *n_out_dev) {
+    SFE_REQUIRE(ex && images_dev && kps_dev && desc_dev && n_out_dev, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(ex->device);
+    int rc = prepare(ex, count, w, h, stride, cap);
+    if (rc != SFE_OK) return rc;
+    OutSet O{kps_dev, kps_dev, desc_dev, desc_dev, n_out_dev, n_out_dev, cap};
+    rc = enqueue_extract(ex, images_dev, images_dev, count, image_stride, stride, count, O);
+    if (rc != SFE_OK) return rc;
+    return check_flags(ex, count);
+}
+
+int sfe_extract_batch(sfe_extractor *ex, const uint8_t *images, size_t image_stride, int count, int w, int h, int stride,
+                      sfe_keypoint *kps, uint8_t *desc, int cap, int32_t *n_out) {
+    SFE_REQUIRE(ex && kps && desc && n_out, SFE_ERR_BAD_ARG, "null argument");
+    if (w == 0 || h == 0 || images == nullptr) {  // empty image: silent return (:1046-1047)
+        for (int i = 0; i < count; i++) n_out[i] = 0;
+        return SFE_OK;
+    }
+    DeviceGuard g(ex->device);
+    int rc = prepare(ex, count, w, h, stride, cap);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * w * h));
+    SFE_CUDA(ex->d_kps.ensure((size_t)ex->max_images * cap));
+    SFE_CUDA(ex->d_desc.ensure((size_t)ex->max_images * cap * 32));
+    SFE_CUDA(ex->d_nout.ensure(ex->max_images));
+    rc = upload_images(ex, images, image_stride, count, w, h, stride, 0);
+    if (rc != SFE_OK) return rc;
+    OutSet O{ex->d_kps.p, ex->d_kps.p, ex->d_desc.p, ex->d_desc.p, ex->d_nout.p, ex->d_nout.p, cap};
+    rc = enqueue_extract(ex, ex->d_in.p, ex->d_in.p, count, (size_t)w * h, w, count, O);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(kps, ex->d_kps.p, sizeof(sfe_keypoint) * (size_t)count * cap, cudaMemcpyDeviceToHost, ex->stream));
+    SFE_CUDA(cudaMemcpyAsync(desc, ex->d_desc.p, (size_t)count * cap * 32, cudaMemcpyDeviceToHost, ex->stream));
+    SFE_CUDA(cudaMemcpyAsync(n_out, ex->d_nout.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ex->stream));
+    return check_flags(ex, count);
+}
+
+int sfe_extract(sfe_extractor *ex, const uint8_t *image, int w, int h, int stride, sfe_keypoint *kps, uint8_t *desc, int cap,
+                int *n_out) {
+    SFE_REQUIRE(n_out, SFE_ERR_BAD_ARG, "null argument");
+    int32_t n = 0;
+    int rc = sfe_extract_batch(ex, image, (size_t)stride * (h > 0 ? h : 0), 1, w, h, stride, kps, desc, cap, &n);
+    *n_out = n;
+    return rc;
+}
+
+static int stereo_frames_impl(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames,
+                              int in_pitch, const sfe_stereo_params *sp, sfe_keypoint *kl, uint8_t *dl, int32_t *nl,
+                              sfe_keypoint *kr, uint8_t *dr, int32_t *nr, int32_t *sidx, int32_t *sdist, int cap) {
+    OutSet O{kl, kr, dl, dr, nl, nr, cap};
+    int rc = enqueue_extract(ex, left, right, frames, image_stride, in_pitch, 2 * frames, O);
+    if (rc != SFE_OK) return rc;
+    launch_stereo_match(ex->stream, frames, cap, kl, dl, nl, kr, dr, nr, sp->y_threshold, sp->max_dx, sp->best12_threshold,
+                        sidx, sdist);
+    prof_mark(ex, 6);
+    ex->prof_has_stereo = true;
+    ex->launches++;
+    SFE_CUDA(cudaGetLastError());
+    return SFE_OK;
+}
+
+static const sfe_stereo_params k_default_stereo = {3.0, 100.0, 0.5};  // src/matcher.cpp:68-70
+
+int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
+                          int frames, int w, int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l_dev,
+                          uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev, uint8_t *desc_r_dev,
+                          int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev, int cap) {
+    SFE_REQUIRE(ex && left_dev && right_dev && kps_l_dev && desc_l_dev && n_l_dev && kps_r_dev && desc_r_dev && n_r_dev &&
+                    stereo_idx_dev,
+                SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
+    DeviceGuard g(ex->device);
+    int rc = prepare(ex, 2 * frames, w, h, stride, cap);
+    if (rc != SFE_OK) return rc;
+    rc = stereo_frames_impl(ex, left_dev, right_dev, image_stride, frames, stride, sp ? sp : &k_default_stereo, kps_l_dev,
+                            desc_l_dev, n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, stereo_idx_dev, stereo_dist_dev, cap);
+    if (rc != SFE_OK) return rc;
+    return check_flags(ex, 2 * frames);
+}
+
+int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
+                      int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l, uint8_t *desc_l, int32_t *n_l,
+                      sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx, int32_t *stereo_dist,
+                      int cap) {
+    SFE_REQUIRE(ex && left && right && kps_l && desc_l && n_l && kps_r && desc_r && n_r && stereo_idx, SFE_ERR_BAD_ARG,
+                "null argument");
+    SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
+    DeviceGuard g(ex->device);
+    int rc = prepare(ex, 2 * frames, w, h, stride, cap);
+    if (rc != SFE_OK) return rc;
+    const size_t F = frames;
+    SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * w * h));
+    SFE_CUDA(ex->d_kps.ensure((size_t)ex->max_images * cap));
+    SFE_CUDA(ex->d_desc.ensure((size_t)ex->max_images * cap * 32));
+    SFE_CUDA(ex->d_nout.ensure(ex->max_images));
+    SFE_CUDA(ex->d_sidx.ensure((size_t)ex->max_images * cap));
+    SFE_CUDA(ex->d_sdist.ensure((size_t)ex->max_images * cap));
+    if ((rc = upload_images(ex, left, image_stride, frames, w, h, stride, 0)) != SFE_OK) return rc;
+    if ((rc = upload_images(ex, right, image_stride, frames, w, h, stride, frames)) != SFE_OK) return rc;
+    sfe_keypoint *kl = ex->d_kps.p, *kr = ex->d_kps.p + F * cap;
+    uint8_t *dl = ex->d_desc.p, *dr = ex->d_desc.p + F * cap * 32;
+    int32_t *nl = ex->d_nout.p, *nr = ex->d_nout.p + F;
+    rc = stereo_frames_impl(ex, ex->d_in.p, ex->d_in.p + F * w * h, (size_t)w * h, frames, w, sp ? sp : &k_default_stereo, kl,
+                            dl, nl, kr, dr, nr, ex->d_sidx.p, ex->d_sdist.p, cap);
+    if (rc != SFE_OK) return rc;
+    cudaStream_t st = ex->stream;
+    SFE_CUDA(cudaMemcpyAsync(kps_l, kl, sizeof(sfe_keypoint) * F * cap, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(kps_r, kr, sizeof(sfe_keypoint) * F * cap, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(desc_l, dl, F * cap * 32, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(desc_r, dr, F * cap * 32, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(stereo_idx, ex->d_sidx.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, st));
+    if (stereo_dist) SFE_CUDA(cudaMemcpyAsync(stereo_dist, ex->d_sdist.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, st));
+    return check_flags(ex, 2 * frames);
+}
+
+// ---- stage taps ---------------------------------------------------------------------------------
+static int tap_check(sfe_extractor *ex, int image, int level) {
+    SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
+    SFE_REQUIRE(ex->last_count > 0 && image >= 0 && image < ex->last_count, SFE_ERR_BAD_ARG, "image index outside the last call");
+    SFE_REQUIRE(level >= 0 && level < ex->prm.nlevels, SFE_ERR_BAD_ARG, "level out of range");
+    return SFE_OK;
+}
+
+int sfe_debug_level(sfe_extractor *ex, int image, int level, uint8_t *out) {
+    int rc = tap_check(ex, image, level);
+    if (rc != SFE_OK) return rc;
+    SFE_REQUIRE(out, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(ex->device);
+    const LevelPlan &L = ex->lv[level];
+    const ImgSet &S = ex->last;
+    const uint8_t *src;
+    int pitch;
+    if (level == 0) {
+        pitch = S.in_pitch;
+        src = image < S.split ? S.in_a + (size_t)image * S.in_stride : S.in_b + (size_t)(image - S.split) * S.in_stride;
+    } else {
+        pitch = L.pitch;
+        src = S.pyr + (size_t)image * S.pyr_stride + L.plane_off;
+    }
+    SFE_CUDA(cudaStreamSynchronize(ex->stream));
+    SFE_CUDA(cudaMemcpy2D(out, L.w, src, pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return SFE_OK;
+}
+
+int sfe_debug_blur(sfe_extractor *ex, int image, int level, uint8_t *out) {
+    int rc = tap_check(ex, image, level);
+    if (rc != SFE_OK) return rc;
+    SFE_REQUIRE(out, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(ex->device);
+    const LevelPlan &L = ex->lv[level];
+    SFE_CUDA(cudaStreamSynchronize(ex->stream));
+    SFE_CUDA(cudaMemcpy2D(out, L.w, ex->last.blur + (size_t)image * ex->last.blur_stride + L.blur_off, L.blur_pitch, L.w, L.h,
+                          cudaMemcpyDeviceToHost));
+    return SFE_OK;
+}
+
+static int tap_points(sfe_extractor *ex, int image, int level, bool distributed, float *xyr, int cap, int *n) {
+    int rc = tap_check(ex, image, level);
+    if (rc != SFE_OK) return rc;
+    SFE_REQUIRE(xyr && n && cap >= 0, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(ex->device);
+    const LevelPlan &L = ex->lv[level];
+    const ImgSet &S = ex->last;
+    SFE_CUDA(cudaStreamSynchronize(ex->stream));
+    int cnt = 0;
+    const int *cp = (distributed ? S.kp_count : S.cand_count) + image * S.nlevels + level;
+    SFE_CUDA(cudaMemcpy(&cnt, cp, sizeof(int), cudaMemcpyDeviceToHost));
+    cnt = std::min(cnt, distributed ? L.kp_cap : L.cand_cap);
+    std::vector<uint32_t> v(std::max(cnt, 1));
+    const uint32_t *src = distributed ? S.kpst + (size_t)image * S.kpst_stride + L.kp_off
+                                      : S.cand + (size_t)image * S.cand_stride + L.cand_off;
+    if (cnt > 0) SFE_CUDA(cudaMemcpy(v.data(), src, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+    v.resize(cnt);
+    if (!distributed) {  // device order is arbitrary; present the reference's cell-major raster order
+        const int wc = L.w_cell, hc = L.h_cell;
+        auto key = [wc, hc](uint32_t p) {
+            const uint64_t x = p & 0xFFF, y = (p >> 12) & 0xFFF;
+            return ((((y - 3) / hc) * 4096 + (x - 3) / wc) * 4096 + y) * 4096 + x;
+        };
+        std::sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    }
+    for (int i = 0; i < cnt && i < cap; i++) {
+        xyr[3 * i] = (float)(v[i] & 0xFFF);
+        xyr[3 * i + 1] = (float)((v[i] >> 12) & 0xFFF);
+        xyr[3 * i + 2] = (float)(v[i] >> 24);
+    }
+    *n = cnt;
+    return SFE_OK;
+}
+
+int sfe_debug_candidates(sfe_extractor *ex, int image, int level, float *xyr, int cap, int *n) {
+    return tap_points(ex, image, level, false, xyr, cap, n);
+}
+int sfe_debug_distributed(sfe_extractor *ex, int image, int level, float *xyr, int cap, int *n) {
+    return tap_points(ex, image, level, true, xyr, cap, n);
+}
+
+int sfe_extractor_set_profiling(sfe_extractor *ex, int enable) {
+    SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
+    DeviceGuard g(ex->device);
+    if (enable && !ex->prof_ev[0])
+        for (int i = 0; i <= kNumStages; i++) SFE_CUDA(cudaEventCreate(&ex->prof_ev[i]));
+    ex->profiling = enable != 0;
+    for (int i = 0; i < kNumStages; i++) ex->stage_ms[i] = 0.0;
+    ex->stage_calls = 0;
+    return SFE_OK;
+}
+
+int sfe_extractor_stage_ms(const sfe_extractor *ex, double *ms, int n, int64_t *calls) {
+    SFE_REQUIRE(ex && ms && calls && n >= 1, SFE_ERR_BAD_ARG, "bad argument");
+    for (int i = 0; i < n; i++) ms[i] = i < kNumStages ? ex->stage_ms[i] : 0.0;
+    *calls = ex->stage_calls;
+    return SFE_OK;
+}
+
+int sfe_event_record_extractor(sfe_event *ev, sfe_extractor *ex) {
+    SFE_REQUIRE(ev && ex, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(ex->device);
+    SFE_CUDA(cudaEventRecord(ev->ev, ex->stream));
+    return SFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Internal layout shared by the extraction kernels and the extractor handle.
+#pragma once
+#include "sfe_common.cuh"
+
+namespace sfe {
+
+constexpr int kMaxLevels = 16;
+constexpr int kEdge = 19;          // EDGE_THRESHOLD, reference src/orb_extractor.cpp:74
+constexpr int kBorder = kEdge - 3; // minBorderX/Y of the FAST window, :771-772
+constexpr int kHalfPatch = 15;     // HALF_PATCH_SIZE, :73
+constexpr int kMaxSub = 66;        // largest FAST cell sub-image side (wCell + 6 < 60 + 6)
+constexpr int kMaxCandCap = 16384; // slot index must fit 14 bits in the quadtree kernel
+constexpr int kBlurTileW = 128, kBlurTileH = 32;
+
+// One pyramid level's geometry for the current image size (host-built, mirrored on device).
+struct LevelPlan {
+    int w, h, pitch;        // level size; row pitch of levels >= 1 in the pyramid buffer
+    int plane_off;          // byte offset of this level inside one image's pyramid buffer (l >= 1)
+    int blur_pitch, blur_off;
+    int win_w, win_h;       // FAST window maxBorder - minBorder, :773-781
+    int n_cols, n_rows, w_cell, h_cell;  // :784-787
+    int quota;              // mnFeaturesPerLevel, :435-446
+    int n_ini;              // quadtree roots, :543
+    float hx;               // root width, :545
+    int cand_cap, cand_off; // FAST candidate slots of this level inside one image's array
+    int kp_cap, kp_off;     // quadtree survivor slots
+    int xtab_off, ytab_off; // resize tables that PRODUCE this level from level-1
+    float scale;            // mvScaleFactor[level]
+    float size;             // (int)(31 * scale), :837
+};
+
+struct CellPlan {  // one cv::FAST call of the reference, :789-816
+    short level, ini_x, ini_y, sub_w, sub_h, pad;
+};
+
+struct TilePlan {  // one blur tile
+    short level, x0, y0, pad;
+};
+
+// Everything a kernel needs to address one batch.  Images [0, split) read/write set A,
+// [split, count) set B (left / right images of a stereo batch).
+struct ImgSet {
+    const uint8_t *in_a, *in_b;  // level-0 pixels
+    size_t in_stride;            // bytes between consecutive images of a set
+    int in_pitch;                // bytes between rows
+    int split;
+    uint8_t *pyr;                // levels 1.. of all images
+    size_t pyr_stride;
+    uint8_t *blur;               // blurred levels 0.. of all images
+    size_t blur_stride;
+    const LevelPlan *lv;
+    int nlevels;
+    uint32_t *cand;              // packed candidates: resp << 24 | y << 12 | x (window-relative)
+    int cand_stride;
+    uint32_t *kpst;              // packed quadtree survivors, same packing, list order
+    int kpst_stride;
+    int *cand_count;             // [image][level]
+    int *kp_count;               // [image][level]
+    int *flags;                  // [image] error bits
+};
+
+enum { kFlagCandOverflow = 1, kFlagNodeOverflow = 2, kFlagOutOverflow = 4 };
+
+struct OutSet {  // final outputs, set A / set B
+    sfe_keypoint *kps_a, *kps_b;
+    uint8_t *desc_a, *desc_b;
+    int32_t *n_a, *n_b;
+    int cap;
+};
+
+__device__ __forceinline__ const uint8_t *level_pixels(const ImgSet &S, int l, int img, int &pitch) {
+    if (l == 0) {
+        pitch = S.in_pitch;
+        return img < S.split ? S.in_a + (size_t)img * S.in_stride
+                             : S.in_b + (size_t)(img - S.split) * S.in_stride;
+    }
+    pitch = S.lv[l].pitch;
+    return S.pyr + (size_t)img * S.pyr_stride + S.lv[l].plane_off;
+}
+
+// stereo matcher launch (sfe_match.cu), used by sfe_stereo_frames on the extractor's stream
+void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoint *kl,
+                         const uint8_t *dl, const int32_t *nl, const sfe_keypoint *kr,
+                         const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
+                         double ratio, int32_t *out_idx, int32_t *out_dist);
+
+}  // namespace sfe

@@ -1,0 +1,544 @@
+// Hamming matchers for sm_100a behind the sfe C ABI: StereoMatch (reference src/matcher.cpp:54-132),
+// ProjectionMatch (:134-209) and the brute-force top-2 that BASELINE config 4 defines over the same
+// inner loop.  XOR + __popc over 8 words; best / second-best kept as packed (dist, index) keys so
+// "strict < in ascending index order" (:114-123) becomes a plain unsigned min.
+#include <algorithm>
+
+#include "sfe_extract.cuh"
+
+namespace sfe {
+
+constexpr uint32_t kNoKey = 0xFFFFFFFFu;
+
+__device__ __forceinline__ void top2_insert(uint32_t &k0, uint32_t &k1, uint32_t key) {
+    k1 = min(k1, max(k0, key));
+    k0 = min(k0, key);
+}
+
+__device__ __forceinline__ void load_desc(const uint8_t *p, uint32_t d[8]) {
+    const uint4 a = __ldg((const uint4 *)p), b = __ldg((const uint4 *)p + 1);
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+    d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// StereoMatch: one warp per left keypoint scans the right keypoints of its frame.
+// The reference's int(y/10) row buckets (:60-66,83-95) only pre-select: |dy| <= 3 < 10 keeps every
+// passing candidate inside buckets b-1..b+1, so the candidate set is every right keypoint passing
+// the dy / dx filters (:103-110).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_keypoint *__restrict__ kl,
+                                                           const uint8_t *__restrict__ dl, const int32_t *__restrict__ nl,
+                                                           const sfe_keypoint *__restrict__ kr,
+                                                           const uint8_t *__restrict__ dr, const int32_t *__restrict__ nr,
+                                                           double y_thr, double max_dx, double ratio,
+                                                           int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist) {
+    const int f = blockIdx.y, lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= cap) return;
+    const int n_l = min(nl[f], cap), n_r = min(nr[f], cap);
+    const size_t base = (size_t)f * cap;
+    if (i >= n_l) {
+        if (lane == 0) {
+            out_idx[base + i] = -1;
+            if (out_dist) out_dist[base + i] = -1;
+        }
+        return;
+    }
+    const float lx = kl[base + i].x, ly = kl[base + i].y;
+    uint32_t a[8];
+    load_desc(dl + (base + i) * 32, a);
+    uint32_t k0 = kNoKey, k1 = kNoKey;
+    for (int j = lane; j < n_r; j += 32) {
+        const sfe_keypoint *r = &kr[base + j];
+        const float dx = __fsub_rn(lx, r->x), dy = __fsub_rn(ly, r->y);  // float subtraction, then widened
+        if (fabs((double)dy) > y_thr) continue;
+        if ((double)dx < 0.) continue;
+        if ((double)dx > max_dx) continue;
+        uint32_t b[8];
+        load_desc(dr + (base + j) * 32, b);
+        top2_insert(k0, k1, (uint32_t)hamming8(a, b) << 16 | (uint32_t)j);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        k1 = min(min(k1, o1), max(k0, o0));
+        k0 = min(k0, o0);
+    }
+    if (lane == 0) {
+        int idx = -1, dist = -1;
+        if (k0 != kNoKey) {
+            const double d0 = (double)(k0 >> 16), d1 = k1 == kNoKey ? 999999999. : (double)(k1 >> 16);
+            if (d0 < d1 * ratio) {  // :125-128
+                idx = (int)(k0 & 0xFFFF);
+                dist = (int)(k0 >> 16);
+            }
+        }
+        out_idx[base + i] = idx;
+        if (out_dist) out_dist[base + i] = dist;
+    }
+}
+
+void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoint *kl, const uint8_t *dl, const int32_t *nl,
+                         const sfe_keypoint *kr, const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
+                         double ratio, int32_t *out_idx, int32_t *out_dist) {
+    stereo_match_kernel<<<dim3(div_up(cap, 8), frames), 256, 0, st>>>(cap, kl, dl, nl, kr, dr, nr, y_thr, max_dx, ratio,
+                                                                      out_idx, out_dist);
+}
+
+// ---------------------------------------------------------------------------------------------
+// ProjectionMatch.  The per-frame FLANN kd-tree (src/frame.cpp:59-68,170-178) is replaced by a
+// uniform 32-px bucket grid over the frame's keypoints, rebuilt per call on the device; the
+// candidate set "all keypoints with d^2 < r^2" is identical, and candidate order does not matter
+// (SURVEY §8a invariants).
+// ---------------------------------------------------------------------------------------------
+constexpr int kGridShift = 5;
+
+struct KpGrid {
+    int gw, gh, m;
+    int *cell_start;   // gw*gh + 1
+    int *cell_fill;    // gw*gh
+    int *order;        // m: keypoint indices sorted by cell
+};
+
+__device__ __forceinline__ int grid_cell(const KpGrid &G, float x, float y) {
+    int cx = (int)floorf(x) >> kGridShift, cy = (int)floorf(y) >> kGridShift;
+    cx = min(max(cx, 0), G.gw - 1);
+    cy = min(max(cy, 0), G.gh - 1);
+    return cy * G.gw + cx;
+}
+
+__global__ void grid_count_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < G.m) atomicAdd(&G.cell_start[grid_cell(G, kps[j].x, kps[j].y) + 1], 1);
+}
+
+__global__ void grid_scan_kernel(KpGrid G) {  // one CTA; the grid has a few hundred cells
+    const int n = G.gw * G.gh;
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int i = 0; i <= n; i++) {
+            acc += G.cell_start[i];
+            G.cell_start[i] = acc;
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) G.cell_fill[i] = 0;
+}
+
+__global__ void grid_fill_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= G.m) return;
+    const int c = grid_cell(G, kps[j].x, kps[j].y);
+    G.order[G.cell_start[c] + atomicAdd(&G.cell_fill[c], 1)] = j;
+}
+
+struct ProjParams {
+    double rt[12];
+    sfe_camera cam;
+    double radius, ratio;
+};
+
+__global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjParams P, int n,
+                                                               const double *__restrict__ xw,
+                                                               const uint8_t *__restrict__ mp_desc,
+                                                               const uint8_t *__restrict__ skip,
+                                                               const sfe_keypoint *__restrict__ kps,
+                                                               const uint8_t *__restrict__ kp_desc,
+                                                               unsigned long long *__restrict__ best) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (skip && skip[i]) return;  // curr_frame->GetIndex(mp) >= 0, :144
+    const double X = xw[3 * (size_t)i], Y = xw[3 * (size_t)i + 1], Z = xw[3 * (size_t)i + 2];
+    // Xc = Tcw * Xw, evaluated left to right without contraction (:150)
+    const double xc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[0], X), __dmul_rn(P.rt[1], Y)), __dmul_rn(P.rt[2], Z)), P.rt[3]);
+    const double yc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[4], X), __dmul_rn(P.rt[5], Y)), __dmul_rn(P.rt[6], Z)), P.rt[7]);
+    const double zc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[8], X), __dmul_rn(P.rt[9], Y)), __dmul_rn(P.rt[10], Z)), P.rt[11]);
+    if (zc < 0.) return;  // :151-153
+    // Camera::Project + Distort, src/camera.cpp:50-79
+    const double x = __ddiv_rn(xc, zc), y = __ddiv_rn(yc, zc);
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), r4 = __dmul_rn(r2, r2);
+    const double a1 = __dmul_rn(__dmul_rn(2., x), y);
+    const double a2 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2., x), x));
+    const double a3 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2., y), y));
+    const double cdist = __dadd_rn(__dadd_rn(1., __dmul_rn(P.cam.d[0], r2)), __dmul_rn(P.cam.d[1], r4));
+    const double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, cdist), __dmul_rn(P.cam.d[2], a1)), __dmul_rn(P.cam.d[3], a2));
+    const double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, cdist), __dmul_rn(P.cam.d[2], a3)), __dmul_rn(P.cam.d[3], a1));
+    const double u = __dadd_rn(__dmul_rn(P.cam.fx, xd), P.cam.cx), v = __dadd_rn(__dmul_rn(P.cam.fy, yd), P.cam.cy);
+    if (u < 0. || v < 0. || u > (double)P.cam.width || v > (double)P.cam.height) return;  // IsInImage, :26-36
+    if (!(u == u) || !(v == v)) return;  // NaN: the radius search finds nothing
+    uint32_t a[8];
+    load_desc(mp_desc + (size_t)i * 32, a);
+    const double r2max = __dmul_rn(P.radius, P.radius);
+    const int cx0 = min(max((int)floor(u - P.radius) >> kGridShift, 0), G.gw - 1);
+    const int cx1 = min(max((int)floor(u + P.radius) >> kGridShift, 0), G.gw - 1);
+    const int cy0 = min(max((int)floor(v - P.radius) >> kGridShift, 0), G.gh - 1);
+    const int cy1 = min(max((int)floor(v + P.radius) >> kGridShift, 0), G.gh - 1);
+    uint32_t k0 = kNoKey, k1 = kNoKey;
+    for (int cy = cy0; cy <= cy1; cy++) {
+        const int s = G.cell_start[cy * G.gw + cx0], e = G.cell_start[cy * G.gw + cx1 + 1];  // cells of a row are contiguous
+        for (int t = s; t < e; t++) {
+            const int j = G.order[t];
+            const double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
+            const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+            if (!(d2 < r2max)) continue;  // FLANN radius search: strict <
+            uint32_t b[8];
+            load_desc(kp_desc + (size_t)j * 32, b);
+            top2_insert(k0, k1, (uint32_t)hamming8(a, b) << 16 | (uint32_t)j);
+        }
+    }
+    if (k0 == kNoKey) return;
+    const double d0 = (double)(k0 >> 16), d1 = k1 == kNoKey ? 999999999. : (double)(k1 >> 16);
+    if (d0 < d1 * P.ratio) {
+        // :197-204 processed sequentially keeps the smaller distance and lets the LATER query win a
+        // tie: that is the minimum of (dist, -query) over all accepted queries of a keypoint
+        const unsigned long long key = (unsigned long long)(k0 >> 16) << 32 | (0xFFFFFFFFu - (uint32_t)i);
+        atomicMin(&best[k0 & 0xFFFF], key);
+    }
+}
+
+__global__ void projection_decode_kernel(int m, const unsigned long long *__restrict__ best, int32_t *__restrict__ to_query,
+                                         int32_t *__restrict__ dist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    const unsigned long long k = best[j];
+    const bool none = k == ~0ull;
+    to_query[j] = none ? -1 : (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu));
+    if (dist) dist[j] = none ? -1 : (int32_t)(k >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Brute-force top-2: thread = query (descriptor + its two best keys in registers), CTA streams a
+// chunk of database rows through shared memory with broadcast reads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kKnnThreads = 256;
+constexpr int kKnnTile = 256;  // database rows per shared-memory tile
+
+__global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint8_t *__restrict__ db, long long rows,
+                                                                   long long idx_base, int chunk_rows,
+                                                                   const uint8_t *__restrict__ queries, int q,
+                                                                   unsigned long long *__restrict__ part) {
+    __shared__ uint4 tile[kKnnTile * 2];
+    const int tid = threadIdx.x, qi = blockIdx.y * kKnnThreads + tid;
+    const long long c0 = (long long)blockIdx.x * chunk_rows, c1 = min(c0 + (long long)chunk_rows, rows);
+    uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (qi < q) load_desc(queries + (size_t)qi * 32, a);
+    uint32_t k0 = kNoKey, k1 = kNoKey;  // dist << 22 | row within the chunk
+    for (long long t0 = c0; t0 < c1; t0 += kKnnTile) {
+        const int tn = (int)min((long long)kKnnTile, c1 - t0);
+        __syncthreads();
+        if (tid < tn) {
+            const uint4 *src = (const uint4 *)(db + (size_t)(t0 + tid) * 32);
+            tile[2 * tid] = __ldg(src);
+            tile[2 * tid + 1] = __ldg(src + 1);
+        }
+        __syncthreads();
+        const uint32_t rbase = (uint32_t)(t0 - c0);
+#pragma unroll 4
+        for (int r = 0; r < tn; r++) {
+            const uint4 u = tile[2 * r], w = tile[2 * r + 1];
+            const int d = __popc(a[0] ^ u.x) + __popc(a[1] ^ u.y) + __popc(a[2] ^ u.z) + __popc(a[3] ^ u.w) +
+                          __popc(a[4] ^ w.x) + __popc(a[5] ^ w.y) + __popc(a[6] ^ w.z) + __popc(a[7] ^ w.w);
+            top2_insert(k0, k1, (uint32_t)d << 22 | (rbase + r));
+        }
+    }
+    if (qi < q) {
+        unsigned long long *o = part + ((size_t)blockIdx.x * q + qi) * 2;
+        const unsigned long long gb = (unsigned long long)(idx_base + c0);
+        o[0] = k0 == kNoKey ? ~0ull : ((unsigned long long)(k0 >> 22) << 32 | (gb + (k0 & 0x3FFFFF)));
+        o[1] = k1 == kNoKey ? ~0ull : ((unsigned long long)(k1 >> 22) << 32 | (gb + (k1 & 0x3FFFFF)));
+    }
+}
+
+// lexicographic (dist, global index) top-2 over `parts` candidate pairs per query
+__global__ void knn2_merge_kernel(const unsigned long long *__restrict__ part, int parts, int q,
+                                  unsigned long long *__restrict__ keys_out, int32_t *__restrict__ quad_out) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= q) return;
+    unsigned long long k0 = ~0ull, k1 = ~0ull;
+    for (int p = 0; p < parts; p++) {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const unsigned long long k = part[((size_t)p * q + qi) * 2 + r];
+            k1 = min(k1, max(k0, k));
+            k0 = min(k0, k);
+        }
+    }
+    if (keys_out) {
+        keys_out[(size_t)qi * 2] = k0;
+        keys_out[(size_t)qi * 2 + 1] = k1;
+    }
+    if (quad_out) {
+        quad_out[4 * qi + 0] = k0 == ~0ull ? -1 : (int32_t)(k0 & 0xFFFFFFFFu);
+        quad_out[4 * qi + 1] = k0 == ~0ull ? 999999999 : (int32_t)(k0 >> 32);
+        quad_out[4 * qi + 2] = k1 == ~0ull ? -1 : (int32_t)(k1 & 0xFFFFFFFFu);
+        quad_out[4 * qi + 3] = k1 == ~0ull ? 999999999 : (int32_t)(k1 >> 32);
+    }
+}
+
+}  // namespace sfe
+
+using namespace sfe;
+
+struct sfe_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    int64_t launches = 0;
+    DevBuf<sfe_keypoint> d_kl, d_kr;
+    DevBuf<uint8_t> d_dl, d_dr, d_skip;
+    DevBuf<int32_t> d_n, d_idx, d_dist;
+    DevBuf<double> d_xw;
+    DevBuf<int> d_grid;
+    DevBuf<unsigned long long> d_best, d_part, d_keys;
+    DevBuf<int32_t> d_quad;
+};
+
+struct sfe_db {
+    int device = 0;
+    uint8_t *rows_dev = nullptr;
+    int64_t rows = 0, idx_base = 0;
+};
+
+static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                           const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
+                           int m_kps, double radius, double ratio, int32_t *to_query, int32_t *dist) {
+    cudaStream_t st = m->stream;
+    if (m_kps == 0) return SFE_OK;
+    KpGrid G;
+    G.gw = (std::max(cam->width, 1) >> kGridShift) + 1;
+    G.gh = (std::max(cam->height, 1) >> kGridShift) + 1;
+    G.m = m_kps;
+    const int cells = G.gw * G.gh;
+    SFE_CUDA(m->d_grid.ensure((size_t)2 * cells + 1 + m_kps));
+    SFE_CUDA(m->d_best.ensure(m_kps));
+    G.cell_start = m->d_grid.p;
+    G.cell_fill = m->d_grid.p + cells + 1;
+    G.order = m->d_grid.p + 2 * cells + 1;
+    SFE_CUDA(cudaMemsetAsync(G.cell_start, 0, sizeof(int) * (cells + 1), st));
+    SFE_CUDA(cudaMemsetAsync(m->d_best.p, 0xFF, sizeof(unsigned long long) * m_kps, st));
+    grid_count_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
+    grid_scan_kernel<<<1, 256, 0, st>>>(G);
+    grid_fill_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
+    m->launches += 3;
+    if (n > 0) {
+        ProjParams P;
+        memcpy(P.rt, rt, sizeof(P.rt));
+        P.cam = *cam;
+        P.radius = radius;
+        P.ratio = ratio;
+        projection_match_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, n, xw, mp_desc, skip, kps, kp_desc, m->d_best.p);
+        m->launches++;
+    }
+    projection_decode_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(m_kps, m->d_best.p, to_query, dist);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    return SFE_OK;
+}
+
+static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, int q, unsigned long long *keys_dev,
+                       int32_t *quad_dev) {
+    cudaStream_t st = m->stream;
+    const int qgroups = div_up(q, kKnnThreads);
+    int chunks = std::max(1, (2 * m->sm_count) / qgroups);
+    int64_t chunk_rows = std::max<int64_t>((db->rows + chunks - 1) / chunks, 1);
+    chunk_rows = (chunk_rows + kKnnTile - 1) / kKnnTile * kKnnTile;
+    SFE_REQUIRE(chunk_rows <= (1 << 22), SFE_ERR_UNSUPPORTED, "database shard larger than 2^22 rows per chunk");
+    chunks = (int)std::max<int64_t>((db->rows + chunk_rows - 1) / chunk_rows, 1);
+    SFE_CUDA(m->d_part.ensure((size_t)chunks * q * 2));
+    knn2_partial_kernel<<<dim3(chunks, qgroups), kKnnThreads, 0, st>>>(db->rows_dev, db->rows, db->idx_base, (int)chunk_rows,
+                                                                      q_dev, q, m->d_part.p);
+    knn2_merge_kernel<<<div_up(q, 128), 128, 0, st>>>(m->d_part.p, chunks, q, keys_dev, quad_dev);
+    m->launches += 2;
+    SFE_CUDA(cudaGetLastError());
+    return SFE_OK;
+}
+
+extern "C" {
+
+int sfe_matcher_create(int device, sfe_matcher **out) {
+    SFE_REQUIRE(out, SFE_ERR_BAD_ARG, "null argument");
+    int ndev = 0;
+    SFE_CUDA(cudaGetDeviceCount(&ndev));
+    SFE_REQUIRE(ndev > 0, SFE_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    SFE_REQUIRE(device >= 0 && device < ndev, SFE_ERR_BAD_ARG, "device index out of range");
+    DeviceGuard g(device);
+    sfe_matcher *m = new sfe_matcher();
+    m->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+        delete m;
+        return SFE_ERR_CUDA;
+    }
+    cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = m;
+    return SFE_OK;
+}
+
+int sfe_matcher_destroy(sfe_matcher *m) {
+    if (!m) return SFE_OK;
+    DeviceGuard g(m->device);
+    cudaStreamSynchronize(m->stream);
+    m->d_kl.release(); m->d_kr.release(); m->d_dl.release(); m->d_dr.release(); m->d_skip.release();
+    m->d_n.release(); m->d_idx.release(); m->d_dist.release(); m->d_xw.release(); m->d_grid.release();
+    m->d_best.release(); m->d_part.release(); m->d_keys.release(); m->d_quad.release();
+    cudaStreamDestroy(m->stream);
+    delete m;
+    return SFE_OK;
+}
+
+int sfe_matcher_launches(const sfe_matcher *m, int64_t *launches) {
+    SFE_REQUIRE(m && launches, SFE_ERR_BAD_ARG, "null argument");
+    *launches = m->launches;
+    return SFE_OK;
+}
+
+int sfe_event_record_matcher(sfe_event *ev, sfe_matcher *m) {
+    SFE_REQUIRE(ev && m, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    SFE_CUDA(cudaEventRecord(ev->ev, m->stream));
+    return SFE_OK;
+}
+
+int sfe_stereo_match(sfe_matcher *m, const sfe_keypoint *kps_l, const uint8_t *desc_l, int n_l, const sfe_keypoint *kps_r,
+                     const uint8_t *desc_r, int n_r, const sfe_stereo_params *sp, int32_t *out_idx, int32_t *out_dist) {
+    SFE_REQUIRE(m && n_l >= 0 && n_r >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    if (n_l == 0) return SFE_OK;
+    SFE_REQUIRE(kps_l && desc_l && out_idx && (n_r == 0 || (kps_r && desc_r)), SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(n_l < 65536 && n_r < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per image");
+    DeviceGuard g(m->device);
+    const sfe_stereo_params def = {3.0, 100.0, 0.5};
+    if (!sp) sp = &def;
+    const int cap = std::max(n_l, std::max(n_r, 1));
+    cudaStream_t st = m->stream;
+    SFE_CUDA(m->d_kl.ensure(cap)); SFE_CUDA(m->d_kr.ensure(cap));
+    SFE_CUDA(m->d_dl.ensure((size_t)cap * 32)); SFE_CUDA(m->d_dr.ensure((size_t)cap * 32));
+    SFE_CUDA(m->d_n.ensure(2)); SFE_CUDA(m->d_idx.ensure(cap)); SFE_CUDA(m->d_dist.ensure(cap));
+    const int32_t nn[2] = {n_l, n_r};
+    SFE_CUDA(cudaMemcpyAsync(m->d_n.p, nn, sizeof(nn), cudaMemcpyHostToDevice, st));
+    SFE_CUDA(cudaMemcpyAsync(m->d_kl.p, kps_l, sizeof(sfe_keypoint) * n_l, cudaMemcpyHostToDevice, st));
+    SFE_CUDA(cudaMemcpyAsync(m->d_dl.p, desc_l, (size_t)n_l * 32, cudaMemcpyHostToDevice, st));
+    if (n_r > 0) {
+        SFE_CUDA(cudaMemcpyAsync(m->d_kr.p, kps_r, sizeof(sfe_keypoint) * n_r, cudaMemcpyHostToDevice, st));
+        SFE_CUDA(cudaMemcpyAsync(m->d_dr.p, desc_r, (size_t)n_r * 32, cudaMemcpyHostToDevice, st));
+    }
+    launch_stereo_match(st, 1, cap, m->d_kl.p, m->d_dl.p, m->d_n.p, m->d_kr.p, m->d_dr.p, m->d_n.p + 1, sp->y_threshold,
+                        sp->max_dx, sp->best12_threshold, m->d_idx.p, m->d_dist.p);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaMemcpyAsync(out_idx, m->d_idx.p, sizeof(int32_t) * n_l, cudaMemcpyDeviceToHost, st));
+    if (out_dist) SFE_CUDA(cudaMemcpyAsync(out_dist, m->d_dist.p, sizeof(int32_t) * n_l, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev, int n,
+                             const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps_dev,
+                             const uint8_t *kp_desc_dev, int m_kps, double radius, double best12_threshold,
+                             int32_t *kp_to_query_dev, int32_t *kp_dist_dev) {
+    SFE_REQUIRE(m && rt && cam && n >= 0 && m_kps >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(m_kps == 0 || (kps_dev && kp_desc_dev && kp_to_query_dev), SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(n == 0 || (xw_dev && mp_desc_dev), SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(m_kps < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per frame");
+    DeviceGuard g(m->device);
+    int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, rt, cam, kps_dev, kp_desc_dev, m_kps, radius,
+                             best12_threshold, kp_to_query_dev, kp_dist_dev);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    return SFE_OK;
+}
+
+int sfe_projection_match(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                         const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
+                         int m_kps, double radius, double best12_threshold, int32_t *kp_to_query, int32_t *kp_dist) {
+    SFE_REQUIRE(m && rt && cam && n >= 0 && m_kps >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    if (m_kps == 0) return SFE_OK;
+    SFE_REQUIRE(kps && kp_desc && kp_to_query, SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(n == 0 || (xw && mp_desc), SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(m_kps < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per frame");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    const int nn = std::max(n, 1);
+    SFE_CUDA(m->d_xw.ensure((size_t)nn * 3)); SFE_CUDA(m->d_dl.ensure((size_t)nn * 32)); SFE_CUDA(m->d_skip.ensure(nn));
+    SFE_CUDA(m->d_kr.ensure(m_kps)); SFE_CUDA(m->d_dr.ensure((size_t)m_kps * 32));
+    SFE_CUDA(m->d_idx.ensure(m_kps)); SFE_CUDA(m->d_dist.ensure(m_kps));
+    if (n > 0) {
+        SFE_CUDA(cudaMemcpyAsync(m->d_xw.p, xw, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+        SFE_CUDA(cudaMemcpyAsync(m->d_dl.p, mp_desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        if (skip) SFE_CUDA(cudaMemcpyAsync(m->d_skip.p, skip, n, cudaMemcpyHostToDevice, st));
+    }
+    SFE_CUDA(cudaMemcpyAsync(m->d_kr.p, kps, sizeof(sfe_keypoint) * m_kps, cudaMemcpyHostToDevice, st));
+    SFE_CUDA(cudaMemcpyAsync(m->d_dr.p, kp_desc, (size_t)m_kps * 32, cudaMemcpyHostToDevice, st));
+    int rc = projection_impl(m, m->d_xw.p, m->d_dl.p, skip ? m->d_skip.p : nullptr, n, rt, cam, m->d_kr.p, m->d_dr.p, m_kps,
+                             radius, best12_threshold, m->d_idx.p, m->d_dist.p);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(kp_to_query, m->d_idx.p, sizeof(int32_t) * m_kps, cudaMemcpyDeviceToHost, st));
+    if (kp_dist) SFE_CUDA(cudaMemcpyAsync(kp_dist, m->d_dist.p, sizeof(int32_t) * m_kps, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+int sfe_db_create(sfe_matcher *m, const uint8_t *desc_host, int64_t rows, int64_t idx_base, sfe_db **out) {
+    SFE_REQUIRE(m && out && rows >= 0 && idx_base >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(rows == 0 || desc_host, SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(idx_base + rows < (1ll << 31), SFE_ERR_UNSUPPORTED, "global row index must fit int32");
+    DeviceGuard g(m->device);
+    sfe_db *db = new sfe_db();
+    db->device = m->device;
+    db->rows = rows;
+    db->idx_base = idx_base;
+    cudaError_t e = cudaMalloc((void **)&db->rows_dev, std::max<size_t>((size_t)rows * 32, 32));
+    if (e == cudaSuccess && rows > 0) e = cudaMemcpy(db->rows_dev, desc_host, (size_t)rows * 32, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("database upload: %s", cudaGetErrorString(e));
+        if (db->rows_dev) cudaFree(db->rows_dev);
+        delete db;
+        return SFE_ERR_CUDA;
+    }
+    *out = db;
+    return SFE_OK;
+}
+
+int sfe_db_destroy(sfe_db *db) {
+    if (!db) return SFE_OK;
+    DeviceGuard g(db->device);
+    cudaFree(db->rows_dev);
+    delete db;
+    return SFE_OK;
+}
+
+int sfe_knn2_dev(sfe_matcher *m, const sfe_db *db, const uint8_t *queries_dev, int q, uint64_t *keys_dev) {
+    SFE_REQUIRE(m && db && queries_dev && keys_dev && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(db->device == m->device, SFE_ERR_BAD_ARG, "database lives on another device");
+    DeviceGuard g(m->device);
+    int rc = knn_partial(m, db, queries_dev, q, (unsigned long long *)keys_dev, nullptr);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    return SFE_OK;
+}
+
+int sfe_knn2_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int q, int32_t *out_dev) {
+    SFE_REQUIRE(m && keys_dev && out_dev && shards >= 1 && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
+    DeviceGuard g(m->device);
+    knn2_merge_kernel<<<div_up(q, 128), 128, 0, m->stream>>>((const unsigned long long *)keys_dev, shards, q, nullptr, out_dev);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    return SFE_OK;
+}
+
+int sfe_knn2(sfe_matcher *m, const sfe_db *db, const uint8_t *queries, int q, int32_t *out) {
+    SFE_REQUIRE(m && db && queries && out && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(db->device == m->device, SFE_ERR_BAD_ARG, "database lives on another device");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    SFE_CUDA(m->d_dl.ensure((size_t)q * 32));
+    SFE_CUDA(m->d_quad.ensure((size_t)q * 4));
+    SFE_CUDA(cudaMemcpyAsync(m->d_dl.p, queries, (size_t)q * 32, cudaMemcpyHostToDevice, st));
+    int rc = knn_partial(m, db, m->d_dl.p, q, nullptr, m->d_quad.p);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(out, m->d_quad.p, sizeof(int32_t) * 4 * q, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,274 @@
+"""Parity tests proper: the CUDA path through the C ABI (libsfe.so) against the CPU oracle and the
+committed golden fixtures.  Integer / byte / index work is compared bit-exactly; the float fields
+of a keypoint (x, y, size, angle, response) are compared bit-exactly too (tolerance stated by the
+north star: angle 1e-4 rad, pyramid +-1 LSB -- we hold 0)."""
+import os
+
+import numpy as np
+import pytest
+
+from slam_toolkit_b200 import api, synth
+from util import sha
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    if api.device_count() < 1:
+        pytest.fail("no CUDA device: the product has no CPU fallback")
+    return 0
+
+
+@pytest.fixture(scope="module")
+def kitti_ex(gpu):
+    return api.ORBextractor(max_images=8)
+
+
+def _stage_report(ex, ref, image_idx, nlevels):
+    bad = []
+    for l in range(nlevels):
+        if not np.array_equal(ex.debug_level(image_idx, l), ref.level(l)):
+            bad.append(f"pyramid L{l}: {(ex.debug_level(image_idx, l) != ref.level(l)).sum()} px differ")
+        c, rc = ex.debug_points(image_idx, l), ref.candidates(l)
+        if not np.array_equal(c, rc):
+            bad.append(f"FAST candidates L{l}: {len(c)} vs {len(rc)}")
+        d, rd = ex.debug_points(image_idx, l, distributed=True), ref.distributed(l)
+        if not np.array_equal(d, rd):
+            bad.append(f"quadtree L{l}: {len(d)} vs {len(rd)}")
+        rb = ref.blur(l)
+        if rb is not None and not np.array_equal(ex.debug_level(image_idx, l, blur=True), rb):
+            bad.append(f"blur L{l}: {(ex.debug_level(image_idx, l, blur=True) != rb).sum()} px differ")
+    return bad
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_extract_kitti_vs_oracle_and_golden(kitti_ex, oracle, golden, seed):
+    L, _ = synth.stereo_pair(seed)
+    k, d = kitti_ex.extract(L)
+    ref = oracle.Extractor()
+    rk, rd = ref.extract(L)
+    stages = _stage_report(kitti_ex, ref, 0, 8)
+    assert not stages, stages
+    assert len(k) == len(rk)
+    for f in ("x", "y", "size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(k[f], rk[f]), f"keypoint field {f}: {(k[f] != rk[f]).sum()} differ"
+    assert np.array_equal(d, rd), f"{(d != rd).any(axis=1).sum()} descriptors differ"
+    g = golden["kitti"][str(seed)]["L"]
+    assert sha(k) == g["kps"] and sha(d) == g["desc"]
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_extract_small_configs(gpu, oracle, golden, case):
+    rec = golden["small"][str(case)]
+    w, h, nf, sf, nl, it, mt = rec["params"]
+    img, _ = synth.stereo_pair(100 + case, w, h)
+    ex = api.ORBextractor(nf, sf, nl, it, mt)
+    k, d = ex.extract(img)
+    ref = oracle.Extractor(nf, sf, nl, it, mt)
+    rk, rd = ref.extract(img)
+    stages = _stage_report(ex, ref, 0, nl)
+    assert not stages, stages
+    assert np.array_equal(k, rk) and np.array_equal(d, rd)
+    assert sha(k) == rec["kps"] and sha(d) == rec["desc"]
+
+
+def test_edge_images(kitti_ex):
+    k, d = kitti_ex.extract(np.zeros((0, 0), np.uint8))
+    assert len(k) == 0 and d.shape == (0, 32)
+    k, d = kitti_ex.extract(np.full((376, 1241), 90, np.uint8))  # flat: no corner anywhere
+    assert len(k) == 0
+    # a FAST cell with < 7 rows, a level whose window is < 30 px (T5), strided input
+    img, _ = synth.stereo_pair(42, 200, 95)
+    ex = api.ORBextractor(200, 1.3, 5, 20, 7)
+    k, d = ex.extract(img)
+    import oracle_c
+    rk, rd = oracle_c.Extractor(200, 1.3, 5, 20, 7).extract(img)
+    assert np.array_equal(k, rk) and np.array_equal(d, rd)
+
+
+def test_fallback_threshold_cells(gpu, oracle):
+    """low-contrast image: most cells find nothing at 20 and retry at 7 (src/orb_extractor.cpp:811-816)."""
+    img, _ = synth.stereo_pair(7, 400, 200)
+    img = (96 + (img.astype(np.int32) - 96) // 3).astype(np.uint8)
+    ex = api.ORBextractor(500, 1.2, 4, 20, 7)
+    k, d = ex.extract(img)
+    ref = oracle.Extractor(500, 1.2, 4, 20, 7)
+    rk, rd = ref.extract(img)
+    assert len(rk) > 50 and (rk["response"] < 20).any()
+    assert not _stage_report(ex, ref, 0, 4)
+    assert np.array_equal(k, rk) and np.array_equal(d, rd)
+
+
+def test_batch_equals_single(kitti_ex, oracle):
+    imgs = np.stack([synth.stereo_pair(s)[i] for s in (4, 5) for i in (0, 1)])
+    kps, desc, n = kitti_ex.extract_batch(imgs)
+    ref = oracle.Extractor()
+    for i in range(4):
+        rk, rd = ref.extract(imgs[i])
+        assert n[i] == len(rk)
+        assert np.array_equal(kps[i, :n[i]], rk) and np.array_equal(desc[i, :n[i]], rd), f"image {i}"
+
+
+def test_stereo_frames_vs_oracle_and_golden(kitti_ex, oracle, golden):
+    seeds = [0, 6, 7]
+    L = np.stack([synth.stereo_pair(s)[0] for s in seeds])
+    R = np.stack([synth.stereo_pair(s)[1] for s in seeds])
+    out = kitti_ex.stereo_frames(L, R)
+    ref = oracle.Extractor()
+    for f, s in enumerate(seeds):
+        kl, dl = ref.extract(L[f])
+        kr, dr = ref.extract(R[f])
+        si, sd = oracle.stereo_match(kl, dl, kr, dr)
+        nl, nr = out["n_l"][f], out["n_r"][f]
+        assert (nl, nr) == (len(kl), len(kr))
+        assert np.array_equal(out["kps_l"][f, :nl], kl) and np.array_equal(out["desc_l"][f, :nl], dl)
+        assert np.array_equal(out["kps_r"][f, :nr], kr) and np.array_equal(out["desc_r"][f, :nr], dr)
+        assert np.array_equal(out["stereo_idx"][f, :nl], si), f"{(out['stereo_idx'][f, :nl] != si).sum()} stereo indices differ"
+        assert np.array_equal(out["stereo_dist"][f, :nl], sd)
+        g = golden["kitti"][str(s)]
+        assert sha(si) == g["stereo_idx"] and int((si >= 0).sum()) == g["n_stereo"]
+        # domain property: uniform disparity 24 px on level-0 matches
+        ok = (si >= 0) & (kl["octave"] == 0)
+        assert np.median(kl["x"][ok] - kr["x"][si[ok]]) == 24.0
+
+
+def test_resident_entry_points_match_host_ones(kitti_ex, oracle):
+    L, R = synth.stereo_pair(3)
+    cap, h, w = kitti_ex.cap, *L.shape
+    host = kitti_ex.stereo_frames(L[None], R[None])
+    dl, dr = api.DeviceBuffer(L.nbytes).upload(L), api.DeviceBuffer(R.nbytes).upload(R)
+    spec = {"kps_l": 28 * cap, "desc_l": 32 * cap, "n_l": 4, "kps_r": 28 * cap, "desc_r": 32 * cap, "n_r": 4,
+            "stereo_idx": 4 * cap, "stereo_dist": 4 * cap}
+    bufs = {k: api.DeviceBuffer(v) for k, v in spec.items()}
+    kitti_ex.stereo_frames_dev(dl.ptr, dr.ptr, 1, w, h, {k: b.ptr for k, b in bufs.items()})
+    nl = int(bufs["n_l"].download((1,), np.int32)[0])
+    assert nl == host["n_l"][0]
+    assert np.array_equal(bufs["kps_l"].download((cap,), api.KP_DTYPE)[:nl], host["kps_l"][0, :nl])
+    assert np.array_equal(bufs["desc_r"].download((cap, 32), np.uint8)[:host["n_r"][0]], host["desc_r"][0, :host["n_r"][0]])
+    assert np.array_equal(bufs["stereo_idx"].download((cap,), np.int32)[:nl], host["stereo_idx"][0, :nl])
+    # extract_batch_dev
+    kitti_ex.extract_batch_dev(dl.ptr, 1, w, h, bufs["kps_r"].ptr, bufs["desc_r"].ptr, bufs["n_r"].ptr)
+    n = int(bufs["n_r"].download((1,), np.int32)[0])
+    assert n == nl and np.array_equal(bufs["desc_r"].download((cap, 32), np.uint8)[:n], host["desc_l"][0, :n])
+
+
+# ---- matchers -------------------------------------------------------------------------------------
+def _mk_kps(xy):
+    k = np.zeros(len(xy), api.KP_DTYPE)
+    k["x"], k["y"] = xy[:, 0], xy[:, 1]
+    return k
+
+
+def test_stereo_match_random_and_edges(gpu, oracle):
+    m = api.Matcher()
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 300, 2500):
+        xyr = np.stack([rng.uniform(0, 1241, n), rng.integers(0, 300, n) * 1.2], 1).astype(np.float32)
+        dr = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        sel = rng.integers(0, n, n)
+        xyl = xyr[sel] + np.stack([rng.uniform(-5, 110, n), rng.integers(-4, 5, n) * 1.0], 1).astype(np.float32)
+        dl = dr[sel].copy()
+        flips = rng.integers(0, 60, n)
+        for i in range(n):
+            for b in rng.integers(0, 256, int(flips[i])):
+                dl[i, b >> 3] ^= np.uint8(1 << (b & 7))
+        idx, dist = m.StereoMatch(_mk_kps(xyl), dl, _mk_kps(xyr), dr)
+        ri, rd = oracle.stereo_match(_mk_kps(xyl), dl, _mk_kps(xyr), dr)
+        assert np.array_equal(idx, ri) and np.array_equal(dist, rd), n
+    d = np.zeros((3, 32), np.uint8)
+    d[1, 0] = 0xFF
+    kl = _mk_kps(np.array([[50.0, 10.0]], np.float32))
+    assert m.StereoMatch(kl, d[:1], _mk_kps(np.array([[40.0, 10.0]], np.float32)), d[1:2])[0].tolist() == [0]  # single candidate
+    kr = _mk_kps(np.array([[40.0, 10.0], [30.0, 12.0]], np.float32))
+    assert m.StereoMatch(kl, d[:1], kr, np.stack([d[1], d[1]]))[0].tolist() == [-1]  # tie for best: rejected
+    assert m.StereoMatch(kl, d[:1], _mk_kps(np.array([[50.0, 13.0]], np.float32)), d[1:2])[0].tolist() == [0]
+    assert m.StereoMatch(kl, d[:1], _mk_kps(np.array([[50.0, 13.5]], np.float32)), d[1:2])[0].tolist() == [-1]
+    assert m.StereoMatch(kl, d[:1], _mk_kps(np.array([[-50.0, 10.0]], np.float32)), d[1:2])[0].tolist() == [0]
+    assert m.StereoMatch(kl, d[:1], _mk_kps(np.array([[50.5, 10.0]], np.float32)), d[1:2])[0].tolist() == [-1]
+    assert m.StereoMatch(kl, d[:1], kr[:0], d[:0])[0].tolist() == [-1]
+    assert m.StereoMatch(kl[:0], d[:0], kr, d[:2])[0].tolist() == []
+
+
+def test_projection_match_vs_oracle(gpu, oracle, kitti_ex):
+    m = api.Matcher()
+    L, _ = synth.stereo_pair(0)
+    kps, desc = kitti_ex.extract(L)
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    th = 0.01
+    poses = [np.eye(3, 4), np.array([[np.cos(th), 0, np.sin(th), 0.05], [0, 1, 0, -0.02], [-np.sin(th), 0, np.cos(th), 0.2]])]
+    for n, seed in ((5000, 1), (60000, 2)):
+        xw, mpd = synth.projection_scene(xy, desc, n, seed=seed)
+        skip = (np.random.default_rng(seed).uniform(0, 1, n) < 0.05).astype(np.uint8)
+        for dcoef in ([0, 0, 0, 0], [-0.05, 0.01, 0.001, -0.002]):
+            for rt in poses:
+                for radius in (10.0, 50.0, 100.0):
+                    if n > 5000 and (radius != 50.0 or rt is poses[1]):
+                        continue
+                    cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, dcoef, 1241, 376)
+                    ocam = oracle.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, dcoef, 1241, 376)
+                    got, gd = m.ProjectionMatch(xw, mpd, skip, rt, cam, kps, desc, radius)
+                    ref, rd = oracle.projection_match(xw, mpd, skip, rt, ocam, kps, desc, radius)
+                    assert np.array_equal(got, ref), f"n={n} r={radius}: {(got != ref).sum()} keypoints differ"
+                    assert np.array_equal(gd, rd)
+    assert (ref >= 0).sum() > 100
+    # conflict rule: equal distance -> the later query wins; skip mask; behind camera
+    kp1 = _mk_kps(np.array([[600.0, 180.0]], np.float32))
+    kd1 = np.zeros((1, 32), np.uint8)
+    z = 10.0
+    X = np.array([[(600.0 - synth.KITTI_CX) / synth.KITTI_FX * z, (180.0 - synth.KITTI_CY) / synth.KITTI_FY * z, z]] * 3)
+    mpd = np.zeros((3, 32), np.uint8)
+    mpd[0, 0], mpd[1, 0], mpd[2, 1] = 0x03, 0x01, 0x80
+    cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0] * 4, 1241, 376)
+    assert m.ProjectionMatch(X, mpd, None, np.eye(3, 4), cam, kp1, kd1, 50.0)[0].tolist() == [2]
+    assert m.ProjectionMatch(X, mpd, np.array([0, 0, 1], np.uint8), np.eye(3, 4), cam, kp1, kd1, 50.0)[0].tolist() == [1]
+    Xb = X.copy()
+    Xb[:, 2] = -z
+    assert m.ProjectionMatch(Xb, mpd, None, np.eye(3, 4), cam, kp1, kd1, 50.0)[0].tolist() == [-1]
+    assert m.ProjectionMatch(X[:0], mpd[:0], None, np.eye(3, 4), cam, kp1, kd1, 50.0)[0].tolist() == [-1]
+
+
+def test_knn2_vs_oracle_and_sharded_merge(gpu, oracle):
+    m = api.Matcher()
+    db = synth.knn_database(30011, seed=1)
+    q, rows = synth.knn_queries(db, 333, seed=2)
+    ref = oracle.knn2(q, db)
+    full = m.knn2(m.create_db(db), q)
+    assert np.array_equal(full, ref)
+    # tiny and degenerate shards
+    for rows_n in (0, 1, 2, 255, 257):
+        got = m.knn2(m.create_db(db[:rows_n]), q[:5])
+        assert np.array_equal(got, oracle.knn2(q[:5], db[:rows_n])), rows_n
+    # sharded: per-shard keys -> gathered -> merge == single pass, independent of the shard boundaries
+    Q = len(q)
+    qd = api.DeviceBuffer(q.nbytes).upload(q)
+    for bounds in ([0, 10000, 30011], [0, 1, 7777, 7778, 30011]):
+        G = len(bounds) - 1
+        keys = api.DeviceBuffer(G * Q * 2 * 8)
+        for s in range(G):
+            shard = m.create_db(db[bounds[s]:bounds[s + 1]], idx_base=bounds[s])
+            m.knn2_dev(shard, qd.ptr, Q, keys.ptr + s * Q * 2 * 8)
+        out = api.DeviceBuffer(Q * 16)
+        m.knn2_merge_dev(keys.ptr, G, Q, out.ptr)
+        assert np.array_equal(out.download((Q, 4), np.int32), ref), bounds
+
+
+def test_knn2_full_size_properties(gpu):
+    """BASELINE config 4 shape at reduced M (2M rows; the 10M run is bench.py --workload knn):
+    size-independent properties instead of the (too slow) oracle."""
+    m = api.Matcher()
+    db = synth.knn_database(2_000_000, seed=1234)
+    q, rows = synth.knn_queries(db, 2000, seed=5678)
+    out = m.knn2(m.create_db(db), q)
+    d_true = np.unpackbits(db[rows] ^ q, axis=1).sum(1)
+    assert (out[:, 1] <= d_true).all()                      # best is at least as good as the planted row
+    exact = out[:, 1] == d_true
+    assert (out[exact, 0] <= rows[exact]).all()             # ties resolved towards the smaller index
+    assert (out[:, 1] <= out[:, 3]).all() and (out[:, 0] != out[:, 2]).all()
+    chk = np.unpackbits(db[out[:, 0]] ^ q, axis=1).sum(1)   # reported distance is the real distance
+    assert np.array_equal(chk, out[:, 1])
+    chk2 = np.unpackbits(db[out[:, 2]] ^ q, axis=1).sum(1)
+    assert np.array_equal(chk2, out[:, 3])
+    ratio_pass = (2 * out[:, 1] < out[:, 3]).mean()
+    assert 0.2 < ratio_pass <= 1.0
