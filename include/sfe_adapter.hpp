@@ -1,0 +1,200 @@
+// sfe_adapter.hpp -- header-only C++ host side above the sfe C ABI that keeps the reference's own
+// call surface, so frame.cpp / posetracker.cpp / pipeline.cpp / loopcloser.cpp compile unchanged:
+//
+//   ORB_SLAM2::ORBextractor          replaces include/orb_extractor.h:45-133 + src/orb_extractor.cpp
+//   sfe_adapter::StereoMatch         body for  void StereoMatch(StereoFrame*)          (src/matcher.cpp:54-132)
+//   sfe_adapter::ProjectionMatch     body for  std::map<int,Mappoint*> ProjectionMatch (src/matcher.cpp:134-209)
+//
+// It is written against the OpenCV 3.4 types the reference uses (cv::Mat, cv::KeyPoint,
+// cv::InputArray, cv::OutputArray).  Where OpenCV is not installed (this repo's CI) define
+// SFE_ADAPTER_CV_STANDIN before including it and provide the few members used below
+// (tests/cpp/cv_standin.hpp does).  The matcher templates only touch the reference's public
+// accessors (GetKeypoints, GetDescription(i), GetCamera()->GetK(), mp->GetXw(), ...), so they bind to
+// the real Frame / StereoFrame / Mappoint / g2o::SE3Quat as they are.
+//
+// Errors: an empty image returns silently with the outputs untouched (src/orb_extractor.cpp:1046-1047);
+// zero keypoints releases the descriptor matrix (:1064-1065); every other failure throws
+// std::runtime_error carrying sfe_last_error().  There is no CPU fallback.
+#ifndef SFE_ADAPTER_HPP_
+#define SFE_ADAPTER_HPP_
+
+#include <cstring>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sfe.h"
+
+#ifndef SFE_ADAPTER_CV_STANDIN
+#include <opencv2/core/core.hpp>
+#include <opencv2/features2d/features2d.hpp>
+#endif
+
+static_assert(sizeof(sfe_keypoint) == 28, "sfe_keypoint must be 28 bytes");
+static_assert(sizeof(cv::KeyPoint) == sizeof(sfe_keypoint), "cv::KeyPoint layout changed: adapter memcpy is invalid");
+
+namespace sfe_adapter {
+
+inline void check(int status, const char *what) {
+    if (status != SFE_OK)
+        throw std::runtime_error(std::string(what) + ": " + sfe_status_string(status) + " (" + sfe_last_error() + ")");
+}
+
+// one matcher handle per thread: ProjectionMatch is entered from the tracking AND the mapping
+// thread of the reference (src/pipeline.cpp:98-141, src/posetracker.cpp:186), handles are not re-entrant
+inline sfe_matcher *thread_matcher(int device = 0) {
+    struct Holder {
+        sfe_matcher *m = nullptr;
+        ~Holder() { sfe_matcher_destroy(m); }
+    };
+    static thread_local Holder h;
+    if (!h.m) check(sfe_matcher_create(device, &h.m), "sfe_matcher_create");
+    return h.m;
+}
+
+}  // namespace sfe_adapter
+
+namespace ORB_SLAM2 {
+
+class ORBextractor {
+public:
+    enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+    ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST)
+        : nfeatures_(nfeatures), scaleFactor_(scaleFactor), nlevels_(nlevels) {
+        sfe_extractor_params p = {nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST};
+        sfe_adapter::check(sfe_extractor_create(&p, 0, 2, &ex_), "sfe_extractor_create");
+        sfe_adapter::check(sfe_extractor_max_keypoints(ex_, &cap_), "sfe_extractor_max_keypoints");
+        mvScaleFactor.resize(nlevels); mvInvScaleFactor.resize(nlevels);
+        mvLevelSigma2.resize(nlevels); mvInvLevelSigma2.resize(nlevels);
+        sfe_adapter::check(sfe_extractor_tables(ex_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                                                mvInvLevelSigma2.data(), nullptr), "sfe_extractor_tables");
+        kps_.resize(cap_);
+    }
+    ~ORBextractor() { sfe_extractor_destroy(ex_); }
+    ORBextractor(const ORBextractor &) = delete;
+    ORBextractor &operator=(const ORBextractor &) = delete;
+
+    // Compute the ORB features and descriptors on an image.  Mask is ignored (as in the reference).
+    void extract(cv::InputArray _image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint> &_keypoints,
+                 cv::OutputArray _descriptors) {
+        if (_image.empty()) return;
+        cv::Mat image = _image.getMat();
+        if (image.type() != CV_8UC1) throw std::invalid_argument("ORBextractor::extract: CV_8UC1 image expected");
+        desc_.resize((size_t)cap_ * 32);
+        int n = 0;
+        sfe_adapter::check(sfe_extract(ex_, image.data, image.cols, image.rows, (int)image.step, kps_.data(), desc_.data(),
+                                       cap_, &n), "sfe_extract");
+        if (n == 0) {
+            _descriptors.release();
+        } else {
+            _descriptors.create(n, 32, CV_8U);
+            cv::Mat d = _descriptors.getMat();
+            for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), desc_.data() + (size_t)i * 32, 32);
+        }
+        _keypoints.resize(n);
+        if (n) std::memcpy((void *)_keypoints.data(), kps_.data(), sizeof(sfe_keypoint) * (size_t)n);
+    }
+
+    int inline GetLevels() { return nlevels_; }
+    float inline GetScaleFactor() { return (float)scaleFactor_; }
+    std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+    std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+    std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+    std::vector<float> inline GetInverseScaleSigmaSquares() const { return mvInvLevelSigma2; }
+
+    // The reference exposes the pyramid as a public member that nothing outside the extractor reads
+    // (grep mvImagePyramid: orb_extractor.* only).  It stays declared for source compatibility and is
+    // left empty: the pyramid lives in HBM.
+    std::vector<cv::Mat> mvImagePyramid;
+
+    static int DescriptorDistance(const cv::Mat &a, const cv::Mat &b) { return sfe_hamming256(a.data, b.data); }
+
+    sfe_extractor *handle() { return ex_; }
+
+protected:
+    int nfeatures_;
+    double scaleFactor_;
+    int nlevels_;
+    std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+
+private:
+    sfe_extractor *ex_ = nullptr;
+    int cap_ = 0;
+    std::vector<sfe_keypoint> kps_;
+    std::vector<uint8_t> desc_;
+};
+
+}  // namespace ORB_SLAM2
+
+namespace sfe_adapter {
+
+// void StereoMatch(StereoFrame* frame)  -- include/matcher.h:33
+template <class StereoFrameT>
+void StereoMatch(StereoFrameT *frame) {
+    const std::vector<cv::KeyPoint> &kl = frame->GetKeypoints();
+    const std::vector<cv::KeyPoint> &kr = frame->GetRightKeypoints();
+    std::vector<uint8_t> dl(kl.size() * 32), dr(kr.size() * 32);
+    for (size_t i = 0; i < kl.size(); i++) std::memcpy(&dl[i * 32], frame->GetDescription((int)i).data, 32);
+    for (size_t j = 0; j < kr.size(); j++) std::memcpy(&dr[j * 32], frame->GetRightDescription((int)j).data, 32);
+    std::vector<int> stereo_indices(kl.size(), -1);
+    const sfe_stereo_params sp = {3., 100., 0.5};  // src/matcher.cpp:68-70
+    static_assert(sizeof(int) == sizeof(int32_t), "int must be 32 bit");
+    check(sfe_stereo_match(thread_matcher(), (const sfe_keypoint *)kl.data(), dl.data(), (int)kl.size(),
+                           (const sfe_keypoint *)kr.data(), dr.data(), (int)kr.size(), &sp, stereo_indices.data(), nullptr),
+          "sfe_stereo_match");
+    frame->SetStereoCorrespond(stereo_indices);
+}
+
+// std::map<int, Mappoint*> ProjectionMatch(const std::set<Mappoint*>&, const g2o::SE3Quat&, const Frame*, double)
+//   -- include/matcher.h:35-38.  PoseT needs rotation().toRotationMatrix() and translation() (g2o::SE3Quat has both).
+template <class MappointT, class PoseT, class FrameT>
+std::map<int, MappointT *> ProjectionMatch(const std::set<MappointT *> &mappoints, const PoseT &predicted_Tcw,
+                                           const FrameT *curr_frame, double search_radius) {
+    const double best12_threshold = 0.5;  // src/matcher.cpp:138
+    const auto *camera = curr_frame->GetCamera();
+    std::vector<MappointT *> order;  // the set's iteration order = the reference's query order (T3)
+    std::vector<double> xw;
+    std::vector<uint8_t> desc, skip;
+    order.reserve(mappoints.size());
+    for (MappointT *mp : mappoints) {
+        order.push_back(mp);
+        const auto X = mp->GetXw();
+        xw.push_back(X[0]); xw.push_back(X[1]); xw.push_back(X[2]);
+        const cv::Mat d = mp->GetDescription();
+        desc.insert(desc.end(), d.data, d.data + 32);
+        skip.push_back(curr_frame->GetIndex(mp) >= 0 ? 1 : 0);  // :144
+    }
+    const auto R = predicted_Tcw.rotation().toRotationMatrix();
+    const auto t = predicted_Tcw.translation();
+    double rt[12];
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) rt[4 * r + c] = R(r, c);
+        rt[4 * r + 3] = t[r];
+    }
+    sfe_camera cam;
+    const auto &K = camera->GetK();
+    const auto &D = camera->GetD();
+    cam.fx = K(0, 0); cam.fy = K(1, 1); cam.cx = K(0, 2); cam.cy = K(1, 2);
+    for (int i = 0; i < 4; i++) cam.d[i] = D(i);
+    cam.width = camera->GetWidth();
+    cam.height = camera->GetHeight();
+    const std::vector<cv::KeyPoint> &kps = curr_frame->GetKeypoints();
+    std::vector<uint8_t> kdesc(kps.size() * 32);
+    for (size_t i = 0; i < kps.size(); i++) std::memcpy(&kdesc[i * 32], curr_frame->GetDescription((int)i).data, 32);
+    std::vector<int32_t> to_query(kps.size(), -1);
+    check(sfe_projection_match(thread_matcher(), xw.data(), desc.data(), skip.data(), (int)order.size(), rt, &cam,
+                               (const sfe_keypoint *)kps.data(), kdesc.data(), (int)kps.size(), search_radius,
+                               best12_threshold, to_query.data(), nullptr),
+          "sfe_projection_match");
+    std::map<int, MappointT *> matches;
+    for (size_t j = 0; j < kps.size(); j++)
+        if (to_query[j] >= 0) matches[(int)j] = order[(size_t)to_query[j]];
+    return matches;
+}
+
+}  // namespace sfe_adapter
+
+#endif  // SFE_ADAPTER_HPP_

@@ -5,6 +5,7 @@
 // in the reference build (no -march => no FMA, CMakeLists.txt:54-55).
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 
 #include "sfe_extract.cuh"
 
@@ -811,7 +812,8 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                         "portrait level (W/H < 0.5): the reference divides by nIni == 0");
             L.hx = (float)L.win_w / (float)L.n_ini;
         }
-        L.cand_cap = tested > 0 ? std::min(std::max(tested / 64, 512), kMaxCandCap) : 0;
+        // NMS'd FAST corners reach ~1 per 30 px on the small pyramid levels of textured frames
+        L.cand_cap = tested > 0 ? std::min(std::max(tested / 12, 1024), kMaxCandCap) : 0;
         L.cand_off = cand_off;
         cand_off += L.cand_cap;
         L.kp_cap = tested > 0 ? std::max(L.quota + 3, 4 * L.n_ini) + 1 : 0;
@@ -876,7 +878,6 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
         SFE_CUDA(cudaMemcpyAsync(ex->d_ytab.p, ytab.data(), sizeof(uint2) * ytab.size(), cudaMemcpyHostToDevice, ex->stream));
     }
     SFE_CUDA(cudaStreamSynchronize(ex->stream));  // the std::vectors above die at return
-    SFE_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
     ex->w = w;
     ex->h = h;
     return SFE_OK;
@@ -918,6 +919,15 @@ static int enqueue_extract(sfe_extractor *ex, const uint8_t *in_a, const uint8_t
         fast_cells_kernel<<<dim3((unsigned)ex->cells.size(), count), 256, 0, st>>>(S, ex->d_cells.p, ex->prm.ini_th_fast,
                                                                                    ex->prm.min_th_fast);
         prof_mark(ex, 2);
+        {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
+            static std::mutex mu;
+            static size_t granted[64] = {};
+            std::lock_guard<std::mutex> lock(mu);
+            if (ex->octree_smem > granted[ex->device & 63]) {
+                SFE_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
+                granted[ex->device & 63] = ex->octree_smem;
+            }
+        }
         octree_kernel<<<dim3(nl, count), 256, ex->octree_smem, st>>>(S, ex->max_cand, ex->max_nodes);
         prof_mark(ex, 3);
         blur_kernel<<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p);

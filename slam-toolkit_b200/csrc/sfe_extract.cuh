@@ -9,7 +9,7 @@ constexpr int kEdge = 19;          // EDGE_THRESHOLD, reference src/orb_extracto
 constexpr int kBorder = kEdge - 3; // minBorderX/Y of the FAST window, :771-772
 constexpr int kHalfPatch = 15;     // HALF_PATCH_SIZE, :73
 constexpr int kMaxSub = 66;        // largest FAST cell sub-image side (wCell + 6 < 60 + 6)
-constexpr int kMaxCandCap = 16384; // slot index must fit 14 bits in the quadtree kernel
+constexpr int kMaxCandCap = 8192;  // per level; the quadtree kernel keeps 14 B per candidate in shared memory
 constexpr int kBlurTileW = 128, kBlurTileH = 32;
 
 // One pyramid level's geometry for the current image size (host-built, mirrored on device).
