@@ -14,41 +14,48 @@ namespace sfe {
 // ---------------------------------------------------------------------------------------------
 // pyramid: cv::resize(INTER_LINEAR) fixed-point model, level l from level l-1 (:1120)
 // ---------------------------------------------------------------------------------------------
+// 4 output pixels per thread (one 32-bit store); the coefficient tables are padded to a multiple of 4.
 __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, int l, const uint2 *__restrict__ xtab,
                                                          const uint2 *__restrict__ ytab) {
     const LevelPlan &L = S.lv[l];
-    const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 4 + threadIdx.y, img = blockIdx.z;
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
     if (x >= L.w || y >= L.h) return;
     int sp;
     const uint8_t *src = level_pixels(S, l - 1, img, sp);
     const int sw = S.lv[l - 1].w;
-    const uint2 xt = __ldg(&xtab[L.xtab_off + x]), yt = __ldg(&ytab[L.ytab_off + y]);
-    const int sx = xt.x, sx1 = min(sx + 1, sw - 1);
-    const int w0 = xt.y & 0xFFFF, w1 = xt.y >> 16;
+    const uint2 yt = __ldg(&ytab[L.ytab_off + y]);
     const int y0 = yt.x & 0xFFFF, y1 = yt.x >> 16;
     const int b0 = yt.y & 0xFFFF, b1 = yt.y >> 16;
     const uint8_t *r0 = src + (size_t)y0 * sp, *r1 = src + (size_t)y1 * sp;
-    const int t0 = r0[sx] * w0 + r0[sx1] * w1;
-    const int t1 = r1[sx] * w0 + r1[sx1] * w1;
-    const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+    const uint4 *xt4 = (const uint4 *)(xtab + L.xtab_off + x);  // xtab_off and x are multiples of 4
+    const uint4 ta = __ldg(xt4), tb = __ldg(xt4 + 1);
+    const uint32_t sxs[4] = {ta.x, ta.z, tb.x, tb.z}, ws[4] = {ta.y, ta.w, tb.y, tb.w};
+    uint32_t packed = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int sx = sxs[k], sx1 = min(sx + 1, sw - 1);
+        const int w0 = ws[k] & 0xFFFF, w1 = ws[k] >> 16;
+        const int t0 = __ldg(r0 + sx) * w0 + __ldg(r0 + sx1) * w1;
+        const int t1 = __ldg(r1 + sx) * w0 + __ldg(r1 + sx1) * w1;
+        const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
+        packed |= (uint32_t)min(max(v, 0), 255) << (8 * k);
+    }
     uint8_t *dst = S.pyr + (size_t)img * S.pyr_stride + L.plane_off;
-    dst[(size_t)y * L.pitch + x] = (uint8_t)min(max(v, 0), 255);
+    *(uint32_t *)(dst + (size_t)y * L.pitch + x) = packed;  // pitch is a multiple of 16: pad bytes absorb the tail
 }
 
 // ---------------------------------------------------------------------------------------------
 // FAST-9-16, one CTA per reference cv::FAST call (one 30-px grid cell, :789-816)
+//   stage 0  compass pre-test on every tested pixel (5 shared-memory bytes, ~20 integer ops):
+//            any 9-arc of the 16-pixel circle contains >= 2 of the 4 compass pixels, so a corner
+//            needs >= 2 compass pixels brighter than v+t or >= 2 darker than v-t; survivors are
+//            compacted with warp-aggregated atomics so later stages run with full warps
+//   stage 1  exact score best(p) on the survivors (3-input min/max, VIMNMX3); corner iff best > t
+//   stage 2  cell-local non-max suppression (strict > over 8 neighbours, outside the cell = 0)
+//   retry the whole cell with minThFAST only if nothing survived (:811-816)
 // ---------------------------------------------------------------------------------------------
 constexpr int kTilePitch = 72;   // >= kMaxSub, multiple of 4
 constexpr int kScorePitch = 64;  // >= kMaxSub - 6 + 2
-
-__device__ __forceinline__ bool has_arc9(uint32_t m) {
-    m |= m << 16;
-    uint32_t r = m & (m >> 1);
-    r &= r >> 2;
-    r &= r >> 4;
-    r &= m >> 8;
-    return (r & 0xFFFFu) != 0;
-}
 
 // d[k] = I(p) - I(p + o_k) on the 16-pixel Bresenham circle, k clockwise from (0, +3)
 __device__ __forceinline__ void circle_diffs(const uint8_t *c, int d[16]) {
@@ -72,36 +79,46 @@ __device__ __forceinline__ void circle_diffs(const uint8_t *c, int d[16]) {
 }
 
 // best(p) = max over the 16 arcs of 9 consecutive k of max(min d_k, min -d_k)   (cv::FAST score + 1)
+// 9 = 3 + 3 + 3: arc minima from 3-input minima of 3-input minima.
 __device__ __forceinline__ int fast_best(const int d[16]) {
-    int lo2[16], hi2[16], lo4[16], hi4[16];
+    int lo3[16], hi3[16];
 #pragma unroll
     for (int s = 0; s < 16; s++) {
-        lo2[s] = min(d[s], d[(s + 1) & 15]);
-        hi2[s] = max(d[s], d[(s + 1) & 15]);
-    }
-#pragma unroll
-    for (int s = 0; s < 16; s++) {
-        lo4[s] = min(lo2[s], lo2[(s + 2) & 15]);
-        hi4[s] = max(hi2[s], hi2[(s + 2) & 15]);
+        lo3[s] = __vimin3_s32(d[s], d[(s + 1) & 15], d[(s + 2) & 15]);
+        hi3[s] = __vimax3_s32(d[s], d[(s + 1) & 15], d[(s + 2) & 15]);
     }
     int a = -256, b = 256;
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-        const int lo9 = min(min(lo4[s], lo4[(s + 4) & 15]), d[(s + 8) & 15]);
-        const int hi9 = max(max(hi4[s], hi4[(s + 4) & 15]), d[(s + 8) & 15]);
-        a = max(a, lo9);
-        b = min(b, hi9);
+    for (int s = 0; s < 16; s += 2) {
+        const int l0 = __vimin3_s32(lo3[s], lo3[(s + 3) & 15], lo3[(s + 6) & 15]);
+        const int l1 = __vimin3_s32(lo3[s + 1], lo3[(s + 4) & 15], lo3[(s + 7) & 15]);
+        const int h0 = __vimax3_s32(hi3[s], hi3[(s + 3) & 15], hi3[(s + 6) & 15]);
+        const int h1 = __vimax3_s32(hi3[s + 1], hi3[(s + 4) & 15], hi3[(s + 7) & 15]);
+        a = __vimax3_s32(a, l0, l1);
+        b = __vimin3_s32(b, h0, h1);
     }
     return max(a, -b);
 }
 
+// append `item` to list[] for the lanes with pred set: one shared atomic per warp
+__device__ __forceinline__ void warp_append(bool pred, uint16_t item, uint16_t *list, int *counter) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) list[base + __popc(m & ((1u << lane) - 1))] = item;
+}
+
 __global__ void __launch_bounds__(256) fast_cells_kernel(ImgSet S, const CellPlan *__restrict__ cells,
                                                          int ini_th, int min_th) {
-    __shared__ uint8_t tile[kMaxSub * kTilePitch];
-    __shared__ uint8_t score[(kMaxSub - 4) * kScorePitch];
-    __shared__ uint16_t det[(kMaxSub - 6) * (kMaxSub - 6)];
+    __shared__ __align__(16) uint8_t tile[kMaxSub * kTilePitch];
+    __shared__ __align__(16) uint8_t score[(kMaxSub - 4) * kScorePitch];
+    __shared__ uint16_t pre[(kMaxSub - 6) * (kMaxSub - 6)];  // y << 6 | x of pixels passing stage 0
+    __shared__ uint16_t det[(kMaxSub - 6) * (kMaxSub - 6)];  // corners
     __shared__ uint16_t surv[(kMaxSub - 6) * (kMaxSub - 6) / 2 + 64];
-    __shared__ int n_det, n_surv, out_base;
+    __shared__ int n_pre, n_det, n_surv, out_base;
 
     const CellPlan C = cells[blockIdx.x];
     const int img = blockIdx.y, tid = threadIdx.x;
@@ -110,48 +127,68 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(ImgSet S, const CellPla
     const uint8_t *src = level_pixels(S, C.level, img, pitch);
     src += (size_t)C.ini_y * pitch + C.ini_x;
     const int sw = C.sub_w, sh = C.sub_h;
-    for (int i = tid; i < sw * sh; i += 256) {
-        const int r = i / sw, c = i - r * sw;
-        tile[r * kTilePitch + c] = __ldg(src + (size_t)r * pitch + c);
+    for (int r = tid >> 5; r < sh; r += 8) {
+        const uint8_t *row = src + (size_t)r * pitch;
+        for (int c = tid & 31; c < sw; c += 32) tile[r * kTilePitch + c] = __ldg(row + c);
     }
     const int tw = sw - 6, th = sh - 6;  // tested pixels: 3-px margin inside the sub-image
+    const int npx = tw * th;
+    const int step_y = 256 / tw, step_x = 256 - step_y * tw;  // (y, x) advance for a stride of 256 pixels
     int t = ini_th;
     for (int attempt = 0; attempt < 2; attempt++) {
-        for (int i = tid; i < (th + 2) * kScorePitch; i += 256) score[i] = 0;
-        if (tid == 0) { n_det = 0; n_surv = 0; }
+        for (int i = tid; i < (th + 2) * (kScorePitch / 4); i += 256) ((uint32_t *)score)[i] = 0;
+        if (tid == 0) { n_pre = 0; n_det = 0; n_surv = 0; }
         __syncthreads();
-        // phase A: segment test at threshold t on every tested pixel, branch-free
-        for (int i = tid; i < tw * th; i += 256) {
-            const int y = i / tw, x = i - y * tw;
-            int d[16];
-            circle_diffs(&tile[(y + 3) * kTilePitch + x + 3], d);
-            uint32_t dark = 0, bright = 0;
-#pragma unroll
-            for (int k = 0; k < 16; k++) {
-                dark |= (uint32_t)(d[k] > t) << k;
-                bright |= (uint32_t)(d[k] < -t) << k;
+        // stage 0: compass pre-test
+        {
+            int y = tid / tw, x = tid - y * tw;
+            for (int i0 = 0; i0 < npx; i0 += 256) {  // whole warps iterate together (ballot inside)
+                bool pass = false;
+                if (i0 + tid < npx) {
+                    const uint8_t *c = &tile[(y + 3) * kTilePitch + x + 3];
+                    const int v = c[0], hi = v + t, lo = v - t;
+                    const int p0 = c[3 * kTilePitch], p4 = c[3], p8 = c[-3 * kTilePitch], p12 = c[-3];
+                    const int nb = (p0 > hi) + (p4 > hi) + (p8 > hi) + (p12 > hi);
+                    const int nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
+                    pass = nb >= 2 || nd >= 2;
+                }
+                warp_append(pass, (uint16_t)(y << 6 | x), pre, &n_pre);
+                y += step_y;
+                x += step_x;
+                if (x >= tw) { x -= tw; y++; }
             }
-            if (has_arc9(dark) || has_arc9(bright)) det[atomicAdd(&n_det, 1)] = (uint16_t)i;
         }
         __syncthreads();
-        // phase B: exact score for the (few) corners, all lanes busy
+        // stage 1: exact score; corner at threshold t iff best > t
+        const int np = n_pre;
+        for (int e0 = 0; e0 < np; e0 += 256) {
+            bool corner = false;
+            uint16_t yx = 0;
+            if (e0 + tid < np) {
+                yx = pre[e0 + tid];
+                const int y = yx >> 6, x = yx & 63;
+                int d[16];
+                circle_diffs(&tile[(y + 3) * kTilePitch + x + 3], d);
+                const int best = fast_best(d);
+                corner = best > t;
+                if (corner) score[(y + 1) * kScorePitch + x + 1] = (uint8_t)best;
+            }
+            warp_append(corner, yx, det, &n_det);
+        }
+        __syncthreads();
+        // stage 2: non-max suppression inside this cell only
         const int nd = n_det;
-        for (int e = tid; e < nd; e += 256) {
-            const int i = det[e], y = i / tw, x = i - y * tw;
-            int d[16];
-            circle_diffs(&tile[(y + 3) * kTilePitch + x + 3], d);
-            score[(y + 1) * kScorePitch + x + 1] = (uint8_t)fast_best(d);
-        }
-        __syncthreads();
-        // non-max suppression inside this cell only: strict > over 8 neighbours, outside = 0
-        for (int e = tid; e < nd; e += 256) {
-            const int i = det[e], y = i / tw, x = i - y * tw;
-            const uint8_t *sc = &score[(y + 1) * kScorePitch + x + 1];
-            const int s = sc[0];
-            const bool keep = s > sc[-1] && s > sc[1] && s > sc[-kScorePitch - 1] && s > sc[-kScorePitch] &&
-                              s > sc[-kScorePitch + 1] && s > sc[kScorePitch - 1] && s > sc[kScorePitch] &&
-                              s > sc[kScorePitch + 1];
-            if (keep) surv[atomicAdd(&n_surv, 1)] = (uint16_t)i;
+        for (int e0 = 0; e0 < nd; e0 += 256) {
+            bool keep = false;
+            uint16_t yx = 0;
+            if (e0 + tid < nd) {
+                yx = det[e0 + tid];
+                const uint8_t *sc = &score[((yx >> 6) + 1) * kScorePitch + (yx & 63) + 1];
+                const int s = sc[0];
+                keep = s > sc[-1] && s > sc[1] && s > sc[-kScorePitch - 1] && s > sc[-kScorePitch] &&
+                       s > sc[-kScorePitch + 1] && s > sc[kScorePitch - 1] && s > sc[kScorePitch] && s > sc[kScorePitch + 1];
+            }
+            warp_append(keep, yx, surv, &n_surv);
         }
         __syncthreads();
         if (n_surv > 0 || min_th >= t) break;  // :811-816: retry with minThFAST only when nothing survived
@@ -165,7 +202,7 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(ImgSet S, const CellPla
     __syncthreads();
     uint32_t *out = S.cand + (size_t)img * S.cand_stride + L.cand_off;
     for (int e = tid; e < ns; e += 256) {
-        const int i = surv[e], y = i / tw, x = i - y * tw;
+        const int yx = surv[e], y = yx >> 6, x = yx & 63;
         const int slot = out_base + e;
         if (slot >= L.cand_cap) {
             atomicOr(&S.flags[img], kFlagCandOverflow);
@@ -509,37 +546,63 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return min(max(i, 0), n - 1);  // only reached by halo pixels of outputs outside the image
 }
 
+// Tile = 128 x 32 outputs.  Load (128+6) x (32+6) pixels with the reflected halo, horizontal pass with
+// 4 outputs per thread from three aligned 32-bit shared loads, vertical pass with 2 columns x 4 rows per
+// thread from packed u16x2 words.  Q8 kernel [18 34 48 56 48 34 18]; sums are exact integers, the only
+// rounding is the final (v + 2^15) >> 16, exactly cv::GaussianBlur's fixed-point path.
 __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__restrict__ tiles) {
-    constexpr int IW = kBlurTileW + 6, IH = kBlurTileH + 6, IP = kBlurTileW + 8;
-    __shared__ uint8_t in[IH * IP];
-    __shared__ uint16_t hb[IH * kBlurTileW];
+    constexpr int IW = kBlurTileW + 6, IH = kBlurTileH + 6, IP = kBlurTileW + 8;  // IP % 4 == 0
+    __shared__ __align__(16) uint8_t in[IH * IP];
+    __shared__ __align__(16) uint16_t hb[IH * kBlurTileW];
     const TilePlan t = tiles[blockIdx.x];
     const int img = blockIdx.y, tid = threadIdx.x, l = t.level;
     if (S.kp_count[img * S.nlevels + l] == 0) return;  // the reference blurs only levels with keypoints
     const LevelPlan &L = S.lv[l];
     int pitch;
     const uint8_t *src = level_pixels(S, l, img, pitch);
-    for (int i = tid; i < IH * IW; i += 256) {
-        const int r = i / IW, c = i - r * IW;
-        const int gy = reflect101(t.y0 + r - 3, L.h), gx = reflect101(t.x0 + c - 3, L.w);
-        in[r * IP + c] = __ldg(src + (size_t)gy * pitch + gx);
+    for (int r = tid >> 5; r < IH; r += 8) {
+        const uint8_t *row = src + (size_t)reflect101(t.y0 + r - 3, L.h) * pitch;
+        for (int c = tid & 31; c < IW; c += 32) in[r * IP + c] = __ldg(row + reflect101(t.x0 + c - 3, L.w));
     }
     __syncthreads();
-    for (int i = tid; i < IH * kBlurTileW; i += 256) {
-        const int r = i / kBlurTileW, c = i - r * kBlurTileW;
-        const uint8_t *p = &in[r * IP + c];
-        hb[i] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    // horizontal: item = (row r, column group g of 4 outputs); 38 * 32 items
+    for (int it = tid; it < IH * (kBlurTileW / 4); it += 256) {
+        const int r = it >> 5, c = (it & 31) * 4;
+        const uint32_t *w = (const uint32_t *)&in[r * IP + c];
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        int p[10];
+        p[0] = w0 & 0xFF; p[1] = (w0 >> 8) & 0xFF; p[2] = (w0 >> 16) & 0xFF; p[3] = w0 >> 24;
+        p[4] = w1 & 0xFF; p[5] = (w1 >> 8) & 0xFF; p[6] = (w1 >> 16) & 0xFF; p[7] = w1 >> 24;
+        p[8] = w2 & 0xFF; p[9] = (w2 >> 8) & 0xFF;
+        uint32_t h[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            h[k] = 18 * (p[k] + p[k + 6]) + 34 * (p[k + 1] + p[k + 5]) + 48 * (p[k + 2] + p[k + 4]) + 56 * p[k + 3];
+        *(uint2 *)&hb[r * kBlurTileW + c] = make_uint2(h[0] | h[1] << 16, h[2] | h[3] << 16);
     }
     __syncthreads();
+    // vertical: item = (4 output rows, column pair); 8 * 64 items
     uint8_t *dst = S.blur + (size_t)img * S.blur_stride + L.blur_off;
-    for (int i = tid; i < kBlurTileH * kBlurTileW; i += 256) {
-        const int r = i / kBlurTileW, c = i - r * kBlurTileW;
-        const int gx = t.x0 + c, gy = t.y0 + r;
-        if (gx >= L.w || gy >= L.h) continue;
-        const uint16_t *p = &hb[r * kBlurTileW + c];
-        const uint32_t v = 18u * (p[0] + p[6 * kBlurTileW]) + 34u * (p[kBlurTileW] + p[5 * kBlurTileW]) +
-                           48u * (p[2 * kBlurTileW] + p[4 * kBlurTileW]) + 56u * p[3 * kBlurTileW];
-        dst[(size_t)gy * L.blur_pitch + gx] = (uint8_t)((v + 32768u) >> 16);
+    for (int it = tid; it < (kBlurTileH / 4) * (kBlurTileW / 2); it += 256) {
+        const int r = (it >> 6) * 4, c = (it & 63) * 2;
+        const int gx = t.x0 + c;
+        if (gx >= L.w) continue;
+        uint32_t lo[10], hi[10];
+#pragma unroll
+        for (int k = 0; k < 10; k++) {
+            const uint32_t w = *(const uint32_t *)&hb[(r + k) * kBlurTileW + c];
+            lo[k] = w & 0xFFFF;
+            hi[k] = w >> 16;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int gy = t.y0 + r + k;
+            if (gy >= L.h) break;
+            const uint32_t a = 18u * (lo[k] + lo[k + 6]) + 34u * (lo[k + 1] + lo[k + 5]) + 48u * (lo[k + 2] + lo[k + 4]) + 56u * lo[k + 3];
+            const uint32_t b = 18u * (hi[k] + hi[k + 6]) + 34u * (hi[k + 1] + hi[k + 5]) + 48u * (hi[k + 2] + hi[k + 4]) + 56u * hi[k + 3];
+            const uint16_t o = (uint16_t)(((a + 32768u) >> 16) | (((b + 32768u) >> 16) << 8));
+            *(uint16_t *)(dst + (size_t)gy * L.blur_pitch + gx) = o;  // pitch and gx even: aligned; pad absorbs an odd tail
+        }
     }
 }
 
@@ -607,7 +670,7 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
     if (lane < 31) {
         const int u = lane - kHalfPatch, au = abs(u);
         const uint8_t *c = lvl + (size_t)y * pitch + x + u;
-#pragma unroll 1
+#pragma unroll
         for (int dv = -kHalfPatch; dv <= kHalfPatch; dv++) {
             if (au <= c_umax[abs(dv)]) {
                 const int val = __ldg(c + dv * pitch);
@@ -827,6 +890,7 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
         // resize coefficient tables producing level l from level l-1
         if (l > 0) {
             const int sw = ex->lv[l - 1].w, sh = ex->lv[l - 1].h;
+            while (xtab.size() % 4) xtab.push_back(xtab.back());  // 16-byte aligned uint4 loads, 4 px per thread
             L.xtab_off = (int)xtab.size();
             L.ytab_off = (int)ytab.size();
             const double scale_x = 1.0 / ((double)L.w / sw), scale_y = 1.0 / ((double)L.h / sh);
@@ -839,6 +903,7 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                 const int w0 = cv_round_f((1.f - fx) * 2048), w1 = cv_round_f(fx * 2048);
                 xtab.push_back(make_uint2((unsigned)sx, (unsigned)w0 | (unsigned)w1 << 16));
             }
+            while (xtab.size() % 4) xtab.push_back(xtab.back());
             for (int dy = 0; dy < L.h; dy++) {
                 float fy = (float)((dy + 0.5) * scale_y - 0.5);
                 int sy = (int)floorf(fy);
@@ -910,8 +975,8 @@ static int enqueue_extract(sfe_extractor *ex, const uint8_t *in_a, const uint8_t
     SFE_CUDA(cudaMemsetAsync(ex->d_counts.p, 0, sizeof(int) * (size_t)ex->max_images * (2 * nl + 1), st));
     prof_mark(ex, 0);
     for (int l = 1; l < nl; l++) {
-        dim3 grid(div_up(ex->lv[l].w, 64), div_up(ex->lv[l].h, 4), count);
-        pyr_resize_kernel<<<grid, dim3(64, 4), 0, st>>>(S, l, ex->d_xtab.p, ex->d_ytab.p);
+        dim3 grid(div_up(ex->lv[l].w, 128), div_up(ex->lv[l].h, 8), count);
+        pyr_resize_kernel<<<grid, dim3(32, 8), 0, st>>>(S, l, ex->d_xtab.p, ex->d_ytab.p);
         ex->launches++;
     }
     prof_mark(ex, 1);

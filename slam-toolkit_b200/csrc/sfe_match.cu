@@ -27,62 +27,83 @@ __device__ __forceinline__ void load_desc(const uint8_t *p, uint32_t d[8]) {
 // passing candidate inside buckets b-1..b+1, so the candidate set is every right keypoint passing
 // the dy / dx filters (:103-110).
 // ---------------------------------------------------------------------------------------------
+constexpr int kStereoChunk = 2048;  // right keypoints staged in shared memory at a time
+constexpr int kStereoPerWarp = 4;   // left keypoints per warp; 32 per CTA
+
+// One CTA = 32 left keypoints of one frame: the right keypoints' (x, y) are staged once per CTA in
+// shared memory (SoA float2) and every warp filters them for its 4 left keypoints; descriptors are
+// only fetched for the few candidates that pass the dy / dx filters.
 __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_keypoint *__restrict__ kl,
                                                            const uint8_t *__restrict__ dl, const int32_t *__restrict__ nl,
                                                            const sfe_keypoint *__restrict__ kr,
                                                            const uint8_t *__restrict__ dr, const int32_t *__restrict__ nr,
                                                            double y_thr, double max_dx, double ratio,
                                                            int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist) {
-    const int f = blockIdx.y, lane = threadIdx.x & 31, i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (i >= cap) return;
+    __shared__ float2 rxy[kStereoChunk];
+    const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_l = min(nl[f], cap), n_r = min(nr[f], cap);
     const size_t base = (size_t)f * cap;
-    if (i >= n_l) {
-        if (lane == 0) {
-            out_idx[base + i] = -1;
-            if (out_dist) out_dist[base + i] = -1;
-        }
-        return;
-    }
-    const float lx = kl[base + i].x, ly = kl[base + i].y;
-    uint32_t a[8];
-    load_desc(dl + (base + i) * 32, a);
-    uint32_t k0 = kNoKey, k1 = kNoKey;
-    for (int j = lane; j < n_r; j += 32) {
-        const sfe_keypoint *r = &kr[base + j];
-        const float dx = __fsub_rn(lx, r->x), dy = __fsub_rn(ly, r->y);  // float subtraction, then widened
-        if (fabs((double)dy) > y_thr) continue;
-        if ((double)dx < 0.) continue;
-        if ((double)dx > max_dx) continue;
-        uint32_t b[8];
-        load_desc(dr + (base + j) * 32, b);
-        top2_insert(k0, k1, (uint32_t)hamming8(a, b) << 16 | (uint32_t)j);
-    }
+    const int i0 = blockIdx.x * (8 * kStereoPerWarp) + warp * kStereoPerWarp;
+    float lx[kStereoPerWarp], ly[kStereoPerWarp];
+    uint32_t a[kStereoPerWarp][8], k0[kStereoPerWarp], k1[kStereoPerWarp];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
-        k1 = min(min(k1, o1), max(k0, o0));
-        k0 = min(k0, o0);
+    for (int k = 0; k < kStereoPerWarp; k++) {
+        k0[k] = k1[k] = kNoKey;
+        const int i = min(i0 + k, max(n_l - 1, 0));
+        lx[k] = n_l > 0 ? kl[base + i].x : 0.f;
+        ly[k] = n_l > 0 ? kl[base + i].y : 0.f;
+        if (n_l > 0) load_desc(dl + (base + i) * 32, a[k]);
     }
-    if (lane == 0) {
-        int idx = -1, dist = -1;
-        if (k0 != kNoKey) {
-            const double d0 = (double)(k0 >> 16), d1 = k1 == kNoKey ? 999999999. : (double)(k1 >> 16);
-            if (d0 < d1 * ratio) {  // :125-128
-                idx = (int)(k0 & 0xFFFF);
-                dist = (int)(k0 >> 16);
+    for (int c0 = 0; c0 < n_r; c0 += kStereoChunk) {
+        const int cn = min(kStereoChunk, n_r - c0);
+        __syncthreads();
+        for (int j = tid; j < cn; j += 256) rxy[j] = make_float2(kr[base + c0 + j].x, kr[base + c0 + j].y);
+        __syncthreads();
+        if (i0 >= n_l) continue;
+        for (int j = lane; j < cn; j += 32) {
+            const float2 r = rxy[j];
+#pragma unroll
+            for (int k = 0; k < kStereoPerWarp; k++) {
+                const float dx = __fsub_rn(lx[k], r.x), dy = __fsub_rn(ly[k], r.y);  // float subtraction, then widened
+                if (fabs((double)dy) > y_thr) continue;
+                if ((double)dx < 0.) continue;
+                if ((double)dx > max_dx) continue;
+                uint32_t b[8];
+                load_desc(dr + (base + c0 + j) * 32, b);
+                top2_insert(k0[k], k1[k], (uint32_t)hamming8(a[k], b) << 16 | (uint32_t)(c0 + j));
             }
         }
-        out_idx[base + i] = idx;
-        if (out_dist) out_dist[base + i] = dist;
+    }
+#pragma unroll
+    for (int k = 0; k < kStereoPerWarp; k++) {
+        uint32_t q0 = k0[k], q1 = k1[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t o0 = __shfl_xor_sync(0xffffffffu, q0, o), o1 = __shfl_xor_sync(0xffffffffu, q1, o);
+            q1 = min(min(q1, o1), max(q0, o0));
+            q0 = min(q0, o0);
+        }
+        const int i = i0 + k;
+        if (lane == 0 && i < cap) {
+            int idx = -1, dist = -1;
+            if (i < n_l && q0 != kNoKey) {
+                const double d0 = (double)(q0 >> 16), d1 = q1 == kNoKey ? 999999999. : (double)(q1 >> 16);
+                if (d0 < d1 * ratio) {  // :125-128
+                    idx = (int)(q0 & 0xFFFF);
+                    dist = (int)(q0 >> 16);
+                }
+            }
+            out_idx[base + i] = idx;
+            if (out_dist) out_dist[base + i] = dist;
+        }
     }
 }
 
 void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoint *kl, const uint8_t *dl, const int32_t *nl,
                          const sfe_keypoint *kr, const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
                          double ratio, int32_t *out_idx, int32_t *out_dist) {
-    stereo_match_kernel<<<dim3(div_up(cap, 8), frames), 256, 0, st>>>(cap, kl, dl, nl, kr, dr, nr, y_thr, max_dx, ratio,
-                                                                      out_idx, out_dist);
+    stereo_match_kernel<<<dim3(div_up(cap, 8 * kStereoPerWarp), frames), 256, 0, st>>>(cap, kl, dl, nl, kr, dr, nr, y_thr,
+                                                                                       max_dx, ratio, out_idx, out_dist);
 }
 
 // ---------------------------------------------------------------------------------------------
