@@ -40,64 +40,76 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, int l, const 
         const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
         packed |= (uint32_t)min(max(v, 0), 255) << (8 * k);
     }
-    uint8_t *dst = S.pyr + (size_t)img * S.pyr_stride + L.plane_off;
+    uint8_t *dst = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + L.plane_off;
     *(uint32_t *)(dst + (size_t)y * L.pitch + x) = packed;  // pitch is a multiple of 16: pad bytes absorb the tail
 }
 
 // ---------------------------------------------------------------------------------------------
 // FAST-9-16, one CTA per reference cv::FAST call (one 30-px grid cell, :789-816)
-//   stage 0  compass pre-test on every tested pixel (5 shared-memory bytes, ~20 integer ops):
-//            any 9-arc of the 16-pixel circle contains >= 2 of the 4 compass pixels, so a corner
-//            needs >= 2 compass pixels brighter than v+t or >= 2 darker than v-t; survivors are
-//            compacted with warp-aggregated atomics so later stages run with full warps
-//   stage 1  exact score best(p) on the survivors (3-input min/max, VIMNMX3); corner iff best > t
+//   load     the cell's sub-image into shared memory as aligned 32-bit words (two global words +
+//            funnel shift per word: cell origins are not word aligned)
+//   stage 0  compass pre-test, 4 pixels per thread in 16x2 SIMD lanes: any 9-arc of the 16-pixel
+//            circle contains >= 2 of the 4 compass pixels, so a corner needs >= 2 compass pixels
+//            brighter than v+t or >= 2 darker than v-t; survivors are compacted (warp scan + one
+//            shared atomic per warp) so later stages run with full warps
+//   stage 1  exact score best(p) on the survivors, two pixels per thread in 16x2 lanes
+//            (VIMNMX3.S16x2); corner iff best > t
 //   stage 2  cell-local non-max suppression (strict > over 8 neighbours, outside the cell = 0)
 //   retry the whole cell with minThFAST only if nothing survived (:811-816)
 // ---------------------------------------------------------------------------------------------
-constexpr int kTilePitch = 72;   // >= kMaxSub, multiple of 4
+constexpr int kTilePitch = 72;   // bytes; shared column = sub-image column + 1, so tested x = 0 sits at column 4
+constexpr int kTileWords = kTilePitch / 4;
 constexpr int kScorePitch = 64;  // >= kMaxSub - 6 + 2
 
-// d[k] = I(p) - I(p + o_k) on the 16-pixel Bresenham circle, k clockwise from (0, +3)
-__device__ __forceinline__ void circle_diffs(const uint8_t *c, int d[16]) {
-    const int v = c[0];
-    d[0] = v - c[3 * kTilePitch + 0];
-    d[1] = v - c[3 * kTilePitch + 1];
-    d[2] = v - c[2 * kTilePitch + 2];
-    d[3] = v - c[1 * kTilePitch + 3];
-    d[4] = v - c[3];
-    d[5] = v - c[-1 * kTilePitch + 3];
-    d[6] = v - c[-2 * kTilePitch + 2];
-    d[7] = v - c[-3 * kTilePitch + 1];
-    d[8] = v - c[-3 * kTilePitch + 0];
-    d[9] = v - c[-3 * kTilePitch - 1];
-    d[10] = v - c[-2 * kTilePitch - 2];
-    d[11] = v - c[-1 * kTilePitch - 3];
-    d[12] = v - c[-3];
-    d[13] = v - c[1 * kTilePitch - 3];
-    d[14] = v - c[2 * kTilePitch - 2];
-    d[15] = v - c[3 * kTilePitch - 1];
+// the 32-bit little-endian word at byte address p, any alignment (reads the two aligned words around it)
+__device__ __forceinline__ uint32_t ldg_word_at(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8);
 }
 
-// best(p) = max over the 16 arcs of 9 consecutive k of max(min d_k, min -d_k)   (cv::FAST score + 1)
-// 9 = 3 + 3 + 3: arc minima from 3-input minima of 3-input minima.
-__device__ __forceinline__ int fast_best(const int d[16]) {
-    int lo3[16], hi3[16];
+// Compass pre-test of two pixels held in the 16-bit lanes of c (centre) and p0..p3 (compass pixels).
+// k = 0x7FFF - t in both lanes.  Lane bit 15 of (p + k - c) is set iff p > c + t, of (c + k - p) iff
+// p < c - t; no lane ever carries or borrows (all values stay inside [0x7E02, 0x80FE]).
+__device__ __forceinline__ uint32_t compass2(uint32_t c, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t k) {
+    const uint32_t A = k - c, B = k + c;
+    const uint32_t b0 = p0 + A, b1 = p1 + A, b2 = p2 + A, b3 = p3 + A;
+    const uint32_t d0 = B - p0, d1 = B - p1, d2 = B - p2, d3 = B - p3;
+    const uint32_t rb = ((b0 & b1) | (b0 & b2) | (b1 & b2)) | (b3 & (b0 | b1 | b2));  // >= 2 of 4 brighter
+    const uint32_t rd = ((d0 & d1) | (d0 & d2) | (d1 & d2)) | (d3 & (d0 | d1 | d2));  // >= 2 of 4 darker
+    return (rb | rd) & 0x80008000u;
+}
+
+// best(p) = max over the 16 arcs of 9 consecutive circle pixels of max(min (v - p_k), min (p_k - v))
+//         = max(v - min_arcs max_k p_k, max_arcs min_k p_k - v)                    (cv::FAST score + 1)
+// for the two pixels at c0 / c1 at once: circle pixels packed as 16x2 lanes, 9 = 3 + 3 + 3 so every arc
+// extremum is a 3-input extremum of 3-input extrema (VIMNMX3.S16x2).
+__device__ __forceinline__ void fast_best_x2(const uint8_t *c0, const uint8_t *c1, int &best0, int &best1) {
+    constexpr int off[16] = {3 * kTilePitch,      3 * kTilePitch + 1,  2 * kTilePitch + 2,  kTilePitch + 3,
+                             3,                   -kTilePitch + 3,     -2 * kTilePitch + 2, -3 * kTilePitch + 1,
+                             -3 * kTilePitch,     -3 * kTilePitch - 1, -2 * kTilePitch - 2, -kTilePitch - 3,
+                             -3,                  kTilePitch - 3,      2 * kTilePitch - 2,  3 * kTilePitch - 1};
+    uint32_t p[16], lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) p[k] = __byte_perm(c0[off[k]], c1[off[k]], 0x5410);
 #pragma unroll
     for (int s = 0; s < 16; s++) {
-        lo3[s] = __vimin3_s32(d[s], d[(s + 1) & 15], d[(s + 2) & 15]);
-        hi3[s] = __vimax3_s32(d[s], d[(s + 1) & 15], d[(s + 2) & 15]);
+        lo3[s] = __vimin3_s16x2(p[s], p[(s + 1) & 15], p[(s + 2) & 15]);
+        hi3[s] = __vimax3_s16x2(p[s], p[(s + 1) & 15], p[(s + 2) & 15]);
     }
-    int a = -256, b = 256;
+    uint32_t max_of_min = 0u, min_of_max = 0x7fff7fffu;
 #pragma unroll
     for (int s = 0; s < 16; s += 2) {
-        const int l0 = __vimin3_s32(lo3[s], lo3[(s + 3) & 15], lo3[(s + 6) & 15]);
-        const int l1 = __vimin3_s32(lo3[s + 1], lo3[(s + 4) & 15], lo3[(s + 7) & 15]);
-        const int h0 = __vimax3_s32(hi3[s], hi3[(s + 3) & 15], hi3[(s + 6) & 15]);
-        const int h1 = __vimax3_s32(hi3[s + 1], hi3[(s + 4) & 15], hi3[(s + 7) & 15]);
-        a = __vimax3_s32(a, l0, l1);
-        b = __vimin3_s32(b, h0, h1);
+        const uint32_t l0 = __vimin3_s16x2(lo3[s], lo3[(s + 3) & 15], lo3[(s + 6) & 15]);
+        const uint32_t l1 = __vimin3_s16x2(lo3[s + 1], lo3[(s + 4) & 15], lo3[(s + 7) & 15]);
+        const uint32_t h0 = __vimax3_s16x2(hi3[s], hi3[(s + 3) & 15], hi3[(s + 6) & 15]);
+        const uint32_t h1 = __vimax3_s16x2(hi3[s + 1], hi3[(s + 4) & 15], hi3[(s + 7) & 15]);
+        max_of_min = __vimax3_s16x2(max_of_min, l0, l1);
+        min_of_max = __vimin3_s16x2(min_of_max, h0, h1);
     }
-    return max(a, -b);
+    const int v0 = c0[0], v1 = c1[0];
+    best0 = max(v0 - (int)(min_of_max & 0xFFFF), (int)(max_of_min & 0xFFFF) - v0);
+    best1 = max(v1 - (int)(min_of_max >> 16), (int)(max_of_min >> 16) - v1);
 }
 
 // append `item` to list[] for the lanes with pred set: one shared atomic per warp
@@ -111,74 +123,118 @@ __device__ __forceinline__ void warp_append(bool pred, uint16_t item, uint16_t *
     if (pred) list[base + __popc(m & ((1u << lane) - 1))] = item;
 }
 
-__global__ void __launch_bounds__(256) fast_cells_kernel(ImgSet S, const CellPlan *__restrict__ cells,
-                                                         int ini_th, int min_th) {
-    __shared__ __align__(16) uint8_t tile[kMaxSub * kTilePitch];
-    __shared__ __align__(16) uint8_t score[(kMaxSub - 4) * kScorePitch];
-    __shared__ uint16_t pre[(kMaxSub - 6) * (kMaxSub - 6)];  // y << 6 | x of pixels passing stage 0
-    __shared__ uint16_t det[(kMaxSub - 6) * (kMaxSub - 6)];  // corners
-    __shared__ uint16_t surv[(kMaxSub - 6) * (kMaxSub - 6) / 2 + 64];
+// Cell geometry travels in the kernel parameters (constant bank): a CTA derives its cv::FAST call from
+// blockIdx.x without touching global memory before the pixel loads.
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, FastPlan P) {
+    extern __shared__ __align__(16) uint32_t fast_smem[];
+    uint32_t *tile32 = fast_smem;                                    // tile_rows x kTileWords
+    uint8_t *score = (uint8_t *)(tile32 + P.tile_rows * kTileWords);  // score_rows x kScorePitch
+    uint16_t *pre = (uint16_t *)(score + P.score_rows * kScorePitch); // y << 6 | x of pixels passing stage 0
+    uint16_t *det = pre + P.list_cap;                                 // corners
+    uint16_t *surv = pre;                                             // NMS survivors (pre is dead by then)
     __shared__ int n_pre, n_det, n_surv, out_base;
+    const uint8_t *tile = (const uint8_t *)tile32;
+    constexpr int T = kFastThreads;
 
-    const CellPlan C = cells[blockIdx.x];
-    const int img = blockIdx.y, tid = threadIdx.x;
-    const LevelPlan &L = S.lv[C.level];
+    // which reference cell is this (:789-806)
+    int level = 0;
+#pragma unroll 1
+    for (int k = 1; k < P.nlevels; k++)
+        if ((int)blockIdx.x >= P.lv[k].first_cell) level = k;
+    const FastLevel &F = P.lv[level];
+    const int cell = blockIdx.x - F.first_cell;
+    const int ci = (int)__umulhi((unsigned)cell, F.inv_cols), cj = cell - ci * F.n_cols;
+    const int ini_x = kBorder + cj * F.w_cell, ini_y = kBorder + ci * F.h_cell;
+    const int sw = min(ini_x + F.w_cell + 6, F.max_bx) - ini_x, sh = min(ini_y + F.h_cell + 6, F.max_by) - ini_y;
+
+    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const uint8_t *src;
     int pitch;
-    const uint8_t *src = level_pixels(S, C.level, img, pitch);
-    src += (size_t)C.ini_y * pitch + C.ini_x;
-    const int sw = C.sub_w, sh = C.sub_h;
-    for (int r = tid >> 5; r < sh; r += 8) {
-        const uint8_t *row = src + (size_t)r * pitch;
-        for (int c = tid & 31; c < sw; c += 32) tile[r * kTilePitch + c] = __ldg(row + c);
+    if (level == 0) {
+        pitch = S.in_pitch;
+        src = img < S.split ? S.in_a + (size_t)img * S.in_stride : S.in_b + (size_t)(img - S.split) * S.in_stride;
+    } else {
+        pitch = F.pitch;
+        src = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + F.plane_off;
+    }
+    src += (size_t)ini_y * pitch + ini_x - 1;  // shared column 0 = sub-image column -1 (ini_x >= 16)
+    {   // shared columns [0, 4 * nw) cover sub-image columns [-1, sw + 6]; the row has >= 16 px beyond the cell
+        const int nw = min((sw + 8) >> 2, kTileWords), inv = 65536 / nw + 1;
+        for (int it = tid; it < sh * nw; it += T) {
+            const int r = (it * inv) >> 16, j = it - r * nw;
+            tile32[r * kTileWords + j] = ldg_word_at(src + (size_t)r * pitch + 4 * j);
+        }
     }
     const int tw = sw - 6, th = sh - 6;  // tested pixels: 3-px margin inside the sub-image
-    const int npx = tw * th;
-    const int step_y = 256 / tw, step_x = 256 - step_y * tw;  // (y, x) advance for a stride of 256 pixels
-    int t = ini_th;
+    const int nq = (tw + 3) >> 2, inv_q = 65536 / nq + 1, nitems = th * nq;
+    int t = P.ini_th;
     for (int attempt = 0; attempt < 2; attempt++) {
-        for (int i = tid; i < (th + 2) * (kScorePitch / 4); i += 256) ((uint32_t *)score)[i] = 0;
+        for (int i = tid; i < (th + 2) * (kScorePitch / 4); i += T) ((uint32_t *)score)[i] = 0;
         if (tid == 0) { n_pre = 0; n_det = 0; n_surv = 0; }
         __syncthreads();
-        // stage 0: compass pre-test
-        {
-            int y = tid / tw, x = tid - y * tw;
-            for (int i0 = 0; i0 < npx; i0 += 256) {  // whole warps iterate together (ballot inside)
-                bool pass = false;
-                if (i0 + tid < npx) {
-                    const uint8_t *c = &tile[(y + 3) * kTilePitch + x + 3];
-                    const int v = c[0], hi = v + t, lo = v - t;
-                    const int p0 = c[3 * kTilePitch], p4 = c[3], p8 = c[-3 * kTilePitch], p12 = c[-3];
-                    const int nb = (p0 > hi) + (p4 > hi) + (p8 > hi) + (p12 > hi);
-                    const int nd = (p0 < lo) + (p4 < lo) + (p8 < lo) + (p12 < lo);
-                    pass = nb >= 2 || nd >= 2;
-                }
-                warp_append(pass, (uint16_t)(y << 6 | x), pre, &n_pre);
-                y += step_y;
-                x += step_x;
-                if (x >= tw) { x -= tw; y++; }
+        // stage 0: compass pre-test, one aligned word of 4 centre pixels per thread
+        const uint32_t k2 = (uint32_t)(0x7FFF - t) * 0x10001u;
+        for (int i0 = 0; i0 < nitems; i0 += T) {  // whole warps iterate together (ballot inside)
+            const int it = i0 + tid;
+            uint32_t mask = 0;
+            int y = 0, x = 0;
+            if (it < nitems) {
+                y = (it * inv_q) >> 16;
+                const int j = it - y * nq;
+                x = 4 * j;
+                const uint32_t *row = tile32 + (y + 3) * kTileWords + j;
+                const uint32_t c = row[1], up = row[1 - 3 * kTileWords], dn = row[1 + 3 * kTileWords];
+                const uint32_t lf = __byte_perm(row[0], c, 0x4321);  // pixels x-3 .. x
+                const uint32_t rt = __byte_perm(c, row[2], 0x6543);  // pixels x+3 .. x+6
+                const uint32_t m_lo = compass2(__byte_perm(c, 0, 0x4140), __byte_perm(up, 0, 0x4140), __byte_perm(dn, 0, 0x4140),
+                                               __byte_perm(lf, 0, 0x4140), __byte_perm(rt, 0, 0x4140), k2);
+                const uint32_t m_hi = compass2(__byte_perm(c, 0, 0x4342), __byte_perm(up, 0, 0x4342), __byte_perm(dn, 0, 0x4342),
+                                               __byte_perm(lf, 0, 0x4342), __byte_perm(rt, 0, 0x4342), k2);
+                mask = ((m_lo >> 15) & 1) | ((m_lo >> 30) & 2) | ((m_hi >> 13) & 4) | ((m_hi >> 28) & 8);
+                mask &= (1u << min(4, tw - x)) - 1;
+            }
+            if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+            const int cnt = __popc(mask);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&n_pre, inc);
+            int pos = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
+            while (mask) {
+                const int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                pre[pos++] = (uint16_t)(y << 6 | (x + b));
             }
         }
         __syncthreads();
-        // stage 1: exact score; corner at threshold t iff best > t
-        const int np = n_pre;
-        for (int e0 = 0; e0 < np; e0 += 256) {
-            bool corner = false;
-            uint16_t yx = 0;
-            if (e0 + tid < np) {
-                yx = pre[e0 + tid];
-                const int y = yx >> 6, x = yx & 63;
-                int d[16];
-                circle_diffs(&tile[(y + 3) * kTilePitch + x + 3], d);
-                const int best = fast_best(d);
-                corner = best > t;
-                if (corner) score[(y + 1) * kScorePitch + x + 1] = (uint8_t)best;
+        // stage 1: exact score, two survivors per thread; corner at threshold t iff best > t
+        const int np = n_pre, npairs = (np + 1) >> 1;
+        for (int e0 = 0; e0 < npairs; e0 += T) {
+            bool corner0 = false, corner1 = false;
+            uint16_t yx0 = 0, yx1 = 0;
+            const int e = e0 + tid;
+            if (e < npairs) {
+                yx0 = pre[2 * e];
+                yx1 = pre[min(2 * e + 1, np - 1)];
+                int best0, best1;
+                fast_best_x2(&tile[((yx0 >> 6) + 3) * kTilePitch + (yx0 & 63) + 4],
+                             &tile[((yx1 >> 6) + 3) * kTilePitch + (yx1 & 63) + 4], best0, best1);
+                corner0 = best0 > t;
+                corner1 = best1 > t && 2 * e + 1 < np;
+                if (corner0) score[((yx0 >> 6) + 1) * kScorePitch + (yx0 & 63) + 1] = (uint8_t)best0;
+                if (corner1) score[((yx1 >> 6) + 1) * kScorePitch + (yx1 & 63) + 1] = (uint8_t)best1;
             }
-            warp_append(corner, yx, det, &n_det);
+            warp_append(corner0, yx0, det, &n_det);
+            warp_append(corner1, yx1, det, &n_det);
         }
         __syncthreads();
         // stage 2: non-max suppression inside this cell only
         const int nd = n_det;
-        for (int e0 = 0; e0 < nd; e0 += 256) {
+        for (int e0 = 0; e0 < nd; e0 += T) {
             bool keep = false;
             uint16_t yx = 0;
             if (e0 + tid < nd) {
@@ -191,25 +247,25 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(ImgSet S, const CellPla
             warp_append(keep, yx, surv, &n_surv);
         }
         __syncthreads();
-        if (n_surv > 0 || min_th >= t) break;  // :811-816: retry with minThFAST only when nothing survived
-        t = min_th;
+        if (n_surv > 0 || P.min_th >= t) break;  // :811-816: retry with minThFAST only when nothing survived
+        t = P.min_th;
         __syncthreads();
     }
     const int ns = n_surv;
     if (ns == 0) return;
-    int *cnt = &S.cand_count[img * S.nlevels + C.level];
-    if (tid == 0) out_base = atomicAdd(cnt, ns);
+    const int slot = slot_of(S, img);
+    if (tid == 0) out_base = atomicAdd(&S.cand_count[slot * S.nlevels + level], ns);
     __syncthreads();
-    uint32_t *out = S.cand + (size_t)img * S.cand_stride + L.cand_off;
-    for (int e = tid; e < ns; e += 256) {
+    uint32_t *out = S.cand + (size_t)slot * S.cand_stride + F.cand_off;
+    for (int e = tid; e < ns; e += T) {
         const int yx = surv[e], y = yx >> 6, x = yx & 63;
         const int slot = out_base + e;
-        if (slot >= L.cand_cap) {
-            atomicOr(&S.flags[img], kFlagCandOverflow);
+        if (slot >= F.cand_cap) {
+            atomicOr(&S.flags[slot], kFlagCandOverflow);
             continue;
         }
         const uint32_t resp = score[(y + 1) * kScorePitch + x + 1] - 1;  // cv::FAST response = best - 1
-        const uint32_t xw = C.ini_x - kBorder + x + 3, yw = C.ini_y - kBorder + y + 3;
+        const uint32_t xw = ini_x - kBorder + x + 3, yw = ini_y - kBorder + y + 3;
         out[slot] = resp << 24 | yw << 12 | xw;
     }
 }
@@ -419,7 +475,7 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
 __global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int max_cand, int max_nodes) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int sh_misc[4];
-    const int l = blockIdx.x, img = blockIdx.y, tid = threadIdx.x, T = blockDim.x;
+    const int l = blockIdx.x, img = slot_of(S, blockIdx.y), tid = threadIdx.x, T = blockDim.x;  // internal buffers only
     const LevelPlan &L = S.lv[l];
     int *kp_count = &S.kp_count[img * S.nlevels + l];
     const int n = min(S.cand_count[img * S.nlevels + l], L.cand_cap);
@@ -546,63 +602,76 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return min(max(i, 0), n - 1);  // only reached by halo pixels of outputs outside the image
 }
 
-// Tile = 128 x 32 outputs.  Load (128+6) x (32+6) pixels with the reflected halo, horizontal pass with
-// 4 outputs per thread from three aligned 32-bit shared loads, vertical pass with 2 columns x 4 rows per
-// thread from packed u16x2 words.  Q8 kernel [18 34 48 56 48 34 18]; sums are exact integers, the only
-// rounding is the final (v + 2^15) >> 16, exactly cv::GaussianBlur's fixed-point path.
+// Tile = 128 x 32 outputs, Q8 kernel [18 34 48 56 48 34 18]; sums are exact integers, the only rounding is
+// the final (v + 2^15) >> 16, exactly cv::GaussianBlur's fixed-point path.
+//   load        (32+6) rows x 34 aligned words (x0-4 .. x0+131) into shared memory, one 32-bit store per 4 px;
+//               words that touch the image border are assembled byte by byte with BORDER_REFLECT_101
+//   horizontal  4 outputs per thread from three shared words, two outputs per register in 16x2 lanes
+//               (a lane never exceeds 255 * 256 = 65280)
+//   vertical    one column pair x 8 rows per thread: 14 packed words unpacked once, 7 multiply-adds per
+//               output with the rounding constant folded in, result bytes picked with one PRMT
 __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__restrict__ tiles) {
-    constexpr int IW = kBlurTileW + 6, IH = kBlurTileH + 6, IP = kBlurTileW + 8;  // IP % 4 == 0
-    __shared__ __align__(16) uint8_t in[IH * IP];
-    __shared__ __align__(16) uint16_t hb[IH * kBlurTileW];
+    constexpr int IH = kBlurTileH + 6, IWW = kBlurTileW / 4 + 2, HW = kBlurTileW / 2;
+    __shared__ __align__(16) uint32_t in32[IH * IWW];
+    __shared__ __align__(16) uint32_t hb[IH * HW];  // horizontal sums, two u16 per word
     const TilePlan t = tiles[blockIdx.x];
-    const int img = blockIdx.y, tid = threadIdx.x, l = t.level;
-    if (S.kp_count[img * S.nlevels + l] == 0) return;  // the reference blurs only levels with keypoints
+    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l = t.level;
+    const int slot = slot_of(S, img);
+    if (S.kp_count[slot * S.nlevels + l] == 0) return;  // the reference blurs only levels with keypoints
     const LevelPlan &L = S.lv[l];
     int pitch;
     const uint8_t *src = level_pixels(S, l, img, pitch);
-    for (int r = tid >> 5; r < IH; r += 8) {
+    const int w = L.w;
+    for (int r = warp; r < IH; r += 8) {
         const uint8_t *row = src + (size_t)reflect101(t.y0 + r - 3, L.h) * pitch;
-        for (int c = tid & 31; c < IW; c += 32) in[r * IP + c] = __ldg(row + reflect101(t.x0 + c - 3, L.w));
+        for (int j = lane; j < IWW; j += 32) {
+            const int x = t.x0 - 4 + 4 * j;
+            uint32_t v;
+            if (x >= 0 && x + 8 <= w) {
+                v = ldg_word_at(row + x);
+            } else {
+                v = __ldg(row + reflect101(x, w)) | (uint32_t)__ldg(row + reflect101(x + 1, w)) << 8 |
+                    (uint32_t)__ldg(row + reflect101(x + 2, w)) << 16 | (uint32_t)__ldg(row + reflect101(x + 3, w)) << 24;
+            }
+            in32[r * IWW + j] = v;
+        }
     }
     __syncthreads();
-    // horizontal: item = (row r, column group g of 4 outputs); 38 * 32 items
+    // horizontal: item = (row r, group g of 4 outputs); input bytes b[0..11] = words g..g+2, tap i of output k = b[k+i+1]
     for (int it = tid; it < IH * (kBlurTileW / 4); it += 256) {
-        const int r = it >> 5, c = (it & 31) * 4;
-        const uint32_t *w = (const uint32_t *)&in[r * IP + c];
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-        int p[10];
-        p[0] = w0 & 0xFF; p[1] = (w0 >> 8) & 0xFF; p[2] = (w0 >> 16) & 0xFF; p[3] = w0 >> 24;
-        p[4] = w1 & 0xFF; p[5] = (w1 >> 8) & 0xFF; p[6] = (w1 >> 16) & 0xFF; p[7] = w1 >> 24;
-        p[8] = w2 & 0xFF; p[9] = (w2 >> 8) & 0xFF;
-        uint32_t h[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            h[k] = 18 * (p[k] + p[k + 6]) + 34 * (p[k + 1] + p[k + 5]) + 48 * (p[k + 2] + p[k + 4]) + 56 * p[k + 3];
-        *(uint2 *)&hb[r * kBlurTileW + c] = make_uint2(h[0] | h[1] << 16, h[2] | h[3] << 16);
+        const int r = it >> 5, g = it & 31;
+        const uint32_t *wp = &in32[r * IWW + g];
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const uint32_t e0 = __byte_perm(w0, 0, 0x4140), e1 = __byte_perm(w0, 0, 0x4342), e2 = __byte_perm(w1, 0, 0x4140),
+                       e3 = __byte_perm(w1, 0, 0x4342), e4 = __byte_perm(w2, 0, 0x4140), e5 = __byte_perm(w2, 0, 0x4342);
+        const uint32_t o0 = __byte_perm(e0, e1, 0x5432), o1 = __byte_perm(e1, e2, 0x5432), o2 = __byte_perm(e2, e3, 0x5432),
+                       o3 = __byte_perm(e3, e4, 0x5432), o4 = __byte_perm(e4, e5, 0x5432);
+        // pairs (b[i+1], b[i+2]) for i = 0..8: o0 e1 o1 e2 o2 e3 o3 e4 o4
+        const uint32_t h01 = 18u * (o0 + o3) + 34u * (e1 + e3) + 48u * (o1 + o2) + 56u * e2;
+        const uint32_t h23 = 18u * (o1 + o4) + 34u * (e2 + e4) + 48u * (o2 + o3) + 56u * e3;
+        *(uint2 *)&hb[r * HW + 2 * g] = make_uint2(h01, h23);
     }
     __syncthreads();
-    // vertical: item = (4 output rows, column pair); 8 * 64 items
-    uint8_t *dst = S.blur + (size_t)img * S.blur_stride + L.blur_off;
-    for (int it = tid; it < (kBlurTileH / 4) * (kBlurTileW / 2); it += 256) {
-        const int r = (it >> 6) * 4, c = (it & 63) * 2;
-        const int gx = t.x0 + c;
-        if (gx >= L.w) continue;
-        uint32_t lo[10], hi[10];
+    // vertical: thread = (column pair cw, strip of 8 output rows)
+    uint8_t *dst = S.blur + (size_t)slot * S.blur_stride + L.blur_off;
+    const int cw = tid & 63, r0 = (tid >> 6) * 8;
+    const int gx = t.x0 + 2 * cw;
+    if (gx >= w) return;
+    uint32_t lo[14], hi[14];
 #pragma unroll
-        for (int k = 0; k < 10; k++) {
-            const uint32_t w = *(const uint32_t *)&hb[(r + k) * kBlurTileW + c];
-            lo[k] = w & 0xFFFF;
-            hi[k] = w >> 16;
-        }
+    for (int k = 0; k < 14; k++) {
+        const uint32_t v = hb[(r0 + k) * HW + cw];
+        lo[k] = v & 0xFFFF;
+        hi[k] = v >> 16;
+    }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int gy = t.y0 + r + k;
-            if (gy >= L.h) break;
-            const uint32_t a = 18u * (lo[k] + lo[k + 6]) + 34u * (lo[k + 1] + lo[k + 5]) + 48u * (lo[k + 2] + lo[k + 4]) + 56u * lo[k + 3];
-            const uint32_t b = 18u * (hi[k] + hi[k + 6]) + 34u * (hi[k + 1] + hi[k + 5]) + 48u * (hi[k + 2] + hi[k + 4]) + 56u * hi[k + 3];
-            const uint16_t o = (uint16_t)(((a + 32768u) >> 16) | (((b + 32768u) >> 16) << 8));
-            *(uint16_t *)(dst + (size_t)gy * L.blur_pitch + gx) = o;  // pitch and gx even: aligned; pad absorbs an odd tail
-        }
+    for (int k = 0; k < 8; k++) {
+        const int gy = t.y0 + r0 + k;
+        if (gy >= L.h) break;
+        const uint32_t a = 18u * (lo[k] + lo[k + 6]) + 34u * (lo[k + 1] + lo[k + 5]) + 48u * (lo[k + 2] + lo[k + 4]) + (56u * lo[k + 3] + 32768u);
+        const uint32_t b = 18u * (hi[k] + hi[k + 6]) + 34u * (hi[k + 1] + hi[k + 5]) + 48u * (hi[k + 2] + hi[k + 4]) + (56u * hi[k + 3] + 32768u);
+        // (v + 2^15) >> 16 <= 255 is byte 2 of each sum
+        *(uint16_t *)(dst + (size_t)gy * L.blur_pitch + gx) = (uint16_t)__byte_perm(a, b, 0x0062);  // pitch, gx even; pad absorbs an odd tail
     }
 }
 
@@ -639,7 +708,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 
 __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O) {
     __shared__ char2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane`
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y, slot = slot_of(S, img);
     for (int i = tid; i < 512; i += 256) {
         const int byte = i >> 4, s = i & 15;
         pat[s * 32 + byte] = make_char2(g_pattern[2 * i], g_pattern[2 * i + 1]);
@@ -649,7 +718,7 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
     const int g = blockIdx.x * 8 + warp;
     int l = -1, local = 0, total = 0;
     for (int k = 0; k < S.nlevels; k++) {
-        const int c = min(S.kp_count[img * S.nlevels + k], S.lv[k].kp_cap);
+        const int c = min(S.kp_count[slot * S.nlevels + k], S.lv[k].kp_cap);
         if (l < 0 && g < total + c) { l = k; local = g - total; }
         total += c;
     }
@@ -657,11 +726,11 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
     const int oi = set_a ? img : img - S.split;
     if (g == 0 && lane == 0) {
         (set_a ? O.n_a : O.n_b)[oi] = min(total, O.cap);
-        if (total > O.cap) atomicOr(&S.flags[img], kFlagOutOverflow);
+        if (total > O.cap) atomicOr(&S.flags[slot], kFlagOutOverflow);
     }
     if (l < 0 || g >= O.cap) return;
     const LevelPlan &L = S.lv[l];
-    const uint32_t v = S.kpst[(size_t)img * S.kpst_stride + L.kp_off + local];
+    const uint32_t v = S.kpst[(size_t)slot * S.kpst_stride + L.kp_off + local];
     const int x = (v & 0xFFF) + kBorder, y = ((v >> 12) & 0xFFF) + kBorder;
     int pitch;
     const uint8_t *lvl = level_pixels(S, l, img, pitch);
@@ -695,7 +764,7 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
     }
     a = __shfl_sync(0xffffffffu, a, 0);
     b = __shfl_sync(0xffffffffu, b, 0);
-    const uint8_t *bl = S.blur + (size_t)img * S.blur_stride + L.blur_off + (size_t)y * L.blur_pitch + x;
+    const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off + (size_t)y * L.blur_pitch + x;
     uint32_t byte = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -748,7 +817,8 @@ struct sfe_extractor {
     // geometry-dependent plan
     int w = 0, h = 0;
     LevelPlan lv[kMaxLevels];
-    std::vector<CellPlan> cells;
+    FastPlan fast{};
+    size_t fast_smem = 0;
     std::vector<TilePlan> tiles;
     size_t pyr_stride = 0, blur_stride = 0;
     int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0, out_cap = 0;
@@ -757,7 +827,6 @@ struct sfe_extractor {
     DevBuf<uint32_t> d_cand, d_kpst;
     DevBuf<int> d_counts;  // cand_count | kp_count | flags
     DevBuf<LevelPlan> d_lv;
-    DevBuf<CellPlan> d_cells;
     DevBuf<TilePlan> d_tiles;
     DevBuf<uint2> d_xtab, d_ytab;
     DevBuf<sfe_keypoint> d_kps;
@@ -812,7 +881,8 @@ static void build_tables(sfe_extractor *ex) {
 static int build_plan(sfe_extractor *ex, int w, int h) {
     const int nl = ex->prm.nlevels;
     std::vector<uint2> xtab, ytab;
-    ex->cells.clear();
+    memset(&ex->fast, 0, sizeof(ex->fast));
+    int max_sw = 7, max_sh = 7;
     ex->tiles.clear();
     size_t pyr_off = 0, blur_off = 0;
     int cand_off = 0, kp_off = 0, max_cand = 0, max_nodes = 8;
@@ -843,29 +913,43 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
         L.n_cols = L.win_w > 0 ? (int)(width / 30.f) : 0;
         L.n_rows = L.win_h > 0 ? (int)(height / 30.f) : 0;
         L.w_cell = L.h_cell = 1;
-        int tested = 0;
+        int tested = 0, n_level_cells = 0;
         if (L.n_cols >= 1 && L.n_rows >= 1) {  // else: reference divides by zero; canonical = no keypoints (T5)
             L.w_cell = (int)ceilf(width / L.n_cols);
             L.h_cell = (int)ceilf(height / L.n_rows);
-            for (int i = 0; i < L.n_rows; i++) {
-                const int ini_y = kBorder + i * L.h_cell;
-                int max_y = ini_y + L.h_cell + 6;
-                if (ini_y >= max_by - 3) continue;
-                if (max_y > max_by) max_y = max_by;
-                for (int j = 0; j < L.n_cols; j++) {
-                    const int ini_x = kBorder + j * L.w_cell;
-                    int max_x = ini_x + L.w_cell + 6;
-                    if (ini_x >= max_bx - 6) continue;
-                    if (max_x > max_bx) max_x = max_bx;
-                    const int sw = max_x - ini_x, sh = max_y - ini_y;
-                    if (sw < 7 || sh < 7) continue;  // cv::FAST tests nothing on such a sub-image
-                    SFE_REQUIRE(sw <= kMaxSub && sh <= kMaxSub, SFE_ERR_UNSUPPORTED, "FAST cell larger than 66 px");
-                    CellPlan c{(short)l, (short)ini_x, (short)ini_y, (short)sw, (short)sh, 0};
-                    ex->cells.push_back(c);
-                    tested += (sw - 6) * (sh - 6);
+            // rows / columns that pass the skip rules (:794,803) and hold a >= 7 px sub-image (cv::FAST tests
+            // nothing on a smaller one) form a prefix of the nominal grid
+            int rows_eff = 0, cols_eff = 0;
+            for (int i = 0; i < L.n_rows; i++)
+                if (kBorder + i * L.h_cell < max_by - 3 && max_by - (kBorder + i * L.h_cell) >= 7) rows_eff = i + 1;
+            for (int j = 0; j < L.n_cols; j++)
+                if (kBorder + j * L.w_cell < max_bx - 6) cols_eff = j + 1;
+            SFE_REQUIRE(L.w_cell + 6 <= kMaxSub && L.h_cell + 6 <= kMaxSub, SFE_ERR_UNSUPPORTED, "FAST cell larger than 66 px");
+            if (rows_eff > 0 && cols_eff > 0) {
+                FastLevel &F = ex->fast.lv[l];
+                F.n_cols = cols_eff;
+                F.inv_cols = (unsigned)(0x100000000ull / (unsigned)cols_eff + 1);
+                F.w_cell = L.w_cell;
+                F.h_cell = L.h_cell;
+                F.max_bx = max_bx;
+                F.max_by = max_by;
+                F.pitch = L.pitch;
+                F.plane_off = L.plane_off;
+                n_level_cells = rows_eff * cols_eff;
+                SFE_REQUIRE(n_level_cells < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 FAST cells on one level");
+                for (int i = 0; i < rows_eff; i++) {
+                    const int ini_y = kBorder + i * L.h_cell, sh = std::min(ini_y + L.h_cell + 6, max_by) - ini_y;
+                    for (int j = 0; j < cols_eff; j++) {
+                        const int ini_x = kBorder + j * L.w_cell, sw = std::min(ini_x + L.w_cell + 6, max_bx) - ini_x;
+                        tested += (sw - 6) * (sh - 6);
+                        max_sw = std::max(max_sw, sw);
+                        max_sh = std::max(max_sh, sh);
+                    }
                 }
             }
         }
+        ex->fast.lv[l].first_cell = ex->fast.n_cells;
+        ex->fast.n_cells += n_level_cells;
         // quadtree roots
         L.n_ini = 1;
         L.hx = 1.f;
@@ -879,6 +963,8 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
         L.cand_cap = tested > 0 ? std::min(std::max(tested / 12, 1024), kMaxCandCap) : 0;
         L.cand_off = cand_off;
         cand_off += L.cand_cap;
+        ex->fast.lv[l].cand_off = L.cand_off;
+        ex->fast.lv[l].cand_cap = L.cand_cap;
         L.kp_cap = tested > 0 ? std::max(L.quota + 3, 4 * L.n_ini) + 1 : 0;
         L.kp_off = kp_off;
         kp_off += L.kp_cap;
@@ -920,6 +1006,13 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     ex->kpst_stride = std::max(kp_off, 1);
     ex->max_cand = std::max(max_cand, 1);
     ex->max_nodes = max_nodes;
+    ex->fast.nlevels = nl;
+    ex->fast.ini_th = ex->prm.ini_th_fast;
+    ex->fast.min_th = ex->prm.min_th_fast;
+    ex->fast.tile_rows = max_sh;
+    ex->fast.score_rows = max_sh - 4;
+    ex->fast.list_cap = ((max_sw - 6) * (max_sh - 6) + 7) & ~7;
+    ex->fast_smem = (size_t)max_sh * kTilePitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
     ex->octree_smem = (size_t)ex->max_cand * (2 * 4 + 3 * 2) + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
     SFE_REQUIRE(ex->octree_smem <= 227 * 1024, SFE_ERR_UNSUPPORTED, "quadtree working set exceeds shared memory");
     const int n = ex->max_images;
@@ -929,13 +1022,10 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     SFE_CUDA(ex->d_kpst.ensure((size_t)ex->kpst_stride * n));
     SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1)));
     SFE_CUDA(ex->d_lv.ensure(kMaxLevels));
-    SFE_CUDA(ex->d_cells.ensure(std::max<size_t>(ex->cells.size(), 1)));
     SFE_CUDA(ex->d_tiles.ensure(std::max<size_t>(ex->tiles.size(), 1)));
     SFE_CUDA(ex->d_xtab.ensure(std::max<size_t>(xtab.size(), 1)));
     SFE_CUDA(ex->d_ytab.ensure(std::max<size_t>(ytab.size(), 1)));
     SFE_CUDA(cudaMemcpyAsync(ex->d_lv.p, ex->lv, sizeof(LevelPlan) * nl, cudaMemcpyHostToDevice, ex->stream));
-    if (!ex->cells.empty())
-        SFE_CUDA(cudaMemcpyAsync(ex->d_cells.p, ex->cells.data(), sizeof(CellPlan) * ex->cells.size(), cudaMemcpyHostToDevice, ex->stream));
     if (!ex->tiles.empty())
         SFE_CUDA(cudaMemcpyAsync(ex->d_tiles.p, ex->tiles.data(), sizeof(TilePlan) * ex->tiles.size(), cudaMemcpyHostToDevice, ex->stream));
     if (!xtab.empty()) {
@@ -980,9 +1070,8 @@ static int enqueue_extract(sfe_extractor *ex, const uint8_t *in_a, const uint8_t
         ex->launches++;
     }
     prof_mark(ex, 1);
-    if (!ex->cells.empty()) {
-        fast_cells_kernel<<<dim3((unsigned)ex->cells.size(), count), 256, 0, st>>>(S, ex->d_cells.p, ex->prm.ini_th_fast,
-                                                                                   ex->prm.min_th_fast);
+    if (ex->fast.n_cells > 0) {
+        fast_cells_kernel<<<dim3((unsigned)ex->fast.n_cells, count), kFastThreads, ex->fast_smem, st>>>(S, ex->fast);
         prof_mark(ex, 2);
         {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
             static std::mutex mu;
@@ -1098,7 +1187,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     cudaStreamSynchronize(ex->stream);
     ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_desc.release();
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release(); ex->d_lv.release();
-    ex->d_cells.release(); ex->d_tiles.release(); ex->d_xtab.release(); ex->d_ytab.release();
+    ex->d_tiles.release(); ex->d_xtab.release(); ex->d_ytab.release();
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
     for (int i = 0; i <= kNumStages; i++)
         if (ex->prof_ev[i]) cudaEventDestroy(ex->prof_ev[i]);

@@ -29,9 +29,25 @@ struct LevelPlan {
     float size;             // (int)(31 * scale), :837
 };
 
-struct CellPlan {  // one cv::FAST call of the reference, :789-816
-    short level, ini_x, ini_y, sub_w, sub_h, pad;
+// FAST cells (one cv::FAST call of the reference each, :789-816).  The cells of a level that survive the
+// skip rules (:794,803) and hold at least a 7x7 sub-image form a prefix grid of n_rows_eff x n_cols rows /
+// columns, so a cell is identified by its index alone; the table rides in the kernel parameters.
+struct FastLevel {
+    int first_cell;        // index of this level's first cell in the launch grid
+    int n_cols;            // cells per row
+    unsigned inv_cols;     // floor(i / n_cols) == __umulhi(i, inv_cols) for i < 2^16
+    int w_cell, h_cell;    // :786-787
+    int max_bx, max_by;    // maxBorderX/Y, :773-776
+    int pitch, plane_off;  // level pixels (levels >= 1; level 0 is the input image)
+    int cand_off, cand_cap;
 };
+struct FastPlan {
+    FastLevel lv[kMaxLevels];
+    int nlevels, n_cells;
+    int ini_th, min_th;
+    int tile_rows, score_rows, list_cap;  // dynamic shared-memory carve-up, sized for the largest cell
+};
+constexpr int kFastThreads = 128;
 
 struct TilePlan {  // one blur tile
     short level, x0, y0, pad;
@@ -44,6 +60,8 @@ struct ImgSet {
     size_t in_stride;            // bytes between consecutive images of a set
     int in_pitch;                // bytes between rows
     int split;
+    int slot_a, slot_b;          // internal buffer slot of image 0 of set A / set B (a pipelined host call runs
+                                 // the batch as chunks that share the handle's buffers)
     uint8_t *pyr;                // levels 1.. of all images
     size_t pyr_stride;
     uint8_t *blur;               // blurred levels 0.. of all images
@@ -68,6 +86,10 @@ struct OutSet {  // final outputs, set A / set B
     int cap;
 };
 
+__device__ __forceinline__ int slot_of(const ImgSet &S, int img) {
+    return img < S.split ? S.slot_a + img : S.slot_b + (img - S.split);
+}
+
 __device__ __forceinline__ const uint8_t *level_pixels(const ImgSet &S, int l, int img, int &pitch) {
     if (l == 0) {
         pitch = S.in_pitch;
@@ -75,7 +97,7 @@ __device__ __forceinline__ const uint8_t *level_pixels(const ImgSet &S, int l, i
                              : S.in_b + (size_t)(img - S.split) * S.in_stride;
     }
     pitch = S.lv[l].pitch;
-    return S.pyr + (size_t)img * S.pyr_stride + S.lv[l].plane_off;
+    return S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + S.lv[l].plane_off;
 }
 
 // stereo matcher launch (sfe_match.cu), used by sfe_stereo_frames on the extractor's stream

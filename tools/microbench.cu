@@ -22,6 +22,13 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
             if (OP == 3) a[i] = min(a[i] ^ seed, a[(i + 1) & 7]);  // LOP + IMNMX
             if (OP == 4) a[i] = a[i] * seed + a[(i + 1) & 7];      // IMAD
             if (OP == 5) a[i] = __popc(a[i] ^ a[(i + 1) & 7]) + (a[i] << 1); // xor+popc+shift-add: hamming-like mix
+            if (OP == 6) a[i] = __vimin3_s16x2(a[i], a[(i + 1) & 7], seed);   // VIMNMX3.S16x2
+            if (OP == 7) a[i] = __vimax3_s32(a[i], a[(i + 1) & 7], seed);     // VIMNMX3
+            if (OP == 8) a[i] = __byte_perm(a[i], a[(i + 1) & 7], seed);      // PRMT
+            if (OP == 9) {                                                    // IMAD (fma pipe) + LOP3 (alu pipe) interleaved
+                if (i & 1) a[i] = a[i] * seed + a[(i + 1) & 7];
+                else a[i] = (a[i] ^ seed) & a[(i + 1) & 7];
+            }
         }
         acc += a[0];
     }
@@ -69,6 +76,10 @@ int main() {
     run<3>("lop+imnmx", 2, d);
     run<4>("imad", 1, d);
     run<5>("xor+popc+shl-add", 3, d);
+    run<6>("vimnmx3.s16x2", 1, d);
+    run<7>("vimnmx3.s32", 1, d);
+    run<8>("prmt", 1, d);
+    run<9>("imad|lop3 interleaved", 1, d);
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
