@@ -35,17 +35,19 @@ N_DISTINCT = 8           # distinct synthetic frames; batches are rotations of t
 PYR_PIXELS = 1_444_097   # sum of level sizes
 B_IMG = 466_616 + PYR_PIXELS + 2000 * 60          # algorithmic bytes per image extraction
 B_FRAME = 2 * B_IMG + 4 * 2000                     # per stereo frame
+WORKLOAD = "kitti_stereo_frontend: extract L + extract R + StereoMatch, 1241x376, 8 levels, 1.2, 2000 feats"
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=0, help="stereo frames in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples (0 = no sampling)")
     return ap.parse_args()
 
 
@@ -58,36 +60,72 @@ def make_frames(n):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md): NVML every 20 ms,
+    `nvidia-smi --query-gpu` every 200 ms when the NVML binding is unavailable."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, period=0.02):
         super().__init__(daemon=True)
-        self.device, self.rows, self.stop_flag = device, [], False
+        self.device, self.sm, self.reasons, self.sm_max, self.stop_flag, self.source = device, [], set(), None, False, None
+        self.period, self.active = period, False   # samples are kept only while a timed region is running
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml as N
+        N.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = self.device
+        if vis:
+            try:
+                idx = int(vis.split(",")[self.device])
+            except (ValueError, IndexError):
+                pass
+        h = N.nvmlDeviceGetHandleByIndex(idx)
+        self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.source = "nvml"
         while not self.stop_flag:
+            if self.active and self.period > 0:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            time.sleep(self.period if self.period > 0 else 0.05)
+
+    def _smi_loop(self):
+        self.source = "nvidia-smi"
+        while not self.stop_flag:
+            if not self.active or self.period <= 0:
+                time.sleep(0.01)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                if len(r) >= 9:
+                    self.sm.append(float(r[1]))
+                    self.sm_max = float(r[2])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:
                 pass
             time.sleep(0.2)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows[0][2].replace(".", "").isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no clock samples"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": self.source}
 
 
 def cpu_sample(frames, threads):
@@ -102,13 +140,16 @@ def cpu_sample(frames, threads):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement of the reference path, all host threads, rank 0 only."""
+    """--impl reference: the CPU restatement of the reference path (oracle/orb_oracle.c; the reference itself cannot be
+    built here), all host threads, one frame per thread, rank 0 only.  One step = a bounded sample of the workload:
+    its size is chosen from a warm-up measurement so that the K steps take about a minute."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    frames = args.cpu_frames or max(cores * 2, 16)
-    for _ in range(min(args.warmup, 1)):
-        cpu_sample(max(cores, 4), cores)
+    est_fps, _, _, _ = cpu_sample(max(cores, 4), cores)          # also the warm-up (builds + pages in the oracle)
+    for _ in range(max(min(args.warmup, 2) - 1, 0)):
+        est_fps, _, _, _ = cpu_sample(max(cores, 4), cores)
+    frames = args.cpu_frames or int(min(max(60.0 * est_fps / max(args.steps, 1), cores), 4 * cores))
     times = []
     tot_matches = 0
     for _ in range(args.steps):
@@ -120,8 +161,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "orb_extract_match_stereo_frames_per_s", "value": value, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "kitti_stereo_frontend: extract L + extract R + StereoMatch, 1241x376, 8 levels, 1.2, 2000 feats",
-                       "frames_per_step": frames},
+            "config": {"workload": WORKLOAD, "frames_per_step": frames},
             "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{frames} synthetic stereo frames per step, {args.steps} steps, one frame per thread"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -169,23 +209,35 @@ def main():
     def step_resident(i):
         ex.stereo_frames_dev(d_left[i % NB].ptr, d_right[i % NB].ptr, F, W, H, ptrs)
 
+    sampler = ClockSampler(dev, args.clock_period)
+    sampler.start()                      # NVML initialises here, outside the timed regions
     for i in range(Wm):
         step_resident(i)
+    # per-stage CUDA-event times: a few synchronous profiled steps outside the timed region
     ex.set_profiling(True)
+    for i in range(min(K, 10)):
+        step_resident(i)
+    stage_ms, calls = ex.stage_ms()
+    ex.set_profiling(False)
+    # timed region: K batches queued back to back on the extractor's stream (asynchronous _dev calls), one wait
+    ex.set_async(True)
+    for i in range(2):
+        step_resident(i)
+    ex.wait()
     l0 = ex.launches()
-    sampler = ClockSampler(dev)
-    sampler.start()
     ev0, ev1 = api.Event(dev), api.Event(dev)
     barrier()
+    sampler.active = True
     ev0.record(ex)
     for i in range(K):
         step_resident(Wm + i)
     ev1.record(ex)
+    ex.wait()
+    sampler.active = False
     ms = ev0.elapsed_ms(ev1)
     barrier()
     launches = ex.launches() - l0
-    stage_ms, calls = ex.stage_ms()
-    ex.set_profiling(False)
+    ex.set_async(False)
     n_match = int((d_out["stereo_idx"].download((F, cap), np.int32) >= 0).sum())
     n_kps = int(d_out["n_l"].download((F,), np.int32).sum() + d_out["n_r"].download((F,), np.int32).sum())
 
@@ -196,10 +248,12 @@ def main():
     for i in range(Wm):
         ex.stereo_frames(pin_l.array, pin_r.array, out)
     barrier()
+    sampler.active = True
     t0 = time.perf_counter()
     for i in range(K):
         ex.stereo_frames(pin_l.array, pin_r.array, out)
     e2e_s = time.perf_counter() - t0
+    sampler.active = False
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -237,8 +291,7 @@ def main():
     line = {"metric": "orb_extract_match_stereo_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "kitti_stereo_frontend: extract L + extract R + StereoMatch, 1241x376, 8 levels, 1.2, 2000 feats",
-                       "frames_per_step_per_gpu": F, "l2": f"inputs rotate over {NB} resident batches ({NB * per_batch / 1e6:.0f} MB > 126 MB L2)",
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "l2": f"inputs rotate over {NB} resident batches ({NB * per_batch / 1e6:.0f} MB > 126 MB L2)",
                        "sharding": "frames partitioned across GPUs, no collective"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
@@ -251,9 +304,10 @@ def main():
             "keypoints_per_frame": n_kps / F, "matches_per_s": value * n_match / F}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        frames = args.cpu_frames or max(2 * cores, 16)
+        frames = args.cpu_frames or 16 * cores   # ~1.5 s per core: 10-30 s of CPU work in all
+        cpu_sample(cores, cores)                 # warm-up
         fps_all, dt_all, _, _ = cpu_sample(frames, cores)
-        fps_1, dt_1, _, _ = cpu_sample(max(4, min(8, frames)), 1)
+        fps_1, dt_1, _, _ = cpu_sample(8, 1)
         line["cpu_baseline"] = {"value": fps_all, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": f"{frames} synthetic stereo frames, one frame per thread ({dt_all:.1f} s)",
                                 "single_thread_value": fps_1}

@@ -141,6 +141,14 @@ int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint
                           int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
                           int cap);
 
+/* Asynchronous mode for the _dev entry points: with enable != 0 they return as soon as the kernels are
+ * enqueued on the handle's stream, so a caller can queue batch after batch without a host round trip
+ * (consecutive calls reuse the handle's buffers in stream order).  Capacity errors of any queued batch are
+ * kept on the device and reported by the next sfe_extractor_wait(), which also synchronises the stream.
+ * The host entry points are always synchronous. */
+int sfe_extractor_set_async(sfe_extractor *ex, int enable);
+int sfe_extractor_wait(sfe_extractor *ex);
+
 /* stage taps for parity tests (valid for the images of the last call on this handle) */
 int sfe_debug_level(sfe_extractor *ex, int image, int level, uint8_t *out /* lw*lh */);
 int sfe_debug_blur(sfe_extractor *ex, int image, int level, uint8_t *out /* lw*lh */);

@@ -80,6 +80,8 @@ SIGNATURES = {
     "sfe_extract_batch_dev": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sfe_stereo_frames": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
     "sfe_stereo_frames_dev": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
+    "sfe_extractor_set_async": (_i, [_vp, _i]),
+    "sfe_extractor_wait": (_i, [_vp]),
     "sfe_debug_level": (_i, [_vp, _i, _i, _vp]),
     "sfe_debug_blur": (_i, [_vp, _i, _i, _vp]),
     "sfe_debug_candidates": (_i, [_vp, _i, _i, _vp, _i, C.POINTER(_i)]),
@@ -351,6 +353,13 @@ class ORBextractor:
                                            _p(ptrs["desc_r"]), _p(ptrs["n_r"]), _p(ptrs["stereo_idx"]),
                                            _p(ptrs["stereo_dist"]), self.cap))
         self._wh = (w, h)
+
+    def set_async(self, enable=True):
+        """_dev calls return once enqueued; errors surface at wait()."""
+        _check(lib().sfe_extractor_set_async(self.h, int(enable)))
+
+    def wait(self):
+        _check(lib().sfe_extractor_wait(self.h))
 
     def launches(self) -> int:
         n = C.c_int64()

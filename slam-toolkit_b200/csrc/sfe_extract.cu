@@ -806,10 +806,18 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
 using namespace sfe;
 
 enum { kStagePyramid, kStageFast, kStageQuadtree, kStageBlur, kStageDescribe, kStageStereo, kNumStages };
+constexpr int kMaxChunks = 16;  // sub-batches one pipelined host call is cut into
 
 struct sfe_extractor {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                  // compute (and everything, for unpipelined calls)
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of the pipelined host entry points
+    cudaStream_t stream2 = nullptr;                 // second compute stream: odd sub-batches (their kernels fill the
+                                                    // tail waves of the even ones)
+    cudaEvent_t ev_start = nullptr;
+    bool async_dev = false;                         // _dev entry points return after enqueueing (sfe_extractor_wait)
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+    int chunks_override = 0;                        // SFE_PIPELINE_CHUNKS
     sfe_extractor_params prm{};
     float scale[kMaxLevels], inv_scale[kMaxLevels], sigma2[kMaxLevels], inv_sigma2[kMaxLevels];
     int quota[kMaxLevels];
@@ -1038,14 +1046,17 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     return SFE_OK;
 }
 
-// enqueue the whole extraction of `count` images on the handle's stream
-static int enqueue_extract(sfe_extractor *ex, const uint8_t *in_a, const uint8_t *in_b, int split, size_t in_stride,
-                           int in_pitch, int count, const OutSet &O) {
+// The batch-wide view of the handle's buffers: set A = images [0, split) of the call at internal slots
+// [0, split), set B behind them.
+static ImgSet make_imgset(sfe_extractor *ex, const uint8_t *in_a, const uint8_t *in_b, int split, size_t in_stride,
+                          int in_pitch) {
     const int nl = ex->prm.nlevels;
     ImgSet S{};
     S.in_a = in_a;
     S.in_b = in_b;
     S.split = split;
+    S.slot_a = 0;
+    S.slot_b = split;
     S.in_stride = in_stride;
     S.in_pitch = in_pitch;
     S.pyr = ex->d_pyr.p;
@@ -1061,8 +1072,37 @@ static int enqueue_extract(sfe_extractor *ex, const uint8_t *in_a, const uint8_t
     S.cand_count = ex->d_counts.p;
     S.kp_count = ex->d_counts.p + (size_t)ex->max_images * nl;
     S.flags = ex->d_counts.p + (size_t)ex->max_images * nl * 2;
-    cudaStream_t st = ex->stream;
-    SFE_CUDA(cudaMemsetAsync(ex->d_counts.p, 0, sizeof(int) * (size_t)ex->max_images * (2 * nl + 1), st));
+    return S;
+}
+
+// frames [f0, f1) of a batch as a self-contained sub-batch (set A first, then set B if the batch has one)
+static ImgSet chunk_of(const ImgSet &B, int f0, int f1, bool has_b) {
+    ImgSet S = B;
+    S.in_a = B.in_a + (size_t)f0 * B.in_stride;
+    S.in_b = B.in_b + (size_t)f0 * B.in_stride;
+    S.split = f1 - f0;
+    S.slot_a = B.slot_a + f0;
+    S.slot_b = has_b ? B.slot_b + f0 : 0;
+    return S;
+}
+static OutSet chunk_of(const OutSet &O, int f0) {
+    OutSet C = O;
+    C.kps_a += (size_t)f0 * O.cap; C.kps_b += (size_t)f0 * O.cap;
+    C.desc_a += (size_t)f0 * O.cap * 32; C.desc_b += (size_t)f0 * O.cap * 32;
+    C.n_a += f0; C.n_b += f0;
+    return C;
+}
+
+static int reset_counters(sfe_extractor *ex) {
+    // layout: cand_count | kp_count | flags.  An asynchronous handle keeps the error flags until sfe_extractor_wait.
+    const size_t n = (size_t)ex->max_images * (2 * ex->prm.nlevels + (ex->async_dev ? 0 : 1));
+    SFE_CUDA(cudaMemsetAsync(ex->d_counts.p, 0, sizeof(int) * n, ex->stream));
+    return SFE_OK;
+}
+
+// enqueue the extraction of the `count` images of S on the handle's compute stream (counters already reset)
+static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count, const OutSet &O) {
+    const int nl = ex->prm.nlevels;
     prof_mark(ex, 0);
     for (int l = 1; l < nl; l++) {
         dim3 grid(div_up(ex->lv[l].w, 128), div_up(ex->lv[l].h, 8), count);
@@ -1096,15 +1136,13 @@ static int enqueue_extract(sfe_extractor *ex, const uint8_t *in_a, const uint8_t
     ex->prof_has_stereo = false;
     ex->launches++;
     SFE_CUDA(cudaGetLastError());
-    ex->last = S;
-    ex->last_count = count;
     return SFE_OK;
 }
 
-static int check_flags(sfe_extractor *ex, int count) {
+static int check_flags(sfe_extractor *ex, cudaStream_t st, int count) {
     ex->h_flags.resize(count);
-    SFE_CUDA(cudaMemcpyAsync(ex->h_flags.data(), ex->last.flags, sizeof(int) * count, cudaMemcpyDeviceToHost, ex->stream));
-    SFE_CUDA(cudaStreamSynchronize(ex->stream));
+    SFE_CUDA(cudaMemcpyAsync(ex->h_flags.data(), ex->last.flags, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
     if (ex->prof_pending) {
         const int ns = ex->prof_has_stereo ? kNumStages : kNumStages - 1;
         for (int i = 0; i < ns; i++) {
@@ -1122,6 +1160,12 @@ static int check_flags(sfe_extractor *ex, int count) {
     return SFE_OK;
 }
 
+// end of a _dev call: synchronous handles wait and report now; asynchronous ones leave both to sfe_extractor_wait
+static int finish_dev(sfe_extractor *ex, int count) {
+    if (ex->async_dev) return SFE_OK;
+    return check_flags(ex, ex->stream, count);
+}
+
 static int prepare(sfe_extractor *ex, int count, int w, int h, int stride, int cap) {
     SFE_REQUIRE(ex != nullptr, SFE_ERR_BAD_ARG, "null handle");
     SFE_REQUIRE(count >= 1 && count <= ex->max_images, SFE_ERR_BAD_ARG, "count outside [1, max_images]");
@@ -1135,17 +1179,109 @@ static int prepare(sfe_extractor *ex, int count, int w, int h, int stride, int c
 }
 
 // upload `count` host images into the tight staging buffer at slot `first`
-static int upload_images(sfe_extractor *ex, const uint8_t *images, size_t image_stride, int count, int w, int h, int stride,
-                         int first) {
+static int upload_images(sfe_extractor *ex, cudaStream_t st, const uint8_t *images, size_t image_stride, int count, int w,
+                         int h, int stride, int first) {
     uint8_t *dst = ex->d_in.p + (size_t)first * w * h;
     if (stride == w && image_stride == (size_t)w * h) {
-        SFE_CUDA(cudaMemcpyAsync(dst, images, (size_t)count * w * h, cudaMemcpyHostToDevice, ex->stream));
+        SFE_CUDA(cudaMemcpyAsync(dst, images, (size_t)count * w * h, cudaMemcpyHostToDevice, st));
     } else {
         for (int i = 0; i < count; i++)
             SFE_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * w * h, w, images + (size_t)i * image_stride, stride, w, h,
-                                       cudaMemcpyHostToDevice, ex->stream));
+                                       cudaMemcpyHostToDevice, st));
     }
     return SFE_OK;
+}
+
+// How many sub-batches a host call of `units` frames is cut into: the copies of one sub-batch overlap the
+// kernels of its neighbours (H2D, compute and D2H each on their own stream).
+static int pipeline_chunks(const sfe_extractor *ex, int units) {
+    int n = ex->chunks_override > 0 ? ex->chunks_override : (units >= 64 ? 8 : units >= 32 ? 4 : units >= 8 ? 2 : 1);
+    return std::max(1, std::min(std::min(n, units), kMaxChunks));
+}
+
+static const sfe_stereo_params k_default_stereo = {3.0, 100.0, 0.5};  // src/matcher.cpp:68-70
+
+// Host-buffer batch: `frames` images (right == nullptr) or stereo pairs, pinned or pageable host memory in and out.
+// Sub-batch c: upload on s_h2d -> kernels on the compute stream -> results on s_d2h, chained with events.
+static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
+                          int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l, uint8_t *desc_l, int32_t *n_l,
+                          sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx, int32_t *stereo_dist,
+                          int cap) {
+    const bool stereo = right != nullptr;
+    const int images = stereo ? 2 * frames : frames;
+    int rc = prepare(ex, images, w, h, stride, cap);
+    if (rc != SFE_OK) return rc;
+    const size_t F = frames, wh = (size_t)w * h;
+    SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * wh));
+    SFE_CUDA(ex->d_kps.ensure((size_t)ex->max_images * cap));
+    SFE_CUDA(ex->d_desc.ensure((size_t)ex->max_images * cap * 32));
+    SFE_CUDA(ex->d_nout.ensure(ex->max_images));
+    if (stereo) {
+        SFE_CUDA(ex->d_sidx.ensure((size_t)ex->max_images * cap));
+        SFE_CUDA(ex->d_sdist.ensure((size_t)ex->max_images * cap));
+    }
+    sfe_keypoint *kl = ex->d_kps.p, *kr = ex->d_kps.p + F * cap;
+    uint8_t *dl = ex->d_desc.p, *dr = ex->d_desc.p + F * cap * 32;
+    int32_t *nl = ex->d_nout.p, *nr = ex->d_nout.p + F;
+    const ImgSet B = make_imgset(ex, ex->d_in.p, ex->d_in.p + F * wh, frames, wh, w);
+    const OutSet O{kl, stereo ? kr : kl, dl, stereo ? dr : dl, nl, stereo ? nr : nl, cap};
+    if ((rc = reset_counters(ex)) != SFE_OK) return rc;
+    const int nch = pipeline_chunks(ex, frames);
+    const bool piped = nch > 1;
+    cudaStream_t sin = piped ? ex->s_h2d : ex->stream, sout = piped ? ex->s_d2h : ex->stream;
+    const bool prof = ex->profiling;
+    if (piped) {
+        ex->profiling = false;  // per-stage events describe one unpipelined batch
+        SFE_CUDA(cudaEventRecord(ex->ev_start, ex->stream));  // the counter reset precedes every sub-batch
+        SFE_CUDA(cudaStreamWaitEvent(ex->stream2, ex->ev_start, 0));
+    }
+    for (int c = 0; c < nch && rc == SFE_OK; c++) {
+        const int f0 = (int)((long long)frames * c / nch), f1 = (int)((long long)frames * (c + 1) / nch), fc = f1 - f0;
+        cudaStream_t sc = (c & 1) ? ex->stream2 : ex->stream;
+        if ((rc = upload_images(ex, sin, left + (size_t)f0 * image_stride, image_stride, fc, w, h, stride, f0)) != SFE_OK) break;
+        if (stereo && (rc = upload_images(ex, sin, right + (size_t)f0 * image_stride, image_stride, fc, w, h, stride,
+                                          frames + f0)) != SFE_OK)
+            break;
+        if (piped) {
+            SFE_CUDA(cudaEventRecord(ex->ev_in[c], sin));
+            SFE_CUDA(cudaStreamWaitEvent(sc, ex->ev_in[c], 0));
+        }
+        const OutSet Oc = chunk_of(O, f0);
+        if ((rc = enqueue_extract(ex, sc, chunk_of(B, f0, f1, stereo), stereo ? 2 * fc : fc, Oc)) != SFE_OK) break;
+        if (stereo) {
+            launch_stereo_match(sc, fc, cap, Oc.kps_a, Oc.desc_a, Oc.n_a, Oc.kps_b, Oc.desc_b, Oc.n_b, sp->y_threshold, sp->max_dx,
+                                sp->best12_threshold, ex->d_sidx.p + (size_t)f0 * cap, ex->d_sdist.p + (size_t)f0 * cap);
+            if (!piped) prof_mark(ex, 6);
+            ex->prof_has_stereo = true;
+            ex->launches++;
+            SFE_CUDA(cudaGetLastError());
+        }
+        if (piped) {
+            SFE_CUDA(cudaEventRecord(ex->ev_done[c], sc));
+            SFE_CUDA(cudaStreamWaitEvent(sout, ex->ev_done[c], 0));
+        }
+        const size_t o = (size_t)f0 * cap, nk = (size_t)fc * cap;
+        SFE_CUDA(cudaMemcpyAsync(kps_l + o, kl + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
+        SFE_CUDA(cudaMemcpyAsync(desc_l + o * 32, dl + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
+        if (stereo) {
+            SFE_CUDA(cudaMemcpyAsync(kps_r + o, kr + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
+            SFE_CUDA(cudaMemcpyAsync(desc_r + o * 32, dr + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
+            SFE_CUDA(cudaMemcpyAsync(stereo_idx + o, ex->d_sidx.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
+            if (stereo_dist)
+                SFE_CUDA(cudaMemcpyAsync(stereo_dist + o, ex->d_sdist.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
+        }
+    }
+    ex->profiling = prof;
+    if (rc != SFE_OK) {
+        cudaStreamSynchronize(sin); cudaStreamSynchronize(ex->stream); cudaStreamSynchronize(ex->stream2); cudaStreamSynchronize(sout);
+        return rc;
+    }
+    SFE_CUDA(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
+    if (stereo) SFE_CUDA(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
+    ex->last = B;
+    if (!stereo) ex->last.split = images;  // one set: every image reads in_a
+    ex->last_count = images;
+    return check_flags(ex, sout, images);  // sout is behind every sub-batch
 }
 
 extern "C" {
@@ -1173,6 +1309,19 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
         delete ex;
         return SFE_ERR_CUDA;
     }
+    bool ok = cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ex->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ex->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kMaxChunks && ok; i++)
+        ok = cudaEventCreateWithFlags(&ex->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ex->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        set_error("stream/event creation: %s", cudaGetErrorString(cudaGetLastError()));
+        sfe_extractor_destroy(ex);
+        return SFE_ERR_CUDA;
+    }
+    if (const char *env = getenv("SFE_PIPELINE_CHUNKS")) ex->chunks_override = atoi(env);
     build_tables(ex);
     int cap = p->nfeatures;
     for (int l = 0; l < p->nlevels; l++) cap += 4;
@@ -1191,6 +1340,14 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
     for (int i = 0; i <= kNumStages; i++)
         if (ex->prof_ev[i]) cudaEventDestroy(ex->prof_ev[i]);
+    for (int i = 0; i < kMaxChunks; i++) {
+        if (ex->ev_in[i]) cudaEventDestroy(ex->ev_in[i]);
+        if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
+    }
+    if (ex->ev_start) cudaEventDestroy(ex->ev_start);
+    if (ex->stream2) cudaStreamDestroy(ex->stream2);
+    if (ex->s_h2d) cudaStreamDestroy(ex->s_h2d);
+    if (ex->s_d2h) cudaStreamDestroy(ex->s_d2h);
     cudaStreamDestroy(ex->stream);
     delete ex;
     return SFE_OK;
@@ -1234,10 +1391,13 @@ int sfe_extract_batch_dev(sfe_extractor *ex, const uint8_t *images_dev, size_t i
     DeviceGuard g(ex->device);
     int rc = prepare(ex, count, w, h, stride, cap);
     if (rc != SFE_OK) return rc;
-    OutSet O{kps_dev, kps_dev, desc_dev, desc_dev, n_out_dev, n_out_dev, cap};
-    rc = enqueue_extract(ex, images_dev, images_dev, count, image_stride, stride, count, O);
-    if (rc != SFE_OK) return rc;
-    return check_flags(ex, count);
+    const OutSet O{kps_dev, kps_dev, desc_dev, desc_dev, n_out_dev, n_out_dev, cap};
+    const ImgSet S = make_imgset(ex, images_dev, images_dev, count, image_stride, stride);
+    if ((rc = reset_counters(ex)) != SFE_OK) return rc;
+    if ((rc = enqueue_extract(ex, ex->stream, S, count, O)) != SFE_OK) return rc;
+    ex->last = S;
+    ex->last_count = count;
+    return finish_dev(ex, count);
 }
 
 int sfe_extract_batch(sfe_extractor *ex, const uint8_t *images, size_t image_stride, int count, int w, int h, int stride,
@@ -1248,21 +1408,8 @@ int sfe_extract_batch(sfe_extractor *ex, const uint8_t *images, size_t image_str
         return SFE_OK;
     }
     DeviceGuard g(ex->device);
-    int rc = prepare(ex, count, w, h, stride, cap);
-    if (rc != SFE_OK) return rc;
-    SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * w * h));
-    SFE_CUDA(ex->d_kps.ensure((size_t)ex->max_images * cap));
-    SFE_CUDA(ex->d_desc.ensure((size_t)ex->max_images * cap * 32));
-    SFE_CUDA(ex->d_nout.ensure(ex->max_images));
-    rc = upload_images(ex, images, image_stride, count, w, h, stride, 0);
-    if (rc != SFE_OK) return rc;
-    OutSet O{ex->d_kps.p, ex->d_kps.p, ex->d_desc.p, ex->d_desc.p, ex->d_nout.p, ex->d_nout.p, cap};
-    rc = enqueue_extract(ex, ex->d_in.p, ex->d_in.p, count, (size_t)w * h, w, count, O);
-    if (rc != SFE_OK) return rc;
-    SFE_CUDA(cudaMemcpyAsync(kps, ex->d_kps.p, sizeof(sfe_keypoint) * (size_t)count * cap, cudaMemcpyDeviceToHost, ex->stream));
-    SFE_CUDA(cudaMemcpyAsync(desc, ex->d_desc.p, (size_t)count * cap * 32, cudaMemcpyDeviceToHost, ex->stream));
-    SFE_CUDA(cudaMemcpyAsync(n_out, ex->d_nout.p, sizeof(int32_t) * count, cudaMemcpyDeviceToHost, ex->stream));
-    return check_flags(ex, count);
+    return run_host_batch(ex, images, nullptr, image_stride, count, w, h, stride, &k_default_stereo, kps, desc, n_out, nullptr,
+                          nullptr, nullptr, nullptr, nullptr, cap);
 }
 
 int sfe_extract(sfe_extractor *ex, const uint8_t *image, int w, int h, int stride, sfe_keypoint *kps, uint8_t *desc, int cap,
@@ -1273,23 +1420,6 @@ int sfe_extract(sfe_extractor *ex, const uint8_t *image, int w, int h, int strid
     *n_out = n;
     return rc;
 }
-
-static int stereo_frames_impl(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames,
-                              int in_pitch, const sfe_stereo_params *sp, sfe_keypoint *kl, uint8_t *dl, int32_t *nl,
-                              sfe_keypoint *kr, uint8_t *dr, int32_t *nr, int32_t *sidx, int32_t *sdist, int cap) {
-    OutSet O{kl, kr, dl, dr, nl, nr, cap};
-    int rc = enqueue_extract(ex, left, right, frames, image_stride, in_pitch, 2 * frames, O);
-    if (rc != SFE_OK) return rc;
-    launch_stereo_match(ex->stream, frames, cap, kl, dl, nl, kr, dr, nr, sp->y_threshold, sp->max_dx, sp->best12_threshold,
-                        sidx, sdist);
-    prof_mark(ex, 6);
-    ex->prof_has_stereo = true;
-    ex->launches++;
-    SFE_CUDA(cudaGetLastError());
-    return SFE_OK;
-}
-
-static const sfe_stereo_params k_default_stereo = {3.0, 100.0, 0.5};  // src/matcher.cpp:68-70
 
 int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
                           int frames, int w, int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l_dev,
@@ -1302,10 +1432,20 @@ int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint
     DeviceGuard g(ex->device);
     int rc = prepare(ex, 2 * frames, w, h, stride, cap);
     if (rc != SFE_OK) return rc;
-    rc = stereo_frames_impl(ex, left_dev, right_dev, image_stride, frames, stride, sp ? sp : &k_default_stereo, kps_l_dev,
-                            desc_l_dev, n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, stereo_idx_dev, stereo_dist_dev, cap);
-    if (rc != SFE_OK) return rc;
-    return check_flags(ex, 2 * frames);
+    if (!sp) sp = &k_default_stereo;
+    const OutSet O{kps_l_dev, kps_r_dev, desc_l_dev, desc_r_dev, n_l_dev, n_r_dev, cap};
+    const ImgSet S = make_imgset(ex, left_dev, right_dev, frames, image_stride, stride);
+    if ((rc = reset_counters(ex)) != SFE_OK) return rc;
+    if ((rc = enqueue_extract(ex, ex->stream, S, 2 * frames, O)) != SFE_OK) return rc;
+    launch_stereo_match(ex->stream, frames, cap, kps_l_dev, desc_l_dev, n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, sp->y_threshold,
+                        sp->max_dx, sp->best12_threshold, stereo_idx_dev, stereo_dist_dev);
+    prof_mark(ex, 6);
+    ex->prof_has_stereo = true;
+    ex->launches++;
+    SFE_CUDA(cudaGetLastError());
+    ex->last = S;
+    ex->last_count = 2 * frames;
+    return finish_dev(ex, 2 * frames);
 }
 
 int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
@@ -1316,33 +1456,31 @@ int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *rig
                 "null argument");
     SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
     DeviceGuard g(ex->device);
-    int rc = prepare(ex, 2 * frames, w, h, stride, cap);
-    if (rc != SFE_OK) return rc;
-    const size_t F = frames;
-    SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * w * h));
-    SFE_CUDA(ex->d_kps.ensure((size_t)ex->max_images * cap));
-    SFE_CUDA(ex->d_desc.ensure((size_t)ex->max_images * cap * 32));
-    SFE_CUDA(ex->d_nout.ensure(ex->max_images));
-    SFE_CUDA(ex->d_sidx.ensure((size_t)ex->max_images * cap));
-    SFE_CUDA(ex->d_sdist.ensure((size_t)ex->max_images * cap));
-    if ((rc = upload_images(ex, left, image_stride, frames, w, h, stride, 0)) != SFE_OK) return rc;
-    if ((rc = upload_images(ex, right, image_stride, frames, w, h, stride, frames)) != SFE_OK) return rc;
-    sfe_keypoint *kl = ex->d_kps.p, *kr = ex->d_kps.p + F * cap;
-    uint8_t *dl = ex->d_desc.p, *dr = ex->d_desc.p + F * cap * 32;
-    int32_t *nl = ex->d_nout.p, *nr = ex->d_nout.p + F;
-    rc = stereo_frames_impl(ex, ex->d_in.p, ex->d_in.p + F * w * h, (size_t)w * h, frames, w, sp ? sp : &k_default_stereo, kl,
-                            dl, nl, kr, dr, nr, ex->d_sidx.p, ex->d_sdist.p, cap);
-    if (rc != SFE_OK) return rc;
-    cudaStream_t st = ex->stream;
-    SFE_CUDA(cudaMemcpyAsync(kps_l, kl, sizeof(sfe_keypoint) * F * cap, cudaMemcpyDeviceToHost, st));
-    SFE_CUDA(cudaMemcpyAsync(kps_r, kr, sizeof(sfe_keypoint) * F * cap, cudaMemcpyDeviceToHost, st));
-    SFE_CUDA(cudaMemcpyAsync(desc_l, dl, F * cap * 32, cudaMemcpyDeviceToHost, st));
-    SFE_CUDA(cudaMemcpyAsync(desc_r, dr, F * cap * 32, cudaMemcpyDeviceToHost, st));
-    SFE_CUDA(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
-    SFE_CUDA(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
-    SFE_CUDA(cudaMemcpyAsync(stereo_idx, ex->d_sidx.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, st));
-    if (stereo_dist) SFE_CUDA(cudaMemcpyAsync(stereo_dist, ex->d_sdist.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, st));
-    return check_flags(ex, 2 * frames);
+    return run_host_batch(ex, left, right, image_stride, frames, w, h, stride, sp ? sp : &k_default_stereo, kps_l, desc_l, n_l,
+                          kps_r, desc_r, n_r, stereo_idx, stereo_dist, cap);
+}
+
+int sfe_extractor_set_async(sfe_extractor *ex, int enable) {
+    SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
+    DeviceGuard g(ex->device);
+    SFE_CUDA(cudaStreamSynchronize(ex->stream));
+    ex->async_dev = enable != 0;
+    if (ex->d_counts.p)  // start from clean flags
+        SFE_CUDA(cudaMemset(ex->d_counts.p + (size_t)ex->max_images * ex->prm.nlevels * 2, 0, sizeof(int) * ex->max_images));
+    return SFE_OK;
+}
+
+int sfe_extractor_wait(sfe_extractor *ex) {
+    SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
+    DeviceGuard g(ex->device);
+    if (ex->last_count <= 0) {
+        SFE_CUDA(cudaStreamSynchronize(ex->stream));
+        return SFE_OK;
+    }
+    int rc = check_flags(ex, ex->stream, ex->max_images);
+    if (ex->async_dev)
+        SFE_CUDA(cudaMemset(ex->d_counts.p + (size_t)ex->max_images * ex->prm.nlevels * 2, 0, sizeof(int) * ex->max_images));
+    return rc;
 }
 
 // ---- stage taps ---------------------------------------------------------------------------------
