@@ -123,9 +123,13 @@ __device__ __forceinline__ void warp_append(bool pred, uint16_t item, uint16_t *
     if (pred) list[base + __popc(m & ((1u << lane) - 1))] = item;
 }
 
-// Cell geometry travels in the kernel parameters (constant bank): a CTA derives its cv::FAST call from
-// blockIdx.x without touching global memory before the pixel loads.
-__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, FastPlan P) {
+// 16.16 reciprocals of the small row lengths the kernel divides by: floor(i / n) == (i * kInv16[n]) >> 16 for i < 3640
+__constant__ unsigned short kInv16[24] = {0,     0,     32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958,
+                                          5462,  5042,  4682,  4370,  4097,  3856,  3641,  3450, 3277, 3121, 2979, 2850};
+
+// One CTA = one cell.  The cell record (8 B) comes from a host-built table; the per-level constants ride in the
+// kernel parameters (constant bank).
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, FastPlan P, const CellRec *__restrict__ cells) {
     extern __shared__ __align__(16) uint32_t fast_smem[];
     uint32_t *tile32 = fast_smem;                                    // tile_rows x kTileWords
     uint8_t *score = (uint8_t *)(tile32 + P.tile_rows * kTileWords);  // score_rows x kScorePitch
@@ -136,17 +140,9 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
     const uint8_t *tile = (const uint8_t *)tile32;
     constexpr int T = kFastThreads;
 
-    // which reference cell is this (:789-806)
-    int level = 0;
-#pragma unroll 1
-    for (int k = 1; k < P.nlevels; k++)
-        if ((int)blockIdx.x >= P.lv[k].first_cell) level = k;
+    const CellRec C = cells[blockIdx.x];  // which reference cell is this (:789-806)
+    const int level = C.level, ini_x = C.ini_x, ini_y = C.ini_y, sw = C.sw, sh = C.sh;
     const FastLevel &F = P.lv[level];
-    const int cell = blockIdx.x - F.first_cell;
-    const int ci = (int)__umulhi((unsigned)cell, F.inv_cols), cj = cell - ci * F.n_cols;
-    const int ini_x = kBorder + cj * F.w_cell, ini_y = kBorder + ci * F.h_cell;
-    const int sw = min(ini_x + F.w_cell + 6, F.max_bx) - ini_x, sh = min(ini_y + F.h_cell + 6, F.max_by) - ini_y;
-
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
     const uint8_t *src;
     int pitch;
@@ -159,17 +155,17 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
     }
     src += (size_t)ini_y * pitch + ini_x - 1;  // shared column 0 = sub-image column -1 (ini_x >= 16)
     {   // shared columns [0, 4 * nw) cover sub-image columns [-1, sw + 6]; the row has >= 16 px beyond the cell
-        const int nw = min((sw + 8) >> 2, kTileWords), inv = 65536 / nw + 1;
+        const int nw = min((sw + 8) >> 2, kTileWords), inv = kInv16[nw];
         for (int it = tid; it < sh * nw; it += T) {
             const int r = (it * inv) >> 16, j = it - r * nw;
             tile32[r * kTileWords + j] = ldg_word_at(src + (size_t)r * pitch + 4 * j);
         }
     }
     const int tw = sw - 6, th = sh - 6;  // tested pixels: 3-px margin inside the sub-image
-    const int nq = (tw + 3) >> 2, inv_q = 65536 / nq + 1, nitems = th * nq;
+    const int nq = (tw + 3) >> 2, inv_q = nq > 1 ? kInv16[nq] : 65536, nitems = th * nq;
     int t = P.ini_th;
     for (int attempt = 0; attempt < 2; attempt++) {
-        for (int i = tid; i < (th + 2) * (kScorePitch / 4); i += T) ((uint32_t *)score)[i] = 0;
+        for (int i = tid; i < (th + 2) * (kScorePitch / 16); i += T) ((uint4 *)score)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { n_pre = 0; n_det = 0; n_surv = 0; }
         __syncthreads();
         // stage 0: compass pre-test, one aligned word of 4 centre pixels per thread
@@ -193,22 +189,20 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
                 mask = ((m_lo >> 15) & 1) | ((m_lo >> 30) & 2) | ((m_hi >> 13) & 4) | ((m_hi >> 28) & 8);
                 mask &= (1u << min(4, tw - x)) - 1;
             }
-            if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
-            const int cnt = __popc(mask);
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += u;
-            }
+            // compaction: one ballot per pixel slot (the list order is irrelevant downstream), one atomic per warp
+            const unsigned b0 = __ballot_sync(0xffffffffu, mask & 1), b1 = __ballot_sync(0xffffffffu, mask & 2),
+                           b2 = __ballot_sync(0xffffffffu, mask & 4), b3 = __ballot_sync(0xffffffffu, mask & 8);
+            if ((b0 | b1 | b2 | b3) == 0) continue;
+            const int c0 = __popc(b0), c1 = c0 + __popc(b1), c2 = c1 + __popc(b2), c3 = c2 + __popc(b3);
             int base = 0;
-            if (lane == 31) base = atomicAdd(&n_pre, inc);
-            int pos = __shfl_sync(0xffffffffu, base, 31) + inc - cnt;
-            while (mask) {
-                const int b = __ffs(mask) - 1;
-                mask &= mask - 1;
-                pre[pos++] = (uint16_t)(y << 6 | (x + b));
-            }
+            if (lane == 0) base = atomicAdd(&n_pre, c3);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned lt = (1u << lane) - 1;
+            const uint16_t item = (uint16_t)(y << 6 | x);
+            if (mask & 1) pre[base + __popc(b0 & lt)] = item;
+            if (mask & 2) pre[base + c0 + __popc(b1 & lt)] = item + 1;
+            if (mask & 4) pre[base + c1 + __popc(b2 & lt)] = item + 2;
+            if (mask & 8) pre[base + c2 + __popc(b3 & lt)] = item + 3;
         }
         __syncthreads();
         // stage 1: exact score, two survivors per thread; corner at threshold t iff best > t
@@ -615,26 +609,28 @@ __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__r
     __shared__ __align__(16) uint32_t in32[IH * IWW];
     __shared__ __align__(16) uint32_t hb[IH * HW];  // horizontal sums, two u16 per word
     const TilePlan t = tiles[blockIdx.x];
-    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l = t.level;
+    const int img = blockIdx.y, tid = threadIdx.x, l = t.level;
     const int slot = slot_of(S, img);
     if (S.kp_count[slot * S.nlevels + l] == 0) return;  // the reference blurs only levels with keypoints
     const LevelPlan &L = S.lv[l];
     int pitch;
     const uint8_t *src = level_pixels(S, l, img, pitch);
     const int w = L.w;
-    for (int r = warp; r < IH; r += 8) {
-        const uint8_t *row = src + (size_t)reflect101(t.y0 + r - 3, L.h) * pitch;
-        for (int j = lane; j < IWW; j += 32) {
-            const int x = t.x0 - 4 + 4 * j;
-            uint32_t v;
-            if (x >= 0 && x + 8 <= w) {
-                v = ldg_word_at(row + x);
-            } else {
-                v = __ldg(row + reflect101(x, w)) | (uint32_t)__ldg(row + reflect101(x + 1, w)) << 8 |
-                    (uint32_t)__ldg(row + reflect101(x + 2, w)) << 16 | (uint32_t)__ldg(row + reflect101(x + 3, w)) << 24;
-            }
-            in32[r * IWW + j] = v;
+    const int h = L.h, x_first = t.x0 - 4;
+    for (int it = tid; it < IH * IWW; it += 256) {
+        const int r = (it * (65536 / IWW + 1)) >> 16, j = it - r * IWW;  // exact for it < 4000
+        int yy = t.y0 + r - 3;
+        if ((unsigned)yy >= (unsigned)h) yy = reflect101(yy, h);
+        const uint8_t *row = src + (size_t)yy * pitch;
+        const int x = x_first + 4 * j;
+        uint32_t v;
+        if (x >= 0 && x + 8 <= w) {
+            v = ldg_word_at(row + x);
+        } else {
+            v = __ldg(row + reflect101(x, w)) | (uint32_t)__ldg(row + reflect101(x + 1, w)) << 8 |
+                (uint32_t)__ldg(row + reflect101(x + 2, w)) << 16 | (uint32_t)__ldg(row + reflect101(x + 3, w)) << 24;
         }
+        in32[it] = v;
     }
     __syncthreads();
     // horizontal: item = (row r, group g of 4 outputs); input bytes b[0..11] = words g..g+2, tap i of output k = b[k+i+1]
@@ -706,48 +702,72 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     return a;
 }
 
+// The disc |u| <= umax[|dv|] is symmetric (|dv| <= umax[|u|] describes the same set), so the rows a column
+// u touches are the contiguous range |dv| <= umax[|u|].  Checked at compile time against the table.
+constexpr int kUmax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+constexpr bool disc_is_symmetric() {
+    for (int u = 0; u < 16; u++)
+        for (int v = 0; v < 16; v++)
+            if ((u <= kUmax[v]) != (v <= kUmax[u])) return false;
+    return true;
+}
+static_assert(disc_is_symmetric(), "IC_Angle disc must be symmetric");
+// bit (dv + 15) set iff pixel (u, dv) lies in the 31-px disc
+__device__ __forceinline__ uint32_t disc_rows(int au) {
+    const int vm = c_umax[au];
+    return ((2u << (2 * vm)) - 1u) << (kHalfPatch - vm);
+}
+
 __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O) {
-    __shared__ char2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane`
+    __shared__ float2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane`, as floats
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y, slot = slot_of(S, img);
     for (int i = tid; i < 512; i += 256) {
         const int byte = i >> 4, s = i & 15;
-        pat[s * 32 + byte] = make_char2(g_pattern[2 * i], g_pattern[2 * i + 1]);
+        pat[s * 32 + byte] = make_float2((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
     }
     __syncthreads();
-    // locate keypoint g: levels are concatenated 0..L-1 (:1076-1104)
+    // locate keypoint g: levels are concatenated 0..L-1 (:1076-1104); lane k holds level k's count
     const int g = blockIdx.x * 8 + warp;
-    int l = -1, local = 0, total = 0;
-    for (int k = 0; k < S.nlevels; k++) {
-        const int c = min(S.kp_count[slot * S.nlevels + k], S.lv[k].kp_cap);
-        if (l < 0 && g < total + c) { l = k; local = g - total; }
-        total += c;
+    const int cnt = lane < S.nlevels ? min(S.kp_count[slot * S.nlevels + lane], S.lv[lane].kp_cap) : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < kMaxLevels; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
     }
+    const int total = __shfl_sync(0xffffffffu, inc, kMaxLevels - 1);
+    const int l = __popc(__ballot_sync(0xffffffffu, lane < S.nlevels && inc <= g));  // first level whose prefix exceeds g
+    const int local = g - __shfl_sync(0xffffffffu, inc - cnt, min(l, 31));
     const bool set_a = img < S.split;
     const int oi = set_a ? img : img - S.split;
     if (g == 0 && lane == 0) {
         (set_a ? O.n_a : O.n_b)[oi] = min(total, O.cap);
         if (total > O.cap) atomicOr(&S.flags[slot], kFlagOutOverflow);
     }
-    if (l < 0 || g >= O.cap) return;
+    if (g >= total || g >= O.cap) return;
     const LevelPlan &L = S.lv[l];
     const uint32_t v = S.kpst[(size_t)slot * S.kpst_stride + L.kp_off + local];
     const int x = (v & 0xFFF) + kBorder, y = ((v >> 12) & 0xFFF) + kBorder;
     int pitch;
     const uint8_t *lvl = level_pixels(S, l, img, pitch);
-    // intensity centroid over the 31-px disc on the UNBLURRED level; lane = column u
-    int m01 = 0, m10 = 0;
+    // intensity centroid over the 31-px disc on the UNBLURRED level; lane = column u:
+    // m_10 = u * (column sum), m_01 = sum dv * I
+    int m01 = 0, colsum = 0;
+    const int u = lane - kHalfPatch;
     if (lane < 31) {
-        const int u = lane - kHalfPatch, au = abs(u);
-        const uint8_t *c = lvl + (size_t)y * pitch + x + u;
+        const uint32_t rows = disc_rows(u < 0 ? -u : u);
+        const uint8_t *c = lvl + (size_t)(y - kHalfPatch) * pitch + x + u;
 #pragma unroll
-        for (int dv = -kHalfPatch; dv <= kHalfPatch; dv++) {
-            if (au <= c_umax[abs(dv)]) {
-                const int val = __ldg(c + dv * pitch);
-                m10 += u * val;
-                m01 += dv * val;
+        for (int k = 0; k <= 2 * kHalfPatch; k++) {
+            if (rows >> k & 1) {
+                const int val = __ldg(c);
+                colsum += val;
+                m01 += (k - kHalfPatch) * val;
             }
+            c += pitch;
         }
     }
+    int m10 = u * colsum;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         m01 += __shfl_xor_sync(0xffffffffu, m01, o);
@@ -759,23 +779,25 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
     if (lane == 0) {
         const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.0);
         const float rad = __fmul_rn(angle, factor_pi);
-        a = (float)cos((double)rad);
-        b = (float)sin((double)rad);
+        double sn, cs;
+        sincos((double)rad, &sn, &cs);
+        a = (float)cs;
+        b = (float)sn;
     }
     a = __shfl_sync(0xffffffffu, a, 0);
     b = __shfl_sync(0xffffffffu, b, 0);
-    const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off + (size_t)y * L.blur_pitch + x;
+    const int bp = L.blur_pitch;
+    const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off + (size_t)y * bp + x;
     uint32_t byte = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         int tv[2];
 #pragma unroll
         for (int s = 0; s < 2; s++) {
-            const char2 pp = pat[(2 * k + s) * 32 + lane];
-            const float px = (float)pp.x, py = (float)pp.y;
-            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            tv[s] = __ldg(bl + ry * L.blur_pitch + rx);
+            const float2 pp = pat[(2 * k + s) * 32 + lane];
+            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)));
+            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)));
+            tv[s] = __ldg(bl + (ry * bp + rx));
         }
         byte |= (uint32_t)(tv[0] < tv[1]) << k;
     }
@@ -826,6 +848,8 @@ struct sfe_extractor {
     int w = 0, h = 0;
     LevelPlan lv[kMaxLevels];
     FastPlan fast{};
+    std::vector<CellRec> cells;
+    DevBuf<CellRec> d_cells;
     size_t fast_smem = 0;
     std::vector<TilePlan> tiles;
     size_t pyr_stride = 0, blur_stride = 0;
@@ -890,6 +914,7 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     const int nl = ex->prm.nlevels;
     std::vector<uint2> xtab, ytab;
     memset(&ex->fast, 0, sizeof(ex->fast));
+    ex->cells.clear();
     int max_sw = 7, max_sh = 7;
     ex->tiles.clear();
     size_t pyr_off = 0, blur_off = 0;
@@ -935,20 +960,15 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
             SFE_REQUIRE(L.w_cell + 6 <= kMaxSub && L.h_cell + 6 <= kMaxSub, SFE_ERR_UNSUPPORTED, "FAST cell larger than 66 px");
             if (rows_eff > 0 && cols_eff > 0) {
                 FastLevel &F = ex->fast.lv[l];
-                F.n_cols = cols_eff;
-                F.inv_cols = (unsigned)(0x100000000ull / (unsigned)cols_eff + 1);
-                F.w_cell = L.w_cell;
-                F.h_cell = L.h_cell;
-                F.max_bx = max_bx;
-                F.max_by = max_by;
                 F.pitch = L.pitch;
                 F.plane_off = L.plane_off;
                 n_level_cells = rows_eff * cols_eff;
-                SFE_REQUIRE(n_level_cells < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 FAST cells on one level");
                 for (int i = 0; i < rows_eff; i++) {
                     const int ini_y = kBorder + i * L.h_cell, sh = std::min(ini_y + L.h_cell + 6, max_by) - ini_y;
                     for (int j = 0; j < cols_eff; j++) {
                         const int ini_x = kBorder + j * L.w_cell, sw = std::min(ini_x + L.w_cell + 6, max_bx) - ini_x;
+                        ex->cells.push_back(CellRec{(short)ini_x, (short)ini_y, (unsigned char)sw, (unsigned char)sh,
+                                                    (unsigned char)l, 0});
                         tested += (sw - 6) * (sh - 6);
                         max_sw = std::max(max_sw, sw);
                         max_sh = std::max(max_sh, sh);
@@ -956,7 +976,6 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                 }
             }
         }
-        ex->fast.lv[l].first_cell = ex->fast.n_cells;
         ex->fast.n_cells += n_level_cells;
         // quadtree roots
         L.n_ini = 1;
@@ -1017,10 +1036,10 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     ex->fast.nlevels = nl;
     ex->fast.ini_th = ex->prm.ini_th_fast;
     ex->fast.min_th = ex->prm.min_th_fast;
-    ex->fast.tile_rows = max_sh;
+    ex->fast.tile_rows = (max_sh + 1) & ~1;  // even: tile_rows * 72 B keeps the score array 16-byte aligned
     ex->fast.score_rows = max_sh - 4;
     ex->fast.list_cap = ((max_sw - 6) * (max_sh - 6) + 7) & ~7;
-    ex->fast_smem = (size_t)max_sh * kTilePitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
+    ex->fast_smem = (size_t)ex->fast.tile_rows * kTilePitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
     ex->octree_smem = (size_t)ex->max_cand * (2 * 4 + 3 * 2) + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
     SFE_REQUIRE(ex->octree_smem <= 227 * 1024, SFE_ERR_UNSUPPORTED, "quadtree working set exceeds shared memory");
     const int n = ex->max_images;
@@ -1031,6 +1050,9 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1)));
     SFE_CUDA(ex->d_lv.ensure(kMaxLevels));
     SFE_CUDA(ex->d_tiles.ensure(std::max<size_t>(ex->tiles.size(), 1)));
+    SFE_CUDA(ex->d_cells.ensure(std::max<size_t>(ex->cells.size(), 1)));
+    if (!ex->cells.empty())
+        SFE_CUDA(cudaMemcpyAsync(ex->d_cells.p, ex->cells.data(), sizeof(CellRec) * ex->cells.size(), cudaMemcpyHostToDevice, ex->stream));
     SFE_CUDA(ex->d_xtab.ensure(std::max<size_t>(xtab.size(), 1)));
     SFE_CUDA(ex->d_ytab.ensure(std::max<size_t>(ytab.size(), 1)));
     SFE_CUDA(cudaMemcpyAsync(ex->d_lv.p, ex->lv, sizeof(LevelPlan) * nl, cudaMemcpyHostToDevice, ex->stream));
@@ -1111,7 +1133,7 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     }
     prof_mark(ex, 1);
     if (ex->fast.n_cells > 0) {
-        fast_cells_kernel<<<dim3((unsigned)ex->fast.n_cells, count), kFastThreads, ex->fast_smem, st>>>(S, ex->fast);
+        fast_cells_kernel<<<dim3((unsigned)ex->fast.n_cells, count), kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_cells.p);
         prof_mark(ex, 2);
         {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
             static std::mutex mu;
@@ -1336,7 +1358,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     cudaStreamSynchronize(ex->stream);
     ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_desc.release();
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release(); ex->d_lv.release();
-    ex->d_tiles.release(); ex->d_xtab.release(); ex->d_ytab.release();
+    ex->d_tiles.release(); ex->d_cells.release(); ex->d_xtab.release(); ex->d_ytab.release();
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
     for (int i = 0; i <= kNumStages; i++)
         if (ex->prof_ev[i]) cudaEventDestroy(ex->prof_ev[i]);

@@ -29,15 +29,14 @@ struct LevelPlan {
     float size;             // (int)(31 * scale), :837
 };
 
-// FAST cells (one cv::FAST call of the reference each, :789-816).  The cells of a level that survive the
-// skip rules (:794,803) and hold at least a 7x7 sub-image form a prefix grid of n_rows_eff x n_cols rows /
-// columns, so a cell is identified by its index alone; the table rides in the kernel parameters.
+// FAST cells (one cv::FAST call of the reference each, :789-816): a host-built record per cell that passes the
+// skip rules (:794,803) and holds at least a 7x7 sub-image; per-level constants ride in the kernel parameters.
+struct CellRec {
+    short ini_x, ini_y;       // iniX, iniY (level pixels)
+    unsigned char sw, sh;     // sub-image size handed to cv::FAST (<= kMaxSub)
+    unsigned char level, pad;
+};
 struct FastLevel {
-    int first_cell;        // index of this level's first cell in the launch grid
-    int n_cols;            // cells per row
-    unsigned inv_cols;     // floor(i / n_cols) == __umulhi(i, inv_cols) for i < 2^16
-    int w_cell, h_cell;    // :786-787
-    int max_bx, max_by;    // maxBorderX/Y, :773-776
     int pitch, plane_off;  // level pixels (levels >= 1; level 0 is the input image)
     int cand_off, cand_cap;
 };

@@ -3,6 +3,7 @@
 // inner loop.  XOR + __popc over 8 words; best / second-best kept as packed (dist, index) keys so
 // "strict < in ascending index order" (:114-123) becomes a plain unsigned min.
 #include <algorithm>
+#include <cmath>
 
 #include "sfe_extract.cuh"
 
@@ -22,56 +23,101 @@ __device__ __forceinline__ void load_desc(const uint8_t *p, uint32_t d[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// StereoMatch: one warp per left keypoint scans the right keypoints of its frame.
-// The reference's int(y/10) row buckets (:60-66,83-95) only pre-select: |dy| <= 3 < 10 keeps every
-// passing candidate inside buckets b-1..b+1, so the candidate set is every right keypoint passing
-// the dy / dx filters (:103-110).
+// StereoMatch.  The reference's int(y/10) row buckets (:60-66,83-95) only pre-select: |dy| <= 3 < 10 keeps
+// every passing candidate inside buckets b-1..b+1, so the candidate set is every right keypoint passing the
+// dy / dx filters (:103-110).  Here: one CTA = 64 left keypoints of one frame.  The CTA counting-sorts the
+// right keypoints of its frame into 8-px row buckets in shared memory, then every warp walks only the buckets
+// that can hold |dy| <= y_thr for each of its left keypoints, applies the reference's exact float filters and
+// fetches descriptors only for the survivors.  Visiting order is free: best / second best are packed
+// (dist << 16 | index) keys, so "strict < in ascending index order" (:114-123) is a plain unsigned min.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStereoChunk = 2048;  // right keypoints staged in shared memory at a time
-constexpr int kStereoPerWarp = 4;   // left keypoints per warp; 32 per CTA
+constexpr int kStereoChunk = 2048;   // right keypoints indexed in shared memory at a time
+constexpr int kStereoPerWarp = 8;    // left keypoints per warp; 64 per CTA
+constexpr int kRowBuckets = 512;     // 8-px rows; y >= 4088 shares the last bucket
+constexpr int kRowShift = 3;
 
-// One CTA = 32 left keypoints of one frame: the right keypoints' (x, y) are staged once per CTA in
-// shared memory (SoA float2) and every warp filters them for its 4 left keypoints; descriptors are
-// only fetched for the few candidates that pass the dy / dx filters.
+__device__ __forceinline__ int row_bucket(float y) {
+    return min(max((int)floorf(y) >> kRowShift, 0), kRowBuckets - 1);  // monotone in y
+}
+
+// thr_y / thr_dx: the largest floats <= y_threshold / max_dx, so that for a float d the reference's double
+// comparison (double)d > T is exactly d > thr (no float lies strictly between thr and T).
 __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_keypoint *__restrict__ kl,
                                                            const uint8_t *__restrict__ dl, const int32_t *__restrict__ nl,
                                                            const sfe_keypoint *__restrict__ kr,
                                                            const uint8_t *__restrict__ dr, const int32_t *__restrict__ nr,
-                                                           double y_thr, double max_dx, double ratio,
+                                                           float thr_y, float thr_dx, float reach_y, double ratio,
                                                            int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist) {
     __shared__ float2 rxy[kStereoChunk];
+    __shared__ uint16_t order[kStereoChunk];       // right keypoints of the chunk sorted by row bucket
+    __shared__ int start[kRowBuckets + 1];         // bucket b = order[start[b] .. start[b + 1])
+    __shared__ int fill[kRowBuckets];
+    __shared__ int warp_tot[8];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_l = min(nl[f], cap), n_r = min(nr[f], cap);
     const size_t base = (size_t)f * cap;
     const int i0 = blockIdx.x * (8 * kStereoPerWarp) + warp * kStereoPerWarp;
-    float lx[kStereoPerWarp], ly[kStereoPerWarp];
-    uint32_t a[kStereoPerWarp][8], k0[kStereoPerWarp], k1[kStereoPerWarp];
+    uint32_t k0[kStereoPerWarp], k1[kStereoPerWarp];
 #pragma unroll
-    for (int k = 0; k < kStereoPerWarp; k++) {
-        k0[k] = k1[k] = kNoKey;
-        const int i = min(i0 + k, max(n_l - 1, 0));
-        lx[k] = n_l > 0 ? kl[base + i].x : 0.f;
-        ly[k] = n_l > 0 ? kl[base + i].y : 0.f;
-        if (n_l > 0) load_desc(dl + (base + i) * 32, a[k]);
-    }
-    for (int c0 = 0; c0 < n_r; c0 += kStereoChunk) {
+    for (int k = 0; k < kStereoPerWarp; k++) k0[k] = k1[k] = kNoKey;
+    const bool block_has_work = blockIdx.x * (8 * kStereoPerWarp) < n_l;
+    for (int c0 = 0; c0 < n_r && block_has_work; c0 += kStereoChunk) {
         const int cn = min(kStereoChunk, n_r - c0);
         __syncthreads();
-        for (int j = tid; j < cn; j += 256) rxy[j] = make_float2(kr[base + c0 + j].x, kr[base + c0 + j].y);
+        for (int b = tid; b < kRowBuckets; b += 256) fill[b] = 0;
         __syncthreads();
-        if (i0 >= n_l) continue;
-        for (int j = lane; j < cn; j += 32) {
-            const float2 r = rxy[j];
+        for (int j = tid; j < cn; j += 256) {
+            const float2 r = make_float2(kr[base + c0 + j].x, kr[base + c0 + j].y);
+            rxy[j] = r;
+            atomicAdd(&fill[row_bucket(r.y)], 1);
+        }
+        __syncthreads();
+        {   // exclusive scan of the 512 bucket counts: 2 per thread
+            const int a = fill[2 * tid], b2 = fill[2 * tid + 1];
+            int inc = a + b2;
 #pragma unroll
-            for (int k = 0; k < kStereoPerWarp; k++) {
-                const float dx = __fsub_rn(lx[k], r.x), dy = __fsub_rn(ly[k], r.y);  // float subtraction, then widened
-                if (fabs((double)dy) > y_thr) continue;
-                if ((double)dx < 0.) continue;
-                if ((double)dx > max_dx) continue;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += u;
+            }
+            if (lane == 31) warp_tot[warp] = inc;
+            __syncthreads();
+            int woff = 0;
+#pragma unroll
+            for (int w2 = 0; w2 < 8; w2++) woff += w2 < warp ? warp_tot[w2] : 0;
+            const int ex = woff + inc - (a + b2);
+            start[2 * tid] = ex;
+            start[2 * tid + 1] = ex + a;
+            if (tid == 255) start[kRowBuckets] = ex + a + b2;
+            fill[2 * tid] = 0;
+            fill[2 * tid + 1] = 0;
+        }
+        __syncthreads();
+        for (int j = tid; j < cn; j += 256) {
+            const int b = row_bucket(rxy[j].y);
+            order[start[b] + atomicAdd(&fill[b], 1)] = (uint16_t)j;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kStereoPerWarp; k++) {
+            const int i = i0 + k;
+            if (i >= n_l) continue;
+            const float lx = kl[base + i].x, ly = kl[base + i].y;
+            uint32_t a[8];
+            load_desc(dl + (base + i) * 32, a);
+            const int t0 = start[row_bucket(ly - reach_y)], t1 = start[row_bucket(ly + reach_y) + 1];
+            uint32_t q0 = kNoKey, q1 = kNoKey;
+            for (int t = t0 + lane; t < t1; t += 32) {
+                const int j = order[t];
+                const float2 r = rxy[j];
+                const float dx = __fsub_rn(lx, r.x), dy = __fsub_rn(ly, r.y);  // float subtraction, as in the reference
+                if (fabsf(dy) > thr_y || dx < 0.f || dx > thr_dx) continue;   // :103-110
                 uint32_t b[8];
                 load_desc(dr + (base + c0 + j) * 32, b);
-                top2_insert(k0[k], k1[k], (uint32_t)hamming8(a[k], b) << 16 | (uint32_t)(c0 + j));
+                top2_insert(q0, q1, (uint32_t)hamming8(a, b) << 16 | (uint32_t)(c0 + j));
             }
+            top2_insert(k0[k], k1[k], q1);
+            top2_insert(k0[k], k1[k], q0);
         }
     }
 #pragma unroll
@@ -99,11 +145,19 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
     }
 }
 
+static float float_at_most(double v) {  // largest float <= v
+    float f = (float)v;
+    if ((double)f > v) f = nextafterf(f, -INFINITY);
+    return f;
+}
+
 void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoint *kl, const uint8_t *dl, const int32_t *nl,
                          const sfe_keypoint *kr, const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
                          double ratio, int32_t *out_idx, int32_t *out_dist) {
-    stereo_match_kernel<<<dim3(div_up(cap, 8 * kStereoPerWarp), frames), 256, 0, st>>>(cap, kl, dl, nl, kr, dr, nr, y_thr,
-                                                                                       max_dx, ratio, out_idx, out_dist);
+    // rows a candidate can sit in: |float(ly - ry)| <= y_thr implies |ly - ry| < y_thr + 1 for coordinates < 2^13
+    const float reach = (float)(std::max(y_thr, 0.0) + 1.0);
+    stereo_match_kernel<<<dim3(div_up(cap, 8 * kStereoPerWarp), frames), 256, 0, st>>>(
+        cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, ratio, out_idx, out_dist);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -63,7 +63,12 @@ def main():
         except StopIteration:
             continue
         ie, sm = h.index("Instructions Executed"), h.index("# Samples")
-        body = [r for r in srows if len(r) > ie and r[ie].isdigit()]
+        body = []
+        for r in srows[srows.index(h) + 1:]:
+            if r and r[0] == "Kernel Name":  # the page repeats per matching launch: keep the first
+                break
+            if len(r) > ie and r[ie].isdigit():
+                body.append(r)
         tot = sum(int(r[ie]) for r in body) or 1
         ts = sum(int(r[sm]) for r in body) or 1
         print(f"\n== {name}: SASS instructions executed by segment (split at BAR.SYNC), first launch in report")
