@@ -141,6 +141,11 @@ int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint
                           int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
                           int cap);
 
+/* Row pitch (bytes) the _dev entry points like best for resident images of width w: the smallest multiple
+ * of 16 >= w.  With such a pitch, a 16-byte aligned base and an image stride that is a multiple of 16 the
+ * kernels fetch level-0 tiles with TMA; any other layout is read with ordinary loads (same results). */
+int sfe_image_pitch(int w);
+
 /* Asynchronous mode for the _dev entry points: with enable != 0 they return as soon as the kernels are
  * enqueued on the handle's stream, so a caller can queue batch after batch without a host round trip
  * (consecutive calls reuse the handle's buffers in stream order).  Capacity errors of any queued batch are

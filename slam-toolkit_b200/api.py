@@ -80,6 +80,7 @@ SIGNATURES = {
     "sfe_extract_batch_dev": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sfe_stereo_frames": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
     "sfe_stereo_frames_dev": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
+    "sfe_image_pitch": (_i, [_i]),
     "sfe_extractor_set_async": (_i, [_vp, _i]),
     "sfe_extractor_wait": (_i, [_vp]),
     "sfe_debug_level": (_i, [_vp, _i, _i, _vp]),
@@ -232,6 +233,11 @@ class Event:
             pass
 
 
+def image_pitch(w: int) -> int:
+    """Row pitch (bytes) at which resident images can be fetched with TMA."""
+    return lib().sfe_image_pitch(w)
+
+
 class ORBextractor:
     """ORB_SLAM2::ORBextractor (reference include/orb_extractor.h:45-133)."""
 
@@ -346,9 +352,12 @@ class ORBextractor:
         self._pinned_out = {k: PinnedArray(s, d) for k, (s, d) in spec.items()}
         return {k: v.array for k, v in self._pinned_out.items()}
 
-    def stereo_frames_dev(self, left_ptr, right_ptr, frames, w, h, ptrs, stereo_params=None):
+    def stereo_frames_dev(self, left_ptr, right_ptr, frames, w, h, ptrs, stereo_params=None, pitch=None):
+        """Resident images: row pitch `pitch` bytes (default w), images pitch*h bytes apart.  A pitch that is a
+        multiple of 16 (image_pitch(w)) on a 16-byte aligned buffer lets the kernels fetch level-0 tiles with TMA."""
         sp = C.byref(stereo_params) if stereo_params is not None else None
-        _check(lib().sfe_stereo_frames_dev(self.h, _p(left_ptr), _p(right_ptr), w * h, frames, w, h, w, sp,
+        pitch = pitch or w
+        _check(lib().sfe_stereo_frames_dev(self.h, _p(left_ptr), _p(right_ptr), pitch * h, frames, w, h, pitch, sp,
                                            _p(ptrs["kps_l"]), _p(ptrs["desc_l"]), _p(ptrs["n_l"]), _p(ptrs["kps_r"]),
                                            _p(ptrs["desc_r"]), _p(ptrs["n_r"]), _p(ptrs["stereo_idx"]),
                                            _p(ptrs["stereo_dist"]), self.cap))

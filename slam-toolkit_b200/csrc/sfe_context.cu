@@ -1,7 +1,45 @@
 // General entry points of the sfe C ABI: status strings, pinned/device memory, events.
+#include <mutex>
+
 #include "sfe_common.cuh"
+#include "sfe_tma.cuh"
 
 namespace sfe {
+// cuTensorMapEncodeTiled through the runtime's driver entry point: libsfe.so does not link libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    });
+    return fn;
+}
+
+bool tma_encode_u8_3d(CUtensorMap *map, const void *base, uint64_t width, uint64_t height, uint64_t images, uint64_t pitch,
+                      uint64_t image_stride, uint32_t box_w, uint32_t box_h) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || !tma_layout_ok(base, pitch, image_stride) || box_w % 16 || box_w > 256 || box_h > 256 || box_h == 0) return false;
+    if (images > 1 && image_stride < pitch * height) return false;
+    const cuuint64_t dims[3] = {width, height, images};
+    const cuuint64_t strides[2] = {pitch, images > 1 ? image_stride : pitch * height};
+    const cuuint32_t box[3] = {box_w, box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    alignas(64) CUtensorMap tmp;
+    const CUresult r = fn(&tmp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    *map = tmp;
+    return true;
+}
+
 static thread_local char g_err[512] = "";
 void set_error(const char *fmt, ...) {
     va_list ap;

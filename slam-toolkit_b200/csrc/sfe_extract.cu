@@ -11,6 +11,35 @@
 
 namespace sfe {
 
+// the 32-bit little-endian word at byte address p, any alignment (reads the two aligned words around it)
+__device__ __forceinline__ uint32_t ldg_word_at(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8);
+}
+
+// ---------------------------------------------------------------------------------------------
+// level-0 staging: images as the host holds them (tight rows) -> rows pitched to 16 bytes, the layout TMA
+// can describe.  One thread = one 16-byte chunk of a destination row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) realign_kernel(const uint8_t *__restrict__ src, size_t src_stride, int src_pitch,
+                                                      uint8_t *__restrict__ dst, size_t dst_stride, int dst_pitch, int w, int h) {
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 16, y = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
+    if (x >= dst_pitch || y >= h) return;
+    const uint8_t *p = src + (size_t)img * src_stride + (size_t)y * src_pitch + x;
+    uint4 v;
+    if (x + 20 <= w) {  // the unaligned word reads stay inside the row
+        v = make_uint4(ldg_word_at(p), ldg_word_at(p + 4), ldg_word_at(p + 8), ldg_word_at(p + 12));
+    } else {
+        uint32_t q[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            if (x + k < w) q[k >> 2] |= (uint32_t)__ldg(p + k) << (8 * (k & 3));
+        v = make_uint4(q[0], q[1], q[2], q[3]);
+    }
+    *(uint4 *)(dst + (size_t)img * dst_stride + (size_t)y * dst_pitch + x) = v;
+}
+
 // ---------------------------------------------------------------------------------------------
 // pyramid: cv::resize(INTER_LINEAR) fixed-point model, level l from level l-1 (:1120)
 // ---------------------------------------------------------------------------------------------
@@ -57,16 +86,9 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, int l, const 
 //   stage 2  cell-local non-max suppression (strict > over 8 neighbours, outside the cell = 0)
 //   retry the whole cell with minThFAST only if nothing survived (:811-816)
 // ---------------------------------------------------------------------------------------------
-constexpr int kTilePitch = 72;   // bytes; shared column = sub-image column + 1, so tested x = 0 sits at column 4
-constexpr int kTileWords = kTilePitch / 4;
+// tile row pitch TP (bytes) is a template parameter: 48 for cells up to 43 px wide, 80 up to kMaxSub.
+// shared column = sub-image column + 1, so tested x = 0 sits at column 4 (word aligned).
 constexpr int kScorePitch = 64;  // >= kMaxSub - 6 + 2
-
-// the 32-bit little-endian word at byte address p, any alignment (reads the two aligned words around it)
-__device__ __forceinline__ uint32_t ldg_word_at(const uint8_t *p) {
-    const uintptr_t a = (uintptr_t)p;
-    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
-    return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8);
-}
 
 // Compass pre-test of two pixels held in the 16-bit lanes of c (centre) and p0..p3 (compass pixels).
 // k = 0x7FFF - t in both lanes.  Lane bit 15 of (p + k - c) is set iff p > c + t, of (c + k - p) iff
@@ -84,11 +106,10 @@ __device__ __forceinline__ uint32_t compass2(uint32_t c, uint32_t p0, uint32_t p
 //         = max(v - min_arcs max_k p_k, max_arcs min_k p_k - v)                    (cv::FAST score + 1)
 // for the two pixels at c0 / c1 at once: circle pixels packed as 16x2 lanes, 9 = 3 + 3 + 3 so every arc
 // extremum is a 3-input extremum of 3-input extrema (VIMNMX3.S16x2).
+template <int TP>
 __device__ __forceinline__ void fast_best_x2(const uint8_t *c0, const uint8_t *c1, int &best0, int &best1) {
-    constexpr int off[16] = {3 * kTilePitch,      3 * kTilePitch + 1,  2 * kTilePitch + 2,  kTilePitch + 3,
-                             3,                   -kTilePitch + 3,     -2 * kTilePitch + 2, -3 * kTilePitch + 1,
-                             -3 * kTilePitch,     -3 * kTilePitch - 1, -2 * kTilePitch - 2, -kTilePitch - 3,
-                             -3,                  kTilePitch - 3,      2 * kTilePitch - 2,  3 * kTilePitch - 1};
+    constexpr int off[16] = {3 * TP,  3 * TP + 1,  2 * TP + 2,  TP + 3,  3,  -TP + 3, -2 * TP + 2, -3 * TP + 1,
+                             -3 * TP, -3 * TP - 1, -2 * TP - 2, -TP - 3, -3, TP - 3,  2 * TP - 2,  3 * TP - 1};
     uint32_t p[16], lo3[16], hi3[16];
 #pragma unroll
     for (int k = 0; k < 16; k++) p[k] = __byte_perm(c0[off[k]], c1[off[k]], 0x5410);
@@ -128,15 +149,21 @@ __constant__ unsigned short kInv16[24] = {0,     0,     32769, 21846, 16385, 131
                                           5462,  5042,  4682,  4370,  4097,  3856,  3641,  3450, 3277, 3121, 2979, 2850};
 
 // One CTA = one cell.  The cell record (8 B) comes from a host-built table; the per-level constants ride in the
-// kernel parameters (constant bank).
-__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, FastPlan P, const CellRec *__restrict__ cells) {
-    extern __shared__ __align__(16) uint32_t fast_smem[];
+// kernel parameters (constant bank).  kTma: the sub-image arrives as one TMA box (TP x tile_rows bytes) issued
+// by thread 0; otherwise (level-0 images whose layout TMA cannot describe) the threads assemble it from
+// aligned global words.
+template <int TP, bool kTma>
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, FastPlan P, const CellRec *__restrict__ cells,
+                                                                  const __grid_constant__ TmaMaps M) {
+    constexpr int kTilePitch = TP, kTileWords = TP / 4;
+    extern __shared__ __align__(128) uint32_t fast_smem[];
     uint32_t *tile32 = fast_smem;                                    // tile_rows x kTileWords
     uint8_t *score = (uint8_t *)(tile32 + P.tile_rows * kTileWords);  // score_rows x kScorePitch
     uint16_t *pre = (uint16_t *)(score + P.score_rows * kScorePitch); // y << 6 | x of pixels passing stage 0
     uint16_t *det = pre + P.list_cap;                                 // corners
     uint16_t *surv = pre;                                             // NMS survivors (pre is dead by then)
     __shared__ int n_pre, n_det, n_surv, out_base;
+    __shared__ uint64_t bar;
     const uint8_t *tile = (const uint8_t *)tile32;
     constexpr int T = kFastThreads;
 
@@ -144,17 +171,28 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
     const int level = C.level, ini_x = C.ini_x, ini_y = C.ini_y, sw = C.sw, sh = C.sh;
     const FastLevel &F = P.lv[level];
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    const uint8_t *src;
-    int pitch;
-    if (level == 0) {
-        pitch = S.in_pitch;
-        src = img < S.split ? S.in_a + (size_t)img * S.in_stride : S.in_b + (size_t)(img - S.split) * S.in_stride;
+    if (kTma) {
+        // shared column 0 = sub-image column -1 (ini_x >= 16); bytes outside the image arrive as zeros and are never tested
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)(P.tile_rows * TP));
+            const bool set_a = img < S.split;
+            const CUtensorMap *map = level == 0 ? (set_a ? &M.lv[0] : &M.l0b) : &M.lv[level];
+            const int z = level == 0 ? S.in_z0 + (set_a ? img : img - S.split) : slot_of(S, img);
+            tma_load_3d(tile32, map, &bar, ini_x - 1, ini_y, z);
+        }
     } else {
-        pitch = F.pitch;
-        src = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + F.plane_off;
-    }
-    src += (size_t)ini_y * pitch + ini_x - 1;  // shared column 0 = sub-image column -1 (ini_x >= 16)
-    {   // shared columns [0, 4 * nw) cover sub-image columns [-1, sw + 6]; the row has >= 16 px beyond the cell
+        const uint8_t *src;
+        int pitch;
+        if (level == 0) {
+            pitch = S.in_pitch;
+            src = img < S.split ? S.in_a + (size_t)img * S.in_stride : S.in_b + (size_t)(img - S.split) * S.in_stride;
+        } else {
+            pitch = F.pitch;
+            src = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + F.plane_off;
+        }
+        src += (size_t)ini_y * pitch + ini_x - 1;  // shared column 0 = sub-image column -1 (ini_x >= 16)
+        // shared columns [0, 4 * nw) cover sub-image columns [-1, sw + 6]; the row has >= 16 px beyond the cell
         const int nw = min((sw + 8) >> 2, kTileWords), inv = kInv16[nw];
         for (int it = tid; it < sh * nw; it += T) {
             const int r = (it * inv) >> 16, j = it - r * nw;
@@ -168,6 +206,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
         for (int i = tid; i < (th + 2) * (kScorePitch / 16); i += T) ((uint4 *)score)[i] = make_uint4(0, 0, 0, 0);
         if (tid == 0) { n_pre = 0; n_det = 0; n_surv = 0; }
         __syncthreads();
+        if (kTma && attempt == 0) mbar_wait(&bar, 0);  // the barrier was initialised by thread 0 before the sync above
         // stage 0: compass pre-test, one aligned word of 4 centre pixels per thread
         const uint32_t k2 = (uint32_t)(0x7FFF - t) * 0x10001u;
         for (int i0 = 0; i0 < nitems; i0 += T) {  // whole warps iterate together (ballot inside)
@@ -215,7 +254,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
                 yx0 = pre[2 * e];
                 yx1 = pre[min(2 * e + 1, np - 1)];
                 int best0, best1;
-                fast_best_x2(&tile[((yx0 >> 6) + 3) * kTilePitch + (yx0 & 63) + 4],
+                fast_best_x2<TP>(&tile[((yx0 >> 6) + 3) * kTilePitch + (yx0 & 63) + 4],
                              &tile[((yx1 >> 6) + 3) * kTilePitch + (yx1 & 63) + 4], best0, best1);
                 corner0 = best0 > t;
                 corner1 = best1 > t && 2 * e + 1 < np;
@@ -598,45 +637,85 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 // Tile = 128 x 32 outputs, Q8 kernel [18 34 48 56 48 34 18]; sums are exact integers, the only rounding is
 // the final (v + 2^15) >> 16, exactly cv::GaussianBlur's fixed-point path.
-//   load        (32+6) rows x 34 aligned words (x0-4 .. x0+131) into shared memory, one 32-bit store per 4 px;
-//               words that touch the image border are assembled byte by byte with BORDER_REFLECT_101
+//   load        (32+6) rows x 36 words (x0-4 .. x0+139) into shared memory.  kTma: one TMA box issued by
+//               thread 0, out-of-image bytes arrive as zeros and the tiles on the image border rebuild their
+//               BORDER_REFLECT_101 halo from the tile itself; otherwise aligned global words (one 32-bit store
+//               per 4 px), border words assembled byte by byte
 //   horizontal  4 outputs per thread from three shared words, two outputs per register in 16x2 lanes
 //               (a lane never exceeds 255 * 256 = 65280)
 //   vertical    one column pair x 8 rows per thread: 14 packed words unpacked once, 7 multiply-adds per
 //               output with the rounding constant folded in, result bytes picked with one PRMT
-__global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__restrict__ tiles) {
-    constexpr int IH = kBlurTileH + 6, IWW = kBlurTileW / 4 + 2, HW = kBlurTileW / 2;
-    __shared__ __align__(16) uint32_t in32[IH * IWW];
+template <bool kTma>
+__global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__restrict__ tiles,
+                                                   const __grid_constant__ TmaMaps M) {
+    constexpr int IH = kBlurTileH + 6, IWW = kBlurInWords, HW = kBlurTileW / 2;
+    __shared__ __align__(128) uint32_t in32[IH * IWW];
     __shared__ __align__(16) uint32_t hb[IH * HW];  // horizontal sums, two u16 per word
+    __shared__ uint64_t bar;
     const TilePlan t = tiles[blockIdx.x];
     const int img = blockIdx.y, tid = threadIdx.x, l = t.level;
     const int slot = slot_of(S, img);
     if (S.kp_count[slot * S.nlevels + l] == 0) return;  // the reference blurs only levels with keypoints
     const LevelPlan &L = S.lv[l];
-    int pitch;
-    const uint8_t *src = level_pixels(S, l, img, pitch);
-    const int w = L.w;
-    const int h = L.h, x_first = t.x0 - 4;
-    for (int it = tid; it < IH * IWW; it += 256) {
-        const int r = (it * (65536 / IWW + 1)) >> 16, j = it - r * IWW;  // exact for it < 4000
-        int yy = t.y0 + r - 3;
-        if ((unsigned)yy >= (unsigned)h) yy = reflect101(yy, h);
-        const uint8_t *row = src + (size_t)yy * pitch;
-        const int x = x_first + 4 * j;
-        uint32_t v;
-        if (x >= 0 && x + 8 <= w) {
-            v = ldg_word_at(row + x);
-        } else {
-            v = __ldg(row + reflect101(x, w)) | (uint32_t)__ldg(row + reflect101(x + 1, w)) << 8 |
-                (uint32_t)__ldg(row + reflect101(x + 2, w)) << 16 | (uint32_t)__ldg(row + reflect101(x + 3, w)) << 24;
+    const int w = L.w, h = L.h, x_first = t.x0 - kBlurLead, y_first = t.y0 - 3;
+    if (kTma) {
+        if (tid == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, IH * IWW * 4);
+            const bool set_a = img < S.split;
+            const CUtensorMap *map = l == 0 ? (set_a ? &M.lv[0] : &M.l0b) : &M.lv[l];
+            const int z = l == 0 ? S.in_z0 + (set_a ? img : img - S.split) : slot;
+            tma_load_3d(in32, map, &bar, x_first, y_first, z);
         }
-        in32[it] = v;
+        __syncthreads();  // barrier initialised
+        mbar_wait(&bar, 0);
+        // BORDER_REFLECT_101 for tiles on the image border (levels are >= 8 px per side on this path): the
+        // source pixel of every missing one lies inside this tile.  Columns first, then whole rows.
+        uint8_t *in8 = (uint8_t *)in32;
+        if (t.x0 == 0 || t.x0 + kBlurTileW + 3 > w) {
+            for (int it = tid; it < IH * 6; it += 256) {
+                const int r = (it * 10923) >> 16, k = it - r * 6;  // it / 6 for it < 228
+                const int x = k < 3 ? k - 3 : w + (k - 3);
+                const int c = x - x_first, sc = (k < 3 ? -x : 2 * w - 2 - x) - x_first;
+                if (c >= 0 && c < IWW * 4 && sc >= 0) in8[r * IWW * 4 + c] = in8[r * IWW * 4 + sc];
+            }
+            __syncthreads();
+        }
+        if (t.y0 == 0 || t.y0 + kBlurTileH + 3 > h) {
+            for (int it = tid; it < 6 * IWW; it += 256) {
+                const int k = (it * (65536 / IWW + 1)) >> 16, j = it - k * IWW;  // it / IWW for it < 6 * IWW
+                const int y = k < 3 ? k - 3 : h + (k - 3);
+                const int r = y - y_first, sr = (k < 3 ? -y : 2 * h - 2 - y) - y_first;
+                if (r >= 0 && r < IH && sr >= 0) in32[r * IWW + j] = in32[sr * IWW + j];
+            }
+            __syncthreads();
+        }
+    } else {
+        int pitch;
+        const uint8_t *src = level_pixels(S, l, img, pitch);
+        constexpr int kFirst = kBlurLead / 4 - 1, kWords = kBlurTileW / 4 + 2;  // only x0-4 .. x0+131 is ever read
+        for (int it = tid; it < IH * kWords; it += 256) {
+            const int r = (it * (65536 / kWords + 1)) >> 16, j = kFirst + it - r * kWords;  // exact for it < 4000
+            int yy = y_first + r;
+            if ((unsigned)yy >= (unsigned)h) yy = reflect101(yy, h);
+            const uint8_t *row = src + (size_t)yy * pitch;
+            const int x = x_first + 4 * j;
+            uint32_t v;
+            if (x >= 0 && x + 8 <= w) {
+                v = ldg_word_at(row + x);
+            } else {
+                v = __ldg(row + reflect101(x, w)) | (uint32_t)__ldg(row + reflect101(x + 1, w)) << 8 |
+                    (uint32_t)__ldg(row + reflect101(x + 2, w)) << 16 | (uint32_t)__ldg(row + reflect101(x + 3, w)) << 24;
+            }
+            in32[r * IWW + j] = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    // horizontal: item = (row r, group g of 4 outputs); input bytes b[0..11] = words g..g+2, tap i of output k = b[k+i+1]
+    // horizontal: item = (row r, group g of 4 outputs); input bytes b[0..11] = the three words from output column
+    // 4g - 4 on, tap i of output k = b[k+i+1]
     for (int it = tid; it < IH * (kBlurTileW / 4); it += 256) {
         const int r = it >> 5, g = it & 31;
-        const uint32_t *wp = &in32[r * IWW + g];
+        const uint32_t *wp = &in32[r * IWW + g + (kBlurLead / 4 - 1)];
         const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
         const uint32_t e0 = __byte_perm(w0, 0, 0x4140), e1 = __byte_perm(w0, 0, 0x4342), e2 = __byte_perm(w1, 0, 0x4140),
                        e3 = __byte_perm(w1, 0, 0x4342), e4 = __byte_perm(w2, 0, 0x4140), e5 = __byte_perm(w2, 0, 0x4342);
@@ -848,6 +927,13 @@ struct sfe_extractor {
     int w = 0, h = 0;
     LevelPlan lv[kMaxLevels];
     FastPlan fast{};
+    // TMA descriptors (fast: TP x tile_rows boxes, blur: 144 x 38 boxes); level >= 1 entries follow the plan,
+    // level-0 entries follow the images of the current call
+    alignas(64) TmaMaps fast_maps{}, blur_maps{};
+    bool tma_plan_ok = false, tma_disabled = false, tma_now = false;
+    const void *l0_key[2] = {nullptr, nullptr};
+    size_t l0_geom[4] = {0, 0, 0, 0};
+    int pitch0 = 0;       // row pitch of the host-path staging buffer
     std::vector<CellRec> cells;
     DevBuf<CellRec> d_cells;
     size_t fast_smem = 0;
@@ -855,7 +941,7 @@ struct sfe_extractor {
     size_t pyr_stride = 0, blur_stride = 0;
     int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0, out_cap = 0;
     size_t octree_smem = 0;
-    DevBuf<uint8_t> d_pyr, d_blur, d_in, d_desc;
+    DevBuf<uint8_t> d_pyr, d_blur, d_in, d_l0, d_desc;  // d_in: images as uploaded (tight), d_l0: pitched level 0
     DevBuf<uint32_t> d_cand, d_kpst;
     DevBuf<int> d_counts;  // cand_count | kp_count | flags
     DevBuf<LevelPlan> d_lv;
@@ -1036,10 +1122,11 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     ex->fast.nlevels = nl;
     ex->fast.ini_th = ex->prm.ini_th_fast;
     ex->fast.min_th = ex->prm.min_th_fast;
-    ex->fast.tile_rows = (max_sh + 1) & ~1;  // even: tile_rows * 72 B keeps the score array 16-byte aligned
+    ex->fast.tile_rows = (max_sh + 1) & ~1;  // even: tile_rows * pitch keeps the score array 16-byte aligned
+    ex->fast.tile_pitch = max_sw + 5 <= 48 ? 48 : 80;
     ex->fast.score_rows = max_sh - 4;
     ex->fast.list_cap = ((max_sw - 6) * (max_sh - 6) + 7) & ~7;
-    ex->fast_smem = (size_t)ex->fast.tile_rows * kTilePitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
+    ex->fast_smem = (size_t)ex->fast.tile_rows * ex->fast.tile_pitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
     ex->octree_smem = (size_t)ex->max_cand * (2 * 4 + 3 * 2) + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
     SFE_REQUIRE(ex->octree_smem <= 227 * 1024, SFE_ERR_UNSUPPORTED, "quadtree working set exceeds shared memory");
     const int n = ex->max_images;
@@ -1063,6 +1150,19 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
         SFE_CUDA(cudaMemcpyAsync(ex->d_ytab.p, ytab.data(), sizeof(uint2) * ytab.size(), cudaMemcpyHostToDevice, ex->stream));
     }
     SFE_CUDA(cudaStreamSynchronize(ex->stream));  // the std::vectors above die at return
+    // tensor maps of the pyramid levels (the reflect patch-up of the TMA blur needs >= 8 px per side)
+    ex->tma_plan_ok = !ex->tma_disabled;
+    for (int l = 0; l < nl && ex->tma_plan_ok; l++) {
+        const LevelPlan &L = ex->lv[l];
+        if (L.w < 8 || L.h < 8) ex->tma_plan_ok = false;
+        if (l == 0 || !ex->tma_plan_ok) continue;
+        ex->tma_plan_ok = tma_encode_u8_3d(&ex->fast_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
+                                           ex->fast.tile_pitch, ex->fast.tile_rows) &&
+                          tma_encode_u8_3d(&ex->blur_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
+                                           kBlurInWords * 4, kBlurTileH + 6);
+    }
+    ex->l0_key[0] = ex->l0_key[1] = nullptr;
+    ex->pitch0 = (int)align_up((size_t)w, 16);
     ex->w = w;
     ex->h = h;
     return SFE_OK;
@@ -1103,6 +1203,7 @@ static ImgSet chunk_of(const ImgSet &B, int f0, int f1, bool has_b) {
     S.in_a = B.in_a + (size_t)f0 * B.in_stride;
     S.in_b = B.in_b + (size_t)f0 * B.in_stride;
     S.split = f1 - f0;
+    S.in_z0 = B.in_z0 + f0;
     S.slot_a = B.slot_a + f0;
     S.slot_b = has_b ? B.slot_b + f0 : 0;
     return S;
@@ -1122,6 +1223,37 @@ static int reset_counters(sfe_extractor *ex) {
     return SFE_OK;
 }
 
+// Level-0 tensor maps for the images of this call (set A: n_a images at `a`, set B: n_b at `b`).  Sets
+// ex->tma_now: whether this call's kernels load their tiles with TMA.
+static void prepare_l0_maps(sfe_extractor *ex, const uint8_t *a, const uint8_t *b, int n_a, int n_b, size_t stride, int pitch) {
+    ex->tma_now = false;
+    if (!ex->tma_plan_ok || !tma_layout_ok(a, pitch, stride) || !tma_layout_ok(b, pitch, stride)) return;
+    const size_t geom[4] = {(size_t)n_a, (size_t)n_b, stride, (size_t)pitch};
+    if (ex->l0_key[0] != a || ex->l0_key[1] != b || memcmp(geom, ex->l0_geom, sizeof(geom)) != 0) {
+        const LevelPlan &L = ex->lv[0];
+        const bool ok = tma_encode_u8_3d(&ex->fast_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, ex->fast.tile_pitch, ex->fast.tile_rows) &&
+                        tma_encode_u8_3d(&ex->fast_maps.l0b, b, L.w, L.h, n_b, pitch, stride, ex->fast.tile_pitch, ex->fast.tile_rows) &&
+                        tma_encode_u8_3d(&ex->blur_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, kBlurInWords * 4, kBlurTileH + 6) &&
+                        tma_encode_u8_3d(&ex->blur_maps.l0b, b, L.w, L.h, n_b, pitch, stride, kBlurInWords * 4, kBlurTileH + 6);
+        ex->l0_key[0] = ok ? a : nullptr;
+        ex->l0_key[1] = ok ? b : nullptr;
+        memcpy(ex->l0_geom, geom, sizeof(geom));
+        if (!ok) return;
+    }
+    ex->tma_now = true;
+}
+
+constexpr bool kFastTma = false;  // the cell box starts at an arbitrary byte: TMA wants 16-byte aligned inner coordinates
+
+template <int TP>
+static void launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count) {
+    const dim3 grid((unsigned)ex->fast.n_cells, count);
+    if (ex->tma_now && kFastTma)
+        fast_cells_kernel<TP, true><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_cells.p, ex->fast_maps);
+    else
+        fast_cells_kernel<TP, false><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_cells.p, ex->fast_maps);
+}
+
 // enqueue the extraction of the `count` images of S on the handle's compute stream (counters already reset)
 static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count, const OutSet &O) {
     const int nl = ex->prm.nlevels;
@@ -1133,7 +1265,8 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     }
     prof_mark(ex, 1);
     if (ex->fast.n_cells > 0) {
-        fast_cells_kernel<<<dim3((unsigned)ex->fast.n_cells, count), kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_cells.p);
+        if (ex->fast.tile_pitch == 48) launch_fast<48>(ex, st, S, count);
+        else launch_fast<80>(ex, st, S, count);
         prof_mark(ex, 2);
         {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
             static std::mutex mu;
@@ -1146,7 +1279,10 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         }
         octree_kernel<<<dim3(nl, count), 256, ex->octree_smem, st>>>(S, ex->max_cand, ex->max_nodes);
         prof_mark(ex, 3);
-        blur_kernel<<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p);
+        if (ex->tma_now)
+            blur_kernel<true><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p, ex->blur_maps);
+        else
+            blur_kernel<false><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p, ex->blur_maps);
         prof_mark(ex, 4);
         ex->launches += 3;
     } else {
@@ -1206,12 +1342,20 @@ static int upload_images(sfe_extractor *ex, cudaStream_t st, const uint8_t *imag
     uint8_t *dst = ex->d_in.p + (size_t)first * w * h;
     if (stride == w && image_stride == (size_t)w * h) {
         SFE_CUDA(cudaMemcpyAsync(dst, images, (size_t)count * w * h, cudaMemcpyHostToDevice, st));
-    } else {
+    } else {  // (a 2-D copy of 1241-byte rows runs at a third of the 1-D rate: only for callers with padded rows)
         for (int i = 0; i < count; i++)
             SFE_CUDA(cudaMemcpy2DAsync(dst + (size_t)i * w * h, w, images + (size_t)i * image_stride, stride, w, h,
                                        cudaMemcpyHostToDevice, st));
     }
     return SFE_OK;
+}
+
+// tight staging slots [first, first + count) -> pitched level-0 planes (same slots) on stream st
+static void realign_images(sfe_extractor *ex, cudaStream_t st, int first, int count, int w, int h) {
+    const size_t p0 = ex->pitch0;
+    realign_kernel<<<dim3(div_up((int)p0 / 16, 32), div_up(h, 8), count), dim3(32, 8), 0, st>>>(
+        ex->d_in.p + (size_t)first * w * h, (size_t)w * h, w, ex->d_l0.p + (size_t)first * p0 * h, p0 * h, (int)p0, w, h);
+    ex->launches++;
 }
 
 // How many sub-batches a host call of `units` frames is cut into: the copies of one sub-batch overlap the
@@ -1233,8 +1377,9 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
     const int images = stereo ? 2 * frames : frames;
     int rc = prepare(ex, images, w, h, stride, cap);
     if (rc != SFE_OK) return rc;
-    const size_t F = frames, wh = (size_t)w * h;
-    SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * wh));
+    const size_t F = frames, wh = (size_t)ex->pitch0 * h;  // level 0 as the kernels see it: pitched rows, images back to back
+    SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * w * h + 32));
+    SFE_CUDA(ex->d_l0.ensure((size_t)ex->max_images * wh + 32));
     SFE_CUDA(ex->d_kps.ensure((size_t)ex->max_images * cap));
     SFE_CUDA(ex->d_desc.ensure((size_t)ex->max_images * cap * 32));
     SFE_CUDA(ex->d_nout.ensure(ex->max_images));
@@ -1245,7 +1390,8 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
     sfe_keypoint *kl = ex->d_kps.p, *kr = ex->d_kps.p + F * cap;
     uint8_t *dl = ex->d_desc.p, *dr = ex->d_desc.p + F * cap * 32;
     int32_t *nl = ex->d_nout.p, *nr = ex->d_nout.p + F;
-    const ImgSet B = make_imgset(ex, ex->d_in.p, ex->d_in.p + F * wh, frames, wh, w);
+    const ImgSet B = make_imgset(ex, ex->d_l0.p, ex->d_l0.p + F * wh, frames, wh, ex->pitch0);
+    prepare_l0_maps(ex, B.in_a, stereo ? B.in_b : B.in_a, frames, frames, wh, ex->pitch0);
     const OutSet O{kl, stereo ? kr : kl, dl, stereo ? dr : dl, nl, stereo ? nr : nl, cap};
     if ((rc = reset_counters(ex)) != SFE_OK) return rc;
     const int nch = pipeline_chunks(ex, frames);
@@ -1268,6 +1414,8 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
             SFE_CUDA(cudaEventRecord(ex->ev_in[c], sin));
             SFE_CUDA(cudaStreamWaitEvent(sc, ex->ev_in[c], 0));
         }
+        realign_images(ex, sc, f0, fc, w, h);
+        if (stereo) realign_images(ex, sc, frames + f0, fc, w, h);
         const OutSet Oc = chunk_of(O, f0);
         if ((rc = enqueue_extract(ex, sc, chunk_of(B, f0, f1, stereo), stereo ? 2 * fc : fc, Oc)) != SFE_OK) break;
         if (stereo) {
@@ -1344,6 +1492,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
         return SFE_ERR_CUDA;
     }
     if (const char *env = getenv("SFE_PIPELINE_CHUNKS")) ex->chunks_override = atoi(env);
+    if (const char *env = getenv("SFE_NO_TMA")) ex->tma_disabled = atoi(env) != 0;
     build_tables(ex);
     int cap = p->nfeatures;
     for (int l = 0; l < p->nlevels; l++) cap += 4;
@@ -1356,7 +1505,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     if (!ex) return SFE_OK;
     DeviceGuard g(ex->device);
     cudaStreamSynchronize(ex->stream);
-    ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_desc.release();
+    ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_l0.release(); ex->d_desc.release();
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release(); ex->d_lv.release();
     ex->d_tiles.release(); ex->d_cells.release(); ex->d_xtab.release(); ex->d_ytab.release();
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
@@ -1415,6 +1564,7 @@ int sfe_extract_batch_dev(sfe_extractor *ex, const uint8_t *images_dev, size_t i
     if (rc != SFE_OK) return rc;
     const OutSet O{kps_dev, kps_dev, desc_dev, desc_dev, n_out_dev, n_out_dev, cap};
     const ImgSet S = make_imgset(ex, images_dev, images_dev, count, image_stride, stride);
+    prepare_l0_maps(ex, images_dev, images_dev, count, count, image_stride, stride);
     if ((rc = reset_counters(ex)) != SFE_OK) return rc;
     if ((rc = enqueue_extract(ex, ex->stream, S, count, O)) != SFE_OK) return rc;
     ex->last = S;
@@ -1457,6 +1607,7 @@ int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint
     if (!sp) sp = &k_default_stereo;
     const OutSet O{kps_l_dev, kps_r_dev, desc_l_dev, desc_r_dev, n_l_dev, n_r_dev, cap};
     const ImgSet S = make_imgset(ex, left_dev, right_dev, frames, image_stride, stride);
+    prepare_l0_maps(ex, left_dev, right_dev, frames, frames, image_stride, stride);
     if ((rc = reset_counters(ex)) != SFE_OK) return rc;
     if ((rc = enqueue_extract(ex, ex->stream, S, 2 * frames, O)) != SFE_OK) return rc;
     launch_stereo_match(ex->stream, frames, cap, kps_l_dev, desc_l_dev, n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, sp->y_threshold,
@@ -1481,6 +1632,8 @@ int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *rig
     return run_host_batch(ex, left, right, image_stride, frames, w, h, stride, sp ? sp : &k_default_stereo, kps_l, desc_l, n_l,
                           kps_r, desc_r, n_r, stereo_idx, stereo_dist, cap);
 }
+
+int sfe_image_pitch(int w) { return w > 0 ? (int)align_up((size_t)w, 16) : 0; }
 
 int sfe_extractor_set_async(sfe_extractor *ex, int enable) {
     SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");

@@ -1,6 +1,7 @@
 // Internal layout shared by the extraction kernels and the extractor handle.
 #pragma once
 #include "sfe_common.cuh"
+#include "sfe_tma.cuh"
 
 namespace sfe {
 
@@ -11,6 +12,9 @@ constexpr int kHalfPatch = 15;     // HALF_PATCH_SIZE, :73
 constexpr int kMaxSub = 66;        // largest FAST cell sub-image side (wCell + 6 < 60 + 6)
 constexpr int kMaxCandCap = 8192;  // per level; the quadtree kernel keeps 14 B per candidate in shared memory
 constexpr int kBlurTileW = 128, kBlurTileH = 32;
+constexpr int kBlurInWords = 40;   // shared-memory row of a blur input tile: x0-16 .. x0+143 (a TMA box starts and ends on 16-byte
+                                   // multiples of the row: the innermost coordinate must be 16-byte aligned)
+constexpr int kBlurLead = 16;      // bytes of a tile row before output column 0
 
 // One pyramid level's geometry for the current image size (host-built, mirrored on device).
 struct LevelPlan {
@@ -45,6 +49,7 @@ struct FastPlan {
     int nlevels, n_cells;
     int ini_th, min_th;
     int tile_rows, score_rows, list_cap;  // dynamic shared-memory carve-up, sized for the largest cell
+    int tile_pitch;                       // 48 (cells up to 43 px wide) or 80 bytes
 };
 constexpr int kFastThreads = 128;
 
@@ -59,6 +64,7 @@ struct ImgSet {
     size_t in_stride;            // bytes between consecutive images of a set
     int in_pitch;                // bytes between rows
     int split;
+    int in_z0;                   // index of image 0 of this (sub-)batch inside the level-0 tensor maps
     int slot_a, slot_b;          // internal buffer slot of image 0 of set A / set B (a pipelined host call runs
                                  // the batch as chunks that share the handle's buffers)
     uint8_t *pyr;                // levels 1.. of all images
@@ -74,6 +80,13 @@ struct ImgSet {
     int *cand_count;             // [image][level]
     int *kp_count;               // [image][level]
     int *flags;                  // [image] error bits
+};
+
+// TMA descriptors of one box shape: lv[l] = pyramid level l over the handle's slots (l >= 1),
+// lv[0] / l0b = the level-0 images of set A / set B of the current call.
+struct TmaMaps {
+    CUtensorMap lv[kMaxLevels];
+    CUtensorMap l0b;
 };
 
 enum { kFlagCandOverflow = 1, kFlagNodeOverflow = 2, kFlagOutOverflow = 4 };

@@ -154,6 +154,74 @@ def test_resident_entry_points_match_host_ones(kitti_ex, oracle):
     assert n == nl and np.array_equal(bufs["desc_r"].download((cap, 32), np.uint8)[:n], host["desc_l"][0, :n])
 
 
+def _stereo_equal(a, b, frames):
+    for f in range(frames):
+        nl, nr = a["n_l"][f], a["n_r"][f]
+        assert (nl, nr) == (b["n_l"][f], b["n_r"][f])
+        for k, n in (("kps_l", nl), ("desc_l", nl), ("kps_r", nr), ("desc_r", nr), ("stereo_idx", nl), ("stereo_dist", nl)):
+            assert np.array_equal(a[k][f, :n], b[k][f, :n]), (k, f)
+
+
+def test_pipelined_sub_batches_and_load_paths_agree(gpu, oracle, monkeypatch):
+    """The host entry point cuts a batch into sub-batches on several streams, and tiles are fetched either by
+    TMA or by plain loads: every combination must give the same bytes, and those of the oracle."""
+    seeds = list(range(9))
+    L = np.stack([synth.stereo_pair(s)[0] for s in seeds])
+    R = np.stack([synth.stereo_pair(s)[1] for s in seeds])
+    outs = {}
+    for chunks, no_tma in ((1, 0), (3, 0), (9, 0), (2, 1)):
+        monkeypatch.setenv("SFE_PIPELINE_CHUNKS", str(chunks))
+        monkeypatch.setenv("SFE_NO_TMA", str(no_tma))
+        ex = api.ORBextractor(max_images=2 * len(seeds))
+        outs[(chunks, no_tma)] = ex.stereo_frames(L, R)
+        if chunks == 3:   # odd images too (single-set batch through the same pipeline)
+            kps, desc, n = ex.extract_batch(L[:5])
+            for i in range(5):
+                assert np.array_equal(kps[i, :n[i]], outs[(chunks, no_tma)]["kps_l"][i, :n[i]])
+                assert np.array_equal(desc[i, :n[i]], outs[(chunks, no_tma)]["desc_l"][i, :n[i]])
+    base = outs[(1, 0)]
+    for key, o in outs.items():
+        _stereo_equal(o, base, len(seeds))
+    ref = oracle.Extractor()
+    for f in (0, 8):
+        kl, dl = ref.extract(L[f])
+        assert np.array_equal(base["kps_l"][f, :len(kl)], kl) and np.array_equal(base["desc_l"][f, :len(kl)], dl)
+
+
+def test_pitched_resident_images_and_async_mode(kitti_ex):
+    """Resident images with a TMA-friendly row pitch give the bytes of the host path; in asynchronous mode the
+    _dev call returns before the kernels finish and wait() reports."""
+    seeds = (1, 2)
+    L = np.stack([synth.stereo_pair(s)[0] for s in seeds])
+    R = np.stack([synth.stereo_pair(s)[1] for s in seeds])
+    host = kitti_ex.stereo_frames(L, R)
+    f, h, w = L.shape
+    pitch = api.image_pitch(w)
+    assert pitch % 16 == 0 and pitch >= w
+
+    def pitched(a):
+        out = np.full((f, h, pitch), 255, np.uint8)   # padding must not influence anything
+        out[:, :, :w] = a
+        return out
+    dl, dr = api.DeviceBuffer(f * h * pitch).upload(pitched(L)), api.DeviceBuffer(f * h * pitch).upload(pitched(R))
+    cap = kitti_ex.cap
+    spec = {"kps_l": 28 * cap * f, "desc_l": 32 * cap * f, "n_l": 4 * f, "kps_r": 28 * cap * f, "desc_r": 32 * cap * f,
+            "n_r": 4 * f, "stereo_idx": 4 * cap * f, "stereo_dist": 4 * cap * f}
+    for async_mode in (False, True):
+        bufs = {k: api.DeviceBuffer(v) for k, v in spec.items()}
+        kitti_ex.set_async(async_mode)
+        kitti_ex.stereo_frames_dev(dl.ptr, dr.ptr, f, w, h, {k: b.ptr for k, b in bufs.items()}, pitch=pitch)
+        if async_mode:
+            kitti_ex.wait()
+        kitti_ex.set_async(False)
+        got = {"n_l": bufs["n_l"].download((f,), np.int32), "n_r": bufs["n_r"].download((f,), np.int32),
+               "kps_l": bufs["kps_l"].download((f, cap), api.KP_DTYPE), "kps_r": bufs["kps_r"].download((f, cap), api.KP_DTYPE),
+               "desc_l": bufs["desc_l"].download((f, cap, 32), np.uint8), "desc_r": bufs["desc_r"].download((f, cap, 32), np.uint8),
+               "stereo_idx": bufs["stereo_idx"].download((f, cap), np.int32),
+               "stereo_dist": bufs["stereo_dist"].download((f, cap), np.int32)}
+        _stereo_equal(got, host, f)
+
+
 # ---- matchers -------------------------------------------------------------------------------------
 def _mk_kps(xy):
     k = np.zeros(len(xy), api.KP_DTYPE)
