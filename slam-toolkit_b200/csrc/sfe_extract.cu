@@ -42,35 +42,57 @@ __global__ void __launch_bounds__(256) realign_kernel(const uint8_t *__restrict_
 
 // ---------------------------------------------------------------------------------------------
 // pyramid: cv::resize(INTER_LINEAR) fixed-point model, level l from level l-1 (:1120)
+//   out = (((b0 * (T0 >> 4)) >> 16) + ((b1 * (T1 >> 4)) >> 16) + 2) >> 2,   T = S[sx] * w0 + S[sx + 1] * w1
+// Separable, so one CTA (64 x 32 outputs) first forms U = T >> 4 (<= 32640, u16) for every source row its
+// outputs touch -- 1.2 source rows per output row instead of 2 -- into shared memory, then combines two
+// rows per output, 4 outputs per thread and one 32-bit store.  Coefficients come from host-built tables.
 // ---------------------------------------------------------------------------------------------
-// 4 output pixels per thread (one 32-bit store); the coefficient tables are padded to a multiple of 4.
+constexpr int kPyrTileW = 64, kPyrTileH = 32;
+
 __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, int l, const uint2 *__restrict__ xtab,
                                                          const uint2 *__restrict__ ytab) {
+    extern __shared__ __align__(16) uint16_t pyr_u[];  // [source row][kPyrTileW]
     const LevelPlan &L = S.lv[l];
-    const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
-    if (x >= L.w || y >= L.h) return;
+    const int x0 = blockIdx.x * kPyrTileW, y0 = blockIdx.y * kPyrTileH, img = blockIdx.z, tid = threadIdx.x;
+    const uint2 *yt = ytab + L.ytab_off;
+    const int sy_first = __ldg(&yt[y0]).x & 0xFFFF;                               // rows are monotone in y
+    const int n_rows = (int)(__ldg(&yt[min(y0 + kPyrTileH, L.h) - 1]).x >> 16) - sy_first + 1;
     int sp;
     const uint8_t *src = level_pixels(S, l - 1, img, sp);
-    const int sw = S.lv[l - 1].w;
-    const uint2 yt = __ldg(&ytab[L.ytab_off + y]);
-    const int y0 = yt.x & 0xFFFF, y1 = yt.x >> 16;
-    const int b0 = yt.y & 0xFFFF, b1 = yt.y >> 16;
-    const uint8_t *r0 = src + (size_t)y0 * sp, *r1 = src + (size_t)y1 * sp;
-    const uint4 *xt4 = (const uint4 *)(xtab + L.xtab_off + x);  // xtab_off and x are multiples of 4
-    const uint4 ta = __ldg(xt4), tb = __ldg(xt4 + 1);
-    const uint32_t sxs[4] = {ta.x, ta.z, tb.x, tb.z}, ws[4] = {ta.y, ta.w, tb.y, tb.w};
-    uint32_t packed = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int sx = sxs[k], sx1 = min(sx + 1, sw - 1);
-        const int w0 = ws[k] & 0xFFFF, w1 = ws[k] >> 16;
-        const int t0 = __ldg(r0 + sx) * w0 + __ldg(r0 + sx1) * w1;
-        const int t1 = __ldg(r1 + sx) * w0 + __ldg(r1 + sx1) * w1;
-        const int v = (((b0 * (t0 >> 4)) >> 16) + ((b1 * (t1 >> 4)) >> 16) + 2) >> 2;
-        packed |= (uint32_t)min(max(v, 0), 255) << (8 * k);
+    {   // horizontal: thread = output column, walking the source rows
+        const int ox = tid & (kPyrTileW - 1);
+        const uint2 xt = __ldg(&xtab[L.xtab_off + min(x0 + ox, L.w - 1)]);
+        const int sx = xt.x, sx1 = min(sx + 1, S.lv[l - 1].w - 1);
+        const int w0 = xt.y & 0xFFFF, w1 = xt.y >> 16;
+        const uint8_t *row = src + (size_t)(sy_first + (tid >> 6)) * sp;
+        for (int r = tid >> 6; r < n_rows; r += 4) {
+            pyr_u[r * kPyrTileW + ox] = (uint16_t)((__ldg(row + sx) * w0 + __ldg(row + sx1) * w1) >> 4);
+            row += 4 * sp;
+        }
     }
-    uint8_t *dst = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + L.plane_off;
-    *(uint32_t *)(dst + (size_t)y * L.pitch + x) = packed;  // pitch is a multiple of 16: pad bytes absorb the tail
+    __syncthreads();
+    // vertical: thread = 4 adjacent outputs on rows ry and ry + 16
+    const int cg = (tid & 15) * 4, ry = tid >> 4;
+    if (x0 + cg >= L.w) return;
+    uint8_t *dst = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + L.plane_off + x0 + cg;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int oy = y0 + ry + 16 * k;
+        if (oy >= L.h) break;
+        const uint2 t = __ldg(&yt[oy]);
+        const int r0 = (int)(t.x & 0xFFFF) - sy_first, r1 = (int)(t.x >> 16) - sy_first;
+        const int b0 = t.y & 0xFFFF, b1 = t.y >> 16;
+        const uint2 A = *(const uint2 *)&pyr_u[r0 * kPyrTileW + cg], B = *(const uint2 *)&pyr_u[r1 * kPyrTileW + cg];
+        const int a[4] = {(int)(A.x & 0xFFFF), (int)(A.x >> 16), (int)(A.y & 0xFFFF), (int)(A.y >> 16)};
+        const int b[4] = {(int)(B.x & 0xFFFF), (int)(B.x >> 16), (int)(B.y & 0xFFFF), (int)(B.y >> 16)};
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int v = (((b0 * a[i]) >> 16) + ((b1 * b[i]) >> 16) + 2) >> 2;
+            packed |= (uint32_t)min(v, 255) << (8 * i);
+        }
+        *(uint32_t *)(dst + (size_t)oy * L.pitch) = packed;  // pitch is a multiple of 16: pad bytes absorb the tail
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -505,7 +527,11 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
     return C + n_unsplit;
 }
 
-__global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int max_cand, int max_nodes) {
+// Candidate-sized arrays (14 B per candidate) live in shared memory when the level has at most smem_cand
+// candidates -- sized for the common case so that several CTAs fit an SM -- and otherwise in one of the
+// handle's global scratch slots (same code, generic pointers; L2-resident).
+__global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int smem_cand, int max_cand, int max_nodes,
+                                                     uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int sh_misc[4];
     const int l = blockIdx.x, img = slot_of(S, blockIdx.y), tid = threadIdx.x, T = blockDim.x;  // internal buffers only
@@ -516,11 +542,32 @@ __global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int max_cand, int
         if (tid == 0) *kp_count = 0;
         return;
     }
+    uint8_t *cbase = smem_raw;
+    int ccap = smem_cand;
+    if (n > smem_cand) {
+        if (tid == 0) sh_misc[0] = atomicAdd(scratch_next, 1);
+        __syncthreads();
+        const int slot = sh_misc[0];
+        __syncthreads();
+        if (slot >= scratch_slots) {
+            if (tid == 0) {
+                atomicOr(&S.flags[img], kFlagNodeOverflow);
+                *kp_count = 0;
+            }
+            return;
+        }
+        ccap = max_cand;
+        cbase = scratch + (size_t)slot * max_cand * 14;
+    }
     OctSmem M;
     {
-        uint8_t *p = smem_raw;
-        M.pk[0] = (uint32_t *)p; p += sizeof(uint32_t) * max_cand;
-        M.pk[1] = (uint32_t *)p; p += sizeof(uint32_t) * max_cand;
+        uint8_t *p = cbase;
+        M.pk[0] = (uint32_t *)p; p += sizeof(uint32_t) * ccap;
+        M.pk[1] = (uint32_t *)p; p += sizeof(uint32_t) * ccap;
+        M.own[0] = (uint16_t *)p; p += sizeof(uint16_t) * ccap;
+        M.own[1] = (uint16_t *)p; p += sizeof(uint16_t) * ccap;
+        M.qs = (uint16_t *)p;
+        p = smem_raw + (size_t)smem_cand * 14;
         M.child = (uint32_t *)p; p += sizeof(uint32_t) * 4 * max_nodes;
         M.tord = (int *)p; p += sizeof(int) * max_nodes;
         M.arr_a = (int *)p; p += sizeof(int) * max_nodes;
@@ -528,9 +575,6 @@ __global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int max_cand, int
         M.warp_sums = (int *)p; p += sizeof(int) * 32;
         M.nd[0] = (ONode *)p; p += sizeof(ONode) * max_nodes;
         M.nd[1] = (ONode *)p; p += sizeof(ONode) * max_nodes;
-        M.own[0] = (uint16_t *)p; p += sizeof(uint16_t) * max_cand;
-        M.own[1] = (uint16_t *)p; p += sizeof(uint16_t) * max_cand;
-        M.qs = (uint16_t *)p; p += sizeof(uint16_t) * max_cand;
         M.eidx[0] = (uint16_t *)p; p += sizeof(uint16_t) * max_nodes;
         M.eidx[1] = (uint16_t *)p; p += sizeof(uint16_t) * max_nodes;
         M.childpos = (uint16_t *)p; p += sizeof(uint16_t) * 4 * max_nodes;
@@ -907,6 +951,7 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
 using namespace sfe;
 
 enum { kStagePyramid, kStageFast, kStageQuadtree, kStageBlur, kStageDescribe, kStageStereo, kNumStages };
+constexpr int kOctreeSmemCand = 3072;
 constexpr int kMaxChunks = 16;  // sub-batches one pipelined host call is cut into
 
 struct sfe_extractor {
@@ -936,11 +981,13 @@ struct sfe_extractor {
     int pitch0 = 0;       // row pitch of the host-path staging buffer
     std::vector<CellRec> cells;
     DevBuf<CellRec> d_cells;
-    size_t fast_smem = 0;
+    size_t fast_smem = 0, pyr_smem = 0;
     std::vector<TilePlan> tiles;
     size_t pyr_stride = 0, blur_stride = 0;
     int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0, out_cap = 0;
     size_t octree_smem = 0;
+    int octree_smem_cand = 0, octree_slots = 0, octree_cand_override = 0;  // SFE_OCTREE_SMEM_CAND (tests)
+    DevBuf<uint8_t> d_octree_scratch;
     DevBuf<uint8_t> d_pyr, d_blur, d_in, d_l0, d_desc;  // d_in: images as uploaded (tight), d_l0: pitched level 0
     DevBuf<uint32_t> d_cand, d_kpst;
     DevBuf<int> d_counts;  // cand_count | kp_count | flags
@@ -999,6 +1046,7 @@ static void build_tables(sfe_extractor *ex) {
 static int build_plan(sfe_extractor *ex, int w, int h) {
     const int nl = ex->prm.nlevels;
     std::vector<uint2> xtab, ytab;
+    int max_src_rows = 1;
     memset(&ex->fast, 0, sizeof(ex->fast));
     ex->cells.clear();
     int max_sw = 7, max_sh = 7;
@@ -1111,14 +1159,21 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                 const int y0 = std::min(std::max(sy, 0), sh - 1), y1 = std::min(std::max(sy + 1, 0), sh - 1);
                 ytab.push_back(make_uint2((unsigned)y0 | (unsigned)y1 << 16, (unsigned)b0 | (unsigned)b1 << 16));
             }
+            for (int ty = 0; ty < L.h; ty += kPyrTileH) {  // source rows one output tile touches
+                const int last = std::min(ty + kPyrTileH, L.h) - 1;
+                const int span = (int)(ytab[L.ytab_off + last].x >> 16) - (int)(ytab[L.ytab_off + ty].x & 0xFFFF) + 1;
+                max_src_rows = std::max(max_src_rows, span);
+            }
         }
     }
     ex->pyr_stride = std::max<size_t>(pyr_off, 128);
     ex->blur_stride = std::max<size_t>(blur_off, 128);
     ex->cand_stride = std::max(cand_off, 1);
     ex->kpst_stride = std::max(kp_off, 1);
-    ex->max_cand = std::max(max_cand, 1);
+    ex->max_cand = (std::max(max_cand, 1) + 7) & ~7;
     ex->max_nodes = max_nodes;
+    ex->pyr_smem = (size_t)max_src_rows * kPyrTileW * sizeof(uint16_t);
+    SFE_REQUIRE(ex->pyr_smem <= 48 * 1024, SFE_ERR_UNSUPPORTED, "scale factor too large for the pyramid tile");
     ex->fast.nlevels = nl;
     ex->fast.ini_th = ex->prm.ini_th_fast;
     ex->fast.min_th = ex->prm.min_th_fast;
@@ -1127,14 +1182,20 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     ex->fast.score_rows = max_sh - 4;
     ex->fast.list_cap = ((max_sw - 6) * (max_sh - 6) + 7) & ~7;
     ex->fast_smem = (size_t)ex->fast.tile_rows * ex->fast.tile_pitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
-    ex->octree_smem = (size_t)ex->max_cand * (2 * 4 + 3 * 2) + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
+    // candidate arrays for up to kOctreeSmemCand points in shared memory (3 CTAs per SM at the KITTI config); fuller
+    // levels spill to global scratch slots
+    ex->octree_smem_cand = std::min(ex->max_cand, ex->octree_cand_override > 0 ? ex->octree_cand_override : kOctreeSmemCand) & ~7;
+    if (ex->octree_smem_cand < 8) ex->octree_smem_cand = 8;
+    ex->octree_smem = (size_t)ex->octree_smem_cand * 14 + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
     SFE_REQUIRE(ex->octree_smem <= 227 * 1024, SFE_ERR_UNSUPPORTED, "quadtree working set exceeds shared memory");
+    ex->octree_slots = ex->max_cand > ex->octree_smem_cand ? 2 * ex->max_images : 0;
+    SFE_CUDA(ex->d_octree_scratch.ensure(std::max<size_t>((size_t)ex->octree_slots * ex->max_cand * 14, 16)));
     const int n = ex->max_images;
     SFE_CUDA(ex->d_pyr.ensure(ex->pyr_stride * n));
     SFE_CUDA(ex->d_blur.ensure(ex->blur_stride * n));
     SFE_CUDA(ex->d_cand.ensure((size_t)ex->cand_stride * n));
     SFE_CUDA(ex->d_kpst.ensure((size_t)ex->kpst_stride * n));
-    SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1)));
+    SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1) + 1));  // cand_count | kp_count | scratch_next | flags
     SFE_CUDA(ex->d_lv.ensure(kMaxLevels));
     SFE_CUDA(ex->d_tiles.ensure(std::max<size_t>(ex->tiles.size(), 1)));
     SFE_CUDA(ex->d_cells.ensure(std::max<size_t>(ex->cells.size(), 1)));
@@ -1193,7 +1254,7 @@ static ImgSet make_imgset(sfe_extractor *ex, const uint8_t *in_a, const uint8_t 
     S.kpst_stride = ex->kpst_stride;
     S.cand_count = ex->d_counts.p;
     S.kp_count = ex->d_counts.p + (size_t)ex->max_images * nl;
-    S.flags = ex->d_counts.p + (size_t)ex->max_images * nl * 2;
+    S.flags = ex->d_counts.p + (size_t)ex->max_images * nl * 2 + 1;
     return S;
 }
 
@@ -1217,8 +1278,8 @@ static OutSet chunk_of(const OutSet &O, int f0) {
 }
 
 static int reset_counters(sfe_extractor *ex) {
-    // layout: cand_count | kp_count | flags.  An asynchronous handle keeps the error flags until sfe_extractor_wait.
-    const size_t n = (size_t)ex->max_images * (2 * ex->prm.nlevels + (ex->async_dev ? 0 : 1));
+    // layout: cand_count | kp_count | scratch_next | flags.  An asynchronous handle keeps the error flags until sfe_extractor_wait.
+    const size_t n = (size_t)ex->max_images * (2 * ex->prm.nlevels + (ex->async_dev ? 0 : 1)) + 1;
     SFE_CUDA(cudaMemsetAsync(ex->d_counts.p, 0, sizeof(int) * n, ex->stream));
     return SFE_OK;
 }
@@ -1259,8 +1320,8 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     const int nl = ex->prm.nlevels;
     prof_mark(ex, 0);
     for (int l = 1; l < nl; l++) {
-        dim3 grid(div_up(ex->lv[l].w, 128), div_up(ex->lv[l].h, 8), count);
-        pyr_resize_kernel<<<grid, dim3(32, 8), 0, st>>>(S, l, ex->d_xtab.p, ex->d_ytab.p);
+        dim3 grid(div_up(ex->lv[l].w, kPyrTileW), div_up(ex->lv[l].h, kPyrTileH), count);
+        pyr_resize_kernel<<<grid, 256, ex->pyr_smem, st>>>(S, l, ex->d_xtab.p, ex->d_ytab.p);
         ex->launches++;
     }
     prof_mark(ex, 1);
@@ -1277,7 +1338,8 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
                 granted[ex->device & 63] = ex->octree_smem;
             }
         }
-        octree_kernel<<<dim3(nl, count), 256, ex->octree_smem, st>>>(S, ex->max_cand, ex->max_nodes);
+        octree_kernel<<<dim3(nl, count), 256, ex->octree_smem, st>>>(S, ex->octree_smem_cand, ex->max_cand, ex->max_nodes, ex->d_octree_scratch.p,
+                                                                     ex->octree_slots, ex->d_counts.p + (size_t)ex->max_images * nl * 2);
         prof_mark(ex, 3);
         if (ex->tma_now)
             blur_kernel<true><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p, ex->blur_maps);
@@ -1493,6 +1555,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     }
     if (const char *env = getenv("SFE_PIPELINE_CHUNKS")) ex->chunks_override = atoi(env);
     if (const char *env = getenv("SFE_NO_TMA")) ex->tma_disabled = atoi(env) != 0;
+    if (const char *env = getenv("SFE_OCTREE_SMEM_CAND")) ex->octree_cand_override = atoi(env);
     build_tables(ex);
     int cap = p->nfeatures;
     for (int l = 0; l < p->nlevels; l++) cap += 4;
@@ -1505,7 +1568,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     if (!ex) return SFE_OK;
     DeviceGuard g(ex->device);
     cudaStreamSynchronize(ex->stream);
-    ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_l0.release(); ex->d_desc.release();
+    ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_l0.release(); ex->d_octree_scratch.release(); ex->d_desc.release();
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release(); ex->d_lv.release();
     ex->d_tiles.release(); ex->d_cells.release(); ex->d_xtab.release(); ex->d_ytab.release();
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
@@ -1641,7 +1704,7 @@ int sfe_extractor_set_async(sfe_extractor *ex, int enable) {
     SFE_CUDA(cudaStreamSynchronize(ex->stream));
     ex->async_dev = enable != 0;
     if (ex->d_counts.p)  // start from clean flags
-        SFE_CUDA(cudaMemset(ex->d_counts.p + (size_t)ex->max_images * ex->prm.nlevels * 2, 0, sizeof(int) * ex->max_images));
+        SFE_CUDA(cudaMemset(ex->d_counts.p + (size_t)ex->max_images * ex->prm.nlevels * 2 + 1, 0, sizeof(int) * ex->max_images));
     return SFE_OK;
 }
 
@@ -1654,7 +1717,7 @@ int sfe_extractor_wait(sfe_extractor *ex) {
     }
     int rc = check_flags(ex, ex->stream, ex->max_images);
     if (ex->async_dev)
-        SFE_CUDA(cudaMemset(ex->d_counts.p + (size_t)ex->max_images * ex->prm.nlevels * 2, 0, sizeof(int) * ex->max_images));
+        SFE_CUDA(cudaMemset(ex->d_counts.p + (size_t)ex->max_images * ex->prm.nlevels * 2 + 1, 0, sizeof(int) * ex->max_images));
     return rc;
 }
 

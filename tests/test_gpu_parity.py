@@ -188,6 +188,19 @@ def test_pipelined_sub_batches_and_load_paths_agree(gpu, oracle, monkeypatch):
         assert np.array_equal(base["kps_l"][f, :len(kl)], kl) and np.array_equal(base["desc_l"][f, :len(kl)], dl)
 
 
+def test_quadtree_spills_to_global_scratch(gpu, oracle, monkeypatch):
+    """Levels with more candidates than the shared-memory arrays hold run the same quadtree code on global scratch."""
+    monkeypatch.setenv("SFE_OCTREE_SMEM_CAND", "512")   # every KITTI level has more candidates than this
+    L, R = synth.stereo_pair(5)
+    ex = api.ORBextractor(max_images=8)            # 2 scratch slots per image slot: 16 for these 16 (image, level) pairs
+    out = ex.stereo_frames(L[None], R[None])
+    ref = oracle.Extractor()
+    for img, kk, dd, nn in ((L, "kps_l", "desc_l", "n_l"), (R, "kps_r", "desc_r", "n_r")):
+        rk, rd = ref.extract(img)
+        assert out[nn][0] == len(rk)
+        assert np.array_equal(out[kk][0, :len(rk)], rk) and np.array_equal(out[dd][0, :len(rk)], rd)
+
+
 def test_pitched_resident_images_and_async_mode(kitti_ex):
     """Resident images with a TMA-friendly row pitch give the bytes of the host path; in asynchronous mode the
     _dev call returns before the kernels finish and wait() reports."""
