@@ -47,51 +47,58 @@ __global__ void __launch_bounds__(256) realign_kernel(const uint8_t *__restrict_
 // outputs touch -- 1.2 source rows per output row instead of 2 -- into shared memory, then combines two
 // rows per output, 4 outputs per thread and one 32-bit store.  Coefficients come from host-built tables.
 // ---------------------------------------------------------------------------------------------
-constexpr int kPyrTileW = 64, kPyrTileH = 32;
+constexpr int kPyrTileW = 64, kPyrTileH = 64;
 
-__global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, int l, const uint2 *__restrict__ xtab,
+struct PyrStep {            // geometry of one resize launch, in the kernel parameters
+    int w, h, pitch, plane_off;      // destination level
+    int src_w, src_pitch, src_plane_off, src_is_input;
+    int xtab_off, ytab_off;
+};
+
+__global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, const uint2 *__restrict__ xtab,
                                                          const uint2 *__restrict__ ytab) {
     extern __shared__ __align__(16) uint16_t pyr_u[];  // [source row][kPyrTileW]
-    const LevelPlan &L = S.lv[l];
     const int x0 = blockIdx.x * kPyrTileW, y0 = blockIdx.y * kPyrTileH, img = blockIdx.z, tid = threadIdx.x;
-    const uint2 *yt = ytab + L.ytab_off;
+    const uint2 *yt = ytab + P.ytab_off;
     const int sy_first = __ldg(&yt[y0]).x & 0xFFFF;                               // rows are monotone in y
-    const int n_rows = (int)(__ldg(&yt[min(y0 + kPyrTileH, L.h) - 1]).x >> 16) - sy_first + 1;
-    int sp;
-    const uint8_t *src = level_pixels(S, l - 1, img, sp);
+    const int n_rows = (int)(__ldg(&yt[min(y0 + kPyrTileH, P.h) - 1]).x >> 16) - sy_first + 1;
+    const int slot = slot_of(S, img);
+    const uint8_t *src;
+    if (P.src_is_input)
+        src = img < S.split ? S.in_a + (size_t)img * S.in_stride : S.in_b + (size_t)(img - S.split) * S.in_stride;
+    else
+        src = S.pyr + (size_t)slot * S.pyr_stride + P.src_plane_off;
     {   // horizontal: thread = output column, walking the source rows
         const int ox = tid & (kPyrTileW - 1);
-        const uint2 xt = __ldg(&xtab[L.xtab_off + min(x0 + ox, L.w - 1)]);
-        const int sx = xt.x, sx1 = min(sx + 1, S.lv[l - 1].w - 1);
-        const int w0 = xt.y & 0xFFFF, w1 = xt.y >> 16;
-        const uint8_t *row = src + (size_t)(sy_first + (tid >> 6)) * sp;
+        const uint2 xt = __ldg(&xtab[P.xtab_off + min(x0 + ox, P.w - 1)]);
+        const int sx = xt.x, d1 = min(sx + 1, P.src_w - 1) - sx;
+        const uint32_t w0 = xt.y & 0xFFFF, w1 = xt.y >> 16;
+        const uint8_t *p = src + (size_t)(sy_first + (tid >> 6)) * P.src_pitch + sx;
+        const int step = 4 * P.src_pitch;
         for (int r = tid >> 6; r < n_rows; r += 4) {
-            pyr_u[r * kPyrTileW + ox] = (uint16_t)((__ldg(row + sx) * w0 + __ldg(row + sx1) * w1) >> 4);
-            row += 4 * sp;
+            pyr_u[r * kPyrTileW + ox] = (uint16_t)((__ldg(p) * w0 + __ldg(p + d1) * w1) >> 4);
+            p += step;
         }
     }
     __syncthreads();
-    // vertical: thread = 4 adjacent outputs on rows ry and ry + 16
+    // vertical: thread = 4 adjacent outputs on rows ry, ry + 16, ry + 32, ry + 48
     const int cg = (tid & 15) * 4, ry = tid >> 4;
-    if (x0 + cg >= L.w) return;
-    uint8_t *dst = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + L.plane_off + x0 + cg;
+    if (x0 + cg >= P.w) return;
+    uint8_t *dst = S.pyr + (size_t)slot * S.pyr_stride + P.plane_off + x0 + cg;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < kPyrTileH / 16; k++) {
         const int oy = y0 + ry + 16 * k;
-        if (oy >= L.h) break;
+        if (oy >= P.h) break;
         const uint2 t = __ldg(&yt[oy]);
         const int r0 = (int)(t.x & 0xFFFF) - sy_first, r1 = (int)(t.x >> 16) - sy_first;
-        const int b0 = t.y & 0xFFFF, b1 = t.y >> 16;
+        const uint32_t b0 = t.y << 16, b1 = t.y & 0xFFFF0000u;  // (b * u) >> 16 == __umulhi(b << 16, u)
         const uint2 A = *(const uint2 *)&pyr_u[r0 * kPyrTileW + cg], B = *(const uint2 *)&pyr_u[r1 * kPyrTileW + cg];
-        const int a[4] = {(int)(A.x & 0xFFFF), (int)(A.x >> 16), (int)(A.y & 0xFFFF), (int)(A.y >> 16)};
-        const int b[4] = {(int)(B.x & 0xFFFF), (int)(B.x >> 16), (int)(B.y & 0xFFFF), (int)(B.y >> 16)};
-        uint32_t packed = 0;
+        const uint32_t a[4] = {A.x & 0xFFFF, A.x >> 16, A.y & 0xFFFF, A.y >> 16};
+        const uint32_t b[4] = {B.x & 0xFFFF, B.x >> 16, B.y & 0xFFFF, B.y >> 16};
+        uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int v = (((b0 * a[i]) >> 16) + ((b1 * b[i]) >> 16) + 2) >> 2;
-            packed |= (uint32_t)min(v, 255) << (8 * i);
-        }
-        *(uint32_t *)(dst + (size_t)oy * L.pitch) = packed;  // pitch is a multiple of 16: pad bytes absorb the tail
+        for (int i = 0; i < 4; i++) v[i] = min((__umulhi(b0, a[i]) + __umulhi(b1, b[i]) + 2) >> 2, 255u);
+        *(uint32_t *)(dst + (size_t)oy * P.pitch) = v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24;  // pitch % 16 == 0: pad absorbs the tail
     }
 }
 
@@ -108,8 +115,9 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, int l, const 
 //   stage 2  cell-local non-max suppression (strict > over 8 neighbours, outside the cell = 0)
 //   retry the whole cell with minThFAST only if nothing survived (:811-816)
 // ---------------------------------------------------------------------------------------------
-// tile row pitch TP (bytes) is a template parameter: 48 for cells up to 43 px wide, 80 up to kMaxSub.
-// shared column = sub-image column + 1, so tested x = 0 sits at column 4 (word aligned).
+// Tile row pitch TP (bytes) is a template parameter: 64 for cells up to 41 px wide, 96 up to kMaxSub.
+// Shared column c of a cell's tile is level column xa + c with xa = (ini_x - 4) rounded down to 16: a TMA box
+// must start on a 16-byte multiple of the row, and stage 0 then works on the level's own 4-pixel words.
 constexpr int kScorePitch = 64;  // >= kMaxSub - 6 + 2
 
 // Compass pre-test of two pixels held in the 16-bit lanes of c (centre) and p0..p3 (compass pixels).
@@ -193,15 +201,17 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
     const int level = C.level, ini_x = C.ini_x, ini_y = C.ini_y, sw = C.sw, sh = C.sh;
     const FastLevel &F = P.lv[level];
     const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    const int xa = (ini_x - 4) & ~15;         // level column of shared column 0 (ini_x >= 16)
+    const int cs = ini_x + 3 - xa;            // shared column of tested x = 0, in [7, 22]
     if (kTma) {
-        // shared column 0 = sub-image column -1 (ini_x >= 16); bytes outside the image arrive as zeros and are never tested
+        // bytes outside the image arrive as zeros and are never tested
         if (tid == 0) {
             mbar_init(&bar, 1);
             mbar_expect_tx(&bar, (uint32_t)(P.tile_rows * TP));
             const bool set_a = img < S.split;
             const CUtensorMap *map = level == 0 ? (set_a ? &M.lv[0] : &M.l0b) : &M.lv[level];
             const int z = level == 0 ? S.in_z0 + (set_a ? img : img - S.split) : slot_of(S, img);
-            tma_load_3d(tile32, map, &bar, ini_x - 1, ini_y, z);
+            tma_load_3d(tile32, map, &bar, xa, ini_y, z);
         }
     } else {
         const uint8_t *src;
@@ -213,16 +223,17 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
             pitch = F.pitch;
             src = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + F.plane_off;
         }
-        src += (size_t)ini_y * pitch + ini_x - 1;  // shared column 0 = sub-image column -1 (ini_x >= 16)
-        // shared columns [0, 4 * nw) cover sub-image columns [-1, sw + 6]; the row has >= 16 px beyond the cell
-        const int nw = min((sw + 8) >> 2, kTileWords), inv = kInv16[nw];
+        src += (size_t)ini_y * pitch + xa;
+        // words up to the one after the last tested pixel's; the row has >= 16 px beyond the cell
+        const int nw = min(((cs + sw - 7) >> 2) + 2, kTileWords), inv = kInv16[nw];
         for (int it = tid; it < sh * nw; it += T) {
             const int r = (it * inv) >> 16, j = it - r * nw;
             tile32[r * kTileWords + j] = ldg_word_at(src + (size_t)r * pitch + 4 * j);
         }
     }
     const int tw = sw - 6, th = sh - 6;  // tested pixels: 3-px margin inside the sub-image
-    const int nq = (tw + 3) >> 2, inv_q = nq > 1 ? kInv16[nq] : 65536, nitems = th * nq;
+    const int jw0 = cs >> 2, nq = ((cs + tw - 1) >> 2) - jw0 + 1;  // level words that hold tested pixels
+    const int inv_q = nq > 1 ? kInv16[nq] : 65536, nitems = th * nq;
     int t = P.ini_th;
     for (int attempt = 0; attempt < 2; attempt++) {
         for (int i = tid; i < (th + 2) * (kScorePitch / 16); i += T) ((uint4 *)score)[i] = make_uint4(0, 0, 0, 0);
@@ -237,18 +248,18 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
             int y = 0, x = 0;
             if (it < nitems) {
                 y = (it * inv_q) >> 16;
-                const int j = it - y * nq;
-                x = 4 * j;
-                const uint32_t *row = tile32 + (y + 3) * kTileWords + j;
-                const uint32_t c = row[1], up = row[1 - 3 * kTileWords], dn = row[1 + 3 * kTileWords];
-                const uint32_t lf = __byte_perm(row[0], c, 0x4321);  // pixels x-3 .. x
-                const uint32_t rt = __byte_perm(c, row[2], 0x6543);  // pixels x+3 .. x+6
+                const int jw = jw0 + it - y * nq;
+                x = 4 * jw - cs;  // tested x of the word's first pixel (negative: the word starts left of the cell)
+                const uint32_t *row = tile32 + (y + 3) * kTileWords + jw;
+                const uint32_t c = row[0], up = row[-3 * kTileWords], dn = row[3 * kTileWords];
+                const uint32_t lf = __byte_perm(row[-1], c, 0x4321);  // pixels x-3 .. x
+                const uint32_t rt = __byte_perm(c, row[1], 0x6543);   // pixels x+3 .. x+6
                 const uint32_t m_lo = compass2(__byte_perm(c, 0, 0x4140), __byte_perm(up, 0, 0x4140), __byte_perm(dn, 0, 0x4140),
                                                __byte_perm(lf, 0, 0x4140), __byte_perm(rt, 0, 0x4140), k2);
                 const uint32_t m_hi = compass2(__byte_perm(c, 0, 0x4342), __byte_perm(up, 0, 0x4342), __byte_perm(dn, 0, 0x4342),
                                                __byte_perm(lf, 0, 0x4342), __byte_perm(rt, 0, 0x4342), k2);
                 mask = ((m_lo >> 15) & 1) | ((m_lo >> 30) & 2) | ((m_hi >> 13) & 4) | ((m_hi >> 28) & 8);
-                mask &= (1u << min(4, tw - x)) - 1;
+                mask &= (0xFu << max(-x, 0)) & ((1u << min(4, tw - x)) - 1);  // pixels of this word inside [0, tw)
             }
             // compaction: one ballot per pixel slot (the list order is irrelevant downstream), one atomic per warp
             const unsigned b0 = __ballot_sync(0xffffffffu, mask & 1), b1 = __ballot_sync(0xffffffffu, mask & 2),
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
             if (lane == 0) base = atomicAdd(&n_pre, c3);
             base = __shfl_sync(0xffffffffu, base, 0);
             const unsigned lt = (1u << lane) - 1;
-            const uint16_t item = (uint16_t)(y << 6 | x);
+            const uint16_t item = (uint16_t)((y << 6) + x);  // bits of a word left of the cell are masked out
             if (mask & 1) pre[base + __popc(b0 & lt)] = item;
             if (mask & 2) pre[base + c0 + __popc(b1 & lt)] = item + 1;
             if (mask & 4) pre[base + c1 + __popc(b2 & lt)] = item + 2;
@@ -276,8 +287,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
                 yx0 = pre[2 * e];
                 yx1 = pre[min(2 * e + 1, np - 1)];
                 int best0, best1;
-                fast_best_x2<TP>(&tile[((yx0 >> 6) + 3) * kTilePitch + (yx0 & 63) + 4],
-                             &tile[((yx1 >> 6) + 3) * kTilePitch + (yx1 & 63) + 4], best0, best1);
+                fast_best_x2<TP>(&tile[((yx0 >> 6) + 3) * kTilePitch + (yx0 & 63) + cs],
+                                 &tile[((yx1 >> 6) + 3) * kTilePitch + (yx1 & 63) + cs], best0, best1);
                 corner0 = best0 > t;
                 corner1 = best1 > t && 2 * e + 1 < np;
                 if (corner0) score[((yx0 >> 6) + 1) * kScorePitch + (yx0 & 63) + 1] = (uint8_t)best0;
@@ -991,7 +1002,6 @@ struct sfe_extractor {
     DevBuf<uint8_t> d_pyr, d_blur, d_in, d_l0, d_desc;  // d_in: images as uploaded (tight), d_l0: pitched level 0
     DevBuf<uint32_t> d_cand, d_kpst;
     DevBuf<int> d_counts;  // cand_count | kp_count | flags
-    DevBuf<LevelPlan> d_lv;
     DevBuf<TilePlan> d_tiles;
     DevBuf<uint2> d_xtab, d_ytab;
     DevBuf<sfe_keypoint> d_kps;
@@ -1178,7 +1188,7 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     ex->fast.ini_th = ex->prm.ini_th_fast;
     ex->fast.min_th = ex->prm.min_th_fast;
     ex->fast.tile_rows = (max_sh + 1) & ~1;  // even: tile_rows * pitch keeps the score array 16-byte aligned
-    ex->fast.tile_pitch = max_sw + 5 <= 48 ? 48 : 80;
+    ex->fast.tile_pitch = max_sw + 23 <= 64 ? 64 : 96;
     ex->fast.score_rows = max_sh - 4;
     ex->fast.list_cap = ((max_sw - 6) * (max_sh - 6) + 7) & ~7;
     ex->fast_smem = (size_t)ex->fast.tile_rows * ex->fast.tile_pitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
@@ -1196,14 +1206,12 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     SFE_CUDA(ex->d_cand.ensure((size_t)ex->cand_stride * n));
     SFE_CUDA(ex->d_kpst.ensure((size_t)ex->kpst_stride * n));
     SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1) + 1));  // cand_count | kp_count | scratch_next | flags
-    SFE_CUDA(ex->d_lv.ensure(kMaxLevels));
     SFE_CUDA(ex->d_tiles.ensure(std::max<size_t>(ex->tiles.size(), 1)));
     SFE_CUDA(ex->d_cells.ensure(std::max<size_t>(ex->cells.size(), 1)));
     if (!ex->cells.empty())
         SFE_CUDA(cudaMemcpyAsync(ex->d_cells.p, ex->cells.data(), sizeof(CellRec) * ex->cells.size(), cudaMemcpyHostToDevice, ex->stream));
     SFE_CUDA(ex->d_xtab.ensure(std::max<size_t>(xtab.size(), 1)));
     SFE_CUDA(ex->d_ytab.ensure(std::max<size_t>(ytab.size(), 1)));
-    SFE_CUDA(cudaMemcpyAsync(ex->d_lv.p, ex->lv, sizeof(LevelPlan) * nl, cudaMemcpyHostToDevice, ex->stream));
     if (!ex->tiles.empty())
         SFE_CUDA(cudaMemcpyAsync(ex->d_tiles.p, ex->tiles.data(), sizeof(TilePlan) * ex->tiles.size(), cudaMemcpyHostToDevice, ex->stream));
     if (!xtab.empty()) {
@@ -1246,7 +1254,7 @@ static ImgSet make_imgset(sfe_extractor *ex, const uint8_t *in_a, const uint8_t 
     S.pyr_stride = ex->pyr_stride;
     S.blur = ex->d_blur.p;
     S.blur_stride = ex->blur_stride;
-    S.lv = ex->d_lv.p;
+    memcpy(S.lv, ex->lv, sizeof(LevelPlan) * nl);
     S.nlevels = nl;
     S.cand = ex->d_cand.p;
     S.cand_stride = ex->cand_stride;
@@ -1304,7 +1312,7 @@ static void prepare_l0_maps(sfe_extractor *ex, const uint8_t *a, const uint8_t *
     ex->tma_now = true;
 }
 
-constexpr bool kFastTma = false;  // the cell box starts at an arbitrary byte: TMA wants 16-byte aligned inner coordinates
+constexpr bool kFastTma = true;
 
 template <int TP>
 static void launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count) {
@@ -1320,14 +1328,16 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     const int nl = ex->prm.nlevels;
     prof_mark(ex, 0);
     for (int l = 1; l < nl; l++) {
-        dim3 grid(div_up(ex->lv[l].w, kPyrTileW), div_up(ex->lv[l].h, kPyrTileH), count);
-        pyr_resize_kernel<<<grid, 256, ex->pyr_smem, st>>>(S, l, ex->d_xtab.p, ex->d_ytab.p);
+        const LevelPlan &D = ex->lv[l], &Q = ex->lv[l - 1];
+        const PyrStep P{D.w, D.h, D.pitch, D.plane_off, Q.w, l == 1 ? S.in_pitch : Q.pitch, Q.plane_off, l == 1, D.xtab_off, D.ytab_off};
+        dim3 grid(div_up(D.w, kPyrTileW), div_up(D.h, kPyrTileH), count);
+        pyr_resize_kernel<<<grid, 256, ex->pyr_smem, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p);
         ex->launches++;
     }
     prof_mark(ex, 1);
     if (ex->fast.n_cells > 0) {
-        if (ex->fast.tile_pitch == 48) launch_fast<48>(ex, st, S, count);
-        else launch_fast<80>(ex, st, S, count);
+        if (ex->fast.tile_pitch == 64) launch_fast<64>(ex, st, S, count);
+        else launch_fast<96>(ex, st, S, count);
         prof_mark(ex, 2);
         {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
             static std::mutex mu;
@@ -1569,7 +1579,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     DeviceGuard g(ex->device);
     cudaStreamSynchronize(ex->stream);
     ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_l0.release(); ex->d_octree_scratch.release(); ex->d_desc.release();
-    ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release(); ex->d_lv.release();
+    ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release();
     ex->d_tiles.release(); ex->d_cells.release(); ex->d_xtab.release(); ex->d_ytab.release();
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
     for (int i = 0; i <= kNumStages; i++)

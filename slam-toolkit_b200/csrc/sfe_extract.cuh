@@ -71,7 +71,7 @@ struct ImgSet {
     size_t pyr_stride;
     uint8_t *blur;               // blurred levels 0.. of all images
     size_t blur_stride;
-    const LevelPlan *lv;
+    LevelPlan lv[kMaxLevels];    // per-level geometry, read from the constant bank (kernel parameters)
     int nlevels;
     uint32_t *cand;              // packed candidates: resp << 24 | y << 12 | x (window-relative)
     int cand_stride;
