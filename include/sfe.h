@@ -199,6 +199,18 @@ int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t
                              double best12_threshold, int32_t *kp_to_query_dev,
                              int32_t *kp_dist_dev);
 
+/* Sharded ProjectionMatch (map points partitioned over GPUs, frame replicated): each shard emits per keypoint
+ * the key (dist << 32 | ~global map-point index) of its best accepted query -- the minimum over shards is the
+ * reference's "smaller distance, later query wins ties" (src/matcher.cpp:197-204) -- keys are exchanged with an
+ * all-gather and merged + decoded by sfe_projection_merge_dev (keys_dev: shards x m_kps). */
+int sfe_projection_match_keys_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev,
+                                  const uint8_t *skip_dev, int n, int64_t idx_base, const double rt[12],
+                                  const sfe_camera *cam, const sfe_keypoint *kps_dev,
+                                  const uint8_t *kp_desc_dev, int m_kps, double radius,
+                                  double best12_threshold, uint64_t *keys_dev /* m_kps */);
+int sfe_projection_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int m_kps,
+                             int32_t *kp_to_query_dev, int32_t *kp_dist_dev);
+
 /* Brute-force top-2 over a resident descriptor database shard.
  * idx_base = global index of the shard's first row (multi-GPU sharding). */
 int sfe_db_create(sfe_matcher *m, const uint8_t *desc_host, int64_t rows, int64_t idx_base,

@@ -97,6 +97,8 @@ SIGNATURES = {
     "sfe_stereo_match": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(StereoParams), _vp, _vp]),
     "sfe_projection_match": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
     "sfe_projection_match_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
+    "sfe_projection_match_keys_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp]),
+    "sfe_projection_merge_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "sfe_db_create": (_i, [_vp, _vp, _i64, _i64, _pp]),
     "sfe_db_destroy": (_i, [_vp]),
     "sfe_knn2": (_i, [_vp, _vp, _vp, _i, _vp]),
@@ -458,6 +460,17 @@ class Matcher:
         rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
         _check(lib().sfe_projection_match_dev(self.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n, _p(rt), C.byref(camera),
                                               _p(kps_ptr), _p(kp_desc_ptr), m, radius, best12, _p(to_q_ptr), _p(dist_ptr)))
+
+    def projection_match_keys_dev(self, xw_ptr, mp_desc_ptr, skip_ptr, n, idx_base, Tcw, camera, kps_ptr, kp_desc_ptr, m,
+                                  radius, keys_ptr, best12=0.5):
+        """One shard of a sharded ProjectionMatch: map points [idx_base, idx_base + n) -> m per-keypoint keys."""
+        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        _check(lib().sfe_projection_match_keys_dev(self.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n, idx_base, _p(rt),
+                                                   C.byref(camera), _p(kps_ptr), _p(kp_desc_ptr), m, radius, best12,
+                                                   _p(keys_ptr)))
+
+    def projection_merge_dev(self, keys_ptr, shards, m, to_q_ptr, dist_ptr):
+        _check(lib().sfe_projection_merge_dev(self.h, _p(keys_ptr), shards, m, _p(to_q_ptr), _p(dist_ptr)))
 
     def create_db(self, desc, idx_base=0):
         return DescriptorDB(self, desc, idx_base)

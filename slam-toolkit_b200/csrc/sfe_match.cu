@@ -212,7 +212,7 @@ struct ProjParams {
     double radius, ratio;
 };
 
-__global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjParams P, int n,
+__global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjParams P, int n, uint32_t idx_base,
                                                                const double *__restrict__ xw,
                                                                const uint8_t *__restrict__ mp_desc,
                                                                const uint8_t *__restrict__ skip,
@@ -265,16 +265,18 @@ __global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjPar
     if (d0 < d1 * P.ratio) {
         // :197-204 processed sequentially keeps the smaller distance and lets the LATER query win a
         // tie: that is the minimum of (dist, -query) over all accepted queries of a keypoint
-        const unsigned long long key = (unsigned long long)(k0 >> 16) << 32 | (0xFFFFFFFFu - (uint32_t)i);
+        const unsigned long long key = (unsigned long long)(k0 >> 16) << 32 | (0xFFFFFFFFu - (idx_base + (uint32_t)i));
         atomicMin(&best[k0 & 0xFFFF], key);
     }
 }
 
-__global__ void projection_decode_kernel(int m, const unsigned long long *__restrict__ best, int32_t *__restrict__ to_query,
-                                         int32_t *__restrict__ dist) {
+// keys of `shards` map-point shards (shards x m) -> per keypoint the minimum (dist, -query) key, decoded
+__global__ void projection_decode_kernel(int m, int shards, const unsigned long long *__restrict__ best,
+                                         int32_t *__restrict__ to_query, int32_t *__restrict__ dist) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= m) return;
-    const unsigned long long k = best[j];
+    unsigned long long k = best[j];
+    for (int s = 1; s < shards; s++) k = min(k, best[(size_t)s * m + j]);
     const bool none = k == ~0ull;
     to_query[j] = none ? -1 : (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu));
     if (dist) dist[j] = none ? -1 : (int32_t)(k >> 32);
@@ -373,9 +375,12 @@ struct sfe_db {
     int64_t rows = 0, idx_base = 0;
 };
 
+// keys_out != nullptr: leave the per-keypoint (dist << 32 | ~global query) keys there (one shard's contribution to a
+// sharded match) instead of decoding them
 static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
                            const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
-                           int m_kps, double radius, double ratio, int32_t *to_query, int32_t *dist) {
+                           int m_kps, double radius, double ratio, int32_t *to_query, int32_t *dist, uint32_t idx_base = 0,
+                           unsigned long long *keys_out = nullptr) {
     cudaStream_t st = m->stream;
     if (m_kps == 0) return SFE_OK;
     KpGrid G;
@@ -385,11 +390,12 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
     const int cells = G.gw * G.gh;
     SFE_CUDA(m->d_grid.ensure((size_t)2 * cells + 1 + m_kps));
     SFE_CUDA(m->d_best.ensure(m_kps));
+    unsigned long long *best = keys_out ? keys_out : m->d_best.p;
     G.cell_start = m->d_grid.p;
     G.cell_fill = m->d_grid.p + cells + 1;
     G.order = m->d_grid.p + 2 * cells + 1;
     SFE_CUDA(cudaMemsetAsync(G.cell_start, 0, sizeof(int) * (cells + 1), st));
-    SFE_CUDA(cudaMemsetAsync(m->d_best.p, 0xFF, sizeof(unsigned long long) * m_kps, st));
+    SFE_CUDA(cudaMemsetAsync(best, 0xFF, sizeof(unsigned long long) * m_kps, st));
     grid_count_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
     grid_scan_kernel<<<1, 256, 0, st>>>(G);
     grid_fill_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
@@ -400,11 +406,13 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
         P.cam = *cam;
         P.radius = radius;
         P.ratio = ratio;
-        projection_match_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, n, xw, mp_desc, skip, kps, kp_desc, m->d_best.p);
+        projection_match_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, n, idx_base, xw, mp_desc, skip, kps, kp_desc, best);
         m->launches++;
     }
-    projection_decode_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(m_kps, m->d_best.p, to_query, dist);
-    m->launches++;
+    if (!keys_out) {
+        projection_decode_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(m_kps, 1, best, to_query, dist);
+        m->launches++;
+    }
     SFE_CUDA(cudaGetLastError());
     return SFE_OK;
 }
@@ -549,6 +557,34 @@ int sfe_projection_match(sfe_matcher *m, const double *xw, const uint8_t *mp_des
     SFE_CUDA(cudaMemcpyAsync(kp_to_query, m->d_idx.p, sizeof(int32_t) * m_kps, cudaMemcpyDeviceToHost, st));
     if (kp_dist) SFE_CUDA(cudaMemcpyAsync(kp_dist, m->d_dist.p, sizeof(int32_t) * m_kps, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+int sfe_projection_match_keys_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev,
+                                  int n, int64_t idx_base, const double rt[12], const sfe_camera *cam,
+                                  const sfe_keypoint *kps_dev, const uint8_t *kp_desc_dev, int m_kps, double radius,
+                                  double best12_threshold, uint64_t *keys_dev) {
+    SFE_REQUIRE(m && rt && cam && n >= 0 && m_kps >= 1 && keys_dev && kps_dev && kp_desc_dev, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(n == 0 || (xw_dev && mp_desc_dev), SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(m_kps < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per frame");
+    SFE_REQUIRE(idx_base >= 0 && idx_base + n < (1ll << 31), SFE_ERR_UNSUPPORTED, "global map-point index must fit int32");
+    DeviceGuard g(m->device);
+    int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, rt, cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold,
+                             nullptr, nullptr, (uint32_t)idx_base, (unsigned long long *)keys_dev);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    return SFE_OK;
+}
+
+int sfe_projection_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int m_kps, int32_t *kp_to_query_dev,
+                             int32_t *kp_dist_dev) {
+    SFE_REQUIRE(m && keys_dev && kp_to_query_dev && shards >= 1 && m_kps >= 1, SFE_ERR_BAD_ARG, "bad argument");
+    DeviceGuard g(m->device);
+    projection_decode_kernel<<<div_up(m_kps, 256), 256, 0, m->stream>>>(m_kps, shards, (const unsigned long long *)keys_dev,
+                                                                         kp_to_query_dev, kp_dist_dev);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
 
