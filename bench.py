@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--frames", type=int, default=64, help="stereo frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=128, help="stereo frames per step per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-frames", type=int, default=0, help="stereo frames in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -294,6 +294,16 @@ def main():
     top = max(stage_ms, key=lambda k: stage_ms[k])
     top_ms = stage_ms[top] / max(calls, 1) / launches_per_step[top]
     achieved = alg_bytes[top] / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
+    # DRAM traffic of that kernel per launch from the committed ncu --set full capture (dram__bytes_read + write, per image
+    # there, scaled to this run's images per launch); well above the algorithmic bytes would mean wasted re-reads
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
+        per_img = tj["kernels"][top]["dram_bytes_per_image"]
+        traffic = per_img * (F if top == "stereo_match" else 2 * F) / launches_per_step[top]
+        traffic_src = tj["source"]
+    except Exception:
+        pass
     line = {"metric": "orb_extract_match_stereo_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -304,9 +314,10 @@ def main():
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": alg_bytes[top], "peak_source": peak_src,
                          "whole_step_achieved": value / world * B_FRAME / 1e9, "whole_step_frac": value / world * B_FRAME / 1e9 / hbm_peak,
-                         "note": "extraction is integer/shared-memory bound, not HBM bound (SURVEY.md §8d)"},
+                         "note": "extraction is integer-issue bound, not HBM bound (SURVEY.md §8d): see profiles/ for pipe utilisation"},
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
             "keypoints_per_frame": n_kps / F, "matches_per_s": value * n_match / F}
     if not args.no_cpu_baseline:
