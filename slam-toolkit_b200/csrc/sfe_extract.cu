@@ -163,17 +163,6 @@ __device__ __forceinline__ void fast_best_x2(const uint8_t *c0, const uint8_t *c
     best1 = max(v1 - (int)(min_of_max >> 16), (int)(max_of_min >> 16) - v1);
 }
 
-// append `item` to list[] for the lanes with pred set: one shared atomic per warp
-__device__ __forceinline__ void warp_append(bool pred, uint16_t item, uint16_t *list, int *counter) {
-    const unsigned m = __ballot_sync(0xffffffffu, pred);
-    if (m == 0) return;
-    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) list[base + __popc(m & ((1u << lane) - 1))] = item;
-}
-
 // 16.16 reciprocals of the small row lengths the kernel divides by: floor(i / n) == (i * kInv16[n]) >> 16 for i < 3640
 __constant__ unsigned short kInv16[24] = {0,     0,     32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958,
                                           5462,  5042,  4682,  4370,  4097,  3856,  3641,  3450, 3277, 3121, 2979, 2850};
@@ -242,7 +231,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
         if (kTma && attempt == 0) mbar_wait(&bar, 0);  // the barrier was initialised by thread 0 before the sync above
         // stage 0: compass pre-test, one aligned word of 4 centre pixels per thread
         const uint32_t k2 = (uint32_t)(0x7FFF - t) * 0x10001u;
-        for (int i0 = 0; i0 < nitems; i0 += T) {  // whole warps iterate together (ballot inside)
+        for (int i0 = 0; i0 < nitems; i0 += T) {
             const int it = i0 + tid;
             uint32_t mask = 0;
             int y = 0, x = 0;
@@ -261,20 +250,16 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
                 mask = ((m_lo >> 15) & 1) | ((m_lo >> 30) & 2) | ((m_hi >> 13) & 4) | ((m_hi >> 28) & 8);
                 mask &= (0xFu << max(-x, 0)) & ((1u << min(4, tw - x)) - 1);  // pixels of this word inside [0, tw)
             }
-            // compaction: one ballot per pixel slot (the list order is irrelevant downstream), one atomic per warp
-            const unsigned b0 = __ballot_sync(0xffffffffu, mask & 1), b1 = __ballot_sync(0xffffffffu, mask & 2),
-                           b2 = __ballot_sync(0xffffffffu, mask & 4), b3 = __ballot_sync(0xffffffffu, mask & 8);
-            if ((b0 | b1 | b2 | b3) == 0) continue;
-            const int c0 = __popc(b0), c1 = c0 + __popc(b1), c2 = c1 + __popc(b2), c3 = c2 + __popc(b3);
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&n_pre, c3);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            const unsigned lt = (1u << lane) - 1;
-            const uint16_t item = (uint16_t)((y << 6) + x);  // bits of a word left of the cell are masked out
-            if (mask & 1) pre[base + __popc(b0 & lt)] = item;
-            if (mask & 2) pre[base + c0 + __popc(b1 & lt)] = item + 1;
-            if (mask & 4) pre[base + c1 + __popc(b2 & lt)] = item + 2;
-            if (mask & 8) pre[base + c2 + __popc(b3 & lt)] = item + 3;
+            // compaction: the list order is irrelevant downstream and only a few lanes per warp hold survivors, so a
+            // shared-memory atomic per such lane costs fewer issue slots than a ballot / prefix scheme
+            if (mask) {
+                int pos = atomicAdd(&n_pre, __popc(mask));
+                const uint16_t item = (uint16_t)((y << 6) + x);  // bits of a word left of the cell are masked out
+                if (mask & 1) pre[pos++] = item;
+                if (mask & 2) pre[pos++] = item + 1;
+                if (mask & 4) pre[pos++] = item + 2;
+                if (mask & 8) pre[pos] = item + 3;
+            }
         }
         __syncthreads();
         // stage 1: exact score, two survivors per thread; corner at threshold t iff best > t
@@ -294,8 +279,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
                 if (corner0) score[((yx0 >> 6) + 1) * kScorePitch + (yx0 & 63) + 1] = (uint8_t)best0;
                 if (corner1) score[((yx1 >> 6) + 1) * kScorePitch + (yx1 & 63) + 1] = (uint8_t)best1;
             }
-            warp_append(corner0, yx0, det, &n_det);
-            warp_append(corner1, yx1, det, &n_det);
+            if (corner0) det[atomicAdd(&n_det, 1)] = yx0;
+            if (corner1) det[atomicAdd(&n_det, 1)] = yx1;
         }
         __syncthreads();
         // stage 2: non-max suppression inside this cell only
@@ -310,7 +295,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
                 keep = s > sc[-1] && s > sc[1] && s > sc[-kScorePitch - 1] && s > sc[-kScorePitch] &&
                        s > sc[-kScorePitch + 1] && s > sc[kScorePitch - 1] && s > sc[kScorePitch] && s > sc[kScorePitch + 1];
             }
-            warp_append(keep, yx, surv, &n_surv);
+            if (keep) surv[atomicAdd(&n_surv, 1)] = yx;
         }
         __syncthreads();
         if (n_surv > 0 || P.min_th >= t) break;  // :811-816: retry with minThFAST only when nothing survived
@@ -710,7 +695,8 @@ __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__r
     const TilePlan t = tiles[blockIdx.x];
     const int img = blockIdx.y, tid = threadIdx.x, l = t.level;
     const int slot = slot_of(S, img);
-    if (S.kp_count[slot * S.nlevels + l] == 0) return;  // the reference blurs only levels with keypoints
+    // (the reference blurs only levels that kept keypoints, :1085; blurring all of them changes no output and lets
+    // this kernel run beside FAST / quadtree instead of after them)
     const LevelPlan &L = S.lv[l];
     const int w = L.w, h = L.h, x_first = t.x0 - kBlurLead, y_first = t.y0 - 3;
     if (kTma) {
@@ -971,6 +957,10 @@ struct sfe_extractor {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of the pipelined host entry points
     cudaStream_t stream2 = nullptr;                 // second compute stream: odd sub-batches (their kernels fill the
                                                     // tail waves of the even ones)
+    cudaStream_t aux[2] = {nullptr, nullptr};       // per compute stream: the blur runs beside FAST + quadtree
+    cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
+    bool overlap_blur = false;                      // SFE_OVERLAP_BLUR=1; measured on B200: no gain (both kernels fill the
+                                                    // machine on their own, the block scheduler runs them back to back)
     cudaEvent_t ev_start = nullptr;
     bool async_dev = false;                         // _dev entry points return after enqueueing (sfe_extractor_wait)
     cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
@@ -1336,6 +1326,23 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     }
     prof_mark(ex, 1);
     if (ex->fast.n_cells > 0) {
+        // The blur only needs the pyramid, so it can run on a side stream beside FAST and the quadtree and join before
+        // the descriptors (opt-in: it bought nothing on B200, see overlap_blur).  Serial when stages are timed.
+        const int si = st == ex->stream2 ? 1 : 0;
+        const bool fork = ex->overlap_blur && !ex->profiling;
+        cudaStream_t sb = fork ? ex->aux[si] : st;
+        auto launch_blur = [&]() {
+            if (ex->tma_now)
+                blur_kernel<true><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
+            else
+                blur_kernel<false><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
+        };
+        if (fork) {
+            SFE_CUDA(cudaEventRecord(ex->ev_fork[si], st));
+            SFE_CUDA(cudaStreamWaitEvent(sb, ex->ev_fork[si], 0));
+            launch_blur();
+            SFE_CUDA(cudaEventRecord(ex->ev_join[si], sb));
+        }
         if (ex->fast.tile_pitch == 64) launch_fast<64>(ex, st, S, count);
         else launch_fast<96>(ex, st, S, count);
         prof_mark(ex, 2);
@@ -1351,10 +1358,8 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         octree_kernel<<<dim3(nl, count), 256, ex->octree_smem, st>>>(S, ex->octree_smem_cand, ex->max_cand, ex->max_nodes, ex->d_octree_scratch.p,
                                                                      ex->octree_slots, ex->d_counts.p + (size_t)ex->max_images * nl * 2);
         prof_mark(ex, 3);
-        if (ex->tma_now)
-            blur_kernel<true><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p, ex->blur_maps);
-        else
-            blur_kernel<false><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, st>>>(S, ex->d_tiles.p, ex->blur_maps);
+        if (fork) SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[si], 0));
+        else launch_blur();
         prof_mark(ex, 4);
         ex->launches += 3;
     } else {
@@ -1556,6 +1561,10 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
               cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ex->stream2, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ex->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+        ok = cudaStreamCreateWithFlags(&ex->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ex->ev_fork[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ex->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < kMaxChunks && ok; i++)
         ok = cudaEventCreateWithFlags(&ex->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ex->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1566,6 +1575,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     }
     if (const char *env = getenv("SFE_PIPELINE_CHUNKS")) ex->chunks_override = atoi(env);
     if (const char *env = getenv("SFE_NO_TMA")) ex->tma_disabled = atoi(env) != 0;
+    if (const char *env = getenv("SFE_OVERLAP_BLUR")) ex->overlap_blur = atoi(env) != 0;
     if (const char *env = getenv("SFE_OCTREE_SMEM_CAND")) ex->octree_cand_override = atoi(env);
     build_tables(ex);
     int cap = p->nfeatures;
@@ -1588,6 +1598,11 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     for (int i = 0; i < kMaxChunks; i++) {
         if (ex->ev_in[i]) cudaEventDestroy(ex->ev_in[i]);
         if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (ex->ev_fork[i]) cudaEventDestroy(ex->ev_fork[i]);
+        if (ex->ev_join[i]) cudaEventDestroy(ex->ev_join[i]);
+        if (ex->aux[i]) cudaStreamDestroy(ex->aux[i]);
     }
     if (ex->ev_start) cudaEventDestroy(ex->ev_start);
     if (ex->stream2) cudaStreamDestroy(ex->stream2);
