@@ -949,14 +949,16 @@ using namespace sfe;
 
 enum { kStagePyramid, kStageFast, kStageQuadtree, kStageBlur, kStageDescribe, kStageStereo, kNumStages };
 constexpr int kOctreeSmemCand = 3072;
+constexpr int kComputeStreams = 4;
 constexpr int kMaxChunks = 16;  // sub-batches one pipelined host call is cut into
 
 struct sfe_extractor {
     int device = 0;
     cudaStream_t stream = nullptr;                  // compute (and everything, for unpipelined calls)
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // copy streams of the pipelined host entry points
-    cudaStream_t stream2 = nullptr;                 // second compute stream: odd sub-batches (their kernels fill the
-                                                    // tail waves of the even ones)
+    cudaStream_t extra[kComputeStreams - 1] = {};   // further compute streams: sub-batch c runs on stream c % n_compute, so the
+                                                    // kernels of one sub-batch fill the tail waves / latency-bound stages of others
+    int n_compute = 3;                              // SFE_COMPUTE_STREAMS
     cudaStream_t aux[2] = {nullptr, nullptr};       // per compute stream: the blur runs beside FAST + quadtree
     cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
     bool overlap_blur = false;                      // SFE_OVERLAP_BLUR=1; measured on B200: no gain (both kernels fill the
@@ -965,6 +967,8 @@ struct sfe_extractor {
     bool async_dev = false;                         // _dev entry points return after enqueueing (sfe_extractor_wait)
     cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
     int chunks_override = 0;                        // SFE_PIPELINE_CHUNKS
+    bool trace = false;                             // SFE_TRACE=1: per-sub-batch timeline of the host pipeline on stderr
+    cudaEvent_t tr_ev[3 * kMaxChunks + 1] = {};
     sfe_extractor_params prm{};
     float scale[kMaxLevels], inv_scale[kMaxLevels], sigma2[kMaxLevels], inv_sigma2[kMaxLevels];
     int quota[kMaxLevels];
@@ -1328,8 +1332,8 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     if (ex->fast.n_cells > 0) {
         // The blur only needs the pyramid, so it can run on a side stream beside FAST and the quadtree and join before
         // the descriptors (opt-in: it bought nothing on B200, see overlap_blur).  Serial when stages are timed.
-        const int si = st == ex->stream2 ? 1 : 0;
-        const bool fork = ex->overlap_blur && !ex->profiling;
+        const int si = 0;
+        const bool fork = ex->overlap_blur && !ex->profiling && st == ex->stream;
         cudaStream_t sb = fork ? ex->aux[si] : st;
         auto launch_blur = [&]() {
             if (ex->tma_now)
@@ -1479,15 +1483,20 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
     if (piped) {
         ex->profiling = false;  // per-stage events describe one unpipelined batch
         SFE_CUDA(cudaEventRecord(ex->ev_start, ex->stream));  // the counter reset precedes every sub-batch
-        SFE_CUDA(cudaStreamWaitEvent(ex->stream2, ex->ev_start, 0));
+        for (int i = 0; i + 1 < ex->n_compute; i++) SFE_CUDA(cudaStreamWaitEvent(ex->extra[i], ex->ev_start, 0));
     }
+    int bound[kMaxChunks + 1];  // sub-batch boundaries (an uneven split -- small first sub-batch -- measured slower)
+    for (int c = 0; c <= nch; c++) bound[c] = (int)((long long)frames * c / nch);
+    if (ex->trace) cudaEventRecord(ex->tr_ev[3 * kMaxChunks], sin);
     for (int c = 0; c < nch && rc == SFE_OK; c++) {
-        const int f0 = (int)((long long)frames * c / nch), f1 = (int)((long long)frames * (c + 1) / nch), fc = f1 - f0;
-        cudaStream_t sc = (c & 1) ? ex->stream2 : ex->stream;
+        const int f0 = bound[c], f1 = bound[c + 1], fc = f1 - f0;
+        if (fc <= 0) continue;
+        cudaStream_t sc = piped && c % ex->n_compute ? ex->extra[c % ex->n_compute - 1] : ex->stream;
         if ((rc = upload_images(ex, sin, left + (size_t)f0 * image_stride, image_stride, fc, w, h, stride, f0)) != SFE_OK) break;
         if (stereo && (rc = upload_images(ex, sin, right + (size_t)f0 * image_stride, image_stride, fc, w, h, stride,
                                           frames + f0)) != SFE_OK)
             break;
+        if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c], sin);
         if (piped) {
             SFE_CUDA(cudaEventRecord(ex->ev_in[c], sin));
             SFE_CUDA(cudaStreamWaitEvent(sc, ex->ev_in[c], 0));
@@ -1504,6 +1513,7 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
             ex->launches++;
             SFE_CUDA(cudaGetLastError());
         }
+        if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 1], sc);
         if (piped) {
             SFE_CUDA(cudaEventRecord(ex->ev_done[c], sc));
             SFE_CUDA(cudaStreamWaitEvent(sout, ex->ev_done[c], 0));
@@ -1518,10 +1528,13 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
             if (stereo_dist)
                 SFE_CUDA(cudaMemcpyAsync(stereo_dist + o, ex->d_sdist.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
         }
+        if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 2], sout);
     }
     ex->profiling = prof;
     if (rc != SFE_OK) {
-        cudaStreamSynchronize(sin); cudaStreamSynchronize(ex->stream); cudaStreamSynchronize(ex->stream2); cudaStreamSynchronize(sout);
+        cudaStreamSynchronize(sin); cudaStreamSynchronize(ex->stream);
+        for (auto &e : ex->extra) cudaStreamSynchronize(e);
+        cudaStreamSynchronize(sout);
         return rc;
     }
     SFE_CUDA(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
@@ -1529,7 +1542,18 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
     ex->last = B;
     if (!stereo) ex->last.split = images;  // one set: every image reads in_a
     ex->last_count = images;
-    return check_flags(ex, sout, images);  // sout is behind every sub-batch
+    rc = check_flags(ex, sout, images);  // sout is behind every sub-batch
+    if (ex->trace) {
+        fprintf(stderr, "sfe trace: %d frames in %d sub-batches (ms since the first upload was queued)\n", frames, nch);
+        for (int c = 0; c < nch; c++) {
+            float a = 0, b = 0, d = 0;
+            cudaEventElapsedTime(&a, ex->tr_ev[3 * kMaxChunks], ex->tr_ev[3 * c]);
+            cudaEventElapsedTime(&b, ex->tr_ev[3 * kMaxChunks], ex->tr_ev[3 * c + 1]);
+            cudaEventElapsedTime(&d, ex->tr_ev[3 * kMaxChunks], ex->tr_ev[3 * c + 2]);
+            fprintf(stderr, "  sub-batch %2d frames [%3d,%3d): uploaded %.3f  computed %.3f  downloaded %.3f\n", c, bound[c], bound[c + 1], a, b, d);
+        }
+    }
+    return rc;
 }
 
 extern "C" {
@@ -1559,8 +1583,8 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     }
     bool ok = cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaStreamCreateWithFlags(&ex->stream2, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ex->ev_start, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kComputeStreams - 1 && ok; i++) ok = cudaStreamCreateWithFlags(&ex->extra[i], cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; i++)
         ok = cudaStreamCreateWithFlags(&ex->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ex->ev_fork[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -1576,6 +1600,10 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_PIPELINE_CHUNKS")) ex->chunks_override = atoi(env);
     if (const char *env = getenv("SFE_NO_TMA")) ex->tma_disabled = atoi(env) != 0;
     if (const char *env = getenv("SFE_OVERLAP_BLUR")) ex->overlap_blur = atoi(env) != 0;
+    if (const char *env = getenv("SFE_TRACE")) ex->trace = atoi(env) != 0;
+    if (const char *env = getenv("SFE_COMPUTE_STREAMS")) ex->n_compute = std::max(1, std::min(atoi(env), kComputeStreams));
+    if (ex->trace)
+        for (auto &e : ex->tr_ev) cudaEventCreate(&e);
     if (const char *env = getenv("SFE_OCTREE_SMEM_CAND")) ex->octree_cand_override = atoi(env);
     build_tables(ex);
     int cap = p->nfeatures;
@@ -1599,13 +1627,16 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
         if (ex->ev_in[i]) cudaEventDestroy(ex->ev_in[i]);
         if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
     }
+    for (auto &e : ex->tr_ev)
+        if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (ex->ev_fork[i]) cudaEventDestroy(ex->ev_fork[i]);
         if (ex->ev_join[i]) cudaEventDestroy(ex->ev_join[i]);
         if (ex->aux[i]) cudaStreamDestroy(ex->aux[i]);
     }
     if (ex->ev_start) cudaEventDestroy(ex->ev_start);
-    if (ex->stream2) cudaStreamDestroy(ex->stream2);
+    for (auto &e : ex->extra)
+        if (e) cudaStreamDestroy(e);
     if (ex->s_h2d) cudaStreamDestroy(ex->s_h2d);
     if (ex->s_d2h) cudaStreamDestroy(ex->s_d2h);
     cudaStreamDestroy(ex->stream);
