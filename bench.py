@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=0, help="stereo frames in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one handle each) issuing the e2e calls")
+    ap.add_argument("--knn-rows", type=int, default=10_000_000, help="rows of the descriptor map of the Hamming leg (0 = skip)")
     ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples (0 = no sampling)")
     return ap.parse_args()
 
@@ -170,6 +171,55 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def hamming_leg(args, dev, rank, world, dist):
+    """BASELINE config 4 beside the headline: brute-force Hamming top-2 of Q queries against a 10 M-row descriptor map
+    sharded by rows over the ranks (all-gather of the per-rank top-2 keys + merge kernel).  Q = 2000 is `popc`-bound
+    (8 popc per pair), Q = 1 streams the map once: that one is the GB/s-vs-HBM figure."""
+    from slam_toolkit_b200 import api, sharding, synth
+    rows = args.knn_rows
+    a, b = sharding.block(rows, world, rank)
+    rng = np.random.default_rng(1234 + rank)
+    local = rng.integers(0, 256, (b - a, 32), dtype=np.uint8)
+    m = api.Matcher(dev)
+    sd = sharding.ShardedDatabase(m, local, rows)
+    queries, _ = synth.knn_queries(local[:100_000], 2000, seed=5678)   # the same on every rank only at world == 1: fine for timing
+    if dist is not None:
+        import torch
+        qt = torch.from_numpy(queries).cuda(dev)
+        dist.broadcast(qt, 0)
+        queries = qt.cpu().numpy()
+    sd.knn2(queries)
+    reps = 5
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out = sd.knn2(queries)
+    dt = (time.perf_counter() - t0) / reps
+    # streaming pass: one query, resident, kernel time by CUDA events on the matcher's stream
+    dq, keys = api.DeviceBuffer(32, dev).upload(queries[:1]), api.DeviceBuffer(16, dev)
+    m.knn2_dev(sd.db, dq.ptr, 1, keys.ptr)
+    e0, e1 = api.Event(dev), api.Event(dev)
+    m.set_async(True)
+    e0.record(m)
+    for _ in range(50):
+        m.knn2_dev(sd.db, dq.ptr, 1, keys.ptr)
+    e1.record(m)
+    m.wait()
+    m.set_async(False)
+    ms1 = e0.elapsed_ms(e1) / 50
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt, ms1], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, ms1 = t.tolist()
+    gbs1 = world * (b - a) * 32 / (ms1 / 1e3) / 1e9
+    return {"map_rows": rows, "sharding": f"{world} row shard(s), all-gather of 2 keys per query + merge",
+            "q2000_ms_per_batch": dt * 1e3, "q2000_pair_distances_per_s": 2000 * rows / dt,
+            "q2000_algorithmic_gbs": (32 * rows + 48 * 2000) / dt / 1e9,
+            "q1_stream_ms": ms1, "q1_stream_gbs": gbs1, "accepted_ratio_test": float((2 * out[:, 1] < out[:, 3]).mean())}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -286,6 +336,7 @@ def main():
     barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    hamming = hamming_leg(args, dev, rank, world, dist) if args.knn_rows > 0 else None
     h2d = 2 * F * W * H
     d2h = sum(v.nbytes for v in out.values())
 
@@ -344,6 +395,9 @@ def main():
                          "note": "extraction is integer-issue bound, not HBM bound (SURVEY.md §8d): see profiles/ for pipe utilisation"},
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
             "keypoints_per_frame": n_kps / F, "matches_per_s": value * n_match / F}
+    if hamming is not None:
+        hamming["q1_stream_frac_of_hbm_peak"] = hamming["q1_stream_gbs"] / (world * hbm_peak)
+        line["hamming"] = hamming
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         frames = args.cpu_frames or 16 * cores   # ~1.5 s per core: 10-30 s of CPU work in all

@@ -175,6 +175,9 @@ int sfe_hamming256(const void *a, const void *b); /* DescriptorDistance of two 3
 int sfe_matcher_create(int device, sfe_matcher **out);
 int sfe_matcher_destroy(sfe_matcher *m);
 int sfe_matcher_launches(const sfe_matcher *m, int64_t *launches);
+/* as sfe_extractor_set_async: the matcher's _dev entry points return once enqueued; sfe_matcher_wait synchronises */
+int sfe_matcher_set_async(sfe_matcher *m, int enable);
+int sfe_matcher_wait(sfe_matcher *m);
 
 /* StereoMatch on one frame's keypoints (host buffers) */
 int sfe_stereo_match(sfe_matcher *m, const sfe_keypoint *kps_l, const uint8_t *desc_l, int n_l,

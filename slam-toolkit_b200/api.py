@@ -94,6 +94,8 @@ SIGNATURES = {
     "sfe_matcher_create": (_i, [_i, _pp]),
     "sfe_matcher_destroy": (_i, [_vp]),
     "sfe_matcher_launches": (_i, [_vp, C.POINTER(_i64)]),
+    "sfe_matcher_set_async": (_i, [_vp, _i]),
+    "sfe_matcher_wait": (_i, [_vp]),
     "sfe_stereo_match": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, C.POINTER(StereoParams), _vp, _vp]),
     "sfe_projection_match": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
     "sfe_projection_match_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
@@ -428,6 +430,12 @@ class Matcher:
         n = C.c_int64()
         _check(lib().sfe_matcher_launches(self.h, C.byref(n)))
         return n.value
+
+    def set_async(self, enable=True):
+        _check(lib().sfe_matcher_set_async(self.h, int(enable)))
+
+    def wait(self):
+        _check(lib().sfe_matcher_wait(self.h))
 
     def StereoMatch(self, kps_l, desc_l, kps_r, desc_r, params=None):
         """-> (stereo_indices, distances): right index or -1 per left keypoint (src/matcher.cpp:54-132)."""

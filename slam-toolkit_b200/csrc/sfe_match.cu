@@ -325,20 +325,106 @@ __global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint8_t
     }
 }
 
-// lexicographic (dist, global index) top-2 over `parts` candidate pairs per query
-__global__ void knn2_merge_kernel(const unsigned long long *__restrict__ part, int parts, int q,
-                                  unsigned long long *__restrict__ keys_out, int32_t *__restrict__ quad_out) {
-    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (qi >= q) return;
-    unsigned long long k0 = ~0ull, k1 = ~0ull;
-    for (int p = 0; p < parts; p++) {
+// Few queries (q <= 128): thread = database row.  A warp streams 64 rows per step with coalesced 128-bit loads
+// (HBM-bound when q <= 2: 32 B per row against 26 instructions per row-query pair), every lane scores its
+// two rows against each query (broadcast from shared memory) and the warp keeps the running top-2 of query
+// g*32 + j in lane j.  A row only enters the reduction when it beats that query's current second best --
+// after the first few thousand rows almost never -- so the steady state is XOR + POPC + one vote per pair.
+constexpr int kRowsQMax = 128;
+
+template <int QPL>  // queries per lane: q <= 32 * QPL
+__global__ void __launch_bounds__(256) knn2_rows_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_base,
+                                                        int chunk_rows, const uint8_t *__restrict__ queries, int q,
+                                                        unsigned long long *__restrict__ part) {
+    __shared__ uint4 sq[kRowsQMax * 2];
+    __shared__ uint32_t sk[8][kRowsQMax][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < q * 2; i += 256) sq[i] = __ldg((const uint4 *)queries + i);
+    __syncthreads();
+    const long long c0 = (long long)blockIdx.x * chunk_rows, c1 = min(c0 + (long long)chunk_rows, rows);
+    uint32_t k0[QPL], k1[QPL];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const unsigned long long k = part[((size_t)p * q + qi) * 2 + r];
-            k1 = min(k1, max(k0, k));
-            k0 = min(k0, k);
+    for (int g = 0; g < QPL; g++) k0[g] = k1[g] = kNoKey;
+    for (long long r0 = c0 + warp * 64; r0 < c1; r0 += 8 * 64) {
+        uint32_t a[2][8];
+        bool valid[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const long long row = r0 + h * 32 + lane;
+            valid[h] = row < c1;
+            if (valid[h]) load_desc(db + (size_t)row * 32, a[h]);
+        }
+        const uint32_t rel = (uint32_t)(r0 - c0) + lane;
+#pragma unroll
+        for (int g = 0; g < QPL; g++) {
+            const int nq = min(32, q - g * 32);
+#pragma unroll 2
+            for (int j = 0; j < nq; j++) {
+                const uint4 u = sq[2 * (g * 32 + j)], w = sq[2 * (g * 32 + j) + 1];
+                const uint32_t thr = __shfl_sync(0xffffffffu, k1[g], j);
+                uint32_t key[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int d = __popc(a[h][0] ^ u.x) + __popc(a[h][1] ^ u.y) + __popc(a[h][2] ^ u.z) + __popc(a[h][3] ^ u.w) +
+                                  __popc(a[h][4] ^ w.x) + __popc(a[h][5] ^ w.y) + __popc(a[h][6] ^ w.z) + __popc(a[h][7] ^ w.w);
+                    key[h] = valid[h] ? (uint32_t)d << 22 | (rel + 32 * h) : kNoKey;
+                }
+                if (__any_sync(0xffffffffu, min(key[0], key[1]) < thr)) {
+                    // the warp's two smallest keys (keys are unique: they carry the row)
+                    uint32_t lo = min(key[0], key[1]), hi = max(key[0], key[1]);
+                    const uint32_t m1 = __reduce_min_sync(0xffffffffu, lo);
+                    if (lo == m1) lo = hi, hi = kNoKey;
+                    const uint32_t m2 = __reduce_min_sync(0xffffffffu, lo);
+                    if (lane == j) {
+                        top2_insert(k0[g], k1[g], m1);
+                        top2_insert(k0[g], k1[g], m2);
+                    }
+                }
+            }
         }
     }
+#pragma unroll
+    for (int g = 0; g < QPL; g++)
+        if (g * 32 + lane < q) {
+            sk[warp][g * 32 + lane][0] = k0[g];
+            sk[warp][g * 32 + lane][1] = k1[g];
+        }
+    __syncthreads();
+    if (tid < q) {
+        uint32_t b0 = kNoKey, b1 = kNoKey;
+#pragma unroll
+        for (int w2 = 0; w2 < 8; w2++) {
+            top2_insert(b0, b1, sk[w2][tid][0]);
+            top2_insert(b0, b1, sk[w2][tid][1]);
+        }
+        unsigned long long *o = part + ((size_t)blockIdx.x * q + tid) * 2;
+        const unsigned long long gb = (unsigned long long)(idx_base + c0);
+        o[0] = b0 == kNoKey ? ~0ull : ((unsigned long long)(b0 >> 22) << 32 | (gb + (b0 & 0x3FFFFF)));
+        o[1] = b1 == kNoKey ? ~0ull : ((unsigned long long)(b1 >> 22) << 32 | (gb + (b1 & 0x3FFFFF)));
+    }
+}
+
+// lexicographic (dist, global index) top-2 over `parts` candidate pairs per query: one warp per query, lanes
+// stride over the parts, butterfly merge of the per-lane pairs
+__global__ void __launch_bounds__(128) knn2_merge_kernel(const unsigned long long *__restrict__ part, int parts, int q,
+                                                         unsigned long long *__restrict__ keys_out, int32_t *__restrict__ quad_out) {
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (qi >= q) return;
+    unsigned long long k0 = ~0ull, k1 = ~0ull;
+    for (int p = lane; p < parts; p += 32) {
+        const ulonglong2 k = __ldg((const ulonglong2 *)(part + ((size_t)p * q + qi) * 2));
+        k1 = min(k1, max(k0, k.x));
+        k0 = min(k0, k.x);
+        k1 = min(k1, max(k0, k.y));
+        k0 = min(k0, k.y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+        k1 = min(min(k1, o1), max(k0, o0));
+        k0 = min(k0, o0);
+    }
+    if (lane != 0) return;
     if (keys_out) {
         keys_out[(size_t)qi * 2] = k0;
         keys_out[(size_t)qi * 2 + 1] = k1;
@@ -360,6 +446,7 @@ struct sfe_matcher {
     cudaStream_t stream = nullptr;
     int sm_count = 148;
     int64_t launches = 0;
+    bool async_dev = false;  // _dev entry points return after enqueueing (sfe_matcher_wait)
     DevBuf<sfe_keypoint> d_kl, d_kr;
     DevBuf<uint8_t> d_dl, d_dr, d_skip;
     DevBuf<int32_t> d_n, d_idx, d_dist;
@@ -420,16 +507,27 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
 static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, int q, unsigned long long *keys_dev,
                        int32_t *quad_dev) {
     cudaStream_t st = m->stream;
-    const int qgroups = div_up(q, kKnnThreads);
-    int chunks = std::max(1, (2 * m->sm_count) / qgroups);
+    const bool by_rows = q <= kRowsQMax;  // thread = row (streaming) for few queries, thread = query otherwise
+    const int qgroups = by_rows ? 1 : div_up(q, kKnnThreads);
+    int chunks = std::max(1, ((by_rows ? 8 : 2) * m->sm_count) / qgroups);
     int64_t chunk_rows = std::max<int64_t>((db->rows + chunks - 1) / chunks, 1);
-    chunk_rows = (chunk_rows + kKnnTile - 1) / kKnnTile * kKnnTile;
+    chunk_rows = (chunk_rows + 511) / 512 * 512;
     SFE_REQUIRE(chunk_rows <= (1 << 22), SFE_ERR_UNSUPPORTED, "database shard larger than 2^22 rows per chunk");
     chunks = (int)std::max<int64_t>((db->rows + chunk_rows - 1) / chunk_rows, 1);
     SFE_CUDA(m->d_part.ensure((size_t)chunks * q * 2));
-    knn2_partial_kernel<<<dim3(chunks, qgroups), kKnnThreads, 0, st>>>(db->rows_dev, db->rows, db->idx_base, (int)chunk_rows,
-                                                                      q_dev, q, m->d_part.p);
-    knn2_merge_kernel<<<div_up(q, 128), 128, 0, st>>>(m->d_part.p, chunks, q, keys_dev, quad_dev);
+    if (by_rows) {
+        const int qpl = div_up(q, 32);
+        if (qpl == 1)
+            knn2_rows_kernel<1><<<chunks, 256, 0, st>>>(db->rows_dev, db->rows, db->idx_base, (int)chunk_rows, q_dev, q, m->d_part.p);
+        else if (qpl == 2)
+            knn2_rows_kernel<2><<<chunks, 256, 0, st>>>(db->rows_dev, db->rows, db->idx_base, (int)chunk_rows, q_dev, q, m->d_part.p);
+        else
+            knn2_rows_kernel<4><<<chunks, 256, 0, st>>>(db->rows_dev, db->rows, db->idx_base, (int)chunk_rows, q_dev, q, m->d_part.p);
+    } else {
+        knn2_partial_kernel<<<dim3(chunks, qgroups), kKnnThreads, 0, st>>>(db->rows_dev, db->rows, db->idx_base, (int)chunk_rows,
+                                                                          q_dev, q, m->d_part.p);
+    }
+    knn2_merge_kernel<<<div_up(q, 4), 128, 0, st>>>(m->d_part.p, chunks, q, keys_dev, quad_dev);
     m->launches += 2;
     SFE_CUDA(cudaGetLastError());
     return SFE_OK;
@@ -466,6 +564,21 @@ int sfe_matcher_destroy(sfe_matcher *m) {
     m->d_best.release(); m->d_part.release(); m->d_keys.release(); m->d_quad.release();
     cudaStreamDestroy(m->stream);
     delete m;
+    return SFE_OK;
+}
+
+int sfe_matcher_set_async(sfe_matcher *m, int enable) {
+    SFE_REQUIRE(m, SFE_ERR_BAD_ARG, "null handle");
+    DeviceGuard g(m->device);
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    m->async_dev = enable != 0;
+    return SFE_OK;
+}
+
+int sfe_matcher_wait(sfe_matcher *m) {
+    SFE_REQUIRE(m, SFE_ERR_BAD_ARG, "null handle");
+    DeviceGuard g(m->device);
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
 
@@ -526,7 +639,7 @@ int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t
     int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, rt, cam, kps_dev, kp_desc_dev, m_kps, radius,
                              best12_threshold, kp_to_query_dev, kp_dist_dev);
     if (rc != SFE_OK) return rc;
-    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
 
@@ -572,7 +685,7 @@ int sfe_projection_match_keys_dev(sfe_matcher *m, const double *xw_dev, const ui
     int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, rt, cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold,
                              nullptr, nullptr, (uint32_t)idx_base, (unsigned long long *)keys_dev);
     if (rc != SFE_OK) return rc;
-    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
 
@@ -584,7 +697,7 @@ int sfe_projection_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shard
                                                                          kp_to_query_dev, kp_dist_dev);
     m->launches++;
     SFE_CUDA(cudaGetLastError());
-    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
 
@@ -623,17 +736,17 @@ int sfe_knn2_dev(sfe_matcher *m, const sfe_db *db, const uint8_t *queries_dev, i
     DeviceGuard g(m->device);
     int rc = knn_partial(m, db, queries_dev, q, (unsigned long long *)keys_dev, nullptr);
     if (rc != SFE_OK) return rc;
-    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
 
 int sfe_knn2_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int q, int32_t *out_dev) {
     SFE_REQUIRE(m && keys_dev && out_dev && shards >= 1 && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
     DeviceGuard g(m->device);
-    knn2_merge_kernel<<<div_up(q, 128), 128, 0, m->stream>>>((const unsigned long long *)keys_dev, shards, q, nullptr, out_dev);
+    knn2_merge_kernel<<<div_up(q, 4), 128, 0, m->stream>>>((const unsigned long long *)keys_dev, shards, q, nullptr, out_dev);
     m->launches++;
     SFE_CUDA(cudaGetLastError());
-    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
 

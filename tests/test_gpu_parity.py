@@ -317,6 +317,17 @@ def test_knn2_vs_oracle_and_sharded_merge(gpu, oracle):
     ref = oracle.knn2(q, db)
     full = m.knn2(m.create_db(db), q)
     assert np.array_equal(full, ref)
+    # few queries run the row-streaming kernel (thread = row); every lane-count edge, plus duplicated rows (ties)
+    db2 = db.copy()
+    db2[20000] = db2[77]
+    db2[29999] = db2[77]
+    dbh = m.create_db(db2)
+    for nq in (1, 2, 3, 31, 32, 33, 64, 65, 100, 128, 129):
+        qq = q[:nq].copy()
+        qq[0] = db2[77]
+        got = m.knn2(dbh, qq)
+        assert np.array_equal(got, oracle.knn2(qq, db2)), nq
+        assert got[0].tolist() == [77, 0, 20000, 0]
     # tiny and degenerate shards
     for rows_n in (0, 1, 2, 255, 257):
         got = m.knn2(m.create_db(db[:rows_n]), q[:5])
@@ -336,7 +347,7 @@ def test_knn2_vs_oracle_and_sharded_merge(gpu, oracle):
 
 
 def test_knn2_full_size_properties(gpu):
-    """BASELINE config 4 shape at reduced M (2M rows; the 10M run is bench.py --workload knn):
+    """BASELINE config 4 shape at reduced M (2M rows; tools/knn_bench.py and bench.py's `hamming` object run 10M):
     size-independent properties instead of the (too slow) oracle."""
     m = api.Matcher()
     db = synth.knn_database(2_000_000, seed=1234)
