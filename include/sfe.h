@@ -80,6 +80,7 @@ typedef struct sfe_extractor sfe_extractor;
 typedef struct sfe_matcher sfe_matcher;
 typedef struct sfe_db sfe_db;
 typedef struct sfe_event sfe_event;
+typedef struct sfe_frame sfe_frame;
 
 /* ---- general -------------------------------------------------------------------------- */
 int sfe_abi_version(void);
@@ -201,6 +202,37 @@ int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t
                              const uint8_t *kp_desc_dev, int m_kps, double radius,
                              double best12_threshold, int32_t *kp_to_query_dev,
                              int32_t *kp_dist_dev);
+
+/* ---- resident frames: the work of Frame::Frame after extract() (src/frame.cpp:50-69) ----------------------
+ * A frame keeps its keypoints + descriptors on the device, with the normalised undistorted keypoints
+ * (Camera::NormalizedUndistort, src/camera.cpp:95-109: what Frame::GetNormalizedPoint returns) and the spatial index
+ * that replaces the per-frame FLANN kd-tree, so matching against it never re-uploads or re-indexes it. */
+int sfe_frame_create(sfe_matcher *m, const sfe_keypoint *kps, const uint8_t *desc, int n,
+                     const sfe_camera *cam, sfe_frame **out);
+/* same from device arrays (e.g. one image's rows of sfe_extract_batch_dev outputs); copied device to device */
+int sfe_frame_create_dev(sfe_matcher *m, const sfe_keypoint *kps_dev, const uint8_t *desc_dev, int n,
+                         const sfe_camera *cam, sfe_frame **out);
+int sfe_frame_destroy(sfe_frame *f);
+int sfe_frame_size(const sfe_frame *f, int *n);
+int sfe_frame_normalized(sfe_matcher *m, const sfe_frame *f, double *xy /* n x 2 */);
+/* StereoFrame::GetDepth (src/frame.cpp:391-409) for every keypoint: xc[i] = (n_x, n_y, 1) * fx * baseline / dx;
+ * valid[i] = 1, 0 (no stereo correspondence) or 2 (dx < 0: the reference throws). */
+int sfe_frame_stereo_depth(sfe_matcher *m, const sfe_frame *f, const sfe_keypoint *kps_r, int n_r,
+                           const int32_t *stereo_idx, double baseline, double *xc /* n x 3 */,
+                           uint8_t *valid /* n */);
+/* ProjectionMatch against a resident frame (map points from host memory) */
+int sfe_frame_projection_match(sfe_matcher *m, const sfe_frame *f, const double *xw,
+                               const uint8_t *mp_desc, const uint8_t *skip, int n, const double rt[12],
+                               double radius, double best12_threshold, int32_t *kp_to_query,
+                               int32_t *kp_dist);
+/* Frame::SearchRadius (src/frame.cpp:157-178) for q points: idx[i*cap ..] = keypoints with d^2 < radius^2 in
+ * ascending index order (at most cap of them), counts[i] = how many there are (may exceed cap). */
+int sfe_frame_search_radius(sfe_matcher *m, const sfe_frame *f, const double *uv /* q x 2 */, int q,
+                            double radius, int32_t *idx /* q x cap */, int cap, int32_t *counts);
+/* Frame::SearchNeareast (src/frame.cpp:180-193): nearest keypoint and SQUARED distance (FLANN L2), ties towards
+ * the smaller index; -1 for an empty frame. */
+int sfe_frame_search_nearest(sfe_matcher *m, const sfe_frame *f, const double *uv /* q x 2 */, int q,
+                             int32_t *kpt_index, double *dist2);
 
 /* Sharded ProjectionMatch (map points partitioned over GPUs, frame replicated): each shard emits per keypoint
  * the key (dist << 32 | ~global map-point index) of its best accepted query -- the minimum over shards is the

@@ -53,6 +53,7 @@ def lib():
         for f in ("orc_get_candidates", "orc_get_distributed"):
             getattr(L, f).restype = ci
             getattr(L, f).argtypes = [vp, ci, vp, ci]
+        L.orc_search_radius.restype = ci
         L.orc_resize_linear_u8.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci]
         L.orc_gaussian7_s2_u8.argtypes = [vp, ci, ci, ci, vp, ci]
         L.orc_fast_score_u8.argtypes = [vp, ci, ci, ci, vp]
@@ -221,6 +222,38 @@ def projection_match(xw, mp_desc, skip, rt, cam, kps, kp_desc, radius, ratio=0.5
     lib().orc_projection_match(_p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), C.byref(cam), _p(kps),
                                _p(kp_desc), m, radius, ratio, _p(to_q), _p(dist))
     return to_q, dist
+
+
+def normalized_undistort(cam, kps):
+    kps = np.ascontiguousarray(kps)
+    out = np.zeros((len(kps), 2), np.float64)
+    lib().orc_normalized_undistort(C.byref(cam), _p(kps), len(kps), _p(out))
+    return out
+
+
+def stereo_depth(cam, baseline, kps_l, norm_xy, kps_r, stereo_idx):
+    kps_l, kps_r = np.ascontiguousarray(kps_l), np.ascontiguousarray(kps_r)
+    norm_xy = np.ascontiguousarray(norm_xy, np.float64)
+    stereo_idx = np.ascontiguousarray(stereo_idx, np.int32)
+    xc = np.zeros((len(kps_l), 3), np.float64)
+    valid = np.zeros(len(kps_l), np.uint8)
+    lib().orc_stereo_depth(C.byref(cam), C.c_double(baseline), _p(kps_l), _p(norm_xy), len(kps_l), _p(kps_r), _p(stereo_idx),
+                           _p(xc), _p(valid))
+    return xc, valid
+
+
+def search_radius(kps, u, v, radius, cap=4096):
+    kps = np.ascontiguousarray(kps)
+    idx = np.zeros(cap, np.int32)
+    n = lib().orc_search_radius(_p(kps), len(kps), C.c_double(u), C.c_double(v), C.c_double(radius), _p(idx), cap)
+    return idx[:min(n, cap)].copy(), n
+
+
+def search_nearest(kps, u, v):
+    kps = np.ascontiguousarray(kps)
+    i, d = C.c_int(), C.c_double()
+    lib().orc_search_nearest(_p(kps), len(kps), C.c_double(u), C.c_double(v), C.byref(i), C.byref(d))
+    return i.value, d.value
 
 
 def knn2(queries, db, idx_base=0):

@@ -694,6 +694,81 @@ void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_
     }
 }
 
+/* ---- Frame glue -------------------------------------------------------------
+ * Camera::NormalizedUndistort src/camera.cpp:95-109 (called per keypoint by Frame::Frame, src/frame.cpp:50-56):
+ * 5 fixed-point iterations x += (x_n - Distort(D, x)), Distort as src/camera.cpp:50-68.  Doubles, no contraction. */
+static void orc_distort(const double d[4], double x, double y, double *xd, double *yd) {
+    double r2 = x * x + y * y, r4 = r2 * r2;
+    double a1 = 2. * x * y, a2 = r2 + 2. * x * x, a3 = r2 + 2. * y * y;
+    double cdist = 1. + d[0] * r2 + d[1] * r4;
+    *xd = x * cdist + d[2] * a1 + d[3] * a2;
+    *yd = y * cdist + d[2] * a3 + d[3] * a1;
+}
+
+void orc_normalized_undistort(const orc_camera *cam, const orc_keypoint *kps, int n, double *xy) {
+    for (int i = 0; i < n; i++) {
+        const double nx = ((double)kps[i].x - cam->cx) / cam->fx, ny = ((double)kps[i].y - cam->cy) / cam->fy;
+        double x = nx, y = ny;
+        for (int it = 0; it < 5; it++) {
+            double xd, yd;
+            orc_distort(cam->d, x, y, &xd, &yd);
+            x += nx - xd;
+            y += ny - yd;
+        }
+        xy[2 * i] = x;
+        xy[2 * i + 1] = y;
+    }
+}
+
+/* StereoFrame::GetDepth src/frame.cpp:391-409 for every left keypoint: valid[i] = 1 and xc = (n_x, n_y, 1) * depth with
+ * depth = fx * baseline / dx, dx = (double)(float)(x_l - x_r) (the reference subtracts two floats); 0 = no stereo
+ * correspondence; 2 = dx < 0 (the reference throws std::invalid_argument). */
+void orc_stereo_depth(const orc_camera *cam, double baseline, const orc_keypoint *kps_l, const double *norm_xy, int n,
+                      const orc_keypoint *kps_r, const int *stereo_idx, double *xc, uint8_t *valid) {
+    for (int i = 0; i < n; i++) {
+        xc[3 * i] = xc[3 * i + 1] = xc[3 * i + 2] = 0.;
+        valid[i] = 0;
+        const int j = stereo_idx[i];
+        if (j < 0) continue;
+        const float dxf = kps_l[i].x - kps_r[j].x;
+        const double dx = (double)dxf;
+        if (dx < 0.) { valid[i] = 2; continue; }
+        const double depth = cam->fx * baseline / dx;
+        xc[3 * i] = norm_xy[2 * i] * depth;
+        xc[3 * i + 1] = norm_xy[2 * i + 1] * depth;
+        xc[3 * i + 2] = depth;
+        valid[i] = 1;
+    }
+}
+
+/* Frame::SearchRadius src/frame.cpp:157-178 (FLANN radiusSearch with radius^2, L2<double> on the keypoints stored as
+ * doubles): all keypoints with d^2 < r^2 (T4), canonical result order = ascending keypoint index.  Returns the count;
+ * at most cap indices are written. */
+int orc_search_radius(const orc_keypoint *kps, int m, double u, double v, double radius, int *idx, int cap) {
+    const double r2max = radius * radius;
+    int n = 0;
+    for (int j = 0; j < m; j++) {
+        double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
+        double d2 = ddx * ddx + ddy * ddy;
+        if (!(d2 < r2max)) continue;
+        if (n < cap) idx[n] = j;
+        n++;
+    }
+    return n;
+}
+
+/* Frame::SearchNeareast src/frame.cpp:180-193 (FLANN knnSearch, k = 1): nearest keypoint and its SQUARED distance
+ * (FLANN L2 returns squared distances); canonical tie rule T6 = the smaller index.  -1 when the frame is empty. */
+void orc_search_nearest(const orc_keypoint *kps, int m, double u, double v, int *kpt_index, double *dist2) {
+    *kpt_index = -1;
+    *dist2 = 0.;
+    for (int j = 0; j < m; j++) {
+        double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
+        double d2 = ddx * ddx + ddy * ddy;
+        if (*kpt_index < 0 || d2 < *dist2) { *kpt_index = j; *dist2 = d2; }
+    }
+}
+
 /* ---- brute-force top-2: the StereoMatch/ProjectionMatch inner loop
  * with the whole database as candidate set; strict < in ascending index = lexicographic
  * (dist, idx). */

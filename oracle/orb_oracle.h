@@ -80,6 +80,15 @@ void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_
 void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base,
               int32_t *out);
 
+/* frame glue: src/camera.cpp:95-109, src/frame.cpp:50-56,157-193,391-409.
+ * T6 (canonical): SearchNeareast resolves equal distances towards the smaller keypoint index; SearchRadius lists
+ * indices in ascending order (FLANN's own order is by distance and irrelevant to every caller). */
+void orc_normalized_undistort(const orc_camera *cam, const orc_keypoint *kps, int n, double *xy);
+void orc_stereo_depth(const orc_camera *cam, double baseline, const orc_keypoint *kps_l, const double *norm_xy, int n,
+                      const orc_keypoint *kps_r, const int *stereo_idx, double *xc, uint8_t *valid);
+int orc_search_radius(const orc_keypoint *kps, int m, double u, double v, double radius, int *idx, int cap);
+void orc_search_nearest(const orc_keypoint *kps, int m, double u, double v, int *kpt_index, double *dist2);
+
 /* CPU baseline helper: extract L + extract R + stereo match for `count` stereo
  * frames with `nthreads` worker threads (one frame per thread at a time).
  * left/right: count contiguous w*h images.  Returns total matches. */

@@ -101,6 +101,15 @@ SIGNATURES = {
     "sfe_projection_match_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
     "sfe_projection_match_keys_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp]),
     "sfe_projection_merge_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "sfe_frame_create": (_i, [_vp, _vp, _vp, _i, C.POINTER(Camera), _pp]),
+    "sfe_frame_create_dev": (_i, [_vp, _vp, _vp, _i, C.POINTER(Camera), _pp]),
+    "sfe_frame_destroy": (_i, [_vp]),
+    "sfe_frame_size": (_i, [_vp, C.POINTER(_i)]),
+    "sfe_frame_normalized": (_i, [_vp, _vp, _vp]),
+    "sfe_frame_stereo_depth": (_i, [_vp, _vp, _vp, _i, _vp, _d, _vp, _vp]),
+    "sfe_frame_projection_match": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _vp, _vp]),
+    "sfe_frame_search_radius": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp]),
+    "sfe_frame_search_nearest": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "sfe_db_create": (_i, [_vp, _vp, _i64, _i64, _pp]),
     "sfe_db_destroy": (_i, [_vp]),
     "sfe_knn2": (_i, [_vp, _vp, _vp, _i, _vp]),
@@ -495,6 +504,79 @@ class Matcher:
 
     def knn2_merge_dev(self, keys_ptr, shards, q, out_ptr):
         _check(lib().sfe_knn2_merge_dev(self.h, _p(keys_ptr), shards, q, _p(out_ptr)))
+
+
+class Frame:
+    """The device-resident part of the reference's Frame (src/frame.cpp:36-69): keypoints + descriptors, normalised
+    undistorted keypoints (GetNormalizedPoint) and the spatial index behind SearchRadius / SearchNeareast /
+    ProjectionMatch.  Build it from host arrays or from device pointers (`dev=True`)."""
+
+    def __init__(self, matcher: "Matcher", kps, desc, camera: Camera, n=None, dev=False):
+        self.m = matcher
+        h = C.c_void_p()
+        if dev:
+            _check(lib().sfe_frame_create_dev(matcher.h, _p(kps), _p(desc), n, C.byref(camera), C.byref(h)))
+        else:
+            kps = np.ascontiguousarray(kps, KP_DTYPE)
+            desc = np.ascontiguousarray(desc, np.uint8)
+            n = len(kps)
+            _check(lib().sfe_frame_create(matcher.h, _p(kps), _p(desc), n, C.byref(camera), C.byref(h)))
+        self.h, self.n = h, n
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sfe_frame_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def normalized(self):
+        """-> n x 2 float64, Frame::GetNormalizedPoint for every keypoint."""
+        out = np.zeros((self.n, 2), np.float64)
+        _check(lib().sfe_frame_normalized(self.m.h, self.h, _p(out)))
+        return out
+
+    def stereo_depth(self, kps_r, stereo_idx, baseline):
+        """StereoFrame::GetDepth for every keypoint -> (Xc n x 3 float64, valid n u8)."""
+        kps_r = np.ascontiguousarray(kps_r, KP_DTYPE)
+        stereo_idx = np.ascontiguousarray(stereo_idx, np.int32)
+        xc = np.zeros((self.n, 3), np.float64)
+        valid = np.zeros(self.n, np.uint8)
+        _check(lib().sfe_frame_stereo_depth(self.m.h, self.h, _p(kps_r), len(kps_r), _p(stereo_idx), baseline, _p(xc), _p(valid)))
+        return xc, valid
+
+    def ProjectionMatch(self, xw, mp_desc, skip, Tcw, search_radius, best12=0.5):
+        xw = np.ascontiguousarray(xw, np.float64)
+        mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
+        skip = None if skip is None else np.ascontiguousarray(skip, np.uint8)
+        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        to_q = np.full(self.n, -1, np.int32)
+        dist = np.full(self.n, -1, np.int32)
+        _check(lib().sfe_frame_projection_match(self.m.h, self.h, _p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), search_radius,
+                                                best12, _p(to_q), _p(dist)))
+        return to_q, dist
+
+    def SearchRadius(self, uv, radius, cap=512):
+        """-> list of index arrays (ascending), one per query point (Frame::SearchRadius, batch form)."""
+        uv = np.ascontiguousarray(np.atleast_2d(uv), np.float64)
+        idx = np.zeros((len(uv), cap), np.int32)
+        counts = np.zeros(len(uv), np.int32)
+        _check(lib().sfe_frame_search_radius(self.m.h, self.h, _p(uv), len(uv), radius, _p(idx), cap, _p(counts)))
+        if (counts > cap).any():
+            raise SfeError(SFE_ERR_CAPACITY, "SearchRadius: more neighbours than cap")
+        return [idx[i, :counts[i]].copy() for i in range(len(uv))]
+
+    def SearchNeareast(self, uv):
+        """-> (kpt_index, squared distance) arrays (Frame::SearchNeareast, batch form; the name is the reference's)."""
+        uv = np.ascontiguousarray(np.atleast_2d(uv), np.float64)
+        idx = np.zeros(len(uv), np.int32)
+        d2 = np.zeros(len(uv), np.float64)
+        _check(lib().sfe_frame_search_nearest(self.m.h, self.h, _p(uv), len(uv), _p(idx), _p(d2)))
+        return idx, d2
 
 
 class DescriptorDB:

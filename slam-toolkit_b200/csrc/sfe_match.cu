@@ -437,6 +437,101 @@ __global__ void __launch_bounds__(128) knn2_merge_kernel(const unsigned long lon
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame glue: what Frame::Frame does after extract() (src/frame.cpp:50-69) and
+// StereoFrame::GetDepth (:391-409), on the device, for a frame whose keypoints / descriptors stay resident.
+// ---------------------------------------------------------------------------------------------
+// Camera::NormalizedUndistort, src/camera.cpp:95-109: 5 iterations of x += x_n - Distort(D, x); one thread per keypoint
+__global__ void normalized_undistort_kernel(sfe_camera cam, const sfe_keypoint *__restrict__ kps, int n, double2 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double nx = __ddiv_rn(__dsub_rn((double)kps[i].x, cam.cx), cam.fx), ny = __ddiv_rn(__dsub_rn((double)kps[i].y, cam.cy), cam.fy);
+    double x = nx, y = ny;
+#pragma unroll 1
+    for (int it = 0; it < 5; it++) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), r4 = __dmul_rn(r2, r2);
+        const double a1 = __dmul_rn(__dmul_rn(2., x), y);
+        const double a2 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2., x), x));
+        const double a3 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2., y), y));
+        const double cdist = __dadd_rn(__dadd_rn(1., __dmul_rn(cam.d[0], r2)), __dmul_rn(cam.d[1], r4));
+        const double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, cdist), __dmul_rn(cam.d[2], a1)), __dmul_rn(cam.d[3], a2));
+        const double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, cdist), __dmul_rn(cam.d[2], a3)), __dmul_rn(cam.d[3], a1));
+        x = __dadd_rn(x, __dsub_rn(nx, xd));
+        y = __dadd_rn(y, __dsub_rn(ny, yd));
+    }
+    out[i] = make_double2(x, y);
+}
+
+// StereoFrame::GetDepth for every left keypoint: depth = fx * baseline / dx, dx = the FLOAT difference of the x's
+__global__ void stereo_depth_kernel(double fx, double baseline, const sfe_keypoint *__restrict__ kl, const double2 *__restrict__ nrm,
+                                    int n, const sfe_keypoint *__restrict__ kr, const int32_t *__restrict__ sidx,
+                                    double *__restrict__ xc, uint8_t *__restrict__ valid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double X = 0., Y = 0., Z = 0.;
+    uint8_t ok = 0;
+    const int j = sidx[i];
+    if (j >= 0) {
+        const double dx = (double)__fsub_rn(kl[i].x, kr[j].x);
+        if (dx < 0.) {
+            ok = 2;  // the reference throws: StereoMatch never lets this through
+        } else {
+            Z = __ddiv_rn(__dmul_rn(fx, baseline), dx);
+            X = __dmul_rn(nrm[i].x, Z);
+            Y = __dmul_rn(nrm[i].y, Z);
+            ok = 1;
+        }
+    }
+    xc[3 * i] = X; xc[3 * i + 1] = Y; xc[3 * i + 2] = Z;
+    valid[i] = ok;
+}
+
+// Frame::SearchRadius / SearchNeareast over the bucket grid; one thread per query point.
+__global__ void search_radius_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps, const double2 *__restrict__ uv, int q,
+                                     double radius, int32_t *__restrict__ idx, int cap, int32_t *__restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    const double u = uv[i].x, v = uv[i].y, r2max = __dmul_rn(radius, radius);
+    int32_t *out = idx + (size_t)i * cap;
+    int n = 0;
+    if (u == u && v == v) {
+        const int cx0 = min(max((int)floor(u - radius) >> kGridShift, 0), G.gw - 1), cx1 = min(max((int)floor(u + radius) >> kGridShift, 0), G.gw - 1);
+        const int cy0 = min(max((int)floor(v - radius) >> kGridShift, 0), G.gh - 1), cy1 = min(max((int)floor(v + radius) >> kGridShift, 0), G.gh - 1);
+        for (int cy = cy0; cy <= cy1; cy++) {
+            const int s = G.cell_start[cy * G.gw + cx0], e = G.cell_start[cy * G.gw + cx1 + 1];
+            for (int t = s; t < e; t++) {
+                const int j = G.order[t];
+                const double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
+                if (!(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) < r2max)) continue;
+                if (n < cap) {  // keep the row sorted by index (canonical order): insertion from the back
+                    int p = n;
+                    while (p > 0 && out[p - 1] > j) { out[p] = out[p - 1]; p--; }
+                    out[p] = j;
+                }
+                n++;
+            }
+        }
+    }
+    counts[i] = n;
+}
+
+__global__ void search_nearest_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps, const double2 *__restrict__ uv, int q,
+                                      int32_t *__restrict__ idx, double *__restrict__ dist2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    // exact nearest neighbour = minimum of (d^2, index) over all keypoints (T6); the frame holds ~2000 of them
+    const double u = uv[i].x, v = uv[i].y;
+    int best = -1;
+    double bd = 0.;
+    for (int j = 0; j < G.m; j++) {
+        const double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
+        const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+        if (best < 0 || d2 < bd) { best = j; bd = d2; }
+    }
+    idx[i] = best;
+    dist2[i] = bd;
+}
+
 }  // namespace sfe
 
 using namespace sfe;
@@ -464,29 +559,52 @@ struct sfe_db {
 
 // keys_out != nullptr: leave the per-keypoint (dist << 32 | ~global query) keys there (one shard's contribution to a
 // sharded match) instead of decoding them
-static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
-                           const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
-                           int m_kps, double radius, double ratio, int32_t *to_query, int32_t *dist, uint32_t idx_base = 0,
-                           unsigned long long *keys_out = nullptr) {
+struct sfe_frame {
+    int device = 0;
+    int n = 0;
+    sfe_camera cam{};
+    KpGrid grid{};
+    DevBuf<sfe_keypoint> kps;
+    DevBuf<uint8_t> desc;
+    DevBuf<double2> nrm;
+    DevBuf<int> grid_mem;
+};
+
+// bucket grid over m_kps keypoints (replaces the per-frame FLANN kd-tree, src/frame.cpp:59-68)
+static int build_grid(sfe_matcher *m, DevBuf<int> &mem, KpGrid &G, const sfe_camera *cam, const sfe_keypoint *kps, int m_kps) {
     cudaStream_t st = m->stream;
-    if (m_kps == 0) return SFE_OK;
-    KpGrid G;
     G.gw = (std::max(cam->width, 1) >> kGridShift) + 1;
     G.gh = (std::max(cam->height, 1) >> kGridShift) + 1;
     G.m = m_kps;
     const int cells = G.gw * G.gh;
-    SFE_CUDA(m->d_grid.ensure((size_t)2 * cells + 1 + m_kps));
+    SFE_CUDA(mem.ensure((size_t)2 * cells + 1 + std::max(m_kps, 1)));
+    G.cell_start = mem.p;
+    G.cell_fill = mem.p + cells + 1;
+    G.order = mem.p + 2 * cells + 1;
+    SFE_CUDA(cudaMemsetAsync(G.cell_start, 0, sizeof(int) * (cells + 1), st));
+    if (m_kps > 0) grid_count_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
+    grid_scan_kernel<<<1, 256, 0, st>>>(G);
+    if (m_kps > 0) grid_fill_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
+    m->launches += 3;
+    return SFE_OK;
+}
+
+static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                           const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
+                           int m_kps, double radius, double ratio, int32_t *to_query, int32_t *dist, uint32_t idx_base = 0,
+                           unsigned long long *keys_out = nullptr, const KpGrid *prebuilt = nullptr) {
+    cudaStream_t st = m->stream;
+    if (m_kps == 0) return SFE_OK;
+    KpGrid G;
+    if (prebuilt) {
+        G = *prebuilt;  // a resident frame brings its own index
+    } else {
+        int rc = build_grid(m, m->d_grid, G, cam, kps, m_kps);
+        if (rc != SFE_OK) return rc;
+    }
     SFE_CUDA(m->d_best.ensure(m_kps));
     unsigned long long *best = keys_out ? keys_out : m->d_best.p;
-    G.cell_start = m->d_grid.p;
-    G.cell_fill = m->d_grid.p + cells + 1;
-    G.order = m->d_grid.p + 2 * cells + 1;
-    SFE_CUDA(cudaMemsetAsync(G.cell_start, 0, sizeof(int) * (cells + 1), st));
     SFE_CUDA(cudaMemsetAsync(best, 0xFF, sizeof(unsigned long long) * m_kps, st));
-    grid_count_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
-    grid_scan_kernel<<<1, 256, 0, st>>>(G);
-    grid_fill_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
-    m->launches += 3;
     if (n > 0) {
         ProjParams P;
         memcpy(P.rt, rt, sizeof(P.rt));
@@ -698,6 +816,174 @@ int sfe_projection_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shard
     m->launches++;
     SFE_CUDA(cudaGetLastError());
     if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
+    return SFE_OK;
+}
+
+// ---- resident frames ---------------------------------------------------------------
+static int frame_finish(sfe_matcher *m, sfe_frame *f) {
+    cudaStream_t st = m->stream;
+    SFE_CUDA(f->nrm.ensure(std::max(f->n, 1)));
+    if (f->n > 0) {
+        normalized_undistort_kernel<<<div_up(f->n, 128), 128, 0, st>>>(f->cam, f->kps.p, f->n, f->nrm.p);
+        m->launches++;
+    }
+    int rc = build_grid(m, f->grid_mem, f->grid, &f->cam, f->kps.p, f->n);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+static int frame_new(sfe_matcher *m, const sfe_keypoint *kps, const uint8_t *desc, int n, const sfe_camera *cam, bool on_device,
+                     sfe_frame **out) {
+    SFE_REQUIRE(m && cam && out && n >= 0 && n < 65536, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(n == 0 || (kps && desc), SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    sfe_frame *f = new sfe_frame();
+    f->device = m->device;
+    f->n = n;
+    f->cam = *cam;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaError_t e = f->kps.ensure(std::max(n, 1));
+    if (e == cudaSuccess) e = f->desc.ensure((size_t)std::max(n, 1) * 32);
+    if (e == cudaSuccess && n > 0) e = cudaMemcpyAsync(f->kps.p, kps, sizeof(sfe_keypoint) * n, kind, m->stream);
+    if (e == cudaSuccess && n > 0) e = cudaMemcpyAsync(f->desc.p, desc, (size_t)n * 32, kind, m->stream);
+    int rc = SFE_OK;
+    if (e != cudaSuccess) {
+        set_error("frame upload: %s", cudaGetErrorString(e));
+        rc = SFE_ERR_CUDA;
+    } else {
+        rc = frame_finish(m, f);
+    }
+    if (rc != SFE_OK) {
+        sfe_frame_destroy(f);
+        return rc;
+    }
+    *out = f;
+    return SFE_OK;
+}
+
+int sfe_frame_create(sfe_matcher *m, const sfe_keypoint *kps, const uint8_t *desc, int n, const sfe_camera *cam, sfe_frame **out) {
+    return frame_new(m, kps, desc, n, cam, false, out);
+}
+
+int sfe_frame_create_dev(sfe_matcher *m, const sfe_keypoint *kps_dev, const uint8_t *desc_dev, int n, const sfe_camera *cam,
+                         sfe_frame **out) {
+    return frame_new(m, kps_dev, desc_dev, n, cam, true, out);
+}
+
+int sfe_frame_destroy(sfe_frame *f) {
+    if (!f) return SFE_OK;
+    DeviceGuard g(f->device);
+    f->kps.release(); f->desc.release(); f->nrm.release(); f->grid_mem.release();
+    delete f;
+    return SFE_OK;
+}
+
+int sfe_frame_size(const sfe_frame *f, int *n) {
+    SFE_REQUIRE(f && n, SFE_ERR_BAD_ARG, "null argument");
+    *n = f->n;
+    return SFE_OK;
+}
+
+int sfe_frame_normalized(sfe_matcher *m, const sfe_frame *f, double *xy) {
+    SFE_REQUIRE(m && f && (xy || f->n == 0), SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
+    DeviceGuard g(m->device);
+    if (f->n > 0) SFE_CUDA(cudaMemcpyAsync(xy, f->nrm.p, sizeof(double2) * f->n, cudaMemcpyDeviceToHost, m->stream));
+    SFE_CUDA(cudaStreamSynchronize(m->stream));
+    return SFE_OK;
+}
+
+int sfe_frame_stereo_depth(sfe_matcher *m, const sfe_frame *f, const sfe_keypoint *kps_r, int n_r, const int32_t *stereo_idx,
+                           double baseline, double *xc, uint8_t *valid) {
+    SFE_REQUIRE(m && f && n_r >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
+    if (f->n == 0) return SFE_OK;
+    SFE_REQUIRE(stereo_idx && xc && valid && (kps_r || n_r == 0), SFE_ERR_BAD_ARG, "null argument");
+    for (int i = 0; i < f->n; i++) SFE_REQUIRE(stereo_idx[i] < n_r, SFE_ERR_BAD_ARG, "stereo index outside the right keypoints");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    SFE_CUDA(m->d_kr.ensure(std::max(n_r, 1)));
+    SFE_CUDA(m->d_idx.ensure(f->n));
+    SFE_CUDA(m->d_xw.ensure((size_t)f->n * 3));
+    SFE_CUDA(m->d_skip.ensure(f->n));
+    if (n_r > 0) SFE_CUDA(cudaMemcpyAsync(m->d_kr.p, kps_r, sizeof(sfe_keypoint) * n_r, cudaMemcpyHostToDevice, st));
+    SFE_CUDA(cudaMemcpyAsync(m->d_idx.p, stereo_idx, sizeof(int32_t) * f->n, cudaMemcpyHostToDevice, st));
+    stereo_depth_kernel<<<div_up(f->n, 128), 128, 0, st>>>(f->cam.fx, baseline, f->kps.p, f->nrm.p, f->n, m->d_kr.p, m->d_idx.p,
+                                                           m->d_xw.p, m->d_skip.p);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaMemcpyAsync(xc, m->d_xw.p, sizeof(double) * 3 * f->n, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(valid, m->d_skip.p, f->n, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+int sfe_frame_projection_match(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *mp_desc, const uint8_t *skip,
+                               int n, const double rt[12], double radius, double best12_threshold, int32_t *kp_to_query,
+                               int32_t *kp_dist) {
+    SFE_REQUIRE(m && f && rt && n >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
+    if (f->n == 0) return SFE_OK;
+    SFE_REQUIRE(kp_to_query && (n == 0 || (xw && mp_desc)), SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    const int nn = std::max(n, 1);
+    SFE_CUDA(m->d_xw.ensure((size_t)nn * 3)); SFE_CUDA(m->d_dl.ensure((size_t)nn * 32)); SFE_CUDA(m->d_skip.ensure(nn));
+    SFE_CUDA(m->d_idx.ensure(f->n)); SFE_CUDA(m->d_dist.ensure(f->n));
+    if (n > 0) {
+        SFE_CUDA(cudaMemcpyAsync(m->d_xw.p, xw, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+        SFE_CUDA(cudaMemcpyAsync(m->d_dl.p, mp_desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        if (skip) SFE_CUDA(cudaMemcpyAsync(m->d_skip.p, skip, n, cudaMemcpyHostToDevice, st));
+    }
+    int rc = projection_impl(m, m->d_xw.p, m->d_dl.p, skip ? m->d_skip.p : nullptr, n, rt, &f->cam, f->kps.p, f->desc.p, f->n, radius,
+                             best12_threshold, m->d_idx.p, m->d_dist.p, 0, nullptr, &f->grid);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(kp_to_query, m->d_idx.p, sizeof(int32_t) * f->n, cudaMemcpyDeviceToHost, st));
+    if (kp_dist) SFE_CUDA(cudaMemcpyAsync(kp_dist, m->d_dist.p, sizeof(int32_t) * f->n, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+int sfe_frame_search_radius(sfe_matcher *m, const sfe_frame *f, const double *uv, int q, double radius, int32_t *idx, int cap,
+                            int32_t *counts) {
+    SFE_REQUIRE(m && f && q >= 0 && cap >= 1, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
+    if (q == 0) return SFE_OK;
+    SFE_REQUIRE(uv && idx && counts, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    SFE_CUDA(m->d_xw.ensure((size_t)q * 2));
+    SFE_CUDA(m->d_quad.ensure((size_t)q * cap));
+    SFE_CUDA(m->d_n.ensure(q));
+    SFE_CUDA(cudaMemcpyAsync(m->d_xw.p, uv, sizeof(double) * 2 * q, cudaMemcpyHostToDevice, st));
+    search_radius_kernel<<<div_up(q, 64), 64, 0, st>>>(f->grid, f->kps.p, (const double2 *)m->d_xw.p, q, radius, m->d_quad.p, cap, m->d_n.p);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaMemcpyAsync(idx, m->d_quad.p, sizeof(int32_t) * (size_t)q * cap, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(counts, m->d_n.p, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+int sfe_frame_search_nearest(sfe_matcher *m, const sfe_frame *f, const double *uv, int q, int32_t *kpt_index, double *dist2) {
+    SFE_REQUIRE(m && f && q >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
+    if (q == 0) return SFE_OK;
+    SFE_REQUIRE(uv && kpt_index && dist2, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    SFE_CUDA(m->d_xw.ensure((size_t)q * 3));
+    SFE_CUDA(m->d_n.ensure(q));
+    SFE_CUDA(cudaMemcpyAsync(m->d_xw.p, uv, sizeof(double) * 2 * q, cudaMemcpyHostToDevice, st));
+    double *d2 = m->d_xw.p + (size_t)2 * q;
+    search_nearest_kernel<<<div_up(q, 64), 64, 0, st>>>(f->grid, f->kps.p, (const double2 *)m->d_xw.p, q, m->d_n.p, d2);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaMemcpyAsync(kpt_index, m->d_n.p, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(dist2, d2, sizeof(double) * q, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
     return SFE_OK;
 }
 

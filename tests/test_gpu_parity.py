@@ -364,3 +364,53 @@ def test_knn2_full_size_properties(gpu):
     assert np.array_equal(chk2, out[:, 3])
     ratio_pass = (2 * out[:, 1] < out[:, 3]).mean()
     assert 0.2 < ratio_pass <= 1.0
+
+
+# ---- frame glue -----------------------------------------------------------------
+def test_resident_frame_glue_vs_oracle(gpu, oracle, kitti_ex):
+    """Frame::Frame's post-extraction work, StereoFrame::GetDepth, SearchRadius / SearchNeareast and ProjectionMatch
+    against a resident frame: doubles compared bit for bit."""
+    m = api.Matcher()
+    L, R = synth.stereo_pair(4)
+    out = kitti_ex.stereo_frames(L[None], R[None])
+    nl, nr = int(out["n_l"][0]), int(out["n_r"][0])
+    kps, desc, kps_r, sidx = out["kps_l"][0, :nl], out["desc_l"][0, :nl], out["kps_r"][0, :nr], out["stereo_idx"][0, :nl]
+    for dcoef in ([0.0, 0.0, 0.0, 0.0], [-0.05, 0.01, 0.001, -0.002]):
+        cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, dcoef, 1241, 376)
+        ocam = oracle.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, dcoef, 1241, 376)
+        f = api.Frame(m, kps, desc, cam)
+        nrm = f.normalized()
+        ref_n = oracle.normalized_undistort(ocam, kps)
+        assert np.array_equal(nrm.view(np.uint64), ref_n.view(np.uint64)), "normalised keypoints differ in some bit"
+        xc, valid = f.stereo_depth(kps_r, sidx, 0.54)
+        rxc, rvalid = oracle.stereo_depth(ocam, 0.54, kps, ref_n, kps_r, sidx)
+        assert np.array_equal(valid, rvalid) and np.array_equal(xc.view(np.uint64), rxc.view(np.uint64))
+        assert (valid == 1).sum() == (sidx >= 0).sum() > 100
+        ok = (valid == 1) & (kps["octave"] == 0)
+        assert np.isclose(np.median(xc[ok, 2]), synth.KITTI_FX * 0.54 / 24.0)   # the synthetic pair has 24 px disparity
+        # radius / nearest search
+        rng = np.random.default_rng(3)
+        uv = np.stack([rng.uniform(-20, 1260, 200), rng.uniform(-20, 396, 200)], 1)
+        uv[0] = [kps["x"][5], kps["y"][5]]
+        for radius in (10.0, 50.0):
+            got = f.SearchRadius(uv, radius)
+            for i in range(len(uv)):
+                ref, cnt = oracle.search_radius(kps, uv[i, 0], uv[i, 1], radius)
+                assert cnt == len(got[i]) and np.array_equal(got[i], ref), (i, radius)
+        gi, gd = f.SearchNeareast(uv)
+        for i in range(len(uv)):
+            ri, rd = oracle.search_nearest(kps, uv[i, 0], uv[i, 1])
+            assert gi[i] == ri and gd[i] == rd
+        assert gi[0] == 5 and gd[0] == 0.0
+        # ProjectionMatch against the resident frame == the plain entry point == the oracle
+        xy = np.stack([kps["x"], kps["y"]], 1)
+        xw, mpd = synth.projection_scene(xy, desc, 20000, seed=8)
+        a, ad = f.ProjectionMatch(xw, mpd, None, np.eye(3, 4), 50.0)
+        b, bd = m.ProjectionMatch(xw, mpd, None, np.eye(3, 4), cam, kps, desc, 50.0)
+        c, cd = oracle.projection_match(xw, mpd, None, np.eye(3, 4), ocam, kps, desc, 50.0)
+        assert np.array_equal(a, b) and np.array_equal(ad, bd) and np.array_equal(a, c) and np.array_equal(ad, cd)
+    # degenerate frames
+    cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0] * 4, 1241, 376)
+    e = api.Frame(m, kps[:0], desc[:0], cam)
+    assert e.normalized().shape == (0, 2) and e.SearchNeareast([[5.0, 5.0]])[0].tolist() == [-1]
+    assert len(e.SearchRadius([[5.0, 5.0]], 50.0)[0]) == 0

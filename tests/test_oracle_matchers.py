@@ -185,3 +185,35 @@ def test_knn2_and_hamming(oracle):
     for i in range(40):
         c = sorted([(a[i, 1], a[i, 0]), (a[i, 3], a[i, 2]), (b[i, 1], b[i, 0]), (b[i, 3], b[i, 2])])
         assert [c[0][1], c[0][0], c[1][1], c[1][0]] == out[i].tolist()
+
+
+def test_frame_glue_oracle_properties(oracle):
+    """orc_normalized_undistort inverts Distort (the reference's 5-step fixed point, src/camera.cpp:95-109) and the
+    searches agree with a numpy restatement."""
+    import numpy as np
+    from slam_toolkit_b200 import synth
+    rng = np.random.default_rng(0)
+    k = np.zeros(500, oracle.KP_DTYPE)
+    k["x"], k["y"] = rng.uniform(0, 1241, 500).astype(np.float32), rng.uniform(0, 376, 500).astype(np.float32)
+    d = [-0.05, 0.01, 0.001, -0.002]
+    cam = oracle.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, d, 1241, 376)
+    n = oracle.normalized_undistort(cam, k)
+    x, y = n[:, 0], n[:, 1]
+    r2 = x * x + y * y
+    cd = 1 + d[0] * r2 + d[1] * r2 * r2
+    xd = x * cd + d[2] * 2 * x * y + d[3] * (r2 + 2 * x * x)
+    yd = y * cd + d[2] * (r2 + 2 * y * y) + d[3] * 2 * x * y
+    # five iterations only (as in the reference): converged to well under a thousandth of a pixel at the image corners
+    assert np.abs(xd * synth.KITTI_FX + synth.KITTI_CX - k["x"]).max() < 1e-3
+    assert np.abs(yd * synth.KITTI_FY + synth.KITTI_CY - k["y"]).max() < 1e-3
+    cam0 = oracle.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0] * 4, 1241, 376)
+    n0 = oracle.normalized_undistort(cam0, k)
+    assert np.abs(n0[:, 0] - (k["x"].astype(np.float64) - synth.KITTI_CX) / synth.KITTI_FX).max() < 1e-15
+    for u, v, r in ((600.0, 180.0, 50.0), (0.0, 0.0, 100.0), (float(k["x"][3]), float(k["y"][3]), 1.0)):
+        d2 = (u - k["x"].astype(np.float64)) ** 2 + (v - k["y"].astype(np.float64)) ** 2
+        idx, cnt = oracle.search_radius(k, u, v, r)
+        assert np.array_equal(idx, np.nonzero(d2 < r * r)[0]) and cnt == len(idx)
+        i, dd = oracle.search_nearest(k, u, v)
+        assert i == int(np.argmin(d2)) and dd == d2.min()
+    xc, valid = oracle.stereo_depth(cam0, 0.5, k[:3], n0[:3], k[3:6], np.array([0, -1, 2], np.int32))
+    assert valid.tolist()[1] == 0 and valid[0] in (1, 2)
