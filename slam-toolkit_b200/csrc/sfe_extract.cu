@@ -53,31 +53,58 @@ struct PyrStep {            // geometry of one resize launch, in the kernel para
     int w, h, pitch, plane_off;      // destination level
     int src_w, src_pitch, src_plane_off, src_is_input;
     int xtab_off, ytab_off;
+    int src_level, box_w, box_h;     // TMA variant: source level and its box
 };
 
+// kTma: the source pixels of the tile (box P.box_w x P.box_h bytes, origin on the 16-byte grid of the source row)
+// arrive by one TMA load, so the horizontal pass reads shared memory instead of waiting on global loads
+// (the plain variant spent 56 % of its stall samples on the long scoreboard).
+template <bool kTma>
 __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, const uint2 *__restrict__ xtab,
-                                                         const uint2 *__restrict__ ytab) {
-    extern __shared__ __align__(16) uint16_t pyr_u[];  // [source row][kPyrTileW]
+                                                         const uint2 *__restrict__ ytab, const __grid_constant__ TmaMaps M) {
+    extern __shared__ __align__(128) uint8_t pyr_smem[];
+    uint16_t *pyr_u = (uint16_t *)(pyr_smem + (kTma ? P.box_w * P.box_h : 0));  // [source row][kPyrTileW]
+    __shared__ uint64_t bar;
     const int x0 = blockIdx.x * kPyrTileW, y0 = blockIdx.y * kPyrTileH, img = blockIdx.z, tid = threadIdx.x;
     const uint2 *yt = ytab + P.ytab_off;
     const int sy_first = __ldg(&yt[y0]).x & 0xFFFF;                               // rows are monotone in y
     const int n_rows = (int)(__ldg(&yt[min(y0 + kPyrTileH, P.h) - 1]).x >> 16) - sy_first + 1;
     const int slot = slot_of(S, img);
-    const uint8_t *src;
-    if (P.src_is_input)
-        src = img < S.split ? S.in_a + (size_t)img * S.in_stride : S.in_b + (size_t)(img - S.split) * S.in_stride;
-    else
-        src = S.pyr + (size_t)slot * S.pyr_stride + P.src_plane_off;
+    const int xa = (int)__ldg(&xtab[P.xtab_off + x0]).x & ~15;  // source column of shared column 0 (columns are monotone in x)
+    if (kTma && tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, (uint32_t)(P.box_w * P.box_h));
+        const bool set_a = img < S.split;
+        const CUtensorMap *map = P.src_is_input ? (set_a ? &M.lv[0] : &M.l0b) : &M.lv[P.src_level];
+        const int z = P.src_is_input ? S.in_z0 + (set_a ? img : img - S.split) : slot;
+        tma_load_3d(pyr_smem, map, &bar, xa, sy_first, z);
+    }
     {   // horizontal: thread = output column, walking the source rows
         const int ox = tid & (kPyrTileW - 1);
         const uint2 xt = __ldg(&xtab[P.xtab_off + min(x0 + ox, P.w - 1)]);
         const int sx = xt.x, d1 = min(sx + 1, P.src_w - 1) - sx;
         const uint32_t w0 = xt.y & 0xFFFF, w1 = xt.y >> 16;
-        const uint8_t *p = src + (size_t)(sy_first + (tid >> 6)) * P.src_pitch + sx;
-        const int step = 4 * P.src_pitch;
-        for (int r = tid >> 6; r < n_rows; r += 4) {
-            pyr_u[r * kPyrTileW + ox] = (uint16_t)((__ldg(p) * w0 + __ldg(p + d1) * w1) >> 4);
-            p += step;
+        if (kTma) {
+            __syncthreads();  // barrier initialised
+            mbar_wait(&bar, 0);
+            const uint8_t *p = pyr_smem + (tid >> 6) * P.box_w + (sx - xa);
+            const int step = 4 * P.box_w;
+            for (int r = tid >> 6; r < n_rows; r += 4) {
+                pyr_u[r * kPyrTileW + ox] = (uint16_t)((p[0] * w0 + p[d1] * w1) >> 4);
+                p += step;
+            }
+        } else {
+            const uint8_t *src;
+            if (P.src_is_input)
+                src = img < S.split ? S.in_a + (size_t)img * S.in_stride : S.in_b + (size_t)(img - S.split) * S.in_stride;
+            else
+                src = S.pyr + (size_t)slot * S.pyr_stride + P.src_plane_off;
+            const uint8_t *p = src + (size_t)(sy_first + (tid >> 6)) * P.src_pitch + sx;
+            const int step = 4 * P.src_pitch;
+            for (int r = tid >> 6; r < n_rows; r += 4) {
+                pyr_u[r * kPyrTileW + ox] = (uint16_t)((__ldg(p) * w0 + __ldg(p + d1) * w1) >> 4);
+                p += step;
+            }
         }
     }
     __syncthreads();
@@ -979,7 +1006,8 @@ struct sfe_extractor {
     FastPlan fast{};
     // TMA descriptors (fast: TP x tile_rows boxes, blur: 144 x 38 boxes); level >= 1 entries follow the plan,
     // level-0 entries follow the images of the current call
-    alignas(64) TmaMaps fast_maps{}, blur_maps{};
+    alignas(64) TmaMaps fast_maps{}, blur_maps{}, pyr_maps{};  // pyr_maps.lv[l] = level l as the SOURCE of level l + 1
+    int pyr_box_w = 0, pyr_box_h = 0;
     bool tma_plan_ok = false, tma_disabled = false, tma_now = false;
     const void *l0_key[2] = {nullptr, nullptr};
     size_t l0_geom[4] = {0, 0, 0, 0};
@@ -1050,7 +1078,7 @@ static void build_tables(sfe_extractor *ex) {
 static int build_plan(sfe_extractor *ex, int w, int h) {
     const int nl = ex->prm.nlevels;
     std::vector<uint2> xtab, ytab;
-    int max_src_rows = 1;
+    int max_src_rows = 1, max_src_cols = 1;
     memset(&ex->fast, 0, sizeof(ex->fast));
     ex->cells.clear();
     int max_sw = 7, max_sh = 7;
@@ -1163,6 +1191,11 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                 const int y0 = std::min(std::max(sy, 0), sh - 1), y1 = std::min(std::max(sy + 1, 0), sh - 1);
                 ytab.push_back(make_uint2((unsigned)y0 | (unsigned)y1 << 16, (unsigned)b0 | (unsigned)b1 << 16));
             }
+            for (int tx = 0; tx < L.w; tx += kPyrTileW) {  // source columns one output tile touches, from the 16-byte grid
+                const int last = std::min(tx + kPyrTileW, L.w) - 1;
+                const int first_sx = (int)xtab[L.xtab_off + tx].x & ~15;
+                max_src_cols = std::max(max_src_cols, std::min((int)xtab[L.xtab_off + last].x + 1, sw - 1) - first_sx + 1);
+            }
             for (int ty = 0; ty < L.h; ty += kPyrTileH) {  // source rows one output tile touches
                 const int last = std::min(ty + kPyrTileH, L.h) - 1;
                 const int span = (int)(ytab[L.ytab_off + last].x >> 16) - (int)(ytab[L.ytab_off + ty].x & 0xFFFF) + 1;
@@ -1177,7 +1210,10 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     ex->max_cand = (std::max(max_cand, 1) + 7) & ~7;
     ex->max_nodes = max_nodes;
     ex->pyr_smem = (size_t)max_src_rows * kPyrTileW * sizeof(uint16_t);
-    SFE_REQUIRE(ex->pyr_smem <= 48 * 1024, SFE_ERR_UNSUPPORTED, "scale factor too large for the pyramid tile");
+    ex->pyr_box_w = (int)align_up((size_t)max_src_cols, 16);
+    ex->pyr_box_h = max_src_rows;
+    SFE_REQUIRE(ex->pyr_smem + (size_t)ex->pyr_box_w * ex->pyr_box_h <= 48 * 1024 && ex->pyr_box_w <= 256 && ex->pyr_box_h <= 256,
+                SFE_ERR_UNSUPPORTED, "scale factor too large for the pyramid tile");
     ex->fast.nlevels = nl;
     ex->fast.ini_th = ex->prm.ini_th_fast;
     ex->fast.min_th = ex->prm.min_th_fast;
@@ -1222,7 +1258,9 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
         ex->tma_plan_ok = tma_encode_u8_3d(&ex->fast_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
                                            ex->fast.tile_pitch, ex->fast.tile_rows) &&
                           tma_encode_u8_3d(&ex->blur_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
-                                           kBlurInWords * 4, kBlurTileH + 6);
+                                           kBlurInWords * 4, kBlurTileH + 6) &&
+                          (nl < 2 || tma_encode_u8_3d(&ex->pyr_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
+                                                      ex->pyr_box_w, ex->pyr_box_h));
     }
     ex->l0_key[0] = ex->l0_key[1] = nullptr;
     ex->pitch0 = (int)align_up((size_t)w, 16);
@@ -1297,7 +1335,10 @@ static void prepare_l0_maps(sfe_extractor *ex, const uint8_t *a, const uint8_t *
         const bool ok = tma_encode_u8_3d(&ex->fast_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, ex->fast.tile_pitch, ex->fast.tile_rows) &&
                         tma_encode_u8_3d(&ex->fast_maps.l0b, b, L.w, L.h, n_b, pitch, stride, ex->fast.tile_pitch, ex->fast.tile_rows) &&
                         tma_encode_u8_3d(&ex->blur_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, kBlurInWords * 4, kBlurTileH + 6) &&
-                        tma_encode_u8_3d(&ex->blur_maps.l0b, b, L.w, L.h, n_b, pitch, stride, kBlurInWords * 4, kBlurTileH + 6);
+                        tma_encode_u8_3d(&ex->blur_maps.l0b, b, L.w, L.h, n_b, pitch, stride, kBlurInWords * 4, kBlurTileH + 6) &&
+                        (ex->prm.nlevels < 2 ||
+                         (tma_encode_u8_3d(&ex->pyr_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, ex->pyr_box_w, ex->pyr_box_h) &&
+                          tma_encode_u8_3d(&ex->pyr_maps.l0b, b, L.w, L.h, n_b, pitch, stride, ex->pyr_box_w, ex->pyr_box_h)));
         ex->l0_key[0] = ok ? a : nullptr;
         ex->l0_key[1] = ok ? b : nullptr;
         memcpy(ex->l0_geom, geom, sizeof(geom));
@@ -1323,9 +1364,13 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     prof_mark(ex, 0);
     for (int l = 1; l < nl; l++) {
         const LevelPlan &D = ex->lv[l], &Q = ex->lv[l - 1];
-        const PyrStep P{D.w, D.h, D.pitch, D.plane_off, Q.w, l == 1 ? S.in_pitch : Q.pitch, Q.plane_off, l == 1, D.xtab_off, D.ytab_off};
+        const PyrStep P{D.w, D.h, D.pitch, D.plane_off, Q.w, l == 1 ? S.in_pitch : Q.pitch, Q.plane_off, l == 1, D.xtab_off, D.ytab_off,
+                        l - 1, ex->pyr_box_w, ex->pyr_box_h};
         dim3 grid(div_up(D.w, kPyrTileW), div_up(D.h, kPyrTileH), count);
-        pyr_resize_kernel<<<grid, 256, ex->pyr_smem, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p);
+        if (ex->tma_now)
+            pyr_resize_kernel<true><<<grid, 256, ex->pyr_smem + (size_t)ex->pyr_box_w * ex->pyr_box_h, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p, ex->pyr_maps);
+        else
+            pyr_resize_kernel<false><<<grid, 256, ex->pyr_smem, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p, ex->pyr_maps);
         ex->launches++;
     }
     prof_mark(ex, 1);
