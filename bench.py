@@ -400,7 +400,7 @@ def main():
         line["hamming"] = hamming
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        frames = args.cpu_frames or 16 * cores   # ~1.5 s per core: 10-30 s of CPU work in all
+        frames = args.cpu_frames or 32 * cores   # ~2 s per core: 10-30 s of CPU work in all
         cpu_sample(cores, cores)                 # warm-up
         fps_all, dt_all, _, _ = cpu_sample(frames, cores)
         fps_1, dt_1, _, _ = cpu_sample(8, 1)

@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, co
 //   load     the cell's sub-image into shared memory as aligned 32-bit words (two global words +
 //            funnel shift per word: cell origins are not word aligned)
 //   stage 0  compass pre-test, 4 pixels per thread in 16x2 SIMD lanes: any 9-arc of the 16-pixel
-//            circle contains >= 2 of the 4 compass pixels, so a corner needs >= 2 compass pixels
-//            brighter than v+t or >= 2 darker than v-t; survivors are compacted (warp scan + one
-//            shared atomic per warp) so later stages run with full warps
+//            circle contains two neighbouring compass pixels, so a corner needs a vertical and a
+//            horizontal compass pixel both brighter than v+t or both darker than v-t; survivors are
+//            compacted into a list so later stages run with full warps
 //   stage 1  exact score best(p) on the survivors, two pixels per thread in 16x2 lanes
 //            (VIMNMX3.S16x2); corner iff best > t
 //   stage 2  cell-local non-max suppression (strict > over 8 neighbours, outside the cell = 0)
@@ -147,15 +147,16 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, co
 // must start on a 16-byte multiple of the row, and stage 0 then works on the level's own 4-pixel words.
 constexpr int kScorePitch = 64;  // >= kMaxSub - 6 + 2
 
-// Compass pre-test of two pixels held in the 16-bit lanes of c (centre) and p0..p3 (compass pixels).
-// k = 0x7FFF - t in both lanes.  Lane bit 15 of (p + k - c) is set iff p > c + t, of (c + k - p) iff
-// p < c - t; no lane ever carries or borrows (all values stay inside [0x7E02, 0x80FE]).
-__device__ __forceinline__ uint32_t compass2(uint32_t c, uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t k) {
+// Compass pre-test of two pixels held in the 16-bit lanes of c (centre), v0 / v1 (the vertical compass pixels, circle
+// positions 8 and 0) and h0 / h1 (the horizontal ones, positions 12 and 4).  Any arc of 9 consecutive circle
+// positions contains two compass positions that are NEIGHBOURS on the compass (0-4, 4-8, 8-12 or 12-0), so a
+// corner needs one vertical AND one horizontal compass pixel brighter than c + t, or both darker than c - t:
+// (v0 | v1) & (h0 | h1).  k = 0x7FFF - t in both lanes: lane bit 15 of (p + k - c) is set iff p > c + t, of
+// (c + k - p) iff p < c - t; no lane ever carries or borrows (all values stay inside [0x7E02, 0x80FE]).
+__device__ __forceinline__ uint32_t compass2(uint32_t c, uint32_t v0, uint32_t v1, uint32_t h0, uint32_t h1, uint32_t k) {
     const uint32_t A = k - c, B = k + c;
-    const uint32_t b0 = p0 + A, b1 = p1 + A, b2 = p2 + A, b3 = p3 + A;
-    const uint32_t d0 = B - p0, d1 = B - p1, d2 = B - p2, d3 = B - p3;
-    const uint32_t rb = ((b0 & b1) | (b0 & b2) | (b1 & b2)) | (b3 & (b0 | b1 | b2));  // >= 2 of 4 brighter
-    const uint32_t rd = ((d0 & d1) | (d0 & d2) | (d1 & d2)) | (d3 & (d0 | d1 | d2));  // >= 2 of 4 darker
+    const uint32_t rb = ((v0 + A) | (v1 + A)) & ((h0 + A) | (h1 + A));
+    const uint32_t rd = ((B - v0) | (B - v1)) & ((B - h0) | (B - h1));
     return (rb | rd) & 0x80008000u;
 }
 
