@@ -81,6 +81,7 @@ typedef struct sfe_matcher sfe_matcher;
 typedef struct sfe_db sfe_db;
 typedef struct sfe_event sfe_event;
 typedef struct sfe_frame sfe_frame;
+typedef struct sfe_vocab sfe_vocab;
 
 /* ---- general -------------------------------------------------------------------------- */
 int sfe_abi_version(void);
@@ -233,6 +234,28 @@ int sfe_frame_search_radius(sfe_matcher *m, const sfe_frame *f, const double *uv
  * the smaller index; -1 for an empty frame. */
 int sfe_frame_search_nearest(sfe_matcher *m, const sfe_frame *f, const double *uv /* q x 2 */, int q,
                              int32_t *kpt_index, double *dist2);
+
+/* ---- BoW transform (Frame::ComputeBoW, src/frame.cpp:419-427 -> DBoW2 TemplatedVocabulary::transform) ----------
+ * The vocabulary as TemplatedVocabulary::loadFromTextFile holds it (thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:
+ * 1338-1421): node 0 = root, node i >= 1 has parent[i] < i, a flag is_leaf[i], a 32-byte descriptor and a weight; the
+ * children of a node are the nodes naming it as parent, in id order; words are numbered over the flagged nodes in
+ * id order.  L = the header's depth (the `nid` level is counted from it). */
+int sfe_vocab_create(sfe_matcher *m, int n_nodes, const int32_t *parent, const uint8_t *is_leaf,
+                     const uint8_t *desc /* n_nodes x 32 */, const double *weight, int L, sfe_vocab **out);
+int sfe_vocab_destroy(sfe_vocab *v);
+int sfe_vocab_words(const sfe_vocab *v, int *n_words);
+/* per feature: transform(feature, word_id, weight, nid, levelsup) (:1218-1259): word, its weight and the node at
+ * level L - levelsup on the way down (0 when the descent ends above that level; the reference leaves it unwritten). */
+int sfe_vocab_transform(sfe_matcher *m, const sfe_vocab *v, const uint8_t *desc /* n x 32 */, int n,
+                        int levelsup, int32_t *word_id, double *weight, int32_t *node_id);
+int sfe_vocab_transform_dev(sfe_matcher *m, const sfe_vocab *v, const uint8_t *desc_dev, int n, int levelsup,
+                            int32_t *word_id_dev, double *weight_dev, int32_t *node_id_dev);
+/* Host-side BowVector assembly in the reference's order of operations (:1127-1194, BowVector.cpp:34-84).
+ * weighting: 0 TF_IDF, 1 TF, 2 IDF, 3 BINARY; norm: 0 none, 1 L1, 2 L2 (what the scoring object's mustNormalize says;
+ * ORBvoc.txt is "10 6 0 0": L1_NORM scoring -> norm 1, TF_IDF).  ids ascending; *n_out entries (ids/values may be
+ * NULL to query the size).  The FeatureVector is node_id -> the feature indices with weight > 0, in feature order. */
+int sfe_bow_assemble(const int32_t *word_id, const double *weight, int n, int weighting, int norm,
+                     int32_t *ids, double *values, int cap, int *n_out);
 
 /* Sharded ProjectionMatch (map points partitioned over GPUs, frame replicated): each shard emits per keypoint
  * the key (dist << 32 | ~global map-point index) of its best accepted query -- the minimum over shards is the

@@ -256,6 +256,19 @@ def search_nearest(kps, u, v):
     return i.value, d.value
 
 
+def vocab_transform(parent, is_leaf, node_desc, node_weight, L, features, levelsup):
+    parent = np.ascontiguousarray(parent, np.int32)
+    is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+    node_desc = np.ascontiguousarray(node_desc, np.uint8)
+    node_weight = np.ascontiguousarray(node_weight, np.float64)
+    features = np.ascontiguousarray(features, np.uint8)
+    n = len(features)
+    wid, w, nid = np.zeros(n, np.int32), np.zeros(n, np.float64), np.zeros(n, np.int32)
+    lib().orc_vocab_transform(len(parent), _p(parent), _p(is_leaf), _p(node_desc), _p(node_weight), L, _p(features), n, levelsup,
+                              _p(wid), _p(w), _p(nid))
+    return wid, w, nid
+
+
 def knn2(queries, db, idx_base=0):
     queries = np.ascontiguousarray(queries, np.uint8)
     db = np.ascontiguousarray(db, np.uint8)

@@ -769,6 +769,50 @@ void orc_search_nearest(const orc_keypoint *kps, int m, double u, double v, int 
     }
 }
 
+/* ---- BoW transform: DBoW2 TemplatedVocabulary::transform(feature, word_id, weight, nid, levelsup),
+ * thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259, on a vocabulary held as loadFromTextFile builds it (:1338-1421):
+ * node 0 = root; node i >= 1 has parent[i], a 32-byte descriptor and a weight; the children of a node are the nodes that
+ * name it as parent, in id order; words are numbered in id order over the nodes flagged is_leaf; isLeaf() = no children.
+ * F::distance = 256-bit Hamming (FORB.cpp:81-101), strict < keeps the first child on ties.
+ * T7 (canonical): the reference leaves *nid unwritten when the descent reaches a leaf above level L - levelsup; here 0. */
+void orc_vocab_transform(int n_nodes, const int32_t *parent, const uint8_t *is_leaf, const uint8_t *node_desc,
+                         const double *node_weight, int L, const uint8_t *features, int n, int levelsup,
+                         int32_t *word_id, double *weight, int32_t *node_id) {
+    int *n_child = (int *)calloc((size_t)n_nodes + 1, sizeof(int));
+    int *start = (int *)calloc((size_t)n_nodes + 2, sizeof(int));
+    int *list = (int *)calloc((size_t)n_nodes + 1, sizeof(int));
+    int *wid = (int *)calloc((size_t)n_nodes + 1, sizeof(int));
+    for (int i = 1; i < n_nodes; i++) n_child[parent[i]]++;
+    for (int i = 0; i < n_nodes; i++) start[i + 1] = start[i] + n_child[i];
+    for (int i = 0; i < n_nodes; i++) n_child[i] = 0;
+    int words = 0;
+    for (int i = 1; i < n_nodes; i++) {
+        list[start[parent[i]] + n_child[parent[i]]++] = i;
+        if (is_leaf[i]) wid[i] = words++;
+    }
+    const int nid_level = L - levelsup;
+    for (int f = 0; f < n; f++) {
+        const uint8_t *feat = features + (size_t)32 * f;
+        int nid = 0, final_id = 0, level = 0;
+        do {
+            ++level;
+            const int *ch = list + start[final_id];
+            const int nc = start[final_id + 1] - start[final_id];
+            final_id = ch[0];
+            double best = (double)orc_hamming256(feat, node_desc + (size_t)32 * final_id);
+            for (int c = 1; c < nc; c++) {
+                const double d = (double)orc_hamming256(feat, node_desc + (size_t)32 * ch[c]);
+                if (d < best) { best = d; final_id = ch[c]; }
+            }
+            if (level == nid_level) nid = final_id;
+        } while (start[final_id + 1] > start[final_id]);
+        word_id[f] = wid[final_id];
+        weight[f] = node_weight[final_id];
+        node_id[f] = nid;
+    }
+    free(n_child); free(start); free(list); free(wid);
+}
+
 /* ---- brute-force top-2: the StereoMatch/ProjectionMatch inner loop
  * with the whole database as candidate set; strict < in ascending index = lexicographic
  * (dist, idx). */

@@ -89,6 +89,12 @@ void orc_stereo_depth(const orc_camera *cam, double baseline, const orc_keypoint
 int orc_search_radius(const orc_keypoint *kps, int m, double u, double v, double radius, int *idx, int cap);
 void orc_search_nearest(const orc_keypoint *kps, int m, double u, double v, int *kpt_index, double *dist2);
 
+/* BoW transform, thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259; T7: nid = 0 when the descent
+ * ends above level L - levelsup (the reference leaves it unwritten). */
+void orc_vocab_transform(int n_nodes, const int32_t *parent, const uint8_t *is_leaf, const uint8_t *node_desc,
+                         const double *node_weight, int L, const uint8_t *features, int n, int levelsup,
+                         int32_t *word_id, double *weight, int32_t *node_id);
+
 /* CPU baseline helper: extract L + extract R + stereo match for `count` stereo
  * frames with `nthreads` worker threads (one frame per thread at a time).
  * left/right: count contiguous w*h images.  Returns total matches. */

@@ -110,6 +110,12 @@ SIGNATURES = {
     "sfe_frame_projection_match": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _vp, _vp]),
     "sfe_frame_search_radius": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp]),
     "sfe_frame_search_nearest": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "sfe_vocab_create": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _pp]),
+    "sfe_vocab_destroy": (_i, [_vp]),
+    "sfe_vocab_words": (_i, [_vp, C.POINTER(_i)]),
+    "sfe_vocab_transform": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sfe_vocab_transform_dev": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sfe_bow_assemble": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "sfe_db_create": (_i, [_vp, _vp, _i64, _i64, _pp]),
     "sfe_db_destroy": (_i, [_vp]),
     "sfe_knn2": (_i, [_vp, _vp, _vp, _i, _vp]),
@@ -577,6 +583,66 @@ class Frame:
         d2 = np.zeros(len(uv), np.float64)
         _check(lib().sfe_frame_search_nearest(self.m.h, self.h, _p(uv), len(uv), _p(idx), _p(d2)))
         return idx, d2
+
+
+class Vocabulary:
+    """DBoW2 ORB vocabulary on the device (thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h): arrays as loadFromTextFile
+    reads them -- parent, is_leaf flag, 32-byte descriptor and weight per node, node 0 = root."""
+    TF_IDF, TF, IDF, BINARY = range(4)
+    NORM_NONE, NORM_L1, NORM_L2 = range(3)
+
+    def __init__(self, matcher: "Matcher", parent, is_leaf, desc, weight, L, weighting=0, norm=1):
+        self.m, self.L, self.weighting, self.norm = matcher, L, weighting, norm
+        parent = np.ascontiguousarray(parent, np.int32)
+        is_leaf = np.ascontiguousarray(is_leaf, np.uint8)
+        desc = np.ascontiguousarray(desc, np.uint8)
+        weight = np.ascontiguousarray(weight, np.float64)
+        h = C.c_void_p()
+        _check(lib().sfe_vocab_create(matcher.h, len(parent), _p(parent), _p(is_leaf), _p(desc), _p(weight), L, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sfe_vocab_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def words(self) -> int:
+        n = C.c_int()
+        _check(lib().sfe_vocab_words(self.h, C.byref(n)))
+        return n.value
+
+    def transform_features(self, desc, levelsup=4):
+        """-> (word_id, weight, node_id) per feature: TemplatedVocabulary::transform(feature, id, w, &nid, levelsup)."""
+        desc = np.ascontiguousarray(desc, np.uint8)
+        n = len(desc)
+        wid, w, nid = np.zeros(n, np.int32), np.zeros(n, np.float64), np.zeros(n, np.int32)
+        _check(lib().sfe_vocab_transform(self.m.h, self.h, _p(desc), n, levelsup, _p(wid), _p(w), _p(nid)))
+        return wid, w, nid
+
+    def transform(self, desc, levelsup=4):
+        """voc->transform(vdesc, bowvec, featvec, levelsup) (src/frame.cpp:419-427) -> (BowVector as (ids, values),
+        FeatureVector as {node id: [feature indices]})."""
+        wid, w, nid = self.transform_features(desc, levelsup)
+        ids, vals = bow_assemble(wid, w, self.weighting, self.norm)
+        fv = {}
+        for i in np.nonzero(w > 0)[0]:
+            fv.setdefault(int(nid[i]), []).append(int(i))
+        return (ids, vals), dict(sorted(fv.items()))
+
+
+def bow_assemble(word_id, weight, weighting=0, norm=1):
+    word_id = np.ascontiguousarray(word_id, np.int32)
+    weight = np.ascontiguousarray(weight, np.float64)
+    n = C.c_int()
+    ids, vals = np.zeros(len(word_id), np.int32), np.zeros(len(word_id), np.float64)
+    _check(lib().sfe_bow_assemble(_p(word_id), _p(weight), len(word_id), weighting, norm, _p(ids), _p(vals), len(ids), C.byref(n)))
+    return ids[:n.value].copy(), vals[:n.value].copy()
 
 
 class DescriptorDB:

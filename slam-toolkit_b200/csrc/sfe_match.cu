@@ -532,6 +532,54 @@ __global__ void search_nearest_kernel(KpGrid G, const sfe_keypoint *__restrict__
     dist2[i] = bd;
 }
 
+// ---------------------------------------------------------------------------------------------
+// BoW transform: the tree descent of DBoW2's TemplatedVocabulary::transform
+// (thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1218-1259).  One warp per feature: lane c scores child c of the
+// current node (256-bit Hamming, FORB.cpp:81-101), the warp takes the minimum of (distance, child rank) -- the
+// reference's strict < keeps the first child on ties -- and steps down until it reaches a node without children.
+// ---------------------------------------------------------------------------------------------
+struct VocabDev {
+    const int *child_start;   // n_nodes + 1
+    const int *child_list;    // children in id order
+    const uint8_t *desc;      // n_nodes x 32
+    const double *weight;
+    const int *word_id;
+    int n_nodes, L;
+};
+
+__global__ void __launch_bounds__(256) vocab_transform_kernel(VocabDev V, const uint8_t *__restrict__ feat, int n, int levelsup,
+                                                              int32_t *__restrict__ word_id, double *__restrict__ weight,
+                                                              int32_t *__restrict__ node_id) {
+    const int f = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (f >= n) return;
+    uint32_t a[8];
+    load_desc(feat + (size_t)f * 32, a);
+    const int nid_level = V.L - levelsup;
+    int nid = 0, cur = 0, level = 0;
+    for (;;) {
+        const int s = V.child_start[cur], nc = V.child_start[cur + 1] - s;
+        if (nc == 0) break;  // isLeaf()
+        ++level;
+        uint32_t best = kNoKey;
+        for (int c0 = 0; c0 < nc; c0 += 32) {  // k <= 20 in DBoW2's text format, so one round
+            uint32_t key = kNoKey;
+            if (c0 + lane < nc) {
+                uint32_t b[8];
+                load_desc(V.desc + (size_t)V.child_list[s + c0 + lane] * 32, b);
+                key = (uint32_t)hamming8(a, b) << 20 | (uint32_t)(c0 + lane);
+            }
+            best = min(best, __reduce_min_sync(0xffffffffu, key));
+        }
+        cur = V.child_list[s + (best & 0xFFFFF)];
+        if (level == nid_level) nid = cur;
+    }
+    if (lane == 0) {
+        word_id[f] = V.word_id[cur];
+        weight[f] = V.weight[cur];
+        node_id[f] = nid;
+    }
+}
+
 }  // namespace sfe
 
 using namespace sfe;
@@ -559,6 +607,13 @@ struct sfe_db {
 
 // keys_out != nullptr: leave the per-keypoint (dist << 32 | ~global query) keys there (one shard's contribution to a
 // sharded match) instead of decoding them
+struct sfe_vocab {
+    int device = 0, n_nodes = 0, L = 0, n_words = 0;
+    DevBuf<int> child_start, child_list, word_id;
+    DevBuf<uint8_t> desc;
+    DevBuf<double> weight;
+};
+
 struct sfe_frame {
     int device = 0;
     int n = 0;
@@ -984,6 +1039,138 @@ int sfe_frame_search_nearest(sfe_matcher *m, const sfe_frame *f, const double *u
     SFE_CUDA(cudaMemcpyAsync(kpt_index, m->d_n.p, sizeof(int32_t) * q, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaMemcpyAsync(dist2, d2, sizeof(double) * q, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+// ---- vocabulary -----------------------------------------------------------------------
+int sfe_vocab_create(sfe_matcher *m, int n_nodes, const int32_t *parent, const uint8_t *is_leaf, const uint8_t *desc,
+                     const double *weight, int L, sfe_vocab **out) {
+    SFE_REQUIRE(m && parent && is_leaf && desc && weight && out, SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(n_nodes >= 2 && L >= 1, SFE_ERR_BAD_ARG, "empty vocabulary");
+    std::vector<int> start(n_nodes + 1, 0), list(n_nodes, 0), fill(n_nodes, 0), wid(n_nodes, 0);
+    for (int i = 1; i < n_nodes; i++) {
+        SFE_REQUIRE(parent[i] >= 0 && parent[i] < i, SFE_ERR_BAD_ARG, "a node must follow its parent (loadFromTextFile order)");
+        start[parent[i] + 1]++;
+    }
+    for (int i = 0; i < n_nodes; i++) start[i + 1] += start[i];
+    int words = 0;
+    for (int i = 1; i < n_nodes; i++) {
+        list[start[parent[i]] + fill[parent[i]]++] = i;
+        if (is_leaf[i]) wid[i] = words++;
+    }
+    SFE_REQUIRE(start[1] > 0, SFE_ERR_BAD_ARG, "the root has no children");
+    DeviceGuard g(m->device);
+    sfe_vocab *v = new sfe_vocab();
+    v->device = m->device;
+    v->n_nodes = n_nodes;
+    v->L = L;
+    v->n_words = words;
+    cudaError_t e = v->child_start.ensure(n_nodes + 1);
+    if (e == cudaSuccess) e = v->child_list.ensure(n_nodes);
+    if (e == cudaSuccess) e = v->word_id.ensure(n_nodes);
+    if (e == cudaSuccess) e = v->desc.ensure((size_t)n_nodes * 32);
+    if (e == cudaSuccess) e = v->weight.ensure(n_nodes);
+    if (e == cudaSuccess) e = cudaMemcpy(v->child_start.p, start.data(), sizeof(int) * (n_nodes + 1), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->child_list.p, list.data(), sizeof(int) * n_nodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->word_id.p, wid.data(), sizeof(int) * n_nodes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->desc.p, desc, (size_t)n_nodes * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(v->weight.p, weight, sizeof(double) * n_nodes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        set_error("vocabulary upload: %s", cudaGetErrorString(e));
+        sfe_vocab_destroy(v);
+        return SFE_ERR_CUDA;
+    }
+    *out = v;
+    return SFE_OK;
+}
+
+int sfe_vocab_destroy(sfe_vocab *v) {
+    if (!v) return SFE_OK;
+    DeviceGuard g(v->device);
+    v->child_start.release(); v->child_list.release(); v->word_id.release(); v->desc.release(); v->weight.release();
+    delete v;
+    return SFE_OK;
+}
+
+int sfe_vocab_words(const sfe_vocab *v, int *n_words) {
+    SFE_REQUIRE(v && n_words, SFE_ERR_BAD_ARG, "null argument");
+    *n_words = v->n_words;
+    return SFE_OK;
+}
+
+static int vocab_launch(sfe_matcher *m, const sfe_vocab *v, const uint8_t *feat_dev, int n, int levelsup, int32_t *wid, double *w,
+                        int32_t *nid) {
+    VocabDev V{v->child_start.p, v->child_list.p, v->desc.p, v->weight.p, v->word_id.p, v->n_nodes, v->L};
+    vocab_transform_kernel<<<div_up(n, 8), 256, 0, m->stream>>>(V, feat_dev, n, levelsup, wid, w, nid);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    return SFE_OK;
+}
+
+int sfe_vocab_transform_dev(sfe_matcher *m, const sfe_vocab *v, const uint8_t *desc_dev, int n, int levelsup, int32_t *word_id_dev,
+                            double *weight_dev, int32_t *node_id_dev) {
+    SFE_REQUIRE(m && v && n >= 0 && levelsup >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(v->device == m->device, SFE_ERR_BAD_ARG, "vocabulary lives on another device");
+    if (n == 0) return SFE_OK;
+    SFE_REQUIRE(desc_dev && word_id_dev && weight_dev && node_id_dev, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    int rc = vocab_launch(m, v, desc_dev, n, levelsup, word_id_dev, weight_dev, node_id_dev);
+    if (rc != SFE_OK) return rc;
+    if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
+    return SFE_OK;
+}
+
+int sfe_vocab_transform(sfe_matcher *m, const sfe_vocab *v, const uint8_t *desc, int n, int levelsup, int32_t *word_id,
+                        double *weight, int32_t *node_id) {
+    SFE_REQUIRE(m && v && n >= 0 && levelsup >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(v->device == m->device, SFE_ERR_BAD_ARG, "vocabulary lives on another device");
+    if (n == 0) return SFE_OK;
+    SFE_REQUIRE(desc && word_id && weight && node_id, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    SFE_CUDA(m->d_dl.ensure((size_t)n * 32));
+    SFE_CUDA(m->d_idx.ensure(n)); SFE_CUDA(m->d_dist.ensure(n)); SFE_CUDA(m->d_xw.ensure(n));
+    SFE_CUDA(cudaMemcpyAsync(m->d_dl.p, desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    int rc = vocab_launch(m, v, m->d_dl.p, n, levelsup, m->d_idx.p, m->d_xw.p, m->d_dist.p);
+    if (rc != SFE_OK) return rc;
+    SFE_CUDA(cudaMemcpyAsync(word_id, m->d_idx.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(weight, m->d_xw.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaMemcpyAsync(node_id, m->d_dist.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+// BowVector assembly on the host, in the reference's order of operations (TemplatedVocabulary.h:1127-1194,
+// BowVector.cpp:34-84): ids ascending, weights accumulated in feature order, then the norm taken in id order.
+int sfe_bow_assemble(const int32_t *word_id, const double *weight, int n, int weighting, int norm, int32_t *ids, double *values,
+                     int cap, int *n_out) {
+    SFE_REQUIRE(n >= 0 && n_out && (n == 0 || (word_id && weight)) && cap >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(weighting >= 0 && weighting <= 3 && norm >= 0 && norm <= 2, SFE_ERR_BAD_ARG, "unknown weighting / norm");
+    std::vector<std::pair<int32_t, double>> v;  // kept sorted by id: what std::map iteration yields
+    v.reserve(n);
+    const bool accumulate = weighting == 0 || weighting == 1;  // TF_IDF, TF: addWeight; IDF, BINARY: addIfNotExist
+    for (int i = 0; i < n; i++) {
+        if (!(weight[i] > 0)) continue;  // stopped word
+        auto it = std::lower_bound(v.begin(), v.end(), word_id[i], [](const std::pair<int32_t, double> &a, int32_t id) { return a.first < id; });
+        if (it != v.end() && it->first == word_id[i]) {
+            if (accumulate) it->second += weight[i];
+        } else {
+            v.insert(it, std::make_pair(word_id[i], weight[i]));
+        }
+    }
+    if (accumulate && !v.empty() && norm == 0) {  // "unnecessary when normalizing"
+        const double nd = (double)v.size();
+        for (auto &e : v) e.second /= nd;
+    }
+    if (norm != 0) {  // 1 = L1, 2 = L2
+        double s = 0.0;
+        if (norm == 1) for (auto &e : v) s += fabs(e.second);
+        else { for (auto &e : v) s += e.second * e.second; s = sqrt(s); }
+        if (s > 0.0) for (auto &e : v) e.second /= s;
+    }
+    *n_out = (int)v.size();
+    SFE_REQUIRE((int)v.size() <= cap || (!ids && !values), SFE_ERR_CAPACITY, "BowVector larger than the caller's capacity");
+    for (size_t i = 0; i < v.size() && ids && values; i++) { ids[i] = v[i].first; values[i] = v[i].second; }
     return SFE_OK;
 }
 

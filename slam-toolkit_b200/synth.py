@@ -116,3 +116,32 @@ def projection_scene(kps_xy: np.ndarray, desc: np.ndarray, n_points: int, seed: 
     X[:, 1] = (v - KITTI_CY) / KITTI_FY * z
     X[:, 2] = z
     return X, np.ascontiguousarray(d)
+
+
+def vocabulary(k: int = 10, L: int = 4, seed: int = 7, stop_fraction: float = 0.05, early_leaf: float = 0.03):
+    """A synthetic DBoW2-style vocabulary tree (the real ORBvoc.txt is not redistributable with the reference):
+    branching k, depth L, breadth-first node numbering as the k-means builder produces, random descriptors that share
+    most bits with their parent (so descents are decided by few bits and ties occur), random idf weights with a few
+    stopped words (weight 0) and a few branches that end above depth L.
+    Returns (parent int32[n], is_leaf u8[n], desc u8[n,32], weight f64[n], L)."""
+    rng = np.random.default_rng(seed)
+    parent, is_leaf, desc, weight, depth = [0], [0], [np.zeros(32, np.uint8)], [0.0], [0]
+    frontier = [0]
+    for level in range(1, L + 1):
+        nxt = []
+        for p in frontier:
+            for _ in range(k):
+                d = desc[p].copy()
+                for b in rng.integers(0, 256, 24 if level > 1 else 128):
+                    d[b >> 3] ^= np.uint8(1 << (b & 7))
+                leaf = level == L or rng.uniform() < early_leaf
+                parent.append(p)
+                is_leaf.append(1 if leaf else 0)
+                desc.append(d)
+                weight.append(0.0 if (leaf and rng.uniform() < stop_fraction) else (float(rng.uniform(0.1, 9.0)) if leaf else 0.0))
+                depth.append(level)
+                if not leaf:
+                    nxt.append(len(parent) - 1)
+        frontier = nxt
+    return (np.array(parent, np.int32), np.array(is_leaf, np.uint8), np.stack(desc).astype(np.uint8),
+            np.array(weight, np.float64), L)

@@ -414,3 +414,32 @@ def test_resident_frame_glue_vs_oracle(gpu, oracle, kitti_ex):
     e = api.Frame(m, kps[:0], desc[:0], cam)
     assert e.normalized().shape == (0, 2) and e.SearchNeareast([[5.0, 5.0]])[0].tolist() == [-1]
     assert len(e.SearchRadius([[5.0, 5.0]], 50.0)[0]) == 0
+
+
+def test_bow_transform_vs_oracle(gpu, oracle, kitti_ex):
+    """Frame::ComputeBoW (src/frame.cpp:419-427): per-feature descent on the GPU against the oracle, BowVector
+    assembly against the literal restatement; real ORB descriptors through a synthetic 10^4-word tree."""
+    from test_oracle_matchers import _bow_literal
+    m = api.Matcher()
+    L_img, _ = synth.stereo_pair(1)
+    _, desc = kitti_ex.extract(L_img)
+    for (k, L, seed) in ((10, 4, 7), (3, 6, 8), (20, 2, 9)):
+        parent, is_leaf, ndesc, weight, L = synth.vocabulary(k=k, L=L, seed=seed)
+        voc = api.Vocabulary(m, parent, is_leaf, ndesc, weight, L)
+        assert voc.words() == int(is_leaf.sum())
+        rng = np.random.default_rng(seed)
+        feats = np.concatenate([desc, ndesc[rng.integers(1, len(ndesc), 500)]])   # image descriptors + exact node hits (ties)
+        for levelsup in (4, 0, 1):
+            wid, w, nid = voc.transform_features(feats, levelsup)
+            rwid, rw, rnid = oracle.vocab_transform(parent, is_leaf, ndesc, weight, L, feats, levelsup)
+            assert np.array_equal(wid, rwid) and np.array_equal(w.view(np.uint64), rw.view(np.uint64)) and np.array_equal(nid, rnid)
+        for weighting in range(4):
+            for norm in range(3):
+                ids, vals = api.bow_assemble(rwid, rw, weighting, norm)
+                lit = _bow_literal(rwid, rw, weighting, norm)
+                assert ids.tolist() == [a for a, _ in lit]
+                assert np.array_equal(vals.view(np.uint64), np.array([b for _, b in lit], np.float64).view(np.uint64))
+        (ids, vals), fv = voc.transform(feats, 4)
+        assert abs(vals.sum() - 1.0) < 1e-12 and sorted(fv) == list(fv)
+        assert sum(len(v) for v in fv.values()) == int((rw > 0).sum())
+    assert voc.transform_features(feats[:0])[0].shape == (0,)

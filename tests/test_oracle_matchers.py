@@ -217,3 +217,64 @@ def test_frame_glue_oracle_properties(oracle):
         assert i == int(np.argmin(d2)) and dd == d2.min()
     xc, valid = oracle.stereo_depth(cam0, 0.5, k[:3], n0[:3], k[3:6], np.array([0, -1, 2], np.int32))
     assert valid.tolist()[1] == 0 and valid[0] in (1, 2)
+
+
+def _bow_literal(wid, w, weighting, norm):
+    """BowVector::addWeight / addIfNotExist + normalize, literally (thirdparty/DBoW2/DBoW2/BowVector.cpp:34-84,
+    TemplatedVocabulary.h:1127-1194), with Python floats (IEEE doubles)."""
+    import math
+    v = {}
+    for i in range(len(wid)):
+        if not w[i] > 0:
+            continue
+        k = int(wid[i])
+        if weighting in (0, 1):
+            v[k] = v[k] + float(w[i]) if k in v else float(w[i])
+        elif k not in v:
+            v[k] = float(w[i])
+    items = sorted(v.items())
+    if weighting in (0, 1) and items and norm == 0:
+        nd = float(len(items))
+        items = [(k, x / nd) for k, x in items]
+    if norm:
+        s = 0.0
+        for _, x in items:
+            s = s + (abs(x) if norm == 1 else x * x)
+        if norm == 2:
+            s = math.sqrt(s)
+        if s > 0.0:
+            items = [(k, x / s) for k, x in items]
+    return items
+
+
+def test_vocab_transform_oracle_vs_literal(oracle):
+    """orc_vocab_transform against a literal Python walk of TemplatedVocabulary::transform (:1218-1259)."""
+    import numpy as np
+    from slam_toolkit_b200 import synth
+    parent, is_leaf, desc, weight, L = synth.vocabulary(k=5, L=3, seed=3, early_leaf=0.1)
+    children = {}
+    words, wid_of = 0, {}
+    for i in range(1, len(parent)):
+        children.setdefault(int(parent[i]), []).append(i)
+        if is_leaf[i]:
+            wid_of[i] = words
+            words += 1
+    rng = np.random.default_rng(0)
+    feats = desc[rng.integers(1, len(desc), 200)].copy()
+    for f in feats:
+        for b in rng.integers(0, 256, 10):
+            f[b >> 3] ^= np.uint8(1 << (b & 7))
+    for levelsup in (0, 1, 2, 5):
+        wid, w, nid = oracle.vocab_transform(parent, is_leaf, desc, weight, L, feats, levelsup)
+        for f in range(len(feats)):
+            final, level, n_at = 0, 0, 0
+            while True:
+                level += 1
+                ch = children[final]
+                d = [int(np.unpackbits(feats[f] ^ desc[c]).sum()) for c in ch]
+                final = ch[int(np.argmin(d))]          # argmin = first minimum = the reference's strict <
+                if level == L - levelsup:
+                    n_at = final
+                if final not in children:
+                    break
+            assert (wid[f], w[f], nid[f]) == (wid_of.get(final, 0), weight[final], n_at)
