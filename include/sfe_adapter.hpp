@@ -19,7 +19,9 @@
 #define SFE_ADAPTER_HPP_
 
 #include <cstring>
+#include <fstream>
 #include <map>
+#include <sstream>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -194,6 +196,90 @@ std::map<int, MappointT *> ProjectionMatch(const std::set<MappointT *> &mappoint
         if (to_query[j] >= 0) matches[(int)j] = order[(size_t)to_query[j]];
     return matches;
 }
+
+// ORB_SLAM2::ORBVocabulary stand-in for Frame::ComputeBoW (src/frame.cpp:419-427): loads the DBoW2 text format
+// (TemplatedVocabulary::loadFromTextFile, thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1338-1421), keeps the tree on the
+// device and fills DBoW2::BowVector / DBoW2::FeatureVector (any std::map<unsigned, double> /
+// std::map<unsigned, std::vector<unsigned>>) with transform()'s exact results: the descent runs on the GPU, the maps are
+// built on the host in the reference's order of operations (sfe_bow_assemble).
+class Vocabulary {
+public:
+    Vocabulary() = default;
+    ~Vocabulary() { sfe_vocab_destroy(voc_); }
+    Vocabulary(const Vocabulary &) = delete;
+    Vocabulary &operator=(const Vocabulary &) = delete;
+
+    bool loadFromTextFile(const std::string &filename) {
+        std::ifstream f(filename.c_str());
+        if (!f.good()) return false;
+        std::string line;
+        std::getline(f, line);
+        int n1 = -1, n2 = -1;
+        {
+            std::stringstream ss(line);
+            ss >> k_ >> L_ >> n1 >> n2;
+        }
+        if (k_ < 0 || k_ > 20 || L_ < 1 || L_ > 10 || n1 < 0 || n1 > 5 || n2 < 0 || n2 > 3) return false;
+        std::vector<int32_t> parent(1, 0);
+        std::vector<uint8_t> is_leaf(1, 0), desc(32, 0);
+        std::vector<double> weight(1, 0.);
+        while (std::getline(f, line)) {
+            if (line.empty()) continue;
+            std::stringstream ss(line);
+            int pid = 0, leaf = 0;
+            ss >> pid >> leaf;
+            parent.push_back(pid);
+            is_leaf.push_back(leaf > 0);
+            for (int i = 0; i < 32; i++) {
+                int v = 0;
+                ss >> v;
+                desc.push_back((uint8_t)v);
+            }
+            double w = 0.;
+            ss >> w;
+            weight.push_back(w);
+        }
+        return create(parent, is_leaf, desc, weight, L_, n1, n2);
+    }
+
+    // the arrays loadFromTextFile would have read; scoring / weighting = DBoW2::ScoringType / WeightingType values
+    bool create(const std::vector<int32_t> &parent, const std::vector<uint8_t> &is_leaf, const std::vector<uint8_t> &desc,
+                const std::vector<double> &weight, int L, int scoring, int weighting) {
+        sfe_vocab_destroy(voc_);
+        voc_ = nullptr;
+        L_ = L;
+        weighting_ = weighting;
+        norm_ = scoring == 5 ? 0 : (scoring == 1 ? 2 : 1);  // ScoringObject.h:74-89: DOT_PRODUCT none, L2_NORM L2, the rest L1
+        return sfe_vocab_create(thread_matcher(), (int)parent.size(), parent.data(), is_leaf.data(), desc.data(), weight.data(), L,
+                                &voc_) == SFE_OK;
+    }
+
+    bool empty() const { return voc_ == nullptr; }
+
+    // void transform(const std::vector<TDescriptor>& features, BowVector &v, FeatureVector &fv, int levelsup) const
+    template <class BowVectorT, class FeatureVectorT>
+    void transform(const std::vector<cv::Mat> &features, BowVectorT &v, FeatureVectorT &fv, int levelsup) const {
+        v.clear();
+        fv.clear();
+        if (empty() || features.empty()) return;
+        const int n = (int)features.size();
+        std::vector<uint8_t> desc((size_t)n * 32);
+        for (int i = 0; i < n; i++) std::memcpy(&desc[(size_t)i * 32], features[i].data, 32);
+        std::vector<int32_t> wid(n), nid(n), ids(n);
+        std::vector<double> w(n), vals(n);
+        check(sfe_vocab_transform(thread_matcher(), voc_, desc.data(), n, levelsup, wid.data(), w.data(), nid.data()),
+              "sfe_vocab_transform");
+        int m = 0;
+        check(sfe_bow_assemble(wid.data(), w.data(), n, weighting_, norm_, ids.data(), vals.data(), n, &m), "sfe_bow_assemble");
+        for (int i = 0; i < m; i++) v[(unsigned)ids[i]] = vals[i];
+        for (int i = 0; i < n; i++)
+            if (w[i] > 0) fv[(unsigned)nid[i]].push_back((unsigned)i);
+    }
+
+private:
+    sfe_vocab *voc_ = nullptr;
+    int k_ = 0, L_ = 0, weighting_ = 0, norm_ = 1;
+};
 
 }  // namespace sfe_adapter
 

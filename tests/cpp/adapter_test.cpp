@@ -76,6 +76,19 @@ int main(int argc, char **argv) {
         for (auto &kv : m) self += kv.second->desc.data == f.descriptions_.ptr(kv.first);
         cv::Mat empty_desc; std::vector<cv::KeyPoint> none;
         extractor.extract(cv::Mat(), cv::noArray(), none, empty_desc);  // empty image: silent return
+        if (argc > 5) {  // Frame::ComputeBoW, src/frame.cpp:419-427
+            sfe_adapter::Vocabulary voc;
+            if (!voc.loadFromTextFile(argv[5])) throw std::runtime_error("vocabulary text file rejected");
+            std::vector<cv::Mat> vdesc;
+            for (int j = 0; j < f.descriptions_.rows; j++) vdesc.push_back(f.descriptions_.row(j));
+            std::map<unsigned, double> bowvec;
+            std::map<unsigned, std::vector<unsigned>> featvec;
+            voc.transform(vdesc, bowvec, featvec, 4);
+            uint64_t hb = 1469598103934665603ull, hf = hb;
+            for (auto &kv : bowvec) { hb = fnv(&kv.first, 4, hb); hb = fnv(&kv.second, 8, hb); }
+            for (auto &kv : featvec) { hf = fnv(&kv.first, 4, hf); hf = fnv(kv.second.data(), kv.second.size() * 4, hf); }
+            printf("bow=%016llx bown=%zu fv=%016llx ", (unsigned long long)hb, bowvec.size(), (unsigned long long)hf);
+        }
         printf("nl=%zu nr=%zu kps=%016llx desc=%016llx stereo=%016llx proj=%zu self=%zu dd=%d\n", f.keypoints_.size(),
                f.r_keypoints_.size(), (unsigned long long)fnv(f.keypoints_.data(), f.keypoints_.size() * 28),
                (unsigned long long)fnv(f.descriptions_.data, (size_t)f.descriptions_.rows * 32),
