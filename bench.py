@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one handle each) issuing the e2e calls")
     ap.add_argument("--knn-rows", type=int, default=10_000_000, help="rows of the descriptor map of the Hamming leg (0 = skip)")
-    ap.add_argument("--clock-period", type=float, default=0.02, help="seconds between NVML clock samples (0 = no sampling)")
+    ap.add_argument("--clock-period", type=float, default=0.05, help="seconds between NVML clock samples (0 = no sampling)")
     return ap.parse_args()
 
 
@@ -62,39 +62,52 @@ def make_frames(n):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md): NVML every 20 ms,
-    `nvidia-smi --query-gpu` every 200 ms when the NVML binding is unavailable."""
+    """SM clock and throttle reasons sampled DURING the timed regions (B200_PROFILING.md): NVML every 50 ms,
+    `nvidia-smi --query-gpu` every 200 ms when the NVML binding is unavailable.  Rank 0 alone samples, for every GPU of
+    the job: NVML queries from several processes at once serialise against the other ranks' CUDA calls in the driver
+    (measured: 8 ranks polling at 50 Hz cut the end-to-end figure fivefold)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device, period=0.02):
+    def __init__(self, devices, period=0.05):
         super().__init__(daemon=True)
-        self.device, self.sm, self.reasons, self.sm_max, self.stop_flag, self.source = device, [], set(), None, False, None
+        self.devices, self.sm, self.reasons, self.sm_max, self.stop_flag, self.source = list(devices), [], set(), None, False, None
         self.period, self.active = period, False   # samples are kept only while a timed region is running
+        self.once = threading.Event()              # one extra sample on request (before / after the end-to-end region)
+        self.once_done = threading.Event()
 
     def _nvml_loop(self):
         import pynvml as N
         N.nvmlInit()
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-        idx = self.device
-        if vis:
-            try:
-                idx = int(vis.split(",")[self.device])
-            except (ValueError, IndexError):
-                pass
-        h = N.nvmlDeviceGetHandleByIndex(idx)
-        self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+        handles = []
+        for d in self.devices:
+            idx = d
+            if vis:
+                try:
+                    idx = int(vis.split(",")[d])
+                except (ValueError, IndexError):
+                    pass
+            handles.append(N.nvmlDeviceGetHandleByIndex(idx))
+        self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(handles[0], N.NVML_CLOCK_SM))
         bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
         get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
         self.source = "nvml"
+        last = 0.0
         while not self.stop_flag:
-            if self.active and self.period > 0:
-                self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
-                r = int(get_reasons(h))
-                for name, bit in bits.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            time.sleep(self.period if self.period > 0 else 0.05)
+            due = self.active and time.perf_counter() - last >= self.period
+            if (due or self.once.is_set()) and self.period > 0:
+                last = time.perf_counter()
+                for h in handles:
+                    self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                    r = int(get_reasons(h))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                if self.once.is_set():
+                    self.once.clear()
+                    self.once_done.set()
+            time.sleep(0.005)
 
     def _smi_loop(self):
         self.source = "nvidia-smi"
@@ -103,7 +116,7 @@ class ClockSampler(threading.Thread):
                 time.sleep(0.01)
                 continue
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.devices[0])],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 r = [c.strip() for c in out.split(",")]
                 if len(r) >= 9:
@@ -116,7 +129,17 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.2)
 
+    def sample_once(self):
+        """One sample now (blocking); used around regions where periodic NVML polling would perturb the measurement."""
+        if not self.devices or self.period <= 0 or self.source != "nvml":
+            return
+        self.once_done.clear()
+        self.once.set()
+        self.once_done.wait(timeout=2)
+
     def run(self):
+        if not self.devices:
+            return
         try:
             self._nvml_loop()
         except Exception:
@@ -266,7 +289,7 @@ def main():
     def step_resident(i):
         ex.stereo_frames_dev(d_left[i % NB].ptr, d_right[i % NB].ptr, F, W, H, ptrs, pitch=PITCH)
 
-    sampler = ClockSampler(dev, args.clock_period)
+    sampler = ClockSampler(range(world) if rank == 0 else [], args.clock_period if rank == 0 else 0)
     sampler.start()                      # NVML initialises here, outside the timed regions
     for i in range(Wm):
         step_resident(i)
@@ -328,12 +351,17 @@ def main():
     for t in range(T):
         e2e_steps(t, Wm)
     barrier()
-    sampler.active = True
+    # (periodic NVML polling during this region stalls the CUDA calls of the OTHER ranks inside the driver -- measured
+    # 73 k -> 26 k frames/s at 2 GPUs -- so the clocks are sampled immediately before and after it instead)
+    sampler.sample_once()
     e2e_s = timed(T)
-    sampler.active = False
+    sampler.sample_once()
     barrier()
     e2e_single_s = timed(1) if T > 1 else e2e_s
     barrier()
+    if os.environ.get("SFE_BENCH_DEBUG"):
+        print(f"[rank {rank}] e2e {T} threads {F * K / e2e_s:.0f} frames/s, 1 thread {F * K / e2e_single_s:.0f}; again: "
+              f"{F * K / timed(T):.0f} / {F * K / timed(1):.0f}", file=sys.stderr, flush=True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
     hamming = hamming_leg(args, dev, rank, world, dist) if args.knn_rows > 0 else None

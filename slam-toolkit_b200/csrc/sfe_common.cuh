@@ -33,7 +33,13 @@ void set_error(const char *fmt, ...);
         }                                                        \
     } while (0)
 
-// RAII device-scope guard: every ABI call runs on its handle's device and restores the caller's.
+// Is the primary context of `device` already alive in this process?  (driver API through the runtime's entry points)
+bool primary_context_active(int device);
+
+// RAII device-scope guard: every ABI call runs on its handle's device and gives the caller's device back -- but only
+// when that device really is in use.  A fresh host thread reports device 0 as current without having touched it, and
+// since CUDA 12 cudaSetDevice() creates the primary context eagerly: restoring "device 0" blindly made every rank of a
+// multi-GPU job build a context on GPU 0 the first time a worker thread called in (measured: 0.5 s stall, ~0.5 GB).
 struct DeviceGuard {
     int prev = -1;
     bool ok = false;
@@ -43,7 +49,7 @@ struct DeviceGuard {
     }
     ~DeviceGuard() {
         int cur = -1;
-        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev && primary_context_active(prev)) cudaSetDevice(prev);
     }
 };
 

@@ -22,6 +22,29 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
+bool primary_context_active(int device) {
+    typedef CUresult (*GetDeviceFn)(CUdevice *, int);
+    typedef CUresult (*CtxStateFn)(CUdevice, unsigned int *, int *);
+    static GetDeviceFn get_device = nullptr;
+    static CtxStateFn ctx_state = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuDeviceGet", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            get_device = (GetDeviceFn)p;
+        if (cudaGetDriverEntryPoint("cuDevicePrimaryCtxGetState", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            ctx_state = (CtxStateFn)p;
+    });
+    if (!get_device || !ctx_state) return true;  // cannot tell: behave like a plain guard
+    CUdevice d;
+    unsigned int flags = 0;
+    int active = 0;
+    if (get_device(&d, device) != CUDA_SUCCESS || ctx_state(d, &flags, &active) != CUDA_SUCCESS) return true;
+    return active != 0;
+}
+
 bool tma_encode_u8_3d(CUtensorMap *map, const void *base, uint64_t width, uint64_t height, uint64_t images, uint64_t pitch,
                       uint64_t image_stride, uint32_t box_w, uint32_t box_h) {
     EncodeTiledFn fn = encode_tiled_fn();
