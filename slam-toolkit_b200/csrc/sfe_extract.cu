@@ -130,35 +130,22 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// FAST-9-16, one CTA per reference cv::FAST call (one 30-px grid cell, :789-816)
-//   load     the cell's sub-image into shared memory as aligned 32-bit words (two global words +
-//            funnel shift per word: cell origins are not word aligned)
-//   stage 0  compass pre-test, 4 pixels per thread in 16x2 SIMD lanes: any 9-arc of the 16-pixel
-//            circle contains two neighbouring compass pixels, so a corner needs a vertical and a
-//            horizontal compass pixel both brighter than v+t or both darker than v-t; survivors are
-//            compacted into a list so later stages run with full warps
+// FAST-9-16, one CTA per segment of up to 128 tested pixels along one cell row (SegRec): the tested
+// regions of the reference's cv::FAST calls (one 30-px grid cell each, :789-816) tile the row, so the
+// per-pixel stages run on the whole segment and only NMS and the 20 -> 7 retry look at cell borders.
+//   load     the segment's sub-image into shared memory (one TMA box, or aligned words + funnel shift)
+//   stage 0  pre-test on the four compass pixels, 4 pixels per lane with VABSDIFF4: any 9-arc of the
+//            16-pixel circle contains a vertical and a horizontal compass pixel, so a corner needs
+//            (|up - c| > t or |dn - c| > t) and (|lf - c| > t or |rt - c| > t); the cheaper superset
+//            ((|up - c| | |dn - c|) > t) and ((|lf - c| | |rt - c|) > t) is what is evaluated.  One warp =
+//            one row of the segment, one lane = one aligned word of 4 centre pixels; survivors go to a list
 //   stage 1  exact score best(p) on the survivors, two pixels per thread in 16x2 lanes
 //            (VIMNMX3.S16x2); corner iff best > t
-//   stage 2  cell-local non-max suppression (strict > over 8 neighbours, outside the cell = 0)
-//   retry the whole cell with minThFAST only if nothing survived (:811-816)
+//   stage 2  non-max suppression inside each cell (strict > over 8 neighbours, outside the cell = 0)
+//   emit, then retry with minThFAST the cells where nothing survived (:811-816)
 // ---------------------------------------------------------------------------------------------
-// Tile row pitch TP (bytes) is a template parameter: 64 for cells up to 41 px wide, 96 up to kMaxSub.
-// Shared column c of a cell's tile is level column xa + c with xa = (ini_x - 4) rounded down to 16: a TMA box
+// Shared column c of the tile is level column xa + c with xa = (ini_x - 4) rounded down to 16: a TMA box
 // must start on a 16-byte multiple of the row, and stage 0 then works on the level's own 4-pixel words.
-constexpr int kScorePitch = 64;  // >= kMaxSub - 6 + 2
-
-// Compass pre-test of two pixels held in the 16-bit lanes of c (centre), v0 / v1 (the vertical compass pixels, circle
-// positions 8 and 0) and h0 / h1 (the horizontal ones, positions 12 and 4).  Any arc of 9 consecutive circle
-// positions contains two compass positions that are NEIGHBOURS on the compass (0-4, 4-8, 8-12 or 12-0), so a
-// corner needs one vertical AND one horizontal compass pixel brighter than c + t, or both darker than c - t:
-// (v0 | v1) & (h0 | h1).  k = 0x7FFF - t in both lanes: lane bit 15 of (p + k - c) is set iff p > c + t, of
-// (c + k - p) iff p < c - t; no lane ever carries or borrows (all values stay inside [0x7E02, 0x80FE]).
-__device__ __forceinline__ uint32_t compass2(uint32_t c, uint32_t v0, uint32_t v1, uint32_t h0, uint32_t h1, uint32_t k) {
-    const uint32_t A = k - c, B = k + c;
-    const uint32_t rb = ((v0 + A) | (v1 + A)) & ((h0 + A) | (h1 + A));
-    const uint32_t rd = ((B - v0) | (B - v1)) & ((B - h0) | (B - h1));
-    return (rb | rd) & 0x80008000u;
-}
 
 // best(p) = max over the 16 arcs of 9 consecutive circle pixels of max(min (v - p_k), min (p_k - v))
 //         = max(v - min_arcs max_k p_k, max_arcs min_k p_k - v)                    (cv::FAST score + 1)
@@ -191,35 +178,30 @@ __device__ __forceinline__ void fast_best_x2(const uint8_t *c0, const uint8_t *c
     best1 = max(v1 - (int)(min_of_max >> 16), (int)(max_of_min >> 16) - v1);
 }
 
-// 16.16 reciprocals of the small row lengths the kernel divides by: floor(i / n) == (i * kInv16[n]) >> 16 for i < 3640
-__constant__ unsigned short kInv16[24] = {0,     0,     32769, 21846, 16385, 13108, 10923, 9363, 8193, 7282, 6554, 5958,
-                                          5462,  5042,  4682,  4370,  4097,  3856,  3641,  3450, 3277, 3121, 2979, 2850};
-
-// One CTA = one cell.  The cell record (8 B) comes from a host-built table; the per-level constants ride in the
-// kernel parameters (constant bank).  kTma: the sub-image arrives as one TMA box (TP x tile_rows bytes) issued
-// by thread 0; otherwise (level-0 images whose layout TMA cannot describe) the threads assemble it from
-// aligned global words.
-template <int TP, bool kTma>
-__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, FastPlan P, const CellRec *__restrict__ cells,
-                                                                  const __grid_constant__ TmaMaps M) {
-    constexpr int kTilePitch = TP, kTileWords = TP / 4;
+// kTma: the sub-image arrives as one TMA box (kFastTilePitch x tile_rows bytes) issued by thread 0; otherwise
+// (level-0 images whose layout TMA cannot describe) the threads assemble it from aligned global words.
+template <bool kTma>
+__global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) fast_segments_kernel(ImgSet S, FastPlan P, const SegRec *__restrict__ segs,
+                                                                     const __grid_constant__ TmaMaps M) {
+    constexpr int TP = kFastTilePitch, TW = TP / 4, SP = kFastScorePitch, T = kFastThreads;
     extern __shared__ __align__(128) uint32_t fast_smem[];
-    uint32_t *tile32 = fast_smem;                                    // tile_rows x kTileWords
-    uint8_t *score = (uint8_t *)(tile32 + P.tile_rows * kTileWords);  // score_rows x kScorePitch
-    uint16_t *pre = (uint16_t *)(score + P.score_rows * kScorePitch); // y << 6 | x of pixels passing stage 0
-    uint16_t *det = pre + P.list_cap;                                 // corners
-    uint16_t *surv = pre;                                             // NMS survivors (pre is dead by then)
-    __shared__ int n_pre, n_det, n_surv, out_base;
+    uint32_t *tile32 = fast_smem;                              // tile_rows x TW
+    uint8_t *score = (uint8_t *)(tile32 + P.tile_rows * TW);   // score_rows x SP
+    uint16_t *pre = (uint16_t *)(score + P.score_rows * SP);   // y << 8 | x of pixels passing stage 0
+    uint16_t *det = pre + P.list_cap;                          // corners
+    __shared__ int n_pre, n_det;
+    __shared__ int cell_surv[kFastMaxCells];
     __shared__ uint64_t bar;
     const uint8_t *tile = (const uint8_t *)tile32;
-    constexpr int T = kFastThreads;
 
-    const CellRec C = cells[blockIdx.x];  // which reference cell is this (:789-806)
-    const int level = C.level, ini_x = C.ini_x, ini_y = C.ini_y, sw = C.sw, sh = C.sh;
+    const uint4 rec = __ldg((const uint4 *)segs + blockIdx.x);  // one 16-byte SegRec
+    const int ini_x = (short)(rec.x & 0xFFFF), ini_y = (short)(rec.x >> 16), tw = (short)(rec.y & 0xFFFF);
+    const int sh = (rec.y >> 16) & 0xFF, level = rec.y >> 24, n_cells = rec.z & 0xFF, w_cell = (rec.z >> 8) & 0xFF;
+    const int inv_w = rec.z >> 16, th = sh - 6;
     const FastLevel &F = P.lv[level];
-    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    const int xa = (ini_x - 4) & ~15;         // level column of shared column 0 (ini_x >= 16)
-    const int cs = ini_x + 3 - xa;            // shared column of tested x = 0, in [7, 22]
+    const int img = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int xa = (ini_x - 4) & ~15;  // level column of shared column 0 (ini_x >= 16)
+    const int cs = ini_x + 3 - xa;     // shared column of tested x = 0, in [7, 22]
     if (kTma) {
         // bytes outside the image arrive as zeros and are never tested
         if (tid == 0) {
@@ -241,52 +223,54 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
             src = S.pyr + (size_t)slot_of(S, img) * S.pyr_stride + F.plane_off;
         }
         src += (size_t)ini_y * pitch + xa;
-        // words up to the one after the last tested pixel's; the row has >= 16 px beyond the cell
-        const int nw = min(((cs + sw - 7) >> 2) + 2, kTileWords), inv = kInv16[nw];
-        for (int it = tid; it < sh * nw; it += T) {
-            const int r = (it * inv) >> 16, j = it - r * nw;
-            tile32[r * kTileWords + j] = ldg_word_at(src + (size_t)r * pitch + 4 * j);
-        }
+        // words up to the one after the last tested pixel's; the row has >= 16 px beyond the segment
+        const int nw = min(((cs + tw - 1) >> 2) + 2, TW);
+        for (int r = warp; r < sh; r += T / 32)
+            for (int j = lane; j < nw; j += 32) tile32[r * TW + j] = ldg_word_at(src + (size_t)r * pitch + 4 * j);
     }
-    const int tw = sw - 6, th = sh - 6;  // tested pixels: 3-px margin inside the sub-image
-    const int jw0 = cs >> 2, nq = ((cs + tw - 1) >> 2) - jw0 + 1;  // level words that hold tested pixels
-    const int inv_q = nq > 1 ? kInv16[nq] : 65536, nitems = th * nq;
+    // stage-0 geometry of this lane: its word of the row, and which of the word's 4 pixels are tested ones
+    const int jw = (cs >> 2) + lane, x0 = 4 * jw - cs;  // tested x of the word's first pixel (may be negative)
+    uint32_t vm = 0;                                    // bit 7 of byte k: pixel k of the word is a tested one
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (x0 + k >= 0 && x0 + k < tw) vm |= 0x80u << (8 * k);
+    uint32_t todo = (1u << n_cells) - 1;  // cells this pass works on
     int t = P.ini_th;
+    for (int i = tid; i < (th + 2) * (SP / 16); i += T) ((uint4 *)score)[i] = make_uint4(0, 0, 0, 0);
     for (int attempt = 0; attempt < 2; attempt++) {
-        for (int i = tid; i < (th + 2) * (kScorePitch / 16); i += T) ((uint4 *)score)[i] = make_uint4(0, 0, 0, 0);
-        if (tid == 0) { n_pre = 0; n_det = 0; n_surv = 0; }
+        if (tid == 0) { n_pre = 0; n_det = 0; }
+        if (tid < kFastMaxCells) cell_surv[tid] = 0;
         __syncthreads();
         if (kTma && attempt == 0) mbar_wait(&bar, 0);  // the barrier was initialised by thread 0 before the sync above
-        // stage 0: compass pre-test, one aligned word of 4 centre pixels per thread
-        const uint32_t k2 = (uint32_t)(0x7FFF - t) * 0x10001u;
-        for (int i0 = 0; i0 < nitems; i0 += T) {
-            const int it = i0 + tid;
-            uint32_t mask = 0;
-            int y = 0, x = 0;
-            if (it < nitems) {
-                y = (it * inv_q) >> 16;
-                const int jw = jw0 + it - y * nq;
-                x = 4 * jw - cs;  // tested x of the word's first pixel (negative: the word starts left of the cell)
-                const uint32_t *row = tile32 + (y + 3) * kTileWords + jw;
-                const uint32_t c = row[0], up = row[-3 * kTileWords], dn = row[3 * kTileWords];
-                const uint32_t lf = __byte_perm(row[-1], c, 0x4321);  // pixels x-3 .. x
-                const uint32_t rt = __byte_perm(c, row[1], 0x6543);   // pixels x+3 .. x+6
-                const uint32_t m_lo = compass2(__byte_perm(c, 0, 0x4140), __byte_perm(up, 0, 0x4140), __byte_perm(dn, 0, 0x4140),
-                                               __byte_perm(lf, 0, 0x4140), __byte_perm(rt, 0, 0x4140), k2);
-                const uint32_t m_hi = compass2(__byte_perm(c, 0, 0x4342), __byte_perm(up, 0, 0x4342), __byte_perm(dn, 0, 0x4342),
-                                               __byte_perm(lf, 0, 0x4342), __byte_perm(rt, 0, 0x4342), k2);
-                mask = ((m_lo >> 15) & 1) | ((m_lo >> 30) & 2) | ((m_hi >> 13) & 4) | ((m_hi >> 28) & 8);
-                mask &= (0xFu << max(-x, 0)) & ((1u << min(4, tw - x)) - 1);  // pixels of this word inside [0, tw)
-            }
-            // compaction: the list order is irrelevant downstream and only a few lanes per warp hold survivors, so a
-            // shared-memory atomic per such lane costs fewer issue slots than a ballot / prefix scheme
-            if (mask) {
-                int pos = atomicAdd(&n_pre, __popc(mask));
-                const uint16_t item = (uint16_t)((y << 6) + x);  // bits of a word left of the cell are masked out
-                if (mask & 1) pre[pos++] = item;
-                if (mask & 2) pre[pos++] = item + 1;
-                if (mask & 4) pre[pos++] = item + 2;
-                if (mask & 8) pre[pos] = item + 3;
+        // stage 0: one row per warp, one word of 4 centre pixels per lane
+        uint32_t vm_now = vm;
+        if (attempt) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (!((todo >> ((max(x0 + k, 0) * inv_w) >> 16)) & 1)) vm_now &= ~(0x80u << (8 * k));
+        }
+        const uint32_t kk = (uint32_t)(0x7F - min(t, 127)) * 0x01010101u;
+        if (vm_now) {
+            const uint32_t *row = tile32 + (warp + 3) * TW + jw;
+            for (int y = warp; y < th; y += T / 32, row += (T / 32) * TW) {
+                const uint32_t c = row[0];
+                const uint32_t dv0 = __vabsdiffu4(row[-3 * TW], c), dv1 = __vabsdiffu4(row[3 * TW], c);
+                const uint32_t dh0 = __vabsdiffu4(__byte_perm(row[-1], c, 0x4321), c);  // pixels x-3 .. x
+                const uint32_t dh1 = __vabsdiffu4(__byte_perm(c, row[1], 0x6543), c);   // pixels x+3 .. x+6
+                // byte > t  <=>  bit 7 of (byte | ((byte & 0x7f) + 0x7f - t)); a | b >= max(a, b) keeps this a superset
+                const uint32_t rv = (((dv0 | dv1) & 0x7F7F7F7Fu) + kk) | dv0 | dv1;
+                const uint32_t rh = (((dh0 | dh1) & 0x7F7F7F7Fu) + kk) | dh0 | dh1;
+                const uint32_t m = rv & rh & vm_now;
+                // the list order is irrelevant downstream and only some lanes hold survivors, so a shared-memory
+                // atomic per such lane costs fewer issue slots than a ballot / prefix scheme
+                if (m) {
+                    int pos = atomicAdd(&n_pre, __popc(m));
+                    const uint16_t item = (uint16_t)((y << 8) + x0);  // pixels left of the segment are masked out
+                    if (m & 0x80u) pre[pos++] = item;
+                    if (m & 0x8000u) pre[pos++] = item + 1;
+                    if (m & 0x800000u) pre[pos++] = item + 2;
+                    if (m & 0x80000000u) pre[pos] = item + 3;
+                }
             }
         }
         __syncthreads();
@@ -300,52 +284,59 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(ImgSet S, Fast
                 yx0 = pre[2 * e];
                 yx1 = pre[min(2 * e + 1, np - 1)];
                 int best0, best1;
-                fast_best_x2<TP>(&tile[((yx0 >> 6) + 3) * kTilePitch + (yx0 & 63) + cs],
-                                 &tile[((yx1 >> 6) + 3) * kTilePitch + (yx1 & 63) + cs], best0, best1);
+                fast_best_x2<TP>(&tile[((yx0 >> 8) + 3) * TP + (yx0 & 255) + cs], &tile[((yx1 >> 8) + 3) * TP + (yx1 & 255) + cs],
+                                 best0, best1);
                 corner0 = best0 > t;
                 corner1 = best1 > t && 2 * e + 1 < np;
-                if (corner0) score[((yx0 >> 6) + 1) * kScorePitch + (yx0 & 63) + 1] = (uint8_t)best0;
-                if (corner1) score[((yx1 >> 6) + 1) * kScorePitch + (yx1 & 63) + 1] = (uint8_t)best1;
+                if (corner0) score[((yx0 >> 8) + 1) * SP + (yx0 & 255) + 1] = (uint8_t)best0;
+                if (corner1) score[((yx1 >> 8) + 1) * SP + (yx1 & 255) + 1] = (uint8_t)best1;
             }
             if (corner0) det[atomicAdd(&n_det, 1)] = yx0;
             if (corner1) det[atomicAdd(&n_det, 1)] = yx1;
         }
         __syncthreads();
-        // stage 2: non-max suppression inside this cell only
-        const int nd = n_det;
-        for (int e0 = 0; e0 < nd; e0 += T) {
+        // stage 2: non-max suppression; a neighbour in another cell counts as 0 (the reference runs cv::FAST per cell).
+        // Survivors go straight to the level's candidate array: one global atomic per warp reserves their slots.
+        const int nd = n_det, slot = slot_of(S, img);
+        uint32_t *out = S.cand + (size_t)slot * S.cand_stride + F.cand_off;
+        for (int e0 = warp * 32; e0 < nd; e0 += T) {
             bool keep = false;
-            uint16_t yx = 0;
-            if (e0 + tid < nd) {
-                yx = det[e0 + tid];
-                const uint8_t *sc = &score[((yx >> 6) + 1) * kScorePitch + (yx & 63) + 1];
+            uint32_t packed = 0;
+            int cell = 0;
+            if (e0 + lane < nd) {
+                const uint16_t yx = det[e0 + lane];
+                const int x = yx & 255, y = yx >> 8;
+                cell = (x * inv_w) >> 16;
+                const int cx0 = cell * w_cell, cx1 = min(cx0 + w_cell, tw);
+                const uint8_t *sc = &score[(y + 1) * SP + x + 1];
                 const int s = sc[0];
-                keep = s > sc[-1] && s > sc[1] && s > sc[-kScorePitch - 1] && s > sc[-kScorePitch] &&
-                       s > sc[-kScorePitch + 1] && s > sc[kScorePitch - 1] && s > sc[kScorePitch] && s > sc[kScorePitch + 1];
+                keep = s > sc[-SP] && s > sc[SP];
+                if (x > cx0) keep = keep && s > sc[-1] && s > sc[-SP - 1] && s > sc[SP - 1];
+                if (x + 1 < cx1) keep = keep && s > sc[1] && s > sc[-SP + 1] && s > sc[SP + 1];
+                // cv::FAST response = best - 1; window-relative coordinates
+                packed = (uint32_t)(s - 1) << 24 | (uint32_t)(ini_y - kBorder + y + 3) << 12 | (uint32_t)(ini_x - kBorder + x + 3);
             }
-            if (keep) surv[atomicAdd(&n_surv, 1)] = yx;
+            const uint32_t kept = __ballot_sync(0xffffffffu, keep);
+            if (kept) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&S.cand_count[slot * S.nlevels + level], __popc(kept));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (keep) {
+                    const int o = base + __popc(kept & ((1u << lane) - 1));
+                    if (o < F.cand_cap) out[o] = packed;
+                    else atomicOr(&S.flags[slot], kFlagCandOverflow);
+                    cell_surv[cell] = 1;
+                }
+            }
         }
         __syncthreads();
-        if (n_surv > 0 || P.min_th >= t) break;  // :811-816: retry with minThFAST only when nothing survived
+        uint32_t retry = 0;  // :811-816: cells of this pass where nothing survived
+        for (int c = 0; c < n_cells; c++)
+            if (((todo >> c) & 1) && cell_surv[c] == 0) retry |= 1u << c;
+        if (retry == 0 || P.min_th >= t) break;  // a higher threshold cannot find what the lower one did not
         t = P.min_th;
+        todo = retry;
         __syncthreads();
-    }
-    const int ns = n_surv;
-    if (ns == 0) return;
-    const int slot = slot_of(S, img);
-    if (tid == 0) out_base = atomicAdd(&S.cand_count[slot * S.nlevels + level], ns);
-    __syncthreads();
-    uint32_t *out = S.cand + (size_t)slot * S.cand_stride + F.cand_off;
-    for (int e = tid; e < ns; e += T) {
-        const int yx = surv[e], y = yx >> 6, x = yx & 63;
-        const int slot = out_base + e;
-        if (slot >= F.cand_cap) {
-            atomicOr(&S.flags[slot], kFlagCandOverflow);
-            continue;
-        }
-        const uint32_t resp = score[(y + 1) * kScorePitch + x + 1] - 1;  // cv::FAST response = best - 1
-        const uint32_t xw = ini_x - kBorder + x + 3, yw = ini_y - kBorder + y + 3;
-        out[slot] = resp << 24 | yw << 12 | xw;
     }
 }
 
@@ -1013,8 +1004,8 @@ struct sfe_extractor {
     const void *l0_key[2] = {nullptr, nullptr};
     size_t l0_geom[4] = {0, 0, 0, 0};
     int pitch0 = 0;       // row pitch of the host-path staging buffer
-    std::vector<CellRec> cells;
-    DevBuf<CellRec> d_cells;
+    std::vector<SegRec> segs;
+    DevBuf<SegRec> d_segs;
     size_t fast_smem = 0, pyr_smem = 0;
     std::vector<TilePlan> tiles;
     size_t pyr_stride = 0, blur_stride = 0;
@@ -1081,8 +1072,8 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     std::vector<uint2> xtab, ytab;
     int max_src_rows = 1, max_src_cols = 1;
     memset(&ex->fast, 0, sizeof(ex->fast));
-    ex->cells.clear();
-    int max_sw = 7, max_sh = 7;
+    ex->segs.clear();
+    int max_sh = 7, max_list = 8;
     ex->tiles.clear();
     size_t pyr_off = 0, blur_off = 0;
     int cand_off = 0, kp_off = 0, max_cand = 0, max_nodes = 8;
@@ -1130,15 +1121,28 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                 F.pitch = L.pitch;
                 F.plane_off = L.plane_off;
                 n_level_cells = rows_eff * cols_eff;
+                const int inv_w = 65536 / L.w_cell + 1;  // x / w_cell == (x * inv_w) >> 16 for x < 256 (w_cell in [30, 60])
+                for (int x = 0; x < 256; x++) SFE_REQUIRE(((x * inv_w) >> 16) == x / L.w_cell && inv_w < 65536, SFE_ERR_UNSUPPORTED, "cell reciprocal");
                 for (int i = 0; i < rows_eff; i++) {
                     const int ini_y = kBorder + i * L.h_cell, sh = std::min(ini_y + L.h_cell + 6, max_by) - ini_y;
-                    for (int j = 0; j < cols_eff; j++) {
-                        const int ini_x = kBorder + j * L.w_cell, sw = std::min(ini_x + L.w_cell + 6, max_bx) - ini_x;
-                        ex->cells.push_back(CellRec{(short)ini_x, (short)ini_y, (unsigned char)sw, (unsigned char)sh,
-                                                    (unsigned char)l, 0});
-                        tested += (sw - 6) * (sh - 6);
-                        max_sw = std::max(max_sw, sw);
-                        max_sh = std::max(max_sh, sh);
+                    max_sh = std::max(max_sh, sh);
+                    // greedy segments: as many cells as keep the tested pixels inside 32 of the level's 4-pixel words
+                    for (int j = 0; j < cols_eff;) {
+                        const int ini_x = kBorder + j * L.w_cell, cs = ini_x + 3 - ((ini_x - 4) & ~15);
+                        int tw = 0, nc = 0;
+                        while (j + nc < cols_eff && nc < kFastMaxCells) {
+                            const int cx = kBorder + (j + nc) * L.w_cell, sw = std::min(cx + L.w_cell + 6, max_bx) - cx;
+                            const int tw2 = tw + sw - 6;
+                            if (nc > 0 && (tw2 > kFastSegPx || ((cs + tw2 - 1) >> 2) - (cs >> 2) + 1 > 32)) break;
+                            tw = tw2;
+                            nc++;
+                        }
+                        SFE_REQUIRE(tw >= 1 && tw <= kFastSegPx && ((cs + tw - 1) >> 2) - (cs >> 2) + 1 <= 32, SFE_ERR_UNSUPPORTED, "FAST segment");
+                        ex->segs.push_back(SegRec{(short)ini_x, (short)ini_y, (short)tw, (unsigned char)sh, (unsigned char)l,
+                                                  (unsigned char)nc, (unsigned char)L.w_cell, (unsigned short)inv_w, 0});
+                        tested += tw * (sh - 6);
+                        max_list = std::max(max_list, tw * (sh - 6));
+                        j += nc;
                     }
                 }
             }
@@ -1218,11 +1222,12 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     ex->fast.nlevels = nl;
     ex->fast.ini_th = ex->prm.ini_th_fast;
     ex->fast.min_th = ex->prm.min_th_fast;
+    ex->fast.n_segs = (int)ex->segs.size();
     ex->fast.tile_rows = (max_sh + 1) & ~1;  // even: tile_rows * pitch keeps the score array 16-byte aligned
-    ex->fast.tile_pitch = max_sw + 23 <= 64 ? 64 : 96;
     ex->fast.score_rows = max_sh - 4;
-    ex->fast.list_cap = ((max_sw - 6) * (max_sh - 6) + 7) & ~7;
-    ex->fast_smem = (size_t)ex->fast.tile_rows * ex->fast.tile_pitch + (size_t)(max_sh - 4) * kScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
+    ex->fast.list_cap = (max_list + 7) & ~7;
+    ex->fast_smem = (size_t)ex->fast.tile_rows * kFastTilePitch + (size_t)ex->fast.score_rows * kFastScorePitch + 2 * 2 * (size_t)ex->fast.list_cap;
+    SFE_REQUIRE(ex->fast_smem <= 200 * 1024, SFE_ERR_UNSUPPORTED, "FAST segment working set exceeds shared memory");
     // candidate arrays for up to kOctreeSmemCand points in shared memory (3 CTAs per SM at the KITTI config); fuller
     // levels spill to global scratch slots
     ex->octree_smem_cand = std::min(ex->max_cand, ex->octree_cand_override > 0 ? ex->octree_cand_override : kOctreeSmemCand) & ~7;
@@ -1238,9 +1243,9 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     SFE_CUDA(ex->d_kpst.ensure((size_t)ex->kpst_stride * n));
     SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1) + 1));  // cand_count | kp_count | scratch_next | flags
     SFE_CUDA(ex->d_tiles.ensure(std::max<size_t>(ex->tiles.size(), 1)));
-    SFE_CUDA(ex->d_cells.ensure(std::max<size_t>(ex->cells.size(), 1)));
-    if (!ex->cells.empty())
-        SFE_CUDA(cudaMemcpyAsync(ex->d_cells.p, ex->cells.data(), sizeof(CellRec) * ex->cells.size(), cudaMemcpyHostToDevice, ex->stream));
+    SFE_CUDA(ex->d_segs.ensure(std::max<size_t>(ex->segs.size(), 1)));
+    if (!ex->segs.empty())
+        SFE_CUDA(cudaMemcpyAsync(ex->d_segs.p, ex->segs.data(), sizeof(SegRec) * ex->segs.size(), cudaMemcpyHostToDevice, ex->stream));
     SFE_CUDA(ex->d_xtab.ensure(std::max<size_t>(xtab.size(), 1)));
     SFE_CUDA(ex->d_ytab.ensure(std::max<size_t>(ytab.size(), 1)));
     if (!ex->tiles.empty())
@@ -1257,7 +1262,7 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
         if (L.w < 8 || L.h < 8) ex->tma_plan_ok = false;
         if (l == 0 || !ex->tma_plan_ok) continue;
         ex->tma_plan_ok = tma_encode_u8_3d(&ex->fast_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
-                                           ex->fast.tile_pitch, ex->fast.tile_rows) &&
+                                           kFastTilePitch, ex->fast.tile_rows) &&
                           tma_encode_u8_3d(&ex->blur_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
                                            kBlurInWords * 4, kBlurTileH + 6) &&
                           (nl < 2 || tma_encode_u8_3d(&ex->pyr_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
@@ -1333,8 +1338,8 @@ static void prepare_l0_maps(sfe_extractor *ex, const uint8_t *a, const uint8_t *
     const size_t geom[4] = {(size_t)n_a, (size_t)n_b, stride, (size_t)pitch};
     if (ex->l0_key[0] != a || ex->l0_key[1] != b || memcmp(geom, ex->l0_geom, sizeof(geom)) != 0) {
         const LevelPlan &L = ex->lv[0];
-        const bool ok = tma_encode_u8_3d(&ex->fast_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, ex->fast.tile_pitch, ex->fast.tile_rows) &&
-                        tma_encode_u8_3d(&ex->fast_maps.l0b, b, L.w, L.h, n_b, pitch, stride, ex->fast.tile_pitch, ex->fast.tile_rows) &&
+        const bool ok = tma_encode_u8_3d(&ex->fast_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, kFastTilePitch, ex->fast.tile_rows) &&
+                        tma_encode_u8_3d(&ex->fast_maps.l0b, b, L.w, L.h, n_b, pitch, stride, kFastTilePitch, ex->fast.tile_rows) &&
                         tma_encode_u8_3d(&ex->blur_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, kBlurInWords * 4, kBlurTileH + 6) &&
                         tma_encode_u8_3d(&ex->blur_maps.l0b, b, L.w, L.h, n_b, pitch, stride, kBlurInWords * 4, kBlurTileH + 6) &&
                         (ex->prm.nlevels < 2 ||
@@ -1350,16 +1355,32 @@ static void prepare_l0_maps(sfe_extractor *ex, const uint8_t *a, const uint8_t *
 
 constexpr bool kFastTma = true;
 
-template <int TP>
-static void launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count) {
-    const dim3 grid((unsigned)ex->fast.n_cells, count);
+static int launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count) {
+    const dim3 grid((unsigned)ex->fast.n_segs, count);
+    if (ex->fast_smem > 48 * 1024) {  // the opt-in shared-memory limit is a per-function attribute: only ever raise it
+        static std::mutex mu;
+        static size_t granted[64] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        if (ex->fast_smem > granted[ex->device & 63]) {
+            SFE_CUDA(cudaFuncSetAttribute(fast_segments_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fast_smem));
+            SFE_CUDA(cudaFuncSetAttribute(fast_segments_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->fast_smem));
+            granted[ex->device & 63] = ex->fast_smem;
+        }
+    }
+    {   // ask for the largest shared-memory carve-out (the default heuristic leaves the kernel at 4 CTAs per SM)
+        static std::once_flag once[64];
+        std::call_once(once[ex->device & 63], [] {
+            cudaFuncSetAttribute(fast_segments_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(fast_segments_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        });
+    }
     if (ex->tma_now && kFastTma)
-        fast_cells_kernel<TP, true><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_cells.p, ex->fast_maps);
+        fast_segments_kernel<true><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p, ex->fast_maps);
     else
-        fast_cells_kernel<TP, false><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_cells.p, ex->fast_maps);
+        fast_segments_kernel<false><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p, ex->fast_maps);
+    return SFE_OK;
 }
 
-// enqueue the extraction of the `count` images of S on the handle's compute stream (counters already reset)
 static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count, const OutSet &O) {
     const int nl = ex->prm.nlevels;
     prof_mark(ex, 0);
@@ -1393,8 +1414,7 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
             launch_blur();
             SFE_CUDA(cudaEventRecord(ex->ev_join[si], sb));
         }
-        if (ex->fast.tile_pitch == 64) launch_fast<64>(ex, st, S, count);
-        else launch_fast<96>(ex, st, S, count);
+        if (int rc = launch_fast(ex, st, S, count)) return rc;
         prof_mark(ex, 2);
         {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
             static std::mutex mu;
@@ -1665,7 +1685,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     cudaStreamSynchronize(ex->stream);
     ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_l0.release(); ex->d_octree_scratch.release(); ex->d_desc.release();
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release();
-    ex->d_tiles.release(); ex->d_cells.release(); ex->d_xtab.release(); ex->d_ytab.release();
+    ex->d_tiles.release(); ex->d_segs.release(); ex->d_xtab.release(); ex->d_ytab.release();
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
     for (int i = 0; i <= kNumStages; i++)
         if (ex->prof_ev[i]) cudaEventDestroy(ex->prof_ev[i]);

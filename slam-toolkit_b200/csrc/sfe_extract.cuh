@@ -33,25 +33,35 @@ struct LevelPlan {
     float size;             // (int)(31 * scale), :837
 };
 
-// FAST cells (one cv::FAST call of the reference each, :789-816): a host-built record per cell that passes the
-// skip rules (:794,803) and holds at least a 7x7 sub-image; per-level constants ride in the kernel parameters.
-struct CellRec {
-    short ini_x, ini_y;       // iniX, iniY (level pixels)
-    unsigned char sw, sh;     // sub-image size handed to cv::FAST (<= kMaxSub)
-    unsigned char level, pad;
+// FAST segments.  One reference cv::FAST call = one 30-px grid cell (:789-816); cells that pass the skip rules
+// (:794,803) and hold at least a 7x7 sub-image are grouped, along their cell row, into segments of up to 128 tested
+// pixels (the tested regions of neighbouring cells tile the row without gaps or overlap).  One CTA runs one segment:
+// the per-pixel work does not care about cells, only the non-max suppression and the 20 -> 7 retry are per cell.
+struct SegRec {
+    short ini_x, ini_y;            // iniX of the first cell, iniY of the cell row (level pixels)
+    short tw;                      // tested pixels across the segment = sum over its cells of (sub-image width - 6)
+    unsigned char sh, level;       // sub-image height handed to cv::FAST (<= kMaxSub)
+    unsigned char n_cells, w_cell; // every cell tests w_cell columns, the last one of a row possibly fewer
+    unsigned short inv_w;          // x / w_cell == (x * inv_w) >> 16 for x < 256
+    unsigned int pad;              // 16 bytes: the kernel fetches a record with one 128-bit load
 };
+static_assert(sizeof(SegRec) == 16, "SegRec is loaded as one uint4");
 struct FastLevel {
     int pitch, plane_off;  // level pixels (levels >= 1; level 0 is the input image)
     int cand_off, cand_cap;
 };
 struct FastPlan {
     FastLevel lv[kMaxLevels];
-    int nlevels, n_cells;
+    int nlevels, n_cells, n_segs;
     int ini_th, min_th;
-    int tile_rows, score_rows, list_cap;  // dynamic shared-memory carve-up, sized for the largest cell
-    int tile_pitch;                       // 48 (cells up to 43 px wide) or 80 bytes
+    int tile_rows, score_rows, list_cap;  // dynamic shared-memory carve-up, sized for the largest segment
 };
-constexpr int kFastThreads = 128;
+constexpr int kFastThreads = 256;
+constexpr int kFastCtasPerSm = 5;    // register budget: 64 K / (5 x 256) = 51 per thread
+constexpr int kFastTilePitch = 160;  // bytes: first tested column at 7..22, 128 tested px, 3 px + one word beyond
+constexpr int kFastScorePitch = 144; // 128 tested px + 2, multiple of 16
+constexpr int kFastSegPx = 128;      // tested pixels per segment row: 32 lanes x one 4-pixel word
+constexpr int kFastMaxCells = 8;
 
 struct TilePlan {  // one blur tile
     short level, x0, y0, pad;

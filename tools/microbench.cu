@@ -25,6 +25,16 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
             if (OP == 6) a[i] = __vimin3_s16x2(a[i], a[(i + 1) & 7], seed);   // VIMNMX3.S16x2
             if (OP == 7) a[i] = __vimax3_s32(a[i], a[(i + 1) & 7], seed);     // VIMNMX3
             if (OP == 8) a[i] = __byte_perm(a[i], a[(i + 1) & 7], seed);      // PRMT
+            if (OP == 10) a[i] = __vabsdiffu4(a[i], a[(i + 1) & 7]) + 0u;       // VABSDIFF4.U8
+            if (OP == 11) a[i] = __vsadu4(a[i], a[(i + 1) & 7]) + seed;        // VABSDIFF4.U8.ACC (sum of abs diffs)
+            if (OP == 12) {                                                   // VABSDIFF4 + LOP3 interleaved
+                if (i & 1) a[i] = __vabsdiffu4(a[i], a[(i + 1) & 7]);
+                else a[i] = (a[i] ^ seed) & a[(i + 1) & 7];
+            }
+            if (OP == 13) {                                                   // Harley-Seal mix: 2 lop3 + 1 popc per slot
+                const uint32_t x = a[i] ^ seed, y = a[(i + 1) & 7];
+                a[i] = __popc(x ^ y ^ acc) + ((x & y) | (acc & (x ^ y)));
+            }
             if (OP == 9) {                                                    // IMAD (fma pipe) + LOP3 (alu pipe) interleaved
                 if (i & 1) a[i] = a[i] * seed + a[(i + 1) & 7];
                 else a[i] = (a[i] ^ seed) & a[(i + 1) & 7];
@@ -80,6 +90,10 @@ int main() {
     run<7>("vimnmx3.s32", 1, d);
     run<8>("prmt", 1, d);
     run<9>("imad|lop3 interleaved", 1, d);
+    run<10>("vabsdiff4.u8", 1, d);
+    run<11>("vabsdiff4.u8.acc", 1, d);
+    run<12>("vabsdiff4|lop3 interleaved", 1, d);
+    run<13>("xor,csa(2 lop3),popc,iadd", 5, d);
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
