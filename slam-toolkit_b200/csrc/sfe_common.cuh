@@ -90,3 +90,20 @@ __device__ __forceinline__ int hamming8(const uint32_t a[8], const uint32_t b[8]
     for (int i = 0; i < 8; i++) d += __popc(a[i] ^ b[i]);
     return d;
 }
+
+// The same distance with half the POPCs: the popc pipe issues 16 lanes/clk/SM against 64 for LOP3 (tools/microbench.cu),
+// so the eight XOR words first go through a carry-save adder tree (sum = a ^ b ^ c, carry = majority: one LOP3 each):
+//   d = popc(ones) + popc(x7) + 2 popc(twos) + 4 popc(fours)
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry) {
+    sum = a ^ b ^ c;
+    carry = (a & b) | (c & (a ^ b));
+}
+__device__ __forceinline__ int hamming8_csa(const uint32_t a[8], uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3, uint32_t b4,
+                                            uint32_t b5, uint32_t b6, uint32_t b7) {
+    uint32_t s1, c1, s2, c2, ones, c3, twos, fours;
+    csa(a[0] ^ b0, a[1] ^ b1, a[2] ^ b2, s1, c1);
+    csa(a[3] ^ b3, a[4] ^ b4, a[5] ^ b5, s2, c2);
+    csa(s1, s2, a[6] ^ b6, ones, c3);
+    csa(c1, c2, c3, twos, fours);
+    return __popc(ones) + __popc(a[7] ^ b7) + 2 * __popc(twos) + 4 * __popc(fours);
+}

@@ -57,7 +57,7 @@ struct FastPlan {
     int tile_rows, score_rows, list_cap;  // dynamic shared-memory carve-up, sized for the largest segment
 };
 constexpr int kFastThreads = 256;
-constexpr int kFastCtasPerSm = 5;    // register budget: 64 K / (5 x 256) = 51 per thread
+constexpr int kFastCtasPerSm = 5;    // register budget: 64 K / (5 x 256) = 51 per thread (6 CTAs = 40 registers measured slower)
 constexpr int kFastTilePitch = 160;  // bytes: first tested column at 7..22, 128 tested px, 3 px + one word beyond
 constexpr int kFastScorePitch = 144; // 128 tested px + 2, multiple of 16
 constexpr int kFastSegPx = 128;      // tested pixels per segment row: 32 lanes x one 4-pixel word

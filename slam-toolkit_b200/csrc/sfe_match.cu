@@ -309,12 +309,24 @@ __global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint8_t
         }
         __syncthreads();
         const uint32_t rbase = (uint32_t)(t0 - c0);
-#pragma unroll 4
-        for (int r = 0; r < tn; r++) {
+        // four rows per step; a row only reaches the top-2 update when it beats the current second best, which after
+        // the first few hundred rows is rare: one compare + branch per four rows instead of three min/max per row
+        int r = 0;
+        for (; r + 4 <= tn; r += 4) {
+            uint32_t key[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint4 u = tile[2 * (r + j)], w = tile[2 * (r + j) + 1];
+                key[j] = (uint32_t)hamming8_csa(a, u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w) << 22 | (rbase + r + j);
+            }
+            if (min(min(key[0], key[1]), min(key[2], key[3])) < k1) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) top2_insert(k0, k1, key[j]);
+            }
+        }
+        for (; r < tn; r++) {
             const uint4 u = tile[2 * r], w = tile[2 * r + 1];
-            const int d = __popc(a[0] ^ u.x) + __popc(a[1] ^ u.y) + __popc(a[2] ^ u.z) + __popc(a[3] ^ u.w) +
-                          __popc(a[4] ^ w.x) + __popc(a[5] ^ w.y) + __popc(a[6] ^ w.z) + __popc(a[7] ^ w.w);
-            top2_insert(k0, k1, (uint32_t)d << 22 | (rbase + r));
+            top2_insert(k0, k1, (uint32_t)hamming8_csa(a, u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w) << 22 | (rbase + r));
         }
     }
     if (qi < q) {
@@ -365,8 +377,7 @@ __global__ void __launch_bounds__(256) knn2_rows_kernel(const uint8_t *__restric
                 uint32_t key[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
-                    const int d = __popc(a[h][0] ^ u.x) + __popc(a[h][1] ^ u.y) + __popc(a[h][2] ^ u.z) + __popc(a[h][3] ^ u.w) +
-                                  __popc(a[h][4] ^ w.x) + __popc(a[h][5] ^ w.y) + __popc(a[h][6] ^ w.z) + __popc(a[h][7] ^ w.w);
+                    const int d = hamming8_csa(a[h], u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w);
                     key[h] = valid[h] ? (uint32_t)d << 22 | (rel + 32 * h) : kNoKey;
                 }
                 if (__any_sync(0xffffffffu, min(key[0], key[1]) < thr)) {
@@ -682,7 +693,7 @@ static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, i
     cudaStream_t st = m->stream;
     const bool by_rows = q <= kRowsQMax;  // thread = row (streaming) for few queries, thread = query otherwise
     const int qgroups = by_rows ? 1 : div_up(q, kKnnThreads);
-    int chunks = std::max(1, ((by_rows ? 8 : 2) * m->sm_count) / qgroups);
+    int chunks = std::max(1, (8 * m->sm_count) / qgroups);  // 8 CTAs of 256 threads per SM: the XOR-CSA-POPC chain needs the warps to hide its latency
     int64_t chunk_rows = std::max<int64_t>((db->rows + chunks - 1) / chunks, 1);
     chunk_rows = (chunk_rows + 511) / 512 * 512;
     SFE_REQUIRE(chunk_rows <= (1 << 22), SFE_ERR_UNSUPPORTED, "database shard larger than 2^22 rows per chunk");
