@@ -813,7 +813,6 @@ __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__r
 // ---------------------------------------------------------------------------------------------
 // IC_Angle (:77-104) + rBRIEF (:107-147), one warp per keypoint; also the final keypoint record
 // ---------------------------------------------------------------------------------------------
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // :452-469
 __device__ const signed char g_pattern[1024] = {
 #include "orb_pattern_data.inc"
 };
@@ -851,11 +850,34 @@ constexpr bool disc_is_symmetric() {
     return true;
 }
 static_assert(disc_is_symmetric(), "IC_Angle disc must be symmetric");
-// bit (dv + 15) set iff pixel (u, dv) lies in the 31-px disc
-__device__ __forceinline__ uint32_t disc_rows(int au) {
-    const int vm = c_umax[au];
-    return ((2u << (2 * vm)) - 1u) << (kHalfPatch - vm);
+// Per disc row dv (|dv| = 0..15) the eight 4-pixel words that cover columns u = -15 .. +16: u[j] = the column
+// offsets as signed bytes, zero outside the disc; in[j] = 1 per pixel inside the disc.  One IDP.4A per word then
+// gives sum(u * I) and sum(I) of four pixels at once.
+struct DiscTable {
+    uint32_t u[16][8], in[16][8];
+};
+constexpr DiscTable make_disc_table() {
+    DiscTable t{};
+    for (int v = 0; v < 16; v++)
+        for (int j = 0; j < 8; j++)
+            for (int k = 0; k < 4; k++) {
+                const int u = -kHalfPatch + 4 * j + k, au = u < 0 ? -u : u;
+                if (au <= kUmax[v]) {
+                    t.u[v][j] |= (uint32_t)(u & 0xFF) << (8 * k);
+                    t.in[v][j] |= 1u << (8 * k);
+                }
+            }
+    return t;
 }
+__device__ const DiscTable g_disc = make_disc_table();
+
+__device__ __forceinline__ int dp4a_u8s8(uint32_t pix, uint32_t w, int acc) {  // acc + sum_k u8(pix.k) * s8(w.k)
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(w), "r"(acc));
+    return d;
+}
+
+constexpr int kKpPerWarp = 4;  // keypoints one warp handles in turn: the pattern / disc table set-up is paid once
 
 __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O) {
     __shared__ float2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane`, as floats
@@ -864,9 +886,18 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
         const int byte = i >> 4, s = i & 15;
         pat[s * 32 + byte] = make_float2((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
     }
+    // IC_Angle: the 31 x 32-byte window is 31 rows x 8 words; lane = word (lane & 7) of rows (lane >> 3) + 4 t,
+    // t = 0..7, so one warp-wide load touches 4 rows (4-8 cache lines).  The lane's weights stay in registers.
+    const int wj = lane & 7, wr0 = lane >> 3;
+    uint32_t wu[8], win[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int r = wr0 + 4 * t, adv = r < 31 ? (r < kHalfPatch ? kHalfPatch - r : r - kHalfPatch) : 0;
+        wu[t] = r < 31 ? __ldg(&g_disc.u[adv][wj]) : 0u;
+        win[t] = r < 31 ? __ldg(&g_disc.in[adv][wj]) : 0u;
+    }
     __syncthreads();
-    // locate keypoint g: levels are concatenated 0..L-1 (:1076-1104); lane k holds level k's count
-    const int g = blockIdx.x * 8 + warp;
+    // keypoints are the levels' survivors concatenated 0..L-1 (:1076-1104); lane k holds level k's count
     const int cnt = lane < S.nlevels ? min(S.kp_count[slot * S.nlevels + lane], S.lv[lane].kp_cap) : 0;
     int inc = cnt;
 #pragma unroll
@@ -875,87 +906,89 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
         if (lane >= o) inc += u;
     }
     const int total = __shfl_sync(0xffffffffu, inc, kMaxLevels - 1);
-    const int l = __popc(__ballot_sync(0xffffffffu, lane < S.nlevels && inc <= g));  // first level whose prefix exceeds g
-    const int local = g - __shfl_sync(0xffffffffu, inc - cnt, min(l, 31));
     const bool set_a = img < S.split;
     const int oi = set_a ? img : img - S.split;
-    if (g == 0 && lane == 0) {
+    if (blockIdx.x == 0 && tid == 0) {
         (set_a ? O.n_a : O.n_b)[oi] = min(total, O.cap);
         if (total > O.cap) atomicOr(&S.flags[slot], kFlagOutOverflow);
     }
-    if (g >= total || g >= O.cap) return;
-    const LevelPlan &L = S.lv[l];
-    const uint32_t v = S.kpst[(size_t)slot * S.kpst_stride + L.kp_off + local];
-    const int x = (v & 0xFFF) + kBorder, y = ((v >> 12) & 0xFFF) + kBorder;
-    int pitch;
-    const uint8_t *lvl = level_pixels(S, l, img, pitch);
-    // intensity centroid over the 31-px disc on the UNBLURRED level; lane = column u:
-    // m_10 = u * (column sum), m_01 = sum dv * I
-    int m01 = 0, colsum = 0;
-    const int u = lane - kHalfPatch;
-    if (lane < 31) {
-        const uint32_t rows = disc_rows(u < 0 ? -u : u);
-        const uint8_t *c = lvl + (size_t)(y - kHalfPatch) * pitch + x + u;
+    const int g0 = (blockIdx.x * 8 + warp) * kKpPerWarp;
+    for (int g = g0; g < g0 + kKpPerWarp; g++) {
+        if (g >= total || g >= O.cap) return;
+        const int l = __popc(__ballot_sync(0xffffffffu, lane < S.nlevels && inc <= g));  // first level whose prefix exceeds g
+        const int local = g - __shfl_sync(0xffffffffu, inc - cnt, min(l, 31));
+        const LevelPlan &L = S.lv[l];
+        const uint32_t v = S.kpst[(size_t)slot * S.kpst_stride + L.kp_off + local];
+        const int x = (v & 0xFFF) + kBorder, y = ((v >> 12) & 0xFFF) + kBorder;
+        int pitch;
+        const uint8_t *lvl = level_pixels(S, l, img, pitch);
+        // intensity centroid over the 31-px disc on the UNBLURRED level (:77-104): m_10 = sum u * I, m_01 = sum dv * I.
+        // Word j of a row = pixels x - 15 + 4 j .. + 3, assembled from the two aligned words around it (rows may
+        // start at any byte); the last word reaches x + 20 at most: keypoints keep 19 px from the border, so that
+        // stays inside the row or spills 2 bytes into the next one.  Four pixels per IDP.4A.
+        int m10 = 0, m01 = 0;
+        {
+            const uint8_t *rp = lvl + (size_t)(y - kHalfPatch + wr0) * pitch + (x - kHalfPatch + 4 * wj);
 #pragma unroll
-        for (int k = 0; k <= 2 * kHalfPatch; k++) {
-            if (rows >> k & 1) {
-                const int val = __ldg(c);
-                colsum += val;
-                m01 += (k - kHalfPatch) * val;
+            for (int t = 0; t < 8; t++, rp += 4 * (size_t)pitch) {
+                if (wr0 + 4 * t < 31) {
+                    const uint32_t *wp = (const uint32_t *)((uintptr_t)rp & ~(uintptr_t)3);
+                    const uint32_t px = __funnelshift_r(__ldg(wp), __ldg(wp + 1), ((uint32_t)(uintptr_t)rp & 3) * 8);
+                    m10 = dp4a_u8s8(px, wu[t], m10);
+                    m01 += (wr0 + 4 * t - kHalfPatch) * dp4a_u8s8(px, win[t], 0);
+                }
             }
-            c += pitch;
         }
-    }
-    int m10 = u * colsum;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        m01 += __shfl_xor_sync(0xffffffffu, m01, o);
-        m10 += __shfl_xor_sync(0xffffffffu, m10, o);
-    }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
-    // rotated pattern lookups on the blurred level; float ops rounded one by one (T2)
-    float a = 0.f, b = 0.f;
-    if (lane == 0) {
-        const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.0);
-        const float rad = __fmul_rn(angle, factor_pi);
-        double sn, cs;
-        sincos((double)rad, &sn, &cs);
-        a = (float)cs;
-        b = (float)sn;
-    }
-    a = __shfl_sync(0xffffffffu, a, 0);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    const int bp = L.blur_pitch;
-    const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off + (size_t)y * bp + x;
-    uint32_t byte = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int tv[2];
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const float2 pp = pat[(2 * k + s) * 32 + lane];
-            const int ry = __float2int_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)));
-            const int rx = __float2int_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)));
-            tv[s] = __ldg(bl + (ry * bp + rx));
+        for (int o = 16; o > 0; o >>= 1) {
+            m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+            m10 += __shfl_xor_sync(0xffffffffu, m10, o);
         }
-        byte |= (uint32_t)(tv[0] < tv[1]) << k;
-    }
-    uint8_t *desc = (set_a ? O.desc_a : O.desc_b) + ((size_t)oi * O.cap + g) * 32;
-    desc[lane] = (uint8_t)byte;
-    if (lane == 0) {
-        sfe_keypoint kp;
-        kp.x = (float)x;
-        kp.y = (float)y;
-        if (l != 0) {  // :1095-1101
-            kp.x = __fmul_rn(kp.x, L.scale);
-            kp.y = __fmul_rn(kp.y, L.scale);
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // rotated pattern lookups on the blurred level; float ops rounded one by one (T2)
+        float a = 0.f, b = 0.f;
+        if (lane == 0) {
+            const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.0);
+            const float rad = __fmul_rn(angle, factor_pi);
+            double sn, cs;
+            sincos((double)rad, &sn, &cs);
+            a = (float)cs;
+            b = (float)sn;
         }
-        kp.size = L.size;
-        kp.angle = angle;
-        kp.response = (float)(v >> 24);
-        kp.octave = l;
-        kp.class_id = -1;
-        (set_a ? O.kps_a : O.kps_b)[(size_t)oi * O.cap + g] = kp;
+        a = __shfl_sync(0xffffffffu, a, 0);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        const int bp = L.blur_pitch;
+        const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off + (size_t)y * bp + x;
+        uint32_t byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int tv[2];
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const float2 pp = pat[(2 * k + s) * 32 + lane];
+                const int ry = __float2int_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)));
+                const int rx = __float2int_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)));
+                tv[s] = __ldg(bl + (ry * bp + rx));
+            }
+            byte |= (uint32_t)(tv[0] < tv[1]) << k;
+        }
+        uint8_t *desc = (set_a ? O.desc_a : O.desc_b) + ((size_t)oi * O.cap + g) * 32;
+        desc[lane] = (uint8_t)byte;
+        if (lane == 0) {
+            sfe_keypoint kp;
+            kp.x = (float)x;
+            kp.y = (float)y;
+            if (l != 0) {  // :1095-1101
+                kp.x = __fmul_rn(kp.x, L.scale);
+                kp.y = __fmul_rn(kp.y, L.scale);
+            }
+            kp.size = L.size;
+            kp.angle = angle;
+            kp.response = (float)(v >> 24);
+            kp.octave = l;
+            kp.class_id = -1;
+            (set_a ? O.kps_a : O.kps_b)[(size_t)oi * O.cap + g] = kp;
+        }
     }
 }
 
@@ -1435,7 +1468,7 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     } else {
         prof_mark(ex, 2); prof_mark(ex, 3); prof_mark(ex, 4);
     }
-    orient_describe_kernel<<<dim3(div_up(O.cap, 8), count), 256, 0, st>>>(S, O);
+    orient_describe_kernel<<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O);
     prof_mark(ex, 5);
     ex->prof_pending = ex->profiling;
     ex->prof_has_stereo = false;
