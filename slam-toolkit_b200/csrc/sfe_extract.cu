@@ -877,11 +877,26 @@ __device__ __forceinline__ int dp4a_u8s8(uint32_t pix, uint32_t w, int acc) {  /
     return d;
 }
 
+constexpr int kPatchR = 18;      // rBRIEF pattern radius: max |(x, y)| = |(-13, -13)| = 18.4, rounds to at most 18
+constexpr int kPatchRows = 2 * kPatchR + 1, kPatchWords = 10;  // 37 px + up to 3 px of word alignment = 40 bytes
+constexpr signed char kPatternHost[1024] = {
+#include "orb_pattern_data.inc"
+};
+constexpr bool pattern_within_patch() {
+    for (int i = 0; i < 512; i++) {
+        const int px = kPatternHost[2 * i], py = kPatternHost[2 * i + 1];
+        if (4 * (px * px + py * py) >= (2 * kPatchR + 1) * (2 * kPatchR + 1)) return false;  // |p| < R + 0.5
+    }
+    return true;
+}
+static_assert(pattern_within_patch(), "a rotated pattern point could round outside the staged window");
 constexpr int kKpPerWarp = 4;  // keypoints one warp handles in turn: the pattern / disc table set-up is paid once
 
-__global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O) {
+__global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSet O) {
     __shared__ float2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane`, as floats
+    __shared__ uint32_t patch_all[8][kPatchRows * kPatchWords];  // per warp: the blurred window the pattern can reach
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y, slot = slot_of(S, img);
+    uint32_t *patch = patch_all[warp];
     for (int i = tid; i < 512; i += 256) {
         const int byte = i >> 4, s = i & 15;
         pat[s * 32 + byte] = make_float2((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
@@ -957,8 +972,23 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
         }
         a = __shfl_sync(0xffffffffu, a, 0);
         b = __shfl_sync(0xffffffffu, b, 0);
+        // The 512 pattern points lie within 18.4 px of the centre, so every rotated sample falls in the 37 x 37 window
+        // around the keypoint: the warp copies it to shared memory with row-coalesced word loads (3 rows of 10 aligned
+        // words per step; blurred planes have 16-byte pitches, so all rows share one alignment) and gathers from there
+        // instead of sending 16 scattered loads per lane through L1.
         const int bp = L.blur_pitch;
-        const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off + (size_t)y * bp + x;
+        const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off;
+        const int xl = x - kPatchR, al = xl & 3;  // window's first column and its offset inside an aligned word
+        __syncwarp();                             // the previous keypoint's gathers are done
+        if (lane < 3 * kPatchWords) {
+            const int rs = lane / kPatchWords, c = lane - rs * kPatchWords;
+            const uint32_t *src = (const uint32_t *)(bl + (size_t)(y - kPatchR + rs) * bp + (xl - al)) + c;
+            uint32_t *dst = patch + rs * kPatchWords + c;
+#pragma unroll
+            for (int r = rs; r < kPatchRows; r += 3, src += 3 * (bp >> 2), dst += 3 * kPatchWords) *dst = __ldg(src);
+        }
+        __syncwarp();
+        const uint8_t *pc = (const uint8_t *)patch + kPatchR * (kPatchWords * 4) + kPatchR + al;  // the keypoint's pixel
         uint32_t byte = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -968,7 +998,7 @@ __global__ void __launch_bounds__(256) orient_describe_kernel(ImgSet S, OutSet O
                 const float2 pp = pat[(2 * k + s) * 32 + lane];
                 const int ry = __float2int_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)));
                 const int rx = __float2int_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)));
-                tv[s] = __ldg(bl + (ry * bp + rx));
+                tv[s] = pc[ry * (kPatchWords * 4) + rx];
             }
             byte |= (uint32_t)(tv[0] < tv[1]) << k;
         }
