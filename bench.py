@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-threads", type=int, default=2, help="host threads (one handle each) issuing the e2e calls")
     ap.add_argument("--knn-rows", type=int, default=10_000_000, help="rows of the descriptor map of the Hamming leg (0 = skip)")
+    ap.add_argument("--proj-points", type=int, default=500_000, help="map points of the ProjectionMatch leg (0 = skip)")
     ap.add_argument("--clock-period", type=float, default=0.05, help="seconds between NVML clock samples (0 = no sampling)")
     return ap.parse_args()
 
@@ -243,6 +244,57 @@ def hamming_leg(args, dev, rank, world, dist):
             "q1_stream_ms": ms1, "q1_stream_gbs": gbs1, "accepted_ratio_test": float((2 * out[:, 1] < out[:, 3]).mean())}
 
 
+def projection_leg(args, dev, rank, world, dist, kps, desc):
+    """BASELINE config 5 beside the headline: ProjectionMatch (r = 50 px, identity pose) of a local map of N points
+    against one frame's keypoints; map points sharded over the ranks (all-gather of the per-keypoint keys + merge).
+    Algorithmic bytes per call: N * (24 + 32) + M * (8 + 32) + 8 * M."""
+    from slam_toolkit_b200 import api, sharding, synth
+    n, m_kps = args.proj_points, len(kps)
+    xy = np.stack([kps["x"], kps["y"]], axis=1).astype(np.float64)
+    xw, mpd = synth.projection_scene(xy, desc, n, seed=99)
+    a, b = sharding.block(n, world, rank)
+    cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, (0, 0, 0, 0), W, H)
+    m = api.Matcher(dev)
+    d_xw = api.DeviceBuffer((b - a) * 24, dev).upload(np.ascontiguousarray(xw[a:b]))
+    d_mpd = api.DeviceBuffer((b - a) * 32, dev).upload(np.ascontiguousarray(mpd[a:b]))
+    d_kps = api.DeviceBuffer(m_kps * 28, dev).upload(np.ascontiguousarray(kps))
+    d_kd = api.DeviceBuffer(m_kps * 32, dev).upload(np.ascontiguousarray(desc))
+    d_q, d_d = api.DeviceBuffer(m_kps * 4, dev), api.DeviceBuffer(m_kps * 4, dev)
+    Tcw = np.eye(4)
+
+    def call():
+        m.projection_match_dev(d_xw.ptr, d_mpd.ptr, None, b - a, Tcw, cam, d_kps.ptr, d_kd.ptr, m_kps, 50.0, d_q.ptr, d_d.ptr)
+    call()
+    e0, e1 = api.Event(dev), api.Event(dev)
+    reps = 20
+    m.set_async(True)
+    e0.record(m)
+    for _ in range(reps):
+        call()
+    e1.record(m)
+    m.wait()
+    m.set_async(False)
+    ms = e0.elapsed_ms(e1) / reps
+    matched = int((d_q.download((m_kps,), np.int32) >= 0).sum())
+    sharded_ms = None
+    if dist is not None:
+        import torch
+        lm = sharding.ShardedLocalMap(m, xw[a:b], mpd[a:b], n)
+        lm.projection_match(Tcw, cam, kps, desc, 50.0)
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            lm.projection_match(Tcw, cam, kps, desc, 50.0)
+        t = torch.tensor([ms, (time.perf_counter() - t0) / 5 * 1e3], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, sharded_ms = t.tolist()
+    alg = n * 56 + m_kps * 48
+    return {"map_points": n, "frame_keypoints": m_kps, "radius_px": 50.0, "ms_per_call_shard_kernels": ms,
+            "map_points_per_s": n / (ms / 1e3), "algorithmic_gbs": alg / (ms / 1e3) / 1e9,
+            "keypoints_matched_this_shard": matched, "sharded_call_ms_with_allgather": sharded_ms,
+            "sharding": f"{world} map-point shard(s)"}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -365,6 +417,10 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
     hamming = hamming_leg(args, dev, rank, world, dist) if args.knn_rows > 0 else None
+    projection = None
+    if args.proj_points > 0:
+        nl0 = int(out["n_l"][0])
+        projection = projection_leg(args, dev, rank, world, dist, out["kps_l"][0, :nl0].copy(), out["desc_l"][0, :nl0].copy())
     h2d = 2 * F * W * H
     d2h = sum(v.nbytes for v in out.values())
 
@@ -426,6 +482,9 @@ def main():
     if hamming is not None:
         hamming["q1_stream_frac_of_hbm_peak"] = hamming["q1_stream_gbs"] / (world * hbm_peak)
         line["hamming"] = hamming
+    if projection is not None:
+        projection["frac_of_hbm_peak"] = projection["algorithmic_gbs"] / hbm_peak
+        line["projection_match"] = projection
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         frames = args.cpu_frames or 32 * cores   # ~2 s per core: 10-30 s of CPU work in all

@@ -173,6 +173,8 @@ struct KpGrid {
     int *cell_start;   // gw*gh + 1
     int *cell_fill;    // gw*gh
     int *order;        // m: keypoint indices sorted by cell
+    double2 *sxy;      // m: keypoint coordinates as doubles, in cell order (the matcher's distance test is in double)
+    uint4 *sdesc;      // 2 m: descriptors in cell order
 };
 
 __device__ __forceinline__ int grid_cell(const KpGrid &G, float x, float y) {
@@ -199,11 +201,18 @@ __global__ void grid_scan_kernel(KpGrid G) {  // one CTA; the grid has a few hun
     for (int i = threadIdx.x; i < n; i += blockDim.x) G.cell_fill[i] = 0;
 }
 
-__global__ void grid_fill_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps) {
+__global__ void grid_fill_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps, const uint8_t *__restrict__ desc) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= G.m) return;
-    const int c = grid_cell(G, kps[j].x, kps[j].y);
-    G.order[G.cell_start[c] + atomicAdd(&G.cell_fill[c], 1)] = j;
+    const float x = kps[j].x, y = kps[j].y;
+    const int c = grid_cell(G, x, y), t = G.cell_start[c] + atomicAdd(&G.cell_fill[c], 1);
+    G.order[t] = j;
+    G.sxy[t] = make_double2((double)x, (double)y);
+    if (desc) {
+        const uint4 *d = (const uint4 *)(desc + (size_t)j * 32);
+        G.sdesc[2 * t] = __ldg(d);
+        G.sdesc[2 * t + 1] = __ldg(d + 1);
+    }
 }
 
 struct ProjParams {
@@ -243,21 +252,27 @@ __global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjPar
     uint32_t a[8];
     load_desc(mp_desc + (size_t)i * 32, a);
     const double r2max = __dmul_rn(P.radius, P.radius);
-    const int cx0 = min(max((int)floor(u - P.radius) >> kGridShift, 0), G.gw - 1);
-    const int cx1 = min(max((int)floor(u + P.radius) >> kGridShift, 0), G.gw - 1);
     const int cy0 = min(max((int)floor(v - P.radius) >> kGridShift, 0), G.gh - 1);
     const int cy1 = min(max((int)floor(v + P.radius) >> kGridShift, 0), G.gh - 1);
     uint32_t k0 = kNoKey, k1 = kNoKey;
     for (int cy = cy0; cy <= cy1; cy++) {
+        // keypoints of cell row cy have y in [32 cy, 32 cy + 32) (the border rows also hold what was clamped into them):
+        // the circle's half-width on that band bounds the cells worth visiting -- a superset of the d^2 < r^2 set
+        const double lo = cy == 0 ? -1e300 : (double)(cy << kGridShift), hi = cy == G.gh - 1 ? 1e300 : (double)((cy + 1) << kGridShift);
+        const double dy = fmax(fmax(lo - v, v - hi), 0.);
+        const double h2 = r2max - dy * dy;
+        if (!(h2 > 0.)) continue;
+        const double hw = sqrt(h2) + 1.;
+        const int cx0 = min(max((int)floor(u - hw) >> kGridShift, 0), G.gw - 1);
+        const int cx1 = min(max((int)floor(u + hw) >> kGridShift, 0), G.gw - 1);
         const int s = G.cell_start[cy * G.gw + cx0], e = G.cell_start[cy * G.gw + cx1 + 1];  // cells of a row are contiguous
         for (int t = s; t < e; t++) {
-            const int j = G.order[t];
-            const double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
+            const double2 p = G.sxy[t];
+            const double ddx = u - p.x, ddy = v - p.y;
             const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
             if (!(d2 < r2max)) continue;  // FLANN radius search: strict <
-            uint32_t b[8];
-            load_desc(kp_desc + (size_t)j * 32, b);
-            top2_insert(k0, k1, (uint32_t)hamming8(a, b) << 16 | (uint32_t)j);
+            const uint4 b0 = G.sdesc[2 * t], b1 = G.sdesc[2 * t + 1];
+            top2_insert(k0, k1, (uint32_t)hamming8_csa(a, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w) << 16 | (uint32_t)G.order[t]);
         }
     }
     if (k0 == kNoKey) return;
@@ -637,20 +652,24 @@ struct sfe_frame {
 };
 
 // bucket grid over m_kps keypoints (replaces the per-frame FLANN kd-tree, src/frame.cpp:59-68)
-static int build_grid(sfe_matcher *m, DevBuf<int> &mem, KpGrid &G, const sfe_camera *cam, const sfe_keypoint *kps, int m_kps) {
+static int build_grid(sfe_matcher *m, DevBuf<int> &mem, KpGrid &G, const sfe_camera *cam, const sfe_keypoint *kps,
+                      const uint8_t *kp_desc, int m_kps) {
     cudaStream_t st = m->stream;
     G.gw = (std::max(cam->width, 1) >> kGridShift) + 1;
     G.gh = (std::max(cam->height, 1) >> kGridShift) + 1;
     G.m = m_kps;
     const int cells = G.gw * G.gh;
-    SFE_CUDA(mem.ensure((size_t)2 * cells + 1 + std::max(m_kps, 1)));
+    const size_t ints = ((size_t)2 * cells + 1 + std::max(m_kps, 1) + 3) & ~(size_t)3;  // what follows is 16-byte aligned
+    SFE_CUDA(mem.ensure(ints + (size_t)std::max(m_kps, 1) * (4 + 8)));
     G.cell_start = mem.p;
     G.cell_fill = mem.p + cells + 1;
     G.order = mem.p + 2 * cells + 1;
+    G.sxy = (double2 *)(mem.p + ints);
+    G.sdesc = (uint4 *)(mem.p + ints + (size_t)std::max(m_kps, 1) * 4);
     SFE_CUDA(cudaMemsetAsync(G.cell_start, 0, sizeof(int) * (cells + 1), st));
     if (m_kps > 0) grid_count_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
     grid_scan_kernel<<<1, 256, 0, st>>>(G);
-    if (m_kps > 0) grid_fill_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps);
+    if (m_kps > 0) grid_fill_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(G, kps, kp_desc);
     m->launches += 3;
     return SFE_OK;
 }
@@ -665,7 +684,7 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
     if (prebuilt) {
         G = *prebuilt;  // a resident frame brings its own index
     } else {
-        int rc = build_grid(m, m->d_grid, G, cam, kps, m_kps);
+        int rc = build_grid(m, m->d_grid, G, cam, kps, kp_desc, m_kps);
         if (rc != SFE_OK) return rc;
     }
     SFE_CUDA(m->d_best.ensure(m_kps));
@@ -893,7 +912,7 @@ static int frame_finish(sfe_matcher *m, sfe_frame *f) {
         normalized_undistort_kernel<<<div_up(f->n, 128), 128, 0, st>>>(f->cam, f->kps.p, f->n, f->nrm.p);
         m->launches++;
     }
-    int rc = build_grid(m, f->grid_mem, f->grid, &f->cam, f->kps.p, f->n);
+    int rc = build_grid(m, f->grid_mem, f->grid, &f->cam, f->kps.p, f->desc.p, f->n);
     if (rc != SFE_OK) return rc;
     SFE_CUDA(cudaGetLastError());
     SFE_CUDA(cudaStreamSynchronize(st));
