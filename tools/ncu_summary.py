@@ -23,6 +23,8 @@ METRICS = [
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "lts__t_sector_hit_rate.pct",
@@ -56,7 +58,8 @@ def main():
                 i = hdr.index(m)
                 print(f"{m:70s} {r[i]:>16s} {units[i]}")
     for name in dict.fromkeys(names):
-        out = ncu(["-i", rep, "--page", "source", "--csv", "--kernel-name", name])
+        base = name.replace("void ", "").split("<")[0].strip()   # templates: ncu matches the base name
+        out = ncu(["-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:^" + base + "$"])
         srows = list(csv.reader(io.StringIO(out)))
         try:
             h = next(r for r in srows if "Instructions Executed" in r)
@@ -69,9 +72,13 @@ def main():
                 break
             if len(r) > ie and r[ie].isdigit():
                 body.append(r)
+        stalls = {c: sum(int(r[i] or 0) for r in body if len(r) > i) for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c}
+        st_tot = sum(stalls.values()) or 1
         tot = sum(int(r[ie]) for r in body) or 1
         ts = sum(int(r[sm]) for r in body) or 1
-        print(f"\n== {name}: SASS instructions executed by segment (split at BAR.SYNC), first launch in report")
+        print(f"\n== {name}: warp stall samples, first launch in report: " +
+              ", ".join(f"{k[6:]} {100 * v / st_tot:.0f} %" for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:6]))
+        print(f"== {name}: SASS instructions executed by segment (split at BAR.SYNC), first launch in report")
         seg = acc = accs = start = 0
         for i, r in enumerate(body):
             acc += int(r[ie])
