@@ -143,6 +143,35 @@ int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint
                           int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
                           int cap);
 
+/* Tracking front end of a stereo SEQUENCE in one call: sfe_stereo_frames over `frames` consecutive stereo pairs, then
+ * for every frame f >= 1 what the tracker does before pose optimisation (src/posetracker.cpp -> src/matcher.cpp:134-209):
+ * the previous frame's keypoints with a stereo correspondence become map points through StereoFrame::GetDepth
+ * (src/frame.cpp:391-409: Xc = (n_x, n_y, 1) * fx * baseline / dx, with the normalised keypoint of
+ * Camera::NormalizedUndistort), in keypoint order, and ProjectionMatch(those points, Tcw = tp->rt, frame f, tp->radius)
+ * matches them against frame f's keypoints.  tp->rt is the motion prior between consecutive frames (identity = the
+ * reference's first guess).  track_idx[f*cap + j] = keypoint index in frame f-1 whose map point matched keypoint j of
+ * frame f, or -1 (frame 0's row is all -1); track_dist (optional) = the accepted Hamming distance or -1. */
+typedef struct sfe_track_params {
+    sfe_camera cam;
+    double baseline;          /* metres; depth = fx * baseline / disparity */
+    double rt[12];            /* Tcw (3x4 row-major) applied to the previous frame's camera-frame points */
+    double radius;            /* ProjectionMatch search radius in pixels (the tracker uses 50) */
+    double best12_threshold;  /* 0.5, src/matcher.cpp:196 */
+} sfe_track_params;
+int sfe_stereo_sequence(sfe_extractor *ex, const uint8_t *left, const uint8_t *right,
+                        size_t image_stride, int frames, int w, int h, int stride,
+                        const sfe_stereo_params *sp, const sfe_track_params *tp, sfe_keypoint *kps_l,
+                        uint8_t *desc_l, int32_t *n_l, sfe_keypoint *kps_r, uint8_t *desc_r,
+                        int32_t *n_r, int32_t *stereo_idx, int32_t *stereo_dist, int32_t *track_idx,
+                        int32_t *track_dist, int cap);
+int sfe_stereo_sequence_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev,
+                            size_t image_stride, int frames, int w, int h, int stride,
+                            const sfe_stereo_params *sp, const sfe_track_params *tp,
+                            sfe_keypoint *kps_l_dev, uint8_t *desc_l_dev, int32_t *n_l_dev,
+                            sfe_keypoint *kps_r_dev, uint8_t *desc_r_dev, int32_t *n_r_dev,
+                            int32_t *stereo_idx_dev, int32_t *stereo_dist_dev, int32_t *track_idx_dev,
+                            int32_t *track_dist_dev, int cap);
+
 /* Row pitch (bytes) the _dev entry points like best for resident images of width w: the smallest multiple
  * of 16 >= w.  With such a pitch, a 16-byte aligned base and an image stride that is a multiple of 16 the
  * kernels fetch level-0 tiles with TMA; any other layout is read with ordinary loads (same results). */

@@ -67,6 +67,10 @@ def lib():
         L.orc_hamming256.argtypes = [vp, vp]
         L.orc_stereo_match.argtypes = [vp, vp, ci, vp, vp, ci, cd, cd, cd, vp, vp]
         L.orc_projection_match.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, cd, vp, vp]
+        L.orc_projection_match_grid.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, cd, vp, vp]
+        L.orc_track_pair.argtypes = [vp, cd, vp, cd, cd, vp, vp, ci, vp, vp, vp, vp, ci, vp, vp, ci]
+        L.orc_stereo_sequence.restype = C.c_int64
+        L.orc_stereo_sequence.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp, cd, cd, vp, vp]
         L.orc_knn2.argtypes = [vp, ci, vp, C.c_int64, C.c_int64, vp]
         L.orc_stereo_frames.restype = C.c_int64
         L.orc_stereo_frames.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp]
@@ -209,7 +213,7 @@ def make_camera(fx, fy, cx, cy, d, width, height):
     return cam
 
 
-def projection_match(xw, mp_desc, skip, rt, cam, kps, kp_desc, radius, ratio=0.5):
+def projection_match(xw, mp_desc, skip, rt, cam, kps, kp_desc, radius, ratio=0.5, grid=False):
     xw = np.ascontiguousarray(xw, np.float64)
     mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
     skip = None if skip is None else np.ascontiguousarray(skip, np.uint8)
@@ -219,9 +223,22 @@ def projection_match(xw, mp_desc, skip, rt, cam, kps, kp_desc, radius, ratio=0.5
     m = len(kps)
     to_q = np.full(m, -1, np.int32)
     dist = np.full(m, -1, np.int32)
-    lib().orc_projection_match(_p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), C.byref(cam), _p(kps),
-                               _p(kp_desc), m, radius, ratio, _p(to_q), _p(dist))
+    fn = lib().orc_projection_match_grid if grid else lib().orc_projection_match
+    fn(_p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), C.byref(cam), _p(kps), _p(kp_desc), m, radius, ratio, _p(to_q), _p(dist))
     return to_q, dist
+
+
+def track_pair(cam, baseline, rt, radius, kl_prev, dl_prev, kr_prev, sidx_prev, kps, desc, ratio=0.5, grid=False):
+    """Tracking step between consecutive stereo frames (orc_track_pair) -> (track_idx, track_dist) per keypoint of `kps`."""
+    kl_prev, kr_prev, kps = np.ascontiguousarray(kl_prev), np.ascontiguousarray(kr_prev), np.ascontiguousarray(kps)
+    dl_prev, desc = np.ascontiguousarray(dl_prev, np.uint8), np.ascontiguousarray(desc, np.uint8)
+    sidx_prev = np.ascontiguousarray(sidx_prev, np.int32)
+    rt = np.ascontiguousarray(np.asarray(rt, np.float64)[:3, :4]).reshape(12)
+    tidx = np.full(len(kps), -1, np.int32)
+    tdist = np.full(len(kps), -1, np.int32)
+    lib().orc_track_pair(C.byref(cam), baseline, _p(rt), radius, ratio, _p(kl_prev), _p(dl_prev), len(kl_prev), _p(kr_prev),
+                         _p(sidx_prev), _p(kps), _p(desc), len(kps), _p(tidx), _p(tdist), int(grid))
+    return tidx, tdist
 
 
 def normalized_undistort(cam, kps):
@@ -285,3 +302,15 @@ def stereo_frames(left, right, nthreads, nfeatures=2000, scale_factor=1.2, nleve
     m = lib().orc_stereo_frames(_p(left), _p(right), count, w, h, nthreads, nfeatures, scale_factor,
                                 nlevels, ini_th, min_th, C.byref(tot))
     return int(m), int(tot.value)
+
+
+def stereo_sequence(left, right, nthreads, cam, baseline, radius=50.0, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20,
+                    min_th=7):
+    """CPU baseline of the sequence workload -> (stereo matches, keypoints, tracked keypoints)."""
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    count, h, w = left.shape
+    tot, trk = C.c_int64(), C.c_int64()
+    m = lib().orc_stereo_sequence(_p(left), _p(right), count, w, h, nthreads, nfeatures, scale_factor, nlevels, ini_th, min_th,
+                                  C.byref(cam), baseline, radius, C.byref(tot), C.byref(trk))
+    return int(m), int(tot.value), int(trk.value)

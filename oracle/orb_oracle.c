@@ -694,6 +694,71 @@ void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_
     }
 }
 
+/* The same ProjectionMatch with the candidate loop restricted by a 32-px bucket grid over the frame's keypoints: the
+ * CPU-baseline stand-in for the reference's per-frame FLANN kd-tree (src/frame.cpp:59-68,170-178), so that the timed
+ * CPU path is not charged an O(n m) scan the reference does not do.  Same candidate set (d^2 < r^2), hence the same
+ * accepted matches for ratio <= 1 (a tie for the best distance fails the ratio test whatever the visiting order,
+ * SURVEY §8a); tests/test_oracle_matchers.py checks it against orc_projection_match. */
+void orc_projection_match_grid(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                               const double rt[12], const orc_camera *cam, const orc_keypoint *kps,
+                               const uint8_t *kp_desc, int m, double radius, double ratio,
+                               int *kp_to_query, int *kp_dist) {
+    for (int j = 0; j < m; j++) { kp_to_query[j] = -1; kp_dist[j] = -1; }
+    const int gw = ((cam->width > 1 ? cam->width : 1) >> 5) + 1, gh = ((cam->height > 1 ? cam->height : 1) >> 5) + 1;
+    int *start = (int *)calloc((size_t)gw * gh + 1, sizeof(int)), *fill = (int *)calloc((size_t)gw * gh, sizeof(int));
+    int *order = (int *)malloc(sizeof(int) * (m > 0 ? m : 1)), *cell = (int *)malloc(sizeof(int) * (m > 0 ? m : 1));
+    for (int j = 0; j < m; j++) {
+        int cx = (int)floorf(kps[j].x) >> 5, cy = (int)floorf(kps[j].y) >> 5;
+        cx = cx < 0 ? 0 : cx >= gw ? gw - 1 : cx;
+        cy = cy < 0 ? 0 : cy >= gh ? gh - 1 : cy;
+        cell[j] = cy * gw + cx;
+        start[cell[j] + 1]++;
+    }
+    for (int c = 0; c < gw * gh; c++) start[c + 1] += start[c];
+    for (int j = 0; j < m; j++) order[start[cell[j]] + fill[cell[j]]++] = j;
+    const double r2max = radius * radius;
+    for (int i = 0; i < n; i++) {
+        if (skip && skip[i]) continue;
+        const double X = xw[3 * i], Y = xw[3 * i + 1], Z = xw[3 * i + 2];
+        double xc = ((rt[0] * X + rt[1] * Y) + rt[2] * Z) + rt[3];
+        double yc = ((rt[4] * X + rt[5] * Y) + rt[6] * Z) + rt[7];
+        double zc = ((rt[8] * X + rt[9] * Y) + rt[10] * Z) + rt[11];
+        if (zc < 0.) continue;
+        double x = xc / zc, y = yc / zc;
+        double r2 = x * x + y * y, r4 = r2 * r2;
+        double a1 = 2. * x * y, a2 = r2 + 2. * x * x, a3 = r2 + 2. * y * y;
+        double cdist = 1. + cam->d[0] * r2 + cam->d[1] * r4;
+        double xd = x * cdist + cam->d[2] * a1 + cam->d[3] * a2;
+        double yd = y * cdist + cam->d[2] * a3 + cam->d[3] * a1;
+        double u = cam->fx * xd + cam->cx, v = cam->fy * yd + cam->cy;
+        if (u < 0. || v < 0. || u > cam->width || v > cam->height) continue;
+        if (!(u == u) || !(v == v)) continue;
+        int cx0 = (int)floor(u - radius) >> 5, cx1 = (int)floor(u + radius) >> 5;
+        int cy0 = (int)floor(v - radius) >> 5, cy1 = (int)floor(v + radius) >> 5;
+        cx0 = cx0 < 0 ? 0 : cx0 >= gw ? gw - 1 : cx0; cx1 = cx1 < 0 ? 0 : cx1 >= gw ? gw - 1 : cx1;
+        cy0 = cy0 < 0 ? 0 : cy0 >= gh ? gh - 1 : cy0; cy1 = cy1 < 0 ? 0 : cy1 >= gh ? gh - 1 : cy1;
+        double dist0 = 999999999., dist1 = dist0;
+        int champ0 = -1;
+        for (int cy = cy0; cy <= cy1; cy++)
+            for (int t = start[cy * gw + cx0]; t < start[cy * gw + cx1 + 1]; t++) {
+                const int j = order[t];
+                double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
+                double d2 = ddx * ddx + ddy * ddy;
+                if (!(d2 < r2max)) continue;
+                double d = orc_hamming256(mp_desc + (size_t)32 * i, kp_desc + (size_t)32 * j);
+                if (d < dist0) { dist1 = dist0; dist0 = d; champ0 = j; }
+                else if (d < dist1) { dist1 = d; }
+            }
+        if (champ0 < 0) continue;
+        if (dist0 < dist1 * ratio) {
+            if (kp_to_query[champ0] >= 0 && (double)kp_dist[champ0] < dist0) continue;
+            kp_to_query[champ0] = i;
+            kp_dist[champ0] = (int)dist0;
+        }
+    }
+    free(start); free(fill); free(order); free(cell);
+}
+
 /* ---- Frame glue -------------------------------------------------------------
  * Camera::NormalizedUndistort src/camera.cpp:95-109 (called per keypoint by Frame::Frame, src/frame.cpp:50-56):
  * 5 fixed-point iterations x += (x_n - Distort(D, x)), Distort as src/camera.cpp:50-68.  Doubles, no contraction. */
@@ -833,20 +898,47 @@ void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64
     }
 }
 
+/* ---- Tracking step between consecutive stereo frames: the previous frame's keypoints that have a stereo
+ * correspondence become map points through StereoFrame::GetDepth (src/frame.cpp:391-409, normalised keypoints of
+ * Camera::NormalizedUndistort, src/camera.cpp:95-109), in keypoint order, and ProjectionMatch (src/matcher.cpp:134-209)
+ * with Tcw = rt matches them against the current frame's keypoints.  track_idx[j] = previous-frame keypoint matched to
+ * keypoint j, or -1.  Points with dx < 0 (the reference throws) are skipped. */
+void orc_track_pair(const orc_camera *cam, double baseline, const double rt[12], double radius, double ratio,
+                    const orc_keypoint *kl_prev, const uint8_t *dl_prev, int nl_prev, const orc_keypoint *kr_prev,
+                    const int *sidx_prev, const orc_keypoint *kps, const uint8_t *desc, int n, int *track_idx,
+                    int *track_dist, int use_grid) {
+    const int np = nl_prev > 0 ? nl_prev : 1;
+    double *nrm = (double *)malloc(sizeof(double) * 2 * np), *xc = (double *)malloc(sizeof(double) * 3 * np);
+    uint8_t *valid = (uint8_t *)malloc(np);
+    orc_normalized_undistort(cam, kl_prev, nl_prev, nrm);
+    orc_stereo_depth(cam, baseline, kl_prev, nrm, nl_prev, kr_prev, sidx_prev, xc, valid);
+    for (int i = 0; i < nl_prev; i++) valid[i] = valid[i] != 1; /* -> skip mask */
+    (use_grid ? orc_projection_match_grid : orc_projection_match)(xc, dl_prev, valid, nl_prev, rt, cam, kps, desc, n, radius, ratio,
+                                                                  track_idx, track_dist);
+    free(nrm); free(xc); free(valid);
+}
+
 /* ---- CPU baseline driver ---------------------------------------------------------- */
 typedef struct {
     const uint8_t *left, *right;
     int count, w, h, nfeatures, nlevels, ini_th, min_th;
     float scale_factor;
     int next;
-    int64_t matches, kps;
+    int64_t matches, kps, tracked;
     pthread_mutex_t mu;
+    /* sequence mode: per-frame results kept for the tracking phase */
+    int cap;
+    orc_keypoint *kl_all, *kr_all;
+    uint8_t *dl_all;
+    int *idx_all, *nl_all;
+    const orc_camera *cam;
+    double baseline, radius;
 } job_t;
 
 static void *worker(void *arg) {
     job_t *jb = (job_t *)arg;
     orc_extractor *ex = orc_extractor_create(jb->nfeatures, jb->scale_factor, jb->nlevels, jb->ini_th, jb->min_th);
-    int cap = jb->nfeatures + 4 * jb->nlevels + 64;
+    int cap = jb->kl_all ? jb->cap : jb->nfeatures + 4 * jb->nlevels + 64;
     orc_keypoint *kl = (orc_keypoint *)malloc(sizeof(orc_keypoint) * cap), *kr = (orc_keypoint *)malloc(sizeof(orc_keypoint) * cap);
     uint8_t *dl = (uint8_t *)malloc((size_t)32 * cap), *dr = (uint8_t *)malloc((size_t)32 * cap);
     int *idx = (int *)malloc(sizeof(int) * cap);
@@ -863,6 +955,14 @@ static void *worker(void *arg) {
         orc_stereo_match(kl, dl, nl, kr, dr, nr, 3., 100., 0.5, idx, NULL);
         for (int i = 0; i < nl; i++) matches += idx[i] >= 0;
         kps += nl + nr;
+        if (jb->kl_all) {
+            const size_t o = (size_t)f * jb->cap;
+            memcpy(jb->kl_all + o, kl, sizeof(orc_keypoint) * nl);
+            memcpy(jb->kr_all + o, kr, sizeof(orc_keypoint) * nr);
+            memcpy(jb->dl_all + o * 32, dl, (size_t)32 * nl);
+            memcpy(jb->idx_all + o, idx, sizeof(int) * nl);
+            jb->nl_all[f] = nl;
+        }
     }
     pthread_mutex_lock(&jb->mu);
     jb->matches += matches;
@@ -889,5 +989,62 @@ int64_t orc_stereo_frames(const uint8_t *left, const uint8_t *right, int count, 
     for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
     pthread_mutex_destroy(&jb.mu);
     if (total_kps) *total_kps = jb.kps;
+    return jb.matches;
+}
+
+static void *track_worker(void *arg) {
+    job_t *jb = (job_t *)arg;
+    static const double ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    int *tidx = (int *)malloc(sizeof(int) * jb->cap), *tdist = (int *)malloc(sizeof(int) * jb->cap);
+    int64_t tracked = 0;
+    for (;;) {
+        pthread_mutex_lock(&jb->mu);
+        int f = jb->next++;
+        pthread_mutex_unlock(&jb->mu);
+        if (f >= jb->count) break;
+        if (f == 0) continue;
+        const size_t o = (size_t)f * jb->cap, q = (size_t)(f - 1) * jb->cap;
+        orc_track_pair(jb->cam, jb->baseline, ident, jb->radius, 0.5, jb->kl_all + q, jb->dl_all + q * 32, jb->nl_all[f - 1],
+                       jb->kr_all + q, jb->idx_all + q, jb->kl_all + o, jb->dl_all + o * 32, jb->nl_all[f], tidx, tdist, 1);
+        for (int j = 0; j < jb->nl_all[f]; j++) tracked += tidx[j] >= 0;
+    }
+    pthread_mutex_lock(&jb->mu);
+    jb->tracked += tracked;
+    pthread_mutex_unlock(&jb->mu);
+    free(tidx); free(tdist);
+    return NULL;
+}
+
+/* CPU baseline helper for the sequence workload: orc_stereo_frames, then the tracking step of every consecutive pair
+ * (identity motion prior, bucket-grid candidate search), both phases over `nthreads` threads. */
+int64_t orc_stereo_sequence(const uint8_t *left, const uint8_t *right, int count, int w, int h, int nthreads, int nfeatures,
+                            float scale_factor, int nlevels, int ini_th, int min_th, const orc_camera *cam, double baseline,
+                            double radius, int64_t *total_kps, int64_t *total_tracked) {
+    job_t jb;
+    memset(&jb, 0, sizeof(jb));
+    jb.left = left; jb.right = right; jb.count = count; jb.w = w; jb.h = h;
+    jb.nfeatures = nfeatures; jb.scale_factor = scale_factor; jb.nlevels = nlevels;
+    jb.ini_th = ini_th; jb.min_th = min_th;
+    jb.cap = nfeatures + 4 * nlevels + 64;
+    jb.cam = cam; jb.baseline = baseline; jb.radius = radius;
+    const size_t tot = (size_t)count * jb.cap;
+    jb.kl_all = (orc_keypoint *)malloc(sizeof(orc_keypoint) * tot);
+    jb.kr_all = (orc_keypoint *)malloc(sizeof(orc_keypoint) * tot);
+    jb.dl_all = (uint8_t *)malloc(32 * tot);
+    jb.idx_all = (int *)malloc(sizeof(int) * tot);
+    jb.nl_all = (int *)calloc(count, sizeof(int));
+    pthread_mutex_init(&jb.mu, NULL);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    pthread_t th[256];
+    for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, worker, &jb);
+    for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+    jb.next = 0;
+    for (int i = 0; i < nthreads; i++) pthread_create(&th[i], NULL, track_worker, &jb);
+    for (int i = 0; i < nthreads; i++) pthread_join(th[i], NULL);
+    pthread_mutex_destroy(&jb.mu);
+    free(jb.kl_all); free(jb.kr_all); free(jb.dl_all); free(jb.idx_all); free(jb.nl_all);
+    if (total_kps) *total_kps = jb.kps;
+    if (total_tracked) *total_tracked = jb.tracked;
     return jb.matches;
 }

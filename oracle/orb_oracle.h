@@ -76,6 +76,11 @@ void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_
                           const double rt[12], const orc_camera *cam,
                           const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
                           double ratio, int *kp_to_query, int *kp_dist);
+/* the same with a 32-px bucket grid over the keypoints as candidate accelerator (CPU-baseline stand-in for FLANN) */
+void orc_projection_match_grid(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                               const double rt[12], const orc_camera *cam,
+                               const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                               double ratio, int *kp_to_query, int *kp_dist);
 /* out[q*4] = {idx0, dist0, idx1, dist1}; lexicographic (dist, idx) top-2 */
 void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base,
               int32_t *out);
@@ -101,6 +106,17 @@ void orc_vocab_transform(int n_nodes, const int32_t *parent, const uint8_t *is_l
 int64_t orc_stereo_frames(const uint8_t *left, const uint8_t *right, int count, int w, int h,
                           int nthreads, int nfeatures, float scale_factor, int nlevels,
                           int ini_th, int min_th, int64_t *total_kps);
+
+/* tracking step between consecutive stereo frames (src/frame.cpp:391-409 + src/matcher.cpp:134-209): GetDepth of the
+ * previous frame's stereo keypoints, ProjectionMatch into the current frame; track_idx[j] = previous keypoint or -1 */
+void orc_track_pair(const orc_camera *cam, double baseline, const double rt[12], double radius, double ratio,
+                    const orc_keypoint *kl_prev, const uint8_t *dl_prev, int nl_prev, const orc_keypoint *kr_prev,
+                    const int *sidx_prev, const orc_keypoint *kps, const uint8_t *desc, int n, int *track_idx,
+                    int *track_dist, int use_grid);
+/* CPU baseline helper for the sequence workload: orc_stereo_frames + orc_track_pair over consecutive frames */
+int64_t orc_stereo_sequence(const uint8_t *left, const uint8_t *right, int count, int w, int h, int nthreads, int nfeatures,
+                            float scale_factor, int nlevels, int ini_th, int min_th, const orc_camera *cam, double baseline,
+                            double radius, int64_t *total_kps, int64_t *total_tracked);
 
 #ifdef __cplusplus
 }

@@ -51,6 +51,21 @@ class Camera(C.Structure):
         return c
 
 
+class TrackParams(C.Structure):
+    """sfe_track_params: camera, stereo baseline, motion prior Tcw (3x4), ProjectionMatch radius and ratio."""
+    _fields_ = [("cam", Camera), ("baseline", C.c_double), ("rt", C.c_double * 12), ("radius", C.c_double),
+                ("best12_threshold", C.c_double)]
+
+    @staticmethod
+    def make(cam, baseline, Tcw=None, radius=50.0, best12=0.5):
+        t = TrackParams()
+        t.cam, t.baseline, t.radius, t.best12_threshold = cam, baseline, radius, best12
+        rt = np.eye(4)[:3, :4] if Tcw is None else np.asarray(Tcw, np.float64)[:3, :4]
+        for i, v in enumerate(np.ascontiguousarray(rt).reshape(12)):
+            t.rt[i] = v
+        return t
+
+
 # every symbol include/sfe.h declares: name -> (restype, argtypes)
 _vp, _i, _sz, _d, _i64 = C.c_void_p, C.c_int, C.c_size_t, C.c_double, C.c_int64
 _pp = C.POINTER(C.c_void_p)
@@ -80,6 +95,8 @@ SIGNATURES = {
     "sfe_extract_batch_dev": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sfe_stereo_frames": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
     "sfe_stereo_frames_dev": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
+    "sfe_stereo_sequence": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams), C.POINTER(TrackParams)] + [_vp] * 10 + [_i]),
+    "sfe_stereo_sequence_dev": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams), C.POINTER(TrackParams)] + [_vp] * 10 + [_i]),
     "sfe_image_pitch": (_i, [_i]),
     "sfe_extractor_set_async": (_i, [_vp, _i]),
     "sfe_extractor_wait": (_i, [_vp]),
@@ -361,11 +378,42 @@ class ORBextractor:
         self._wh = (w, h)
         return out
 
-    def alloc_stereo_out(self, frames, pinned=False):
+    def stereo_sequence(self, left, right, track_params, out=None, stereo_params=None):
+        """Tracking front end of a stereo sequence: stereo_frames + per frame f >= 1 the ProjectionMatch of frame f-1's
+        stereo-triangulated keypoints into frame f (sfe_stereo_sequence).  out["track_idx"][f, j] = keypoint of frame
+        f-1 matched to keypoint j of frame f, or -1."""
+        left = np.ascontiguousarray(left, np.uint8)
+        right = np.ascontiguousarray(right, np.uint8)
+        f, h, w = left.shape
+        assert right.shape == left.shape
+        if out is None:
+            out = self.alloc_stereo_out(f, track=True)
+        sp = C.byref(stereo_params) if stereo_params is not None else None
+        _check(lib().sfe_stereo_sequence(self.h, _p(left), _p(right), w * h, f, w, h, w, sp, C.byref(track_params),
+                                         _p(out["kps_l"]), _p(out["desc_l"]), _p(out["n_l"]), _p(out["kps_r"]),
+                                         _p(out["desc_r"]), _p(out["n_r"]), _p(out["stereo_idx"]), _p(out["stereo_dist"]),
+                                         _p(out["track_idx"]), _p(out["track_dist"]), self.cap))
+        self._wh = (w, h)
+        return out
+
+    def stereo_sequence_dev(self, left_ptr, right_ptr, frames, w, h, ptrs, track_params, stereo_params=None, pitch=None):
+        """stereo_frames_dev + tracking; ptrs additionally holds "track_idx" / "track_dist" (frames x cap int32)."""
+        sp = C.byref(stereo_params) if stereo_params is not None else None
+        pitch = pitch or w
+        _check(lib().sfe_stereo_sequence_dev(self.h, _p(left_ptr), _p(right_ptr), pitch * h, frames, w, h, pitch, sp,
+                                             C.byref(track_params), _p(ptrs["kps_l"]), _p(ptrs["desc_l"]), _p(ptrs["n_l"]),
+                                             _p(ptrs["kps_r"]), _p(ptrs["desc_r"]), _p(ptrs["n_r"]), _p(ptrs["stereo_idx"]),
+                                             _p(ptrs["stereo_dist"]), _p(ptrs["track_idx"]), _p(ptrs["track_dist"]), self.cap))
+        self._wh = (w, h)
+
+    def alloc_stereo_out(self, frames, pinned=False, track=False):
         spec = {"kps_l": ((frames, self.cap), KP_DTYPE), "desc_l": ((frames, self.cap, 32), np.uint8),
                 "n_l": ((frames,), np.int32), "kps_r": ((frames, self.cap), KP_DTYPE),
                 "desc_r": ((frames, self.cap, 32), np.uint8), "n_r": ((frames,), np.int32),
                 "stereo_idx": ((frames, self.cap), np.int32), "stereo_dist": ((frames, self.cap), np.int32)}
+        if track:
+            spec["track_idx"] = ((frames, self.cap), np.int32)
+            spec["track_dist"] = ((frames, self.cap), np.int32)
         if not pinned:
             return {k: np.zeros(s, d) for k, (s, d) in spec.items()}
         self._pinned_out = {k: PinnedArray(s, d) for k, (s, d) in spec.items()}
@@ -394,7 +442,7 @@ class ORBextractor:
         _check(lib().sfe_extractor_launches(self.h, C.byref(n)))
         return n.value
 
-    STAGES = ("pyramid", "fast_cells", "quadtree", "blur", "orient_describe", "stereo_match")
+    STAGES = ("pyramid", "fast_cells", "quadtree", "blur", "orient_describe", "stereo_match", "track")
 
     def set_profiling(self, enable=True):
         _check(lib().sfe_extractor_set_profiling(self.h, int(enable)))

@@ -1029,7 +1029,7 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
 // =============================================================================================
 using namespace sfe;
 
-enum { kStagePyramid, kStageFast, kStageQuadtree, kStageBlur, kStageDescribe, kStageStereo, kNumStages };
+enum { kStagePyramid, kStageFast, kStageQuadtree, kStageBlur, kStageDescribe, kStageStereo, kStageTrack, kNumStages };
 constexpr int kOctreeSmemCand = 3072;
 constexpr int kComputeStreams = 4;
 constexpr int kMaxChunks = 16;  // sub-batches one pipelined host call is cut into
@@ -1082,13 +1082,14 @@ struct sfe_extractor {
     DevBuf<TilePlan> d_tiles;
     DevBuf<uint2> d_xtab, d_ytab;
     DevBuf<sfe_keypoint> d_kps;
-    DevBuf<int32_t> d_nout, d_sidx, d_sdist;
+    DevBuf<int32_t> d_nout, d_sidx, d_sdist, d_tidx, d_tdist;
     std::vector<int> h_flags;
     int64_t launches = 0;
     // optional per-stage CUDA-event timing on the handle's own stream (bench roofline)
     bool profiling = false;
     cudaEvent_t prof_ev[kNumStages + 1] = {};
-    bool prof_pending = false, prof_has_stereo = false;
+    bool prof_pending = false, prof_has_stereo = false, prof_has_track = false;
+    TrackScratch track;  // sfe_stereo_sequence: per-frame bucket grids + keys
     double stage_ms[kNumStages] = {};
     int64_t stage_calls = 0;
     // what the last call processed (stage taps)
@@ -1501,7 +1502,7 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     orient_describe_kernel<<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O);
     prof_mark(ex, 5);
     ex->prof_pending = ex->profiling;
-    ex->prof_has_stereo = false;
+    ex->prof_has_stereo = ex->prof_has_track = false;
     ex->launches++;
     SFE_CUDA(cudaGetLastError());
     return SFE_OK;
@@ -1512,7 +1513,7 @@ static int check_flags(sfe_extractor *ex, cudaStream_t st, int count) {
     SFE_CUDA(cudaMemcpyAsync(ex->h_flags.data(), ex->last.flags, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaStreamSynchronize(st));
     if (ex->prof_pending) {
-        const int ns = ex->prof_has_stereo ? kNumStages : kNumStages - 1;
+        const int ns = ex->prof_has_track ? kNumStages : ex->prof_has_stereo ? kNumStages - 1 : kNumStages - 2;
         for (int i = 0; i < ns; i++) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ex->prof_ev[i], ex->prof_ev[i + 1]) == cudaSuccess) ex->stage_ms[i] += ms;
@@ -1583,7 +1584,8 @@ static const sfe_stereo_params k_default_stereo = {3.0, 100.0, 0.5};  // src/mat
 static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
                           int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l, uint8_t *desc_l, int32_t *n_l,
                           sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx, int32_t *stereo_dist,
-                          int cap) {
+                          int cap, const sfe_track_params *tp = nullptr, int32_t *track_idx = nullptr,
+                          int32_t *track_dist = nullptr) {
     const bool stereo = right != nullptr;
     const int images = stereo ? 2 * frames : frames;
     int rc = prepare(ex, images, w, h, stride, cap);
@@ -1665,6 +1667,20 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
         for (auto &e : ex->extra) cudaStreamSynchronize(e);
         cudaStreamSynchronize(sout);
         return rc;
+    }
+    if (tp && stereo) {
+        // tracking needs consecutive frames, which may sit in different sub-batches: it runs once, behind all of them
+        // (sout already waits for every sub-batch), on the D2H stream's tail
+        SFE_CUDA(ex->d_tidx.ensure((size_t)ex->max_images * cap));
+        SFE_CUDA(ex->d_tdist.ensure((size_t)ex->max_images * cap));
+        if ((rc = launch_track_frames(sout, ex->device, ex->track, frames, cap, kl, dl, nl, kr, ex->d_sidx.p, *tp, ex->d_tidx.p,
+                                      ex->d_tdist.p)) != SFE_OK) {
+            cudaStreamSynchronize(sout);
+            return rc;
+        }
+        ex->launches += 3;
+        SFE_CUDA(cudaMemcpyAsync(track_idx, ex->d_tidx.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
+        if (track_dist) SFE_CUDA(cudaMemcpyAsync(track_dist, ex->d_tdist.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
     }
     SFE_CUDA(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
     if (stereo) SFE_CUDA(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
@@ -1749,7 +1765,8 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_l0.release(); ex->d_octree_scratch.release(); ex->d_desc.release();
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release();
     ex->d_tiles.release(); ex->d_segs.release(); ex->d_xtab.release(); ex->d_ytab.release();
-    ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release();
+    ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release(); ex->d_tidx.release(); ex->d_tdist.release();
+    ex->track.cell_start.release(); ex->track.order.release(); ex->track.sxy.release(); ex->track.sdesc.release(); ex->track.best.release();
     for (int i = 0; i <= kNumStages; i++)
         if (ex->prof_ev[i]) cudaEventDestroy(ex->prof_ev[i]);
     for (int i = 0; i < kMaxChunks; i++) {
@@ -1842,10 +1859,11 @@ int sfe_extract(sfe_extractor *ex, const uint8_t *image, int w, int h, int strid
     return rc;
 }
 
-int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
-                          int frames, int w, int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l_dev,
-                          uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev, uint8_t *desc_r_dev,
-                          int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev, int cap) {
+static int stereo_frames_dev_impl(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
+                                  int frames, int w, int h, int stride, const sfe_stereo_params *sp, const sfe_track_params *tp,
+                                  sfe_keypoint *kps_l_dev, uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev,
+                                  uint8_t *desc_r_dev, int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
+                                  int32_t *track_idx_dev, int32_t *track_dist_dev, int cap) {
     SFE_REQUIRE(ex && left_dev && right_dev && kps_l_dev && desc_l_dev && n_l_dev && kps_r_dev && desc_r_dev && n_r_dev &&
                     stereo_idx_dev,
                 SFE_ERR_BAD_ARG, "null argument");
@@ -1865,9 +1883,43 @@ int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint
     ex->prof_has_stereo = true;
     ex->launches++;
     SFE_CUDA(cudaGetLastError());
+    if (tp) {
+        if ((rc = launch_track_frames(ex->stream, ex->device, ex->track, frames, cap, kps_l_dev, desc_l_dev, n_l_dev, kps_r_dev,
+                                      stereo_idx_dev, *tp, track_idx_dev, track_dist_dev)) != SFE_OK)
+            return rc;
+        prof_mark(ex, 7);
+        ex->prof_has_track = true;
+        ex->launches += 3;
+    }
     ex->last = S;
     ex->last_count = 2 * frames;
     return finish_dev(ex, 2 * frames);
+}
+
+int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
+                          int frames, int w, int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l_dev,
+                          uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev, uint8_t *desc_r_dev,
+                          int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev, int cap) {
+    return stereo_frames_dev_impl(ex, left_dev, right_dev, image_stride, frames, w, h, stride, sp, nullptr, kps_l_dev, desc_l_dev,
+                                  n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, stereo_idx_dev, stereo_dist_dev, nullptr, nullptr, cap);
+}
+
+static int check_track_params(const sfe_track_params *tp, const int32_t *track_idx) {
+    SFE_REQUIRE(tp && track_idx, SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(tp->cam.width >= 1 && tp->cam.height >= 1 && tp->cam.fx != 0. && tp->cam.fy != 0., SFE_ERR_BAD_ARG, "bad camera");
+    SFE_REQUIRE(tp->radius >= 0. && tp->radius == tp->radius, SFE_ERR_BAD_ARG, "bad radius");
+    return SFE_OK;
+}
+
+int sfe_stereo_sequence_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride, int frames,
+                            int w, int h, int stride, const sfe_stereo_params *sp, const sfe_track_params *tp,
+                            sfe_keypoint *kps_l_dev, uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev,
+                            uint8_t *desc_r_dev, int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
+                            int32_t *track_idx_dev, int32_t *track_dist_dev, int cap) {
+    if (int rc = check_track_params(tp, track_idx_dev)) return rc;
+    return stereo_frames_dev_impl(ex, left_dev, right_dev, image_stride, frames, w, h, stride, sp, tp, kps_l_dev, desc_l_dev,
+                                  n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, stereo_idx_dev, stereo_dist_dev, track_idx_dev,
+                                  track_dist_dev, cap);
 }
 
 int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
@@ -1880,6 +1932,19 @@ int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *rig
     DeviceGuard g(ex->device);
     return run_host_batch(ex, left, right, image_stride, frames, w, h, stride, sp ? sp : &k_default_stereo, kps_l, desc_l, n_l,
                           kps_r, desc_r, n_r, stereo_idx, stereo_dist, cap);
+}
+
+int sfe_stereo_sequence(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
+                        int h, int stride, const sfe_stereo_params *sp, const sfe_track_params *tp, sfe_keypoint *kps_l,
+                        uint8_t *desc_l, int32_t *n_l, sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx,
+                        int32_t *stereo_dist, int32_t *track_idx, int32_t *track_dist, int cap) {
+    SFE_REQUIRE(ex && left && right && kps_l && desc_l && n_l && kps_r && desc_r && n_r && stereo_idx, SFE_ERR_BAD_ARG,
+                "null argument");
+    if (int rc = check_track_params(tp, track_idx)) return rc;
+    SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
+    DeviceGuard g(ex->device);
+    return run_host_batch(ex, left, right, image_stride, frames, w, h, stride, sp ? sp : &k_default_stereo, kps_l, desc_l, n_l,
+                          kps_r, desc_r, n_r, stereo_idx, stereo_dist, cap, tp, track_idx, track_dist);
 }
 
 int sfe_image_pitch(int w) { return w > 0 ? (int)align_up((size_t)w, 16) : 0; }

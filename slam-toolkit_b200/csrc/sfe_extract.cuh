@@ -128,4 +128,16 @@ void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoin
                          const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
                          double ratio, int32_t *out_idx, int32_t *out_dist);
 
+// sequence tracking launch (sfe_match.cu), used by sfe_stereo_sequence on the extractor's stream: per-frame bucket grids,
+// GetDepth + ProjectionMatch of frame f-1's stereo points into frame f, decode.  3 launches.
+struct TrackScratch {
+    DevBuf<int> cell_start, order;
+    DevBuf<double2> sxy;
+    DevBuf<uint4> sdesc;
+    DevBuf<unsigned long long> best;
+};
+int launch_track_frames(cudaStream_t st, int device, TrackScratch &T, int frames, int cap, const sfe_keypoint *kl, const uint8_t *dl,
+                        const int32_t *nl, const sfe_keypoint *kr, const int32_t *sidx, const sfe_track_params &tp,
+                        int32_t *track_idx, int32_t *track_dist);
+
 }  // namespace sfe

@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <mutex>
+
 #include "sfe_extract.cuh"
 
 namespace sfe {
@@ -221,17 +223,11 @@ struct ProjParams {
     double radius, ratio;
 };
 
-__global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjParams P, int n, uint32_t idx_base,
-                                                               const double *__restrict__ xw,
-                                                               const uint8_t *__restrict__ mp_desc,
-                                                               const uint8_t *__restrict__ skip,
-                                                               const sfe_keypoint *__restrict__ kps,
-                                                               const uint8_t *__restrict__ kp_desc,
-                                                               unsigned long long *__restrict__ best) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    if (skip && skip[i]) return;  // curr_frame->GetIndex(mp) >= 0, :144
-    const double X = xw[3 * (size_t)i], Y = xw[3 * (size_t)i + 1], Z = xw[3 * (size_t)i + 2];
+// One map point against the frame behind G: Xc = Tcw Xw, Camera::Project, radius search over the bucket grid,
+// best / second-best Hamming, ratio test, then the conflict rule as an atomicMin on the winning keypoint's key.
+// `query` is the point's position in the caller's order (the later query wins a distance tie, :197-204).
+__device__ __forceinline__ void project_and_match(const KpGrid &G, const ProjParams &P, double X, double Y, double Z,
+                                                  const uint32_t a[8], uint32_t query, unsigned long long *__restrict__ best) {
     // Xc = Tcw * Xw, evaluated left to right without contraction (:150)
     const double xc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[0], X), __dmul_rn(P.rt[1], Y)), __dmul_rn(P.rt[2], Z)), P.rt[3]);
     const double yc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[4], X), __dmul_rn(P.rt[5], Y)), __dmul_rn(P.rt[6], Z)), P.rt[7]);
@@ -249,8 +245,6 @@ __global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjPar
     const double u = __dadd_rn(__dmul_rn(P.cam.fx, xd), P.cam.cx), v = __dadd_rn(__dmul_rn(P.cam.fy, yd), P.cam.cy);
     if (u < 0. || v < 0. || u > (double)P.cam.width || v > (double)P.cam.height) return;  // IsInImage, :26-36
     if (!(u == u) || !(v == v)) return;  // NaN: the radius search finds nothing
-    uint32_t a[8];
-    load_desc(mp_desc + (size_t)i * 32, a);
     const double r2max = __dmul_rn(P.radius, P.radius);
     const int cy0 = min(max((int)floor(v - P.radius) >> kGridShift, 0), G.gh - 1);
     const int cy1 = min(max((int)floor(v + P.radius) >> kGridShift, 0), G.gh - 1);
@@ -280,9 +274,22 @@ __global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjPar
     if (d0 < d1 * P.ratio) {
         // :197-204 processed sequentially keeps the smaller distance and lets the LATER query win a
         // tie: that is the minimum of (dist, -query) over all accepted queries of a keypoint
-        const unsigned long long key = (unsigned long long)(k0 >> 16) << 32 | (0xFFFFFFFFu - (idx_base + (uint32_t)i));
+        const unsigned long long key = (unsigned long long)(k0 >> 16) << 32 | (0xFFFFFFFFu - query);
         atomicMin(&best[k0 & 0xFFFF], key);
     }
+}
+
+__global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjParams P, int n, uint32_t idx_base,
+                                                               const double *__restrict__ xw,
+                                                               const uint8_t *__restrict__ mp_desc,
+                                                               const uint8_t *__restrict__ skip,
+                                                               unsigned long long *__restrict__ best) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (skip && skip[i]) return;  // curr_frame->GetIndex(mp) >= 0, :144
+    uint32_t a[8];
+    load_desc(mp_desc + (size_t)i * 32, a);
+    project_and_match(G, P, xw[3 * (size_t)i], xw[3 * (size_t)i + 1], xw[3 * (size_t)i + 2], a, idx_base + (uint32_t)i, best);
 }
 
 // keys of `shards` map-point shards (shards x m) -> per keypoint the minimum (dist, -query) key, decoded
@@ -468,10 +475,8 @@ __global__ void __launch_bounds__(128) knn2_merge_kernel(const unsigned long lon
 // StereoFrame::GetDepth (:391-409), on the device, for a frame whose keypoints / descriptors stay resident.
 // ---------------------------------------------------------------------------------------------
 // Camera::NormalizedUndistort, src/camera.cpp:95-109: 5 iterations of x += x_n - Distort(D, x); one thread per keypoint
-__global__ void normalized_undistort_kernel(sfe_camera cam, const sfe_keypoint *__restrict__ kps, int n, double2 *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double nx = __ddiv_rn(__dsub_rn((double)kps[i].x, cam.cx), cam.fx), ny = __ddiv_rn(__dsub_rn((double)kps[i].y, cam.cy), cam.fy);
+__device__ __forceinline__ double2 normalized_undistort(const sfe_camera &cam, float px, float py) {
+    const double nx = __ddiv_rn(__dsub_rn((double)px, cam.cx), cam.fx), ny = __ddiv_rn(__dsub_rn((double)py, cam.cy), cam.fy);
     double x = nx, y = ny;
 #pragma unroll 1
     for (int it = 0; it < 5; it++) {
@@ -485,7 +490,12 @@ __global__ void normalized_undistort_kernel(sfe_camera cam, const sfe_keypoint *
         x = __dadd_rn(x, __dsub_rn(nx, xd));
         y = __dadd_rn(y, __dsub_rn(ny, yd));
     }
-    out[i] = make_double2(x, y);
+    return make_double2(x, y);
+}
+
+__global__ void normalized_undistort_kernel(sfe_camera cam, const sfe_keypoint *__restrict__ kps, int n, double2 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = normalized_undistort(cam, kps[i].x, kps[i].y);
 }
 
 // StereoFrame::GetDepth for every left keypoint: depth = fx * baseline / dx, dx = the FLOAT difference of the x's
@@ -510,6 +520,100 @@ __global__ void stereo_depth_kernel(double fx, double baseline, const sfe_keypoi
     }
     xc[3 * i] = X; xc[3 * i + 1] = Y; xc[3 * i + 2] = Z;
     valid[i] = ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sequence tracking over a resident stereo batch: what the reference does per frame between extract() and the pose
+// optimiser -- Frame::Frame's spatial index (src/frame.cpp:59-68), StereoFrame::GetDepth of the previous frame's
+// keypoints (:391-409) and ProjectionMatch of those points into the current frame (src/matcher.cpp:134-209) -- for
+// all consecutive pairs of a batch at once, straight from the extractor's cap-strided device outputs.
+// ---------------------------------------------------------------------------------------------
+struct TrackArrays {
+    int frames, cap, gw, gh;
+    const sfe_keypoint *kl, *kr;
+    const uint8_t *dl;
+    const int32_t *nl, *sidx;
+    int *cell_start;  // frames x (cells + 1)
+    int *order;       // frames x cap
+    double2 *sxy;     // frames x cap
+    uint4 *sdesc;     // frames x 2 cap
+};
+
+__device__ __forceinline__ KpGrid track_grid(const TrackArrays &A, int f) {
+    KpGrid G;
+    G.gw = A.gw; G.gh = A.gh;
+    G.m = min(A.nl[f], A.cap);
+    G.cell_start = A.cell_start + (size_t)f * (A.gw * A.gh + 1);
+    G.cell_fill = nullptr;
+    G.order = A.order + (size_t)f * A.cap;
+    G.sxy = A.sxy + (size_t)f * A.cap;
+    G.sdesc = A.sdesc + (size_t)f * 2 * A.cap;
+    return G;
+}
+
+// One CTA builds one frame's bucket grid: count and scan in shared memory (cells + 1 counters, then fill cursors)
+__global__ void __launch_bounds__(256) track_grids_kernel(TrackArrays A) {
+    extern __shared__ int tg_smem[];
+    const int f = blockIdx.x, tid = threadIdx.x, cells = A.gw * A.gh;
+    int *start = tg_smem, *fill = tg_smem + cells + 1;
+    __shared__ int chunk_sum[256];
+    const KpGrid G = track_grid(A, f);
+    const sfe_keypoint *kps = A.kl + (size_t)f * A.cap;
+    for (int c = tid; c <= cells; c += 256) start[c] = 0;
+    __syncthreads();
+    for (int j = tid; j < G.m; j += 256) atomicAdd(&start[grid_cell(G, kps[j].x, kps[j].y) + 1], 1);
+    __syncthreads();
+    // inclusive scan of start[0 .. cells]: a contiguous chunk per thread, then the chunk totals
+    const int per = (cells + 1 + 255) / 256, c0 = min(tid * per, cells + 1), c1 = min(c0 + per, cells + 1);
+    int acc = 0;
+    for (int c = c0; c < c1; c++) acc += start[c];
+    chunk_sum[tid] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < 256; i++) {
+            const int v = chunk_sum[i];
+            chunk_sum[i] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    acc = chunk_sum[tid];
+    for (int c = c0; c < c1; c++) {
+        acc += start[c];
+        start[c] = acc;
+        G.cell_start[c] = acc;
+    }
+    for (int c = tid; c < cells; c += 256) fill[c] = 0;
+    __syncthreads();
+    const uint8_t *desc = A.dl + (size_t)f * A.cap * 32;
+    for (int j = tid; j < G.m; j += 256) {
+        const float x = kps[j].x, y = kps[j].y;
+        const int c = grid_cell(G, x, y), t = start[c] + atomicAdd(&fill[c], 1);
+        G.order[t] = j;
+        G.sxy[t] = make_double2((double)x, (double)y);
+        const uint4 *d = (const uint4 *)(desc + (size_t)j * 32);
+        G.sdesc[2 * t] = __ldg(d);
+        G.sdesc[2 * t + 1] = __ldg(d + 1);
+    }
+}
+
+// thread = keypoint i of frame f - 1 (f = blockIdx.y + 1): GetDepth, then ProjectionMatch into frame f
+__global__ void __launch_bounds__(128) track_match_kernel(TrackArrays A, ProjParams P, double baseline,
+                                                          unsigned long long *__restrict__ best) {
+    const int f = blockIdx.y + 1, prev = f - 1, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(A.nl[prev], A.cap)) return;
+    const int j = A.sidx[(size_t)prev * A.cap + i];
+    if (j < 0) return;  // no stereo correspondence: no depth, no map point
+    const sfe_keypoint kp = A.kl[(size_t)prev * A.cap + i];
+    const double dx = (double)__fsub_rn(kp.x, A.kr[(size_t)prev * A.cap + j].x);  // :398, float difference
+    if (dx < 0.) return;  // the reference throws (:399-402); StereoMatch never lets this through
+    const double Z = __ddiv_rn(__dmul_rn(P.cam.fx, baseline), dx);
+    const double2 nrm = normalized_undistort(P.cam, kp.x, kp.y);
+    uint32_t a[8];
+    load_desc(A.dl + ((size_t)prev * A.cap + i) * 32, a);
+    const KpGrid G = track_grid(A, f);
+    project_and_match(G, P, __dmul_rn(nrm.x, Z), __dmul_rn(nrm.y, Z), Z, a, (uint32_t)i, best + (size_t)f * A.cap);
 }
 
 // Frame::SearchRadius / SearchNeareast over the bucket grid; one thread per query point.
@@ -606,6 +710,45 @@ __global__ void __launch_bounds__(256) vocab_transform_kernel(VocabDev V, const 
     }
 }
 
+int launch_track_frames(cudaStream_t st, int device, TrackScratch &T, int frames, int cap, const sfe_keypoint *kl, const uint8_t *dl,
+                        const int32_t *nl, const sfe_keypoint *kr, const int32_t *sidx, const sfe_track_params &tp,
+                        int32_t *track_idx, int32_t *track_dist) {
+    TrackArrays A{};
+    A.frames = frames; A.cap = cap;
+    A.gw = (std::max(tp.cam.width, 1) >> kGridShift) + 1;
+    A.gh = (std::max(tp.cam.height, 1) >> kGridShift) + 1;
+    const int cells = A.gw * A.gh;
+    const size_t smem = sizeof(int) * (2 * (size_t)cells + 1), fc = (size_t)frames * cap;
+    SFE_REQUIRE(cap < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per frame");
+    SFE_REQUIRE(smem <= 200 * 1024, SFE_ERR_UNSUPPORTED, "camera image too large for the per-frame bucket grid");
+    SFE_CUDA(T.cell_start.ensure((size_t)frames * (cells + 1)));
+    SFE_CUDA(T.order.ensure(fc)); SFE_CUDA(T.sxy.ensure(fc)); SFE_CUDA(T.sdesc.ensure(2 * fc)); SFE_CUDA(T.best.ensure(fc));
+    A.kl = kl; A.kr = kr; A.dl = dl; A.nl = nl; A.sidx = sidx;
+    A.cell_start = T.cell_start.p; A.order = T.order.p; A.sxy = T.sxy.p; A.sdesc = T.sdesc.p;
+    if (smem > 48 * 1024) {  // per-function opt-in limit: only ever raise it
+        static std::mutex mu;
+        static size_t granted[64] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        if (smem > granted[device & 63]) {
+            SFE_CUDA(cudaFuncSetAttribute(track_grids_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            granted[device & 63] = smem;
+        }
+    }
+    SFE_CUDA(cudaMemsetAsync(T.best.p, 0xFF, sizeof(unsigned long long) * fc, st));
+    track_grids_kernel<<<frames, 256, smem, st>>>(A);
+    if (frames > 1) {
+        ProjParams P;
+        memcpy(P.rt, tp.rt, sizeof(P.rt));
+        P.cam = tp.cam;
+        P.radius = tp.radius;
+        P.ratio = tp.best12_threshold;
+        track_match_kernel<<<dim3(div_up(cap, 128), frames - 1), 128, 0, st>>>(A, P, tp.baseline, T.best.p);
+    }
+    projection_decode_kernel<<<div_up((int)fc, 256), 256, 0, st>>>((int)fc, 1, T.best.p, track_idx, track_dist);
+    SFE_CUDA(cudaGetLastError());
+    return SFE_OK;
+}
+
 }  // namespace sfe
 
 using namespace sfe;
@@ -696,7 +839,7 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
         P.cam = *cam;
         P.radius = radius;
         P.ratio = ratio;
-        projection_match_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, n, idx_base, xw, mp_desc, skip, kps, kp_desc, best);
+        projection_match_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, n, idx_base, xw, mp_desc, skip, best);
         m->launches++;
     }
     if (!keys_out) {

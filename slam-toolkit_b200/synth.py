@@ -86,6 +86,17 @@ def knn_queries(db: np.ndarray, q: int, seed: int = 5678, max_flips: int = 40):
     return out, rows
 
 
+def stereo_sequence(seed: int, n: int, step: int = 4, width: int = KITTI_W, height: int = KITTI_H):
+    """`n` consecutive stereo frames of scene `seed`: the camera slides `step` px per frame along the canvas
+    (left_k = columns [k step, k step + W), right_k = the same window 24 px further), so consecutive frames share their
+    content and the tracker's ProjectionMatch has true correspondences within a few pixels.  n * step <= 104."""
+    assert (n - 1) * step + DISPARITY <= _EXTRA, "sequence runs off the canvas"
+    c = canvas(seed, width, height)
+    left = np.stack([c[:, k * step:k * step + width] for k in range(n)])
+    right = np.stack([c[:, k * step + DISPARITY:k * step + DISPARITY + width] for k in range(n)])
+    return np.ascontiguousarray(left), np.ascontiguousarray(right)
+
+
 def projection_scene(kps_xy: np.ndarray, desc: np.ndarray, n_points: int, seed: int = 99,
                      width: int = KITTI_W, height: int = KITTI_H):
     """Map points for BASELINE config 5: Xw uniform in the KITTI frustum

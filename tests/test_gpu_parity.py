@@ -134,6 +134,66 @@ def test_stereo_frames_vs_oracle_and_golden(kitti_ex, oracle, golden):
         assert np.median(kl["x"][ok] - kr["x"][si[ok]]) == 24.0
 
 
+def _kitti_track_params(radius=50.0, Tcw=None):
+    cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, (0, 0, 0, 0), synth.KITTI_W, synth.KITTI_H)
+    return api.TrackParams.make(cam, synth.KITTI_BASELINE, Tcw, radius)
+
+
+def _check_tracking(oracle, out, frames, tp, rt):
+    ocam = oracle.make_camera(tp.cam.fx, tp.cam.fy, tp.cam.cx, tp.cam.cy, list(tp.cam.d), tp.cam.width, tp.cam.height)
+    assert (out["track_idx"][0] == -1).all() and (out["track_dist"][0] == -1).all()
+    tracked = 0
+    for f in range(1, frames):
+        nl, npv, nrp = out["n_l"][f], out["n_l"][f - 1], out["n_r"][f - 1]
+        ti, td = oracle.track_pair(ocam, tp.baseline, rt, tp.radius, out["kps_l"][f - 1, :npv], out["desc_l"][f - 1, :npv],
+                                   out["kps_r"][f - 1, :nrp], out["stereo_idx"][f - 1, :npv], out["kps_l"][f, :nl],
+                                   out["desc_l"][f, :nl])
+        assert np.array_equal(out["track_idx"][f, :nl], ti), f"frame {f}: {(out['track_idx'][f, :nl] != ti).sum()} track indices differ"
+        assert np.array_equal(out["track_dist"][f, :nl], td)
+        assert (out["track_idx"][f, nl:] == -1).all()
+        tracked += int((ti >= 0).sum())
+    return tracked
+
+
+def test_stereo_sequence_tracking_vs_oracle(kitti_ex, oracle, monkeypatch):
+    """sfe_stereo_sequence: the extraction / stereo outputs equal sfe_stereo_frames', and every frame's track_idx equals
+    GetDepth + ProjectionMatch of the oracle on the previous frame (host path, pipelined host path, resident path)."""
+    F = 4
+    L, R = synth.stereo_sequence(5, F, step=4)
+    tp = _kitti_track_params()
+    plain = kitti_ex.stereo_frames(L, R)
+    out = kitti_ex.stereo_sequence(L, R, tp)
+    _stereo_equal(out, plain, F)
+    tracked = _check_tracking(oracle, out, F, tp, np.eye(4))
+    # the camera slid 4 px between frames: most stereo points of a frame are found again in the next one
+    assert tracked > 0.5 * int((out["stereo_idx"][:F - 1] >= 0).sum())
+    ok = out["track_idx"][1] >= 0
+    dxs = out["kps_l"][0]["x"][out["track_idx"][1][ok]] - out["kps_l"][1]["x"][ok]
+    assert np.median(dxs[out["kps_l"][1]["octave"][ok] == 0]) == 4.0
+    # sub-batches of one frame each: consecutive frames live in different chunks
+    monkeypatch.setenv("SFE_PIPELINE_CHUNKS", "4")
+    ex2 = api.ORBextractor(max_images=8)
+    out2 = ex2.stereo_sequence(L, R, tp)
+    _stereo_equal(out2, out, F)
+    assert np.array_equal(out2["track_idx"], out["track_idx"]) and np.array_equal(out2["track_dist"], out["track_dist"])
+    monkeypatch.delenv("SFE_PIPELINE_CHUNKS")
+    # resident entry point, a motion prior that is not the identity, a small radius
+    Tcw = np.eye(4)
+    Tcw[0, 3], Tcw[2, 3] = -0.05, 0.02
+    tp2 = _kitti_track_params(radius=12.0, Tcw=Tcw)
+    cap, h, w = kitti_ex.cap, *L.shape[1:]
+    dl, dr = api.DeviceBuffer(L.nbytes).upload(L), api.DeviceBuffer(R.nbytes).upload(R)
+    spec = {"kps_l": (28, api.KP_DTYPE, (F, cap)), "desc_l": (32, np.uint8, (F, cap, 32)), "n_l": (0, np.int32, (F,)),
+            "kps_r": (28, api.KP_DTYPE, (F, cap)), "desc_r": (32, np.uint8, (F, cap, 32)), "n_r": (0, np.int32, (F,)),
+            "stereo_idx": (4, np.int32, (F, cap)), "stereo_dist": (4, np.int32, (F, cap)), "track_idx": (4, np.int32, (F, cap)),
+            "track_dist": (4, np.int32, (F, cap))}
+    bufs = {k: api.DeviceBuffer(max(b * cap * F, 4 * F)) for k, (b, _, _) in spec.items()}
+    kitti_ex.stereo_sequence_dev(dl.ptr, dr.ptr, F, w, h, {k: b.ptr for k, b in bufs.items()}, tp2)
+    dev = {k: bufs[k].download(shape, dt) for k, (_, dt, shape) in spec.items()}
+    _stereo_equal(dev, plain, F)
+    _check_tracking(oracle, dev, F, tp2, Tcw)
+
+
 def test_resident_entry_points_match_host_ones(kitti_ex, oracle):
     L, R = synth.stereo_pair(3)
     cap, h, w = kitti_ex.cap, *L.shape

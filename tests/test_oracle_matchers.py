@@ -278,3 +278,47 @@ def test_vocab_transform_oracle_vs_literal(oracle):
                 if final not in children:
                     break
             assert (wid[f], w[f], nid[f]) == (wid_of.get(final, 0), weight[final], n_at)
+
+
+def test_grid_projection_match_equals_brute_force_and_track_pair_composes(oracle):
+    oc = oracle
+    """orc_projection_match_grid (the CPU baseline's stand-in for the FLANN kd-tree) visits the same candidate set as the
+    brute-force oracle; orc_track_pair = NormalizedUndistort + GetDepth + ProjectionMatch with the no-depth points skipped."""
+    rng = np.random.default_rng(11)
+    cam = oc.make_camera(718.856, 718.856, 607.1928, 185.2157, [0.01, -0.002, 0.0005, -0.0003], 1241, 376)
+    for trial in range(6):
+        m, n = int(rng.integers(1, 600)), int(rng.integers(1, 900))
+        kps = np.zeros(m, oc.KP_DTYPE)
+        kps["x"] = rng.uniform(-5, 1250, m).astype(np.float32)   # a few keypoints outside the image: clamped cells
+        kps["y"] = rng.uniform(-5, 380, m).astype(np.float32)
+        desc = rng.integers(0, 256, (m, 32), dtype=np.uint8)
+        z = rng.uniform(-1, 60, n)
+        xw = np.stack([(rng.uniform(-50, 1300, n) - 607.1928) / 718.856 * z, (rng.uniform(-50, 420, n) - 185.2157) / 718.856 * z, z], 1)
+        mpd = desc[rng.integers(0, m, n)] ^ (rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8)
+                                             & rng.integers(0, 256, (n, 32), dtype=np.uint8))
+        skip = (rng.uniform(size=n) < 0.1).astype(np.uint8)
+        rt = np.eye(4)[:3]
+        for radius in (0.0, 7.5, 50.0, 400.0):
+            a = oc.projection_match(xw, mpd, skip, rt, cam, kps, desc, radius)
+            b = oc.projection_match(xw, mpd, skip, rt, cam, kps, desc, radius, grid=True)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (trial, radius)
+    # track_pair against its parts
+    n_prev, n_cur = 500, 450
+    kl = np.zeros(n_prev, oc.KP_DTYPE)
+    kl["x"], kl["y"] = rng.uniform(30, 1200, n_prev).astype(np.float32), rng.uniform(30, 350, n_prev).astype(np.float32)
+    kr = kl.copy()
+    kr["x"] -= rng.uniform(-2, 60, n_prev).astype(np.float32)     # some negative disparities: skipped
+    sidx = np.where(rng.uniform(size=n_prev) < 0.7, rng.permutation(n_prev), -1).astype(np.int32)
+    dl = rng.integers(0, 256, (n_prev, 32), dtype=np.uint8)
+    cur = np.zeros(n_cur, oc.KP_DTYPE)
+    src = rng.integers(0, n_prev, n_cur)
+    cur["x"], cur["y"] = kl["x"][src] + rng.uniform(-6, 6, n_cur).astype(np.float32), kl["y"][src] + rng.uniform(-6, 6, n_cur).astype(np.float32)
+    dc = dl[src] ^ (1 << rng.integers(0, 8, (n_cur, 32))).astype(np.uint8) * (rng.uniform(size=(n_cur, 32)) < 0.1)
+    dc = dc.astype(np.uint8)
+    nrm = oc.normalized_undistort(cam, kl)
+    xc, valid = oc.stereo_depth(cam, 0.537, kl, nrm, kr, sidx)
+    ref = oc.projection_match(xc, dl, (valid != 1).astype(np.uint8), np.eye(4)[:3], cam, cur, dc, 30.0)
+    for grid in (False, True):
+        got = oc.track_pair(cam, 0.537, np.eye(4), 30.0, kl, dl, kr, sidx, cur, dc, grid=grid)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    assert (ref[0] >= 0).sum() > 20
