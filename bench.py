@@ -4,13 +4,14 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One step = one batch of F stereo frames (1241x376, 8 levels, scale 1.2, 2000 features) through
-the hot path: extract(left) + extract(right) + StereoMatch, i.e. the keyframe path of the
-reference pipeline (src/pipeline.cpp:243-249), BASELINE.json configs[1].
-  value : whole-job stereo frames/s with inputs resident in HBM (sfe_stereo_frames_dev), timed
+One step = one batch of F consecutive stereo frames (1241x376, 8 levels, scale 1.2, 2000 features) through
+the hot path, BASELINE.json configs[1] as SURVEY.md §8d defines it: extract(left) + extract(right) + StereoMatch
+(the keyframe path of the reference pipeline, src/pipeline.cpp:243-249) + the tracker's ProjectionMatch of the
+previous frame's stereo-triangulated keypoints into the frame (StereoFrame::GetDepth, identity motion prior, r = 50).
+  value : whole-job stereo frames/s with inputs resident in HBM (sfe_stereo_sequence_dev), timed
           with CUDA events on the extractor's own stream, max over ranks.
-  e2e   : the same metric through the host entry point (sfe_stereo_frames): pinned host images in,
-          host keypoints/descriptors/stereo indices out, copies inside the timed region.
+  e2e   : the same metric through the host entry point (sfe_stereo_sequence): pinned host images in,
+          host keypoints/descriptors/stereo indices/track indices out, copies inside the timed region.
   roofline     : the dominant kernel's algorithmic bytes / its CUDA-event time, vs the measured HBM peak.
   cpu_baseline : the CPU oracle (port of the reference) on a bounded sample, host cores stated.
 --impl reference times that CPU oracle alone (the reference itself cannot be built here:
@@ -31,11 +32,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 W, H = 1241, 376
-N_DISTINCT = 8           # distinct synthetic frames; batches are rotations of them
+SEQ_LEN, SEQ_STEP = 16, 4  # a batch is made of 16-frame sequences: the camera slides 4 px per frame over one synthetic scene
 PYR_PIXELS = 1_444_097   # sum of level sizes
 B_IMG = 466_616 + PYR_PIXELS + 2000 * 60          # algorithmic bytes per image extraction
 B_FRAME = 2 * B_IMG + 4 * 2000                     # per stereo frame
-WORKLOAD = "kitti_stereo_frontend: extract L + extract R + StereoMatch, 1241x376, 8 levels, 1.2, 2000 feats"
+WORKLOAD = ("kitti_stereo_frontend: extract L + extract R + StereoMatch + ProjectionMatch(previous frame's stereo points, r=50), "
+            "1241x376, 8 levels, 1.2, 2000 feats")
 
 
 def parse():
@@ -55,11 +57,20 @@ def parse():
 
 
 def make_frames(n):
+    """n consecutive stereo frames: 16-frame sequences over scenes 0, 1, 2, ... (synth.stereo_sequence)."""
     from slam_toolkit_b200 import synth
-    base = [synth.stereo_pair(s) for s in range(min(n, N_DISTINCT))]
-    L = np.stack([base[i % len(base)][0] for i in range(n)])
-    R = np.stack([base[i % len(base)][1] for i in range(n)])
-    return L, R
+    Ls, Rs = [], []
+    for s in range((n + SEQ_LEN - 1) // SEQ_LEN):
+        l, r = synth.stereo_sequence(s, min(SEQ_LEN, n - s * SEQ_LEN), SEQ_STEP)
+        Ls.append(l)
+        Rs.append(r)
+    return np.concatenate(Ls), np.concatenate(Rs)
+
+
+def track_params():
+    from slam_toolkit_b200 import api, synth
+    cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, (0, 0, 0, 0), W, H)
+    return api.TrackParams.make(cam, synth.KITTI_BASELINE, None, 50.0)
 
 
 class ClockSampler(threading.Thread):
@@ -158,11 +169,13 @@ def cpu_sample(frames, threads):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c
     oracle_c.build()
+    from slam_toolkit_b200 import synth
     L, R = make_frames(frames)
+    cam = oracle_c.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0, 0, 0, 0], W, H)
     t0 = time.perf_counter()
-    matches, kps = oracle_c.stereo_frames(L, R, threads)
+    matches, kps, tracked = oracle_c.stereo_sequence(L, R, threads, cam, synth.KITTI_BASELINE, 50.0)
     dt = time.perf_counter() - t0
-    return frames / dt, dt, matches, kps
+    return frames / dt, dt, matches + tracked, kps
 
 
 def run_reference(args, rank, world):
@@ -326,11 +339,13 @@ def main():
     NB = max(2, int(np.ceil(2.2 * 126e6 / per_batch)))
     d_left, d_right = [], []
     for b in range(NB):
-        sh = (b * 3) % F
+        sh = (b * SEQ_LEN) % F       # rotated by whole sequences: consecutive frames stay consecutive
         d_left.append(api.DeviceBuffer(F * PITCH * H, dev).upload(pitched(np.roll(L, sh, axis=0))))
         d_right.append(api.DeviceBuffer(F * PITCH * H, dev).upload(pitched(np.roll(R, sh, axis=0))))
     spec = {"kps_l": 28 * cap * F, "desc_l": 32 * cap * F, "n_l": 4 * F, "kps_r": 28 * cap * F, "desc_r": 32 * cap * F,
-            "n_r": 4 * F, "stereo_idx": 4 * cap * F, "stereo_dist": 4 * cap * F}
+            "n_r": 4 * F, "stereo_idx": 4 * cap * F, "stereo_dist": 4 * cap * F, "track_idx": 4 * cap * F,
+            "track_dist": 4 * cap * F}
+    tp = track_params()
     d_out = {k: api.DeviceBuffer(v, dev) for k, v in spec.items()}
     ptrs = {k: b.ptr for k, b in d_out.items()}
 
@@ -339,7 +354,7 @@ def main():
             dist.barrier()
 
     def step_resident(i):
-        ex.stereo_frames_dev(d_left[i % NB].ptr, d_right[i % NB].ptr, F, W, H, ptrs, pitch=PITCH)
+        ex.stereo_sequence_dev(d_left[i % NB].ptr, d_right[i % NB].ptr, F, W, H, ptrs, tp, pitch=PITCH)
 
     sampler = ClockSampler(range(world) if rank == 0 else [], args.clock_period if rank == 0 else 0)
     sampler.start()                      # NVML initialises here, outside the timed regions
@@ -370,7 +385,9 @@ def main():
     barrier()
     launches = ex.launches() - l0
     ex.set_async(False)
-    n_match = int((d_out["stereo_idx"].download((F, cap), np.int32) >= 0).sum())
+    n_stereo = int((d_out["stereo_idx"].download((F, cap), np.int32) >= 0).sum())
+    n_track = int((d_out["track_idx"].download((F, cap), np.int32) >= 0).sum())
+    n_match = n_stereo + n_track
     n_kps = int(d_out["n_l"].download((F,), np.int32).sum() + d_out["n_r"].download((F,), np.int32).sum())
 
     # ---- e2e: pinned host images -> host results through the public host entry point (sfe_stereo_frames), synchronous
@@ -382,13 +399,13 @@ def main():
     for h in handles:
         pl, pr = api.PinnedArray((F, H, W), np.uint8), api.PinnedArray((F, H, W), np.uint8)
         pl.array[:], pr.array[:] = L, R
-        pins.append((pl, pr, h.alloc_stereo_out(F, pinned=True)))
+        pins.append((pl, pr, h.alloc_stereo_out(F, pinned=True, track=True)))
     out = pins[0][2]
 
     def e2e_steps(t, count):
         pl, pr, o = pins[t]
         for _ in range(count):
-            handles[t].stereo_frames(pl.array, pr.array, o)
+            handles[t].stereo_sequence(pl.array, pr.array, tp, o)
 
     def timed(nthreads):
         shares = [K // nthreads + (1 if t < K % nthreads else 0) for t in range(nthreads)]
@@ -447,8 +464,9 @@ def main():
     alg_bytes = {"pyramid": 2 * F * (466_616 + PYR_PIXELS) / 7.0,  # per launch: 7 launches per step
                  "fast_cells": 2 * F * (PYR_PIXELS + 11_800 * 4), "quadtree": 2 * F * (11_800 * 4 + 2000 * 4),
                  "blur": 2 * F * 2 * PYR_PIXELS, "orient_describe": 2 * F * (2000 * (749 + 512) + 2000 * 60),
-                 "stereo_match": F * (2 * 2000 * 40 + 2000 * 8)}
-    launches_per_step = {"pyramid": 7, "fast_cells": 1, "quadtree": 1, "blur": 1, "orient_describe": 1, "stereo_match": 1}
+                 "stereo_match": F * (2 * 2000 * 40 + 2000 * 8),
+                 "track": F * 2000 * (2 * 60 + 28 + 4 + 8) / 3.0}
+    launches_per_step = {"pyramid": 7, "fast_cells": 1, "quadtree": 1, "blur": 1, "orient_describe": 1, "stereo_match": 1, "track": 3}
     top = max(stage_ms, key=lambda k: stage_ms[k])
     top_ms = stage_ms[top] / max(calls, 1) / launches_per_step[top]
     achieved = alg_bytes[top] / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
@@ -478,7 +496,8 @@ def main():
                          "whole_step_achieved": value / world * B_FRAME / 1e9, "whole_step_frac": value / world * B_FRAME / 1e9 / hbm_peak,
                          "note": "extraction is integer-issue bound, not HBM bound (SURVEY.md §8d): see profiles/ for pipe utilisation"},
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
-            "keypoints_per_frame": n_kps / F, "matches_per_s": value * n_match / F}
+            "keypoints_per_frame": n_kps / F, "matches_per_s": value * n_match / F,
+            "stereo_matches_per_frame": n_stereo / F, "tracked_matches_per_frame": n_track / F}
     if hamming is not None:
         hamming["q1_stream_frac_of_hbm_peak"] = hamming["q1_stream_gbs"] / (world * hbm_peak)
         line["hamming"] = hamming
