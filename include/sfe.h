@@ -314,6 +314,29 @@ int sfe_knn2_dev(sfe_matcher *m, const sfe_db *db, const uint8_t *queries_dev, i
 int sfe_knn2_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int q,
                        int32_t *out_dev);
 
+/* ---- Front-end results as one byte stream -------------------------------------------------
+ * The reference has no on-disk form of a frame (Memento save is `#if 0`, src/pipeline.cpp:231-241); this is the one
+ * the batched front end hands to an unchanged back end or another process.  Host-only, little-endian, packed:
+ *   header (48 B): "SFER", u32 version = 1, u32 frames, u32 flags (SFE_RES_*), u32 w, u32 h, u64 payload bytes,
+ *                  u64 FNV-1a-64 of the payload, 8 B reserved
+ *   per frame    : u32 n_l, u32 n_r, kps_l[n_l] (28 B each = cv::KeyPoint), desc_l[n_l][32],
+ *                  if STEREO: kps_r[n_r], desc_r[n_r][32], stereo_idx[n_l] i32, stereo_dist[n_l] i32
+ *                  if TRACK : track_idx[n_l] i32, track_dist[n_l] i32
+ * Arrays are the cap-strided ones sfe_stereo_frames / sfe_stereo_sequence fill; only the n valid rows travel. */
+enum { SFE_RES_STEREO = 1, SFE_RES_TRACK = 2 };
+int sfe_results_size(int frames, const int32_t *n_l, const int32_t *n_r, int flags, size_t *bytes);
+int sfe_results_pack(void *buf, size_t buf_bytes, int frames, int cap, int w, int h, int flags,
+                     const sfe_keypoint *kps_l, const uint8_t *desc_l, const int32_t *n_l,
+                     const sfe_keypoint *kps_r, const uint8_t *desc_r, const int32_t *n_r,
+                     const int32_t *stereo_idx, const int32_t *stereo_dist, const int32_t *track_idx,
+                     const int32_t *track_dist, size_t *written);
+/* header fields + the largest per-frame keypoint count (the cap an unpack needs); verifies magic, sizes, checksum */
+int sfe_results_info(const void *buf, size_t bytes, int *frames, int *flags, int *w, int *h, int *max_n);
+/* inverse of pack into cap-strided arrays; rows past n are left untouched; absent sections may be NULL */
+int sfe_results_unpack(const void *buf, size_t bytes, int cap, sfe_keypoint *kps_l, uint8_t *desc_l, int32_t *n_l,
+                       sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx,
+                       int32_t *stereo_dist, int32_t *track_idx, int32_t *track_dist);
+
 #ifdef __cplusplus
 }
 #endif

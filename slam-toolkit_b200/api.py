@@ -95,6 +95,10 @@ SIGNATURES = {
     "sfe_extract_batch_dev": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sfe_stereo_frames": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
     "sfe_stereo_frames_dev": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams)] + [_vp] * 8 + [_i]),
+    "sfe_results_size": (_i, [_i, _vp, _vp, _i, C.POINTER(_sz)]),
+    "sfe_results_pack": (_i, [_vp, _sz, _i, _i, _i, _i, _i] + [_vp] * 10 + [C.POINTER(_sz)]),
+    "sfe_results_info": (_i, [_vp, _sz] + [C.POINTER(_i)] * 5),
+    "sfe_results_unpack": (_i, [_vp, _sz, _i] + [_vp] * 10),
     "sfe_stereo_sequence": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams), C.POINTER(TrackParams)] + [_vp] * 10 + [_i]),
     "sfe_stereo_sequence_dev": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, C.POINTER(StereoParams), C.POINTER(TrackParams)] + [_vp] * 10 + [_i]),
     "sfe_image_pitch": (_i, [_i]),
@@ -711,3 +715,39 @@ class DescriptorDB:
             self.close()
         except Exception:
             pass
+
+
+# ---- front-end results as one byte stream (include/sfe.h "SFER") -------------------------------
+RES_STEREO, RES_TRACK = 1, 2
+_RES_KEYS = ("kps_l", "desc_l", "n_l", "kps_r", "desc_r", "n_r", "stereo_idx", "stereo_dist", "track_idx", "track_dist")
+
+
+def pack_results(out, w=0, h=0) -> bytes:
+    """The dict alloc_stereo_out / extract_batch style calls fill (cap-strided arrays) -> one byte string that holds
+    only the valid rows.  Sections present: stereo if out has "kps_r", tracking if it has "track_idx"."""
+    frames, cap = out["kps_l"].shape
+    flags = (RES_STEREO if "kps_r" in out else 0) | (RES_TRACK if "track_idx" in out else 0)
+    arr = {k: np.ascontiguousarray(out[k]) if k in out else None for k in _RES_KEYS}
+    n = C.c_size_t()
+    _check(lib().sfe_results_size(frames, _p(arr["n_l"]), _p(arr["n_r"]), flags, C.byref(n)))
+    buf = np.empty(n.value, np.uint8)
+    wr = C.c_size_t()
+    _check(lib().sfe_results_pack(_p(buf), buf.nbytes, frames, cap, w, h, flags, *[_p(arr[k]) for k in _RES_KEYS], C.byref(wr)))
+    assert wr.value == n.value
+    return buf.tobytes()
+
+
+def unpack_results(data: bytes):
+    """-> (out dict of cap-strided arrays with cap = the largest frame, (w, h))."""
+    buf = np.frombuffer(data, np.uint8)
+    frames, flags, w, h, mx = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _check(lib().sfe_results_info(_p(buf), buf.nbytes, C.byref(frames), C.byref(flags), C.byref(w), C.byref(h), C.byref(mx)))
+    f, cap = frames.value, max(mx.value, 1)
+    out = {"kps_l": np.zeros((f, cap), KP_DTYPE), "desc_l": np.zeros((f, cap, 32), np.uint8), "n_l": np.zeros(f, np.int32)}
+    if flags.value & RES_STEREO:
+        out.update({"kps_r": np.zeros((f, cap), KP_DTYPE), "desc_r": np.zeros((f, cap, 32), np.uint8), "n_r": np.zeros(f, np.int32),
+                    "stereo_idx": np.full((f, cap), -1, np.int32), "stereo_dist": np.full((f, cap), -1, np.int32)})
+    if flags.value & RES_TRACK:
+        out.update({"track_idx": np.full((f, cap), -1, np.int32), "track_dist": np.full((f, cap), -1, np.int32)})
+    _check(lib().sfe_results_unpack(_p(buf), buf.nbytes, cap, *[_p(out.get(k)) for k in _RES_KEYS]))
+    return out, (w.value, h.value)
