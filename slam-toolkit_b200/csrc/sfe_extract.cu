@@ -1043,7 +1043,8 @@ struct sfe_extractor {
     int n_compute = 3;                              // SFE_COMPUTE_STREAMS
     cudaStream_t aux[2] = {nullptr, nullptr};       // per compute stream: the blur runs beside FAST + quadtree
     cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
-    bool overlap_blur = false;                      // SFE_OVERLAP_BLUR=1; measured on B200: no gain (both kernels fill the
+    int overlap_blur = 0;   // 0 off, 1 = blur forks before FAST, 2 = blur forks after FAST (beside the quadtree only)
+    bool overlap_blur_unused = false;                      // SFE_OVERLAP_BLUR=1; measured on B200: no gain (both kernels fill the
                                                     // machine on their own, the block scheduler runs them back to back)
     cudaEvent_t ev_start = nullptr;
     bool async_dev = false;                         // _dev entry points return after enqueueing (sfe_extractor_wait)
@@ -1464,7 +1465,7 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         // The blur only needs the pyramid, so it can run on a side stream beside FAST and the quadtree and join before
         // the descriptors (opt-in: it bought nothing on B200, see overlap_blur).  Serial when stages are timed.
         const int si = 0;
-        const bool fork = ex->overlap_blur && !ex->profiling && st == ex->stream;
+        const bool fork = ex->overlap_blur && !ex->profiling && st == ex->stream, late = ex->overlap_blur == 2;
         cudaStream_t sb = fork ? ex->aux[si] : st;
         auto launch_blur = [&]() {
             if (ex->tma_now)
@@ -1472,14 +1473,19 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
             else
                 blur_kernel<false><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
         };
-        if (fork) {
+        auto fork_blur = [&]() -> int {
             SFE_CUDA(cudaEventRecord(ex->ev_fork[si], st));
             SFE_CUDA(cudaStreamWaitEvent(sb, ex->ev_fork[si], 0));
             launch_blur();
             SFE_CUDA(cudaEventRecord(ex->ev_join[si], sb));
-        }
+            return SFE_OK;
+        };
+        if (fork && !late)
+            if (int rc = fork_blur()) return rc;
         if (int rc = launch_fast(ex, st, S, count)) return rc;
         prof_mark(ex, 2);
+        if (fork && late)
+            if (int rc = fork_blur()) return rc;
         {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
             static std::mutex mu;
             static size_t granted[64] = {};
@@ -1744,7 +1750,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     }
     if (const char *env = getenv("SFE_PIPELINE_CHUNKS")) ex->chunks_override = atoi(env);
     if (const char *env = getenv("SFE_NO_TMA")) ex->tma_disabled = atoi(env) != 0;
-    if (const char *env = getenv("SFE_OVERLAP_BLUR")) ex->overlap_blur = atoi(env) != 0;
+    if (const char *env = getenv("SFE_OVERLAP_BLUR")) ex->overlap_blur = atoi(env);
     if (const char *env = getenv("SFE_TRACE")) ex->trace = atoi(env) != 0;
     if (const char *env = getenv("SFE_COMPUTE_STREAMS")) ex->n_compute = std::max(1, std::min(atoi(env), kComputeStreams));
     if (ex->trace)

@@ -27,56 +27,72 @@ __device__ __forceinline__ void load_desc(const uint8_t *p, uint32_t d[8]) {
 // ---------------------------------------------------------------------------------------------
 // StereoMatch.  The reference's int(y/10) row buckets (:60-66,83-95) only pre-select: |dy| <= 3 < 10 keeps
 // every passing candidate inside buckets b-1..b+1, so the candidate set is every right keypoint passing the
-// dy / dx filters (:103-110).  Here: one CTA = 64 left keypoints of one frame.  The CTA counting-sorts the
-// right keypoints of its frame into 8-px row buckets in shared memory, then every warp walks only the buckets
-// that can hold |dy| <= y_thr for each of its left keypoints, applies the reference's exact float filters and
-// fetches descriptors only for the survivors.  Visiting order is free: best / second best are packed
-// (dist << 16 | index) keys, so "strict < in ascending index order" (:114-123) is a plain unsigned min.
+// dy / dx filters (:103-110).  Here: one CTA = 512 left keypoints of one frame.  The CTA counting-sorts the
+// right keypoints of its frame into a 2-D bucket grid in shared memory (8-px rows x 64-px columns: the dx window
+// [0, max_dx] is as selective as the dy one), then one thread per left keypoint walks the few buckets that can hold
+// a candidate -- per bucket row a contiguous range of the sorted order -- applies the reference's exact float
+// filters and fetches descriptors only for the survivors (about ten candidates instead of the ~90 of a row-only
+// index).  Visiting order is free: best / second best are packed (dist << 16 | index) keys, so "strict < in
+// ascending index order" (:114-123) is a plain unsigned min.
 // ---------------------------------------------------------------------------------------------
-constexpr int kStereoChunk = 2048;   // right keypoints indexed in shared memory at a time
-constexpr int kStereoPerWarp = 8;    // left keypoints per warp; 64 per CTA
-constexpr int kRowBuckets = 512;     // 8-px rows; y >= 4088 shares the last bucket
-constexpr int kRowShift = 3;
+constexpr int kStereoChunk = 2048;    // right keypoints indexed in shared memory at a time
+constexpr int kStereoPerThread = 2;   // left keypoints per thread; 512 per CTA
+constexpr int kStereoPerCta = 256 * kStereoPerThread;
+constexpr int kRowShift = 3, kRowBuckets = 128;  // 8-px rows; y >= 1016 shares the last row of buckets
+constexpr int kColShift = 6, kColBuckets = 32;   // 64-px columns; x >= 1984 shares the last column
+constexpr int kStereoCells = kRowBuckets * kColBuckets;
 
 __device__ __forceinline__ int row_bucket(float y) {
     return min(max((int)floorf(y) >> kRowShift, 0), kRowBuckets - 1);  // monotone in y
 }
+__device__ __forceinline__ int col_bucket(float x) {
+    return min(max((int)floorf(x) >> kColShift, 0), kColBuckets - 1);  // monotone in x
+}
 
 // thr_y / thr_dx: the largest floats <= y_threshold / max_dx, so that for a float d the reference's double
-// comparison (double)d > T is exactly d > thr (no float lies strictly between thr and T).
+// comparison (double)d > T is exactly d > thr (no float lies strictly between thr and T).  reach_y / reach_dx:
+// |float(a - b)| <= T implies |a - b| < T + 1 for coordinates < 2^13, which bounds the buckets worth visiting.
 __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_keypoint *__restrict__ kl,
                                                            const uint8_t *__restrict__ dl, const int32_t *__restrict__ nl,
                                                            const sfe_keypoint *__restrict__ kr,
                                                            const uint8_t *__restrict__ dr, const int32_t *__restrict__ nr,
-                                                           float thr_y, float thr_dx, float reach_y, double ratio,
+                                                           float thr_y, float thr_dx, float reach_y, float reach_dx, double ratio,
                                                            int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist) {
-    __shared__ float2 rxy[kStereoChunk];
-    __shared__ uint16_t order[kStereoChunk];       // right keypoints of the chunk sorted by row bucket
-    __shared__ int start[kRowBuckets + 1];         // bucket b = order[start[b] .. start[b + 1])
-    __shared__ int fill[kRowBuckets];
+    __shared__ float2 rxy[kStereoChunk];            // right keypoints of the chunk, in bucket order
+    __shared__ uint16_t order[kStereoChunk];        // their indices inside the chunk
+    __shared__ uint16_t start[kStereoCells + 1];    // bucket c = positions start[c] .. start[c + 1]
+    __shared__ __align__(16) uint16_t fill[kStereoCells];
     __shared__ int warp_tot[8];
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_l = min(nl[f], cap), n_r = min(nr[f], cap);
     const size_t base = (size_t)f * cap;
-    const int i0 = blockIdx.x * (8 * kStereoPerWarp) + warp * kStereoPerWarp;
-    uint32_t k0[kStereoPerWarp], k1[kStereoPerWarp];
+    const int i0 = blockIdx.x * kStereoPerCta;
+    uint32_t k0[kStereoPerThread], k1[kStereoPerThread];
 #pragma unroll
-    for (int k = 0; k < kStereoPerWarp; k++) k0[k] = k1[k] = kNoKey;
-    const bool block_has_work = blockIdx.x * (8 * kStereoPerWarp) < n_l;
+    for (int k = 0; k < kStereoPerThread; k++) k0[k] = k1[k] = kNoKey;
+    const bool block_has_work = i0 < n_l;
     for (int c0 = 0; c0 < n_r && block_has_work; c0 += kStereoChunk) {
         const int cn = min(kStereoChunk, n_r - c0);
         __syncthreads();
-        for (int b = tid; b < kRowBuckets; b += 256) fill[b] = 0;
+        for (int c = tid; c < kStereoCells; c += 256) fill[c] = 0;
         __syncthreads();
+        // count: the shared-memory atomics work on 32-bit words, two 16-bit counters per word
+        uint32_t *fill32 = (uint32_t *)fill;
         for (int j = tid; j < cn; j += 256) {
-            const float2 r = make_float2(kr[base + c0 + j].x, kr[base + c0 + j].y);
-            rxy[j] = r;
-            atomicAdd(&fill[row_bucket(r.y)], 1);
+            const sfe_keypoint &q = kr[base + c0 + j];
+            const int c = row_bucket(q.y) * kColBuckets + col_bucket(q.x);
+            atomicAdd(&fill32[c >> 1], 1u << (16 * (c & 1)));
         }
         __syncthreads();
-        {   // exclusive scan of the 512 bucket counts: 2 per thread
-            const int a = fill[2 * tid], b2 = fill[2 * tid + 1];
-            int inc = a + b2;
+        {   // exclusive scan of the bucket counts: 16 consecutive buckets per thread
+            constexpr int kPer = kStereoCells / 256;
+            int cnt[kPer], tot = 0;
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                cnt[k] = fill[tid * kPer + k];
+                tot += cnt[k];
+            }
+            int inc = tot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int u = __shfl_up_sync(0xffffffffu, inc, o);
@@ -84,66 +100,69 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
             }
             if (lane == 31) warp_tot[warp] = inc;
             __syncthreads();
-            int woff = 0;
+            int run = inc - tot;
 #pragma unroll
-            for (int w2 = 0; w2 < 8; w2++) woff += w2 < warp ? warp_tot[w2] : 0;
-            const int ex = woff + inc - (a + b2);
-            start[2 * tid] = ex;
-            start[2 * tid + 1] = ex + a;
-            if (tid == 255) start[kRowBuckets] = ex + a + b2;
-            fill[2 * tid] = 0;
-            fill[2 * tid + 1] = 0;
+            for (int w2 = 0; w2 < 8; w2++) run += w2 < warp ? warp_tot[w2] : 0;
+#pragma unroll
+            for (int k = 0; k < kPer; k++) {
+                start[tid * kPer + k] = (uint16_t)run;
+                fill[tid * kPer + k] = (uint16_t)run;  // becomes the bucket's write cursor
+                run += cnt[k];
+            }
+            if (tid == 255) start[kStereoCells] = (uint16_t)run;
         }
         __syncthreads();
         for (int j = tid; j < cn; j += 256) {
-            const int b = row_bucket(rxy[j].y);
-            order[start[b] + atomicAdd(&fill[b], 1)] = (uint16_t)j;
+            const sfe_keypoint &q = kr[base + c0 + j];
+            const float x = q.x, y = q.y;
+            const int c = row_bucket(y) * kColBuckets + col_bucket(x);
+            const uint32_t old = atomicAdd(&fill32[c >> 1], 1u << (16 * (c & 1)));
+            const int t = (old >> (16 * (c & 1))) & 0xFFFF;
+            order[t] = (uint16_t)j;
+            rxy[t] = make_float2(x, y);
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kStereoPerWarp; k++) {
-            const int i = i0 + k;
+        for (int k = 0; k < kStereoPerThread; k++) {
+            const int i = i0 + k * 256 + tid;
             if (i >= n_l) continue;
             const float lx = kl[base + i].x, ly = kl[base + i].y;
             uint32_t a[8];
             load_desc(dl + (base + i) * 32, a);
-            const int t0 = start[row_bucket(ly - reach_y)], t1 = start[row_bucket(ly + reach_y) + 1];
-            uint32_t q0 = kNoKey, q1 = kNoKey;
-            for (int t = t0 + lane; t < t1; t += 32) {
-                const int j = order[t];
-                const float2 r = rxy[j];
-                const float dx = __fsub_rn(lx, r.x), dy = __fsub_rn(ly, r.y);  // float subtraction, as in the reference
-                if (fabsf(dy) > thr_y || dx < 0.f || dx > thr_dx) continue;   // :103-110
-                uint32_t b[8];
-                load_desc(dr + (base + c0 + j) * 32, b);
-                top2_insert(q0, q1, (uint32_t)hamming8(a, b) << 16 | (uint32_t)(c0 + j));
+            const int yb0 = row_bucket(ly - reach_y), yb1 = row_bucket(ly + reach_y);
+            const int xb0 = col_bucket(lx - reach_dx), xb1 = col_bucket(lx + 1.f);
+            uint32_t q0 = k0[k], q1 = k1[k];
+            for (int yb = yb0; yb <= yb1; yb++) {
+                const int t1 = start[yb * kColBuckets + xb1 + 1];
+                for (int t = start[yb * kColBuckets + xb0]; t < t1; t++) {
+                    const float2 r = rxy[t];
+                    const float dx = __fsub_rn(lx, r.x), dy = __fsub_rn(ly, r.y);  // float subtraction, as in the reference
+                    if (fabsf(dy) > thr_y || dx < 0.f || dx > thr_dx) continue;   // :103-110
+                    const int j = c0 + order[t];
+                    const uint4 *d = (const uint4 *)(dr + (base + j) * 32);
+                    const uint4 b0 = __ldg(d), b1 = __ldg(d + 1);
+                    top2_insert(q0, q1, (uint32_t)hamming8_csa(a, b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w) << 16 | (uint32_t)j);
+                }
             }
-            top2_insert(k0[k], k1[k], q1);
-            top2_insert(k0[k], k1[k], q0);
+            k0[k] = q0;
+            k1[k] = q1;
         }
     }
 #pragma unroll
-    for (int k = 0; k < kStereoPerWarp; k++) {
-        uint32_t q0 = k0[k], q1 = k1[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const uint32_t o0 = __shfl_xor_sync(0xffffffffu, q0, o), o1 = __shfl_xor_sync(0xffffffffu, q1, o);
-            q1 = min(min(q1, o1), max(q0, o0));
-            q0 = min(q0, o0);
-        }
-        const int i = i0 + k;
-        if (lane == 0 && i < cap) {
-            int idx = -1, dist = -1;
-            if (i < n_l && q0 != kNoKey) {
-                const double d0 = (double)(q0 >> 16), d1 = q1 == kNoKey ? 999999999. : (double)(q1 >> 16);
-                if (d0 < d1 * ratio) {  // :125-128
-                    idx = (int)(q0 & 0xFFFF);
-                    dist = (int)(q0 >> 16);
-                }
+    for (int k = 0; k < kStereoPerThread; k++) {
+        const int i = i0 + k * 256 + tid;
+        if (i >= cap) continue;
+        const uint32_t q0 = k0[k], q1 = k1[k];
+        int idx = -1, dist = -1;
+        if (i < n_l && q0 != kNoKey) {
+            const double d0 = (double)(q0 >> 16), d1 = q1 == kNoKey ? 999999999. : (double)(q1 >> 16);
+            if (d0 < d1 * ratio) {  // :125-128
+                idx = (int)(q0 & 0xFFFF);
+                dist = (int)(q0 >> 16);
             }
-            out_idx[base + i] = idx;
-            if (out_dist) out_dist[base + i] = dist;
         }
+        out_idx[base + i] = idx;
+        if (out_dist) out_dist[base + i] = dist;
     }
 }
 
@@ -157,9 +176,9 @@ void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoin
                          const sfe_keypoint *kr, const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
                          double ratio, int32_t *out_idx, int32_t *out_dist) {
     // rows a candidate can sit in: |float(ly - ry)| <= y_thr implies |ly - ry| < y_thr + 1 for coordinates < 2^13
-    const float reach = (float)(std::max(y_thr, 0.0) + 1.0);
-    stereo_match_kernel<<<dim3(div_up(cap, 8 * kStereoPerWarp), frames), 256, 0, st>>>(
-        cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, ratio, out_idx, out_dist);
+    const float reach = (float)(std::max(y_thr, 0.0) + 1.0), reach_dx = (float)(std::max(max_dx, 0.0) + 1.0);
+    stereo_match_kernel<<<dim3(div_up(cap, kStereoPerCta), frames), 256, 0, st>>>(
+        cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
 }
 
 // ---------------------------------------------------------------------------------------------

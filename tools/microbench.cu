@@ -35,6 +35,12 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed) {
                 const uint32_t x = a[i] ^ seed, y = a[(i + 1) & 7];
                 a[i] = __popc(x ^ y ^ acc) + ((x & y) | (acc & (x ^ y)));
             }
+            if (OP == 14) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a[i]), "r"(a[(i + 1) & 7]), "r"(seed)); a[i] = d; }  // IDP.4A
+            if (OP == 15) { int d; asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a[i]), "r"(a[(i + 1) & 7]), "r"(seed)); a[i] = d; }  // IDP.2A
+            if (OP == 16) {                                                   // IDP.4A + LOP3 interleaved
+                if (i & 1) { int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a[i]), "r"(a[(i + 1) & 7]), "r"(seed)); a[i] = d; }
+                else a[i] = (a[i] ^ seed) & a[(i + 1) & 7];
+            }
             if (OP == 9) {                                                    // IMAD (fma pipe) + LOP3 (alu pipe) interleaved
                 if (i & 1) a[i] = a[i] * seed + a[(i + 1) & 7];
                 else a[i] = (a[i] ^ seed) & a[(i + 1) & 7];
@@ -94,6 +100,9 @@ int main() {
     run<11>("vabsdiff4.u8.acc", 1, d);
     run<12>("vabsdiff4|lop3 interleaved", 1, d);
     run<13>("xor,csa(2 lop3),popc,iadd", 5, d);
+    run<14>("idp.4a", 1, d);
+    run<15>("idp.2a", 1, d);
+    run<16>("idp.4a|lop3 interleaved", 1, d);
     int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
