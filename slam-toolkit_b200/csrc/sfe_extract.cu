@@ -694,22 +694,40 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return min(max(i, 0), n - 1);  // only reached by halo pixels of outputs outside the image
 }
 
+__device__ __forceinline__ uint32_t dp4a_u8u8(uint32_t a, uint32_t b, uint32_t c) {  // c + sum_k a.byte[k] * b.byte[k]
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {  // c + a.lo16 * b.byte0 + a.hi16 * b.byte1
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {  // c + a.lo16 * b.byte2 + a.hi16 * b.byte3
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // Tile = 128 x 32 outputs, Q8 kernel [18 34 48 56 48 34 18]; sums are exact integers, the only rounding is
 // the final (v + 2^15) >> 16, exactly cv::GaussianBlur's fixed-point path.
 //   load        (32+6) rows x 36 words (x0-4 .. x0+139) into shared memory.  kTma: one TMA box issued by
 //               thread 0, out-of-image bytes arrive as zeros and the tiles on the image border rebuild their
 //               BORDER_REFLECT_101 halo from the tile itself; otherwise aligned global words (one 32-bit store
 //               per 4 px), border words assembled byte by byte
-//   horizontal  4 outputs per thread from three shared words, two outputs per register in 16x2 lanes
-//               (a lane never exceeds 255 * 256 = 65280)
-//   vertical    one column pair x 8 rows per thread: 14 packed words unpacked once, 7 multiply-adds per
-//               output with the rounding constant folded in, result bytes picked with one PRMT
+//   horizontal  4 outputs x 2 rows per thread from three shared words per row: two IDP.4A per output on byte-shifted
+//               windows (PRMT); the two rows' sums of a column are packed into one word (a sum never exceeds
+//               255 * 256 = 65280)
+//   vertical    4 columns x 4 rows per thread: four IDP.2A per output on the row pairs, the rounding constant
+//               folded into the first, result bytes picked with PRMT, one 32-bit store per row
 template <bool kTma>
 __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__restrict__ tiles,
                                                    const __grid_constant__ TmaMaps M) {
-    constexpr int IH = kBlurTileH + 6, IWW = kBlurInWords, HW = kBlurTileW / 2;
+    constexpr int IH = kBlurTileH + 6, IWW = kBlurInWords;
+    static_assert(IH % 2 == 0 && kBlurTileW == 128 && kBlurTileH == 32, "the blur passes pair rows and map 32 x 8 threads onto the tile");
     __shared__ __align__(128) uint32_t in32[IH * IWW];
-    __shared__ __align__(16) uint32_t hb[IH * HW];  // horizontal sums, two u16 per word
+    __shared__ __align__(16) uint32_t hb[(IH / 2) * kBlurTileW];  // horizontal sums: word = (row 2p, row 2p + 1) of one column, u16 each
     __shared__ uint64_t bar;
     const TilePlan t = tiles[blockIdx.x];
     const int img = blockIdx.y, tid = threadIdx.x, l = t.level;
@@ -771,42 +789,54 @@ __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__r
         }
         __syncthreads();
     }
-    // horizontal: item = (row r, group g of 4 outputs); input bytes b[0..11] = the three words from output column
-    // 4g - 4 on, tap i of output k = b[k+i+1]
-    for (int it = tid; it < IH * (kBlurTileW / 4); it += 256) {
-        const int r = it >> 5, g = it & 31;
-        const uint32_t *wp = &in32[r * IWW + g + (kBlurLead / 4 - 1)];
-        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-        const uint32_t e0 = __byte_perm(w0, 0, 0x4140), e1 = __byte_perm(w0, 0, 0x4342), e2 = __byte_perm(w1, 0, 0x4140),
-                       e3 = __byte_perm(w1, 0, 0x4342), e4 = __byte_perm(w2, 0, 0x4140), e5 = __byte_perm(w2, 0, 0x4342);
-        const uint32_t o0 = __byte_perm(e0, e1, 0x5432), o1 = __byte_perm(e1, e2, 0x5432), o2 = __byte_perm(e2, e3, 0x5432),
-                       o3 = __byte_perm(e3, e4, 0x5432), o4 = __byte_perm(e4, e5, 0x5432);
-        // pairs (b[i+1], b[i+2]) for i = 0..8: o0 e1 o1 e2 o2 e3 o3 e4 o4
-        const uint32_t h01 = 18u * (o0 + o3) + 34u * (e1 + e3) + 48u * (o1 + o2) + 56u * e2;
-        const uint32_t h23 = 18u * (o1 + o4) + 34u * (e2 + e4) + 48u * (o2 + o3) + 56u * e3;
-        *(uint2 *)&hb[r * HW + 2 * g] = make_uint2(h01, h23);
+    // horizontal: item = (row pair rp, group g of 4 outputs).  Output k of a row = taps on bytes 4g+k-3 .. 4g+k+3 = one
+    // IDP.4A over the byte window starting at 4g+k-3 (taps 0..3) + one over the window at 4g+k+1 (taps 4..6); the
+    // windows are byte shifts of three consecutive words.  The two rows' sums of a column share a word (u16 each, a sum
+    // never exceeds 255 * 256), which is the operand layout IDP.2A wants for the vertical pass.
+    constexpr uint32_t kTapLo = 18u | 34u << 8 | 48u << 16 | 56u << 24, kTapHi = 48u | 34u << 8 | 18u << 16;
+    for (int it = tid; it < (IH / 2) * (kBlurTileW / 4); it += 256) {
+        const int rp = it >> 5, g = it & 31;
+        uint32_t hsum[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const uint32_t *wp = &in32[(2 * rp + q) * IWW + g + (kBlurLead / 4 - 1)];
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            hsum[q][0] = dp4a_u8u8(__byte_perm(w0, w1, 0x4321), kTapLo, dp4a_u8u8(__byte_perm(w1, w2, 0x4321), kTapHi, 0));
+            hsum[q][1] = dp4a_u8u8(__byte_perm(w0, w1, 0x5432), kTapLo, dp4a_u8u8(__byte_perm(w1, w2, 0x5432), kTapHi, 0));
+            hsum[q][2] = dp4a_u8u8(__byte_perm(w0, w1, 0x6543), kTapLo, dp4a_u8u8(__byte_perm(w1, w2, 0x6543), kTapHi, 0));
+            hsum[q][3] = dp4a_u8u8(w1, kTapLo, dp4a_u8u8(w2, kTapHi, 0));
+        }
+        *(uint4 *)&hb[rp * kBlurTileW + 4 * g] =
+            make_uint4(__byte_perm(hsum[0][0], hsum[1][0], 0x5410), __byte_perm(hsum[0][1], hsum[1][1], 0x5410),
+                       __byte_perm(hsum[0][2], hsum[1][2], 0x5410), __byte_perm(hsum[0][3], hsum[1][3], 0x5410));
     }
     __syncthreads();
-    // vertical: thread = (column pair cw, strip of 8 output rows)
+    // vertical: thread = (4 columns, strip of 4 output rows).  Output row k taps tile rows k .. k+6; with the rows paired
+    // (2p, 2p+1) that is four IDP.2A per pixel, the pair coefficients depending on the parity of k.
     uint8_t *dst = S.blur + (size_t)slot * S.blur_stride + L.blur_off;
-    const int cw = tid & 63, r0 = (tid >> 6) * 8;
-    const int gx = t.x0 + 2 * cw;
+    const int cg = tid & 31, r0 = (tid >> 5) * 4;  // r0 is even: the strip starts on a pair
+    const int gx = t.x0 + 4 * cg;
     if (gx >= w) return;
-    uint32_t lo[14], hi[14];
+    uint4 pr[5];  // pairs r0/2 .. r0/2 + 4 = tile rows r0 .. r0 + 9, four columns each
 #pragma unroll
-    for (int k = 0; k < 14; k++) {
-        const uint32_t v = hb[(r0 + k) * HW + cw];
-        lo[k] = v & 0xFFFF;
-        hi[k] = v >> 16;
-    }
+    for (int p = 0; p < 5; p++) pr[p] = *(const uint4 *)&hb[(r0 / 2 + p) * kBlurTileW + 4 * cg];
+    constexpr uint32_t kEvenA = 18u | 34u << 8 | 48u << 16 | 56u << 24, kEvenB = 48u | 34u << 8 | 18u << 16;   // (c0 c1)(c2 c3) (c4 c5)(c6 0)
+    constexpr uint32_t kOddA = 18u << 8 | 34u << 16 | 48u << 24, kOddB = 56u | 48u << 8 | 34u << 16 | 18u << 24;  // (0 c0)(c1 c2) (c3 c4)(c5 c6)
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 4; k++) {
         const int gy = t.y0 + r0 + k;
-        if (gy >= L.h) break;
-        const uint32_t a = 18u * (lo[k] + lo[k + 6]) + 34u * (lo[k + 1] + lo[k + 5]) + 48u * (lo[k + 2] + lo[k + 4]) + (56u * lo[k + 3] + 32768u);
-        const uint32_t b = 18u * (hi[k] + hi[k + 6]) + 34u * (hi[k + 1] + hi[k + 5]) + 48u * (hi[k + 2] + hi[k + 4]) + (56u * hi[k + 3] + 32768u);
+        if (gy >= h) break;
+        const int p = k >> 1;
+        uint32_t v[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint32_t a0 = (&pr[p].x)[c], a1 = (&pr[p + 1].x)[c], a2 = (&pr[p + 2].x)[c], a3 = (&pr[p + 3].x)[c];
+            v[c] = (k & 1) ? dp2a_hi(a3, kOddB, dp2a_lo(a2, kOddB, dp2a_hi(a1, kOddA, dp2a_lo(a0, kOddA, 32768u))))
+                           : dp2a_hi(a3, kEvenB, dp2a_lo(a2, kEvenB, dp2a_hi(a1, kEvenA, dp2a_lo(a0, kEvenA, 32768u))));
+        }
         // (v + 2^15) >> 16 <= 255 is byte 2 of each sum
-        *(uint16_t *)(dst + (size_t)gy * L.blur_pitch + gx) = (uint16_t)__byte_perm(a, b, 0x0062);  // pitch, gx even; pad absorbs an odd tail
+        *(uint32_t *)(dst + (size_t)gy * L.blur_pitch + gx) =
+            __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);  // pitch, gx multiples of 4
     }
 }
 
@@ -1772,7 +1802,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release();
     ex->d_tiles.release(); ex->d_segs.release(); ex->d_xtab.release(); ex->d_ytab.release();
     ex->d_kps.release(); ex->d_nout.release(); ex->d_sidx.release(); ex->d_sdist.release(); ex->d_tidx.release(); ex->d_tdist.release();
-    ex->track.cell_start.release(); ex->track.order.release(); ex->track.sxy.release(); ex->track.sdesc.release(); ex->track.best.release();
+    ex->track.cell_start.release(); ex->track.order.release(); ex->track.valid.release(); ex->track.sxy.release(); ex->track.sdesc.release(); ex->track.best.release();
     for (int i = 0; i <= kNumStages; i++)
         if (ex->prof_ev[i]) cudaEventDestroy(ex->prof_ev[i]);
     for (int i = 0; i < kMaxChunks; i++) {

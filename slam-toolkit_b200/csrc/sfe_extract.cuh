@@ -131,7 +131,7 @@ void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoin
 // sequence tracking launch (sfe_match.cu), used by sfe_stereo_sequence on the extractor's stream: per-frame bucket grids,
 // GetDepth + ProjectionMatch of frame f-1's stereo points into frame f, decode.  3 launches.
 struct TrackScratch {
-    DevBuf<int> cell_start, order;
+    DevBuf<int> cell_start, order, valid;
     DevBuf<double2> sxy;
     DevBuf<uint4> sdesc;
     DevBuf<unsigned long long> best;

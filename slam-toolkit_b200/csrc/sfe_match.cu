@@ -556,6 +556,8 @@ struct TrackArrays {
     int *order;       // frames x cap
     double2 *sxy;     // frames x cap
     uint4 *sdesc;     // frames x 2 cap
+    int *valid;       // frames x cap: the frame's keypoints that have a stereo correspondence (any order)
+    int *n_valid;     // frames
 };
 
 __device__ __forceinline__ KpGrid track_grid(const TrackArrays &A, int f) {
@@ -576,7 +578,9 @@ __global__ void __launch_bounds__(256) track_grids_kernel(TrackArrays A) {
     const int f = blockIdx.x, tid = threadIdx.x, cells = A.gw * A.gh;
     int *start = tg_smem, *fill = tg_smem + cells + 1;
     __shared__ int chunk_sum[256];
+    __shared__ int nv;
     const KpGrid G = track_grid(A, f);
+    if (tid == 0) nv = 0;
     const sfe_keypoint *kps = A.kl + (size_t)f * A.cap;
     for (int c = tid; c <= cells; c += 256) start[c] = 0;
     __syncthreads();
@@ -615,15 +619,28 @@ __global__ void __launch_bounds__(256) track_grids_kernel(TrackArrays A) {
         G.sdesc[2 * t] = __ldg(d);
         G.sdesc[2 * t + 1] = __ldg(d + 1);
     }
+    // the keypoints that will be projected into the next frame, compacted so that the matcher's warps are full
+    const int32_t *sidx = A.sidx + (size_t)f * A.cap;
+    int *valid = A.valid + (size_t)f * A.cap;
+    for (int j0 = 0; j0 < G.m; j0 += 256) {
+        const int j = j0 + tid;
+        const bool ok = j < G.m && sidx[j] >= 0;
+        const uint32_t b = __ballot_sync(0xffffffffu, ok);
+        int base = 0;
+        if ((tid & 31) == 0 && b) base = atomicAdd(&nv, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (ok) valid[base + __popc(b & ((1u << (tid & 31)) - 1))] = j;
+    }
+    __syncthreads();
+    if (tid == 0) A.n_valid[f] = nv;
 }
 
 // thread = keypoint i of frame f - 1 (f = blockIdx.y + 1): GetDepth, then ProjectionMatch into frame f
 __global__ void __launch_bounds__(128) track_match_kernel(TrackArrays A, ProjParams P, double baseline,
                                                           unsigned long long *__restrict__ best) {
-    const int f = blockIdx.y + 1, prev = f - 1, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= min(A.nl[prev], A.cap)) return;
-    const int j = A.sidx[(size_t)prev * A.cap + i];
-    if (j < 0) return;  // no stereo correspondence: no depth, no map point
+    const int f = blockIdx.y + 1, prev = f - 1, e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.n_valid[prev]) return;  // keypoints without a stereo correspondence have no depth, hence no map point
+    const int i = A.valid[(size_t)prev * A.cap + e], j = A.sidx[(size_t)prev * A.cap + i];
     const sfe_keypoint kp = A.kl[(size_t)prev * A.cap + i];
     const double dx = (double)__fsub_rn(kp.x, A.kr[(size_t)prev * A.cap + j].x);  // :398, float difference
     if (dx < 0.) return;  // the reference throws (:399-402); StereoMatch never lets this through
@@ -742,8 +759,10 @@ int launch_track_frames(cudaStream_t st, int device, TrackScratch &T, int frames
     SFE_REQUIRE(smem <= 200 * 1024, SFE_ERR_UNSUPPORTED, "camera image too large for the per-frame bucket grid");
     SFE_CUDA(T.cell_start.ensure((size_t)frames * (cells + 1)));
     SFE_CUDA(T.order.ensure(fc)); SFE_CUDA(T.sxy.ensure(fc)); SFE_CUDA(T.sdesc.ensure(2 * fc)); SFE_CUDA(T.best.ensure(fc));
+    SFE_CUDA(T.valid.ensure(fc + frames));
     A.kl = kl; A.kr = kr; A.dl = dl; A.nl = nl; A.sidx = sidx;
     A.cell_start = T.cell_start.p; A.order = T.order.p; A.sxy = T.sxy.p; A.sdesc = T.sdesc.p;
+    A.valid = T.valid.p; A.n_valid = T.valid.p + fc;
     if (smem > 48 * 1024) {  // per-function opt-in limit: only ever raise it
         static std::mutex mu;
         static size_t granted[64] = {};
