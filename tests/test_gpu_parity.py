@@ -101,6 +101,31 @@ def test_fallback_threshold_cells(gpu, oracle):
     assert np.array_equal(k, rk) and np.array_equal(d, rd)
 
 
+def test_fast_segments_mixed_retry_noise_and_high_thresholds(gpu, oracle):
+    """FAST by segments: a segment whose cells partly retry at minThFAST (the neighbours must not see each other's scores),
+    a noise image where most pixels survive the compass pre-test (list capacity = every tested pixel), cells 32 px wide
+    (3 cells per segment) and thresholds above 127 (the VABSDIFF4 pre-test clamps its threshold there)."""
+    img, _ = synth.stereo_pair(9, 500, 230)
+    mixed = img.copy()
+    mixed[:, 130:330] = (96 + (mixed[:, 130:330].astype(np.int32) - 96) // 4).astype(np.uint8)   # low-contrast stripe: retry cells
+    rng = np.random.default_rng(5)
+    noise = np.clip(rng.normal(128, 22, (230, 500)), 0, 255).astype(np.uint8)
+    contrast = ((img.astype(np.int32) > 110) * 255).astype(np.uint8)
+    for name, im, prm in (("mixed", mixed, (600, 1.2, 4, 20, 7)), ("noise", noise, (400, 1.2, 3, 20, 7)),
+                          ("wide cells", img[:, :470], (500, 1.25, 4, 20, 7)), ("t>127", contrast, (300, 1.2, 3, 150, 130)),
+                          ("ini<min", img, (300, 1.2, 3, 10, 25))):
+        ex = api.ORBextractor(*prm)
+        ref = oracle.Extractor(*prm)
+        rk, rd = ref.extract(np.ascontiguousarray(im))
+        k, d = ex.extract(np.ascontiguousarray(im))
+        bad = _stage_report(ex, ref, 0, prm[2])
+        assert not bad, (name, bad)
+        assert np.array_equal(k, rk) and np.array_equal(d, rd), name
+        assert len(rk) > 20, (name, len(rk))
+    rk, _ = oracle.Extractor(600, 1.2, 4, 20, 7).extract(mixed)
+    assert (rk["response"] < 20).any() and (rk["response"] >= 20).any()
+
+
 def test_batch_equals_single(kitti_ex, oracle):
     imgs = np.stack([synth.stereo_pair(s)[i] for s in (4, 5) for i in (0, 1)])
     kps, desc, n = kitti_ex.extract_batch(imgs)
@@ -318,6 +343,19 @@ def test_stereo_match_random_and_edges(gpu, oracle):
         idx, dist = m.StereoMatch(_mk_kps(xyl), dl, _mk_kps(xyr), dr)
         ri, rd = oracle.stereo_match(_mk_kps(xyl), dl, _mk_kps(xyr), dr)
         assert np.array_equal(idx, ri) and np.array_equal(dist, rd), n
+    # coordinates far beyond the bucket grid (clamped buckets), wide dx / dy windows, > 2048 right keypoints (chunks)
+    for n, span, sp in ((3000, (5000, 3000), api.StereoParams(10.0, 500.0, 0.8)), (700, (300, 2500), api.StereoParams(0.0, 3.0, 0.5)),
+                        (500, (4000, 40), api.StereoParams(3.0, 5000.0, 0.9))):
+        xyr = np.stack([rng.uniform(-20, span[0], n), rng.integers(-5, span[1], n) * 1.0], 1).astype(np.float32)
+        dr = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        sel = rng.integers(0, n, n)
+        xyl = xyr[sel] + np.stack([rng.uniform(-5, sp.max_dx * 1.1, n), rng.integers(-12, 13, n) * 1.0], 1).astype(np.float32)
+        dl = dr[sel] ^ (rng.integers(0, 256, (n, 32), dtype=np.uint8) & rng.integers(0, 256, (n, 32), dtype=np.uint8)
+                        & rng.integers(0, 256, (n, 32), dtype=np.uint8))
+        idx, dist = m.StereoMatch(_mk_kps(xyl), dl, _mk_kps(xyr), dr, sp)
+        ri, rd = oracle.stereo_match(_mk_kps(xyl), dl, _mk_kps(xyr), dr, sp.y_threshold, sp.max_dx, sp.best12_threshold)
+        assert np.array_equal(idx, ri) and np.array_equal(dist, rd), (n, span)
+        assert (ri >= 0).sum() > 10
     d = np.zeros((3, 32), np.uint8)
     d[1, 0] = 0xFF
     kl = _mk_kps(np.array([[50.0, 10.0]], np.float32))
