@@ -472,12 +472,22 @@ def main():
     achieved = alg_bytes[top] / (top_ms / 1e3) / 1e9 if top_ms > 0 else 0.0
     # DRAM traffic of that kernel per launch from the committed ncu --set full capture (dram__bytes_read + write, per image
     # there, scaled to this run's images per launch); well above the algorithmic bytes would mean wasted re-reads
-    traffic, traffic_src = None, None
+    traffic, traffic_src, issue = None, None, None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json")))
-        per_img = tj["kernels"][top]["dram_bytes_per_image"]
-        traffic = per_img * (F if top == "stereo_match" else 2 * F) / launches_per_step[top]
+        units = F if top in ("stereo_match", "track") else 2 * F
+        traffic = tj["kernels"][top]["dram_bytes_per_image"] * units / launches_per_step[top]
         traffic_src = tj["source"]
+        # the pipe that actually binds extraction: warp instructions of the kernel (ncu smsp__inst_executed.sum of the same
+        # committed capture, per image) over its live CUDA-event time, against the issue peak 4 per clk per SM at the
+        # sampled SM clock
+        winst = tj["kernels"][top].get("warp_instructions_per_image", 0) * units / launches_per_step[top]
+        clk = (sampler.summary() or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        sms = 148
+        if winst > 0 and top_ms > 0:
+            issue = {"warp_instructions_per_launch": winst, "achieved_gwarp_inst_per_s": winst / (top_ms / 1e3) / 1e9,
+                     "peak_gwarp_inst_per_s": 4 * sms * clk * 1e6 / 1e9, "sm_clock_mhz": clk}
+            issue["frac"] = issue["achieved_gwarp_inst_per_s"] / issue["peak_gwarp_inst_per_s"]
     except Exception:
         pass
     line = {"metric": "orb_extract_match_stereo_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -494,7 +504,9 @@ def main():
                          "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg_bytes[top], "peak_source": peak_src,
                          "whole_step_achieved": value / world * B_FRAME / 1e9, "whole_step_frac": value / world * B_FRAME / 1e9 / hbm_peak,
-                         "note": "extraction is integer-issue bound, not HBM bound (SURVEY.md §8d): see profiles/ for pipe utilisation"},
+                         "issue": issue,
+                         "note": "extraction is integer-issue bound, not HBM bound (SURVEY.md §8d): `issue` = the kernel's warp "
+                                 "instructions over its live time against 4 issues/clk/SM; profiles/ holds the pipe utilisation"},
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
             "keypoints_per_frame": n_kps / F, "matches_per_s": value * n_match / F,
             "stereo_matches_per_frame": n_stereo / F, "tracked_matches_per_frame": n_track / F}

@@ -18,6 +18,23 @@ __device__ __forceinline__ uint32_t ldg_word_at(const uint8_t *p) {
     return __funnelshift_r(__ldg(w), __ldg(w + 1), (uint32_t)(a & 3) * 8);
 }
 
+// integer dot products (IDP.4A / IDP.2A: full rate, on the FMA pipe beside the ALU's LOP3 / PRMT -- tools/microbench.cu)
+__device__ __forceinline__ uint32_t dp4a_u8u8(uint32_t a, uint32_t b, uint32_t c) {  // c + sum_k a.byte[k] * b.byte[k]
+    uint32_t d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {  // c + a.lo16 * b.byte0 + a.hi16 * b.byte1
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {  // c + a.lo16 * b.byte2 + a.hi16 * b.byte3
+    uint32_t d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // ---------------------------------------------------------------------------------------------
 // level-0 staging: images as the host holds them (tight rows) -> rows pitched to 16 bytes, the layout TMA
 // can describe.  One thread = one 16-byte chunk of a destination row.
@@ -54,6 +71,7 @@ struct PyrStep {            // geometry of one resize launch, in the kernel para
     int src_w, src_pitch, src_plane_off, src_is_input;
     int xtab_off, ytab_off;
     int src_level, box_w, box_h;     // TMA variant: source level and its box
+    int wide_h;                      // TMA variant: 4 outputs per thread in the horizontal pass (their sources span <= 7 px)
 };
 
 // kTma: the source pixels of the tile (box P.box_w x P.box_h bytes, origin on the 16-byte grid of the source row)
@@ -84,7 +102,29 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, co
         const uint2 xt = __ldg(&xtab[P.xtab_off + min(x0 + ox, P.w - 1)]);
         const int sx = xt.x, d1 = min(sx + 1, P.src_w - 1) - sx;
         const uint32_t w0 = xt.y & 0xFFFF, w1 = xt.y >> 16;
-        if (kTma) {
+        if (kTma && P.wide_h) {
+            // thread = 4 adjacent output columns: their source pixels lie within 8 bytes of the first one's (host-checked),
+            // so three aligned words realigned by two funnel shifts hold all four (S[sx], S[sx + 1]) pairs; a PRMT per
+            // output puts its pair into the low bytes and one IDP.2A forms S[sx] * w0 + S[sx + 1] * w1 (the table packs
+            // w0 | w1 << 16).  At the right border w1 = 0, so whatever byte follows the last column is harmless.
+            const int g4 = (tid & 15) * 4, gi = P.xtab_off + min(x0 + g4, (P.w - 1) & ~3);  // the table is padded to whole groups
+            const uint4 ta = __ldg((const uint4 *)&xtab[gi]), tb = __ldg((const uint4 *)&xtab[gi + 2]);
+            const int o0 = (int)ta.x - xa;
+            const uint32_t sh8 = (uint32_t)(o0 & 3) * 8;
+            const uint32_t r1 = ta.z - ta.x, r2 = tb.x - ta.x, r3 = tb.z - ta.x;
+            const uint32_t s0 = 0x10u, s1 = r1 | (r1 + 1) << 4, s2 = r2 | (r2 + 1) << 4, s3 = r3 | (r3 + 1) << 4;
+            __syncthreads();  // barrier initialised
+            mbar_wait(&bar, 0);
+            const uint32_t *p = (const uint32_t *)pyr_smem + (tid >> 4) * (P.box_w >> 2) + (o0 >> 2);
+            const int step = 16 * (P.box_w >> 2);
+            for (int r = tid >> 4; r < n_rows; r += 16) {
+                const uint32_t a = __funnelshift_r(p[0], p[1], sh8), b = __funnelshift_r(p[1], p[2], sh8);
+                const uint32_t u0 = dp2a_lo(ta.y, __byte_perm(a, b, s0), 0) >> 4, u1 = dp2a_lo(ta.w, __byte_perm(a, b, s1), 0) >> 4;
+                const uint32_t u2 = dp2a_lo(tb.y, __byte_perm(a, b, s2), 0) >> 4, u3 = dp2a_lo(tb.w, __byte_perm(a, b, s3), 0) >> 4;
+                *(uint2 *)&pyr_u[r * kPyrTileW + g4] = make_uint2(u0 | u1 << 16, u2 | u3 << 16);
+                p += step;
+            }
+        } else if (kTma) {
             __syncthreads();  // barrier initialised
             mbar_wait(&bar, 0);
             const uint8_t *p = pyr_smem + (tid >> 6) * P.box_w + (sx - xa);
@@ -124,7 +164,7 @@ __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, co
         const uint32_t b[4] = {B.x & 0xFFFF, B.x >> 16, B.y & 0xFFFF, B.y >> 16};
         uint32_t v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = min((__umulhi(b0, a[i]) + __umulhi(b1, b[i]) + 2) >> 2, 255u);
+        for (int i = 0; i < 4; i++) v[i] = (__umulhi(b0, a[i]) + __umulhi(b1, b[i]) + 2) >> 2;  // <= (2048 * 32640 >> 16) + 2 >> 2 = 255
         *(uint32_t *)(dst + (size_t)oy * P.pitch) = v[0] | v[1] << 8 | v[2] << 16 | v[3] << 24;  // pitch % 16 == 0: pad absorbs the tail
     }
 }
@@ -694,22 +734,6 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return min(max(i, 0), n - 1);  // only reached by halo pixels of outputs outside the image
 }
 
-__device__ __forceinline__ uint32_t dp4a_u8u8(uint32_t a, uint32_t b, uint32_t c) {  // c + sum_k a.byte[k] * b.byte[k]
-    uint32_t d;
-    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t dp2a_lo(uint32_t a, uint32_t b, uint32_t c) {  // c + a.lo16 * b.byte0 + a.hi16 * b.byte1
-    uint32_t d;
-    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-__device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) {  // c + a.lo16 * b.byte2 + a.hi16 * b.byte3
-    uint32_t d;
-    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-    return d;
-}
-
 // Tile = 128 x 32 outputs, Q8 kernel [18 34 48 56 48 34 18]; sums are exact integers, the only rounding is
 // the final (v + 2^15) >> 16, exactly cv::GaussianBlur's fixed-point path.
 //   load        (32+6) rows x 36 words (x0-4 .. x0+139) into shared memory.  kTma: one TMA box issued by
@@ -1101,6 +1125,7 @@ struct sfe_extractor {
     std::vector<SegRec> segs;
     DevBuf<SegRec> d_segs;
     size_t fast_smem = 0, pyr_smem = 0;
+    int pyr_wide_h[kMaxLevels] = {};
     std::vector<TilePlan> tiles;
     size_t pyr_stride = 0, blur_stride = 0;
     int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0, out_cap = 0;
@@ -1283,6 +1308,10 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                 xtab.push_back(make_uint2((unsigned)sx, (unsigned)w0 | (unsigned)w1 << 16));
             }
             while (xtab.size() % 4) xtab.push_back(xtab.back());
+            // 4-outputs-per-thread horizontal pass: the 4 source pairs of every aligned group must fit 8 bytes
+            ex->pyr_wide_h[l] = 1;
+            for (int gx = 0; gx < L.w; gx += 4)
+                if (xtab[L.xtab_off + gx + 3].x - xtab[L.xtab_off + gx].x > 6) ex->pyr_wide_h[l] = 0;
             for (int dy = 0; dy < L.h; dy++) {
                 float fy = (float)((dy + 0.5) * scale_y - 0.5);
                 int sy = (int)floorf(fy);
@@ -1482,7 +1511,7 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     for (int l = 1; l < nl; l++) {
         const LevelPlan &D = ex->lv[l], &Q = ex->lv[l - 1];
         const PyrStep P{D.w, D.h, D.pitch, D.plane_off, Q.w, l == 1 ? S.in_pitch : Q.pitch, Q.plane_off, l == 1, D.xtab_off, D.ytab_off,
-                        l - 1, ex->pyr_box_w, ex->pyr_box_h};
+                        l - 1, ex->pyr_box_w, ex->pyr_box_h, ex->pyr_wide_h[l]};
         dim3 grid(div_up(D.w, kPyrTileW), div_up(D.h, kPyrTileH), count);
         if (ex->tma_now)
             pyr_resize_kernel<true><<<grid, 256, ex->pyr_smem + (size_t)ex->pyr_box_w * ex->pyr_box_h, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p, ex->pyr_maps);

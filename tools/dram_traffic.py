@@ -11,9 +11,11 @@ import sys
 
 src, images, frames = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 stage_of = {"pyr_resize_kernel": "pyramid", "fast_segments_kernel": "fast_cells", "octree_kernel": "quadtree",
-            "blur_kernel": "blur", "orient_describe_kernel": "orient_describe", "stereo_match_kernel": "stereo_match"}
+            "blur_kernel": "blur", "orient_describe_kernel": "orient_describe", "stereo_match_kernel": "stereo_match",
+            "track_grids_kernel": "track", "track_match_kernel": "track", "projection_decode_kernel": "track"}
+per_frame = ("stereo_match", "track")   # these stages run once per stereo frame, the others once per image
 unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-acc, launches, cur = {}, {}, None
+acc, inst, launches, cur = {}, {}, {}, None
 for line in open(src):
     m = re.match(r"== launch \d+: (?:void )?(\w+)", line)
     if m:
@@ -24,9 +26,14 @@ for line in open(src):
     m = re.match(r"dram__bytes_(read|write)\.sum\s+([\d.]+)\s+(\w+)", line)
     if m and cur:
         acc[cur] = acc.get(cur, 0.0) + float(m.group(2)) * unit[m.group(3)]
+    m = re.match(r"smsp__inst_executed\.sum\s+([\d.]+)", line)
+    if m and cur:
+        inst[cur] = inst.get(cur, 0.0) + float(m.group(1))
 out = {"source": f"{src} (ncu --set full, {images} images per launch, dram__bytes_read.sum + dram__bytes_write.sum; pyramid = sum over "
-                 f"its launches; stereo_match is per image of a {frames}-frame batch)",
-       "kernels": {k: {"dram_bytes_per_image": int(round(v / (frames if k == "stereo_match" else images))), "launches": launches[k]}
+                 f"its launches; stereo_match and track are per frame of a {frames}-frame batch; warp_instructions = smsp__inst_executed.sum)",
+       "kernels": {k: {"dram_bytes_per_image": int(round(v / (frames if k in per_frame else images))),
+                       "warp_instructions_per_image": int(round(inst.get(k, 0.0) / (frames if k in per_frame else images))),
+                       "launches": launches[k]}
                    for k, v in acc.items()}}
 json.dump(out, open("profiles/dram_traffic.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
