@@ -44,12 +44,13 @@ def ncu(args):
 
 def main():
     rep = sys.argv[1]
-    print(sys.argv[2] if len(sys.argv) > 2 else rep)
+    drop = int(sys.argv[3]) if len(sys.argv) > 3 else 0   # leading launches of the report to leave out (a window that
+    print(sys.argv[2] if len(sys.argv) > 2 else rep)      # starts in the middle of a step)
     rows = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     hdr, units = rows[0], rows[1]
     kcol = hdr.index("Kernel Name")
     names = []
-    for r in rows[2:]:
+    for r in rows[2 + drop:]:
         name = r[kcol].split("(")[0]
         names.append(name)
         print(f"\n== launch {r[0]}: {r[kcol]}")
