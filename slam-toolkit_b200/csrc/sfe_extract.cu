@@ -331,8 +331,16 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) fast_segments_ke
                 if (corner0) score[((yx0 >> 8) + 1) * SP + (yx0 & 255) + 1] = (uint8_t)best0;
                 if (corner1) score[((yx1 >> 8) + 1) * SP + (yx1 & 255) + 1] = (uint8_t)best1;
             }
-            if (corner0) det[atomicAdd(&n_det, 1)] = yx0;
-            if (corner1) det[atomicAdd(&n_det, 1)] = yx1;
+            // one shared-memory atomic per warp reserves the slots of both corner flags
+            const uint32_t c0 = __ballot_sync(0xffffffffu, corner0), c1 = __ballot_sync(0xffffffffu, corner1);
+            if (c0 | c1) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&n_det, __popc(c0) + __popc(c1));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t lt = (1u << lane) - 1;
+                if (corner0) det[base + __popc(c0 & lt)] = yx0;
+                if (corner1) det[base + __popc(c0) + __popc(c1 & lt)] = yx1;
+            }
         }
         __syncthreads();
         // stage 2: non-max suppression; a neighbour in another cell counts as 0 (the reference runs cv::FAST per cell).
@@ -370,9 +378,8 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) fast_segments_ke
             }
         }
         __syncthreads();
-        uint32_t retry = 0;  // :811-816: cells of this pass where nothing survived
-        for (int c = 0; c < n_cells; c++)
-            if (((todo >> c) & 1) && cell_surv[c] == 0) retry |= 1u << c;
+        // :811-816: cells of this pass where nothing survived (lane c looks at cell c; every warp forms the same mask)
+        const uint32_t retry = __ballot_sync(0xffffffffu, lane < n_cells && ((todo >> lane) & 1) && cell_surv[min(lane, kFastMaxCells - 1)] == 0);
         if (retry == 0 || P.min_th >= t) break;  // a higher threshold cannot find what the lower one did not
         t = P.min_th;
         todo = retry;
