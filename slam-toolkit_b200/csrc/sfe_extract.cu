@@ -3,6 +3,8 @@
 // reference src/orb_extractor.cpp:410-853,1034-1132 bit-for-bit under the canonical rules of
 // oracle/orb_oracle.h.  Compiled with -fmad=false: every float op is individually rounded, as
 // in the reference build (no -march => no FMA, CMakeLists.txt:54-55).
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <cmath>
 #include <mutex>
@@ -954,13 +956,13 @@ static_assert(pattern_within_patch(), "a rotated pattern point could round outsi
 constexpr int kKpPerWarp = 4;  // keypoints one warp handles in turn: the pattern / disc table set-up is paid once
 
 __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSet O) {
-    __shared__ float2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane`, as floats
+    __shared__ __half2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane` (|x|, |y| <= 13: exact in fp16)
     __shared__ uint32_t patch_all[8][kPatchRows * kPatchWords];  // per warp: the blurred window the pattern can reach
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y, slot = slot_of(S, img);
     uint32_t *patch = patch_all[warp];
     for (int i = tid; i < 512; i += 256) {
         const int byte = i >> 4, s = i & 15;
-        pat[s * 32 + byte] = make_float2((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
+        pat[s * 32 + byte] = __floats2half2_rn((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
     }
     // IC_Angle: the 31 x 32-byte window is 31 rows x 8 words; lane = word (lane & 7) of rows (lane >> 3) + 4 t,
     // t = 0..7, so one warp-wide load touches 4 rows (4-8 cache lines).  The lane's weights stay in registers.
@@ -1056,7 +1058,7 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
             int tv[2];
 #pragma unroll
             for (int s = 0; s < 2; s++) {
-                const float2 pp = pat[(2 * k + s) * 32 + lane];
+                const float2 pp = __half22float2(pat[(2 * k + s) * 32 + lane]);
                 const int ry = __float2int_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)));
                 const int rx = __float2int_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)));
                 tv[s] = pc[ry * (kPatchWords * 4) + rx];
