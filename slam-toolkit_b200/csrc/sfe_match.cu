@@ -210,16 +210,41 @@ __global__ void grid_count_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps
     if (j < G.m) atomicAdd(&G.cell_start[grid_cell(G, kps[j].x, kps[j].y) + 1], 1);
 }
 
-__global__ void grid_scan_kernel(KpGrid G) {  // one CTA; the grid has a few hundred cells
-    const int n = G.gw * G.gh;
-    if (threadIdx.x == 0) {
-        int acc = 0;
-        for (int i = 0; i <= n; i++) {
-            acc += G.cell_start[i];
-            G.cell_start[i] = acc;
+__global__ void __launch_bounds__(256) grid_scan_kernel(KpGrid G) {  // one CTA: inclusive scan of cell_start[0 .. cells]
+    __shared__ int chunk_sum[256];
+    const int n = G.gw * G.gh, tid = threadIdx.x;
+    const int per = (n + 1 + 255) / 256, c0 = min(tid * per, n + 1), c1 = min(c0 + per, n + 1);
+    int acc = 0;
+    for (int c = c0; c < c1; c++) acc += G.cell_start[c];
+    chunk_sum[tid] = acc;
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 256 chunk totals by one warp, 8 per lane
+        int v[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = chunk_sum[tid * 8 + k];
+            tot += v[k];
+        }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += x;
+        }
+        int run = inc - tot;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            chunk_sum[tid * 8 + k] = run;
+            run += v[k];
         }
     }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) G.cell_fill[i] = 0;
+    __syncthreads();
+    acc = chunk_sum[tid];
+    for (int c = c0; c < c1; c++) {
+        acc += G.cell_start[c];
+        G.cell_start[c] = acc;
+    }
+    for (int i = tid; i < n; i += 256) G.cell_fill[i] = 0;
 }
 
 __global__ void grid_fill_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps, const uint8_t *__restrict__ desc) {
@@ -242,16 +267,13 @@ struct ProjParams {
     double radius, ratio;
 };
 
-// One map point against the frame behind G: Xc = Tcw Xw, Camera::Project, radius search over the bucket grid,
-// best / second-best Hamming, ratio test, then the conflict rule as an atomicMin on the winning keypoint's key.
-// `query` is the point's position in the caller's order (the later query wins a distance tie, :197-204).
-__device__ __forceinline__ void project_and_match(const KpGrid &G, const ProjParams &P, double X, double Y, double Z,
-                                                  const uint32_t a[8], uint32_t query, unsigned long long *__restrict__ best) {
+// Xc = Tcw Xw, Camera::Project, IsInImage: false when the point is behind the camera, outside the image or not a number
+__device__ __forceinline__ bool project_point(const ProjParams &P, double X, double Y, double Z, double &u, double &v) {
     // Xc = Tcw * Xw, evaluated left to right without contraction (:150)
     const double xc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[0], X), __dmul_rn(P.rt[1], Y)), __dmul_rn(P.rt[2], Z)), P.rt[3]);
     const double yc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[4], X), __dmul_rn(P.rt[5], Y)), __dmul_rn(P.rt[6], Z)), P.rt[7]);
     const double zc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[8], X), __dmul_rn(P.rt[9], Y)), __dmul_rn(P.rt[10], Z)), P.rt[11]);
-    if (zc < 0.) return;  // :151-153
+    if (zc < 0.) return false;  // :151-153
     // Camera::Project + Distort, src/camera.cpp:50-79
     const double x = __ddiv_rn(xc, zc), y = __ddiv_rn(yc, zc);
     const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), r4 = __dmul_rn(r2, r2);
@@ -261,9 +283,17 @@ __device__ __forceinline__ void project_and_match(const KpGrid &G, const ProjPar
     const double cdist = __dadd_rn(__dadd_rn(1., __dmul_rn(P.cam.d[0], r2)), __dmul_rn(P.cam.d[1], r4));
     const double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, cdist), __dmul_rn(P.cam.d[2], a1)), __dmul_rn(P.cam.d[3], a2));
     const double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, cdist), __dmul_rn(P.cam.d[2], a3)), __dmul_rn(P.cam.d[3], a1));
-    const double u = __dadd_rn(__dmul_rn(P.cam.fx, xd), P.cam.cx), v = __dadd_rn(__dmul_rn(P.cam.fy, yd), P.cam.cy);
-    if (u < 0. || v < 0. || u > (double)P.cam.width || v > (double)P.cam.height) return;  // IsInImage, :26-36
-    if (!(u == u) || !(v == v)) return;  // NaN: the radius search finds nothing
+    u = __dadd_rn(__dmul_rn(P.cam.fx, xd), P.cam.cx);
+    v = __dadd_rn(__dmul_rn(P.cam.fy, yd), P.cam.cy);
+    if (u < 0. || v < 0. || u > (double)P.cam.width || v > (double)P.cam.height) return false;  // IsInImage, :26-36
+    return u == u && v == v;  // NaN: the radius search finds nothing
+}
+
+// One projected map point against the frame behind G: radius search over the bucket grid, best / second-best Hamming,
+// ratio test, then the conflict rule as an atomicMin on the winning keypoint's key.  `query` is the point's position in
+// the caller's order (the later query wins a distance tie, :197-204).
+__device__ __forceinline__ void match_projected(const KpGrid &G, const ProjParams &P, double u, double v, const uint32_t a[8],
+                                                uint32_t query, unsigned long long *__restrict__ best) {
     const double r2max = __dmul_rn(P.radius, P.radius);
     const int cy0 = min(max((int)floor(v - P.radius) >> kGridShift, 0), G.gh - 1);
     const int cy1 = min(max((int)floor(v + P.radius) >> kGridShift, 0), G.gh - 1);
@@ -298,6 +328,12 @@ __device__ __forceinline__ void project_and_match(const KpGrid &G, const ProjPar
     }
 }
 
+__device__ __forceinline__ void project_and_match(const KpGrid &G, const ProjParams &P, double X, double Y, double Z,
+                                                  const uint32_t a[8], uint32_t query, unsigned long long *__restrict__ best) {
+    double u, v;
+    if (project_point(P, X, Y, Z, u, v)) match_projected(G, P, u, v, a, query, best);
+}
+
 __global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjParams P, int n, uint32_t idx_base,
                                                                const double *__restrict__ xw,
                                                                const uint8_t *__restrict__ mp_desc,
@@ -309,6 +345,111 @@ __global__ void __launch_bounds__(128) projection_match_kernel(KpGrid G, ProjPar
     uint32_t a[8];
     load_desc(mp_desc + (size_t)i * 32, a);
     project_and_match(G, P, xw[3 * (size_t)i], xw[3 * (size_t)i + 1], xw[3 * (size_t)i + 2], a, idx_base + (uint32_t)i, best);
+}
+
+// Large local maps: the lanes of a warp walk the bucket grid in lock step, so a warp costs as much as its longest
+// candidate list, and with the points in the caller's order that is 3x the average (ncu: 11 of 32 lanes active).  The
+// points are therefore counting-sorted by the grid cell they project into (1024 row-major bins; points that project
+// nowhere are dropped) and matched in that order: neighbouring lanes see the same cells and about the same number of
+// candidates.  Results do not depend on the order -- a point's key carries its own index.
+//   proj_bin_kernel      per chunk of 2048 points: bin of every point + the chunk's histogram
+//   proj_offsets_kernel  per bin: exclusive prefix of the chunk counts, bin total
+//   proj_scan_kernel     exclusive scan of the 1024 bin totals
+//   proj_scatter_kernel  per chunk: positions from shared-memory cursors -> perm
+//   proj_match_sorted_kernel  thread e handles point perm[e]
+constexpr int kProjChunk = 2048, kProjBins = 1024;
+constexpr int kProjSortMin = 32768;  // below this many map points the five extra launches cost more than the divergence
+
+__global__ void __launch_bounds__(256) proj_bin_kernel(int gw, int gh, ProjParams P, int n, const double *__restrict__ xw,
+                                                       const uint8_t *__restrict__ skip, uint16_t *__restrict__ bins,
+                                                       int *__restrict__ hist) {
+    __shared__ int h[kProjBins];
+    const int tid = threadIdx.x, base = blockIdx.x * kProjChunk, cn = min(kProjChunk, n - base), cells = gw * gh;
+    for (int b = tid; b < kProjBins; b += 256) h[b] = 0;
+    __syncthreads();
+    for (int k = tid; k < cn; k += 256) {
+        const int i = base + k;
+        uint16_t bin = 0xFFFF;  // dropped
+        double u, v;
+        if (!(skip && skip[i]) && project_point(P, xw[3 * (size_t)i], xw[3 * (size_t)i + 1], xw[3 * (size_t)i + 2], u, v)) {
+            const int cx = min(max((int)floor(u) >> kGridShift, 0), gw - 1), cy = min(max((int)floor(v) >> kGridShift, 0), gh - 1);
+            bin = (uint16_t)(((long long)(cy * gw + cx) * kProjBins) / cells);
+            atomicAdd(&h[bin], 1);
+        }
+        bins[i] = bin;
+    }
+    __syncthreads();
+    for (int b = tid; b < kProjBins; b += 256) hist[(size_t)blockIdx.x * kProjBins + b] = h[b];
+}
+
+// warp = bin: hist[c][bin] becomes the number of the bin's points in chunks before c; tot[bin] = the bin's size
+__global__ void __launch_bounds__(256) proj_offsets_kernel(int chunks, int *__restrict__ hist, int *__restrict__ tot) {
+    const int bin = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    int run = 0;
+    for (int c0 = 0; c0 < chunks; c0 += 32) {
+        const int c = c0 + lane;
+        const int v = c < chunks ? hist[(size_t)c * kProjBins + bin] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += x;
+        }
+        if (c < chunks) hist[(size_t)c * kProjBins + bin] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) tot[bin] = run;
+}
+
+__global__ void __launch_bounds__(kProjBins) proj_scan_kernel(int *__restrict__ tot) {  // tot[b] -> first position of bin b; tot[1024] = all
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = tot[tid];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += x;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = wsum[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += x;
+        }
+        wsum[lane] = winc - w;
+    }
+    __syncthreads();
+    tot[tid] = wsum[warp] + inc - v;
+    if (tid == kProjBins - 1) tot[kProjBins] = wsum[warp] + inc;
+}
+
+__global__ void __launch_bounds__(256) proj_scatter_kernel(int n, const uint16_t *__restrict__ bins, const int *__restrict__ hist,
+                                                           const int *__restrict__ tot, uint32_t *__restrict__ perm) {
+    __shared__ int cur[kProjBins];
+    const int tid = threadIdx.x, base = blockIdx.x * kProjChunk, cn = min(kProjChunk, n - base);
+    for (int b = tid; b < kProjBins; b += 256) cur[b] = tot[b] + hist[(size_t)blockIdx.x * kProjBins + b];
+    __syncthreads();
+    for (int k = tid; k < cn; k += 256) {
+        const int bin = bins[base + k];
+        if (bin != 0xFFFF) perm[atomicAdd(&cur[bin], 1)] = (uint32_t)(base + k);
+    }
+}
+
+__global__ void __launch_bounds__(128) proj_match_sorted_kernel(KpGrid G, ProjParams P, uint32_t idx_base, const int *__restrict__ n_valid,
+                                                                const uint32_t *__restrict__ perm, const double *__restrict__ xw,
+                                                                const uint8_t *__restrict__ mp_desc,
+                                                                unsigned long long *__restrict__ best) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= *n_valid) return;
+    const uint32_t i = perm[e];
+    uint32_t a[8];
+    load_desc(mp_desc + (size_t)i * 32, a);
+    project_and_match(G, P, xw[3 * (size_t)i], xw[3 * (size_t)i + 1], xw[3 * (size_t)i + 2], a, idx_base + i, best);
 }
 
 // keys of `shards` map-point shards (shards x m) -> per keypoint the minimum (dist, -query) key, decoded
@@ -592,12 +733,24 @@ __global__ void __launch_bounds__(256) track_grids_kernel(TrackArrays A) {
     for (int c = c0; c < c1; c++) acc += start[c];
     chunk_sum[tid] = acc;
     __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        for (int i = 0; i < 256; i++) {
-            const int v = chunk_sum[i];
-            chunk_sum[i] = run;
-            run += v;
+    if (tid < 32) {  // exclusive scan of the 256 chunk totals by one warp, 8 per lane
+        int v[8], tot = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v[k] = chunk_sum[tid * 8 + k];
+            tot += v[k];
+        }
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= o) inc += x;
+        }
+        int run = inc - tot;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            chunk_sum[tid * 8 + k] = run;
+            run += v[k];
         }
     }
     __syncthreads();
@@ -804,6 +957,9 @@ struct sfe_matcher {
     DevBuf<int> d_grid;
     DevBuf<unsigned long long> d_best, d_part, d_keys;
     DevBuf<int32_t> d_quad;
+    DevBuf<uint16_t> d_proj_bins;  // sorted ProjectionMatch: bin per map point,
+    DevBuf<int> d_proj_hist;       // per-chunk bin histograms + bin totals,
+    DevBuf<uint32_t> d_proj_perm;  // map points in bin order
 };
 
 struct sfe_db {
@@ -877,8 +1033,22 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
         P.cam = *cam;
         P.radius = radius;
         P.ratio = ratio;
-        projection_match_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, n, idx_base, xw, mp_desc, skip, best);
-        m->launches++;
+        if (n < kProjSortMin) {
+            projection_match_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, n, idx_base, xw, mp_desc, skip, best);
+            m->launches++;
+        } else {
+            const int chunks = div_up(n, kProjChunk);
+            SFE_CUDA(m->d_proj_bins.ensure(n));
+            SFE_CUDA(m->d_proj_hist.ensure((size_t)chunks * kProjBins + kProjBins + 1));
+            SFE_CUDA(m->d_proj_perm.ensure(n));
+            int *hist = m->d_proj_hist.p, *tot = hist + (size_t)chunks * kProjBins;
+            proj_bin_kernel<<<chunks, 256, 0, st>>>(G.gw, G.gh, P, n, xw, skip, m->d_proj_bins.p, hist);
+            proj_offsets_kernel<<<kProjBins / 8, 256, 0, st>>>(chunks, hist, tot);
+            proj_scan_kernel<<<1, kProjBins, 0, st>>>(tot);
+            proj_scatter_kernel<<<chunks, 256, 0, st>>>(n, m->d_proj_bins.p, hist, tot, m->d_proj_perm.p);
+            proj_match_sorted_kernel<<<div_up(n, 128), 128, 0, st>>>(G, P, idx_base, tot + kProjBins, m->d_proj_perm.p, xw, mp_desc, best);
+            m->launches += 5;
+        }
     }
     if (!keys_out) {
         projection_decode_kernel<<<div_up(m_kps, 256), 256, 0, st>>>(m_kps, 1, best, to_query, dist);
@@ -946,6 +1116,7 @@ int sfe_matcher_destroy(sfe_matcher *m) {
     m->d_kl.release(); m->d_kr.release(); m->d_dl.release(); m->d_dr.release(); m->d_skip.release();
     m->d_n.release(); m->d_idx.release(); m->d_dist.release(); m->d_xw.release(); m->d_grid.release();
     m->d_best.release(); m->d_part.release(); m->d_keys.release(); m->d_quad.release();
+    m->d_proj_bins.release(); m->d_proj_hist.release(); m->d_proj_perm.release();
     cudaStreamDestroy(m->stream);
     delete m;
     return SFE_OK;
