@@ -772,19 +772,30 @@ __global__ void __launch_bounds__(256) track_grids_kernel(TrackArrays A) {
         G.sdesc[2 * t] = __ldg(d);
         G.sdesc[2 * t + 1] = __ldg(d + 1);
     }
-    // the keypoints that will be projected into the next frame, compacted so that the matcher's warps are full
+    // the keypoints that will be projected into the next frame: compacted so that the matcher's warps are full, and in
+    // the grid's cell order so that the lanes of a warp project into the same neighbourhood (the motion between
+    // consecutive frames is small) and walk the same cells
+    __syncthreads();  // order[] of this frame is complete
     const int32_t *sidx = A.sidx + (size_t)f * A.cap;
     int *valid = A.valid + (size_t)f * A.cap;
-    for (int j0 = 0; j0 < G.m; j0 += 256) {
-        const int j = j0 + tid;
-        const bool ok = j < G.m && sidx[j] >= 0;
+    __shared__ int wcount[8];
+    for (int t0 = 0; t0 < G.m; t0 += 256) {
+        const int t = t0 + tid, j = t < G.m ? G.order[t] : -1;
+        const bool ok = j >= 0 && sidx[j] >= 0;
         const uint32_t b = __ballot_sync(0xffffffffu, ok);
-        int base = 0;
-        if ((tid & 31) == 0 && b) base = atomicAdd(&nv, __popc(b));
-        base = __shfl_sync(0xffffffffu, base, 0);
+        if ((tid & 31) == 0) wcount[tid >> 5] = __popc(b);
+        __syncthreads();
+        int base = nv;
+        for (int w2 = 0; w2 < (tid >> 5); w2++) base += wcount[w2];
         if (ok) valid[base + __popc(b & ((1u << (tid & 31)) - 1))] = j;
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w2 = 0; w2 < 8; w2++) tot += wcount[w2];
+            nv += tot;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (tid == 0) A.n_valid[f] = nv;
 }
 
