@@ -360,9 +360,10 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) fast_segments_ke
                 const int cx0 = cell * w_cell, cx1 = min(cx0 + w_cell, tw);
                 const uint8_t *sc = &score[(y + 1) * SP + x + 1];
                 const int s = sc[0];
-                keep = s > sc[-SP] && s > sc[SP];
-                if (x > cx0) keep = keep && s > sc[-1] && s > sc[-SP - 1] && s > sc[SP - 1];
-                if (x + 1 < cx1) keep = keep && s > sc[1] && s > sc[-SP + 1] && s > sc[SP + 1];
+                // branch-free: the three neighbours of a side count as 0 when that side lies in another cell
+                const int lft = x > cx0 ? __vimax3_s32(sc[-1], sc[-SP - 1], sc[SP - 1]) : 0;
+                const int rgt = x + 1 < cx1 ? __vimax3_s32(sc[1], sc[-SP + 1], sc[SP + 1]) : 0;
+                keep = s > __vimax3_s32(max(sc[-SP], sc[SP]), lft, rgt);
                 // cv::FAST response = best - 1; window-relative coordinates
                 packed = (uint32_t)(s - 1) << 24 | (uint32_t)(ini_y - kBorder + y + 3) << 12 | (uint32_t)(ini_x - kBorder + x + 3);
             }
