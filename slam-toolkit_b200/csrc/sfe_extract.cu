@@ -595,11 +595,11 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
 // Candidate-sized arrays (14 B per candidate) live in shared memory when the level has at most smem_cand
 // candidates -- sized for the common case so that several CTAs fit an SM -- and otherwise in one of the
 // handle's global scratch slots (same code, generic pointers; L2-resident).
-__global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int smem_cand, int max_cand, int max_nodes,
-                                                     uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
+__device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, int smem_cand, int max_cand, int max_nodes,
+                            uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int sh_misc[4];
-    const int l = blockIdx.x, img = slot_of(S, blockIdx.y), tid = threadIdx.x, T = blockDim.x;  // internal buffers only
+    const int img = slot_of(S, image), tid = threadIdx.x, T = blockDim.x;  // internal buffers only
     const LevelPlan &L = S.lv[l];
     int *kp_count = &S.kp_count[img * S.nlevels + l];
     const int n = min(S.cand_count[img * S.nlevels + l], L.cand_cap);
@@ -733,6 +733,18 @@ __global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int smem_cand, in
         out[i] = best;
     }
     if (tid == 0) *kp_count = nL;
+}
+
+// (level, image) items in level-major order -- the fullest levels first -- handed out round-robin: with one CTA per item
+// this is the plain launch, with fewer CTAs (SFE_OCTREE_CTAS) the kernel is persistent and leaves shared memory to a
+// kernel running beside it.
+__global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int count, int smem_cand, int max_cand, int max_nodes,
+                                                     uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
+    const int items = S.nlevels * count;
+    for (int w = blockIdx.x; w < items; w += gridDim.x) {
+        octree_item(S, w / count, w % count, smem_cand, max_cand, max_nodes, scratch, scratch_slots, scratch_next);
+        __syncthreads();  // the next item reuses the shared arrays
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1107,9 +1119,11 @@ struct sfe_extractor {
     int n_compute = 3;                              // SFE_COMPUTE_STREAMS
     cudaStream_t aux[2] = {nullptr, nullptr};       // per compute stream: the blur runs beside FAST + quadtree
     cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
-    int overlap_blur = 0;   // 0 off, 1 = blur forks before FAST, 2 = blur forks after FAST (beside the quadtree only)
-    bool overlap_blur_unused = false;                      // SFE_OVERLAP_BLUR=1; measured on B200: no gain (both kernels fill the
-                                                    // machine on their own, the block scheduler runs them back to back)
+    int octree_ctas = 0;    // SFE_OCTREE_CTAS: > 0 = persistent quadtree kernel with that many CTAs
+    int sm_count = 148;
+    bool piped_now = false; // a pipelined host call is enqueueing its sub-batches
+    int overlap_blur = 2;   // SFE_OVERLAP_BLUR: 0 off, 1 = blur forks before FAST (no gain: both kernels fill the machine on their
+                            // own), 2 = blur forks after FAST and runs beside the latency-bound quadtree (default)
     cudaEvent_t ev_start = nullptr;
     bool async_dev = false;                         // _dev entry points return after enqueueing (sfe_extractor_wait)
     cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
@@ -1531,10 +1545,11 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     }
     prof_mark(ex, 1);
     if (ex->fast.n_cells > 0) {
-        // The blur only needs the pyramid, so it can run on a side stream beside FAST and the quadtree and join before
-        // the descriptors (opt-in: it bought nothing on B200, see overlap_blur).  Serial when stages are timed.
+        // The blur only needs the pyramid, so it runs on a side stream beside the quadtree (which is latency-bound: 35 %
+        // issue-active) and joins before the descriptors.  Serial when stages are timed and on the pipelined host path,
+        // whose sub-batches already overlap across compute streams.
         const int si = 0;
-        const bool fork = ex->overlap_blur && !ex->profiling && st == ex->stream, late = ex->overlap_blur == 2;
+        const bool fork = ex->overlap_blur && !ex->profiling && !ex->piped_now && st == ex->stream, late = ex->overlap_blur == 2;
         cudaStream_t sb = fork ? ex->aux[si] : st;
         auto launch_blur = [&]() {
             if (ex->tma_now)
@@ -1564,7 +1579,12 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
                 granted[ex->device & 63] = ex->octree_smem;
             }
         }
-        octree_kernel<<<dim3(nl, count), 256, ex->octree_smem, st>>>(S, ex->octree_smem_cand, ex->max_cand, ex->max_nodes, ex->d_octree_scratch.p,
+        // beside the forked blur the quadtree runs persistent with 2 CTAs per SM: its ~60 KB of shared memory per CTA would
+        // otherwise leave the blur one CTA per SM (measured: 2.12 -> 2.06 ms per 128-frame step; alone, fewer CTAs are slower)
+        const int oct_items = nl * count;
+        const int oct_ctas = ex->octree_ctas > 0 ? ex->octree_ctas : (fork && late ? 2 * ex->sm_count : 0);
+        const int oct_grid = oct_ctas > 0 ? std::min(oct_items, oct_ctas) : oct_items;
+        octree_kernel<<<oct_grid, 256, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes, ex->d_octree_scratch.p,
                                                                      ex->octree_slots, ex->d_counts.p + (size_t)ex->max_images * nl * 2);
         prof_mark(ex, 3);
         if (fork) SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[si], 0));
@@ -1686,6 +1706,7 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
     const bool piped = nch > 1;
     cudaStream_t sin = piped ? ex->s_h2d : ex->stream, sout = piped ? ex->s_d2h : ex->stream;
     const bool prof = ex->profiling;
+    ex->piped_now = piped;
     if (piped) {
         ex->profiling = false;  // per-stage events describe one unpipelined batch
         SFE_CUDA(cudaEventRecord(ex->ev_start, ex->stream));  // the counter reset precedes every sub-batch
@@ -1737,6 +1758,7 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 2], sout);
     }
     ex->profiling = prof;
+    ex->piped_now = false;
     if (rc != SFE_OK) {
         cudaStreamSynchronize(sin); cudaStreamSynchronize(ex->stream);
         for (auto &e : ex->extra) cudaStreamSynchronize(e);
@@ -1820,6 +1842,8 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_PIPELINE_CHUNKS")) ex->chunks_override = atoi(env);
     if (const char *env = getenv("SFE_NO_TMA")) ex->tma_disabled = atoi(env) != 0;
     if (const char *env = getenv("SFE_OVERLAP_BLUR")) ex->overlap_blur = atoi(env);
+    cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *env = getenv("SFE_OCTREE_CTAS")) ex->octree_ctas = atoi(env);
     if (const char *env = getenv("SFE_TRACE")) ex->trace = atoi(env) != 0;
     if (const char *env = getenv("SFE_COMPUTE_STREAMS")) ex->n_compute = std::max(1, std::min(atoi(env), kComputeStreams));
     if (ex->trace)
