@@ -1382,7 +1382,11 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     if (ex->octree_smem_cand < 8) ex->octree_smem_cand = 8;
     ex->octree_smem = (size_t)ex->octree_smem_cand * 14 + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
     SFE_REQUIRE(ex->octree_smem <= 227 * 1024, SFE_ERR_UNSUPPORTED, "quadtree working set exceeds shared memory");
-    ex->octree_slots = ex->max_cand > ex->octree_smem_cand ? 2 * ex->max_images : 0;
+    {   // one global scratch slot for every (level, image) whose candidate buffer can outgrow the shared-memory arrays
+        int big_levels = 0;
+        for (int l = 0; l < nl; l++) big_levels += ex->lv[l].cand_cap > ex->octree_smem_cand;
+        ex->octree_slots = big_levels * ex->max_images;
+    }
     SFE_CUDA(ex->d_octree_scratch.ensure(std::max<size_t>((size_t)ex->octree_slots * ex->max_cand * 14, 16)));
     const int n = ex->max_images;
     SFE_CUDA(ex->d_pyr.ensure(ex->pyr_stride * n));

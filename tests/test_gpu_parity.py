@@ -126,6 +126,26 @@ def test_fast_segments_mixed_retry_noise_and_high_thresholds(gpu, oracle):
     assert (rk["response"] < 20).any() and (rk["response"] >= 20).any()
 
 
+@pytest.mark.parametrize("w,h,nf,sf,nl", [(1920, 1080, 3000, 1.2, 8), (752, 480, 1200, 1.5, 5), (640, 480, 1000, 2.0, 4),
+                                           (1024, 300, 1500, 1.1, 10), (333, 217, 400, 1.7, 3), (2048, 256, 2000, 1.25, 6)])
+def test_other_geometries_and_scale_factors(gpu, oracle, w, h, nf, sf, nl):
+    """Other camera geometries and pyramid scale factors through the whole extractor: cell widths / segment packing,
+    the 4-outputs-per-thread pyramid pass (source pairs must fit 8 bytes: scale <= 2.33) and its fallback, TMA boxes."""
+    img, right = synth.stereo_pair(31, w, h)
+    ex = api.ORBextractor(nf, sf, nl, 20, 7, max_images=2)
+    ref = oracle.Extractor(nf, sf, nl, 20, 7)
+    out = ex.stereo_frames(img[None], right[None])
+    rk, rd = ref.extract(img)
+    bad = _stage_report(ex, ref, 0, nl)
+    assert not bad, bad
+    n = out["n_l"][0]
+    assert n == len(rk) and np.array_equal(out["kps_l"][0, :n], rk) and np.array_equal(out["desc_l"][0, :n], rd)
+    rkr, rdr = ref.extract(right)
+    si, sd = oracle.stereo_match(rk, rd, rkr, rdr)
+    assert np.array_equal(out["stereo_idx"][0, :n], si) and np.array_equal(out["stereo_dist"][0, :n], sd)
+    assert len(rk) > nf // 3
+
+
 def test_batch_equals_single(kitti_ex, oracle):
     imgs = np.stack([synth.stereo_pair(s)[i] for s in (4, 5) for i in (0, 1)])
     kps, desc, n = kitti_ex.extract_batch(imgs)
