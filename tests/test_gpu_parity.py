@@ -146,6 +146,41 @@ def test_other_geometries_and_scale_factors(gpu, oracle, w, h, nf, sf, nl):
     assert len(rk) > nf // 3
 
 
+def test_sequence_edge_cases_and_replanning(gpu, oracle):
+    """A flat frame in the middle of a sequence (zero keypoints: nothing to track from or to), a one-frame sequence, few and
+    many requested features, and the same handle re-planned for another image size between calls."""
+    w, h = 480, 200
+    L, R = synth.stereo_sequence(3, 4, 4, w, h)
+    L[2] = 77
+    R[2] = 77
+    cam = api.Camera.make(300.0, 300.0, w / 2.0, h / 2.0, (0.01, -0.001, 0, 0), w, h)
+    tp = api.TrackParams.make(cam, 0.4, None, 25.0)
+    ex = api.ORBextractor(300, 1.2, 4, 20, 7, max_images=8)
+    out = ex.stereo_sequence(L, R, tp)
+    assert out["n_l"][2] == 0 and out["n_r"][2] == 0 and out["n_l"][1] > 100
+    assert (out["track_idx"][2] == -1).all() and (out["track_idx"][3] == -1).all()   # nothing in frame 2, nothing from it
+    tracked = _check_tracking(oracle, out, 4, tp, np.eye(4))
+    assert tracked > 50
+    one = ex.stereo_sequence(L[:1], R[:1], tp)
+    assert (one["track_idx"] == -1).all() and one["n_l"][0] == out["n_l"][0]
+    assert np.array_equal(one["kps_l"][0], out["kps_l"][0])
+    # re-plan the same handle for another size, then back
+    img2, _ = synth.stereo_pair(8, 301, 177)
+    k2, d2 = ex.extract(img2)
+    rk2, rd2 = oracle.Extractor(300, 1.2, 4, 20, 7).extract(img2)
+    assert np.array_equal(k2, rk2) and np.array_equal(d2, rd2)
+    again = ex.stereo_sequence(L, R, tp)
+    _stereo_equal(again, out, 4)   # (rows past a frame's keypoint count are not defined)
+    assert np.array_equal(again["track_idx"], out["track_idx"]) and np.array_equal(again["track_dist"], out["track_dist"])
+    for nf in (20, 6000):
+        img, _ = synth.stereo_pair(12, 900, 400)
+        e2 = api.ORBextractor(nf, 1.2, 5, 20, 7)
+        k, d = e2.extract(img)
+        rk, rd = oracle.Extractor(nf, 1.2, 5, 20, 7).extract(img)
+        assert np.array_equal(k, rk) and np.array_equal(d, rd), nf
+        assert len(rk) >= nf if nf == 20 else len(rk) > 3000
+
+
 def test_batch_equals_single(kitti_ex, oracle):
     imgs = np.stack([synth.stereo_pair(s)[i] for s in (4, 5) for i in (0, 1)])
     kps, desc, n = kitti_ex.extract_batch(imgs)
