@@ -1122,6 +1122,9 @@ struct sfe_extractor {
     int octree_ctas = 0;    // SFE_OCTREE_CTAS: > 0 = persistent quadtree kernel with that many CTAs
     int sm_count = 148;
     bool piped_now = false; // a pipelined host call is enqueueing its sub-batches
+    bool overlap_tail = true;   // SFE_OVERLAP_TAIL=0 turns it off: asynchronous resident stereo calls run StereoMatch + tracking on
+    bool tail_pending = false;  // aux[1], beside the next call's pyramid / FAST (the next call's descriptor kernel, the first
+                                // writer of the caller's output arrays, waits for it: ev_join[1])
     int overlap_blur = 2;   // SFE_OVERLAP_BLUR: 0 off, 1 = blur forks before FAST (no gain: both kernels fill the machine on their
                             // own), 2 = blur forks after FAST and runs beside the latency-bound quadtree (default)
     cudaEvent_t ev_start = nullptr;
@@ -1533,6 +1536,15 @@ static int launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int 
     return SFE_OK;
 }
 
+// Order the handle's main stream behind a matching tail still running on the side stream.
+static int join_tail(sfe_extractor *ex) {
+    if (ex->tail_pending) {
+        SFE_CUDA(cudaStreamWaitEvent(ex->stream, ex->ev_join[1], 0));
+        ex->tail_pending = false;
+    }
+    return SFE_OK;
+}
+
 static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count, const OutSet &O) {
     const int nl = ex->prm.nlevels;
     prof_mark(ex, 0);
@@ -1598,6 +1610,11 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     } else {
         prof_mark(ex, 2); prof_mark(ex, 3); prof_mark(ex, 4);
     }
+    if (st == ex->stream) {  // the previous call's matchers may still be reading the output arrays this kernel writes
+        if (int rc = join_tail(ex)) return rc;
+    } else if (ex->tail_pending) {
+        SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[1], 0));
+    }
     orient_describe_kernel<<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O);
     prof_mark(ex, 5);
     ex->prof_pending = ex->profiling;
@@ -1640,6 +1657,7 @@ static int prepare(sfe_extractor *ex, int count, int w, int h, int stride, int c
     SFE_REQUIRE(w > 0 && h > 0 && stride >= w, SFE_ERR_BAD_ARG, "bad image geometry");
     SFE_REQUIRE(cap >= 1 && cap < 65536, SFE_ERR_BAD_ARG, "capacity must be in [1, 65535]");
     if (w != ex->w || h != ex->h) {
+        if (ex->tail_pending) SFE_CUDA(cudaStreamSynchronize(ex->aux[1]));  // buffers are about to be reallocated
         int rc = build_plan(ex, w, h);
         if (rc != SFE_OK) { ex->w = ex->h = 0; return rc; }
     }
@@ -1687,8 +1705,9 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
                           int32_t *track_dist = nullptr) {
     const bool stereo = right != nullptr;
     const int images = stereo ? 2 * frames : frames;
-    int rc = prepare(ex, images, w, h, stride, cap);
+    int rc = join_tail(ex);  // an asynchronous resident call may still be matching on the side stream
     if (rc != SFE_OK) return rc;
+    if ((rc = prepare(ex, images, w, h, stride, cap)) != SFE_OK) return rc;
     const size_t F = frames, wh = (size_t)ex->pitch0 * h;  // level 0 as the kernels see it: pitched rows, images back to back
     SFE_CUDA(ex->d_in.ensure((size_t)ex->max_images * w * h + 32));
     SFE_CUDA(ex->d_l0.ensure((size_t)ex->max_images * wh + 32));
@@ -1848,6 +1867,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_OVERLAP_BLUR")) ex->overlap_blur = atoi(env);
     cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *env = getenv("SFE_OCTREE_CTAS")) ex->octree_ctas = atoi(env);
+    if (const char *env = getenv("SFE_OVERLAP_TAIL")) ex->overlap_tail = atoi(env) != 0;
     if (const char *env = getenv("SFE_TRACE")) ex->trace = atoi(env) != 0;
     if (const char *env = getenv("SFE_COMPUTE_STREAMS")) ex->n_compute = std::max(1, std::min(atoi(env), kComputeStreams));
     if (ex->trace)
@@ -1980,19 +2000,36 @@ static int stereo_frames_dev_impl(sfe_extractor *ex, const uint8_t *left_dev, co
     prepare_l0_maps(ex, left_dev, right_dev, frames, frames, image_stride, stride);
     if ((rc = reset_counters(ex)) != SFE_OK) return rc;
     if ((rc = enqueue_extract(ex, ex->stream, S, 2 * frames, O)) != SFE_OK) return rc;
-    launch_stereo_match(ex->stream, frames, cap, kps_l_dev, desc_l_dev, n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, sp->y_threshold,
+    // asynchronous calls: the matchers are small latency-bound kernels, so they go to a side stream and run beside the
+    // next call's pyramid and FAST kernels
+    const bool tail = ex->async_dev && ex->overlap_tail && !ex->profiling;
+    cudaStream_t sm = tail ? ex->aux[1] : ex->stream;
+    if (!tail) {
+        if ((rc = join_tail(ex)) != SFE_OK) return rc;
+    } else if (tp && ex->tail_pending && (size_t)frames * cap > ex->track.best.n) {
+        SFE_CUDA(cudaStreamSynchronize(ex->aux[1]));  // the tracking scratch is about to grow under a running tail
+    }
+    if (tail) {
+        SFE_CUDA(cudaEventRecord(ex->ev_fork[1], ex->stream));
+        SFE_CUDA(cudaStreamWaitEvent(sm, ex->ev_fork[1], 0));
+    }
+    launch_stereo_match(sm, frames, cap, kps_l_dev, desc_l_dev, n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, sp->y_threshold,
                         sp->max_dx, sp->best12_threshold, stereo_idx_dev, stereo_dist_dev);
     prof_mark(ex, 6);
     ex->prof_has_stereo = true;
     ex->launches++;
     SFE_CUDA(cudaGetLastError());
     if (tp) {
-        if ((rc = launch_track_frames(ex->stream, ex->device, ex->track, frames, cap, kps_l_dev, desc_l_dev, n_l_dev, kps_r_dev,
+        if ((rc = launch_track_frames(sm, ex->device, ex->track, frames, cap, kps_l_dev, desc_l_dev, n_l_dev, kps_r_dev,
                                       stereo_idx_dev, *tp, track_idx_dev, track_dist_dev)) != SFE_OK)
             return rc;
         prof_mark(ex, 7);
         ex->prof_has_track = true;
         ex->launches += 3;
+    }
+    if (tail) {
+        SFE_CUDA(cudaEventRecord(ex->ev_join[1], sm));
+        ex->tail_pending = true;
     }
     ex->last = S;
     ex->last_count = 2 * frames;
@@ -2055,6 +2092,7 @@ int sfe_image_pitch(int w) { return w > 0 ? (int)align_up((size_t)w, 16) : 0; }
 int sfe_extractor_set_async(sfe_extractor *ex, int enable) {
     SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
     DeviceGuard g(ex->device);
+    if (int rc = join_tail(ex)) return rc;
     SFE_CUDA(cudaStreamSynchronize(ex->stream));
     ex->async_dev = enable != 0;
     if (ex->d_counts.p)  // start from clean flags
@@ -2065,6 +2103,7 @@ int sfe_extractor_set_async(sfe_extractor *ex, int enable) {
 int sfe_extractor_wait(sfe_extractor *ex) {
     SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
     DeviceGuard g(ex->device);
+    if (int rc = join_tail(ex)) return rc;
     if (ex->last_count <= 0) {
         SFE_CUDA(cudaStreamSynchronize(ex->stream));
         return SFE_OK;
@@ -2178,6 +2217,7 @@ int sfe_extractor_stage_ms(const sfe_extractor *ex, double *ms, int n, int64_t *
 int sfe_event_record_extractor(sfe_event *ev, sfe_extractor *ex) {
     SFE_REQUIRE(ev && ex, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(ex->device);
+    if (int rc = join_tail(ex)) return rc;  // the event marks the end of everything enqueued so far
     SFE_CUDA(cudaEventRecord(ev->ev, ex->stream));
     return SFE_OK;
 }

@@ -302,6 +302,55 @@ def _stereo_equal(a, b, frames):
             assert np.array_equal(a[k][f, :n], b[k][f, :n]), (k, f)
 
 
+def test_async_queue_with_matchers_on_the_side_stream(gpu):
+    """Asynchronous resident calls queue back to back; StereoMatch + tracking of call i run on a side stream beside the
+    extraction kernels of call i+1.  Calls that write the SAME output arrays and calls that write different ones must both
+    end with exactly what synchronous calls produce -- also when a host-path call or a re-plan follows a pending tail."""
+    F, w, h = 3, 640, 240
+    seqs = [synth.stereo_sequence(s, F, 4, w, h) for s in (1, 2, 3)]
+    cam = api.Camera.make(400.0, 400.0, w / 2.0, h / 2.0, (0, 0, 0, 0), w, h)
+    tp = api.TrackParams.make(cam, 0.5, None, 30.0)
+    ex = api.ORBextractor(800, 1.2, 5, 20, 7, max_images=2 * F)
+    cap = ex.cap
+    sync = [ex.stereo_sequence(L, R, tp) for L, R in seqs]
+    spec = {"kps_l": (28, api.KP_DTYPE, (F, cap)), "desc_l": (32, np.uint8, (F, cap, 32)), "n_l": (0, np.int32, (F,)),
+            "kps_r": (28, api.KP_DTYPE, (F, cap)), "desc_r": (32, np.uint8, (F, cap, 32)), "n_r": (0, np.int32, (F,)),
+            "stereo_idx": (4, np.int32, (F, cap)), "stereo_dist": (4, np.int32, (F, cap)), "track_idx": (4, np.int32, (F, cap)),
+            "track_dist": (4, np.int32, (F, cap))}
+    imgs = [(api.DeviceBuffer(L.nbytes).upload(L), api.DeviceBuffer(R.nbytes).upload(R)) for L, R in seqs]
+    sets = [{k: api.DeviceBuffer(max(b * cap * F, 4 * F)) for k, (b, _, _) in spec.items()} for _ in range(3)]
+
+    def fetch(bufs):
+        return {k: bufs[k].download(shape, dt) for k, (_, dt, shape) in spec.items()}
+
+    def same(a, b):
+        _stereo_equal(a, b, F)
+        for f in range(F):
+            n = b["n_l"][f]
+            assert np.array_equal(a["track_idx"][f, :n], b["track_idx"][f, :n]) and np.array_equal(a["track_dist"][f, :n], b["track_dist"][f, :n])
+
+    ex.set_async(True)
+    for rep in range(2):   # different output arrays per call, twice over
+        for i in range(3):
+            ex.stereo_sequence_dev(imgs[i][0].ptr, imgs[i][1].ptr, F, w, h, {k: b.ptr for k, b in sets[i].items()}, tp)
+    ex.wait()
+    for i in range(3):
+        same(fetch(sets[i]), sync[i])
+    for i in (0, 1, 2, 1):  # the same output arrays for every call: the last one must win, untouched by earlier tails
+        ex.stereo_sequence_dev(imgs[i][0].ptr, imgs[i][1].ptr, F, w, h, {k: b.ptr for k, b in sets[0].items()}, tp)
+    ex.wait()
+    same(fetch(sets[0]), sync[1])
+    # a tail still pending when a host-path call and a call at another image size arrive
+    ex.stereo_sequence_dev(imgs[2][0].ptr, imgs[2][1].ptr, F, w, h, {k: b.ptr for k, b in sets[2].items()}, tp)
+    host = ex.stereo_sequence(*seqs[0], tp)
+    small = synth.stereo_pair(4, 320, 200)
+    ex.stereo_frames(small[0][None], small[1][None])
+    ex.wait()
+    same(host, sync[0])
+    same(fetch(sets[2]), sync[2])
+    ex.set_async(False)
+
+
 def test_pipelined_sub_batches_and_load_paths_agree(gpu, oracle, monkeypatch):
     """The host entry point cuts a batch into sub-batches on several streams, and tiles are fetched either by
     TMA or by plain loads: every combination must give the same bytes, and those of the oracle."""
