@@ -384,6 +384,25 @@ def main():
     ms = ev0.elapsed_ms(ev1)
     barrier()
     launches = ex.launches() - l0
+    # BASELINE config 3 beside the headline: extraction only (sfe_extract_batch_dev) of the same resident images, 2F
+    # independent frames per step (two calls of F), sharded over the ranks like the headline
+    def step_extract(i):
+        for d in (d_left[i % NB], d_right[i % NB]):
+            api._check(api.lib().sfe_extract_batch_dev(ex.h, api._p(d.ptr), PITCH * H, F, W, H, PITCH, api._p(ptrs["kps_l"]),
+                                                       api._p(ptrs["desc_l"]), cap, api._p(ptrs["n_l"])))
+    KX = max(K // 4, 5)
+    for i in range(3):
+        step_extract(i)
+    ex.wait()
+    ev2, ev3 = api.Event(dev), api.Event(dev)
+    barrier()
+    ev2.record(ex)
+    for i in range(KX):
+        step_extract(3 + i)
+    ev3.record(ex)
+    ex.wait()
+    ms_x = ev2.elapsed_ms(ev3) / KX
+    barrier()
     ex.set_async(False)
     n_stereo = int((d_out["stereo_idx"].download((F, cap), np.int32) >= 0).sum())
     n_track = int((d_out["track_idx"].download((F, cap), np.int32) >= 0).sum())
@@ -443,9 +462,9 @@ def main():
 
     if dist is not None:
         import torch
-        t = torch.tensor([ms, e2e_s * 1e3, e2e_single_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+        t = torch.tensor([ms, e2e_s * 1e3, e2e_single_s * 1e3, ms_x], dtype=torch.float64, device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms, e2e_single_ms = t.tolist()
+        ms, e2e_ms, e2e_single_ms, ms_x = t.tolist()
         e2e_s, e2e_single_s = e2e_ms / 1e3, e2e_single_ms / 1e3
     if rank != 0:
         if dist is not None:
@@ -509,7 +528,10 @@ def main():
                                  "instructions over its live time against 4 issues/clk/SM; profiles/ holds the pipe utilisation"},
             "stage_ms_per_step": {k: v / max(calls, 1) for k, v in stage_ms.items()},
             "keypoints_per_frame": n_kps / F, "matches_per_s": value * n_match / F,
-            "stereo_matches_per_frame": n_stereo / F, "tracked_matches_per_frame": n_track / F}
+            "stereo_matches_per_frame": n_stereo / F, "tracked_matches_per_frame": n_track / F,
+            "extract_only": {"images_per_s": world * 2 * F / (ms_x / 1e3), "ms_per_call_of_F_images": ms_x / 2,
+                             "algorithmic_gbs": world * 2 * F / (ms_x / 1e3) * B_IMG / 1e9,
+                             "note": "BASELINE config 3: sfe_extract_batch_dev on resident images, no matching"}}
     if hamming is not None:
         hamming["q1_stream_frac_of_hbm_peak"] = hamming["q1_stream_gbs"] / (world * hbm_peak)
         line["hamming"] = hamming
