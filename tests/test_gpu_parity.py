@@ -181,6 +181,40 @@ def test_sequence_edge_cases_and_replanning(gpu, oracle):
         assert len(rk) >= nf if nf == 20 else len(rk) > 3000
 
 
+def test_4k_frames_and_the_candidate_capacity_error(gpu, oracle):
+    """3840 x 2160: coordinates beyond the stereo matcher's bucket grid (clamped buckets), a tracking bucket grid that
+    needs the opt-in shared-memory size, wide levels.  A frame with more FAST corners than a level's candidate buffer
+    (16000) is refused with SFE_ERR_CAPACITY, never truncated."""
+    w, h = 3840, 2160
+    Ls, Rs = synth.stereo_sequence(2, 2, 4, 1280, 720)
+
+    def up(a):   # 3x upsampling + 3x3 box filter: 4K frames with a moderate corner density (~10 k on level 0)
+        b = np.pad(np.repeat(np.repeat(a.astype(np.float32), 3, axis=0), 3, axis=1), 1, mode="edge")
+        s = sum(b[dy:dy + h, dx:dx + w] for dy in range(3) for dx in range(3)) / 9.0
+        return np.clip(np.rint(s), 0, 255).astype(np.uint8)
+    L, R = np.stack([up(x) for x in Ls]), np.stack([up(x) for x in Rs])
+    cam = api.Camera.make(2100.0, 2100.0, w / 2.0, h / 2.0, (0, 0, 0, 0), w, h)
+    tp = api.TrackParams.make(cam, 0.5, None, 60.0)
+    ex = api.ORBextractor(5000, 1.2, 8, 20, 7, max_images=4)
+    ref = oracle.Extractor(5000, 1.2, 8, 20, 7)
+    rk, rd = ref.extract(L[0])
+    assert 3072 < max(len(ref.candidates(l)) for l in range(8)) <= 16000
+    out = ex.stereo_sequence(L, R, tp)
+    n = out["n_l"][0]
+    assert n == len(rk) and np.array_equal(out["kps_l"][0, :n], rk) and np.array_equal(out["desc_l"][0, :n], rd)
+    rkr, rdr = ref.extract(R[0])
+    si, sd = oracle.stereo_match(rk, rd, rkr, rdr)
+    assert np.array_equal(out["stereo_idx"][0, :n], si) and np.array_equal(out["stereo_dist"][0, :n], sd)
+    assert (si >= 0).sum() > 500
+    assert _check_tracking(oracle, out, 2, tp, np.eye(4)) > 200
+    dense, _ = synth.stereo_pair(2, w, h)     # ~44 k corners on level 0
+    with pytest.raises(api.SfeError) as err:
+        ex.extract(dense)
+    assert err.value.status == api.SFE_ERR_CAPACITY and "candidate buffer" in str(err.value)
+    k, d = ex.extract(L[0])                   # the handle is still usable afterwards
+    assert np.array_equal(k, rk) and np.array_equal(d, rd)
+
+
 def test_batch_equals_single(kitti_ex, oracle):
     imgs = np.stack([synth.stereo_pair(s)[i] for s in (4, 5) for i in (0, 1)])
     kps, desc, n = kitti_ex.extract_batch(imgs)
