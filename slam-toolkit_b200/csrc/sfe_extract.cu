@@ -405,7 +405,7 @@ struct ONode {
 struct OctSmem {
     uint32_t *pk[2];       // packed candidates, grouped by node
     uint16_t *own[2];      // list index of the node owning each position
-    uint16_t *qs;          // quadrant << 14 | slot within the child
+    uint16_t *qs;          // slot within the child node (the quadrant is recomputed from the coordinates)
     ONode *nd[2];
     uint16_t *eidx[2];     // creation order among expandable nodes (tie rule T1)
     uint32_t *child;       // [node][4]: child counts, then child start positions
@@ -465,8 +465,7 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
             const int x = v & 0xFFF, y = (v >> 12) & 0xFFF;
             const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
             const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);
-            const int s = atomicAdd(&M.child[i * 4 + q], 1u);
-            M.qs[p] = (uint16_t)(q << 14 | s);
+            M.qs[p] = (uint16_t)atomicAdd(&M.child[i * 4 + q], 1u);
         }
     }
     __syncthreads();
@@ -579,9 +578,13 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
     for (int p = tid; p < n; p += T) {
         const int i = M.own[cur][p];
         if (M.tord[i] >= 0) {
-            const int q = M.qs[p] >> 14, s = M.qs[p] & 0x3FFF;
-            const int np = M.child[i * 4 + q] + s;
-            M.pk[nxt][np] = M.pk[cur][p];
+            const ONode o = nd[i];
+            const uint32_t v = M.pk[cur][p];
+            const int x = v & 0xFFF, y = (v >> 12) & 0xFFF;
+            const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
+            const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);  // as in the counting loop above
+            const int np = M.child[i * 4 + q] + M.qs[p];
+            M.pk[nxt][np] = v;
             M.own[nxt][np] = M.childpos[i * 4 + q];
         } else {
             M.pk[nxt][p] = M.pk[cur][p];
