@@ -1,30 +1,26 @@
 #!/usr/bin/env python3
 """Latency of the reference-shaped calls (one image / one stereo frame per call, host buffers, synchronous):
-what ORB_SLAM2::ORBextractor::extract and the keyframe path cost when the caller does not batch."""
-import os
-import sys
-import time
-
+what ORB_SLAM2::ORBextractor::extract and the keyframe path cost when the caller does not batch, and how the
+kernel time of such a call splits over the stages (CUDA events)."""
+import os, sys, time
 import numpy as np
-
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from slam_toolkit_b200 import api, synth  # noqa: E402
-
+from slam_toolkit_b200 import api, synth
 L, R = synth.stereo_pair(0)
 ex = api.ORBextractor(max_images=2)
 pl, pr = api.PinnedArray(L.shape, np.uint8), api.PinnedArray(R.shape, np.uint8)
 pl.array[:], pr.array[:] = L, R
 out = ex.alloc_stereo_out(1, pinned=True)
 for _ in range(20):
-    ex.extract(pl.array)
-    ex.stereo_frames(pl.array[None], pr.array[None], out)
+    ex.extract(pl.array); ex.stereo_frames(pl.array[None], pr.array[None], out)
 n = 300
 t0 = time.perf_counter()
-for _ in range(n):
-    ex.extract(pl.array)
+for _ in range(n): ex.extract(pl.array)
 t1 = time.perf_counter()
-for _ in range(n):
-    ex.stereo_frames(pl.array[None], pr.array[None], out)
+for _ in range(n): ex.stereo_frames(pl.array[None], pr.array[None], out)
 t2 = time.perf_counter()
-print(f"extract(image): {1e6 * (t1 - t0) / n:.0f} us/call   stereo_frames(1 pair): {1e6 * (t2 - t1) / n:.0f} us/call "
-      f"({n / (t2 - t1):.0f} frames/s unbatched)")
+print(f"extract(image): {1e6*(t1-t0)/n:.0f} us/call   stereo_frames(1 pair): {1e6*(t2-t1)/n:.0f} us/call")
+ex.set_profiling(True)
+for _ in range(50): ex.stereo_frames(pl.array[None], pr.array[None], out)
+ms, calls = ex.stage_ms()
+print({k: round(1e3*v/calls,1) for k,v in ms.items()}, "us per call; sum", round(1e3*sum(ms.values())/calls,1))
