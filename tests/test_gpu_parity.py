@@ -274,6 +274,21 @@ def _check_tracking(oracle, out, frames, tp, rt):
     return tracked
 
 
+def test_stereo_sequence_vs_golden(kitti_ex, golden):
+    """The committed hashes of the 4-frame sequence (tools/gen_golden.py: cv2 restatement + matcher oracle)."""
+    g = golden["sequence"]
+    L, R = synth.stereo_sequence(5, 4, 4)
+    assert [sha(L), sha(R)] == g["inputs"]
+    out = kitti_ex.stereo_sequence(L, R, _kitti_track_params())
+    for f, fr in enumerate(g["frames"]):
+        n = out["n_l"][f]
+        assert sha(out["kps_l"][f, :n]) == fr["kps_l"] and sha(out["desc_l"][f, :n]) == fr["desc_l"]
+        assert sha(out["stereo_idx"][f, :n]) == fr["stereo_idx"]
+        if f:
+            assert sha(out["track_idx"][f, :n]) == fr["track_idx"] and sha(out["track_dist"][f, :n]) == fr["track_dist"]
+            assert int((out["track_idx"][f, :n] >= 0).sum()) == fr["n_tracked"]
+
+
 def test_stereo_sequence_tracking_vs_oracle(kitti_ex, oracle, monkeypatch):
     """sfe_stereo_sequence: the extraction / stereo outputs equal sfe_stereo_frames', and every frame's track_idx equals
     GetDepth + ProjectionMatch of the oracle on the previous frame (host path, pipelined host path, resident path)."""

@@ -81,3 +81,24 @@ def test_edge_cases(oracle):
     assert len(k) == 0
     k, d = ex.extract(np.full((376, 1241), 77, np.uint8))  # flat image: no corners anywhere
     assert len(k) == 0 and d.shape == (0, 32)
+
+
+def test_sequence_with_tracking(oracle, golden):
+    """4-frame stereo sequence: the C oracle's extraction equals the cv2 restatement's, and StereoMatch + the tracking
+    step (GetDepth + ProjectionMatch) reproduce the committed hashes."""
+    g = golden["sequence"]
+    L, R = synth.stereo_sequence(5, 4, 4)
+    assert [sha(L), sha(R)] == g["inputs"], "synthetic generator drifted"
+    cam = oracle.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0, 0, 0, 0], synth.KITTI_W, synth.KITTI_H)
+    ex = oracle.Extractor()
+    prev = None
+    for f, fr in enumerate(g["frames"]):
+        kl, dl = ex.extract(L[f])
+        kr, dr = ex.extract(R[f])
+        si, _ = oracle.stereo_match(kl, dl, kr, dr)
+        assert sha(kl) == fr["kps_l"] and sha(dl) == fr["desc_l"] and sha(si) == fr["stereo_idx"]
+        if prev is not None:
+            for grid in (False, True):
+                ti, td = oracle.track_pair(cam, synth.KITTI_BASELINE, np.eye(4), 50.0, *prev, kl, dl, grid=grid)
+                assert sha(ti) == fr["track_idx"] and sha(td) == fr["track_dist"] and int((ti >= 0).sum()) == fr["n_tracked"]
+        prev = (kl, dl, kr, si)
