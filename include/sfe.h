@@ -250,6 +250,13 @@ int sfe_frame_normalized(sfe_matcher *m, const sfe_frame *f, double *xy /* n x 2
 int sfe_frame_stereo_depth(sfe_matcher *m, const sfe_frame *f, const sfe_keypoint *kps_r, int n_r,
                            const int32_t *stereo_idx, double baseline, double *xc /* n x 3 */,
                            uint8_t *valid /* n */);
+/* ReprojectionFilter::GetOutlier's per-keypoint test quantity (src/posetracker.cpp:106-137): xw[i] = the map point of
+ * keypoint i (has_mp[i] != 0), err[i] = |Project(Tcw Xw) - keypoint| in pixels, +inf when the point is behind the camera
+ * (an outlier whatever the threshold), -1 without a map point.  The caller compares with max_reprojection_error.  (As
+ * written, the reference's own loop skips every map point the frame holds -- `GetIndex(mp) >= 0`, :118-119 -- so its
+ * filter never fires; the quantity is what the comparison at :131-133 would see.) */
+int sfe_frame_reprojection_error(sfe_matcher *m, const sfe_frame *f, const double *xw /* n x 3 */,
+                                 const uint8_t *has_mp /* n */, const double rt[12], double *err /* n */);
 /* ProjectionMatch against a resident frame (map points from host memory) */
 int sfe_frame_projection_match(sfe_matcher *m, const sfe_frame *f, const double *xw,
                                const uint8_t *mp_desc, const uint8_t *skip, int n, const double rt[12],

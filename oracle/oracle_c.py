@@ -71,6 +71,7 @@ def lib():
         L.orc_track_pair.argtypes = [vp, cd, vp, cd, cd, vp, vp, ci, vp, vp, vp, vp, ci, vp, vp, ci]
         L.orc_stereo_sequence.restype = C.c_int64
         L.orc_stereo_sequence.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp, cd, cd, vp, vp]
+        L.orc_reprojection_error.argtypes = [vp, vp, vp, ci, vp, vp, vp]
         L.orc_knn2.argtypes = [vp, ci, vp, C.c_int64, C.c_int64, vp]
         L.orc_stereo_frames.restype = C.c_int64
         L.orc_stereo_frames.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp]
@@ -257,6 +258,16 @@ def stereo_depth(cam, baseline, kps_l, norm_xy, kps_r, stereo_idx):
     lib().orc_stereo_depth(C.byref(cam), C.c_double(baseline), _p(kps_l), _p(norm_xy), len(kps_l), _p(kps_r), _p(stereo_idx),
                            _p(xc), _p(valid))
     return xc, valid
+
+
+def reprojection_error(cam, rt, kps, xw, has_mp):
+    kps = np.ascontiguousarray(kps)
+    xw = np.ascontiguousarray(xw, np.float64)
+    has_mp = np.ascontiguousarray(has_mp, np.uint8)
+    rt = np.ascontiguousarray(np.asarray(rt, np.float64)[:3, :4]).reshape(12)
+    err = np.zeros(len(kps), np.float64)
+    lib().orc_reprojection_error(C.byref(cam), _p(rt), _p(kps), len(kps), _p(xw), _p(has_mp), _p(err))
+    return err
 
 
 def search_radius(kps, u, v, radius, cap=4096):

@@ -806,6 +806,27 @@ void orc_stereo_depth(const orc_camera *cam, double baseline, const orc_keypoint
     }
 }
 
+/* ReprojectionFilter::GetOutlier src/posetracker.cpp:106-137, the quantity its threshold test sees: err[i] = the distance
+ * between keypoint i and Camera::Project(Tcw Xw_i) (src/camera.cpp:50-79, no IsInImage test here), +inf for z < 0 (:122-125
+ * flags those unconditionally), -1 when keypoint i has no map point (:115-116). */
+void orc_reprojection_error(const orc_camera *cam, const double rt[12], const orc_keypoint *kps, int n, const double *xw,
+                            const uint8_t *has_mp, double *err) {
+    for (int i = 0; i < n; i++) {
+        err[i] = -1.;
+        if (!has_mp[i]) continue;
+        const double X = xw[3 * i], Y = xw[3 * i + 1], Z = xw[3 * i + 2];
+        double xc = ((rt[0] * X + rt[1] * Y) + rt[2] * Z) + rt[3];
+        double yc = ((rt[4] * X + rt[5] * Y) + rt[6] * Z) + rt[7];
+        double zc = ((rt[8] * X + rt[9] * Y) + rt[10] * Z) + rt[11];
+        if (zc < 0.) { err[i] = INFINITY; continue; }
+        double x = xc / zc, y = yc / zc, xd, yd;
+        orc_distort(cam->d, x, y, &xd, &yd);
+        const double u = cam->fx * xd + cam->cx, v = cam->fy * yd + cam->cy;
+        const double dx = u - (double)kps[i].x, dy = v - (double)kps[i].y;
+        err[i] = sqrt(dx * dx + dy * dy);
+    }
+}
+
 /* Frame::SearchRadius src/frame.cpp:157-178 (FLANN radiusSearch with radius^2, L2<double> on the keypoints stored as
  * doubles): all keypoints with d^2 < r^2 (T4), canonical result order = ascending keypoint index.  Returns the count;
  * at most cap indices are written. */

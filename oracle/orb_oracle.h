@@ -91,6 +91,8 @@ void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64
 void orc_normalized_undistort(const orc_camera *cam, const orc_keypoint *kps, int n, double *xy);
 void orc_stereo_depth(const orc_camera *cam, double baseline, const orc_keypoint *kps_l, const double *norm_xy, int n,
                       const orc_keypoint *kps_r, const int *stereo_idx, double *xc, uint8_t *valid);
+void orc_reprojection_error(const orc_camera *cam, const double rt[12], const orc_keypoint *kps, int n, const double *xw,
+                            const uint8_t *has_mp, double *err);
 int orc_search_radius(const orc_keypoint *kps, int m, double u, double v, double radius, int *idx, int cap);
 void orc_search_nearest(const orc_keypoint *kps, int m, double u, double v, int *kpt_index, double *dist2);
 

@@ -128,6 +128,7 @@ SIGNATURES = {
     "sfe_frame_size": (_i, [_vp, C.POINTER(_i)]),
     "sfe_frame_normalized": (_i, [_vp, _vp, _vp]),
     "sfe_frame_stereo_depth": (_i, [_vp, _vp, _vp, _i, _vp, _d, _vp, _vp]),
+    "sfe_frame_reprojection_error": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sfe_frame_projection_match": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _d, _d, _vp, _vp]),
     "sfe_frame_search_radius": (_i, [_vp, _vp, _vp, _i, _d, _vp, _i, _vp]),
     "sfe_frame_search_nearest": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
@@ -597,6 +598,16 @@ class Frame:
         out = np.zeros((self.n, 2), np.float64)
         _check(lib().sfe_frame_normalized(self.m.h, self.h, _p(out)))
         return out
+
+    def reprojection_error(self, xw, has_mp, Tcw):
+        """ReprojectionFilter::GetOutlier's test quantity per keypoint: |Project(Tcw Xw_i) - keypoint_i|, +inf behind the
+        camera, -1 where has_mp[i] == 0."""
+        xw = np.ascontiguousarray(xw, np.float64)
+        has_mp = np.ascontiguousarray(has_mp, np.uint8)
+        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        err = np.zeros(self.n, np.float64)
+        _check(lib().sfe_frame_reprojection_error(self.m.h, self.h, _p(xw), _p(has_mp), _p(rt), _p(err)))
+        return err
 
     def stereo_depth(self, kps_r, stereo_idx, baseline):
         """StereoFrame::GetDepth for every keypoint -> (Xc n x 3 float64, valid n u8)."""

@@ -268,25 +268,33 @@ struct ProjParams {
 };
 
 // Xc = Tcw Xw, Camera::Project, IsInImage: false when the point is behind the camera, outside the image or not a number
+// Xc = Tcw Xw and Camera::Project (with distortion); false when the point is behind the camera (z < 0)
+__device__ __forceinline__ bool project_uv(const double rt[12], const sfe_camera &cam, double X, double Y, double Z, double &u, double &v);
+
 __device__ __forceinline__ bool project_point(const ProjParams &P, double X, double Y, double Z, double &u, double &v) {
+    if (!project_uv(P.rt, P.cam, X, Y, Z, u, v)) return false;  // :151-153
+    if (u < 0. || v < 0. || u > (double)P.cam.width || v > (double)P.cam.height) return false;  // IsInImage, :26-36
+    return u == u && v == v;  // NaN: the radius search finds nothing
+}
+
+__device__ __forceinline__ bool project_uv(const double rt[12], const sfe_camera &cam, double X, double Y, double Z, double &u, double &v) {
     // Xc = Tcw * Xw, evaluated left to right without contraction (:150)
-    const double xc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[0], X), __dmul_rn(P.rt[1], Y)), __dmul_rn(P.rt[2], Z)), P.rt[3]);
-    const double yc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[4], X), __dmul_rn(P.rt[5], Y)), __dmul_rn(P.rt[6], Z)), P.rt[7]);
-    const double zc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.rt[8], X), __dmul_rn(P.rt[9], Y)), __dmul_rn(P.rt[10], Z)), P.rt[11]);
-    if (zc < 0.) return false;  // :151-153
+    const double xc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[0], X), __dmul_rn(rt[1], Y)), __dmul_rn(rt[2], Z)), rt[3]);
+    const double yc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[4], X), __dmul_rn(rt[5], Y)), __dmul_rn(rt[6], Z)), rt[7]);
+    const double zc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[8], X), __dmul_rn(rt[9], Y)), __dmul_rn(rt[10], Z)), rt[11]);
+    if (zc < 0.) return false;
     // Camera::Project + Distort, src/camera.cpp:50-79
     const double x = __ddiv_rn(xc, zc), y = __ddiv_rn(yc, zc);
     const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), r4 = __dmul_rn(r2, r2);
     const double a1 = __dmul_rn(__dmul_rn(2., x), y);
     const double a2 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2., x), x));
     const double a3 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2., y), y));
-    const double cdist = __dadd_rn(__dadd_rn(1., __dmul_rn(P.cam.d[0], r2)), __dmul_rn(P.cam.d[1], r4));
-    const double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, cdist), __dmul_rn(P.cam.d[2], a1)), __dmul_rn(P.cam.d[3], a2));
-    const double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, cdist), __dmul_rn(P.cam.d[2], a3)), __dmul_rn(P.cam.d[3], a1));
-    u = __dadd_rn(__dmul_rn(P.cam.fx, xd), P.cam.cx);
-    v = __dadd_rn(__dmul_rn(P.cam.fy, yd), P.cam.cy);
-    if (u < 0. || v < 0. || u > (double)P.cam.width || v > (double)P.cam.height) return false;  // IsInImage, :26-36
-    return u == u && v == v;  // NaN: the radius search finds nothing
+    const double cdist = __dadd_rn(__dadd_rn(1., __dmul_rn(cam.d[0], r2)), __dmul_rn(cam.d[1], r4));
+    const double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, cdist), __dmul_rn(cam.d[2], a1)), __dmul_rn(cam.d[3], a2));
+    const double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, cdist), __dmul_rn(cam.d[2], a3)), __dmul_rn(cam.d[3], a1));
+    u = __dadd_rn(__dmul_rn(cam.fx, xd), cam.cx);
+    v = __dadd_rn(__dmul_rn(cam.fy, yd), cam.cy);
+    return true;
 }
 
 // One projected map point against the frame behind G: radius search over the bucket grid, best / second-best Hamming,
@@ -814,6 +822,27 @@ __global__ void __launch_bounds__(128) track_match_kernel(TrackArrays A, ProjPar
     load_desc(A.dl + ((size_t)prev * A.cap + i) * 32, a);
     const KpGrid G = track_grid(A, f);
     project_and_match(G, P, __dmul_rn(nrm.x, Z), __dmul_rn(nrm.y, Z), Z, a, (uint32_t)i, best + (size_t)f * A.cap);
+}
+
+// ReprojectionFilter::GetOutlier's per-keypoint quantity (src/posetracker.cpp:106-137): the distance between keypoint i
+// and the projection of its map point under Tcw; +inf when the point is behind the camera (an outlier whatever the
+// threshold), -1 when the keypoint has no map point
+__global__ void reprojection_error_kernel(sfe_camera cam, ProjParams P, const sfe_keypoint *__restrict__ kps, int n,
+                                          const double *__restrict__ xw, const uint8_t *__restrict__ has_mp,
+                                          double *__restrict__ err) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double e = -1.;
+    if (has_mp[i]) {
+        double u, v;
+        if (!project_uv(P.rt, cam, xw[3 * (size_t)i], xw[3 * (size_t)i + 1], xw[3 * (size_t)i + 2], u, v)) {
+            e = __longlong_as_double(0x7FF0000000000000ll);
+        } else {
+            const double dx = __dsub_rn(u, (double)kps[i].x), dy = __dsub_rn(v, (double)kps[i].y);
+            e = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));  // Eigen's norm() of a 2-vector
+        }
+    }
+    err[i] = e;
 }
 
 // Frame::SearchRadius / SearchNeareast over the bucket grid; one thread per query point.
@@ -1364,6 +1393,29 @@ int sfe_frame_stereo_depth(sfe_matcher *m, const sfe_frame *f, const sfe_keypoin
     SFE_CUDA(cudaGetLastError());
     SFE_CUDA(cudaMemcpyAsync(xc, m->d_xw.p, sizeof(double) * 3 * f->n, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaMemcpyAsync(valid, m->d_skip.p, f->n, cudaMemcpyDeviceToHost, st));
+    SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+int sfe_frame_reprojection_error(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *has_mp, const double rt[12],
+                                 double *err) {
+    SFE_REQUIRE(m && f && rt, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
+    if (f->n == 0) return SFE_OK;
+    SFE_REQUIRE(xw && has_mp && err, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(m->device);
+    cudaStream_t st = m->stream;
+    SFE_CUDA(m->d_xw.ensure((size_t)f->n * 4));  // n x 3 points, then n errors
+    SFE_CUDA(m->d_skip.ensure(f->n));
+    SFE_CUDA(cudaMemcpyAsync(m->d_xw.p, xw, sizeof(double) * 3 * f->n, cudaMemcpyHostToDevice, st));
+    SFE_CUDA(cudaMemcpyAsync(m->d_skip.p, has_mp, f->n, cudaMemcpyHostToDevice, st));
+    ProjParams P{};
+    memcpy(P.rt, rt, sizeof(P.rt));
+    reprojection_error_kernel<<<div_up(f->n, 128), 128, 0, st>>>(f->cam, P, f->kps.p, f->n, m->d_xw.p, m->d_skip.p,
+                                                                 m->d_xw.p + (size_t)f->n * 3);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    SFE_CUDA(cudaMemcpyAsync(err, m->d_xw.p + (size_t)f->n * 3, sizeof(double) * f->n, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaStreamSynchronize(st));
     return SFE_OK;
 }

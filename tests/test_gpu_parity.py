@@ -658,6 +658,17 @@ def test_resident_frame_glue_vs_oracle(gpu, oracle, kitti_ex):
             ri, rd = oracle.search_nearest(kps, uv[i, 0], uv[i, 1])
             assert gi[i] == ri and gd[i] == rd
         assert gi[0] == 5 and gd[0] == 0.0
+        # reprojection error of each keypoint's own stereo point under a slightly wrong pose (ReprojectionFilter::GetOutlier)
+        th = 0.004
+        Tcw = np.array([[np.cos(th), 0, np.sin(th), 0.03], [0, 1, 0, -0.01], [-np.sin(th), 0, np.cos(th), -0.4], [0, 0, 0, 1.0]])
+        xmp = xc.copy()
+        xmp[5] = [0.5, 0.2, 0.1]           # lands behind the camera after the -0.4 m shift
+        has = (valid == 1).astype(np.uint8)
+        has[5] = 1
+        err = f.reprojection_error(xmp, has, Tcw)
+        ref_err = oracle.reprojection_error(ocam, Tcw, kps, xmp, has)
+        assert np.array_equal(err.view(np.uint64), ref_err.view(np.uint64))
+        assert np.isinf(err[5]) and (err[has == 0] == -1).all() and 0 < np.median(err[(has == 1) & np.isfinite(err)]) < 30
         # ProjectionMatch against the resident frame == the plain entry point == the oracle
         xy = np.stack([kps["x"], kps["y"]], 1)
         xw, mpd = synth.projection_scene(xy, desc, 20000, seed=8)
