@@ -547,15 +547,26 @@ __global__ void __launch_bounds__(256) knn2_rows_kernel(const uint8_t *__restric
     uint32_t k0[QPL], k1[QPL];
 #pragma unroll
     for (int g = 0; g < QPL; g++) k0[g] = k1[g] = kNoKey;
-    for (long long r0 = c0 + warp * 64; r0 < c1; r0 += 8 * 64) {
-        uint32_t a[2][8];
-        bool valid[2];
+    // the rows of the next step are fetched before this step's distances are computed: two steps of loads in flight per warp
+    uint32_t a[2][8], nx[2][8];
+    bool valid[2], nvalid[2];
+    auto fetch = [&](long long r, uint32_t (&dst)[2][8], bool (&ok)[2]) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const long long row = r0 + h * 32 + lane;
-            valid[h] = row < c1;
-            if (valid[h]) load_desc(db + (size_t)row * 32, a[h]);
+            const long long row = r + h * 32 + lane;
+            ok[h] = row < c1;
+            if (ok[h]) load_desc(db + (size_t)row * 32, dst[h]);
         }
+    };
+    fetch(c0 + warp * 64, nx, nvalid);
+    for (long long r0 = c0 + warp * 64; r0 < c1; r0 += 8 * 64) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            valid[h] = nvalid[h];
+#pragma unroll
+            for (int k = 0; k < 8; k++) a[h][k] = nx[h][k];
+        }
+        fetch(r0 + 8 * 64, nx, nvalid);
         const uint32_t rel = (uint32_t)(r0 - c0) + lane;
 #pragma unroll
         for (int g = 0; g < QPL; g++) {
