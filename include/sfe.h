@@ -181,6 +181,9 @@ int sfe_image_pitch(int w);
  * enqueued on the handle's stream, so a caller can queue batch after batch without a host round trip
  * (consecutive calls reuse the handle's buffers in stream order).  Capacity errors of any queued batch are
  * kept on the device and reported by the next sfe_extractor_wait(), which also synchronises the stream.
+ * The matchers of an asynchronous stereo call run on a side stream beside the next call's extraction kernels; the
+ * handle orders every later writer of the same output arrays behind them, and sfe_extractor_wait() /
+ * sfe_event_record_extractor() cover them -- other streams must not read the outputs before one of the two.
  * The host entry points are always synchronous. */
 int sfe_extractor_set_async(sfe_extractor *ex, int enable);
 int sfe_extractor_wait(sfe_extractor *ex);
