@@ -971,11 +971,25 @@ constexpr bool pattern_within_patch() {
 static_assert(pattern_within_patch(), "a rotated pattern point could round outside the staged window");
 constexpr int kKpPerWarp = 4;  // keypoints one warp handles in turn: the pattern / disc table set-up is paid once
 
-__global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSet O) {
+// kTma: both windows of a keypoint -- the 31 rows x 48 bytes of the unblurred level around it for IC_Angle and the 37 rows x
+// 64 bytes of the blurred level for rBRIEF, each starting on the 16-byte grid of its row -- arrive by two TMA boxes issued by
+// lane 0 of the keypoint's warp; otherwise the lanes read the first with global loads and stage the second themselves.
+constexpr int kIcBoxW = 48, kIcBoxH = 2 * kHalfPatch + 1, kBdBoxW = 64, kBdBoxH = kPatchRows;
+constexpr int kIcBytes = 1536, kWinBytes = kIcBytes + 2432;  // per warp: IC box (1488 B) padded to 128, blurred box (2368 B) padded
+struct OrientMaps {
+    CUtensorMap ic[kMaxLevels], ic_l0b;  // unblurred levels (ic[0] / ic_l0b = the level-0 images of set A / set B of the call)
+    CUtensorMap bd[kMaxLevels];          // blurred levels
+};
+
+template <bool kTma>
+__global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSet O, const __grid_constant__ OrientMaps M) {
     __shared__ __half2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane` (|x|, |y| <= 13: exact in fp16)
-    __shared__ uint32_t patch_all[8][kPatchRows * kPatchWords];  // per warp: the blurred window the pattern can reach
+    __shared__ __align__(128) uint8_t win_all[8][kTma ? kWinBytes : kPatchRows * kPatchWords * 4];  // per warp: the windows
+    __shared__ uint64_t bars[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y, slot = slot_of(S, img);
-    uint32_t *patch = patch_all[warp];
+    uint32_t *patch = (uint32_t *)win_all[warp];
+    uint32_t phase = 0;
+    if (kTma && lane == 0) mbar_init(&bars[warp], 1);
     for (int i = tid; i < 512; i += 256) {
         const int byte = i >> 4, s = i & 15;
         pat[s * 32 + byte] = __floats2half2_rn((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
@@ -1021,7 +1035,31 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
         // start at any byte); the last word reaches x + 20 at most: keypoints keep 19 px from the border, so that
         // stays inside the row or spills 2 bytes into the next one.  Four pixels per IDP.4A.
         int m10 = 0, m01 = 0;
-        {
+        const int xl = x - kPatchR, xb0 = xl & ~15;  // blurred window: first column, and the 16-byte grid column before it
+        if (kTma) {
+            const int xi = x - kHalfPatch, xi0 = xi & ~15;
+            __syncwarp();  // the previous keypoint's reads of both windows are done
+            if (lane == 0) {
+                mbar_expect_tx(&bars[warp], kIcBoxW * kIcBoxH + kBdBoxW * kBdBoxH);
+                const bool sa = img < S.split;
+                const CUtensorMap *mi = l == 0 ? (sa ? &M.ic[0] : &M.ic_l0b) : &M.ic[l];
+                tma_load_3d(win_all[warp], mi, &bars[warp], xi0, y - kHalfPatch, l == 0 ? S.in_z0 + (sa ? img : img - S.split) : slot);
+                tma_load_3d(win_all[warp] + kIcBytes, &M.bd[l], &bars[warp], xb0, y - kPatchR, slot);
+            }
+            mbar_wait(&bars[warp], phase);
+            phase ^= 1;
+            const int o = xi - xi0;  // 0..15: byte offset of the window's first pixel inside the box row
+            const uint32_t *wp = (const uint32_t *)(win_all[warp] + wr0 * kIcBoxW + (o & ~3) + 4 * wj);
+            const uint32_t sh8 = (uint32_t)(o & 3) * 8;
+#pragma unroll
+            for (int t = 0; t < 8; t++, wp += 4 * (kIcBoxW / 4)) {
+                if (wr0 + 4 * t < 31) {
+                    const uint32_t px = __funnelshift_r(wp[0], wp[1], sh8);
+                    m10 = dp4a_u8s8(px, wu[t], m10);
+                    m01 += (wr0 + 4 * t - kHalfPatch) * dp4a_u8s8(px, win[t], 0);
+                }
+            }
+        } else {
             const uint8_t *rp = lvl + (size_t)(y - kHalfPatch + wr0) * pitch + (x - kHalfPatch + 4 * wj);
 #pragma unroll
             for (int t = 0; t < 8; t++, rp += 4 * (size_t)pitch) {
@@ -1055,19 +1093,27 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
         // around the keypoint: the warp copies it to shared memory with row-coalesced word loads (3 rows of 10 aligned
         // words per step; blurred planes have 16-byte pitches, so all rows share one alignment) and gathers from there
         // instead of sending 16 scattered loads per lane through L1.
-        const int bp = L.blur_pitch;
-        const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off;
-        const int xl = x - kPatchR, al = xl & 3;  // window's first column and its offset inside an aligned word
-        __syncwarp();                             // the previous keypoint's gathers are done
-        if (lane < 3 * kPatchWords) {
-            const int rs = lane / kPatchWords, c = lane - rs * kPatchWords;
-            const uint32_t *src = (const uint32_t *)(bl + (size_t)(y - kPatchR + rs) * bp + (xl - al)) + c;
-            uint32_t *dst = patch + rs * kPatchWords + c;
+        const uint8_t *pc;  // the keypoint's pixel inside the staged blurred window
+        int wpitch;
+        if (kTma) {
+            wpitch = kBdBoxW;
+            pc = win_all[warp] + kIcBytes + kPatchR * kBdBoxW + (xl - xb0) + kPatchR;
+        } else {
+            const int bp = L.blur_pitch;
+            const uint8_t *bl = S.blur + (size_t)slot * S.blur_stride + L.blur_off;
+            const int al = xl & 3;        // the window's first column inside an aligned word
+            __syncwarp();                 // the previous keypoint's gathers are done
+            if (lane < 3 * kPatchWords) {
+                const int rs = lane / kPatchWords, c = lane - rs * kPatchWords;
+                const uint32_t *src = (const uint32_t *)(bl + (size_t)(y - kPatchR + rs) * bp + (xl - al)) + c;
+                uint32_t *dst = patch + rs * kPatchWords + c;
 #pragma unroll
-            for (int r = rs; r < kPatchRows; r += 3, src += 3 * (bp >> 2), dst += 3 * kPatchWords) *dst = __ldg(src);
+                for (int r = rs; r < kPatchRows; r += 3, src += 3 * (bp >> 2), dst += 3 * kPatchWords) *dst = __ldg(src);
+            }
+            __syncwarp();
+            wpitch = kPatchWords * 4;
+            pc = (const uint8_t *)patch + kPatchR * (kPatchWords * 4) + kPatchR + al;
         }
-        __syncwarp();
-        const uint8_t *pc = (const uint8_t *)patch + kPatchR * (kPatchWords * 4) + kPatchR + al;  // the keypoint's pixel
         uint32_t byte = 0;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -1077,7 +1123,7 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
                 const float2 pp = __half22float2(pat[(2 * k + s) * 32 + lane]);
                 const int ry = __float2int_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)));
                 const int rx = __float2int_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)));
-                tv[s] = pc[ry * (kPatchWords * 4) + rx];
+                tv[s] = pc[ry * wpitch + rx];
             }
             byte |= (uint32_t)(tv[0] < tv[1]) << k;
         }
@@ -1125,6 +1171,7 @@ struct sfe_extractor {
     int octree_ctas = 0;    // SFE_OCTREE_CTAS: > 0 = persistent quadtree kernel with that many CTAs
     int sm_count = 148;
     bool piped_now = false; // a pipelined host call is enqueueing its sub-batches
+    bool orient_tma = true; // SFE_ORIENT_TMA=0: the orientation / descriptor kernel stages its windows with plain loads
     bool overlap_tail = true;   // SFE_OVERLAP_TAIL=0 turns it off: asynchronous resident stereo calls run StereoMatch + tracking on
     bool tail_pending = false;  // aux[1], beside the next call's pyramid / FAST (the next call's descriptor kernel, the first
                                 // writer of the caller's output arrays, waits for it: ev_join[1])
@@ -1147,6 +1194,7 @@ struct sfe_extractor {
     // TMA descriptors (fast: TP x tile_rows boxes, blur: 144 x 38 boxes); level >= 1 entries follow the plan,
     // level-0 entries follow the images of the current call
     alignas(64) TmaMaps fast_maps{}, blur_maps{}, pyr_maps{};  // pyr_maps.lv[l] = level l as the SOURCE of level l + 1
+    alignas(64) OrientMaps orient_maps{};                      // per-keypoint windows of the orientation / descriptor kernel
     int pyr_box_w = 0, pyr_box_h = 0;
     bool tma_plan_ok = false, tma_disabled = false, tma_now = false;
     const void *l0_key[2] = {nullptr, nullptr};
@@ -1424,7 +1472,14 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                           tma_encode_u8_3d(&ex->blur_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
                                            kBlurInWords * 4, kBlurTileH + 6) &&
                           (nl < 2 || tma_encode_u8_3d(&ex->pyr_maps.lv[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
-                                                      ex->pyr_box_w, ex->pyr_box_h));
+                                                      ex->pyr_box_w, ex->pyr_box_h)) &&
+                          tma_encode_u8_3d(&ex->orient_maps.ic[l], ex->d_pyr.p + L.plane_off, L.w, L.h, n, L.pitch, ex->pyr_stride,
+                                           kIcBoxW, kIcBoxH);
+    }
+    for (int l = 0; l < nl && ex->tma_plan_ok; l++) {
+        const LevelPlan &L = ex->lv[l];
+        ex->tma_plan_ok = tma_encode_u8_3d(&ex->orient_maps.bd[l], ex->d_blur.p + L.blur_off, L.w, L.h, n, L.blur_pitch, ex->blur_stride,
+                                           kBdBoxW, kBdBoxH);
     }
     ex->l0_key[0] = ex->l0_key[1] = nullptr;
     ex->pitch0 = (int)align_up((size_t)w, 16);
@@ -1502,7 +1557,9 @@ static void prepare_l0_maps(sfe_extractor *ex, const uint8_t *a, const uint8_t *
                         tma_encode_u8_3d(&ex->blur_maps.l0b, b, L.w, L.h, n_b, pitch, stride, kBlurInWords * 4, kBlurTileH + 6) &&
                         (ex->prm.nlevels < 2 ||
                          (tma_encode_u8_3d(&ex->pyr_maps.lv[0], a, L.w, L.h, n_a, pitch, stride, ex->pyr_box_w, ex->pyr_box_h) &&
-                          tma_encode_u8_3d(&ex->pyr_maps.l0b, b, L.w, L.h, n_b, pitch, stride, ex->pyr_box_w, ex->pyr_box_h)));
+                          tma_encode_u8_3d(&ex->pyr_maps.l0b, b, L.w, L.h, n_b, pitch, stride, ex->pyr_box_w, ex->pyr_box_h))) &&
+                        tma_encode_u8_3d(&ex->orient_maps.ic[0], a, L.w, L.h, n_a, pitch, stride, kIcBoxW, kIcBoxH) &&
+                        tma_encode_u8_3d(&ex->orient_maps.ic_l0b, b, L.w, L.h, n_b, pitch, stride, kIcBoxW, kIcBoxH);
         ex->l0_key[0] = ok ? a : nullptr;
         ex->l0_key[1] = ok ? b : nullptr;
         memcpy(ex->l0_geom, geom, sizeof(geom));
@@ -1618,7 +1675,10 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     } else if (ex->tail_pending) {
         SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[1], 0));
     }
-    orient_describe_kernel<<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O);
+    if (ex->tma_now && ex->orient_tma)
+        orient_describe_kernel<true><<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O, ex->orient_maps);
+    else
+        orient_describe_kernel<false><<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O, ex->orient_maps);
     prof_mark(ex, 5);
     ex->prof_pending = ex->profiling;
     ex->prof_has_stereo = ex->prof_has_track = false;
@@ -1870,6 +1930,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_OVERLAP_BLUR")) ex->overlap_blur = atoi(env);
     cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *env = getenv("SFE_OCTREE_CTAS")) ex->octree_ctas = atoi(env);
+    if (const char *env = getenv("SFE_ORIENT_TMA")) ex->orient_tma = atoi(env) != 0;
     if (const char *env = getenv("SFE_OVERLAP_TAIL")) ex->overlap_tail = atoi(env) != 0;
     if (const char *env = getenv("SFE_TRACE")) ex->trace = atoi(env) != 0;
     if (const char *env = getenv("SFE_COMPUTE_STREAMS")) ex->n_compute = std::max(1, std::min(atoi(env), kComputeStreams));
