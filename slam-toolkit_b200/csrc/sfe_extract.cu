@@ -994,13 +994,15 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
         const int byte = i >> 4, s = i & 15;
         pat[s * 32 + byte] = __floats2half2_rn((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
     }
-    // IC_Angle: the 31 x 32-byte window is 31 rows x 8 words; lane = word (lane & 7) of rows (lane >> 3) + 4 t,
-    // t = 0..7, so one warp-wide load touches 4 rows (4-8 cache lines).  The lane's weights stay in registers.
-    const int wj = lane & 7, wr0 = lane >> 3;
+    // IC_Angle: the 31 x 32-byte window is 31 rows x 8 words; lane = word (lane & 7) of the rows ic_row(t), t = 0..7: step t
+    // covers rows b, b + 2, b + 4, b + 6 with b = 8 (t / 2) + t % 2, so one warp-wide load touches 4 rows (4-8 cache
+    // lines) and, in the TMA box with its 12-word rows, 32 different banks.  The lane's weights stay in registers.
+    const int wj = lane & 7, wr0 = 2 * (lane >> 3);
+    auto ic_row = [wr0](int t) { return 8 * (t >> 1) + (t & 1) + wr0; };
     uint32_t wu[8], win[8];
 #pragma unroll
     for (int t = 0; t < 8; t++) {
-        const int r = wr0 + 4 * t, adv = r < 31 ? (r < kHalfPatch ? kHalfPatch - r : r - kHalfPatch) : 0;
+        const int r = ic_row(t), adv = r < 31 ? (r < kHalfPatch ? kHalfPatch - r : r - kHalfPatch) : 0;
         wu[t] = r < 31 ? __ldg(&g_disc.u[adv][wj]) : 0u;
         win[t] = r < 31 ? __ldg(&g_disc.in[adv][wj]) : 0u;
     }
@@ -1049,25 +1051,29 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
             mbar_wait(&bars[warp], phase);
             phase ^= 1;
             const int o = xi - xi0;  // 0..15: byte offset of the window's first pixel inside the box row
-            const uint32_t *wp = (const uint32_t *)(win_all[warp] + wr0 * kIcBoxW + (o & ~3) + 4 * wj);
+            const uint32_t *w0 = (const uint32_t *)(win_all[warp] + (o & ~3) + 4 * wj);
             const uint32_t sh8 = (uint32_t)(o & 3) * 8;
 #pragma unroll
-            for (int t = 0; t < 8; t++, wp += 4 * (kIcBoxW / 4)) {
-                if (wr0 + 4 * t < 31) {
+            for (int t = 0; t < 8; t++) {
+                const int r = ic_row(t);
+                if (r < 31) {
+                    const uint32_t *wp = w0 + r * (kIcBoxW / 4);
                     const uint32_t px = __funnelshift_r(wp[0], wp[1], sh8);
                     m10 = dp4a_u8s8(px, wu[t], m10);
-                    m01 += (wr0 + 4 * t - kHalfPatch) * dp4a_u8s8(px, win[t], 0);
+                    m01 += (r - kHalfPatch) * dp4a_u8s8(px, win[t], 0);
                 }
             }
         } else {
-            const uint8_t *rp = lvl + (size_t)(y - kHalfPatch + wr0) * pitch + (x - kHalfPatch + 4 * wj);
+            const uint8_t *r0p = lvl + (size_t)(y - kHalfPatch) * pitch + (x - kHalfPatch + 4 * wj);
 #pragma unroll
-            for (int t = 0; t < 8; t++, rp += 4 * (size_t)pitch) {
-                if (wr0 + 4 * t < 31) {
+            for (int t = 0; t < 8; t++) {
+                const int r = ic_row(t);
+                if (r < 31) {
+                    const uint8_t *rp = r0p + (size_t)r * pitch;
                     const uint32_t *wp = (const uint32_t *)((uintptr_t)rp & ~(uintptr_t)3);
                     const uint32_t px = __funnelshift_r(__ldg(wp), __ldg(wp + 1), ((uint32_t)(uintptr_t)rp & 3) * 8);
                     m10 = dp4a_u8s8(px, wu[t], m10);
-                    m01 += (wr0 + 4 * t - kHalfPatch) * dp4a_u8s8(px, win[t], 0);
+                    m01 += (r - kHalfPatch) * dp4a_u8s8(px, win[t], 0);
                 }
             }
         }
