@@ -405,6 +405,44 @@ def test_async_queue_with_matchers_on_the_side_stream(gpu):
     ex.set_async(False)
 
 
+def test_execution_variants_of_the_resident_path_agree(gpu, monkeypatch):
+    """Blur forked beside a persistent quadtree or serial, TMA or lane-staged windows in the descriptor kernel, matchers on
+    the side stream or not: every switch of DESIGN.md §10 leaves the bytes unchanged."""
+    F = 3
+    L, R = synth.stereo_sequence(6, F, 4)
+    tp = _kitti_track_params()
+    base = api.ORBextractor(max_images=2 * F).stereo_sequence(L, R, tp)
+    cap, h, w = base["kps_l"].shape[1], *L.shape[1:]
+    pitch = api.image_pitch(w)
+
+    def pitched(a):
+        out = np.zeros((a.shape[0], h, pitch), np.uint8)
+        out[:, :, :w] = a
+        return out
+    dl, dr = api.DeviceBuffer(F * pitch * h).upload(pitched(L)), api.DeviceBuffer(F * pitch * h).upload(pitched(R))
+    spec = {"kps_l": (28, api.KP_DTYPE, (F, cap)), "desc_l": (32, np.uint8, (F, cap, 32)), "n_l": (0, np.int32, (F,)),
+            "kps_r": (28, api.KP_DTYPE, (F, cap)), "desc_r": (32, np.uint8, (F, cap, 32)), "n_r": (0, np.int32, (F,)),
+            "stereo_idx": (4, np.int32, (F, cap)), "stereo_dist": (4, np.int32, (F, cap)), "track_idx": (4, np.int32, (F, cap)),
+            "track_dist": (4, np.int32, (F, cap))}
+    for env in ({}, {"SFE_OVERLAP_BLUR": "0"}, {"SFE_OVERLAP_BLUR": "1"}, {"SFE_ORIENT_TMA": "0"}, {"SFE_OVERLAP_TAIL": "0"},
+                {"SFE_OCTREE_CTAS": "7"}, {"SFE_NO_TMA": "1", "SFE_OVERLAP_BLUR": "2"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ex = api.ORBextractor(max_images=2 * F)
+        bufs = {k: api.DeviceBuffer(max(b * cap * F, 4 * F)) for k, (b, _, _) in spec.items()}
+        ex.set_async(True)
+        for _ in range(2):
+            ex.stereo_sequence_dev(dl.ptr, dr.ptr, F, w, h, {k: b.ptr for k, b in bufs.items()}, tp, pitch=pitch)
+        ex.wait()
+        got = {k: bufs[k].download(shape, dt) for k, (_, dt, shape) in spec.items()}
+        _stereo_equal(got, base, F)
+        for f in range(F):
+            n = base["n_l"][f]
+            assert np.array_equal(got["track_idx"][f, :n], base["track_idx"][f, :n]), env
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 def test_pipelined_sub_batches_and_load_paths_agree(gpu, oracle, monkeypatch):
     """The host entry point cuts a batch into sub-batches on several streams, and tiles are fetched either by
     TMA or by plain loads: every combination must give the same bytes, and those of the oracle."""
