@@ -63,11 +63,19 @@ def lib():
         L.orc_fast_atan2.argtypes = [cf, cf]
         L.orc_distribute.restype = ci
         L.orc_distribute.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, ci]
+        L.orc_distribute_ex.restype = ci
+        L.orc_distribute_ex.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, ci, vp]
+        L.orc_get_tie_cut.restype = ci
+        L.orc_get_tie_cut.argtypes = [vp, ci]
         L.orc_hamming256.restype = ci
         L.orc_hamming256.argtypes = [vp, vp]
         L.orc_stereo_match.argtypes = [vp, vp, ci, vp, vp, ci, cd, cd, cd, vp, vp]
         L.orc_projection_match.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, cd, vp, vp]
         L.orc_projection_match_grid.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, cd, vp, vp]
+        L.orc_projection_match_se3.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, cd, vp, vp]
+        L.orc_projection_match_grid_se3.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, cd, vp, vp]
+        L.orc_se3_apply.argtypes = [vp, vp, ci, vp]
+        L.orc_reprojection_error_se3.argtypes = [vp, vp, vp, ci, vp, vp, vp]
         L.orc_track_pair.argtypes = [vp, cd, vp, cd, cd, vp, vp, ci, vp, vp, vp, vp, ci, vp, vp, ci]
         L.orc_stereo_sequence.restype = C.c_int64
         L.orc_stereo_sequence.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp, cd, cd, vp, vp]
@@ -112,7 +120,7 @@ class Extractor:
     def extract(self, img):
         img = np.ascontiguousarray(img, np.uint8)
         h, w = img.shape if img.ndim == 2 else (0, 0)
-        cap = self.nfeatures + 4 * self.nlevels + 64
+        cap = self.nfeatures + 64 * self.nlevels + 64  # a level keeps all 4*n_ini first-split nodes even over its quota
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         n = self.L.orc_extract(self.h, _p(img) if img.size else None, w, h, w, _p(kps), _p(desc), cap)
@@ -141,6 +149,10 @@ class Extractor:
         out = np.zeros((cap, 3), np.float32)
         n = self.L.orc_get_candidates(self.h, l, _p(out), cap)
         return out[:n].copy()
+
+    def tie_cut(self, l):
+        """True when level l's quadtree stopped between two equally-full nodes (heap-address order decides in the reference)."""
+        return bool(self.L.orc_get_tie_cut(self.h, l))
 
     def distributed(self, l, cap=1 << 16):
         out = np.zeros((cap, 3), np.float32)
@@ -180,13 +192,14 @@ def fast_atan2(y, x):
     return np.float32(lib().orc_fast_atan2(float(y), float(x)))
 
 
-def distribute(xyr, min_x, max_x, min_y, max_y, n_want):
+def distribute(xyr, min_x, max_x, min_y, max_y, n_want, with_tie_cut=False):
     xyr = np.ascontiguousarray(xyr, np.float32)
     out = np.zeros((max(len(xyr), 1), 3), np.float32)
-    n = lib().orc_distribute(_p(xyr), len(xyr), min_x, max_x, min_y, max_y, n_want, _p(out), len(out))
+    cut = C.c_int(0)
+    n = lib().orc_distribute_ex(_p(xyr), len(xyr), min_x, max_x, min_y, max_y, n_want, _p(out), len(out), C.byref(cut))
     if n < 0:
         raise ValueError("distribute failed")
-    return out[:n].copy()
+    return (out[:n].copy(), bool(cut.value)) if with_tie_cut else out[:n].copy()
 
 
 def hamming256(a, b):
@@ -214,17 +227,31 @@ def make_camera(fx, fy, cx, cy, d, width, height):
     return cam
 
 
+def se3_apply(qt, x):
+    """Xc = t + q * x the way g2o::SE3Quat / Eigen evaluate it; qt = (qx, qy, qz, qw, tx, ty, tz)."""
+    qt = np.ascontiguousarray(qt, np.float64)
+    x = np.ascontiguousarray(x, np.float64).reshape(-1, 3)
+    out = np.zeros_like(x)
+    lib().orc_se3_apply(_p(qt), _p(x), len(x), _p(out))
+    return out
+
+
 def projection_match(xw, mp_desc, skip, rt, cam, kps, kp_desc, radius, ratio=0.5, grid=False):
+    """rt: 12 values = row-major 3x4 [R|t]; 7 values = g2o::SE3Quat (qx, qy, qz, qw, tx, ty, tz)."""
     xw = np.ascontiguousarray(xw, np.float64)
     mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
     skip = None if skip is None else np.ascontiguousarray(skip, np.uint8)
-    rt = np.ascontiguousarray(rt, np.float64).reshape(12)
+    rt = np.ascontiguousarray(rt, np.float64).reshape(-1)
+    assert rt.size in (7, 12)
     kps = np.ascontiguousarray(kps)
     kp_desc = np.ascontiguousarray(kp_desc, np.uint8)
     m = len(kps)
     to_q = np.full(m, -1, np.int32)
     dist = np.full(m, -1, np.int32)
-    fn = lib().orc_projection_match_grid if grid else lib().orc_projection_match
+    if rt.size == 7:
+        fn = lib().orc_projection_match_grid_se3 if grid else lib().orc_projection_match_se3
+    else:
+        fn = lib().orc_projection_match_grid if grid else lib().orc_projection_match
     fn(_p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), C.byref(cam), _p(kps), _p(kp_desc), m, radius, ratio, _p(to_q), _p(dist))
     return to_q, dist
 
@@ -264,8 +291,12 @@ def reprojection_error(cam, rt, kps, xw, has_mp):
     kps = np.ascontiguousarray(kps)
     xw = np.ascontiguousarray(xw, np.float64)
     has_mp = np.ascontiguousarray(has_mp, np.uint8)
-    rt = np.ascontiguousarray(np.asarray(rt, np.float64)[:3, :4]).reshape(12)
     err = np.zeros(len(kps), np.float64)
+    if np.size(rt) == 7:
+        qt = np.ascontiguousarray(rt, np.float64).reshape(7)
+        lib().orc_reprojection_error_se3(C.byref(cam), _p(qt), _p(kps), len(kps), _p(xw), _p(has_mp), _p(err))
+        return err
+    rt = np.ascontiguousarray(np.asarray(rt, np.float64)[:3, :4]).reshape(12)
     lib().orc_reprojection_error(C.byref(cam), _p(rt), _p(kps), len(kps), _p(xw), _p(has_mp), _p(err))
     return err
 

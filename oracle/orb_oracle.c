@@ -31,7 +31,7 @@ struct orc_extractor {
     int lw[MAXL], lh[MAXL];
     uint8_t *level[MAXL], *blur[MAXL];
     float *cands[MAXL], *dist[MAXL];
-    int ncands[MAXL], ndist[MAXL];
+    int ncands[MAXL], ndist[MAXL], tie_cut[MAXL];
 };
 
 /* ---- ctor tables: src/orb_extractor.cpp:410-470 ------------------------------------ */
@@ -356,8 +356,12 @@ static int szref_cmp(const void *a, const void *b) {
     return p->seq < q->seq ? -1 : (p->seq > q->seq ? 1 : 0); /* T1: creation order replaces the address */
 }
 
-int orc_distribute(const float *xyr, int n, int min_x, int max_x, int min_y, int max_y,
-                   int n_want, float *out, int cap) {
+/* tie_cut (optional): set to 1 when the careful phase stopped (:730-731) inside a group of nodes of EQUAL point count --
+ * or would have under another order of that group -- i.e. when the reference's heap-address order (:684) decides
+ * which of them are split; 0 = the survivor set does not depend on the tie rule (only its order does). */
+int orc_distribute_ex(const float *xyr, int n, int min_x, int max_x, int min_y, int max_y,
+                      int n_want, float *out, int cap, int *tie_cut) {
+    if (tie_cut) *tie_cut = 0;
     if (n <= 0) return 0;
     const int W = max_x - min_x, H = max_y - min_y;
     const int n_ini = (int)roundf((float)W / H);
@@ -415,6 +419,7 @@ int orc_distribute(const float *xyr, int n, int min_x, int max_x, int min_y, int
                 qsort(vprev, np, sizeof(szref), szref_cmp);
                 for (int j = np - 1; j >= 0; j--) {
                     int pi = vprev[j].seq, c[4];
+                    const int size_before = L.size;
                     divide(&L, pi, xyr, c);
                     for (int q = 0; q < 4; q++)
                         if (L.n[c[q]].cnt > 0) {
@@ -424,7 +429,22 @@ int orc_distribute(const float *xyr, int n, int min_x, int max_x, int min_y, int
                             }
                         }
                     list_erase(&L, pi);
-                    if (L.size >= n_want) break;
+                    vprev[j].seq = L.size - size_before; /* the slot now holds the node's growth (its id is spent) */
+                    if (L.size >= n_want) {
+                        if (tie_cut) {
+                            /* the stop is order-independent iff no other order of the equally-full group containing j
+                             * reaches n_want before the group is exhausted, and the group ends here */
+                            int e = j, total = 0, min_inc = 4;
+                            while (e + 1 < np && vprev[e + 1].cnt == vprev[j].cnt) e++;
+                            for (int t = j; t <= e; t++) {
+                                total += vprev[t].seq;
+                                if (vprev[t].seq < min_inc) min_inc = vprev[t].seq;
+                            }
+                            if (j > 0 && vprev[j - 1].cnt == vprev[j].cnt) *tie_cut = 1;
+                            else if (e > j && (L.size - total) + total - min_inc >= n_want) *tie_cut = 1;
+                        }
+                        break;
+                    }
                 }
                 if (L.size >= n_want || L.size == prev_size) finish = 1;
             }
@@ -445,6 +465,11 @@ int orc_distribute(const float *xyr, int n, int min_x, int max_x, int min_y, int
     for (int i = 0; i < L.used; i++) free(L.n[i].keys);
     free(L.n); free(roots); free(vsz); free(vprev);
     return m;
+}
+
+int orc_distribute(const float *xyr, int n, int min_x, int max_x, int min_y, int max_y,
+                   int n_want, float *out, int cap) {
+    return orc_distribute_ex(xyr, n, min_x, max_x, min_y, max_y, n_want, out, cap, NULL);
 }
 
 /* ---- per-cell FAST: src/orb_extractor.cpp:765-829 ------------------------------------ */
@@ -553,8 +578,9 @@ int orc_extract(orc_extractor *ex, const uint8_t *img, int w, int h, int stride,
         ex->ncands[l] = level_candidates(ex, ex->level[l], lw, lh, &ex->cands[l], bx);
         int nc = ex->ncands[l];
         ex->dist[l] = (float *)malloc(sizeof(float) * 3 * (nc > 0 ? nc : 1));
-        int nd = nc > 0 ? orc_distribute(ex->cands[l], nc, bx[0], bx[1], bx[2], bx[3],
-                                          ex->per_level[l], ex->dist[l], nc) : 0;
+        ex->tie_cut[l] = 0;
+        int nd = nc > 0 ? orc_distribute_ex(ex->cands[l], nc, bx[0], bx[1], bx[2], bx[3],
+                                             ex->per_level[l], ex->dist[l], nc, &ex->tie_cut[l]) : 0;
         if (nd < 0) return -3;
         ex->ndist[l] = nd;
     }
@@ -600,6 +626,7 @@ int orc_get_candidates(const orc_extractor *ex, int l, float *xyr, int cap) {
     if (n > 0) memcpy(xyr, ex->cands[l], sizeof(float) * 3 * n);
     return ex->ncands[l];
 }
+int orc_get_tie_cut(const orc_extractor *ex, int l) { return ex->tie_cut[l]; }
 int orc_get_distributed(const orc_extractor *ex, int l, float *xyr, int cap) {
     int n = ex->ndist[l] < cap ? ex->ndist[l] : cap;
     if (n > 0) memcpy(xyr, ex->dist[l], sizeof(float) * 3 * n);
@@ -650,11 +677,36 @@ void orc_stereo_match(const orc_keypoint *kl, const uint8_t *dl, int nl, const o
     }
 }
 
+/* ---- Xc = predicted_Tcw * Xw (src/matcher.cpp:151).  The reference holds the pose as a g2o::SE3Quat, so the product is
+ * g2o's `_t + _r * v` with Eigen's quaternion-vector product (Eigen/src/Geometry/Quaternion.h, _transformVector):
+ *   uv = q.vec x v;  uv += uv;  r = (v + q.w * uv) + q.vec x uv;   cross(a, b) = (a1 b2 - a2 b1, a2 b0 - a0 b2, a0 b1 - a1 b0)
+ * quat != 0: pose = {qx, qy, qz, qw, tx, ty, tz} (the unit quaternion as the SE3Quat holds it).
+ * quat == 0: pose = row-major 3x4 [R|t], rows evaluated left to right (for callers that hold a matrix; rule T6).
+ * tests/test_ref_pinning.py checks the quaternion form bit-for-bit against oracle/_ref. */
+static void apply_pose(const double *p, int quat, double X, double Y, double Z, double *xc, double *yc, double *zc) {
+    if (!quat) {
+        *xc = ((p[0] * X + p[1] * Y) + p[2] * Z) + p[3];
+        *yc = ((p[4] * X + p[5] * Y) + p[6] * Z) + p[7];
+        *zc = ((p[8] * X + p[9] * Y) + p[10] * Z) + p[11];
+        return;
+    }
+    const double qx = p[0], qy = p[1], qz = p[2], qw = p[3];
+    double ux = qy * Z - qz * Y, uy = qz * X - qx * Z, uz = qx * Y - qy * X;
+    ux += ux; uy += uy; uz += uz;
+    const double cx = qy * uz - qz * uy, cy = qz * ux - qx * uz, cz = qx * uy - qy * ux;
+    *xc = p[4] + ((X + qw * ux) + cx);
+    *yc = p[5] + ((Y + qw * uy) + cy);
+    *zc = p[6] + ((Z + qw * uz) + cz);
+}
+void orc_se3_apply(const double qt[7], const double *x, int n, double *out) {
+    for (int i = 0; i < n; i++) apply_pose(qt, 1, x[3 * i], x[3 * i + 1], x[3 * i + 2], out + 3 * i, out + 3 * i + 1, out + 3 * i + 2);
+}
+
 /* ---- ProjectionMatch: src/matcher.cpp:134-209 + Camera::Project src/camera.cpp:50-79 +
  * IsInImage :26-36 + FLANN radius search (strict d^2 < r^2, T4).  Map-point order = array
  * order (T3).  Tcw given as row-major [R|t] 3x4 (T: reference uses g2o::SE3Quat). */
-void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
-                          const double rt[12], const orc_camera *cam, const orc_keypoint *kps,
+static void projection_match_impl(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                          const double *rt, int quat, const orc_camera *cam, const orc_keypoint *kps,
                           const uint8_t *kp_desc, int m, double radius, double ratio,
                           int *kp_to_query, int *kp_dist) {
     for (int j = 0; j < m; j++) { kp_to_query[j] = -1; kp_dist[j] = -1; }
@@ -662,9 +714,8 @@ void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_
     for (int i = 0; i < n; i++) {
         if (skip && skip[i]) continue;
         const double X = xw[3 * i], Y = xw[3 * i + 1], Z = xw[3 * i + 2];
-        double xc = ((rt[0] * X + rt[1] * Y) + rt[2] * Z) + rt[3];
-        double yc = ((rt[4] * X + rt[5] * Y) + rt[6] * Z) + rt[7];
-        double zc = ((rt[8] * X + rt[9] * Y) + rt[10] * Z) + rt[11];
+        double xc, yc, zc;
+        apply_pose(rt, quat, X, Y, Z, &xc, &yc, &zc);
         if (zc < 0.) continue;
         double x = xc / zc, y = yc / zc;
         double r2 = x * x + y * y, r4 = r2 * r2;
@@ -699,8 +750,19 @@ void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_
  * CPU path is not charged an O(n m) scan the reference does not do.  Same candidate set (d^2 < r^2), hence the same
  * accepted matches for ratio <= 1 (a tie for the best distance fails the ratio test whatever the visiting order,
  * SURVEY §8a); tests/test_oracle_matchers.py checks it against orc_projection_match. */
-void orc_projection_match_grid(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
-                               const double rt[12], const orc_camera *cam, const orc_keypoint *kps,
+void orc_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n, const double rt[12],
+                          const orc_camera *cam, const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                          double ratio, int *kp_to_query, int *kp_dist) {
+    projection_match_impl(xw, mp_desc, skip, n, rt, 0, cam, kps, kp_desc, m, radius, ratio, kp_to_query, kp_dist);
+}
+void orc_projection_match_se3(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n, const double qt[7],
+                              const orc_camera *cam, const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                              double ratio, int *kp_to_query, int *kp_dist) {
+    projection_match_impl(xw, mp_desc, skip, n, qt, 1, cam, kps, kp_desc, m, radius, ratio, kp_to_query, kp_dist);
+}
+
+static void projection_match_grid_impl(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                               const double *rt, int quat, const orc_camera *cam, const orc_keypoint *kps,
                                const uint8_t *kp_desc, int m, double radius, double ratio,
                                int *kp_to_query, int *kp_dist) {
     for (int j = 0; j < m; j++) { kp_to_query[j] = -1; kp_dist[j] = -1; }
@@ -720,9 +782,8 @@ void orc_projection_match_grid(const double *xw, const uint8_t *mp_desc, const u
     for (int i = 0; i < n; i++) {
         if (skip && skip[i]) continue;
         const double X = xw[3 * i], Y = xw[3 * i + 1], Z = xw[3 * i + 2];
-        double xc = ((rt[0] * X + rt[1] * Y) + rt[2] * Z) + rt[3];
-        double yc = ((rt[4] * X + rt[5] * Y) + rt[6] * Z) + rt[7];
-        double zc = ((rt[8] * X + rt[9] * Y) + rt[10] * Z) + rt[11];
+        double xc, yc, zc;
+        apply_pose(rt, quat, X, Y, Z, &xc, &yc, &zc);
         if (zc < 0.) continue;
         double x = xc / zc, y = yc / zc;
         double r2 = x * x + y * y, r4 = r2 * r2;
@@ -757,6 +818,17 @@ void orc_projection_match_grid(const double *xw, const uint8_t *mp_desc, const u
         }
     }
     free(start); free(fill); free(order); free(cell);
+}
+
+void orc_projection_match_grid(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n, const double rt[12],
+                               const orc_camera *cam, const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                               double ratio, int *kp_to_query, int *kp_dist) {
+    projection_match_grid_impl(xw, mp_desc, skip, n, rt, 0, cam, kps, kp_desc, m, radius, ratio, kp_to_query, kp_dist);
+}
+void orc_projection_match_grid_se3(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n, const double qt[7],
+                                   const orc_camera *cam, const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                                   double ratio, int *kp_to_query, int *kp_dist) {
+    projection_match_grid_impl(xw, mp_desc, skip, n, qt, 1, cam, kps, kp_desc, m, radius, ratio, kp_to_query, kp_dist);
 }
 
 /* ---- Frame glue -------------------------------------------------------------
@@ -809,15 +881,14 @@ void orc_stereo_depth(const orc_camera *cam, double baseline, const orc_keypoint
 /* ReprojectionFilter::GetOutlier src/posetracker.cpp:106-137, the quantity its threshold test sees: err[i] = the distance
  * between keypoint i and Camera::Project(Tcw Xw_i) (src/camera.cpp:50-79, no IsInImage test here), +inf for z < 0 (:122-125
  * flags those unconditionally), -1 when keypoint i has no map point (:115-116). */
-void orc_reprojection_error(const orc_camera *cam, const double rt[12], const orc_keypoint *kps, int n, const double *xw,
-                            const uint8_t *has_mp, double *err) {
+static void reprojection_error_impl(const orc_camera *cam, const double *rt, int quat, const orc_keypoint *kps, int n,
+                                    const double *xw, const uint8_t *has_mp, double *err) {
     for (int i = 0; i < n; i++) {
         err[i] = -1.;
         if (!has_mp[i]) continue;
         const double X = xw[3 * i], Y = xw[3 * i + 1], Z = xw[3 * i + 2];
-        double xc = ((rt[0] * X + rt[1] * Y) + rt[2] * Z) + rt[3];
-        double yc = ((rt[4] * X + rt[5] * Y) + rt[6] * Z) + rt[7];
-        double zc = ((rt[8] * X + rt[9] * Y) + rt[10] * Z) + rt[11];
+        double xc, yc, zc;
+        apply_pose(rt, quat, X, Y, Z, &xc, &yc, &zc);
         if (zc < 0.) { err[i] = INFINITY; continue; }
         double x = xc / zc, y = yc / zc, xd, yd;
         orc_distort(cam->d, x, y, &xd, &yd);
@@ -825,6 +896,15 @@ void orc_reprojection_error(const orc_camera *cam, const double rt[12], const or
         const double dx = u - (double)kps[i].x, dy = v - (double)kps[i].y;
         err[i] = sqrt(dx * dx + dy * dy);
     }
+}
+
+void orc_reprojection_error(const orc_camera *cam, const double rt[12], const orc_keypoint *kps, int n, const double *xw,
+                            const uint8_t *has_mp, double *err) {
+    reprojection_error_impl(cam, rt, 0, kps, n, xw, has_mp, err);
+}
+void orc_reprojection_error_se3(const orc_camera *cam, const double qt[7], const orc_keypoint *kps, int n, const double *xw,
+                                const uint8_t *has_mp, double *err) {
+    reprojection_error_impl(cam, qt, 1, kps, n, xw, has_mp, err);
 }
 
 /* Frame::SearchRadius src/frame.cpp:157-178 (FLANN radiusSearch with radius^2, L2<double> on the keypoints stored as

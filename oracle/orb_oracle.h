@@ -50,6 +50,11 @@ int orc_get_score(const orc_extractor *ex, int level, uint8_t *out /* lw*lh, FAS
 int orc_get_candidates(const orc_extractor *ex, int level, float *xyr /* cap*3 */, int cap);
 int orc_get_distributed(const orc_extractor *ex, int level, float *xyr /* cap*3 */, int cap);
 
+/* 1 when level's quadtree stopped between two equally-full nodes (the reference's heap-address order decides, T1) */
+int orc_get_tie_cut(const orc_extractor *ex, int level);
+int orc_distribute_ex(const float *xyr, int n, int min_x, int max_x, int min_y, int max_y,
+                      int n_want, float *out_xyr, int cap, int *tie_cut);
+
 /* primitive models (pinned to cv2) */
 void orc_resize_linear_u8(const uint8_t *src, int sw, int sh, int sstride,
                           uint8_t *dst, int dw, int dh, int dstride);
@@ -81,6 +86,17 @@ void orc_projection_match_grid(const double *xw, const uint8_t *mp_desc, const u
                                const double rt[12], const orc_camera *cam,
                                const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
                                double ratio, int *kp_to_query, int *kp_dist);
+/* The same three with the pose as the reference holds it (g2o::SE3Quat, src/matcher.cpp:151): qt = {qx, qy, qz, qw, tx, ty, tz},
+ * Xc = t + q * Xw with Eigen's quaternion-vector product.  This is the form pinned bit-for-bit to oracle/_ref. */
+void orc_se3_apply(const double qt[7], const double *x, int n, double *out);
+void orc_projection_match_se3(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                              const double qt[7], const orc_camera *cam,
+                              const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                              double ratio, int *kp_to_query, int *kp_dist);
+void orc_projection_match_grid_se3(const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                                   const double qt[7], const orc_camera *cam,
+                                   const orc_keypoint *kps, const uint8_t *kp_desc, int m, double radius,
+                                   double ratio, int *kp_to_query, int *kp_dist);
 /* out[q*4] = {idx0, dist0, idx1, dist1}; lexicographic (dist, idx) top-2 */
 void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base,
               int32_t *out);
@@ -93,6 +109,8 @@ void orc_stereo_depth(const orc_camera *cam, double baseline, const orc_keypoint
                       const orc_keypoint *kps_r, const int *stereo_idx, double *xc, uint8_t *valid);
 void orc_reprojection_error(const orc_camera *cam, const double rt[12], const orc_keypoint *kps, int n, const double *xw,
                             const uint8_t *has_mp, double *err);
+void orc_reprojection_error_se3(const orc_camera *cam, const double qt[7], const orc_keypoint *kps, int n, const double *xw,
+                                const uint8_t *has_mp, double *err);
 int orc_search_radius(const orc_keypoint *kps, int m, double u, double v, double radius, int *idx, int cap);
 void orc_search_nearest(const orc_keypoint *kps, int m, double u, double v, int *kpt_index, double *dist2);
 
