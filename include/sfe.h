@@ -31,12 +31,15 @@
 extern "C" {
 #endif
 
-#define SFE_ABI_VERSION 1
+#define SFE_ABI_VERSION 2
 
 enum {
     SFE_OK = 0,
     SFE_ERR_BAD_ARG = 1,     /* null pointer, non-positive size, unsupported geometry */
-    SFE_ERR_CAPACITY = 2,    /* caller capacity or an internal candidate buffer too small */
+    SFE_ERR_CAPACITY = 2,    /* caller capacity too small; or one pyramid level of one image holds more than 60000 FAST
+                              * corners (the quadtree's candidate index).  The reference's candidate list is unbounded
+                              * (src/orb_extractor.cpp:778-779): below that limit a call whose internal candidate buffers
+                              * overflow is re-run with buffers sized from its own exact count, never refused. */
     SFE_ERR_CUDA = 3,        /* a CUDA runtime call failed; see sfe_last_error() */
     SFE_ERR_NO_DEVICE = 4,   /* no CUDA device (there is no CPU fallback) */
     SFE_ERR_UNSUPPORTED = 5  /* parameters outside what the kernels were built for */
@@ -76,6 +79,16 @@ typedef struct sfe_camera {
     int32_t width, height;
 } sfe_camera;
 
+/* predicted_Tcw as the reference holds it, a g2o::SE3Quat (src/matcher.cpp:135,151): unit quaternion + translation.
+ * The *_se3 entry points evaluate Xc = Tcw * Xw exactly as g2o / Eigen do (t + q * Xw with Eigen's quaternion-vector
+ * product, no contraction), so a point on the z = 0, image-border or radius boundary falls on the same side as in the
+ * reference.  The rt[12] entry points take a row-major 3x4 [R|t] for callers that hold a matrix (rows evaluated left to
+ * right); the two agree except in the last unit of precision of Xc. */
+typedef struct sfe_se3 {
+    double qx, qy, qz, qw; /* Eigen::Quaterniond::x(), y(), z(), w() of SE3Quat::rotation() */
+    double tx, ty, tz;     /* SE3Quat::translation() */
+} sfe_se3;
+
 typedef struct sfe_extractor sfe_extractor;
 typedef struct sfe_matcher sfe_matcher;
 typedef struct sfe_db sfe_db;
@@ -111,7 +124,11 @@ int sfe_extractor_destroy(sfe_extractor *ex);
 int sfe_extractor_tables(const sfe_extractor *ex, float *scale, float *inv_scale, float *sigma2,
                          float *inv_sigma2, int32_t *features_per_level);
 int sfe_extractor_level_size(const sfe_extractor *ex, int w, int h, int level, int *lw, int *lh);
-/* upper bound of keypoints one image can return (nfeatures + 3 per level + slack) */
+/* Upper bound of the keypoints one w x h image can return: per level max(quota + 3, 4 * nIni) -- DistributeOctTree stops at
+ * the first size >= N and one split adds at most 3 nodes, but its first pass over the nIni root nodes is unconditional
+ * (src/orb_extractor.cpp:543,606-669).  sfe_extractor_max_keypoints uses the geometry of the last call (before any call:
+ * aspect ratios up to 4.5 : 1). */
+int sfe_extractor_max_keypoints_for(const sfe_extractor *ex, int w, int h, int *cap);
 int sfe_extractor_max_keypoints(const sfe_extractor *ex, int *cap);
 
 /* extract(): one 8-bit gray image in, keypoints + 256-bit descriptors out (row i <-> keypoint i).
@@ -157,6 +174,8 @@ typedef struct sfe_track_params {
     double rt[12];            /* Tcw (3x4 row-major) applied to the previous frame's camera-frame points */
     double radius;            /* ProjectionMatch search radius in pixels (the tracker uses 50) */
     double best12_threshold;  /* 0.5, src/matcher.cpp:196 */
+    int32_t use_se3;          /* != 0: the motion prior is `se3` (evaluated like g2o::SE3Quat), rt is ignored */
+    sfe_se3 se3;
 } sfe_track_params;
 int sfe_stereo_sequence(sfe_extractor *ex, const uint8_t *left, const uint8_t *right,
                         size_t image_stride, int frames, int w, int h, int stride,
@@ -236,6 +255,18 @@ int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t
                              double best12_threshold, int32_t *kp_to_query_dev,
                              int32_t *kp_dist_dev);
 
+/* the same with the pose as a g2o::SE3Quat: what the adapter's ProjectionMatch calls */
+int sfe_projection_match_se3(sfe_matcher *m, const double *xw, const uint8_t *mp_desc,
+                             const uint8_t *skip, int n, const sfe_se3 *Tcw, const sfe_camera *cam,
+                             const sfe_keypoint *kps, const uint8_t *kp_desc, int m_kps, double radius,
+                             double best12_threshold, int32_t *kp_to_query, int32_t *kp_dist);
+int sfe_projection_match_se3_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev,
+                                 const uint8_t *skip_dev, int n, const sfe_se3 *Tcw,
+                                 const sfe_camera *cam, const sfe_keypoint *kps_dev,
+                                 const uint8_t *kp_desc_dev, int m_kps, double radius,
+                                 double best12_threshold, int32_t *kp_to_query_dev,
+                                 int32_t *kp_dist_dev);
+
 /* ---- resident frames: the work of Frame::Frame after extract() (src/frame.cpp:50-69) ----------------------
  * A frame keeps its keypoints + descriptors on the device, with the normalised undistorted keypoints
  * (Camera::NormalizedUndistort, src/camera.cpp:95-109: what Frame::GetNormalizedPoint returns) and the spatial index
@@ -260,13 +291,20 @@ int sfe_frame_stereo_depth(sfe_matcher *m, const sfe_frame *f, const sfe_keypoin
  * filter never fires; the quantity is what the comparison at :131-133 would see.) */
 int sfe_frame_reprojection_error(sfe_matcher *m, const sfe_frame *f, const double *xw /* n x 3 */,
                                  const uint8_t *has_mp /* n */, const double rt[12], double *err /* n */);
+int sfe_frame_reprojection_error_se3(sfe_matcher *m, const sfe_frame *f, const double *xw /* n x 3 */,
+                                     const uint8_t *has_mp /* n */, const sfe_se3 *Tcw, double *err /* n */);
 /* ProjectionMatch against a resident frame (map points from host memory) */
 int sfe_frame_projection_match(sfe_matcher *m, const sfe_frame *f, const double *xw,
                                const uint8_t *mp_desc, const uint8_t *skip, int n, const double rt[12],
                                double radius, double best12_threshold, int32_t *kp_to_query,
                                int32_t *kp_dist);
-/* Frame::SearchRadius (src/frame.cpp:157-178) for q points: idx[i*cap ..] = keypoints with d^2 < radius^2 in
- * ascending index order (at most cap of them), counts[i] = how many there are (may exceed cap). */
+int sfe_frame_projection_match_se3(sfe_matcher *m, const sfe_frame *f, const double *xw,
+                                   const uint8_t *mp_desc, const uint8_t *skip, int n, const sfe_se3 *Tcw,
+                                   double radius, double best12_threshold, int32_t *kp_to_query,
+                                   int32_t *kp_dist);
+/* Frame::SearchRadius (src/frame.cpp:157-178) for q points: idx[i*cap ..] = the keypoints with d^2 < radius^2 in
+ * ascending index order, counts[i] = how many there are.  When counts[i] > cap the row holds the cap SMALLEST indices
+ * (call again with cap >= counts[i] for all of them). */
 int sfe_frame_search_radius(sfe_matcher *m, const sfe_frame *f, const double *uv /* q x 2 */, int q,
                             double radius, int32_t *idx /* q x cap */, int cap, int32_t *counts);
 /* Frame::SearchNeareast (src/frame.cpp:180-193): nearest keypoint and SQUARED distance (FLANN L2), ties towards
@@ -305,6 +343,11 @@ int sfe_projection_match_keys_dev(sfe_matcher *m, const double *xw_dev, const ui
                                   const sfe_camera *cam, const sfe_keypoint *kps_dev,
                                   const uint8_t *kp_desc_dev, int m_kps, double radius,
                                   double best12_threshold, uint64_t *keys_dev /* m_kps */);
+int sfe_projection_match_keys_se3_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev,
+                                      const uint8_t *skip_dev, int n, int64_t idx_base, const sfe_se3 *Tcw,
+                                      const sfe_camera *cam, const sfe_keypoint *kps_dev,
+                                      const uint8_t *kp_desc_dev, int m_kps, double radius,
+                                      double best12_threshold, uint64_t *keys_dev /* m_kps */);
 int sfe_projection_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int m_kps,
                              int32_t *kp_to_query_dev, int32_t *kp_dist_dev);
 

@@ -85,6 +85,9 @@ public:
         if (_image.empty()) return;
         cv::Mat image = _image.getMat();
         if (image.type() != CV_8UC1) throw std::invalid_argument("ORBextractor::extract: CV_8UC1 image expected");
+        int need = 0;  // a very wide image can return more than the default bound (4 * nIni nodes per level)
+        sfe_adapter::check(sfe_extractor_max_keypoints_for(ex_, image.cols, image.rows, &need), "sfe_extractor_max_keypoints_for");
+        if (need > cap_) { cap_ = need; kps_.resize(cap_); }
         desc_.resize((size_t)cap_ * 32);
         int n = 0;
         sfe_adapter::check(sfe_extract(ex_, image.data, image.cols, image.rows, (int)image.step, kps_.data(), desc_.data(),
@@ -151,7 +154,9 @@ void StereoMatch(StereoFrameT *frame) {
 }
 
 // std::map<int, Mappoint*> ProjectionMatch(const std::set<Mappoint*>&, const g2o::SE3Quat&, const Frame*, double)
-//   -- include/matcher.h:35-38.  PoseT needs rotation().toRotationMatrix() and translation() (g2o::SE3Quat has both).
+//   -- include/matcher.h:35-38.  PoseT needs rotation() -> a quaternion with x(), y(), z(), w() and translation()
+//   (g2o::SE3Quat has both); the pose travels as that unit quaternion + translation and the device evaluates
+//   predicted_Tcw * Xw the way g2o / Eigen do (sfe_se3), so boundary points fall on the reference's side.
 template <class MappointT, class PoseT, class FrameT>
 std::map<int, MappointT *> ProjectionMatch(const std::set<MappointT *> &mappoints, const PoseT &predicted_Tcw,
                                            const FrameT *curr_frame, double search_radius) {
@@ -169,13 +174,9 @@ std::map<int, MappointT *> ProjectionMatch(const std::set<MappointT *> &mappoint
         desc.insert(desc.end(), d.data, d.data + 32);
         skip.push_back(curr_frame->GetIndex(mp) >= 0 ? 1 : 0);  // :144
     }
-    const auto R = predicted_Tcw.rotation().toRotationMatrix();
-    const auto t = predicted_Tcw.translation();
-    double rt[12];
-    for (int r = 0; r < 3; r++) {
-        for (int c = 0; c < 3; c++) rt[4 * r + c] = R(r, c);
-        rt[4 * r + 3] = t[r];
-    }
+    const auto &q = predicted_Tcw.rotation();
+    const auto &t = predicted_Tcw.translation();
+    const sfe_se3 Tcw = {q.x(), q.y(), q.z(), q.w(), t[0], t[1], t[2]};
     sfe_camera cam;
     const auto &K = camera->GetK();
     const auto &D = camera->GetD();
@@ -187,10 +188,10 @@ std::map<int, MappointT *> ProjectionMatch(const std::set<MappointT *> &mappoint
     std::vector<uint8_t> kdesc(kps.size() * 32);
     for (size_t i = 0; i < kps.size(); i++) std::memcpy(&kdesc[i * 32], curr_frame->GetDescription((int)i).data, 32);
     std::vector<int32_t> to_query(kps.size(), -1);
-    check(sfe_projection_match(thread_matcher(), xw.data(), desc.data(), skip.data(), (int)order.size(), rt, &cam,
-                               (const sfe_keypoint *)kps.data(), kdesc.data(), (int)kps.size(), search_radius,
-                               best12_threshold, to_query.data(), nullptr),
-          "sfe_projection_match");
+    check(sfe_projection_match_se3(thread_matcher(), xw.data(), desc.data(), skip.data(), (int)order.size(), &Tcw, &cam,
+                                   (const sfe_keypoint *)kps.data(), kdesc.data(), (int)kps.size(), search_radius,
+                                   best12_threshold, to_query.data(), nullptr),
+          "sfe_projection_match_se3");
     std::map<int, MappointT *> matches;
     for (size_t j = 0; j < kps.size(); j++)
         if (to_query[j] >= 0) matches[(int)j] = order[(size_t)to_query[j]];

@@ -81,6 +81,7 @@ def lib():
         L.orc_stereo_sequence.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp, cd, cd, vp, vp]
         L.orc_reprojection_error.argtypes = [vp, vp, vp, ci, vp, vp, vp]
         L.orc_knn2.argtypes = [vp, ci, vp, C.c_int64, C.c_int64, vp]
+        L.orc_knn2_mt.argtypes = [vp, ci, vp, C.c_int64, C.c_int64, vp, ci]
         L.orc_stereo_frames.restype = C.c_int64
         L.orc_stereo_frames.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp]
         _lib = L
@@ -328,11 +329,11 @@ def vocab_transform(parent, is_leaf, node_desc, node_weight, L, features, levels
     return wid, w, nid
 
 
-def knn2(queries, db, idx_base=0):
+def knn2(queries, db, idx_base=0, nthreads=1):
     queries = np.ascontiguousarray(queries, np.uint8)
     db = np.ascontiguousarray(db, np.uint8)
     out = np.zeros((len(queries), 4), np.int32)
-    lib().orc_knn2(_p(queries), len(queries), _p(db), len(db), idx_base, _p(out))
+    lib().orc_knn2_mt(_p(queries), len(queries), _p(db), len(db), idx_base, _p(out), int(nthreads))
     return out
 
 

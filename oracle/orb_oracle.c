@@ -982,21 +982,97 @@ void orc_vocab_transform(int n_nodes, const int32_t *parent, const uint8_t *is_l
 /* ---- brute-force top-2: the StereoMatch/ProjectionMatch inner loop
  * with the whole database as candidate set; strict < in ascending index = lexicographic
  * (dist, idx). */
-void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base,
-              int32_t *out) {
-    for (int i = 0; i < q; i++) {
-        int d0 = 999999999, d1 = 999999999;
-        int64_t i0 = -1, i1 = -1;
-        for (int64_t j = 0; j < m; j++) {
-            int d = orc_hamming256(queries + (size_t)32 * i, db + (size_t)32 * j);
-            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
-            else if (d < d1) { d1 = d; i1 = j; }
-        }
-        out[4 * i] = (int32_t)(i0 < 0 ? -1 : i0 + idx_base);
-        out[4 * i + 1] = d0;
-        out[4 * i + 2] = (int32_t)(i1 < 0 ? -1 : i1 + idx_base);
-        out[4 * i + 3] = d1;
+/* Brute-force top-2: per query the lexicographically smallest two (distance, row index), i.e. the strict-< ascending-index
+ * loop of src/matcher.cpp:114-123 over the whole database.  Queries are split over threads; every thread walks the
+ * database in cache-sized tiles of rows (ascending, so ties still resolve towards the smaller index) and scans each tile
+ * for all of its queries, which is what makes the 2000 x 10 M case of BASELINE config 4 checkable in seconds.
+ * The distance is DescriptorDistance (orc_hamming256's SWAR count) computed with the popcount instruction when the CPU
+ * has one -- the same integer. */
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("popcnt"))) static int hamming256_popcnt(const uint64_t *a, const uint64_t *b) {
+    return __builtin_popcountll(a[0] ^ b[0]) + __builtin_popcountll(a[1] ^ b[1]) + __builtin_popcountll(a[2] ^ b[2]) +
+           __builtin_popcountll(a[3] ^ b[3]);
+}
+__attribute__((target("popcnt"))) static void knn2_tile_popcnt(const uint64_t *qv, const uint8_t *rows, int64_t j0, int64_t j1,
+                                                               int *d0, int *d1, int64_t *i0, int64_t *i1) {
+    for (int64_t j = j0; j < j1; j++) {
+        uint64_t r[4];
+        memcpy(r, rows + (size_t)32 * j, 32);
+        const int d = hamming256_popcnt(qv, r);
+        if (d < *d0) { *d1 = *d0; *i1 = *i0; *d0 = d; *i0 = j; }
+        else if (d < *d1) { *d1 = d; *i1 = j; }
     }
+}
+#define ORC_HAVE_POPCNT_PATH 1
+#endif
+
+typedef struct {
+    const uint8_t *queries, *db;
+    int q0, q1;
+    int64_t m, idx_base;
+    int32_t *out;
+    int use_popcnt;
+} knn_job;
+
+static void *knn_worker(void *arg) {
+    knn_job *jb = (knn_job *)arg;
+    const int nq = jb->q1 - jb->q0;
+    if (nq <= 0) return NULL;
+    int *d0 = (int *)malloc(sizeof(int) * nq), *d1 = (int *)malloc(sizeof(int) * nq);
+    int64_t *i0 = (int64_t *)malloc(sizeof(int64_t) * nq), *i1 = (int64_t *)malloc(sizeof(int64_t) * nq);
+    for (int i = 0; i < nq; i++) { d0[i] = d1[i] = 999999999; i0[i] = i1[i] = -1; }
+    const int64_t tile = 1024; /* 32 KB of rows: stays in L1/L2 while every query of this thread scans it */
+    for (int64_t t0 = 0; t0 < jb->m; t0 += tile) {
+        const int64_t t1 = t0 + tile < jb->m ? t0 + tile : jb->m;
+        for (int i = 0; i < nq; i++) {
+            const uint8_t *qp = jb->queries + (size_t)32 * (jb->q0 + i);
+#ifdef ORC_HAVE_POPCNT_PATH
+            if (jb->use_popcnt) {
+                uint64_t qv[4];
+                memcpy(qv, qp, 32);
+                knn2_tile_popcnt(qv, jb->db, t0, t1, &d0[i], &d1[i], &i0[i], &i1[i]);
+                continue;
+            }
+#endif
+            for (int64_t j = t0; j < t1; j++) {
+                const int d = orc_hamming256(qp, jb->db + (size_t)32 * j);
+                if (d < d0[i]) { d1[i] = d0[i]; i1[i] = i0[i]; d0[i] = d; i0[i] = j; }
+                else if (d < d1[i]) { d1[i] = d; i1[i] = j; }
+            }
+        }
+    }
+    for (int i = 0; i < nq; i++) {
+        int32_t *o = jb->out + 4 * (size_t)(jb->q0 + i);
+        o[0] = (int32_t)(i0[i] < 0 ? -1 : i0[i] + jb->idx_base);
+        o[1] = d0[i];
+        o[2] = (int32_t)(i1[i] < 0 ? -1 : i1[i] + jb->idx_base);
+        o[3] = d1[i];
+    }
+    free(d0); free(d1); free(i0); free(i1);
+    return NULL;
+}
+
+void orc_knn2_mt(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base, int32_t *out, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 256) nthreads = 256;
+    if (nthreads > q) nthreads = q > 0 ? q : 1;
+    int use_popcnt = 0;
+#ifdef ORC_HAVE_POPCNT_PATH
+    use_popcnt = __builtin_cpu_supports("popcnt") ? 1 : 0;
+#endif
+    knn_job jobs[256];
+    pthread_t th[256];
+    for (int t = 0; t < nthreads; t++) {
+        knn_job jb = {queries, db, (int)((int64_t)q * t / nthreads), (int)((int64_t)q * (t + 1) / nthreads), m, idx_base, out, use_popcnt};
+        jobs[t] = jb;
+    }
+    for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, knn_worker, &jobs[t]);
+    knn_worker(&jobs[0]);
+    for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+}
+
+void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base, int32_t *out) {
+    orc_knn2_mt(queries, q, db, m, idx_base, out, 1);
 }
 
 /* ---- Tracking step between consecutive stereo frames: the previous frame's keypoints that have a stereo

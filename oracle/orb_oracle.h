@@ -100,6 +100,9 @@ void orc_projection_match_grid_se3(const double *xw, const uint8_t *mp_desc, con
 /* out[q*4] = {idx0, dist0, idx1, dist1}; lexicographic (dist, idx) top-2 */
 void orc_knn2(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base,
               int32_t *out);
+/* the same with the queries split over nthreads worker threads (database walked in cache-sized tiles) */
+void orc_knn2_mt(const uint8_t *queries, int q, const uint8_t *db, int64_t m, int64_t idx_base,
+                 int32_t *out, int nthreads);
 
 /* frame glue: src/camera.cpp:95-109, src/frame.cpp:50-56,157-193,391-409.
  * T6 (canonical): SearchNeareast resolves equal distances towards the smaller keypoint index; SearchRadius lists

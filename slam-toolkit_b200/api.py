@@ -51,17 +51,39 @@ class Camera(C.Structure):
         return c
 
 
+class SE3(C.Structure):
+    """sfe_se3: g2o::SE3Quat as the reference's ProjectionMatch receives it (unit quaternion x, y, z, w + translation)."""
+    _fields_ = [("qx", C.c_double), ("qy", C.c_double), ("qz", C.c_double), ("qw", C.c_double),
+                ("tx", C.c_double), ("ty", C.c_double), ("tz", C.c_double)]
+
+
+def _pose(Tcw):
+    """A pose argument is either 7 numbers (qx, qy, qz, qw, tx, ty, tz) = g2o::SE3Quat -> ("_se3", SE3) or a 3x4 / 4x4
+    matrix [R|t] -> ("", 12 doubles)."""
+    a = np.asarray(Tcw, np.float64)
+    if a.ndim == 1 and a.size == 7:
+        return "_se3", SE3(*[float(v) for v in a])
+    return "", np.ascontiguousarray(a[:3, :4]).reshape(12)
+
+
+def _pose_arg(p):
+    return C.byref(p) if isinstance(p, SE3) else _p(p)
+
+
 class TrackParams(C.Structure):
-    """sfe_track_params: camera, stereo baseline, motion prior Tcw (3x4), ProjectionMatch radius and ratio."""
+    """sfe_track_params: camera, stereo baseline, motion prior Tcw (3x4 matrix or SE3), ProjectionMatch radius and ratio."""
     _fields_ = [("cam", Camera), ("baseline", C.c_double), ("rt", C.c_double * 12), ("radius", C.c_double),
-                ("best12_threshold", C.c_double)]
+                ("best12_threshold", C.c_double), ("use_se3", C.c_int32), ("se3", SE3)]
 
     @staticmethod
     def make(cam, baseline, Tcw=None, radius=50.0, best12=0.5):
         t = TrackParams()
         t.cam, t.baseline, t.radius, t.best12_threshold = cam, baseline, radius, best12
-        rt = np.eye(4)[:3, :4] if Tcw is None else np.asarray(Tcw, np.float64)[:3, :4]
-        for i, v in enumerate(np.ascontiguousarray(rt).reshape(12)):
+        kind, pose = _pose(np.eye(4) if Tcw is None else Tcw)
+        if kind:
+            t.use_se3, t.se3 = 1, pose
+            pose = np.eye(4)[:3, :4].reshape(12)
+        for i, v in enumerate(pose):
             t.rt[i] = v
         return t
 
@@ -90,6 +112,7 @@ SIGNATURES = {
     "sfe_extractor_tables": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sfe_extractor_level_size": (_i, [_vp, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "sfe_extractor_max_keypoints": (_i, [_vp, C.POINTER(_i)]),
+    "sfe_extractor_max_keypoints_for": (_i, [_vp, _i, _i, C.POINTER(_i)]),
     "sfe_extract": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, C.POINTER(_i)]),
     "sfe_extract_batch": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
     "sfe_extract_batch_dev": (_i, [_vp, _vp, _sz, _i, _i, _i, _i, _vp, _vp, _i, _vp]),
@@ -122,6 +145,11 @@ SIGNATURES = {
     "sfe_projection_match_dev": (_i, [_vp, _vp, _vp, _vp, _i, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
     "sfe_projection_match_keys_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp]),
     "sfe_projection_merge_dev": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "sfe_projection_match_se3": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(SE3), C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
+    "sfe_projection_match_se3_dev": (_i, [_vp, _vp, _vp, _vp, _i, C.POINTER(SE3), C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp, _vp]),
+    "sfe_projection_match_keys_se3_dev": (_i, [_vp, _vp, _vp, _vp, _i, _i64, C.POINTER(SE3), C.POINTER(Camera), _vp, _vp, _i, _d, _d, _vp]),
+    "sfe_frame_reprojection_error_se3": (_i, [_vp, _vp, _vp, _vp, C.POINTER(SE3), _vp]),
+    "sfe_frame_projection_match_se3": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(SE3), _d, _d, _vp, _vp]),
     "sfe_frame_create": (_i, [_vp, _vp, _vp, _i, C.POINTER(Camera), _pp]),
     "sfe_frame_create_dev": (_i, [_vp, _vp, _vp, _i, C.POINTER(Camera), _pp]),
     "sfe_frame_destroy": (_i, [_vp]),
@@ -159,7 +187,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.sfe_abi_version() != 1:
+        if L.sfe_abi_version() != 2:
             raise SfeError(SFE_ERR_UNSUPPORTED, "libsfe.so ABI version mismatch")
         _lib = L
     return _lib
@@ -293,6 +321,15 @@ class ORBextractor:
         self.cap = cap.value
         self._wh = None
 
+    def cap_for(self, w, h) -> int:
+        """upper bound of the keypoints one w x h image returns (sfe_extractor_max_keypoints_for)"""
+        cap = C.c_int()
+        _check(lib().sfe_extractor_max_keypoints_for(self.h, w, h, C.byref(cap)))
+        return cap.value
+
+    def _grow_cap(self, w, h):  # a very wide image can return more than the default bound: 4 * nIni nodes per level
+        self.cap = max(self.cap, self.cap_for(w, h))
+
     def close(self):
         if getattr(self, "h", None):
             lib().sfe_extractor_destroy(self.h)
@@ -344,6 +381,7 @@ class ORBextractor:
             return np.zeros(0, KP_DTYPE), np.zeros((0, 32), np.uint8)
         assert image.ndim == 2, "CV_8UC1 expected (reference asserts the same, src/orb_extractor.cpp:1050)"
         h, w = image.shape
+        self._grow_cap(w, h)
         kps = np.zeros(self.cap, KP_DTYPE)
         desc = np.zeros((self.cap, 32), np.uint8)
         n = C.c_int()
@@ -356,6 +394,7 @@ class ORBextractor:
         images = np.ascontiguousarray(images, np.uint8)
         count, h, w = images.shape
         if out is None:
+            self._grow_cap(w, h)
             out = (np.zeros((count, self.cap), KP_DTYPE), np.zeros((count, self.cap, 32), np.uint8), np.zeros(count, np.int32))
         kps, desc, n = out
         _check(lib().sfe_extract_batch(self.h, _p(images), w * h, count, w, h, w, _p(kps), _p(desc), self.cap, _p(n)))
@@ -375,6 +414,7 @@ class ORBextractor:
         f, h, w = left.shape
         assert right.shape == left.shape
         if out is None:
+            self._grow_cap(w, h)
             out = self.alloc_stereo_out(f)
         sp = C.byref(stereo_params) if stereo_params is not None else None
         _check(lib().sfe_stereo_frames(self.h, _p(left), _p(right), w * h, f, w, h, w, sp, _p(out["kps_l"]), _p(out["desc_l"]),
@@ -392,6 +432,7 @@ class ORBextractor:
         f, h, w = left.shape
         assert right.shape == left.shape
         if out is None:
+            self._grow_cap(w, h)
             out = self.alloc_stereo_out(f, track=True)
         sp = C.byref(stereo_params) if stereo_params is not None else None
         _check(lib().sfe_stereo_sequence(self.h, _p(left), _p(right), w * h, f, w, h, w, sp, C.byref(track_params),
@@ -518,32 +559,35 @@ class Matcher:
 
     def ProjectionMatch(self, xw, mp_desc, skip, Tcw, camera, kps, kp_desc, search_radius, best12=0.5):
         """-> (kp_to_query, kp_dist): for every frame keypoint the matched map-point index or -1
-        (the reference's std::map<int, Mappoint*>, src/matcher.cpp:134-209).  Tcw: 3x4 [R|t]."""
+        (the reference's std::map<int, Mappoint*>, src/matcher.cpp:134-209).  Tcw: 7 numbers (qx, qy, qz, qw, tx, ty, tz) =
+        the reference's g2o::SE3Quat, or a 3x4 [R|t] matrix."""
         xw = np.ascontiguousarray(xw, np.float64)
         mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
         skip = None if skip is None else np.ascontiguousarray(skip, np.uint8)
-        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        kind, pose = _pose(Tcw)
         kps = np.ascontiguousarray(kps, KP_DTYPE)
         kp_desc = np.ascontiguousarray(kp_desc, np.uint8)
         to_q = np.full(len(kps), -1, np.int32)
         dist = np.full(len(kps), -1, np.int32)
-        _check(lib().sfe_projection_match(self.h, _p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), C.byref(camera), _p(kps),
-                                          _p(kp_desc), len(kps), search_radius, best12, _p(to_q), _p(dist)))
+        _check(getattr(lib(), "sfe_projection_match" + kind)(self.h, _p(xw), _p(mp_desc), _p(skip), len(xw), _pose_arg(pose),
+                                                             C.byref(camera), _p(kps), _p(kp_desc), len(kps), search_radius,
+                                                             best12, _p(to_q), _p(dist)))
         return to_q, dist
 
     def projection_match_dev(self, xw_ptr, mp_desc_ptr, skip_ptr, n, Tcw, camera, kps_ptr, kp_desc_ptr, m, radius,
                              to_q_ptr, dist_ptr, best12=0.5):
-        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
-        _check(lib().sfe_projection_match_dev(self.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n, _p(rt), C.byref(camera),
-                                              _p(kps_ptr), _p(kp_desc_ptr), m, radius, best12, _p(to_q_ptr), _p(dist_ptr)))
+        kind, pose = _pose(Tcw)
+        _check(getattr(lib(), f"sfe_projection_match{kind}_dev")(self.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n,
+                                                                 _pose_arg(pose), C.byref(camera), _p(kps_ptr), _p(kp_desc_ptr),
+                                                                 m, radius, best12, _p(to_q_ptr), _p(dist_ptr)))
 
     def projection_match_keys_dev(self, xw_ptr, mp_desc_ptr, skip_ptr, n, idx_base, Tcw, camera, kps_ptr, kp_desc_ptr, m,
                                   radius, keys_ptr, best12=0.5):
         """One shard of a sharded ProjectionMatch: map points [idx_base, idx_base + n) -> m per-keypoint keys."""
-        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
-        _check(lib().sfe_projection_match_keys_dev(self.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n, idx_base, _p(rt),
-                                                   C.byref(camera), _p(kps_ptr), _p(kp_desc_ptr), m, radius, best12,
-                                                   _p(keys_ptr)))
+        kind, pose = _pose(Tcw)
+        _check(getattr(lib(), f"sfe_projection_match_keys{kind}_dev")(self.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n,
+                                                                      idx_base, _pose_arg(pose), C.byref(camera), _p(kps_ptr),
+                                                                      _p(kp_desc_ptr), m, radius, best12, _p(keys_ptr)))
 
     def projection_merge_dev(self, keys_ptr, shards, m, to_q_ptr, dist_ptr):
         _check(lib().sfe_projection_merge_dev(self.h, _p(keys_ptr), shards, m, _p(to_q_ptr), _p(dist_ptr)))
@@ -604,9 +648,9 @@ class Frame:
         camera, -1 where has_mp[i] == 0."""
         xw = np.ascontiguousarray(xw, np.float64)
         has_mp = np.ascontiguousarray(has_mp, np.uint8)
-        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        kind, pose = _pose(Tcw)
         err = np.zeros(self.n, np.float64)
-        _check(lib().sfe_frame_reprojection_error(self.m.h, self.h, _p(xw), _p(has_mp), _p(rt), _p(err)))
+        _check(getattr(lib(), "sfe_frame_reprojection_error" + kind)(self.m.h, self.h, _p(xw), _p(has_mp), _pose_arg(pose), _p(err)))
         return err
 
     def stereo_depth(self, kps_r, stereo_idx, baseline):
@@ -622,11 +666,11 @@ class Frame:
         xw = np.ascontiguousarray(xw, np.float64)
         mp_desc = np.ascontiguousarray(mp_desc, np.uint8)
         skip = None if skip is None else np.ascontiguousarray(skip, np.uint8)
-        rt = np.ascontiguousarray(np.asarray(Tcw, np.float64)[:3, :4]).reshape(12)
+        kind, pose = _pose(Tcw)
         to_q = np.full(self.n, -1, np.int32)
         dist = np.full(self.n, -1, np.int32)
-        _check(lib().sfe_frame_projection_match(self.m.h, self.h, _p(xw), _p(mp_desc), _p(skip), len(xw), _p(rt), search_radius,
-                                                best12, _p(to_q), _p(dist)))
+        _check(getattr(lib(), "sfe_frame_projection_match" + kind)(self.m.h, self.h, _p(xw), _p(mp_desc), _p(skip), len(xw),
+                                                                   _pose_arg(pose), search_radius, best12, _p(to_q), _p(dist)))
         return to_q, dist
 
     def SearchRadius(self, uv, radius, cap=512):

@@ -125,6 +125,7 @@ int sfe_device_alloc(int device, void **ptr, size_t bytes) {
 
 int sfe_device_free(int device, void *ptr) {
     DeviceGuard g(device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     if (ptr) SFE_CUDA(cudaFree(ptr));
     return SFE_OK;
 }
@@ -132,6 +133,7 @@ int sfe_device_free(int device, void *ptr) {
 int sfe_copy_to_device(int device, void *dst_dev, const void *src_host, size_t bytes) {
     SFE_REQUIRE(dst_dev && src_host, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     SFE_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
     return SFE_OK;
 }
@@ -139,6 +141,7 @@ int sfe_copy_to_device(int device, void *dst_dev, const void *src_host, size_t b
 int sfe_copy_to_host(int device, void *dst_host, const void *src_dev, size_t bytes) {
     SFE_REQUIRE(dst_host && src_dev, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     SFE_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
     return SFE_OK;
 }
@@ -161,6 +164,7 @@ int sfe_event_create(int device, sfe_event **ev) {
 int sfe_event_destroy(sfe_event *ev) {
     if (!ev) return SFE_OK;
     DeviceGuard g(ev->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaEventDestroy(ev->ev);
     delete ev;
     return SFE_OK;
@@ -169,6 +173,7 @@ int sfe_event_destroy(sfe_event *ev) {
 int sfe_event_elapsed_ms(sfe_event *start, sfe_event *stop, float *ms) {
     SFE_REQUIRE(start && stop && ms, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(stop->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     SFE_CUDA(cudaEventSynchronize(stop->ev));
     SFE_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
     return SFE_OK;

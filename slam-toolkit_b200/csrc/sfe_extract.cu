@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <mutex>
+#include <type_traits>
 
 #include "sfe_extract.cuh"
 
@@ -397,15 +398,23 @@ __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) fast_segments_ke
 // function of coordinates, and the only order-dependent step (first max response wins, :742-760)
 // uses the explicit order key of the reference's cell-major / raster candidate list.
 // ---------------------------------------------------------------------------------------------
-struct ONode {
+// kWide = false: a level holds at most 60000 candidates and positions / counts fit 16 bits (14 B of working set per
+// candidate, 12-byte nodes); kWide = true: 32-bit positions for fuller levels (dense 4K frames, noise), always on global
+// scratch.  Same code, same results; the narrow instance is the one every ordinary frame runs.
+template <bool kWide>
+struct ONodeT {
+    typedef typename std::conditional<kWide, uint32_t, unsigned short>::type pos_t;
     short x0, x1, y0, y1;
-    unsigned short start, cnt;
+    pos_t start, cnt;
 };
 
-struct OctSmem {
+template <bool kWide>
+struct OctSmemT {
+    typedef ONodeT<kWide> ONode;
+    typedef typename ONode::pos_t pos_t;
     uint32_t *pk[2];       // packed candidates, grouped by node
     uint16_t *own[2];      // list index of the node owning each position
-    uint16_t *qs;          // slot within the child node (the quadrant is recomputed from the coordinates)
+    pos_t *qs;             // slot within the child node (the quadrant is recomputed from the coordinates)
     ONode *nd[2];
     uint16_t *eidx[2];     // creation order among expandable nodes (tie rule T1)
     uint32_t *child;       // [node][4]: child counts, then child start positions
@@ -451,8 +460,11 @@ __device__ int block_excl_scan(int *a, int n, int *warp_sums) {
 // One pass over the node list.  careful == false: split every expandable node in list order
 // (:594-665).  careful == true: split expandable nodes in descending (count, creation order)
 // until the list reaches n_want (:673-738).  Returns new list size; *n_expand = new |E|.
-__device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool careful, int *n_expand,
+template <bool kWide>
+__device__ int octree_pass(OctSmemT<kWide> &M, int cur, int n, int nL, int n_want, bool careful, int *n_expand,
                            int *sh_misc) {
+    typedef ONodeT<kWide> ONode;
+    typedef typename ONode::pos_t pos_t;
     const int tid = threadIdx.x, T = blockDim.x, nxt = cur ^ 1;
     const ONode *nd = M.nd[cur];
     for (int i = tid; i < nL * 4; i += T) M.child[i] = 0;
@@ -465,7 +477,7 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
             const int x = v & 0xFFF, y = (v >> 12) & 0xFFF;
             const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
             const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);
-            M.qs[p] = (uint16_t)atomicAdd(&M.child[i * 4 + q], 1u);
+            M.qs[p] = (pos_t)atomicAdd(&M.child[i * 4 + q], 1u);
         }
     }
     __syncthreads();
@@ -478,16 +490,20 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
         for (int i = tid; i < nL; i += T) M.tord[i] = nd[i].cnt > 1 ? M.arr_a[i] : -1;
         __syncthreads();
     } else {
-        for (int i = tid; i < nL; i += T)
-            M.arr_a[i] = nd[i].cnt > 1 ? (int)((uint32_t)nd[i].cnt << 16 | M.eidx[cur][i]) : 0;
+        // rank by (count, creation order) descending: count in arr_a (0 = not expandable), creation order in eidx
+        for (int i = tid; i < nL; i += T) M.arr_a[i] = nd[i].cnt > 1 ? (int)nd[i].cnt : 0;
         __syncthreads();
         int n_e_local = 0;
         for (int i = tid; i < nL; i += T) {
-            const int key = M.arr_a[i];
+            const int cnt_i = M.arr_a[i];
             int rank = -1;
-            if (key > 0) {
+            if (cnt_i > 0) {
+                const int e_i = M.eidx[cur][i];
                 rank = 0;
-                for (int j = 0; j < nL; j++) rank += M.arr_a[j] > key;
+                for (int j = 0; j < nL; j++) {
+                    const int cnt_j = M.arr_a[j];
+                    rank += cnt_j > cnt_i || (cnt_j == cnt_i && M.eidx[cur][j] > e_i);
+                }
                 n_e_local++;
             }
             M.tord[i] = rank;
@@ -557,8 +573,8 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
                     c.x1 = (q & 1) ? o.x1 : mx;
                     c.y0 = (q & 2) ? my : o.y0;
                     c.y1 = (q & 2) ? o.y1 : my;
-                    c.start = (unsigned short)(o.start + off);
-                    c.cnt = (unsigned short)cc[q];
+                    c.start = (pos_t)(o.start + off);
+                    c.cnt = (pos_t)cc[q];
                     M.nd[nxt][pos] = c;
                     M.eidx[nxt][pos] = (uint16_t)(cc[q] > 1 ? ep + ke : 0);
                     M.childpos[i * 4 + q] = (uint16_t)pos;
@@ -598,8 +614,12 @@ __device__ int octree_pass(OctSmem &M, int cur, int n, int nL, int n_want, bool 
 // Candidate-sized arrays (14 B per candidate) live in shared memory when the level has at most smem_cand
 // candidates -- sized for the common case so that several CTAs fit an SM -- and otherwise in one of the
 // handle's global scratch slots (same code, generic pointers; L2-resident).
+template <bool kWide>
 __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, int smem_cand, int max_cand, int max_nodes,
                             uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
+    typedef ONodeT<kWide> ONode;
+    typedef typename ONode::pos_t pos_t;
+    constexpr int kCandBytes = 2 * 4 + 2 * 2 + (int)sizeof(pos_t);
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int sh_misc[4];
     const int img = slot_of(S, image), tid = threadIdx.x, T = blockDim.x;  // internal buffers only
@@ -625,17 +645,17 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
             return;
         }
         ccap = max_cand;
-        cbase = scratch + (size_t)slot * max_cand * 14;
+        cbase = scratch + (size_t)slot * max_cand * kCandBytes;
     }
-    OctSmem M;
+    OctSmemT<kWide> M;
     {
         uint8_t *p = cbase;
         M.pk[0] = (uint32_t *)p; p += sizeof(uint32_t) * ccap;
         M.pk[1] = (uint32_t *)p; p += sizeof(uint32_t) * ccap;
         M.own[0] = (uint16_t *)p; p += sizeof(uint16_t) * ccap;
         M.own[1] = (uint16_t *)p; p += sizeof(uint16_t) * ccap;
-        M.qs = (uint16_t *)p;
-        p = smem_raw + (size_t)smem_cand * 14;
+        M.qs = (pos_t *)p;
+        p = smem_raw + (size_t)smem_cand * kCandBytes;
         M.child = (uint32_t *)p; p += sizeof(uint32_t) * 4 * max_nodes;
         M.tord = (int *)p; p += sizeof(int) * max_nodes;
         M.arr_a = (int *)p; p += sizeof(int) * max_nodes;
@@ -658,7 +678,7 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
         int r = (int)__fdiv_rn((float)(v & 0xFFF), hx);
         r = min(r, n_ini - 1);
         M.own[1][p] = (uint16_t)r;
-        M.qs[p] = (uint16_t)atomicAdd(&M.child[r], 1u);
+        M.qs[p] = (pos_t)atomicAdd(&M.child[r], 1u);
     }
     __syncthreads();
     for (int i = tid; i < n_ini; i += T) {
@@ -676,8 +696,8 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
             o.x1 = (short)(int)__fmul_rn(hx, (float)(i + 1));
             o.y0 = 0;
             o.y1 = (short)L.win_h;
-            o.start = (unsigned short)M.arr_a[i];
-            o.cnt = (unsigned short)c;
+            o.start = (pos_t)M.arr_a[i];
+            o.cnt = (pos_t)c;
             M.nd[0][M.arr_b[i]] = o;
             M.eidx[0][M.arr_b[i]] = 0;
         }
@@ -725,13 +745,13 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
         const ONode o = M.nd[cur][i];
         uint32_t best = 0;
         unsigned long long best_key = 0;
-        for (int p = o.start; p < o.start + o.cnt; p++) {
+        for (int p = (int)o.start; p < (int)(o.start + o.cnt); p++) {
             const uint32_t v = M.pk[cur][p];
             const uint32_t x = v & 0xFFF, y = (v >> 12) & 0xFFF, r = v >> 24;
             const uint32_t ci = (y - 3) / L.h_cell, cj = (x - 3) / L.w_cell;
             const unsigned long long ord = (((unsigned long long)ci * 4096 + cj) * 4096 + y) * 4096 + x;
             const unsigned long long key = (unsigned long long)r << 48 | (0xFFFFFFFFFFFFull - ord);
-            if (p == o.start || key > best_key) { best_key = key; best = v; }
+            if (p == (int)o.start || key > best_key) { best_key = key; best = v; }
         }
         out[i] = best;
     }
@@ -741,11 +761,12 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
 // (level, image) items in level-major order -- the fullest levels first -- handed out round-robin: with one CTA per item
 // this is the plain launch, with fewer CTAs (SFE_OCTREE_CTAS) the kernel is persistent and leaves shared memory to a
 // kernel running beside it.
+template <bool kWide>
 __global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int count, int smem_cand, int max_cand, int max_nodes,
                                                      uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
     const int items = S.nlevels * count;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        octree_item(S, w / count, w % count, smem_cand, max_cand, max_nodes, scratch, scratch_slots, scratch_next);
+        octree_item<kWide>(S, w / count, w % count, smem_cand, max_cand, max_nodes, scratch, scratch_slots, scratch_next);
         __syncthreads();  // the next item reuses the shared arrays
     }
 }
@@ -1212,9 +1233,13 @@ struct sfe_extractor {
     int pyr_wide_h[kMaxLevels] = {};
     std::vector<TilePlan> tiles;
     size_t pyr_stride = 0, blur_stride = 0;
-    int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0, out_cap = 0;
+    int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0;
     size_t octree_smem = 0;
     int octree_smem_cand = 0, octree_slots = 0, octree_cand_override = 0;  // SFE_OCTREE_SMEM_CAND (tests)
+    bool octree_wide = false;         // some level's candidate buffer exceeds 16-bit positions: the quadtree runs its 32-bit instance
+    int cand_floor[kMaxLevels] = {};  // per-level candidate capacity learnt from an overflow (the reference's list is unbounded,
+                                      // src/orb_extractor.cpp:778-779: a call that overflows is re-run with room for what it counted)
+    int cand_cap_override = 0;        // SFE_CAND_CAP (tests): initial per-level capacity instead of tested / 12
     DevBuf<uint8_t> d_octree_scratch;
     DevBuf<uint8_t> d_pyr, d_blur, d_in, d_l0, d_desc;  // d_in: images as uploaded (tight), d_l0: pitched level 0
     DevBuf<uint32_t> d_cand, d_kpst;
@@ -1362,7 +1387,10 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
             L.hx = (float)L.win_w / (float)L.n_ini;
         }
         // NMS'd FAST corners reach ~1 per 30 px on the small pyramid levels of textured frames
-        L.cand_cap = tested > 0 ? std::min(std::max(tested / 12, 1024), kMaxCandCap) : 0;
+        // first guess: one corner per 12 tested pixels, within the quadtree's 16-bit instance; a level that really holds more
+        // teaches the handle its floor (grow_candidate_buffers)
+        L.cand_cap = tested > 0 ? std::max(std::min(ex->cand_cap_override > 0 ? ex->cand_cap_override : std::max(tested / 12, 1024), kNarrowCandCap),
+                                           std::min(ex->cand_floor[l], kMaxCandCap)) : 0;
         L.cand_off = cand_off;
         cand_off += L.cand_cap;
         ex->fast.lv[l].cand_off = L.cand_off;
@@ -1440,14 +1468,16 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     // levels spill to global scratch slots
     ex->octree_smem_cand = std::min(ex->max_cand, ex->octree_cand_override > 0 ? ex->octree_cand_override : kOctreeSmemCand) & ~7;
     if (ex->octree_smem_cand < 8) ex->octree_smem_cand = 8;
-    ex->octree_smem = (size_t)ex->octree_smem_cand * 14 + (size_t)max_nodes * (16 + 3 * 4 + 2 * sizeof(ONode) + 2 * 2 + 8) + 32 * 4 + 64;
+    ex->octree_wide = ex->max_cand > kNarrowCandCap;
+    const size_t oct_cand_bytes = ex->octree_wide ? 16 : 14, oct_node_bytes = ex->octree_wide ? sizeof(ONodeT<true>) : sizeof(ONodeT<false>);
+    ex->octree_smem = (size_t)ex->octree_smem_cand * oct_cand_bytes + (size_t)max_nodes * (16 + 3 * 4 + 2 * oct_node_bytes + 2 * 2 + 8) + 32 * 4 + 64;
     SFE_REQUIRE(ex->octree_smem <= 227 * 1024, SFE_ERR_UNSUPPORTED, "quadtree working set exceeds shared memory");
     {   // one global scratch slot for every (level, image) whose candidate buffer can outgrow the shared-memory arrays
         int big_levels = 0;
         for (int l = 0; l < nl; l++) big_levels += ex->lv[l].cand_cap > ex->octree_smem_cand;
         ex->octree_slots = big_levels * ex->max_images;
     }
-    SFE_CUDA(ex->d_octree_scratch.ensure(std::max<size_t>((size_t)ex->octree_slots * ex->max_cand * 14, 16)));
+    SFE_CUDA(ex->d_octree_scratch.ensure(std::max<size_t>((size_t)ex->octree_slots * ex->max_cand * oct_cand_bytes, 16)));
     const int n = ex->max_images;
     SFE_CUDA(ex->d_pyr.ensure(ex->pyr_stride * n));
     SFE_CUDA(ex->d_blur.ensure(ex->blur_stride * n));
@@ -1657,7 +1687,8 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
             static size_t granted[64] = {};
             std::lock_guard<std::mutex> lock(mu);
             if (ex->octree_smem > granted[ex->device & 63]) {
-                SFE_CUDA(cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
+                SFE_CUDA(cudaFuncSetAttribute(octree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
+                SFE_CUDA(cudaFuncSetAttribute(octree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
                 granted[ex->device & 63] = ex->octree_smem;
             }
         }
@@ -1666,8 +1697,13 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         const int oct_items = nl * count;
         const int oct_ctas = ex->octree_ctas > 0 ? ex->octree_ctas : (fork && late ? 2 * ex->sm_count : 0);
         const int oct_grid = oct_ctas > 0 ? std::min(oct_items, oct_ctas) : oct_items;
-        octree_kernel<<<oct_grid, 256, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes, ex->d_octree_scratch.p,
-                                                                     ex->octree_slots, ex->d_counts.p + (size_t)ex->max_images * nl * 2);
+        int *scratch_next = ex->d_counts.p + (size_t)ex->max_images * nl * 2;
+        if (ex->octree_wide)
+            octree_kernel<true><<<oct_grid, 256, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
+                                                                       ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
+        else
+            octree_kernel<false><<<oct_grid, 256, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
+                                                                        ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
         prof_mark(ex, 3);
         if (fork) SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[si], 0));
         else launch_blur();
@@ -1693,6 +1729,43 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     return SFE_OK;
 }
 
+// Internal status of a finished call whose FAST candidate buffers overflowed: the buffers have been enlarged to what the
+// call counted (the counters are exact even when stores were dropped) and the caller re-runs the batch.
+constexpr int kStatusRerun = -1000;
+
+// After a candidate overflow: raise the per-level capacities to what the flagged images counted and drop the plan so that
+// the next prepare() rebuilds the buffers.  SFE_ERR_CAPACITY only when a level holds more corners than the quadtree's
+// 16-bit candidate index can address.
+static int grow_candidate_buffers(sfe_extractor *ex, int count) {
+    const int nl = ex->prm.nlevels;
+    std::vector<int> cnt((size_t)count * nl);
+    SFE_CUDA(cudaMemcpy(cnt.data(), ex->d_counts.p, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost));
+    bool grew = false;
+    for (int l = 0; l < nl; l++) {
+        int most = 0, who = 0;
+        for (int i = 0; i < count; i++)
+            if (cnt[(size_t)i * nl + l] > most) { most = cnt[(size_t)i * nl + l]; who = i; }
+        if (most <= ex->lv[l].cand_cap) continue;
+        if (most > kMaxCandCap) {
+            set_error("image slot %d, level %d: %d FAST corners, more than the %d a level may hold", who, l, most, kMaxCandCap);
+            return SFE_ERR_CAPACITY;
+        }
+        ex->cand_floor[l] = std::min(kMaxCandCap, most + most / 8 + 64);
+        grew = true;
+    }
+    if (!grew)  // asynchronous handle: a later call already reset the counters of the one that overflowed
+        for (int l = 0; l < nl; l++) {
+            if (ex->lv[l].cand_cap >= kMaxCandCap) continue;
+            ex->cand_floor[l] = std::min(kMaxCandCap, 2 * std::max(ex->lv[l].cand_cap, 1024));
+            grew = true;
+        }
+    if (!grew) { set_error("FAST candidate buffers are at their maximum (%d per level)", kMaxCandCap); return SFE_ERR_CAPACITY; }
+    if (ex->tail_pending) { cudaStreamSynchronize(ex->aux[1]); ex->tail_pending = false; }
+    ex->w = ex->h = 0;  // forces build_plan
+    ex->last_count = 0;
+    return kStatusRerun;
+}
+
 static int check_flags(sfe_extractor *ex, cudaStream_t st, int count) {
     ex->h_flags.resize(count);
     SFE_CUDA(cudaMemcpyAsync(ex->h_flags.data(), ex->last.flags, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
@@ -1706,11 +1779,14 @@ static int check_flags(sfe_extractor *ex, cudaStream_t st, int count) {
         ex->stage_calls++;
         ex->prof_pending = false;
     }
+    bool cand = false;
     for (int i = 0; i < count; i++) {
-        if (ex->h_flags[i] & kFlagCandOverflow) { set_error("image %d: FAST candidate buffer overflow", i); return SFE_ERR_CAPACITY; }
         if (ex->h_flags[i] & kFlagNodeOverflow) { set_error("image %d: quadtree node buffer overflow", i); return SFE_ERR_CAPACITY; }
-        if (ex->h_flags[i] & kFlagOutOverflow) { set_error("image %d: more keypoints than the caller's capacity", i); return SFE_ERR_CAPACITY; }
+        cand = cand || (ex->h_flags[i] & kFlagCandOverflow);
     }
+    if (cand) return grow_candidate_buffers(ex, count);
+    for (int i = 0; i < count; i++)
+        if (ex->h_flags[i] & kFlagOutOverflow) { set_error("image %d: more keypoints than the caller's capacity", i); return SFE_ERR_CAPACITY; }
     return SFE_OK;
 }
 
@@ -1767,11 +1843,29 @@ static const sfe_stereo_params k_default_stereo = {3.0, 100.0, 0.5};  // src/mat
 
 // Host-buffer batch: `frames` images (right == nullptr) or stereo pairs, pinned or pageable host memory in and out.
 // Sub-batch c: upload on s_h2d -> kernels on the compute stream -> results on s_d2h, chained with events.
-static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
-                          int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l, uint8_t *desc_l, int32_t *n_l,
-                          sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx, int32_t *stereo_dist,
-                          int cap, const sfe_track_params *tp = nullptr, int32_t *track_idx = nullptr,
-                          int32_t *track_dist = nullptr) {
+// inside the sub-batch loop an error must not return past the clean-up that waits for the copies already queued into the
+// caller's buffers: record it and leave the loop
+#define SFE_CUDA_BREAK(call)                                                                            \
+    {                                                                                                   \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            ::sfe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+            rc = SFE_ERR_CUDA;                                                                          \
+            break;                                                                                      \
+        }                                                                                               \
+    }
+#define SFE_CUDA_DRAIN(call)                                                                            \
+    {                                                                                                   \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess) {                                                                        \
+            ::sfe::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+            return drain(SFE_ERR_CUDA);                                                                 \
+        }                                                                                               \
+    }
+static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
+                               int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l, uint8_t *desc_l, int32_t *n_l,
+                               sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx, int32_t *stereo_dist,
+                               int cap, const sfe_track_params *tp, int32_t *track_idx, int32_t *track_dist) {
     const bool stereo = right != nullptr;
     const int images = stereo ? 2 * frames : frames;
     int rc = join_tail(ex);  // an asynchronous resident call may still be matching on the side stream
@@ -1798,6 +1892,10 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
     const bool piped = nch > 1;
     cudaStream_t sin = piped ? ex->s_h2d : ex->stream, sout = piped ? ex->s_d2h : ex->stream;
     const bool prof = ex->profiling;
+    struct Restore {  // every exit puts the handle's mode switches back
+        sfe_extractor *ex; bool prof;
+        ~Restore() { ex->profiling = prof; ex->piped_now = false; }
+    } restore{ex, prof};
     ex->piped_now = piped;
     if (piped) {
         ex->profiling = false;  // per-stage events describe one unpipelined batch
@@ -1817,8 +1915,8 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
             break;
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c], sin);
         if (piped) {
-            SFE_CUDA(cudaEventRecord(ex->ev_in[c], sin));
-            SFE_CUDA(cudaStreamWaitEvent(sc, ex->ev_in[c], 0));
+            SFE_CUDA_BREAK(cudaEventRecord(ex->ev_in[c], sin));
+            SFE_CUDA_BREAK(cudaStreamWaitEvent(sc, ex->ev_in[c], 0));
         }
         realign_images(ex, sc, f0, fc, w, h);
         if (stereo) realign_images(ex, sc, frames + f0, fc, w, h);
@@ -1830,49 +1928,48 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
             if (!piped) prof_mark(ex, 6);
             ex->prof_has_stereo = true;
             ex->launches++;
-            SFE_CUDA(cudaGetLastError());
+            SFE_CUDA_BREAK(cudaGetLastError());
         }
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 1], sc);
         if (piped) {
-            SFE_CUDA(cudaEventRecord(ex->ev_done[c], sc));
-            SFE_CUDA(cudaStreamWaitEvent(sout, ex->ev_done[c], 0));
+            SFE_CUDA_BREAK(cudaEventRecord(ex->ev_done[c], sc));
+            SFE_CUDA_BREAK(cudaStreamWaitEvent(sout, ex->ev_done[c], 0));
         }
         const size_t o = (size_t)f0 * cap, nk = (size_t)fc * cap;
-        SFE_CUDA(cudaMemcpyAsync(kps_l + o, kl + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
-        SFE_CUDA(cudaMemcpyAsync(desc_l + o * 32, dl + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
+        SFE_CUDA_BREAK(cudaMemcpyAsync(kps_l + o, kl + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
+        SFE_CUDA_BREAK(cudaMemcpyAsync(desc_l + o * 32, dl + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
         if (stereo) {
-            SFE_CUDA(cudaMemcpyAsync(kps_r + o, kr + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
-            SFE_CUDA(cudaMemcpyAsync(desc_r + o * 32, dr + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
-            SFE_CUDA(cudaMemcpyAsync(stereo_idx + o, ex->d_sidx.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
+            SFE_CUDA_BREAK(cudaMemcpyAsync(kps_r + o, kr + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
+            SFE_CUDA_BREAK(cudaMemcpyAsync(desc_r + o * 32, dr + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
+            SFE_CUDA_BREAK(cudaMemcpyAsync(stereo_idx + o, ex->d_sidx.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
             if (stereo_dist)
-                SFE_CUDA(cudaMemcpyAsync(stereo_dist + o, ex->d_sdist.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
+                SFE_CUDA_BREAK(cudaMemcpyAsync(stereo_dist + o, ex->d_sdist.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
         }
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 2], sout);
     }
     ex->profiling = prof;
     ex->piped_now = false;
-    if (rc != SFE_OK) {
+    auto drain = [&](int status) {  // nothing may still be writing into the caller's buffers once the call has returned
         cudaStreamSynchronize(sin); cudaStreamSynchronize(ex->stream);
         for (auto &e : ex->extra) cudaStreamSynchronize(e);
         cudaStreamSynchronize(sout);
-        return rc;
-    }
+        return status;
+    };
+    if (rc != SFE_OK) return drain(rc);
     if (tp && stereo) {
         // tracking needs consecutive frames, which may sit in different sub-batches: it runs once, behind all of them
         // (sout already waits for every sub-batch), on the D2H stream's tail
-        SFE_CUDA(ex->d_tidx.ensure((size_t)ex->max_images * cap));
-        SFE_CUDA(ex->d_tdist.ensure((size_t)ex->max_images * cap));
+        SFE_CUDA_DRAIN(ex->d_tidx.ensure((size_t)ex->max_images * cap));
+        SFE_CUDA_DRAIN(ex->d_tdist.ensure((size_t)ex->max_images * cap));
         if ((rc = launch_track_frames(sout, ex->device, ex->track, frames, cap, kl, dl, nl, kr, ex->d_sidx.p, *tp, ex->d_tidx.p,
-                                      ex->d_tdist.p)) != SFE_OK) {
-            cudaStreamSynchronize(sout);
-            return rc;
-        }
+                                      ex->d_tdist.p)) != SFE_OK)
+            return drain(rc);
         ex->launches += 3;
-        SFE_CUDA(cudaMemcpyAsync(track_idx, ex->d_tidx.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
-        if (track_dist) SFE_CUDA(cudaMemcpyAsync(track_dist, ex->d_tdist.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
+        SFE_CUDA_DRAIN(cudaMemcpyAsync(track_idx, ex->d_tidx.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
+        if (track_dist) SFE_CUDA_DRAIN(cudaMemcpyAsync(track_dist, ex->d_tdist.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
     }
-    SFE_CUDA(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
-    if (stereo) SFE_CUDA(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
+    SFE_CUDA_DRAIN(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
+    if (stereo) SFE_CUDA_DRAIN(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
     ex->last = B;
     if (!stereo) ex->last.split = images;  // one set: every image reads in_a
     ex->last_count = images;
@@ -1887,6 +1984,19 @@ static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t 
             fprintf(stderr, "  sub-batch %2d frames [%3d,%3d): uploaded %.3f  computed %.3f  downloaded %.3f\n", c, bound[c], bound[c + 1], a, b, d);
         }
     }
+    return rc;
+}
+
+static int run_host_batch(sfe_extractor *ex, const uint8_t *left, const uint8_t *right, size_t image_stride, int frames, int w,
+                          int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l, uint8_t *desc_l, int32_t *n_l,
+                          sfe_keypoint *kps_r, uint8_t *desc_r, int32_t *n_r, int32_t *stereo_idx, int32_t *stereo_dist,
+                          int cap, const sfe_track_params *tp = nullptr, int32_t *track_idx = nullptr,
+                          int32_t *track_dist = nullptr) {
+    int rc = kStatusRerun;
+    for (int attempt = 0; attempt < 3 && rc == kStatusRerun; attempt++)  // one re-run suffices: the first pass counted exactly
+        rc = run_host_batch_once(ex, left, right, image_stride, frames, w, h, stride, sp, kps_l, desc_l, n_l, kps_r, desc_r, n_r,
+                                 stereo_idx, stereo_dist, cap, tp, track_idx, track_dist);
+    if (rc == kStatusRerun) { set_error("FAST candidate buffers still overflow after two re-runs"); rc = SFE_ERR_CAPACITY; }
     return rc;
 }
 
@@ -1905,6 +2015,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     SFE_REQUIRE(ndev > 0, SFE_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     SFE_REQUIRE(device >= 0 && device < ndev, SFE_ERR_BAD_ARG, "device index out of range");
     DeviceGuard g(device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     sfe_extractor *ex = new sfe_extractor();
     ex->device = device;
     ex->prm = *p;
@@ -1943,10 +2054,8 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (ex->trace)
         for (auto &e : ex->tr_ev) cudaEventCreate(&e);
     if (const char *env = getenv("SFE_OCTREE_SMEM_CAND")) ex->octree_cand_override = atoi(env);
+    if (const char *env = getenv("SFE_CAND_CAP")) ex->cand_cap_override = std::max(8, atoi(env));
     build_tables(ex);
-    int cap = p->nfeatures;
-    for (int l = 0; l < p->nlevels; l++) cap += 4;
-    ex->out_cap = cap;
     *out = ex;
     return SFE_OK;
 }
@@ -1954,6 +2063,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
 int sfe_extractor_destroy(sfe_extractor *ex) {
     if (!ex) return SFE_OK;
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStreamSynchronize(ex->stream);
     ex->d_pyr.release(); ex->d_blur.release(); ex->d_in.release(); ex->d_l0.release(); ex->d_octree_scratch.release(); ex->d_desc.release();
     ex->d_cand.release(); ex->d_kpst.release(); ex->d_counts.release();
@@ -2003,10 +2113,26 @@ int sfe_extractor_level_size(const sfe_extractor *ex, int w, int h, int level, i
     return SFE_OK;
 }
 
-int sfe_extractor_max_keypoints(const sfe_extractor *ex, int *cap) {
+// A level returns at most max(quota + 2, 4 * nIni) keypoints: DistributeOctTree stops at the first size >= N and one split adds
+// at most 3 nodes (:669,730), but the first pass over the nIni roots is unconditional (:606-665) and may leave 4 * nIni nodes
+// even when that exceeds N (small nfeatures on a wide image).
+int sfe_extractor_max_keypoints_for(const sfe_extractor *ex, int w, int h, int *cap) {
     SFE_REQUIRE(ex && cap, SFE_ERR_BAD_ARG, "null argument");
-    *cap = ex->out_cap;
+    int total = 0;
+    for (int l = 0; l < ex->prm.nlevels; l++) {
+        int n_ini = 4;  // without a geometry: aspect ratios up to 4.5 : 1
+        if (w > 0 && h > 0) {
+            const int ww = cv_round_f((float)w * ex->inv_scale[l]) - 2 * kBorder, wh = cv_round_f((float)h * ex->inv_scale[l]) - 2 * kBorder;
+            n_ini = ww > 0 && wh > 0 ? std::max(1, (int)roundf((float)ww / (float)wh)) : 1;
+        }
+        total += std::max(ex->quota[l] + 3, 4 * n_ini);
+    }
+    *cap = total;
     return SFE_OK;
+}
+int sfe_extractor_max_keypoints(const sfe_extractor *ex, int *cap) {
+    SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null argument");
+    return sfe_extractor_max_keypoints_for(ex, ex->w, ex->h, cap);
 }
 
 int sfe_extractor_launches(const sfe_extractor *ex, int64_t *launches) {
@@ -2015,10 +2141,8 @@ int sfe_extractor_launches(const sfe_extractor *ex, int64_t *launches) {
     return SFE_OK;
 }
 
-int sfe_extract_batch_dev(sfe_extractor *ex, const uint8_t *images_dev, size_t image_stride, int count, int w, int h,
-                          int stride, sfe_keypoint *kps_dev, uint8_t *desc_dev, int cap, int32_t *n_out_dev) {
-    SFE_REQUIRE(ex && images_dev && kps_dev && desc_dev && n_out_dev, SFE_ERR_BAD_ARG, "null argument");
-    DeviceGuard g(ex->device);
+static int extract_batch_dev_once(sfe_extractor *ex, const uint8_t *images_dev, size_t image_stride, int count, int w, int h,
+                                  int stride, sfe_keypoint *kps_dev, uint8_t *desc_dev, int cap, int32_t *n_out_dev) {
     int rc = prepare(ex, count, w, h, stride, cap);
     if (rc != SFE_OK) return rc;
     const OutSet O{kps_dev, kps_dev, desc_dev, desc_dev, n_out_dev, n_out_dev, cap};
@@ -2031,6 +2155,21 @@ int sfe_extract_batch_dev(sfe_extractor *ex, const uint8_t *images_dev, size_t i
     return finish_dev(ex, count);
 }
 
+// a synchronous _dev call whose candidate buffers overflowed is run again with the enlarged buffers (the inputs are resident)
+#define SFE_RERUN(call)                                                                                          \
+    int rc = kStatusRerun;                                                                                       \
+    for (int attempt = 0; attempt < 3 && rc == kStatusRerun; attempt++) rc = (call);                             \
+    if (rc == kStatusRerun) { set_error("FAST candidate buffers still overflow after two re-runs"); rc = SFE_ERR_CAPACITY; } \
+    return rc;
+
+int sfe_extract_batch_dev(sfe_extractor *ex, const uint8_t *images_dev, size_t image_stride, int count, int w, int h,
+                          int stride, sfe_keypoint *kps_dev, uint8_t *desc_dev, int cap, int32_t *n_out_dev) {
+    SFE_REQUIRE(ex && images_dev && kps_dev && desc_dev && n_out_dev, SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    SFE_RERUN(extract_batch_dev_once(ex, images_dev, image_stride, count, w, h, stride, kps_dev, desc_dev, cap, n_out_dev));
+}
+
 int sfe_extract_batch(sfe_extractor *ex, const uint8_t *images, size_t image_stride, int count, int w, int h, int stride,
                       sfe_keypoint *kps, uint8_t *desc, int cap, int32_t *n_out) {
     SFE_REQUIRE(ex && kps && desc && n_out, SFE_ERR_BAD_ARG, "null argument");
@@ -2039,6 +2178,7 @@ int sfe_extract_batch(sfe_extractor *ex, const uint8_t *images, size_t image_str
         return SFE_OK;
     }
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     return run_host_batch(ex, images, nullptr, image_stride, count, w, h, stride, &k_default_stereo, kps, desc, n_out, nullptr,
                           nullptr, nullptr, nullptr, nullptr, cap);
 }
@@ -2052,16 +2192,11 @@ int sfe_extract(sfe_extractor *ex, const uint8_t *image, int w, int h, int strid
     return rc;
 }
 
-static int stereo_frames_dev_impl(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
+static int stereo_frames_dev_once(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
                                   int frames, int w, int h, int stride, const sfe_stereo_params *sp, const sfe_track_params *tp,
                                   sfe_keypoint *kps_l_dev, uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev,
                                   uint8_t *desc_r_dev, int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
                                   int32_t *track_idx_dev, int32_t *track_dist_dev, int cap) {
-    SFE_REQUIRE(ex && left_dev && right_dev && kps_l_dev && desc_l_dev && n_l_dev && kps_r_dev && desc_r_dev && n_r_dev &&
-                    stereo_idx_dev,
-                SFE_ERR_BAD_ARG, "null argument");
-    SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
-    DeviceGuard g(ex->device);
     int rc = prepare(ex, 2 * frames, w, h, stride, cap);
     if (rc != SFE_OK) return rc;
     if (!sp) sp = &k_default_stereo;
@@ -2106,6 +2241,22 @@ static int stereo_frames_dev_impl(sfe_extractor *ex, const uint8_t *left_dev, co
     return finish_dev(ex, 2 * frames);
 }
 
+static int stereo_frames_dev_impl(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
+                                  int frames, int w, int h, int stride, const sfe_stereo_params *sp, const sfe_track_params *tp,
+                                  sfe_keypoint *kps_l_dev, uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev,
+                                  uint8_t *desc_r_dev, int32_t *n_r_dev, int32_t *stereo_idx_dev, int32_t *stereo_dist_dev,
+                                  int32_t *track_idx_dev, int32_t *track_dist_dev, int cap) {
+    SFE_REQUIRE(ex && left_dev && right_dev && kps_l_dev && desc_l_dev && n_l_dev && kps_r_dev && desc_r_dev && n_r_dev &&
+                    stereo_idx_dev,
+                SFE_ERR_BAD_ARG, "null argument");
+    SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
+    DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    SFE_RERUN(stereo_frames_dev_once(ex, left_dev, right_dev, image_stride, frames, w, h, stride, sp, tp, kps_l_dev, desc_l_dev,
+                                     n_l_dev, kps_r_dev, desc_r_dev, n_r_dev, stereo_idx_dev, stereo_dist_dev, track_idx_dev,
+                                     track_dist_dev, cap));
+}
+
 int sfe_stereo_frames_dev(sfe_extractor *ex, const uint8_t *left_dev, const uint8_t *right_dev, size_t image_stride,
                           int frames, int w, int h, int stride, const sfe_stereo_params *sp, sfe_keypoint *kps_l_dev,
                           uint8_t *desc_l_dev, int32_t *n_l_dev, sfe_keypoint *kps_r_dev, uint8_t *desc_r_dev,
@@ -2140,6 +2291,7 @@ int sfe_stereo_frames(sfe_extractor *ex, const uint8_t *left, const uint8_t *rig
                 "null argument");
     SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     return run_host_batch(ex, left, right, image_stride, frames, w, h, stride, sp ? sp : &k_default_stereo, kps_l, desc_l, n_l,
                           kps_r, desc_r, n_r, stereo_idx, stereo_dist, cap);
 }
@@ -2153,6 +2305,7 @@ int sfe_stereo_sequence(sfe_extractor *ex, const uint8_t *left, const uint8_t *r
     if (int rc = check_track_params(tp, track_idx)) return rc;
     SFE_REQUIRE(frames >= 1 && 2 * frames <= ex->max_images, SFE_ERR_BAD_ARG, "2*frames exceeds max_images");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     return run_host_batch(ex, left, right, image_stride, frames, w, h, stride, sp ? sp : &k_default_stereo, kps_l, desc_l, n_l,
                           kps_r, desc_r, n_r, stereo_idx, stereo_dist, cap, tp, track_idx, track_dist);
 }
@@ -2162,6 +2315,7 @@ int sfe_image_pitch(int w) { return w > 0 ? (int)align_up((size_t)w, 16) : 0; }
 int sfe_extractor_set_async(sfe_extractor *ex, int enable) {
     SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     if (int rc = join_tail(ex)) return rc;
     SFE_CUDA(cudaStreamSynchronize(ex->stream));
     ex->async_dev = enable != 0;
@@ -2173,13 +2327,18 @@ int sfe_extractor_set_async(sfe_extractor *ex, int enable) {
 int sfe_extractor_wait(sfe_extractor *ex) {
     SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     if (int rc = join_tail(ex)) return rc;
     if (ex->last_count <= 0) {
         SFE_CUDA(cudaStreamSynchronize(ex->stream));
         return SFE_OK;
     }
     int rc = check_flags(ex, ex->stream, ex->max_images);
-    if (ex->async_dev)
+    if (rc == kStatusRerun) {  // the inputs of a queued batch are the caller's: it has to be submitted again
+        set_error("a queued batch overflowed its FAST candidate buffers; they have been enlarged, submit the batch again");
+        rc = SFE_ERR_CAPACITY;
+    }
+    if (ex->async_dev && ex->d_counts.p)
         SFE_CUDA(cudaMemset(ex->d_counts.p + (size_t)ex->max_images * ex->prm.nlevels * 2 + 1, 0, sizeof(int) * ex->max_images));
     return rc;
 }
@@ -2197,6 +2356,7 @@ int sfe_debug_level(sfe_extractor *ex, int image, int level, uint8_t *out) {
     if (rc != SFE_OK) return rc;
     SFE_REQUIRE(out, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     const LevelPlan &L = ex->lv[level];
     const ImgSet &S = ex->last;
     const uint8_t *src;
@@ -2218,6 +2378,7 @@ int sfe_debug_blur(sfe_extractor *ex, int image, int level, uint8_t *out) {
     if (rc != SFE_OK) return rc;
     SFE_REQUIRE(out, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     const LevelPlan &L = ex->lv[level];
     SFE_CUDA(cudaStreamSynchronize(ex->stream));
     SFE_CUDA(cudaMemcpy2D(out, L.w, ex->last.blur + (size_t)image * ex->last.blur_stride + L.blur_off, L.blur_pitch, L.w, L.h,
@@ -2230,6 +2391,7 @@ static int tap_points(sfe_extractor *ex, int image, int level, bool distributed,
     if (rc != SFE_OK) return rc;
     SFE_REQUIRE(xyr && n && cap >= 0, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     const LevelPlan &L = ex->lv[level];
     const ImgSet &S = ex->last;
     SFE_CUDA(cudaStreamSynchronize(ex->stream));
@@ -2269,6 +2431,7 @@ int sfe_debug_distributed(sfe_extractor *ex, int image, int level, float *xyr, i
 int sfe_extractor_set_profiling(sfe_extractor *ex, int enable) {
     SFE_REQUIRE(ex, SFE_ERR_BAD_ARG, "null handle");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     if (enable && !ex->prof_ev[0])
         for (int i = 0; i <= kNumStages; i++) SFE_CUDA(cudaEventCreate(&ex->prof_ev[i]));
     ex->profiling = enable != 0;
@@ -2287,6 +2450,7 @@ int sfe_extractor_stage_ms(const sfe_extractor *ex, double *ms, int n, int64_t *
 int sfe_event_record_extractor(sfe_event *ev, sfe_extractor *ex) {
     SFE_REQUIRE(ev && ex, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(ex->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     if (int rc = join_tail(ex)) return rc;  // the event marks the end of everything enqueued so far
     SFE_CUDA(cudaEventRecord(ev->ev, ex->stream));
     return SFE_OK;

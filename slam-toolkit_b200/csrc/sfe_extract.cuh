@@ -10,8 +10,11 @@ constexpr int kEdge = 19;          // EDGE_THRESHOLD, reference src/orb_extracto
 constexpr int kBorder = kEdge - 3; // minBorderX/Y of the FAST window, :771-772
 constexpr int kHalfPatch = 15;     // HALF_PATCH_SIZE, :73
 constexpr int kMaxSub = 66;        // largest FAST cell sub-image side (wCell + 6 < 60 + 6)
-constexpr int kMaxCandCap = 60000; // per level: the quadtree indexes candidates with 16 bits; up to 3072 candidates live in
-                                   // shared memory (14 B each), fuller levels in a global scratch slot
+constexpr int kNarrowCandCap = 60000;   // per level: up to here the quadtree indexes candidates with 16 bits (up to 3072 of them in
+                                        // shared memory, 14 B each; fuller levels in a global scratch slot)
+constexpr int kMaxCandCap = 1 << 22;    // hard limit of a level's candidate buffer: non-max-suppressed corners cannot be 8-neighbours,
+                                        // so a 4096 x 4096 window holds at most 2^22 of them; above kNarrowCandCap the quadtree runs
+                                        // its 32-bit instance
 constexpr int kBlurTileW = 128, kBlurTileH = 32;
 constexpr int kBlurInWords = 40;   // shared-memory row of a blur input tile: x0-16 .. x0+143 (a TMA box starts and ends on 16-byte
                                    // multiples of the row: the innermost coordinate must be 16-byte aligned)

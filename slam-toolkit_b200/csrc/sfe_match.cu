@@ -261,27 +261,63 @@ __global__ void grid_fill_kernel(KpGrid G, const sfe_keypoint *__restrict__ kps,
     }
 }
 
+// predicted_Tcw as the caller holds it.  quat != 0: v = {qx, qy, qz, qw, tx, ty, tz}, a g2o::SE3Quat (the reference,
+// src/matcher.cpp:151); quat == 0: v = row-major 3x4 [R|t].
+struct Pose {
+    double v[12];
+    int quat;
+};
+static Pose pose_from_rt(const double rt[12]) {
+    Pose T{};
+    memcpy(T.v, rt, sizeof(double) * 12);
+    return T;
+}
+static Pose pose_from_se3(const sfe_se3 *q) {
+    Pose T{};
+    T.v[0] = q->qx; T.v[1] = q->qy; T.v[2] = q->qz; T.v[3] = q->qw; T.v[4] = q->tx; T.v[5] = q->ty; T.v[6] = q->tz;
+    T.quat = 1;
+    return T;
+}
+
 struct ProjParams {
-    double rt[12];
+    Pose T;
     sfe_camera cam;
     double radius, ratio;
 };
 
 // Xc = Tcw Xw, Camera::Project, IsInImage: false when the point is behind the camera, outside the image or not a number
 // Xc = Tcw Xw and Camera::Project (with distortion); false when the point is behind the camera (z < 0)
-__device__ __forceinline__ bool project_uv(const double rt[12], const sfe_camera &cam, double X, double Y, double Z, double &u, double &v);
+__device__ __forceinline__ bool project_uv(const Pose &T, const sfe_camera &cam, double X, double Y, double Z, double &u, double &v);
 
 __device__ __forceinline__ bool project_point(const ProjParams &P, double X, double Y, double Z, double &u, double &v) {
-    if (!project_uv(P.rt, P.cam, X, Y, Z, u, v)) return false;  // :151-153
+    if (!project_uv(P.T, P.cam, X, Y, Z, u, v)) return false;  // :151-153
     if (u < 0. || v < 0. || u > (double)P.cam.width || v > (double)P.cam.height) return false;  // IsInImage, :26-36
     return u == u && v == v;  // NaN: the radius search finds nothing
 }
 
-__device__ __forceinline__ bool project_uv(const double rt[12], const sfe_camera &cam, double X, double Y, double Z, double &u, double &v) {
-    // Xc = Tcw * Xw, evaluated left to right without contraction (:150)
-    const double xc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[0], X), __dmul_rn(rt[1], Y)), __dmul_rn(rt[2], Z)), rt[3]);
-    const double yc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[4], X), __dmul_rn(rt[5], Y)), __dmul_rn(rt[6], Z)), rt[7]);
-    const double zc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[8], X), __dmul_rn(rt[9], Y)), __dmul_rn(rt[10], Z)), rt[11]);
+__device__ __forceinline__ bool project_uv(const Pose &T, const sfe_camera &cam, double X, double Y, double Z, double &u, double &v) {
+    // Xc = Tcw * Xw without contraction (:151)
+    double xc, yc, zc;
+    if (T.quat) {
+        // g2o::SE3Quat::operator*: _t + _r * v, with Eigen's quaternion-vector product (Quaternion.h, _transformVector):
+        // uv = q.vec x v; uv += uv; (v + q.w * uv) + q.vec x uv
+        const double qx = T.v[0], qy = T.v[1], qz = T.v[2], qw = T.v[3];
+        double ux = __dsub_rn(__dmul_rn(qy, Z), __dmul_rn(qz, Y));
+        double uy = __dsub_rn(__dmul_rn(qz, X), __dmul_rn(qx, Z));
+        double uz = __dsub_rn(__dmul_rn(qx, Y), __dmul_rn(qy, X));
+        ux = __dadd_rn(ux, ux); uy = __dadd_rn(uy, uy); uz = __dadd_rn(uz, uz);
+        const double cx = __dsub_rn(__dmul_rn(qy, uz), __dmul_rn(qz, uy));
+        const double cy = __dsub_rn(__dmul_rn(qz, ux), __dmul_rn(qx, uz));
+        const double cz = __dsub_rn(__dmul_rn(qx, uy), __dmul_rn(qy, ux));
+        xc = __dadd_rn(T.v[4], __dadd_rn(__dadd_rn(X, __dmul_rn(qw, ux)), cx));
+        yc = __dadd_rn(T.v[5], __dadd_rn(__dadd_rn(Y, __dmul_rn(qw, uy)), cy));
+        zc = __dadd_rn(T.v[6], __dadd_rn(__dadd_rn(Z, __dmul_rn(qw, uz)), cz));
+    } else {
+        const double *rt = T.v;  // rows left to right
+        xc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[0], X), __dmul_rn(rt[1], Y)), __dmul_rn(rt[2], Z)), rt[3]);
+        yc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[4], X), __dmul_rn(rt[5], Y)), __dmul_rn(rt[6], Z)), rt[7]);
+        zc = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(rt[8], X), __dmul_rn(rt[9], Y)), __dmul_rn(rt[10], Z)), rt[11]);
+    }
     if (zc < 0.) return false;
     // Camera::Project + Distort, src/camera.cpp:50-79
     const double x = __ddiv_rn(xc, zc), y = __ddiv_rn(yc, zc);
@@ -846,7 +882,7 @@ __global__ void reprojection_error_kernel(sfe_camera cam, ProjParams P, const sf
     double e = -1.;
     if (has_mp[i]) {
         double u, v;
-        if (!project_uv(P.rt, cam, xw[3 * (size_t)i], xw[3 * (size_t)i + 1], xw[3 * (size_t)i + 2], u, v)) {
+        if (!project_uv(P.T, cam, xw[3 * (size_t)i], xw[3 * (size_t)i + 1], xw[3 * (size_t)i + 2], u, v)) {
             e = __longlong_as_double(0x7FF0000000000000ll);
         } else {
             const double dx = __dsub_rn(u, (double)kps[i].x), dy = __dsub_rn(v, (double)kps[i].y);
@@ -873,8 +909,10 @@ __global__ void search_radius_kernel(KpGrid G, const sfe_keypoint *__restrict__ 
                 const int j = G.order[t];
                 const double ddx = u - (double)kps[j].x, ddy = v - (double)kps[j].y;
                 if (!(__dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)) < r2max)) continue;
-                if (n < cap) {  // keep the row sorted by index (canonical order): insertion from the back
-                    int p = n;
+                // keep the row sorted by index (canonical order): insertion from the back; a full row keeps its cap
+                // smallest indices whatever order the cells are visited in
+                if (n < cap || j < out[cap - 1]) {
+                    int p = min(n, cap - 1);
                     while (p > 0 && out[p - 1] > j) { out[p] = out[p - 1]; p--; }
                     out[p] = j;
                 }
@@ -980,7 +1018,7 @@ int launch_track_frames(cudaStream_t st, int device, TrackScratch &T, int frames
     track_grids_kernel<<<frames, 256, smem, st>>>(A);
     if (frames > 1) {
         ProjParams P;
-        memcpy(P.rt, tp.rt, sizeof(P.rt));
+        P.T = tp.use_se3 ? pose_from_se3(&tp.se3) : pose_from_rt(tp.rt);
         P.cam = tp.cam;
         P.radius = tp.radius;
         P.ratio = tp.best12_threshold;
@@ -1063,7 +1101,7 @@ static int build_grid(sfe_matcher *m, DevBuf<int> &mem, KpGrid &G, const sfe_cam
 }
 
 static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
-                           const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
+                           const Pose &T, const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
                            int m_kps, double radius, double ratio, int32_t *to_query, int32_t *dist, uint32_t idx_base = 0,
                            unsigned long long *keys_out = nullptr, const KpGrid *prebuilt = nullptr) {
     cudaStream_t st = m->stream;
@@ -1080,7 +1118,7 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
     SFE_CUDA(cudaMemsetAsync(best, 0xFF, sizeof(unsigned long long) * m_kps, st));
     if (n > 0) {
         ProjParams P;
-        memcpy(P.rt, rt, sizeof(P.rt));
+        P.T = T;
         P.cam = *cam;
         P.radius = radius;
         P.ratio = ratio;
@@ -1147,6 +1185,7 @@ int sfe_matcher_create(int device, sfe_matcher **out) {
     SFE_REQUIRE(ndev > 0, SFE_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
     SFE_REQUIRE(device >= 0 && device < ndev, SFE_ERR_BAD_ARG, "device index out of range");
     DeviceGuard g(device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     sfe_matcher *m = new sfe_matcher();
     m->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
@@ -1163,6 +1202,7 @@ int sfe_matcher_create(int device, sfe_matcher **out) {
 int sfe_matcher_destroy(sfe_matcher *m) {
     if (!m) return SFE_OK;
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStreamSynchronize(m->stream);
     m->d_kl.release(); m->d_kr.release(); m->d_dl.release(); m->d_dr.release(); m->d_skip.release();
     m->d_n.release(); m->d_idx.release(); m->d_dist.release(); m->d_xw.release(); m->d_grid.release();
@@ -1176,6 +1216,7 @@ int sfe_matcher_destroy(sfe_matcher *m) {
 int sfe_matcher_set_async(sfe_matcher *m, int enable) {
     SFE_REQUIRE(m, SFE_ERR_BAD_ARG, "null handle");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     SFE_CUDA(cudaStreamSynchronize(m->stream));
     m->async_dev = enable != 0;
     return SFE_OK;
@@ -1184,6 +1225,7 @@ int sfe_matcher_set_async(sfe_matcher *m, int enable) {
 int sfe_matcher_wait(sfe_matcher *m) {
     SFE_REQUIRE(m, SFE_ERR_BAD_ARG, "null handle");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
@@ -1197,6 +1239,7 @@ int sfe_matcher_launches(const sfe_matcher *m, int64_t *launches) {
 int sfe_event_record_matcher(sfe_event *ev, sfe_matcher *m) {
     SFE_REQUIRE(ev && m, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     SFE_CUDA(cudaEventRecord(ev->ev, m->stream));
     return SFE_OK;
 }
@@ -1208,6 +1251,7 @@ int sfe_stereo_match(sfe_matcher *m, const sfe_keypoint *kps_l, const uint8_t *d
     SFE_REQUIRE(kps_l && desc_l && out_idx && (n_r == 0 || (kps_r && desc_r)), SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(n_l < 65536 && n_r < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per image");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     const sfe_stereo_params def = {3.0, 100.0, 0.5};
     if (!sp) sp = &def;
     const int cap = std::max(n_l, std::max(n_r, 1));
@@ -1233,31 +1277,47 @@ int sfe_stereo_match(sfe_matcher *m, const sfe_keypoint *kps_l, const uint8_t *d
     return SFE_OK;
 }
 
-int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev, int n,
-                             const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps_dev,
+static int projection_match_dev_pose(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev, int n,
+                             const Pose &T, const sfe_camera *cam, const sfe_keypoint *kps_dev,
                              const uint8_t *kp_desc_dev, int m_kps, double radius, double best12_threshold,
                              int32_t *kp_to_query_dev, int32_t *kp_dist_dev) {
-    SFE_REQUIRE(m && rt && cam && n >= 0 && m_kps >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(m && cam && n >= 0 && m_kps >= 0, SFE_ERR_BAD_ARG, "bad argument");
     SFE_REQUIRE(m_kps == 0 || (kps_dev && kp_desc_dev && kp_to_query_dev), SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(n == 0 || (xw_dev && mp_desc_dev), SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(m_kps < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per frame");
     DeviceGuard g(m->device);
-    int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, rt, cam, kps_dev, kp_desc_dev, m_kps, radius,
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, T, cam, kps_dev, kp_desc_dev, m_kps, radius,
                              best12_threshold, kp_to_query_dev, kp_dist_dev);
     if (rc != SFE_OK) return rc;
     if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
 }
+int sfe_projection_match_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev, int n,
+                             const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps_dev,
+                             const uint8_t *kp_desc_dev, int m_kps, double radius, double best12_threshold,
+                             int32_t *kp_to_query_dev, int32_t *kp_dist_dev) {
+    SFE_REQUIRE(rt, SFE_ERR_BAD_ARG, "null pose");
+    return projection_match_dev_pose(m, xw_dev, mp_desc_dev, skip_dev, n, pose_from_rt(rt), cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold, kp_to_query_dev, kp_dist_dev);
+}
+int sfe_projection_match_se3_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev, int n,
+                             const sfe_se3 *Tcw, const sfe_camera *cam, const sfe_keypoint *kps_dev,
+                             const uint8_t *kp_desc_dev, int m_kps, double radius, double best12_threshold,
+                             int32_t *kp_to_query_dev, int32_t *kp_dist_dev) {
+    SFE_REQUIRE(Tcw, SFE_ERR_BAD_ARG, "null pose");
+    return projection_match_dev_pose(m, xw_dev, mp_desc_dev, skip_dev, n, pose_from_se3(Tcw), cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold, kp_to_query_dev, kp_dist_dev);
+}
 
-int sfe_projection_match(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
-                         const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
+static int projection_match_pose(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                         const Pose &T, const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
                          int m_kps, double radius, double best12_threshold, int32_t *kp_to_query, int32_t *kp_dist) {
-    SFE_REQUIRE(m && rt && cam && n >= 0 && m_kps >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(m && cam && n >= 0 && m_kps >= 0, SFE_ERR_BAD_ARG, "bad argument");
     if (m_kps == 0) return SFE_OK;
     SFE_REQUIRE(kps && kp_desc && kp_to_query, SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(n == 0 || (xw && mp_desc), SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(m_kps < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per frame");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     const int nn = std::max(n, 1);
     SFE_CUDA(m->d_xw.ensure((size_t)nn * 3)); SFE_CUDA(m->d_dl.ensure((size_t)nn * 32)); SFE_CUDA(m->d_skip.ensure(nn));
@@ -1270,7 +1330,7 @@ int sfe_projection_match(sfe_matcher *m, const double *xw, const uint8_t *mp_des
     }
     SFE_CUDA(cudaMemcpyAsync(m->d_kr.p, kps, sizeof(sfe_keypoint) * m_kps, cudaMemcpyHostToDevice, st));
     SFE_CUDA(cudaMemcpyAsync(m->d_dr.p, kp_desc, (size_t)m_kps * 32, cudaMemcpyHostToDevice, st));
-    int rc = projection_impl(m, m->d_xw.p, m->d_dl.p, skip ? m->d_skip.p : nullptr, n, rt, cam, m->d_kr.p, m->d_dr.p, m_kps,
+    int rc = projection_impl(m, m->d_xw.p, m->d_dl.p, skip ? m->d_skip.p : nullptr, n, T, cam, m->d_kr.p, m->d_dr.p, m_kps,
                              radius, best12_threshold, m->d_idx.p, m->d_dist.p);
     if (rc != SFE_OK) return rc;
     SFE_CUDA(cudaMemcpyAsync(kp_to_query, m->d_idx.p, sizeof(int32_t) * m_kps, cudaMemcpyDeviceToHost, st));
@@ -1278,27 +1338,55 @@ int sfe_projection_match(sfe_matcher *m, const double *xw, const uint8_t *mp_des
     SFE_CUDA(cudaStreamSynchronize(st));
     return SFE_OK;
 }
+int sfe_projection_match(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                         const double rt[12], const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
+                         int m_kps, double radius, double best12_threshold, int32_t *kp_to_query, int32_t *kp_dist) {
+    SFE_REQUIRE(rt, SFE_ERR_BAD_ARG, "null pose");
+    return projection_match_pose(m, xw, mp_desc, skip, n, pose_from_rt(rt), cam, kps, kp_desc, m_kps, radius, best12_threshold, kp_to_query, kp_dist);
+}
+int sfe_projection_match_se3(sfe_matcher *m, const double *xw, const uint8_t *mp_desc, const uint8_t *skip, int n,
+                         const sfe_se3 *Tcw, const sfe_camera *cam, const sfe_keypoint *kps, const uint8_t *kp_desc,
+                         int m_kps, double radius, double best12_threshold, int32_t *kp_to_query, int32_t *kp_dist) {
+    SFE_REQUIRE(Tcw, SFE_ERR_BAD_ARG, "null pose");
+    return projection_match_pose(m, xw, mp_desc, skip, n, pose_from_se3(Tcw), cam, kps, kp_desc, m_kps, radius, best12_threshold, kp_to_query, kp_dist);
+}
 
-int sfe_projection_match_keys_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev,
-                                  int n, int64_t idx_base, const double rt[12], const sfe_camera *cam,
+static int projection_match_keys_dev_pose(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev,
+                                  int n, int64_t idx_base, const Pose &T, const sfe_camera *cam,
                                   const sfe_keypoint *kps_dev, const uint8_t *kp_desc_dev, int m_kps, double radius,
                                   double best12_threshold, uint64_t *keys_dev) {
-    SFE_REQUIRE(m && rt && cam && n >= 0 && m_kps >= 1 && keys_dev && kps_dev && kp_desc_dev, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(m && cam && n >= 0 && m_kps >= 1 && keys_dev && kps_dev && kp_desc_dev, SFE_ERR_BAD_ARG, "bad argument");
     SFE_REQUIRE(n == 0 || (xw_dev && mp_desc_dev), SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(m_kps < 65536, SFE_ERR_UNSUPPORTED, "more than 65535 keypoints per frame");
     SFE_REQUIRE(idx_base >= 0 && idx_base + n < (1ll << 31), SFE_ERR_UNSUPPORTED, "global map-point index must fit int32");
     DeviceGuard g(m->device);
-    int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, rt, cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold,
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    int rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, T, cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold,
                              nullptr, nullptr, (uint32_t)idx_base, (unsigned long long *)keys_dev);
     if (rc != SFE_OK) return rc;
     if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
+}
+int sfe_projection_match_keys_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev,
+                                  int n, int64_t idx_base, const double rt[12], const sfe_camera *cam,
+                                  const sfe_keypoint *kps_dev, const uint8_t *kp_desc_dev, int m_kps, double radius,
+                                  double best12_threshold, uint64_t *keys_dev) {
+    SFE_REQUIRE(rt, SFE_ERR_BAD_ARG, "null pose");
+    return projection_match_keys_dev_pose(m, xw_dev, mp_desc_dev, skip_dev, n, idx_base, pose_from_rt(rt), cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold, keys_dev);
+}
+int sfe_projection_match_keys_se3_dev(sfe_matcher *m, const double *xw_dev, const uint8_t *mp_desc_dev, const uint8_t *skip_dev,
+                                  int n, int64_t idx_base, const sfe_se3 *Tcw, const sfe_camera *cam,
+                                  const sfe_keypoint *kps_dev, const uint8_t *kp_desc_dev, int m_kps, double radius,
+                                  double best12_threshold, uint64_t *keys_dev) {
+    SFE_REQUIRE(Tcw, SFE_ERR_BAD_ARG, "null pose");
+    return projection_match_keys_dev_pose(m, xw_dev, mp_desc_dev, skip_dev, n, idx_base, pose_from_se3(Tcw), cam, kps_dev, kp_desc_dev, m_kps, radius, best12_threshold, keys_dev);
 }
 
 int sfe_projection_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int m_kps, int32_t *kp_to_query_dev,
                              int32_t *kp_dist_dev) {
     SFE_REQUIRE(m && keys_dev && kp_to_query_dev && shards >= 1 && m_kps >= 1, SFE_ERR_BAD_ARG, "bad argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     projection_decode_kernel<<<div_up(m_kps, 256), 256, 0, m->stream>>>(m_kps, shards, (const unsigned long long *)keys_dev,
                                                                          kp_to_query_dev, kp_dist_dev);
     m->launches++;
@@ -1327,6 +1415,7 @@ static int frame_new(sfe_matcher *m, const sfe_keypoint *kps, const uint8_t *des
     SFE_REQUIRE(m && cam && out && n >= 0 && n < 65536, SFE_ERR_BAD_ARG, "bad argument");
     SFE_REQUIRE(n == 0 || (kps && desc), SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     sfe_frame *f = new sfe_frame();
     f->device = m->device;
     f->n = n;
@@ -1363,6 +1452,7 @@ int sfe_frame_create_dev(sfe_matcher *m, const sfe_keypoint *kps_dev, const uint
 int sfe_frame_destroy(sfe_frame *f) {
     if (!f) return SFE_OK;
     DeviceGuard g(f->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     f->kps.release(); f->desc.release(); f->nrm.release(); f->grid_mem.release();
     delete f;
     return SFE_OK;
@@ -1378,6 +1468,7 @@ int sfe_frame_normalized(sfe_matcher *m, const sfe_frame *f, double *xy) {
     SFE_REQUIRE(m && f && (xy || f->n == 0), SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     if (f->n > 0) SFE_CUDA(cudaMemcpyAsync(xy, f->nrm.p, sizeof(double2) * f->n, cudaMemcpyDeviceToHost, m->stream));
     SFE_CUDA(cudaStreamSynchronize(m->stream));
     return SFE_OK;
@@ -1391,6 +1482,7 @@ int sfe_frame_stereo_depth(sfe_matcher *m, const sfe_frame *f, const sfe_keypoin
     SFE_REQUIRE(stereo_idx && xc && valid && (kps_r || n_r == 0), SFE_ERR_BAD_ARG, "null argument");
     for (int i = 0; i < f->n; i++) SFE_REQUIRE(stereo_idx[i] < n_r, SFE_ERR_BAD_ARG, "stereo index outside the right keypoints");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     SFE_CUDA(m->d_kr.ensure(std::max(n_r, 1)));
     SFE_CUDA(m->d_idx.ensure(f->n));
@@ -1408,20 +1500,21 @@ int sfe_frame_stereo_depth(sfe_matcher *m, const sfe_frame *f, const sfe_keypoin
     return SFE_OK;
 }
 
-int sfe_frame_reprojection_error(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *has_mp, const double rt[12],
+static int frame_reprojection_error_pose(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *has_mp, const Pose &T,
                                  double *err) {
-    SFE_REQUIRE(m && f && rt, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(m && f, SFE_ERR_BAD_ARG, "bad argument");
     SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
     if (f->n == 0) return SFE_OK;
     SFE_REQUIRE(xw && has_mp && err, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     SFE_CUDA(m->d_xw.ensure((size_t)f->n * 4));  // n x 3 points, then n errors
     SFE_CUDA(m->d_skip.ensure(f->n));
     SFE_CUDA(cudaMemcpyAsync(m->d_xw.p, xw, sizeof(double) * 3 * f->n, cudaMemcpyHostToDevice, st));
     SFE_CUDA(cudaMemcpyAsync(m->d_skip.p, has_mp, f->n, cudaMemcpyHostToDevice, st));
     ProjParams P{};
-    memcpy(P.rt, rt, sizeof(P.rt));
+    P.T = T;
     reprojection_error_kernel<<<div_up(f->n, 128), 128, 0, st>>>(f->cam, P, f->kps.p, f->n, m->d_xw.p, m->d_skip.p,
                                                                  m->d_xw.p + (size_t)f->n * 3);
     m->launches++;
@@ -1430,15 +1523,26 @@ int sfe_frame_reprojection_error(sfe_matcher *m, const sfe_frame *f, const doubl
     SFE_CUDA(cudaStreamSynchronize(st));
     return SFE_OK;
 }
+int sfe_frame_reprojection_error(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *has_mp, const double rt[12],
+                                 double *err) {
+    SFE_REQUIRE(rt, SFE_ERR_BAD_ARG, "null pose");
+    return frame_reprojection_error_pose(m, f, xw, has_mp, pose_from_rt(rt), err);
+}
+int sfe_frame_reprojection_error_se3(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *has_mp, const sfe_se3 *Tcw,
+                                 double *err) {
+    SFE_REQUIRE(Tcw, SFE_ERR_BAD_ARG, "null pose");
+    return frame_reprojection_error_pose(m, f, xw, has_mp, pose_from_se3(Tcw), err);
+}
 
-int sfe_frame_projection_match(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *mp_desc, const uint8_t *skip,
-                               int n, const double rt[12], double radius, double best12_threshold, int32_t *kp_to_query,
+static int frame_projection_match_pose(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *mp_desc, const uint8_t *skip,
+                               int n, const Pose &T, double radius, double best12_threshold, int32_t *kp_to_query,
                                int32_t *kp_dist) {
-    SFE_REQUIRE(m && f && rt && n >= 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(m && f && n >= 0, SFE_ERR_BAD_ARG, "bad argument");
     SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
     if (f->n == 0) return SFE_OK;
     SFE_REQUIRE(kp_to_query && (n == 0 || (xw && mp_desc)), SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     const int nn = std::max(n, 1);
     SFE_CUDA(m->d_xw.ensure((size_t)nn * 3)); SFE_CUDA(m->d_dl.ensure((size_t)nn * 32)); SFE_CUDA(m->d_skip.ensure(nn));
@@ -1448,13 +1552,25 @@ int sfe_frame_projection_match(sfe_matcher *m, const sfe_frame *f, const double 
         SFE_CUDA(cudaMemcpyAsync(m->d_dl.p, mp_desc, (size_t)n * 32, cudaMemcpyHostToDevice, st));
         if (skip) SFE_CUDA(cudaMemcpyAsync(m->d_skip.p, skip, n, cudaMemcpyHostToDevice, st));
     }
-    int rc = projection_impl(m, m->d_xw.p, m->d_dl.p, skip ? m->d_skip.p : nullptr, n, rt, &f->cam, f->kps.p, f->desc.p, f->n, radius,
+    int rc = projection_impl(m, m->d_xw.p, m->d_dl.p, skip ? m->d_skip.p : nullptr, n, T, &f->cam, f->kps.p, f->desc.p, f->n, radius,
                              best12_threshold, m->d_idx.p, m->d_dist.p, 0, nullptr, &f->grid);
     if (rc != SFE_OK) return rc;
     SFE_CUDA(cudaMemcpyAsync(kp_to_query, m->d_idx.p, sizeof(int32_t) * f->n, cudaMemcpyDeviceToHost, st));
     if (kp_dist) SFE_CUDA(cudaMemcpyAsync(kp_dist, m->d_dist.p, sizeof(int32_t) * f->n, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaStreamSynchronize(st));
     return SFE_OK;
+}
+int sfe_frame_projection_match(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *mp_desc, const uint8_t *skip,
+                               int n, const double rt[12], double radius, double best12_threshold, int32_t *kp_to_query,
+                               int32_t *kp_dist) {
+    SFE_REQUIRE(rt, SFE_ERR_BAD_ARG, "null pose");
+    return frame_projection_match_pose(m, f, xw, mp_desc, skip, n, pose_from_rt(rt), radius, best12_threshold, kp_to_query, kp_dist);
+}
+int sfe_frame_projection_match_se3(sfe_matcher *m, const sfe_frame *f, const double *xw, const uint8_t *mp_desc, const uint8_t *skip,
+                               int n, const sfe_se3 *Tcw, double radius, double best12_threshold, int32_t *kp_to_query,
+                               int32_t *kp_dist) {
+    SFE_REQUIRE(Tcw, SFE_ERR_BAD_ARG, "null pose");
+    return frame_projection_match_pose(m, f, xw, mp_desc, skip, n, pose_from_se3(Tcw), radius, best12_threshold, kp_to_query, kp_dist);
 }
 
 int sfe_frame_search_radius(sfe_matcher *m, const sfe_frame *f, const double *uv, int q, double radius, int32_t *idx, int cap,
@@ -1464,6 +1580,7 @@ int sfe_frame_search_radius(sfe_matcher *m, const sfe_frame *f, const double *uv
     if (q == 0) return SFE_OK;
     SFE_REQUIRE(uv && idx && counts, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     SFE_CUDA(m->d_xw.ensure((size_t)q * 2));
     SFE_CUDA(m->d_quad.ensure((size_t)q * cap));
@@ -1484,6 +1601,7 @@ int sfe_frame_search_nearest(sfe_matcher *m, const sfe_frame *f, const double *u
     if (q == 0) return SFE_OK;
     SFE_REQUIRE(uv && kpt_index && dist2, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     SFE_CUDA(m->d_xw.ensure((size_t)q * 3));
     SFE_CUDA(m->d_n.ensure(q));
@@ -1516,6 +1634,7 @@ int sfe_vocab_create(sfe_matcher *m, int n_nodes, const int32_t *parent, const u
     }
     SFE_REQUIRE(start[1] > 0, SFE_ERR_BAD_ARG, "the root has no children");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     sfe_vocab *v = new sfe_vocab();
     v->device = m->device;
     v->n_nodes = n_nodes;
@@ -1543,6 +1662,7 @@ int sfe_vocab_create(sfe_matcher *m, int n_nodes, const int32_t *parent, const u
 int sfe_vocab_destroy(sfe_vocab *v) {
     if (!v) return SFE_OK;
     DeviceGuard g(v->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     v->child_start.release(); v->child_list.release(); v->word_id.release(); v->desc.release(); v->weight.release();
     delete v;
     return SFE_OK;
@@ -1570,6 +1690,7 @@ int sfe_vocab_transform_dev(sfe_matcher *m, const sfe_vocab *v, const uint8_t *d
     if (n == 0) return SFE_OK;
     SFE_REQUIRE(desc_dev && word_id_dev && weight_dev && node_id_dev, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     int rc = vocab_launch(m, v, desc_dev, n, levelsup, word_id_dev, weight_dev, node_id_dev);
     if (rc != SFE_OK) return rc;
     if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
@@ -1583,6 +1704,7 @@ int sfe_vocab_transform(sfe_matcher *m, const sfe_vocab *v, const uint8_t *desc,
     if (n == 0) return SFE_OK;
     SFE_REQUIRE(desc && word_id && weight && node_id, SFE_ERR_BAD_ARG, "null argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     SFE_CUDA(m->d_dl.ensure((size_t)n * 32));
     SFE_CUDA(m->d_idx.ensure(n)); SFE_CUDA(m->d_dist.ensure(n)); SFE_CUDA(m->d_xw.ensure(n));
@@ -1635,6 +1757,7 @@ int sfe_db_create(sfe_matcher *m, const uint8_t *desc_host, int64_t rows, int64_
     SFE_REQUIRE(rows == 0 || desc_host, SFE_ERR_BAD_ARG, "null argument");
     SFE_REQUIRE(idx_base + rows < (1ll << 31), SFE_ERR_UNSUPPORTED, "global row index must fit int32");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     sfe_db *db = new sfe_db();
     db->device = m->device;
     db->rows = rows;
@@ -1654,6 +1777,7 @@ int sfe_db_create(sfe_matcher *m, const uint8_t *desc_host, int64_t rows, int64_
 int sfe_db_destroy(sfe_db *db) {
     if (!db) return SFE_OK;
     DeviceGuard g(db->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaFree(db->rows_dev);
     delete db;
     return SFE_OK;
@@ -1663,6 +1787,7 @@ int sfe_knn2_dev(sfe_matcher *m, const sfe_db *db, const uint8_t *queries_dev, i
     SFE_REQUIRE(m && db && queries_dev && keys_dev && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
     SFE_REQUIRE(db->device == m->device, SFE_ERR_BAD_ARG, "database lives on another device");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     int rc = knn_partial(m, db, queries_dev, q, (unsigned long long *)keys_dev, nullptr);
     if (rc != SFE_OK) return rc;
     if (!m->async_dev) SFE_CUDA(cudaStreamSynchronize(m->stream));
@@ -1672,6 +1797,7 @@ int sfe_knn2_dev(sfe_matcher *m, const sfe_db *db, const uint8_t *queries_dev, i
 int sfe_knn2_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int q, int32_t *out_dev) {
     SFE_REQUIRE(m && keys_dev && out_dev && shards >= 1 && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     knn2_merge_kernel<<<div_up(q, 4), 128, 0, m->stream>>>((const unsigned long long *)keys_dev, shards, q, nullptr, out_dev);
     m->launches++;
     SFE_CUDA(cudaGetLastError());
@@ -1683,6 +1809,7 @@ int sfe_knn2(sfe_matcher *m, const sfe_db *db, const uint8_t *queries, int q, in
     SFE_REQUIRE(m && db && queries && out && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
     SFE_REQUIRE(db->device == m->device, SFE_ERR_BAD_ARG, "database lives on another device");
     DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStream_t st = m->stream;
     SFE_CUDA(m->d_dl.ensure((size_t)q * 32));
     SFE_CUDA(m->d_quad.ensure((size_t)q * 4));

@@ -72,9 +72,12 @@ def knn_database(m: int, seed: int = 1234) -> np.ndarray:
     return np.random.default_rng(seed).integers(0, 256, (m, 32), dtype=np.uint8)
 
 
-def knn_queries(db: np.ndarray, q: int, seed: int = 5678, max_flips: int = 40):
-    """q rows picked from db with 0..max_flips random bit flips each, so the
-    ratio test of reference src/matcher.cpp:125 both passes and fails."""
+def knn_queries(db: np.ndarray, q: int, seed: int = 5678, max_flips: int = 40, hard_fraction: float = 0.0,
+                hard_flips=(45, 90)):
+    """q rows picked from db with 0..max_flips random bit flips each.  Among 10 M random 256-bit rows the second-best
+    distance of such a query is ~85, so up to 40 flips always pass the ratio test of reference src/matcher.cpp:125
+    (2 * dist0 < dist1); `hard_fraction` of the queries get hard_flips[0]..hard_flips[1] flips instead, so that the
+    test both passes and fails."""
     rng = np.random.default_rng(seed)
     rows = rng.choice(db.shape[0], q, replace=db.shape[0] < q)
     out = db[rows].copy()
@@ -83,6 +86,12 @@ def knn_queries(db: np.ndarray, q: int, seed: int = 5678, max_flips: int = 40):
         bits = rng.integers(0, 256, nf)
         for b in bits:
             out[i, b >> 3] ^= np.uint8(1 << (b & 7))
+    if hard_fraction > 0:
+        rng2 = np.random.default_rng(seed + 1)
+        for i in np.nonzero(rng2.random(q) < hard_fraction)[0]:
+            out[i] = db[rows[i]]
+            for b in rng2.choice(256, int(rng2.integers(hard_flips[0], hard_flips[1] + 1)), replace=False):
+                out[i, b >> 3] ^= np.uint8(1 << (b & 7))
     return out, rows
 
 

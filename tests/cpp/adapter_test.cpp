@@ -10,9 +10,8 @@
 #include <fstream>
 
 struct Vec3 { double v[3]; double operator[](int i) const { return v[i]; } };
-struct Mat3 { double m[3][3]; double operator()(int r, int c) const { return m[r][c]; } };
-struct Rot { Mat3 R; Mat3 toRotationMatrix() const { return R; } };
-struct SE3 { Rot r; Vec3 t; const Rot &rotation() const { return r; } const Vec3 &translation() const { return t; } };
+struct Quat { double x_, y_, z_, w_; double x() const { return x_; } double y() const { return y_; } double z() const { return z_; } double w() const { return w_; } };
+struct SE3 { Quat r; Vec3 t; const Quat &rotation() const { return r; } const Vec3 &translation() const { return t; } };  // g2o::SE3Quat's accessors
 struct KMat { double k[3][3]; double operator()(int r, int c) const { return k[r][c]; } };
 struct DVec { double d[4]; double operator()(int i) const { return d[i]; } };
 struct Camera {
@@ -70,7 +69,7 @@ int main(int argc, char **argv) {
                                    f.descriptions_.row((int)i)});
         }
         for (auto &p : pts) mps.insert(&p);
-        SE3 T{{{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}}}, {{0, 0, 0}}};
+        SE3 T{{0, 0, 0, 1}, {{0, 0, 0}}};
         std::map<int, Mappoint *> m = sfe_adapter::ProjectionMatch(mps, T, &f, 50.);                              // posetracker.cpp:186
         size_t self = 0;
         for (auto &kv : m) self += kv.second->desc.data == f.descriptions_.ptr(kv.first);

@@ -41,7 +41,7 @@ def test_keypoint_layout_is_cv_keypoint():
 
 
 def test_host_only_entry_points(built, oracle):
-    assert built.sfe_abi_version() == 1
+    assert built.sfe_abi_version() == 2
     assert built.sfe_status_string(0) == b"ok"
     rng = np.random.default_rng(0)
     for _ in range(50):

@@ -26,15 +26,15 @@ def kitti_ex(gpu):
     return api.ORBextractor(max_images=8)
 
 
-def _stage_report(ex, ref, image_idx, nlevels):
+def _stage_report(ex, ref, image_idx, nlevels, cap=1 << 15):
     bad = []
     for l in range(nlevels):
         if not np.array_equal(ex.debug_level(image_idx, l), ref.level(l)):
             bad.append(f"pyramid L{l}: {(ex.debug_level(image_idx, l) != ref.level(l)).sum()} px differ")
-        c, rc = ex.debug_points(image_idx, l), ref.candidates(l)
+        c, rc = ex.debug_points(image_idx, l, cap=cap), ref.candidates(l, cap=cap)
         if not np.array_equal(c, rc):
             bad.append(f"FAST candidates L{l}: {len(c)} vs {len(rc)}")
-        d, rd = ex.debug_points(image_idx, l, distributed=True), ref.distributed(l)
+        d, rd = ex.debug_points(image_idx, l, distributed=True, cap=cap), ref.distributed(l, cap=cap)
         if not np.array_equal(d, rd):
             bad.append(f"quadtree L{l}: {len(d)} vs {len(rd)}")
         rb = ref.blur(l)
@@ -181,10 +181,12 @@ def test_sequence_edge_cases_and_replanning(gpu, oracle):
         assert len(rk) >= nf if nf == 20 else len(rk) > 3000
 
 
-def test_4k_frames_and_the_candidate_capacity_error(gpu, oracle):
+def test_4k_frames_dense_and_noise_images(gpu, oracle):
     """3840 x 2160: coordinates beyond the stereo matcher's bucket grid (clamped buckets), a tracking bucket grid that
-    needs the opt-in shared-memory size, wide levels, 44 k corners on one level.  A frame with more FAST corners than a
-    level's candidate buffer (60000) is refused with SFE_ERR_CAPACITY, never truncated."""
+    needs the opt-in shared-memory size, wide levels, 44 k corners on one level.  A noise frame with 840 k FAST corners on
+    level 0 -- far beyond any pre-sized candidate buffer and beyond the quadtree's 16-bit instance -- is NOT refused (the
+    reference's candidate list is unbounded, src/orb_extractor.cpp:778-779): the call re-runs itself with buffers sized
+    from its own count and returns the reference's keypoints."""
     w, h = 3840, 2160
     Ls, Rs = synth.stereo_sequence(2, 2, 4, 1280, 720)
 
@@ -212,12 +214,83 @@ def test_4k_frames_and_the_candidate_capacity_error(gpu, oracle):
     assert max(len(ref.candidates(l)) for l in range(8)) > 40000
     k, d = ex.extract(dense)
     assert np.array_equal(k, dk) and np.array_equal(d, dd)
-    noise = np.random.default_rng(1).integers(0, 256, (h, w), dtype=np.uint8)   # several hundred thousand corners per level
-    with pytest.raises(api.SfeError) as err:
-        ex.extract(noise)
-    assert err.value.status == api.SFE_ERR_CAPACITY and "candidate buffer" in str(err.value)
-    k, d = ex.extract(L[0])                   # the handle is still usable afterwards
+    noise = np.random.default_rng(1).integers(0, 256, (h, w), dtype=np.uint8)   # 840 k / 533 k / 332 k ... corners per level
+    nk, nd = ref.extract(noise)
+    assert len(ref.candidates(0, cap=1 << 21)) > 800000
+    k, d = ex.extract(noise)                  # first pass overflows, the call re-runs with the 32-bit quadtree
+    assert len(k) == len(nk) >= 5000 and np.array_equal(k, nk) and np.array_equal(d, nd)
+    assert _stage_report(ex, ref, 0, 8, cap=1 << 21) == []
+    k, d = ex.extract(L[0])                   # and ordinary frames still match afterwards
     assert np.array_equal(k, rk) and np.array_equal(d, rd)
+
+
+def test_candidate_overflow_reruns_instead_of_failing(gpu, oracle, monkeypatch):
+    """Tiny initial candidate buffers (SFE_CAND_CAP=64): every entry point -- single image, pipelined host batch, resident
+    batch -- re-runs with room for what the first pass counted and returns the oracle's bytes; an asynchronous resident
+    queue reports SFE_ERR_CAPACITY at wait() (its inputs belong to the caller) and succeeds when the batch is re-submitted."""
+    monkeypatch.setenv("SFE_CAND_CAP", "64")
+    ex = api.ORBextractor(max_images=8)
+    ref = oracle.Extractor()
+    imgs = np.stack([synth.stereo_pair(s)[i] for s in (20, 21) for i in (0, 1)])
+    want = [ref.extract(im) for im in imgs]
+    k, d = ex.extract(imgs[0])
+    assert np.array_equal(k, want[0][0]) and np.array_equal(d, want[0][1])
+    monkeypatch.setenv("SFE_PIPELINE_CHUNKS", "2")
+    ex2 = api.ORBextractor(max_images=8)
+    kps, desc, n = ex2.extract_batch(imgs)
+    for i, (wk, wd) in enumerate(want):
+        assert n[i] == len(wk) and np.array_equal(kps[i, :n[i]], wk) and np.array_equal(desc[i, :n[i]], wd)
+    out = ex2.stereo_frames(imgs[0::2], imgs[1::2])
+    for f in range(2):
+        assert np.array_equal(out["kps_r"][f, :out["n_r"][f]], want[2 * f + 1][0])
+    # resident, synchronous and asynchronous
+    ex3 = api.ORBextractor(max_images=8)
+    H, W = imgs.shape[1:]
+    d_img = api.DeviceBuffer(imgs.nbytes)
+    d_img.upload(imgs)
+    cap = ex3.cap
+    d_k, d_d, d_n = api.DeviceBuffer(4 * cap * 28), api.DeviceBuffer(4 * cap * 32), api.DeviceBuffer(16)
+    ex3.extract_batch_dev(d_img.ptr, 4, W, H, d_k.ptr, d_d.ptr, d_n.ptr)
+    n = d_n.download((4,), np.int32)
+    kk = d_k.download((4, cap), api.KP_DTYPE)
+    for i, (wk, _) in enumerate(want):
+        assert n[i] == len(wk) and np.array_equal(kk[i, :n[i]], wk)
+    ex4 = api.ORBextractor(max_images=8)
+    ex4.set_async(True)
+    ex4.extract_batch_dev(d_img.ptr, 4, W, H, d_k.ptr, d_d.ptr, d_n.ptr)
+    with pytest.raises(api.SfeError) as err:
+        ex4.wait()
+    assert err.value.status == api.SFE_ERR_CAPACITY and "submit the batch again" in str(err.value)
+    ex4.extract_batch_dev(d_img.ptr, 4, W, H, d_k.ptr, d_d.ptr, d_n.ptr)
+    ex4.wait()
+    n = d_n.download((4,), np.int32)
+    kk = d_k.download((4, cap), api.KP_DTYPE)
+    for i, (wk, _) in enumerate(want):
+        assert n[i] == len(wk) and np.array_equal(kk[i, :n[i]], wk)
+
+
+def test_few_features_on_a_wide_image(gpu, oracle):
+    """nfeatures = 20 on a KITTI frame: a level keeps all 4 * nIni = 16 first-split nodes although its quota is 2-4
+    (src/orb_extractor.cpp:606-669), so the frame returns far more than nfeatures + a few per level"""
+    img = synth.stereo_pair(3)[0]
+    ex = api.ORBextractor(20, 1.2, 8, 20, 7)
+    rk, rd = oracle.Extractor(20, 1.2, 8, 20, 7).extract(img)
+    assert len(rk) > 20 + 4 * 8
+    assert ex.cap_for(1241, 376) >= len(rk)
+    k, d = ex.extract(img)
+    assert np.array_equal(k, rk) and np.array_equal(d, rd)
+
+
+def test_ctor_tables_equal_the_oracle(gpu, oracle):
+    """GetScaleFactors / GetInverseScaleFactors / GetScaleSigmaSquares / GetInverseScaleSigmaSquares (the last is the one
+    the reference reads, src/pipeline.cpp:89) and the per-level quotas, by float bits"""
+    for nf, sf, nl in [(2000, 1.2, 8), (500, 1.2, 4), (300, 1.5, 3), (1500, 1.1, 12), (4000, 2.0, 5), (777, 1.33, 7)]:
+        ex = api.ORBextractor(nf, sf, nl, 20, 7)
+        t = oracle.Extractor(nf, sf, nl, 20, 7).tables()
+        for got, key in zip((ex.GetScaleFactors(), ex.GetInverseScaleFactors(), ex.GetScaleSigmaSquares(),
+                             ex.GetInverseScaleSigmaSquares()), ("scale", "inv_scale", "sigma2", "inv_sigma2")):
+            assert np.array_equal(np.asarray(got, np.float32).view(np.uint32), t[key].view(np.uint32)), (key, nf, sf, nl)
+        assert np.array_equal(np.asarray(ex.features_per_level(), np.int32), t["per_level"])
 
 
 def test_batch_equals_single(kitti_ex, oracle):
@@ -640,24 +713,82 @@ def test_knn2_vs_oracle_and_sharded_merge(gpu, oracle):
         assert np.array_equal(out.download((Q, 4), np.int32), ref), bounds
 
 
-def test_knn2_full_size_properties(gpu):
-    """BASELINE config 4 shape at reduced M (2M rows; tools/knn_bench.py and bench.py's `hamming` object run 10M):
-    size-independent properties instead of the (too slow) oracle."""
+def test_knn2_baseline_config4_full_size_bit_exact(gpu, oracle):
+    """BASELINE config 4 exactly as SURVEY §8d states it: 10 M x 32 B map from default_rng(1234), 2000 queries = map rows
+    picked by default_rng(5678) with bit flips (a fifth of them flipped hard enough to FAIL the ratio test), every
+    {idx0, dist0, idx1, dist1} compared with the threaded C oracle -- and the same over 3 uneven row shards + merge."""
+    import os
     m = api.Matcher()
-    db = synth.knn_database(2_000_000, seed=1234)
-    q, rows = synth.knn_queries(db, 2000, seed=5678)
-    out = m.knn2(m.create_db(db), q)
-    d_true = np.unpackbits(db[rows] ^ q, axis=1).sum(1)
-    assert (out[:, 1] <= d_true).all()                      # best is at least as good as the planted row
-    exact = out[:, 1] == d_true
-    assert (out[exact, 0] <= rows[exact]).all()             # ties resolved towards the smaller index
-    assert (out[:, 1] <= out[:, 3]).all() and (out[:, 0] != out[:, 2]).all()
-    chk = np.unpackbits(db[out[:, 0]] ^ q, axis=1).sum(1)   # reported distance is the real distance
-    assert np.array_equal(chk, out[:, 1])
-    chk2 = np.unpackbits(db[out[:, 2]] ^ q, axis=1).sum(1)
-    assert np.array_equal(chk2, out[:, 3])
-    ratio_pass = (2 * out[:, 1] < out[:, 3]).mean()
-    assert 0.2 < ratio_pass <= 1.0
+    db = synth.knn_database(10_000_000, seed=1234)
+    q, rows = synth.knn_queries(db, 2000, seed=5678, hard_fraction=0.2)
+    q[7] = db[123]          # exact duplicates of one row: (0, 123) then the tie partner by index
+    db[9_999_999] = db[123]
+    ref = oracle.knn2(q, db, nthreads=os.cpu_count() or 8)
+    dbh = m.create_db(db)
+    out = m.knn2(dbh, q)
+    assert np.array_equal(out, ref), f"{(out != ref).any(1).sum()} of 2000 queries differ"
+    assert out[7].tolist() == [123, 0, 9_999_999, 0]
+    passed = 2 * out[:, 1] < out[:, 3]
+    assert 0.6 < passed.mean() < 0.95, "the ratio test must both pass and fail on this workload"
+    for nq in (1, 2, 4):    # the streaming kernels (thread = row)
+        assert np.array_equal(m.knn2(dbh, q[:nq]), ref[:nq])
+    del dbh
+    # shards: contiguous, uneven, merged through the packed keys exactly as the multi-GPU path does
+    bounds = [0, 3_333_333, 3_333_334, 10_000_000]
+    keys = api.DeviceBuffer(3 * 2000 * 2 * 8)
+    d_q = api.DeviceBuffer(q.nbytes).upload(q)
+    for sidx in range(3):
+        lo, hi = bounds[sidx], bounds[sidx + 1]
+        sh = m.create_db(db[lo:hi], idx_base=lo)
+        m.knn2_dev(sh, d_q.ptr, 2000, keys.ptr + sidx * 2000 * 2 * 8)
+        del sh
+    d_out = api.DeviceBuffer(2000 * 16)
+    m.knn2_merge_dev(keys.ptr, 3, 2000, d_out.ptr)
+    assert np.array_equal(d_out.download((2000, 4), np.int32), ref)
+
+
+def test_projection_match_baseline_config5_full_size_bit_exact(gpu, oracle, kitti_ex):
+    """BASELINE config 5 at its stated size: 500 k map points against the seed-0 frame, r = 50, identity pose given as the
+    reference's SE3Quat -- every keypoint's (map point, distance) equals the C oracle (grid-accelerated, which
+    tests/test_oracle_matchers.py ties to the exhaustive one), plus a real pose with distortion and a skip mask."""
+    m = api.Matcher()
+    L, _ = synth.stereo_pair(0)
+    kps, desc = kitti_ex.extract(L)
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    xw, mpd = synth.projection_scene(xy, desc, 500_000, seed=99)
+    for dcoef, pose, skip in (([0, 0, 0, 0], [0, 0, 0, 1, 0, 0, 0], None),
+                              ([-0.05, 0.01, 0.001, -0.002], [0.003, -0.004, 0.001, 0.99998650, 0.05, -0.02, 0.2],
+                               (np.random.default_rng(5).uniform(0, 1, len(xw)) < 0.05).astype(np.uint8))):
+        cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, dcoef, 1241, 376)
+        ocam = oracle.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, dcoef, 1241, 376)
+        qt = np.array(pose, np.float64)
+        qt[:4] /= np.linalg.norm(qt[:4])
+        got, gd = m.ProjectionMatch(xw, mpd, skip, qt, cam, kps, desc, 50.0)
+        ref, rd = oracle.projection_match(xw, mpd, skip, qt, ocam, kps, desc, 50.0, grid=True)
+        assert np.array_equal(got, ref), f"{(got != ref).sum()} keypoints differ"
+        assert np.array_equal(gd, rd)
+        assert (ref >= 0).sum() > 300
+    # the matrix form of the identity pose gives the same matches
+    got2, _ = m.ProjectionMatch(xw, mpd, None, np.eye(3, 4), api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX,
+                                synth.KITTI_CY, [0, 0, 0, 0], 1241, 376), kps, desc, 50.0)
+    ref2, _ = oracle.projection_match(xw, mpd, None, np.array([0, 0, 0, 1, 0, 0, 0.0]), oracle.make_camera(
+        synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0, 0, 0, 0], 1241, 376), kps, desc, 50.0, grid=True)
+    assert np.array_equal(got2, ref2)
+
+
+def test_projection_match_se3_golden_fixture_of_the_reference(gpu, kitti_ex):
+    """tests/golden/golden_proj.npz: the result of the reference's own ProjectionMatch (oracle/_ref) on 3000 map points
+    with a distorted camera and a real SE3 pose; keypoints from the seed-0 golden frame"""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_proj.npz"))
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_seed0.npz"))
+    m = api.Matcher()
+    cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, z["dist4"], 1241, 376)
+    for radius in (50, 10):
+        got, _ = m.ProjectionMatch(z["xw"], z["mp_desc"], z["skip"], z["qt"], cam, g["kl"], g["dl"], float(radius))
+        assert np.array_equal(got, z[f"to_query_r{radius}"])
+    fr = api.Frame(m, g["kl"], g["dl"], cam)
+    got, _ = fr.ProjectionMatch(z["xw"], z["mp_desc"], z["skip"], z["qt"], 50.0)
+    assert np.array_equal(got, z["to_query_r50"])
 
 
 # ---- frame glue (SURVEY §8f rows 1, 3) -----------------------------------------------------------------
