@@ -95,6 +95,7 @@ typedef struct sfe_db sfe_db;
 typedef struct sfe_event sfe_event;
 typedef struct sfe_frame sfe_frame;
 typedef struct sfe_vocab sfe_vocab;
+typedef struct sfe_comm sfe_comm;
 
 /* ---- general -------------------------------------------------------------------------- */
 int sfe_abi_version(void);
@@ -366,6 +367,41 @@ int sfe_knn2_dev(sfe_matcher *m, const sfe_db *db, const uint8_t *queries_dev, i
 /* merge `shards` gathered key arrays (shards x q x 2) into out_dev[q*4] */
 int sfe_knn2_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shards, int q,
                        int32_t *out_dev);
+
+/* ---- multi-GPU: sharded database / sharded local map -----------------------------------------------
+ * A communicator is one rank's end of an exchange between `world` GPUs of one box.  The data path is ONE step: every rank's
+ * kernel stores its per-query top-2 keys (kNN) or per-keypoint best keys (ProjectionMatch) straight into every peer's
+ * inbox over NVLink peer memory and raises a flag; the merge kernel of each rank waits on its own flags.  No host
+ * round trip, no NCCL call and no extra copy between the local kernels, the exchange and the merge; every rank ends up
+ * with the full merged result (all-gather semantics).  Results are exact and independent of the shard boundaries
+ * (ties break on the global index / the global query order).
+ *   - one process per GPU (torchrun, MPI): sfe_comm_create on every rank, exchange the 64-byte handles of
+ *     sfe_comm_export by any means (one all-gather at set-up time), sfe_comm_connect with all of them;
+ *   - one process driving several GPUs: sfe_comm_create_local fills one connected communicator per device.
+ * The sharded calls are COLLECTIVE: every rank must issue the same sequence of them, with its own shard.  They return
+ * as soon as their kernels are enqueued on the matcher's stream (whatever the matcher's async mode: a host thread that
+ * drives several ranks could not otherwise enqueue rank 1 while rank 0 waits for it); sfe_matcher_wait completes them.
+ * Use one communicator per matcher.  A rank that never shows up is detected by its peers after 5 s: their results are
+ * invalid and sfe_comm_status reports it. */
+#define SFE_COMM_HANDLE_BYTES 64
+int sfe_comm_create(int device, int rank, int world, sfe_comm **out); /* world <= 16 */
+int sfe_comm_export(sfe_comm *c, uint8_t handle[SFE_COMM_HANDLE_BYTES]);
+int sfe_comm_connect(sfe_comm *c, const uint8_t *handles /* world x SFE_COMM_HANDLE_BYTES, rank order */);
+int sfe_comm_create_local(const int *devices, int n, sfe_comm **out /* n handles */);
+int sfe_comm_destroy(sfe_comm *c);
+int sfe_comm_status(sfe_comm *c, int *stalled_rank /* optional: -1 = none */);
+/* Brute-force top-2 of q resident queries (the same on every rank) against the row-sharded map: `shard` = this rank's
+ * rows (sfe_db_create with idx_base = global index of its first row).  out_dev[q*4] = {idx0, dist0, idx1, dist1} over
+ * the WHOLE map, on every rank.  q <= 32768. */
+int sfe_knn2_sharded(sfe_matcher *m, sfe_comm *c, const sfe_db *shard, const uint8_t *queries_dev, int q,
+                     int32_t *out_dev);
+/* ProjectionMatch of a local map sharded by map points against one resident frame (the same on every rank): this rank's
+ * n points are the global map points [idx_base, idx_base + n) of the caller's order.  kp_to_query_dev[j] = GLOBAL index of
+ * the map point matched to keypoint j or -1, kp_dist_dev[j] (optional) = its distance, on every rank. */
+int sfe_projection_match_sharded(sfe_matcher *m, sfe_comm *c, const sfe_frame *f, const double *xw_dev,
+                                 const uint8_t *mp_desc_dev, const uint8_t *skip_dev, int n, int64_t idx_base,
+                                 const sfe_se3 *Tcw, double radius, double best12_threshold,
+                                 int32_t *kp_to_query_dev, int32_t *kp_dist_dev);
 
 /* ---- Front-end results as one byte stream -------------------------------------------------
  * The reference has no on-disk form of a frame (Memento save is `#if 0`, src/pipeline.cpp:231-241); this is the one

@@ -171,6 +171,14 @@ SIGNATURES = {
     "sfe_knn2": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sfe_knn2_dev": (_i, [_vp, _vp, _vp, _i, _vp]),
     "sfe_knn2_merge_dev": (_i, [_vp, _vp, _i, _i, _vp]),
+    "sfe_comm_create": (_i, [_i, _i, _i, _pp]),
+    "sfe_comm_export": (_i, [_vp, _vp]),
+    "sfe_comm_connect": (_i, [_vp, _vp]),
+    "sfe_comm_create_local": (_i, [_vp, _i, _pp]),
+    "sfe_comm_destroy": (_i, [_vp]),
+    "sfe_comm_status": (_i, [_vp, C.POINTER(_i)]),
+    "sfe_knn2_sharded": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "sfe_projection_match_sharded": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, C.POINTER(SE3), _d, _d, _vp, _vp]),
 }
 
 _lib = None
@@ -605,8 +613,70 @@ class Matcher:
     def knn2_dev(self, db, queries_ptr, q, keys_ptr):
         _check(lib().sfe_knn2_dev(self.h, db.h, _p(queries_ptr), q, _p(keys_ptr)))
 
+    def knn2_sharded(self, comm: "Comm", db, queries_ptr, q, out_ptr):
+        """collective over comm.world ranks; returns once enqueued (wait() completes it)"""
+        _check(lib().sfe_knn2_sharded(self.h, comm.h, db.h, _p(queries_ptr), q, _p(out_ptr)))
+
+    def projection_match_sharded(self, comm: "Comm", frame: "Frame", xw_ptr, mp_desc_ptr, skip_ptr, n, idx_base, Tcw, radius,
+                                 to_q_ptr, dist_ptr, best12=0.5):
+        """collective; Tcw = 7 numbers (qx, qy, qz, qw, tx, ty, tz); returns once enqueued (wait() completes it)"""
+        kind, pose = _pose(Tcw)
+        assert kind == "_se3", "the sharded call takes the pose as an SE3Quat"
+        _check(lib().sfe_projection_match_sharded(self.h, comm.h, frame.h, _p(xw_ptr), _p(mp_desc_ptr), _p(skip_ptr), n, idx_base,
+                                                  C.byref(pose), radius, best12, _p(to_q_ptr), _p(dist_ptr)))
+
     def knn2_merge_dev(self, keys_ptr, shards, q, out_ptr):
         _check(lib().sfe_knn2_merge_dev(self.h, _p(keys_ptr), shards, q, _p(out_ptr)))
+
+
+class Comm:
+    """sfe_comm: one rank's end of the NVLink peer-memory exchange behind the sharded kNN / ProjectionMatch calls."""
+
+    def __init__(self, device=0, rank=0, world=1, _handle=None):
+        self.device, self.rank, self.world = device, rank, world
+        if _handle is None:
+            h = C.c_void_p()
+            _check(lib().sfe_comm_create(device, rank, world, C.byref(h)))
+            _handle = h
+        self.h = _handle
+
+    def export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _check(lib().sfe_comm_export(self.h, buf))
+        return bytes(buf)
+
+    def connect(self, handles):
+        """handles: the export() of every rank, in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(lib().sfe_comm_connect(self.h, buf))
+        return self
+
+    @staticmethod
+    def create_local(devices):
+        """one process driving several GPUs: a connected communicator per device"""
+        n = len(devices)
+        devs = (C.c_int * n)(*devices)
+        hs = (C.c_void_p * n)()
+        _check(lib().sfe_comm_create_local(devs, n, hs))
+        return [Comm(devices[i], i, n, _handle=C.c_void_p(hs[i])) for i in range(n)]
+
+    def status(self):
+        """raises when a peer never delivered its part of a collective"""
+        r = C.c_int()
+        _check(lib().sfe_comm_status(self.h, C.byref(r)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sfe_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Frame:

@@ -1029,6 +1029,142 @@ int launch_track_frames(cudaStream_t st, int device, TrackScratch &T, int frames
     return SFE_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU exchange: every rank's kernel stores its contribution straight into every peer's inbox over
+// NVLink (peer-mapped device memory: cudaIpc handles between processes, peer access inside one process), then raises a
+// per-(parity, sender) flag there; the consumer kernel of each rank waits on its own flags and merges.  No NCCL, no host
+// round trip between the local kernels, the exchange and the merge.
+//   inbox layout (device memory of the owning rank):
+//     [2 parities][world][slot_bytes] payload | u32 flags[2][kMaxWorld] | u32 push_counter | u32 status
+//   flags[p][r] = sequence number of the last collective whose payload rank r finished writing into parity p.
+//   Two parities suffice: a rank can be at most one collective ahead of a peer, because its merge of collective e+1
+//   waits for the peer's push e+1, which the peer's stream orders behind its own merge of collective e.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxWorld = 16;
+constexpr size_t kCommSlotBytes = 512 * 1024;  // per sender and parity: 65535 keypoints x 8 B, or 32768 queries x 2 keys
+
+struct CommView {
+    uint8_t *base[kMaxWorld];  // inbox of every rank as mapped here; base[rank] is local memory
+    int rank, world;
+    uint32_t epoch;            // sequence number of this collective (>= 1), the same on every rank
+};
+__device__ __forceinline__ uint8_t *comm_slot(const CommView &C, int owner, int from) {
+    return C.base[owner] + ((size_t)(C.epoch & 1) * C.world + from) * kCommSlotBytes;
+}
+__device__ __forceinline__ uint32_t *comm_flags(const CommView &C, int owner) {
+    return (uint32_t *)(C.base[owner] + 2 * (size_t)C.world * kCommSlotBytes) + (C.epoch & 1) * kMaxWorld;
+}
+__device__ __forceinline__ uint32_t *comm_counter(const CommView &C) { return (uint32_t *)(C.base[C.rank] + 2 * (size_t)C.world * kCommSlotBytes) + 2 * kMaxWorld; }
+__device__ __forceinline__ uint32_t *comm_status(const CommView &C) { return comm_counter(C) + 1; }
+
+// end of a pushing kernel: the last CTA to get here publishes the flags.  Every CTA fences its remote stores first.
+__device__ __forceinline__ void comm_publish(const CommView &C) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned ticket = atomicAdd(comm_counter(C), 1u);
+        if (ticket == total - 1) {
+            *comm_counter(C) = 0;
+            __threadfence_system();
+            for (int p = 0; p < C.world; p++) {
+                uint32_t *f = comm_flags(C, p) + C.rank;
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(C.epoch) : "memory");
+            }
+        }
+    }
+}
+// start of a consuming kernel: wait until every rank's payload of this collective has landed in the local inbox.
+// Bounded: a peer that never arrives sets the status word instead of hanging the GPU.
+__device__ __forceinline__ void comm_wait_all(const CommView &C) {
+    if (threadIdx.x < C.world) {
+        const uint32_t *f = comm_flags(C, C.rank) + threadIdx.x;
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v == C.epoch) break;
+            __nanosleep(200);
+            unsigned long long t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 5000000000ull) {  // 5 s
+                atomicExch(comm_status(C), 1u + threadIdx.x);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// n16 16-byte units of the local slot (already holding this rank's payload) -> every peer's slot for this rank
+__global__ void __launch_bounds__(256) comm_push_kernel(CommView C, int n16) {
+    const ulonglong2 *src = (const ulonglong2 *)comm_slot(C, C.rank, C.rank);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) {
+        const ulonglong2 v = src[i];
+        for (int p = 0; p < C.world; p++)
+            if (p != C.rank) ((ulonglong2 *)comm_slot(C, p, C.rank))[i] = v;
+    }
+    comm_publish(C);
+}
+
+// kNN: merge of this rank's chunk partials (as knn2_merge_kernel), the query's two keys stored into every rank's inbox by
+// lanes 0 .. world-1 of the warp that owns the query -- the push is the merge kernel's epilogue
+__global__ void __launch_bounds__(128) knn2_merge_push_kernel(CommView C, const unsigned long long *__restrict__ part, int parts, int q) {
+    const int qi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (qi < q) {
+        unsigned long long k0 = ~0ull, k1 = ~0ull;
+        for (int p = lane; p < parts; p += 32) {
+            const ulonglong2 k = __ldg((const ulonglong2 *)(part + ((size_t)p * q + qi) * 2));
+            k1 = min(k1, max(k0, k.x));
+            k0 = min(k0, k.x);
+            k1 = min(k1, max(k0, k.y));
+            k0 = min(k0, k.y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0, o), o1 = __shfl_xor_sync(0xffffffffu, k1, o);
+            k1 = min(min(k1, o1), max(k0, o0));
+            k0 = min(k0, o0);
+        }
+        if (lane < C.world) ((ulonglong2 *)comm_slot(C, lane, C.rank))[qi] = make_ulonglong2(k0, k1);
+    }
+    comm_publish(C);
+}
+
+// kNN: wait for every shard's keys, then lexicographic top-2 of the 2 * world candidates per query, decoded
+__global__ void __launch_bounds__(128) knn2_gather_merge_kernel(CommView C, int q, int32_t *__restrict__ quad_out) {
+    comm_wait_all(C);
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= q) return;
+    unsigned long long k0 = ~0ull, k1 = ~0ull;
+    for (int r = 0; r < C.world; r++) {
+        const ulonglong2 k = ((const ulonglong2 *)comm_slot(C, C.rank, r))[qi];
+        k1 = min(k1, max(k0, k.x));
+        k0 = min(k0, k.x);
+        k1 = min(k1, max(k0, k.y));
+        k0 = min(k0, k.y);
+    }
+    quad_out[4 * qi + 0] = k0 == ~0ull ? -1 : (int32_t)(k0 & 0xFFFFFFFFu);
+    quad_out[4 * qi + 1] = k0 == ~0ull ? 999999999 : (int32_t)(k0 >> 32);
+    quad_out[4 * qi + 2] = k1 == ~0ull ? -1 : (int32_t)(k1 & 0xFFFFFFFFu);
+    quad_out[4 * qi + 3] = k1 == ~0ull ? 999999999 : (int32_t)(k1 >> 32);
+}
+
+// ProjectionMatch: wait for every shard's per-keypoint keys, minimum = "smaller distance, later query wins" (:197-204)
+__global__ void __launch_bounds__(256) projection_gather_decode_kernel(CommView C, int m, int32_t *__restrict__ to_query,
+                                                                       int32_t *__restrict__ dist) {
+    comm_wait_all(C);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    unsigned long long k = ~0ull;
+    for (int r = 0; r < C.world; r++) k = min(k, ((const unsigned long long *)comm_slot(C, C.rank, r))[j]);
+    const bool none = k == ~0ull;
+    to_query[j] = none ? -1 : (int32_t)(0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFu));
+    if (dist) dist[j] = none ? -1 : (int32_t)(k >> 32);
+}
+
 }  // namespace sfe
 
 using namespace sfe;
@@ -1148,7 +1284,7 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
 }
 
 static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, int q, unsigned long long *keys_dev,
-                       int32_t *quad_dev) {
+                       int32_t *quad_dev, const CommView *push = nullptr) {
     cudaStream_t st = m->stream;
     const bool by_rows = q <= kRowsQMax;  // thread = row (streaming) for few queries, thread = query otherwise
     const int qgroups = by_rows ? 1 : div_up(q, kKnnThreads);
@@ -1170,7 +1306,10 @@ static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, i
         knn2_partial_kernel<<<dim3(chunks, qgroups), kKnnThreads, 0, st>>>(db->rows_dev, db->rows, db->idx_base, (int)chunk_rows,
                                                                           q_dev, q, m->d_part.p);
     }
-    knn2_merge_kernel<<<div_up(q, 4), 128, 0, st>>>(m->d_part.p, chunks, q, keys_dev, quad_dev);
+    if (push)  // sharded: the merged keys go straight into every rank's inbox
+        knn2_merge_push_kernel<<<div_up(q, 4), 128, 0, st>>>(*push, m->d_part.p, chunks, q);
+    else
+        knn2_merge_kernel<<<div_up(q, 4), 128, 0, st>>>(m->d_part.p, chunks, q, keys_dev, quad_dev);
     m->launches += 2;
     SFE_CUDA(cudaGetLastError());
     return SFE_OK;
@@ -1818,6 +1957,203 @@ int sfe_knn2(sfe_matcher *m, const sfe_db *db, const uint8_t *queries, int q, in
     if (rc != SFE_OK) return rc;
     SFE_CUDA(cudaMemcpyAsync(out, m->d_quad.p, sizeof(int32_t) * 4 * q, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaStreamSynchronize(st));
+    return SFE_OK;
+}
+
+
+// ---- multi-GPU exchange: handles and collectives ---------------------------------------------------------
+struct sfe_comm {
+    int device = 0, rank = 0, world = 1;
+    uint8_t *inbox = nullptr;             // local inbox (cudaMalloc)
+    size_t inbox_bytes = 0;
+    uint8_t *base[kMaxWorld] = {};        // every rank's inbox as mapped in this process
+    bool ipc_mapped[kMaxWorld] = {};
+    bool connected = false;
+    uint32_t epoch = 0;
+};
+
+static size_t comm_inbox_bytes(int world) { return 2 * (size_t)world * kCommSlotBytes + sizeof(uint32_t) * (2 * kMaxWorld + 2); }
+
+static int comm_alloc(int device, int rank, int world, sfe_comm **out) {
+    DeviceGuard g(device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the device");
+    sfe_comm *c = new sfe_comm();
+    c->device = device; c->rank = rank; c->world = world;
+    c->inbox_bytes = comm_inbox_bytes(world);
+    cudaError_t e = cudaMalloc((void **)&c->inbox, c->inbox_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->inbox, 0, c->inbox_bytes);
+    if (e != cudaSuccess) {
+        set_error("sfe_comm: inbox allocation: %s", cudaGetErrorString(e));
+        if (c->inbox) cudaFree(c->inbox);
+        delete c;
+        return SFE_ERR_CUDA;
+    }
+    c->base[rank] = c->inbox;
+    c->connected = world == 1;
+    *out = c;
+    return SFE_OK;
+}
+
+static CommView comm_view(sfe_comm *c) {
+    CommView V{};
+    for (int r = 0; r < c->world; r++) V.base[r] = c->base[r];
+    V.rank = c->rank; V.world = c->world; V.epoch = c->epoch;
+    return V;
+}
+
+int sfe_comm_create(int device, int rank, int world, sfe_comm **out) {
+    SFE_REQUIRE(out && world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, SFE_ERR_BAD_ARG, "bad rank / world (world <= 16)");
+    int ndev = 0;
+    SFE_CUDA(cudaGetDeviceCount(&ndev));
+    SFE_REQUIRE(device >= 0 && device < ndev, SFE_ERR_BAD_ARG, "device index out of range");
+    return comm_alloc(device, rank, world, out);
+}
+
+int sfe_comm_export(sfe_comm *c, uint8_t handle[SFE_COMM_HANDLE_BYTES]) {
+    SFE_REQUIRE(c && handle, SFE_ERR_BAD_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= SFE_COMM_HANDLE_BYTES, "IPC handle larger than the ABI's handle");
+    DeviceGuard g(c->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    cudaIpcMemHandle_t h;
+    SFE_CUDA(cudaIpcGetMemHandle(&h, c->inbox));
+    memset(handle, 0, SFE_COMM_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    return SFE_OK;
+}
+
+int sfe_comm_connect(sfe_comm *c, const uint8_t *handles) {
+    SFE_REQUIRE(c && (handles || c->world == 1), SFE_ERR_BAD_ARG, "null argument");
+    DeviceGuard g(c->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank || c->base[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * SFE_COMM_HANDLE_BYTES, sizeof(h));
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error("sfe_comm_connect: rank %d's inbox cannot be mapped (%s): the GPUs need peer access (NVLink / PCIe P2P)", r,
+                      cudaGetErrorString(e));
+            cudaGetLastError();
+            return SFE_ERR_CUDA;
+        }
+        c->base[r] = (uint8_t *)p;
+        c->ipc_mapped[r] = true;
+    }
+    c->connected = true;
+    return SFE_OK;
+}
+
+int sfe_comm_create_local(const int *devices, int n, sfe_comm **out) {
+    SFE_REQUIRE(devices && out && n >= 1 && n <= kMaxWorld, SFE_ERR_BAD_ARG, "bad argument (at most 16 devices)");
+    for (int i = 0; i < n; i++) out[i] = nullptr;
+    for (int i = 0; i < n; i++) {
+        int rc = comm_alloc(devices[i], i, n, &out[i]);
+        if (rc != SFE_OK) {
+            for (int j = 0; j < i; j++) { sfe_comm_destroy(out[j]); out[j] = nullptr; }
+            return rc;
+        }
+    }
+    for (int i = 0; i < n; i++) {
+        DeviceGuard g(devices[i]);
+        for (int j = 0; j < n; j++) {
+            if (devices[j] != devices[i]) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+                cudaError_t e = can ? cudaDeviceEnablePeerAccess(devices[j], 0) : cudaErrorPeerAccessUnsupported;
+                if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+                if (e != cudaSuccess) {
+                    set_error("sfe_comm_create_local: device %d cannot access device %d (%s)", devices[i], devices[j], cudaGetErrorString(e));
+                    for (int k = 0; k < n; k++) { sfe_comm_destroy(out[k]); out[k] = nullptr; }
+                    return SFE_ERR_UNSUPPORTED;
+                }
+            }
+            out[i]->base[j] = out[j]->inbox;
+        }
+        out[i]->connected = true;
+    }
+    return SFE_OK;
+}
+
+int sfe_comm_destroy(sfe_comm *c) {
+    if (!c) return SFE_OK;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < c->world; r++)
+        if (c->ipc_mapped[r]) cudaIpcCloseMemHandle(c->base[r]);
+    if (c->inbox) cudaFree(c->inbox);
+    delete c;
+    return SFE_OK;
+}
+
+int sfe_comm_status(sfe_comm *c, int *stalled_rank) {
+    SFE_REQUIRE(c, SFE_ERR_BAD_ARG, "null handle");
+    DeviceGuard g(c->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    uint32_t st = 0;
+    SFE_CUDA(cudaMemcpy(&st, c->inbox + 2 * (size_t)c->world * kCommSlotBytes + sizeof(uint32_t) * (2 * kMaxWorld + 1), sizeof(st),
+                        cudaMemcpyDeviceToHost));
+    if (stalled_rank) *stalled_rank = st ? (int)st - 1 : -1;
+    if (st) {
+        set_error("sfe_comm: rank %u never delivered its part of a collective (5 s); results of that call are invalid", st - 1);
+        return SFE_ERR_CUDA;
+    }
+    return SFE_OK;
+}
+
+static int comm_check(sfe_matcher *m, sfe_comm *c) {
+    SFE_REQUIRE(m && c, SFE_ERR_BAD_ARG, "null handle");
+    SFE_REQUIRE(c->connected, SFE_ERR_BAD_ARG, "sfe_comm is not connected (sfe_comm_connect)");
+    SFE_REQUIRE(c->device == m->device, SFE_ERR_BAD_ARG, "communicator and matcher live on different devices");
+    return SFE_OK;
+}
+
+int sfe_knn2_sharded(sfe_matcher *m, sfe_comm *c, const sfe_db *shard, const uint8_t *queries_dev, int q, int32_t *out_dev) {
+    int rc = comm_check(m, c);
+    if (rc != SFE_OK) return rc;
+    SFE_REQUIRE(shard && queries_dev && out_dev && q >= 1, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE((size_t)q * 16 <= kCommSlotBytes, SFE_ERR_UNSUPPORTED, "more than 32768 queries per sharded call");
+    SFE_REQUIRE(shard->device == m->device, SFE_ERR_BAD_ARG, "database shard lives on another device");
+    DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    c->epoch++;
+    const CommView V = comm_view(c);
+    if ((rc = knn_partial(m, shard, queries_dev, q, nullptr, nullptr, &V)) != SFE_OK) return rc;
+    knn2_gather_merge_kernel<<<div_up(q, 128), 128, 0, m->stream>>>(V, q, out_dev);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
+    return SFE_OK;
+}
+
+int sfe_projection_match_sharded(sfe_matcher *m, sfe_comm *c, const sfe_frame *f, const double *xw_dev, const uint8_t *mp_desc_dev,
+                                 const uint8_t *skip_dev, int n, int64_t idx_base, const sfe_se3 *Tcw, double radius,
+                                 double best12_threshold, int32_t *kp_to_query_dev, int32_t *kp_dist_dev) {
+    int rc = comm_check(m, c);
+    if (rc != SFE_OK) return rc;
+    SFE_REQUIRE(f && Tcw && kp_to_query_dev && n >= 0 && (n == 0 || (xw_dev && mp_desc_dev)), SFE_ERR_BAD_ARG, "bad argument");
+    SFE_REQUIRE(f->device == m->device, SFE_ERR_BAD_ARG, "frame lives on another device");
+    SFE_REQUIRE(f->n >= 1, SFE_ERR_BAD_ARG, "empty frame");
+    SFE_REQUIRE(idx_base >= 0 && idx_base + n < (1ll << 31), SFE_ERR_UNSUPPORTED, "global map-point index must fit int32");
+    DeviceGuard g(m->device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    c->epoch++;
+    const CommView V = comm_view(c);
+    // the shard's per-keypoint keys are built directly in this rank's own inbox slot, then pushed to the peers
+    unsigned long long *own = (unsigned long long *)(c->inbox + ((size_t)(c->epoch & 1) * c->world + c->rank) * kCommSlotBytes);
+    const int m16 = (f->n + 1) / 2;  // 16-byte units; the odd tail key is padding inside the slot
+    if ((rc = projection_impl(m, xw_dev, mp_desc_dev, skip_dev, n, pose_from_se3(Tcw), &f->cam, f->kps.p, f->desc.p, f->n, radius,
+                              best12_threshold, nullptr, nullptr, (uint32_t)idx_base, own, &f->grid)) != SFE_OK)
+        return rc;
+    if (c->world > 1) {
+        comm_push_kernel<<<std::min(div_up(m16, 256), 64), 256, 0, m->stream>>>(V, m16);
+        m->launches++;
+    }
+    if (c->world > 1)
+        projection_gather_decode_kernel<<<div_up(f->n, 256), 256, 0, m->stream>>>(V, f->n, kp_to_query_dev, kp_dist_dev);
+    else
+        projection_decode_kernel<<<div_up(f->n, 256), 256, 0, m->stream>>>(f->n, 1, own, kp_to_query_dev, kp_dist_dev);
+    m->launches++;
+    SFE_CUDA(cudaGetLastError());
     return SFE_OK;
 }
 

@@ -25,9 +25,14 @@ def main():
     queries, _ = synth.knn_queries(db, 300, seed=22)
     queries[0] = db[150_000]
     a, b = sharding.block(len(db), world, rank)
-    got = sharding.ShardedDatabase(m, db[a:b], len(db)).knn2(queries)
-    ref = oracle_c.knn2(queries, db)
-    assert np.array_equal(got, ref), f"rank {rank}: kNN differs on {(got != ref).any(axis=1).sum()} queries"
+    ref = oracle_c.knn2(queries, db, nthreads=4)
+    for exchange in ("peer", "collective"):   # the library's NVLink peer-memory step, and NCCL all-gather as the carrier
+        sdb = sharding.ShardedDatabase(m, db[a:b], len(db), exchange=exchange)
+        for rep in range(3):                  # consecutive collectives reuse the two inbox parities
+            got = sdb.knn2(queries[: 300 - 7 * rep])
+            assert np.array_equal(got, ref[: 300 - 7 * rep]), f"rank {rank} {exchange}: kNN differs on {(got != ref[: 300 - 7 * rep]).any(axis=1).sum()} queries"
+        if exchange == "peer":
+            sdb.comm.status()
     # ProjectionMatch over sharded map points
     ex = api.ORBextractor(device=local, max_images=2)
     L, _ = synth.stereo_pair(0)
@@ -37,9 +42,16 @@ def main():
     cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0] * 4, 1241, 376)
     ocam = oracle_c.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0] * 4, 1241, 376)
     a, b = sharding.block(len(xw), world, rank)
-    gq, gd = sharding.ShardedLocalMap(m, xw[a:b], mpd[a:b], len(xw)).projection_match(np.eye(3, 4), cam, kps, desc, 50.0)
-    rq, rd = oracle_c.projection_match(xw, mpd, None, np.eye(3, 4), ocam, kps, desc, 50.0)
-    assert np.array_equal(gq, rq) and np.array_equal(gd, rd), f"rank {rank}: sharded projection match differs"
+    qt = np.array([0.003, -0.004, 0.001, 0.0, 0.05, -0.02, 0.2])
+    qt[3] = np.sqrt(1 - (qt[:3] ** 2).sum())
+    for pose in (np.array([0, 0, 0, 1, 0, 0, 0.0]), qt):
+        rq, rd = oracle_c.projection_match(xw, mpd, None, pose, ocam, kps, desc, 50.0, grid=True)
+        for exchange in ("peer", "collective"):
+            lm = sharding.ShardedLocalMap(m, xw[a:b], mpd[a:b], len(xw), exchange=exchange)
+            for rep in range(2):
+                gq, gd = lm.projection_match(pose, cam, kps, desc, 50.0)
+                assert np.array_equal(gq, rq) and np.array_equal(gd, rd), f"rank {rank} {exchange}: sharded projection match differs"
+    assert (rq >= 0).sum() > 100
     # frame sharding: this rank's block of a batch, checked against the oracle
     seeds = list(range(world * 2 + 1))
     f0, f1 = sharding.block(len(seeds), world, rank)

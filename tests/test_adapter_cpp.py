@@ -92,3 +92,5 @@ def test_adapter_results_equal_oracle(tmp_path, oracle):
     assert int(got["bown"]) == len(lit) and int(got["bow"], 16) == hb and int(got["fv"], 16) == hf
     # every triangulated point re-projects onto its own keypoint; most are accepted by the ratio test
     assert int(got["proj"]) > 0.5 * (si >= 0).sum() and int(got["self"]) > 0.9 * int(got["proj"])
+    # sfe_comm_create_local + sfe_knn2_sharded + sfe_projection_match_sharded called from C++ on every visible GPU
+    assert int(got["sharded_gpus"]) >= 1 and got["sharded_knn"] == "ok" and got["sharded_proj"] == "ok"
