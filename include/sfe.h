@@ -103,6 +103,10 @@ const char *sfe_status_string(int status);
 const char *sfe_last_error(void); /* thread-local detail of the last failure */
 int sfe_device_count(int *count);
 int sfe_host_alloc(void **ptr, size_t bytes); /* pinned host memory for the host entry points */
+/* flags: SFE_HOST_WRITE_COMBINED = write-combined pages for buffers the host only WRITES (input images): the device reads
+ * them over PCIe without snooping the CPU caches; host reads of such memory are very slow */
+#define SFE_HOST_WRITE_COMBINED 1
+int sfe_host_alloc_ex(void **ptr, size_t bytes, int flags);
 int sfe_host_free(void *ptr);
 int sfe_device_alloc(int device, void **ptr, size_t bytes);
 int sfe_device_free(int device, void *ptr);

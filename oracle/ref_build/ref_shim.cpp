@@ -12,6 +12,7 @@
 #include <sys/mman.h>
 
 #include <atomic>
+#include <thread>
 #include <cstdio>
 #include <new>
 
@@ -289,6 +290,86 @@ void ref_projection_match(const double *xw, const uint8_t *mp_desc, const uint8_
     for (int j = 0; j < m; j++) kp_to_query[j] = -1;
     for (std::map<int, Mappoint *>::const_iterator it = matches.begin(); it != matches.end(); ++it)
         kp_to_query[it->first] = (int)(it->second - mps.data());
+}
+
+// ---- CPU baseline driver (bench.py --impl reference / cpu_baseline) -----------------------------------------------------
+// The reference's front end on `count` consecutive stereo frames, nthreads worker threads (the reference itself is one
+// serial tracking thread, src/pipeline.cpp:143-147; threads here only keep all host cores busy with independent frames):
+//   per frame      ORBextractor::extract(left), extract(right)  (src/frame.cpp:47,388), StereoMatch (src/pipeline.cpp:248)
+//   per frame >= 1 ProjectionMatch of the previous frame's stereo points with an identity motion prior, r = radius
+//                  (src/posetracker.cpp:186); the points come from StereoFrame::GetDepth, restated here from
+//                  src/frame.cpp:391-409 (its translation unit needs FLANN / DBoW2) on the real Camera::NormalizedUndistort.
+// glibc heap (as the reference runs).  Returns the number of stereo matches.
+struct SeqFrame {
+    StereoFrame f;
+    cv::Mat dl, dr;
+    std::vector<Eigen::Vector2d> nrm;
+};
+
+int64_t ref_stereo_sequence(const uint8_t *left, const uint8_t *right, int count, int w, int h, int nthreads, int nfeatures,
+                            float scale_factor, int nlevels, int ini_th, int min_th, const ref_camera *c, double baseline,
+                            double radius, int64_t *total_kps, int64_t *total_tracked) {
+    const int was = g_monotonic.exchange(0);
+    std::unique_ptr<Camera> cam(make_camera(c));
+    std::vector<SeqFrame> fr((size_t)count);
+    std::atomic<int> next(0);
+    std::atomic<int64_t> kps(0), stereo(0), tracked(0);
+    if (nthreads < 1) nthreads = 1;
+    auto phase1 = [&]() {
+        ORB_SLAM2::ORBextractor ex(nfeatures, scale_factor, nlevels, ini_th, min_th);
+        for (int i = next++; i < count; i = next++) {
+            SeqFrame &s = fr[(size_t)i];
+            s.f.camera_ = cam.get();
+            cv::Mat L(h, w, CV_8UC1, (void *)(left + (size_t)i * w * h)), R(h, w, CV_8UC1, (void *)(right + (size_t)i * w * h));
+            ex.extract(L, cv::noArray(), s.f.keypoints_, s.dl);
+            ex.extract(R, cv::noArray(), s.f.r_keypoints_, s.dr);
+            s.f.descriptions_ = s.dl;
+            s.f.r_descriptions_ = s.dr;
+            s.f.mappoints_.assign(s.f.keypoints_.size(), nullptr);
+            for (size_t k = 0; k < s.f.keypoints_.size(); k++) {  // src/frame.cpp:52-56
+                const Eigen::Vector3d nuv = cam->NormalizedUndistort(Eigen::Vector2d(s.f.keypoints_[k].pt.x, s.f.keypoints_[k].pt.y));
+                s.nrm.push_back(nuv.head<2>());
+            }
+            StereoMatch(&s.f);
+            kps += (int64_t)(s.f.keypoints_.size() + s.f.r_keypoints_.size());
+            for (size_t k = 0; k < s.f.stereo_correspond_.size(); k++) stereo += s.f.stereo_correspond_[k] >= 0;
+        }
+    };
+    auto phase2 = [&]() {
+        const g2o::SE3Quat Tcw(Eigen::Quaterniond(1, 0, 0, 0), Eigen::Vector3d(0, 0, 0));
+        for (int i = next++; i < count; i = next++) {
+            if (i == 0) continue;
+            const SeqFrame &p = fr[(size_t)i - 1];
+            std::vector<Mappoint> mps;
+            mps.reserve(p.f.keypoints_.size());
+            for (size_t k = 0; k < p.f.keypoints_.size(); k++) {  // StereoFrame::GetDepth, src/frame.cpp:391-409
+                const int j = p.f.stereo_correspond_[k];
+                if (j < 0) continue;
+                const double dx = p.f.keypoints_[k].pt.x - p.f.r_keypoints_[(size_t)j].pt.x;
+                if (dx < 0.) continue;
+                const double depth = c->fx * baseline / dx;
+                Mappoint mp;
+                const Eigen::Vector2d xy = p.nrm[k] * depth;
+                mp.xw_ = Eigen::Vector3d(xy[0], xy[1], depth);
+                mp.desc_ = p.dl.row((int)k);
+                mps.push_back(mp);
+            }
+            std::set<Mappoint *> all;
+            for (size_t k = 0; k < mps.size(); k++) all.insert(&mps[k]);
+            tracked += (int64_t)ProjectionMatch(all, Tcw, &fr[(size_t)i].f, radius).size();
+        }
+    };
+    for (int ph = 0; ph < 2; ph++) {
+        next = 0;
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; t++) th.push_back(ph == 0 ? std::thread(phase1) : std::thread(phase2));
+        if (ph == 0) phase1(); else phase2();
+        for (size_t t = 0; t < th.size(); t++) th[t].join();
+    }
+    if (total_kps) *total_kps = kps.load();
+    if (total_tracked) *total_tracked = tracked.load();
+    g_monotonic = was;
+    return stereo.load();
 }
 
 }  // extern "C"

@@ -77,6 +77,8 @@ def lib():
         L.ref_se3_apply.argtypes = [vp, vp, ci, vp, vp]
         L.ref_stereo_match.argtypes = [vp, vp, ci, vp, vp, ci, vp, vp]
         L.ref_projection_match.argtypes = [vp, vp, vp, ci, vp, vp, vp, vp, ci, cd, vp]
+        L.ref_stereo_sequence.restype = C.c_int64
+        L.ref_stereo_sequence.argtypes = [vp, vp, ci, ci, ci, ci, ci, cf, ci, ci, ci, vp, cd, cd, vp, vp]
         L.ref_set_heap_mode.argtypes = [ci]
         L.ref_arena_allocations.restype = C.c_long
         _lib = L
@@ -207,3 +209,16 @@ def projection_match(xw, mp_desc, skip, qt, cam, kps, kp_desc, radius):
     lib().ref_projection_match(_p(xw), _p(mp_desc), _p(skip), len(xw), _p(qt), C.byref(cam), _p(kps), _p(kp_desc), len(kps),
                                C.c_double(radius), _p(to_q))
     return to_q
+
+
+def stereo_sequence(left, right, nthreads, cam, baseline, radius=50.0, nfeatures=2000, scale_factor=1.2, nlevels=8, ini_th=20,
+                    min_th=7):
+    """CPU baseline of the sequence workload on the reference's own code (ref_stereo_sequence) ->
+    (stereo matches, keypoints, tracked keypoints).  glibc heap, as the reference runs."""
+    left = np.ascontiguousarray(left, np.uint8)
+    right = np.ascontiguousarray(right, np.uint8)
+    count, h, w = left.shape
+    tot, trk = C.c_int64(), C.c_int64()
+    m = lib().ref_stereo_sequence(_p(left), _p(right), count, w, h, nthreads, nfeatures, scale_factor, nlevels, ini_th, min_th,
+                                  C.byref(cam), baseline, radius, C.byref(tot), C.byref(trk))
+    return int(m), int(tot.value), int(trk.value)

@@ -97,6 +97,7 @@ SIGNATURES = {
     "sfe_last_error": (C.c_char_p, []),
     "sfe_device_count": (_i, [C.POINTER(_i)]),
     "sfe_host_alloc": (_i, [_pp, _sz]),
+    "sfe_host_alloc_ex": (_i, [_pp, _sz, _i]),
     "sfe_host_free": (_i, [_vp]),
     "sfe_device_alloc": (_i, [_i, _pp, _sz]),
     "sfe_device_free": (_i, [_i, _vp]),
@@ -230,12 +231,12 @@ def hamming256(a, b) -> int:
 class PinnedArray:
     """numpy view of pinned host memory (cudaHostAlloc) for the host entry points."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, write_combined=False):
         self.dtype = np.dtype(dtype)
         self.shape = tuple(int(s) for s in np.atleast_1d(shape))
         self.nbytes = max(int(np.prod(self.shape)) * self.dtype.itemsize, 1)
         ptr = C.c_void_p()
-        _check(lib().sfe_host_alloc(C.byref(ptr), self.nbytes))
+        _check(lib().sfe_host_alloc_ex(C.byref(ptr), self.nbytes, 1 if write_combined else 0))
         self.ptr = ptr.value
         buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)

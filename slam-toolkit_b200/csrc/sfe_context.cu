@@ -110,6 +110,12 @@ int sfe_host_alloc(void **ptr, size_t bytes) {
     return SFE_OK;
 }
 
+int sfe_host_alloc_ex(void **ptr, size_t bytes, int flags) {
+    SFE_REQUIRE(ptr && bytes > 0, SFE_ERR_BAD_ARG, "bad argument");
+    SFE_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | ((flags & SFE_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0)));
+    return SFE_OK;
+}
+
 int sfe_host_free(void *ptr) {
     if (ptr) SFE_CUDA(cudaFreeHost(ptr));
     return SFE_OK;
