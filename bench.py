@@ -14,8 +14,9 @@ previous frame's stereo-triangulated keypoints into the frame (StereoFrame::GetD
           host keypoints/descriptors/stereo indices/track indices out, copies inside the timed region.
   roofline     : the dominant kernel's algorithmic bytes / its CUDA-event time, vs the measured HBM peak.
   cpu_baseline : the CPU oracle (port of the reference) on a bounded sample, host cores stated.
---impl reference times that CPU oracle alone (the reference itself cannot be built here:
-OpenCV 3.4 C++/Eigen/g2o/FLANN are absent), all host threads, same metric/config.
+--impl reference times the reference's own CPU code alone (oracle/_ref: src/orb_extractor.cpp, matcher.cpp, camera.cpp
+compiled unmodified against stand-in third-party headers; the C port when that prebuilt library is absent), all host
+threads, same metric/config.
 Frames are sharded across GPUs with no data-path collective (weak scaling: F frames per GPU).
 """
 import argparse
@@ -165,101 +166,141 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm), "source": self.source}
 
 
-def cpu_sample(frames, threads):
+def cpu_impl():
+    """("reference", module) when oracle/_ref/libslamref.so -- the reference's own src/orb_extractor.cpp + src/matcher.cpp +
+    src/camera.cpp compiled unmodified, prebuilt in the authoring container -- is present, else ("port", the C oracle)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c
     oracle_c.build()
+    try:
+        import ref_c
+        if ref_c.available():
+            ref_c.lib()
+            return "reference", ref_c, oracle_c
+    except Exception:
+        pass
+    return "port", oracle_c, oracle_c
+
+
+def cpu_sample(frames, threads, impl=None):
+    kind, mod, oracle_c = impl or cpu_impl()
     from slam_toolkit_b200 import synth
     L, R = make_frames(frames)
     cam = oracle_c.make_camera(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, [0, 0, 0, 0], W, H)
     t0 = time.perf_counter()
-    matches, kps, tracked = oracle_c.stereo_sequence(L, R, threads, cam, synth.KITTI_BASELINE, 50.0)
+    matches, kps, tracked = mod.stereo_sequence(L, R, threads, cam, synth.KITTI_BASELINE, 50.0)
     dt = time.perf_counter() - t0
     return frames / dt, dt, matches + tracked, kps
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the CPU restatement of the reference path (oracle/orb_oracle.c; the reference itself cannot be
-    built here), all host threads, one frame per thread, rank 0 only.  One step = a bounded sample of the workload:
-    its size is chosen from a warm-up measurement so that the K steps take about a minute."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref: its sources compiled unmodified
+    against stand-in third-party headers; the C oracle port when that library is absent), all host threads, one frame per
+    thread, rank 0 only.  One step = a bounded sample of the workload: its size is chosen from a warm-up measurement so that
+    the K steps take about a minute."""
     if rank != 0:
         return
+    impl = cpu_impl()
     cores = os.cpu_count() or 1
-    est_fps, _, _, _ = cpu_sample(max(cores, 4), cores)          # also the warm-up (builds + pages in the oracle)
+    est_fps, _, _, _ = cpu_sample(max(cores, 4), cores, impl)          # also the warm-up (pages in the library)
     for _ in range(max(min(args.warmup, 2) - 1, 0)):
-        est_fps, _, _, _ = cpu_sample(max(cores, 4), cores)
+        est_fps, _, _, _ = cpu_sample(max(cores, 4), cores, impl)
     frames = args.cpu_frames or int(min(max(60.0 * est_fps / max(args.steps, 1), cores), 4 * cores))
     times = []
     tot_matches = 0
     for _ in range(args.steps):
-        fps, dt, matches, _ = cpu_sample(frames, cores)
+        fps, dt, matches, _ = cpu_sample(frames, cores, impl)
         times.append(dt)
         tot_matches += matches
     total = sum(times)
     value = frames * args.steps / total
+    what = ("the reference's own orb_extractor.cpp / matcher.cpp / camera.cpp (oracle/_ref, -O1)" if impl[0] == "reference"
+            else "C port of the reference path (oracle/orb_oracle.c)")
     line = {"impl": "reference", "metric": "orb_extract_match_stereo_frames_per_s", "value": value, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{frames} synthetic stereo frames per step, {args.steps} steps, one frame per thread"},
+            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": args.frames, "cpu_sample_frames_per_step": frames},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": impl[0],
+                             "sample": f"{frames} synthetic stereo frames per step, {args.steps} steps, one frame per thread; {what}"},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "matches_per_s": tot_matches / total, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+def _max_over_ranks(dist, dev, values):
+    if dist is None:
+        return list(values)
+    import torch
+    t = torch.tensor(list(values), dtype=torch.float64, device=f"cuda:{dev}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def _event_ms(api, m, dev, fn, reps, barrier):
+    """reps calls of fn queued back to back on the matcher's stream, timed with CUDA events on that stream"""
+    fn()
+    m.wait()
+    e0, e1 = api.Event(dev), api.Event(dev)
+    barrier()
+    e0.record(m)
+    for _ in range(reps):
+        fn()
+    e1.record(m)
+    m.wait()
+    return e0.elapsed_ms(e1) / reps
+
+
 def hamming_leg(args, dev, rank, world, dist):
-    """BASELINE config 4 beside the headline: brute-force Hamming top-2 of Q queries against a 10 M-row descriptor map
-    sharded by rows over the ranks (all-gather of the per-rank top-2 keys + merge kernel).  Q = 2000 is `popc`-bound
-    (8 popc per pair), Q = 1 streams the map once: that one is the GB/s-vs-HBM figure."""
+    """BASELINE config 4 beside the headline, as SURVEY §8d states it: brute-force Hamming top-2 of Q queries against the
+    10 M-row map `default_rng(1234)`, queries = map rows picked by `default_rng(5678)` with bit flips (a fifth of them
+    hard enough to fail the ratio test).  Rows are sharded over the ranks; the exchange is the library's own step
+    (sfe_knn2_sharded: every rank's merge kernel stores its top-2 keys into every peer's inbox over NVLink peer memory,
+    the final merge waits on flags) -- resident queries, no host round trip, timed with CUDA events on the matcher's stream,
+    max over ranks.  Q = 2000 is `popc`-bound; Q in {1, 2, 4} stream the map once: those are the
+    GB/s-vs-HBM figures.  At world > 1 rank 0 also runs the UNSHARDED query on its own GPU and compares every value."""
     from slam_toolkit_b200 import api, sharding, synth
     rows = args.knn_rows
     a, b = sharding.block(rows, world, rank)
-    rng = np.random.default_rng(1234 + rank)
-    local = rng.integers(0, 256, (b - a, 32), dtype=np.uint8)
+    db = synth.knn_database(rows, seed=1234)                       # the same on every rank; each keeps its block resident
+    queries, _ = synth.knn_queries(db, 2000, seed=5678, hard_fraction=0.2)
     m = api.Matcher(dev)
-    sd = sharding.ShardedDatabase(m, local, rows)
-    queries, _ = synth.knn_queries(local[:100_000], 2000, seed=5678)   # the same on every rank only at world == 1: fine for timing
-    if dist is not None:
-        import torch
-        qt = torch.from_numpy(queries).cuda(dev)
-        dist.broadcast(qt, 0)
-        queries = qt.cpu().numpy()
-    sd.knn2(queries)
-    reps = 5
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        out = sd.knn2(queries)
-    dt = (time.perf_counter() - t0) / reps
-    # streaming pass: one query, resident, kernel time by CUDA events on the matcher's stream
-    dq, keys = api.DeviceBuffer(32, dev).upload(queries[:1]), api.DeviceBuffer(16, dev)
-    m.knn2_dev(sd.db, dq.ptr, 1, keys.ptr)
-    e0, e1 = api.Event(dev), api.Event(dev)
-    m.set_async(True)
-    e0.record(m)
-    for _ in range(50):
-        m.knn2_dev(sd.db, dq.ptr, 1, keys.ptr)
-    e1.record(m)
+    sd = sharding.ShardedDatabase(m, db[a:b], rows)
+    d_q = api.DeviceBuffer(queries.nbytes, dev).upload(queries)
+    d_o = api.DeviceBuffer(2000 * 16, dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+    out_ms = {}
+    for nq, reps in ((2000, 5), (1, 50), (2, 50), (4, 50)):
+        out_ms[nq] = _event_ms(api, m, dev, lambda: sd.knn2_dev(d_q.ptr, nq, d_o.ptr), reps, barrier)
+    sd.knn2_dev(d_q.ptr, 2000, d_o.ptr)
     m.wait()
-    m.set_async(False)
-    ms1 = e0.elapsed_ms(e1) / 50
-    if dist is not None:
-        import torch
-        t = torch.tensor([dt, ms1], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt, ms1 = t.tolist()
-    gbs1 = world * (b - a) * 32 / (ms1 / 1e3) / 1e9
-    return {"map_rows": rows, "sharding": f"{world} row shard(s), all-gather of 2 keys per query + merge",
-            "q2000_ms_per_batch": dt * 1e3, "q2000_pair_distances_per_s": 2000 * rows / dt,
-            "q2000_algorithmic_gbs": (32 * rows + 48 * 2000) / dt / 1e9,
-            "q1_stream_ms": ms1, "q1_stream_gbs": gbs1, "accepted_ratio_test": float((2 * out[:, 1] < out[:, 3]).mean())}
+    out = d_o.download((2000, 4), np.int32)
+    sd.comm.status()
+    equal = None
+    if world > 1 and rank == 0:                                   # the unsharded map fits one GPU (320 MB)
+        whole = m.create_db(db)
+        equal = bool(np.array_equal(m.knn2(whole, queries), out))
+        del whole
+    ms = _max_over_ranks(dist, dev, [out_ms[2000], out_ms[1], out_ms[2], out_ms[4]])
+    res = {"map_rows": rows, "map": "default_rng(1234), queries default_rng(5678) rows + flips (SURVEY §8d config 4)",
+           "sharding": f"{world} row shard(s); exchange = peer-memory stores + flags inside the merge kernels (sfe_knn2_sharded)",
+           "q2000_ms_per_batch": ms[0], "q2000_pair_distances_per_s": 2000 * rows / (ms[0] / 1e3),
+           "q2000_algorithmic_gbs": (32 * rows + 48 * 2000) / (ms[0] / 1e3) / 1e9,
+           "accepted_ratio_test": float((2 * out[:, 1] < out[:, 3]).mean())}
+    for i, nq in ((1, 1), (2, 2), (3, 4)):
+        res[f"q{nq}_stream_ms"] = ms[i]
+        res[f"q{nq}_stream_gbs"] = (32 * rows + 48 * nq) / (ms[i] / 1e3) / 1e9
+    if world > 1:
+        res["sharded_equals_unsharded"] = equal
+    return res
 
 
 def projection_leg(args, dev, rank, world, dist, kps, desc):
-    """BASELINE config 5 beside the headline: ProjectionMatch (r = 50 px, identity pose) of a local map of N points
-    against one frame's keypoints; map points sharded over the ranks (all-gather of the per-keypoint keys + merge).
+    """BASELINE config 5 beside the headline: ProjectionMatch (r = 50 px, identity pose as an SE3Quat) of a local map of N
+    points against one resident frame; map points sharded over the ranks, exchange inside the library
+    (sfe_projection_match_sharded).  Timed with CUDA events on the matcher's stream, max over ranks.
     Algorithmic bytes per call: N * (24 + 32) + M * (8 + 32) + 8 * M."""
     from slam_toolkit_b200 import api, sharding, synth
     n, m_kps = args.proj_points, len(kps)
@@ -268,44 +309,32 @@ def projection_leg(args, dev, rank, world, dist, kps, desc):
     a, b = sharding.block(n, world, rank)
     cam = api.Camera.make(synth.KITTI_FX, synth.KITTI_FY, synth.KITTI_CX, synth.KITTI_CY, (0, 0, 0, 0), W, H)
     m = api.Matcher(dev)
-    d_xw = api.DeviceBuffer((b - a) * 24, dev).upload(np.ascontiguousarray(xw[a:b]))
-    d_mpd = api.DeviceBuffer((b - a) * 32, dev).upload(np.ascontiguousarray(mpd[a:b]))
-    d_kps = api.DeviceBuffer(m_kps * 28, dev).upload(np.ascontiguousarray(kps))
-    d_kd = api.DeviceBuffer(m_kps * 32, dev).upload(np.ascontiguousarray(desc))
+    frame = api.Frame(m, kps, desc, cam)
+    lm = sharding.ShardedLocalMap(m, xw[a:b], mpd[a:b], n)
     d_q, d_d = api.DeviceBuffer(m_kps * 4, dev), api.DeviceBuffer(m_kps * 4, dev)
-    Tcw = np.eye(4)
+    Tcw = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
 
-    def call():
-        m.projection_match_dev(d_xw.ptr, d_mpd.ptr, None, b - a, Tcw, cam, d_kps.ptr, d_kd.ptr, m_kps, 50.0, d_q.ptr, d_d.ptr)
-    call()
-    e0, e1 = api.Event(dev), api.Event(dev)
-    reps = 20
-    m.set_async(True)
-    e0.record(m)
-    for _ in range(reps):
-        call()
-    e1.record(m)
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+    ms = _event_ms(api, m, dev, lambda: lm.projection_match_dev(frame, Tcw, 50.0, d_q.ptr, d_d.ptr), 20, barrier)
+    lm.projection_match_dev(frame, Tcw, 50.0, d_q.ptr, d_d.ptr)
     m.wait()
-    m.set_async(False)
-    ms = e0.elapsed_ms(e1) / reps
-    matched = int((d_q.download((m_kps,), np.int32) >= 0).sum())
-    sharded_ms = None
-    if dist is not None:
-        import torch
-        lm = sharding.ShardedLocalMap(m, xw[a:b], mpd[a:b], n)
-        lm.projection_match(Tcw, cam, kps, desc, 50.0)
-        dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(5):
-            lm.projection_match(Tcw, cam, kps, desc, 50.0)
-        t = torch.tensor([ms, (time.perf_counter() - t0) / 5 * 1e3], dtype=torch.float64, device=f"cuda:{dev}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, sharded_ms = t.tolist()
+    got_q, got_d = d_q.download((m_kps,), np.int32), d_d.download((m_kps,), np.int32)
+    lm.comm.status()
+    equal, single_ms = None, None
+    if world > 1 and rank == 0:
+        want_q, want_d = frame.ProjectionMatch(xw, mpd, None, Tcw, 50.0)
+        equal = bool(np.array_equal(want_q, got_q) and np.array_equal(want_d, got_d))
+    ms, = _max_over_ranks(dist, dev, [ms])
     alg = n * 56 + m_kps * 48
-    return {"map_points": n, "frame_keypoints": m_kps, "radius_px": 50.0, "ms_per_call_shard_kernels": ms,
-            "map_points_per_s": n / (ms / 1e3), "algorithmic_gbs": alg / (ms / 1e3) / 1e9,
-            "keypoints_matched_this_shard": matched, "sharded_call_ms_with_allgather": sharded_ms,
-            "sharding": f"{world} map-point shard(s)"}
+    res = {"map_points": n, "frame_keypoints": m_kps, "radius_px": 50.0, "ms_per_call": ms,
+           "map_points_per_s": n / (ms / 1e3), "algorithmic_gbs": alg / (ms / 1e3) / 1e9,
+           "keypoints_matched": int((got_q >= 0).sum()),
+           "sharding": f"{world} map-point shard(s); exchange = peer-memory stores + flags (sfe_projection_match_sharded)"}
+    if world > 1:
+        res["sharded_equals_unsharded"] = equal
+    return res
 
 
 def main():
@@ -409,47 +438,60 @@ def main():
     n_match = n_stereo + n_track
     n_kps = int(d_out["n_l"].download((F,), np.int32).sum() + d_out["n_r"].download((F,), np.int32).sum())
 
-    # ---- e2e: pinned host images -> host results through the public host entry point (sfe_stereo_frames), synchronous
-    # calls.  T host threads, one extractor handle each (handles are per-thread objects, include/sfe.h), take the K
-    # steps in turn, so one call's pipeline fill / drain overlaps the other's steady state; T = 1 is reported beside it.
+    # ---- e2e: pinned host images -> host results through the public host entry point (sfe_stereo_sequence), synchronous
+    # calls.  T host threads, one extractor handle each (handles are per-thread objects, include/sfe.h), issue calls back to
+    # back, so one call's pipeline fill / drain overlaps the other's steady state; T = 1 is reported beside it.  The
+    # threads are started and parked on a barrier BEFORE the clock; the region runs a call count sized for >= 2.5 s.
     T = max(1, args.e2e_threads)
+    wc = os.environ.get("SFE_BENCH_WC", "0") == "1"   # write-combined input pages (tools/copy_probe.py measures both)
     handles = [ex] + [api.ORBextractor(2000, 1.2, 8, 20, 7, device=dev, max_images=2 * F) for _ in range(T - 1)]
     pins = []
     for h in handles:
-        pl, pr = api.PinnedArray((F, H, W), np.uint8), api.PinnedArray((F, H, W), np.uint8)
+        pl, pr = api.PinnedArray((F, H, W), np.uint8, write_combined=wc), api.PinnedArray((F, H, W), np.uint8, write_combined=wc)
         pl.array[:], pr.array[:] = L, R
         pins.append((pl, pr, h.alloc_stereo_out(F, pinned=True, track=True)))
     out = pins[0][2]
 
-    def e2e_steps(t, count):
-        pl, pr, o = pins[t]
-        for _ in range(count):
-            handles[t].stereo_sequence(pl.array, pr.array, tp, o)
+    def timed(nthreads, calls_each):
+        gate = threading.Barrier(nthreads + 1)
+        done = threading.Barrier(nthreads + 1)
 
-    def timed(nthreads):
-        shares = [K // nthreads + (1 if t < K % nthreads else 0) for t in range(nthreads)]
-        ths = [threading.Thread(target=e2e_steps, args=(t, shares[t])) for t in range(nthreads)]
-        t0 = time.perf_counter()
+        def work(t):
+            pl, pr, o = pins[t]
+            gate.wait()
+            for _ in range(calls_each):
+                handles[t].stereo_sequence(pl.array, pr.array, tp, o)
+            done.wait()
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(nthreads)]
         for th in ths:
             th.start()
+        barrier()                       # every rank's threads are parked
+        gate.wait()
+        t0 = time.perf_counter()
+        done.wait()
+        dt = time.perf_counter() - t0
         for th in ths:
             th.join()
-        return time.perf_counter() - t0
+        return dt
 
-    for t in range(T):
-        e2e_steps(t, Wm)
-    barrier()
+    est = timed(T, max(Wm // T, 2)) / max(Wm // T, 2)          # warm-up + seconds per call per thread
+    est, = _max_over_ranks(dist, dev, [est])
+    calls_each = int(min(max(np.ceil(2.5 / max(est, 1e-4)), 4), 2000))
     # (periodic NVML polling during this region stalls the CUDA calls of the OTHER ranks inside the driver -- measured
     # 73 k -> 26 k frames/s at 2 GPUs -- so the clocks are sampled immediately before and after it instead)
     sampler.sample_once()
-    e2e_s = timed(T)
+    e2e_s = timed(T, calls_each)
     sampler.sample_once()
+    e2e_calls = T * calls_each
+    calls_single = max(calls_each * T // 2, 4)
+    e2e_single_s = timed(1, calls_single) if T > 1 else e2e_s
+    if T == 1:
+        calls_single = e2e_calls
     barrier()
-    e2e_single_s = timed(1) if T > 1 else e2e_s
+    # copy-only ceiling of the same path: the bytes of one step, both directions at once, every rank at the same time
     barrier()
-    if os.environ.get("SFE_BENCH_DEBUG"):
-        print(f"[rank {rank}] e2e {T} threads {F * K / e2e_s:.0f} frames/s, 1 thread {F * K / e2e_single_s:.0f}; again: "
-              f"{F * K / timed(T):.0f} / {F * K / timed(1):.0f}", file=sys.stderr, flush=True)
+    ceil_h2d, ceil_d2h = api.copy_probe(dev, 2 * F * W * H, sum(v.nbytes for v in out.values()), 8, 1.5, wc)
+    barrier()
     sampler.stop_flag = True
     sampler.join(timeout=2)
     hamming = hamming_leg(args, dev, rank, world, dist) if args.knn_rows > 0 else None
@@ -466,12 +508,15 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_ms, e2e_single_ms, ms_x = t.tolist()
         e2e_s, e2e_single_s = e2e_ms / 1e3, e2e_single_ms / 1e3
+        t = torch.tensor([ceil_h2d, ceil_d2h], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ceil_h2d, ceil_d2h = t.tolist()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     value = world * F * K / (ms / 1e3)
-    e2e = world * F * K / e2e_s
+    e2e = world * F * e2e_calls / e2e_s
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -516,11 +561,15 @@ def main():
                        "resident_layout": f"row pitch {PITCH} B (sfe_image_pitch)",
                        "sharding": "frames partitioned across GPUs, no collective"},
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "host_threads": T, "single_thread_value": world * F * K / e2e_single_s},
+                    "host_threads": T, "single_thread_value": world * F * calls_single / e2e_single_s,
+                    "calls_timed": world * e2e_calls, "seconds_timed": e2e_s, "input_pages": "write-combined" if wc else "pinned",
+                    "h2d_ceiling_gbs": ceil_h2d, "d2h_ceiling_gbs": ceil_d2h,
+                    "ceiling_frames_per_s": ceil_h2d * 1e9 / (2 * W * H), "frac_of_copy_ceiling": e2e / (ceil_h2d * 1e9 / (2 * W * H)),
+                    "ceiling_note": "sfe_copy_probe: the bytes of one step, H2D + D2H at once, all ranks at once, no kernels"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+            "roofline": {"bound": "hbm", "binding_resource": "issue" if issue else None, "kernel": top, "achieved": achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": alg_bytes[top], "peak_source": peak_src,
                          "whole_step_achieved": value / world * B_FRAME / 1e9, "whole_step_frac": value / world * B_FRAME / 1e9 / hbm_peak,
                          "issue": issue,
@@ -533,23 +582,36 @@ def main():
                              "algorithmic_gbs": world * 2 * F / (ms_x / 1e3) * B_IMG / 1e9,
                              "note": "BASELINE config 3: sfe_extract_batch_dev on resident images, no matching"}}
     if hamming is not None:
-        hamming["q1_stream_frac_of_hbm_peak"] = hamming["q1_stream_gbs"] / (world * hbm_peak)
+        for nq in (1, 2, 4):
+            hamming[f"q{nq}_stream_frac_of_hbm_peak"] = hamming[f"q{nq}_stream_gbs"] / (world * hbm_peak)
         line["hamming"] = hamming
     if projection is not None:
         projection["frac_of_hbm_peak"] = projection["algorithmic_gbs"] / hbm_peak
         line["projection_match"] = projection
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        frames = args.cpu_frames or 32 * cores   # ~2 s per core: 10-30 s of CPU work in all
-        cpu_sample(cores, cores)                 # warm-up
-        fps_all, dt_all, _, _ = cpu_sample(frames, cores)
-        fps_1, dt_1, _, _ = cpu_sample(8, 1)
-        line["cpu_baseline"] = {"value": fps_all, "unit": "frames/s", "cores": cores, "kind": "port",
+        impl = cpu_impl()
+        frames = args.cpu_frames or (24 if impl[0] == "reference" else 32) * cores   # ~2 s per core: 10-30 s of CPU work in all
+        cpu_sample(cores, cores, impl)                 # warm-up
+        fps_all, dt_all, _, _ = cpu_sample(frames, cores, impl)
+        fps_1, dt_1, _, _ = cpu_sample(8, 1, impl)
+        line["cpu_baseline"] = {"value": fps_all, "unit": "frames/s", "cores": cores, "kind": impl[0],
                                 "sample": f"{frames} synthetic stereo frames, one frame per thread ({dt_all:.1f} s)",
-                                "single_thread_value": fps_1}
+                                "single_thread_value": fps_1,
+                                "what": ("oracle/_ref: the reference's own sources compiled unmodified (-O1; its own build uses no "
+                                         "optimisation) against stand-in third-party headers" if impl[0] == "reference"
+                                         else "oracle/orb_oracle.c, the C restatement")}
+        if impl[0] == "reference":
+            port = ("port", impl[2], impl[2])
+            cpu_sample(cores, cores, port)
+            line["cpu_baseline"]["port_value"] = cpu_sample(frames, cores, port)[0]
     print(json.dumps(line), flush=True)
+    bad = [k for k in ("hamming", "projection_match") if line.get(k) and line[k].get("sharded_equals_unsharded") is False]
     if dist is not None:
         dist.destroy_process_group()
+    if bad:
+        print(f"sharded result differs from the unsharded one: {bad}", file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -108,6 +108,11 @@ int sfe_host_alloc(void **ptr, size_t bytes); /* pinned host memory for the host
 #define SFE_HOST_WRITE_COMBINED 1
 int sfe_host_alloc_ex(void **ptr, size_t bytes, int flags);
 int sfe_host_free(void *ptr);
+/* Measurement aid: the ceiling of the host entry points.  Moves h2d_bytes pinned host -> device and d2h_bytes device ->
+ * pinned host per step (each split into `chunks` copies, the two directions on two streams at once) for about `seconds`,
+ * no kernels, and reports the sustained GB/s of each direction.  flags as sfe_host_alloc_ex, applied to the input pages. */
+int sfe_copy_probe(int device, size_t h2d_bytes, size_t d2h_bytes, int chunks, double seconds, int flags,
+                   double *h2d_gbs, double *d2h_gbs);
 int sfe_device_alloc(int device, void **ptr, size_t bytes);
 int sfe_device_free(int device, void *ptr);
 int sfe_copy_to_device(int device, void *dst_dev, const void *src_host, size_t bytes);

@@ -99,6 +99,7 @@ SIGNATURES = {
     "sfe_host_alloc": (_i, [_pp, _sz]),
     "sfe_host_alloc_ex": (_i, [_pp, _sz, _i]),
     "sfe_host_free": (_i, [_vp]),
+    "sfe_copy_probe": (_i, [_i, _sz, _sz, _i, _d, _i, C.POINTER(_d), C.POINTER(_d)]),
     "sfe_device_alloc": (_i, [_i, _pp, _sz]),
     "sfe_device_free": (_i, [_i, _vp]),
     "sfe_copy_to_device": (_i, [_i, _vp, _vp, _sz]),
@@ -226,6 +227,13 @@ def hamming256(a, b) -> int:
     a = np.ascontiguousarray(a, np.uint8)
     b = np.ascontiguousarray(b, np.uint8)
     return lib().sfe_hamming256(_p(a), _p(b))
+
+
+def copy_probe(device, h2d_bytes, d2h_bytes, chunks=8, seconds=1.0, write_combined=False):
+    """copy-only ceiling of the host path -> (h2d GB/s, d2h GB/s), both directions at once (sfe_copy_probe)"""
+    a, b = C.c_double(), C.c_double()
+    _check(lib().sfe_copy_probe(device, h2d_bytes, d2h_bytes, chunks, seconds, 1 if write_combined else 0, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 class PinnedArray:

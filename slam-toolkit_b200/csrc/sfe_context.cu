@@ -1,6 +1,8 @@
 // General entry points of the sfe C ABI: status strings, pinned/device memory, events.
 #include <mutex>
 
+#include <algorithm>
+
 #include "sfe_common.cuh"
 #include "sfe_tma.cuh"
 
@@ -114,6 +116,66 @@ int sfe_host_alloc_ex(void **ptr, size_t bytes, int flags) {
     SFE_REQUIRE(ptr && bytes > 0, SFE_ERR_BAD_ARG, "bad argument");
     SFE_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | ((flags & SFE_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0)));
     return SFE_OK;
+}
+
+// Copy-only probe of the host <-> device path: what a pipelined host call moves per step, without kernels.
+int sfe_copy_probe(int device, size_t h2d_bytes, size_t d2h_bytes, int chunks, double seconds, int flags, double *h2d_gbs,
+                   double *d2h_gbs) {
+    SFE_REQUIRE(h2d_gbs && d2h_gbs && chunks >= 1 && seconds > 0 && (h2d_bytes > 0 || d2h_bytes > 0), SFE_ERR_BAD_ARG, "bad argument");
+    DeviceGuard g(device);
+    SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select device");
+    void *hi = nullptr, *ho = nullptr, *di = nullptr, *dout = nullptr;
+    cudaStream_t si = nullptr, so = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    int rc = SFE_OK;
+    auto ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && rc == SFE_OK) { set_error("sfe_copy_probe: %s: %s", what, cudaGetErrorString(e)); rc = SFE_ERR_CUDA; }
+        return e == cudaSuccess;
+    };
+    const unsigned hflags = cudaHostAllocPortable | ((flags & SFE_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0);
+    if (h2d_bytes) { ok(cudaHostAlloc(&hi, h2d_bytes, hflags), "host alloc"); ok(cudaMalloc(&di, h2d_bytes), "device alloc"); }
+    if (d2h_bytes) { ok(cudaHostAlloc(&ho, d2h_bytes, cudaHostAllocPortable), "host alloc"); ok(cudaMalloc(&dout, d2h_bytes), "device alloc"); }
+    ok(cudaStreamCreateWithFlags(&si, cudaStreamNonBlocking), "stream");
+    ok(cudaStreamCreateWithFlags(&so, cudaStreamNonBlocking), "stream");
+    ok(cudaEventCreate(&e0), "event"); ok(cudaEventCreate(&e1), "event"); ok(cudaEventCreate(&e2), "event"); ok(cudaEventCreate(&e3), "event");
+    if (rc == SFE_OK) {
+        if (hi) memset(hi, 1, h2d_bytes);
+        if (dout) cudaMemset(dout, 2, d2h_bytes);
+        auto step = [&]() {
+            for (int c = 0; c < chunks; c++) {
+                const size_t a = h2d_bytes * c / chunks, b = h2d_bytes * (c + 1) / chunks;
+                if (b > a) cudaMemcpyAsync((char *)di + a, (char *)hi + a, b - a, cudaMemcpyHostToDevice, si);
+                const size_t p = d2h_bytes * c / chunks, q = d2h_bytes * (c + 1) / chunks;
+                if (q > p) cudaMemcpyAsync((char *)ho + p, (char *)dout + p, q - p, cudaMemcpyDeviceToHost, so);
+            }
+        };
+        step();
+        cudaStreamSynchronize(si); cudaStreamSynchronize(so);
+        // calibrate one step, then time a fixed number of steps with events on each stream
+        cudaEventRecord(e0, si); cudaEventRecord(e2, so);
+        step();
+        cudaEventRecord(e1, si); cudaEventRecord(e3, so);
+        cudaStreamSynchronize(si); cudaStreamSynchronize(so);
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e2, e3);
+        const double one = std::max((double)std::max(a, b), 0.05);
+        const int steps = (int)std::min(std::max(seconds * 1e3 / one, 2.0), 100000.0);
+        cudaEventRecord(e0, si); cudaEventRecord(e2, so);
+        for (int i = 0; i < steps; i++) step();
+        cudaEventRecord(e1, si); cudaEventRecord(e3, so);
+        ok(cudaStreamSynchronize(si), "sync"); ok(cudaStreamSynchronize(so), "sync");
+        cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e2, e3);
+        *h2d_gbs = h2d_bytes && a > 0 ? (double)h2d_bytes * steps / (a * 1e-3) / 1e9 : 0.0;
+        *d2h_gbs = d2h_bytes && b > 0 ? (double)d2h_bytes * steps / (b * 1e-3) / 1e9 : 0.0;
+    }
+    if (hi) cudaFreeHost(hi);
+    if (ho) cudaFreeHost(ho);
+    if (di) cudaFree(di);
+    if (dout) cudaFree(dout);
+    if (si) cudaStreamDestroy(si);
+    if (so) cudaStreamDestroy(so);
+    for (cudaEvent_t e : {e0, e1, e2, e3}) if (e) cudaEventDestroy(e);
+    return rc;
 }
 
 int sfe_host_free(void *ptr) {
