@@ -474,7 +474,8 @@ def main():
             th.join()
         return dt
 
-    est = timed(T, max(Wm // T, 2)) / max(Wm // T, 2)          # warm-up + seconds per call per thread
+    timed(T, max(Wm // T, 2))                                  # warm-up (the extra handles allocate their buffers here)
+    est = timed(T, 4) / 4                                       # seconds per call per thread
     est, = _max_over_ranks(dist, dev, [est])
     calls_each = int(min(max(np.ceil(2.5 / max(est, 1e-4)), 4), 2000))
     # (periodic NVML polling during this region stalls the CUDA calls of the OTHER ranks inside the driver -- measured

@@ -119,6 +119,30 @@ public:
 
     sfe_extractor *handle() { return ex_; }
 
+    // The keyframe path of StereoFrame in ONE call -- extract(left) (src/frame.cpp:47), extract(right) (:388) and
+    // StereoMatch (src/pipeline.cpp:248) -- with a single upload / download round trip instead of three; same results.
+    // stereo_indices is what StereoMatch hands to SetStereoCorrespond.  (An addition to the reference's surface for
+    // callers that hold both images; the three separate calls keep working.)
+    void extractStereo(cv::InputArray _left, cv::InputArray _right, std::vector<cv::KeyPoint> &kps_l, cv::OutputArray _desc_l,
+                       std::vector<cv::KeyPoint> &kps_r, cv::OutputArray _desc_r, std::vector<int> &stereo_indices) {
+        if (_left.empty() || _right.empty()) return;
+        cv::Mat L = _left.getMat(), R = _right.getMat();
+        if (L.type() != CV_8UC1 || R.type() != CV_8UC1 || L.rows != R.rows || L.cols != R.cols || L.step != R.step)
+            throw std::invalid_argument("ORBextractor::extractStereo: two CV_8UC1 images of the same geometry expected");
+        int need = 0;
+        sfe_adapter::check(sfe_extractor_max_keypoints_for(ex_, L.cols, L.rows, &need), "sfe_extractor_max_keypoints_for");
+        if (need > cap_) { cap_ = need; kps_.resize(cap_); }
+        desc_.resize((size_t)cap_ * 32);
+        kps_r_.resize(cap_); desc_r_.resize((size_t)cap_ * 32); sidx_.resize(cap_);
+        int32_t nl = 0, nr = 0;
+        sfe_adapter::check(sfe_stereo_frames(ex_, L.data, R.data, (size_t)L.step * L.rows, 1, L.cols, L.rows, (int)L.step, nullptr,
+                                             kps_.data(), desc_.data(), &nl, kps_r_.data(), desc_r_.data(), &nr, sidx_.data(), nullptr,
+                                             cap_), "sfe_stereo_frames");
+        fill(kps_, desc_, nl, kps_l, _desc_l);
+        fill(kps_r_, desc_r_, nr, kps_r, _desc_r);
+        stereo_indices.assign(sidx_.begin(), sidx_.begin() + nl);
+    }
+
 protected:
     int nfeatures_;
     double scaleFactor_;
@@ -126,10 +150,23 @@ protected:
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
 
 private:
+    static void fill(const std::vector<sfe_keypoint> &k, const std::vector<uint8_t> &d, int n, std::vector<cv::KeyPoint> &kps,
+                     cv::OutputArray desc) {
+        if (n == 0) {
+            desc.release();
+        } else {
+            desc.create(n, 32, CV_8U);
+            cv::Mat m = desc.getMat();
+            for (int i = 0; i < n; i++) std::memcpy(m.ptr(i), d.data() + (size_t)i * 32, 32);
+        }
+        kps.resize(n);
+        if (n) std::memcpy((void *)kps.data(), k.data(), sizeof(sfe_keypoint) * (size_t)n);
+    }
     sfe_extractor *ex_ = nullptr;
     int cap_ = 0;
-    std::vector<sfe_keypoint> kps_;
-    std::vector<uint8_t> desc_;
+    std::vector<sfe_keypoint> kps_, kps_r_;
+    std::vector<uint8_t> desc_, desc_r_;
+    std::vector<int32_t> sidx_;
 };
 
 }  // namespace ORB_SLAM2

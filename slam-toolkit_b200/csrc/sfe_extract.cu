@@ -490,23 +490,39 @@ __device__ int octree_pass(OctSmemT<kWide> &M, int cur, int n, int nL, int n_wan
         for (int i = tid; i < nL; i += T) M.tord[i] = nd[i].cnt > 1 ? M.arr_a[i] : -1;
         __syncthreads();
     } else {
-        // rank by (count, creation order) descending: count in arr_a (0 = not expandable), creation order in eidx
-        for (int i = tid; i < nL; i += T) M.arr_a[i] = nd[i].cnt > 1 ? (int)nd[i].cnt : 0;
-        __syncthreads();
+        // rank by (count, creation order) descending (0 = not expandable)
         int n_e_local = 0;
-        for (int i = tid; i < nL; i += T) {
-            const int cnt_i = M.arr_a[i];
-            int rank = -1;
-            if (cnt_i > 0) {
-                const int e_i = M.eidx[cur][i];
-                rank = 0;
-                for (int j = 0; j < nL; j++) {
-                    const int cnt_j = M.arr_a[j];
-                    rank += cnt_j > cnt_i || (cnt_j == cnt_i && M.eidx[cur][j] > e_i);
+        if (!kWide) {  // count < 65536: one unsigned key per node
+            for (int i = tid; i < nL; i += T)
+                M.arr_a[i] = nd[i].cnt > 1 ? (int)((uint32_t)nd[i].cnt << 16 | M.eidx[cur][i]) : 0;
+            __syncthreads();
+            for (int i = tid; i < nL; i += T) {
+                const uint32_t key = (uint32_t)M.arr_a[i];
+                int rank = -1;
+                if (key != 0) {
+                    rank = 0;
+                    for (int j = 0; j < nL; j++) rank += (uint32_t)M.arr_a[j] > key;
+                    n_e_local++;
                 }
-                n_e_local++;
+                M.tord[i] = rank;
             }
-            M.tord[i] = rank;
+        } else {       // count in arr_a, creation order in eidx
+            for (int i = tid; i < nL; i += T) M.arr_a[i] = nd[i].cnt > 1 ? (int)nd[i].cnt : 0;
+            __syncthreads();
+            for (int i = tid; i < nL; i += T) {
+                const int cnt_i = M.arr_a[i];
+                int rank = -1;
+                if (cnt_i > 0) {
+                    const int e_i = M.eidx[cur][i];
+                    rank = 0;
+                    for (int j = 0; j < nL; j++) {
+                        const int cnt_j = M.arr_a[j];
+                        rank += cnt_j > cnt_i || (cnt_j == cnt_i && M.eidx[cur][j] > e_i);
+                    }
+                    n_e_local++;
+                }
+                M.tord[i] = rank;
+            }
         }
         if (tid == 0) { sh_misc[0] = 0; sh_misc[1] = 0x7fffffff; }
         __syncthreads();
@@ -762,7 +778,7 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
 // this is the plain launch, with fewer CTAs (SFE_OCTREE_CTAS) the kernel is persistent and leaves shared memory to a
 // kernel running beside it.
 template <bool kWide>
-__global__ void __launch_bounds__(256) octree_kernel(ImgSet S, int count, int smem_cand, int max_cand, int max_nodes,
+__global__ void __launch_bounds__(1024) octree_kernel(ImgSet S, int count, int smem_cand, int max_cand, int max_nodes,
                                                      uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
     const int items = S.nlevels * count;
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
@@ -1236,6 +1252,20 @@ struct sfe_extractor {
     int cand_stride = 0, kpst_stride = 0, max_cand = 0, max_nodes = 0;
     size_t octree_smem = 0;
     int octree_smem_cand = 0, octree_slots = 0, octree_cand_override = 0;  // SFE_OCTREE_SMEM_CAND (tests)
+    // CUDA graphs of the kernel sequence of small unpipelined host calls (one image, one stereo pair: the reference-shaped
+    // calls): the second call with a signature captures it, later ones replay it with one launch
+    struct GraphEntry {
+        uint64_t plan_gen = 0;
+        int frames = 0, cap = 0, stereo = 0, seen = 0;
+        double sp[3] = {0, 0, 0};
+        const void *ptr[7] = {};
+        cudaGraphExec_t exec = nullptr;
+        int64_t launches = 0;
+        uint64_t used = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    uint64_t plan_gen = 0, graph_clock = 0;
+    bool use_graphs = true;           // SFE_GRAPHS=0 turns it off
     bool octree_wide = false;         // some level's candidate buffer exceeds 16-bit positions: the quadtree runs its 32-bit instance
     int cand_floor[kMaxLevels] = {};  // per-level candidate capacity learnt from an overflow (the reference's list is unbounded,
                                       // src/orb_extractor.cpp:778-779: a call that overflows is re-run with room for what it counted)
@@ -1296,8 +1326,16 @@ static void build_tables(sfe_extractor *ex) {
 
 // geometry plan for a w x h input: level sizes (:1111-1112), FAST cells (:771-806), quadtree roots
 // (:543-545), buffer layout, resize tables (cv::resize INTER_LINEAR coefficient tables)
+static void drop_graphs(sfe_extractor *ex) {
+    for (auto &g : ex->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    ex->graphs.clear();
+}
+
 static int build_plan(sfe_extractor *ex, int w, int h) {
     const int nl = ex->prm.nlevels;
+    drop_graphs(ex);  // they hold the old buffers and geometry
+    ex->plan_gen++;
     std::vector<uint2> xtab, ytab;
     int max_src_rows = 1, max_src_cols = 1;
     memset(&ex->fast, 0, sizeof(ex->fast));
@@ -1698,12 +1736,15 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         const int oct_ctas = ex->octree_ctas > 0 ? ex->octree_ctas : (fork && late ? 2 * ex->sm_count : 0);
         const int oct_grid = oct_ctas > 0 ? std::min(oct_items, oct_ctas) : oct_items;
         int *scratch_next = ex->d_counts.p + (size_t)ex->max_images * nl * 2;
+        // a call with few images cannot fill the machine with (level, image) items: their latency is what counts, and a
+        // 1024-thread CTA walks a level's candidates in a quarter of the iterations (38.6 -> measured in DESIGN.md §6)
+        const int oct_threads = oct_items <= ex->sm_count / 2 ? 1024 : 256;
         if (ex->octree_wide)
-            octree_kernel<true><<<oct_grid, 256, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
-                                                                       ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
+            octree_kernel<true><<<oct_grid, oct_threads, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
+                                                                               ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
         else
-            octree_kernel<false><<<oct_grid, 256, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
-                                                                        ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
+            octree_kernel<false><<<oct_grid, oct_threads, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
+                                                                                ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
         prof_mark(ex, 3);
         if (fork) SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[si], 0));
         else launch_blur();
@@ -1840,6 +1881,7 @@ static int pipeline_chunks(const sfe_extractor *ex, int units) {
 }
 
 static const sfe_stereo_params k_default_stereo = {3.0, 100.0, 0.5};  // src/matcher.cpp:68-70
+constexpr int kGraphMaxImages = 8;  // host calls with at most this many images replay their kernels as a CUDA graph
 
 // Host-buffer batch: `frames` images (right == nullptr) or stereo pairs, pinned or pageable host memory in and out.
 // Sub-batch c: upload on s_h2d -> kernels on the compute stream -> results on s_d2h, chained with events.
@@ -1918,17 +1960,73 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
             SFE_CUDA_BREAK(cudaEventRecord(ex->ev_in[c], sin));
             SFE_CUDA_BREAK(cudaStreamWaitEvent(sc, ex->ev_in[c], 0));
         }
-        realign_images(ex, sc, f0, fc, w, h);
-        if (stereo) realign_images(ex, sc, frames + f0, fc, w, h);
-        const OutSet Oc = chunk_of(O, f0);
-        if ((rc = enqueue_extract(ex, sc, chunk_of(B, f0, f1, stereo), stereo ? 2 * fc : fc, Oc)) != SFE_OK) break;
-        if (stereo) {
-            launch_stereo_match(sc, fc, cap, Oc.kps_a, Oc.desc_a, Oc.n_a, Oc.kps_b, Oc.desc_b, Oc.n_b, sp->y_threshold, sp->max_dx,
-                                sp->best12_threshold, ex->d_sidx.p + (size_t)f0 * cap, ex->d_sdist.p + (size_t)f0 * cap);
-            if (!piped) prof_mark(ex, 6);
-            ex->prof_has_stereo = true;
-            ex->launches++;
-            SFE_CUDA_BREAK(cudaGetLastError());
+        auto compute = [&]() -> int {  // the kernels of this sub-batch, on stream sc
+            realign_images(ex, sc, f0, fc, w, h);
+            if (stereo) realign_images(ex, sc, frames + f0, fc, w, h);
+            const OutSet Oc = chunk_of(O, f0);
+            if (int r = enqueue_extract(ex, sc, chunk_of(B, f0, f1, stereo), stereo ? 2 * fc : fc, Oc)) return r;
+            if (stereo) {
+                launch_stereo_match(sc, fc, cap, Oc.kps_a, Oc.desc_a, Oc.n_a, Oc.kps_b, Oc.desc_b, Oc.n_b, sp->y_threshold, sp->max_dx,
+                                    sp->best12_threshold, ex->d_sidx.p + (size_t)f0 * cap, ex->d_sdist.p + (size_t)f0 * cap);
+                if (!piped) prof_mark(ex, 6);
+                ex->prof_has_stereo = true;
+                ex->launches++;
+                SFE_CUDA(cudaGetLastError());
+            }
+            return SFE_OK;
+        };
+        // Reference-shaped calls (one image, one stereo pair) are launch-bound: their kernel sequence is replayed as a CUDA
+        // graph.  First sighting of a signature: run eagerly (every buffer gets allocated); second: capture + instantiate.
+        sfe_extractor::GraphEntry *ge = nullptr;
+        if (ex->use_graphs && !piped && images <= kGraphMaxImages && !prof && !ex->trace) {
+            sfe_extractor::GraphEntry key;
+            key.plan_gen = ex->plan_gen; key.frames = frames; key.cap = cap; key.stereo = stereo;
+            key.sp[0] = sp->y_threshold; key.sp[1] = sp->max_dx; key.sp[2] = sp->best12_threshold;
+            const void *ptrs[7] = {ex->d_in.p, ex->d_l0.p, ex->d_kps.p, ex->d_desc.p, ex->d_nout.p, stereo ? ex->d_sidx.p : nullptr,
+                                   stereo ? ex->d_sdist.p : nullptr};
+            memcpy(key.ptr, ptrs, sizeof(ptrs));
+            for (auto &g : ex->graphs)
+                if (g.plan_gen == key.plan_gen && g.frames == key.frames && g.cap == key.cap && g.stereo == key.stereo &&
+                    !memcmp(g.sp, key.sp, sizeof(key.sp)) && !memcmp(g.ptr, key.ptr, sizeof(key.ptr)))
+                    ge = &g;
+            if (!ge) {
+                if (ex->graphs.size() >= 4) {  // evict the least recently used signature
+                    size_t lru = 0;
+                    for (size_t i = 1; i < ex->graphs.size(); i++)
+                        if (ex->graphs[i].used < ex->graphs[lru].used) lru = i;
+                    if (ex->graphs[lru].exec) cudaGraphExecDestroy(ex->graphs[lru].exec);
+                    ex->graphs.erase(ex->graphs.begin() + lru);
+                }
+                ex->graphs.push_back(key);
+                ge = &ex->graphs.back();
+            }
+            ge->used = ++ex->graph_clock;
+        }
+        if (ge && ge->exec) {
+            SFE_CUDA_BREAK(cudaGraphLaunch(ge->exec, sc));
+            ex->launches += ge->launches;
+            ex->prof_has_stereo = stereo;
+        } else if (ge && ge->seen) {
+            const int64_t l0 = ex->launches;
+            SFE_CUDA_BREAK(cudaStreamBeginCapture(sc, cudaStreamCaptureModeRelaxed));
+            rc = compute();
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(sc, &graph);
+            if (rc == SFE_OK && ce != cudaSuccess) {
+                set_error("graph capture of a small host call failed: %s", cudaGetErrorString(ce));
+                rc = SFE_ERR_CUDA;
+            }
+            if (rc == SFE_OK) {
+                const cudaError_t ie = cudaGraphInstantiate(&ge->exec, graph, 0);
+                if (ie != cudaSuccess) { set_error("cudaGraphInstantiate: %s", cudaGetErrorString(ie)); ge->exec = nullptr; rc = SFE_ERR_CUDA; }
+            }
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != SFE_OK) { cudaGetLastError(); break; }
+            ge->launches = ex->launches - l0;
+            SFE_CUDA_BREAK(cudaGraphLaunch(ge->exec, sc));
+        } else {
+            if ((rc = compute()) != SFE_OK) break;
+            if (ge) ge->seen = 1;
         }
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 1], sc);
         if (piped) {
@@ -2055,6 +2153,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
         for (auto &e : ex->tr_ev) cudaEventCreate(&e);
     if (const char *env = getenv("SFE_OCTREE_SMEM_CAND")) ex->octree_cand_override = atoi(env);
     if (const char *env = getenv("SFE_CAND_CAP")) ex->cand_cap_override = std::max(8, atoi(env));
+    if (const char *env = getenv("SFE_GRAPHS")) ex->use_graphs = atoi(env) != 0;
     build_tables(ex);
     *out = ex;
     return SFE_OK;
@@ -2062,6 +2161,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
 
 int sfe_extractor_destroy(sfe_extractor *ex) {
     if (!ex) return SFE_OK;
+    drop_graphs(ex);
     DeviceGuard g(ex->device);
     SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStreamSynchronize(ex->stream);

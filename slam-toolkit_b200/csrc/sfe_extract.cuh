@@ -62,7 +62,11 @@ struct FastPlan {
 };
 constexpr int kFastThreads = 256;
 constexpr int kFastCtasPerSm = 5;    // register budget: 64 K / (5 x 256) = 51 per thread (6 CTAs = 40 registers measured slower)
-constexpr int kFastTilePitch = 160;  // bytes: first tested column at 7..22, 128 tested px, 3 px + one word beyond
+#ifndef SFE_FAST_TILE_PITCH
+#define SFE_FAST_TILE_PITCH 176
+#endif
+constexpr int kFastTilePitch = SFE_FAST_TILE_PITCH;  // bytes: first tested column at 7..22, 128 tested px, 3 px + one word beyond (>= 160,
+                                                     // multiple of 16: the row of a TMA box)
 constexpr int kFastScorePitch = 144; // 128 tested px + 2, multiple of 16
 constexpr int kFastSegPx = 128;      // tested pixels per segment row: 32 lanes x one 4-pixel word
 constexpr int kFastMaxCells = 8;

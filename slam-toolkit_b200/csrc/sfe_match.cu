@@ -36,8 +36,8 @@ __device__ __forceinline__ void load_desc(const uint8_t *p, uint32_t d[8]) {
 // ascending index order" (:114-123) is a plain unsigned min.
 // ---------------------------------------------------------------------------------------------
 constexpr int kStereoChunk = 2048;    // right keypoints indexed in shared memory at a time
-constexpr int kStereoPerThread = 2;   // left keypoints per thread; 512 per CTA
-constexpr int kStereoPerCta = 256 * kStereoPerThread;
+constexpr int kStereoPerThreadMax = 2; // left keypoints per thread: 2 (512 per CTA) for batches, 1 when a call carries so few
+                                       // frames that more CTAs shorten it
 constexpr int kRowShift = 3, kRowBuckets = 128;  // 8-px rows; y >= 1016 shares the last row of buckets
 constexpr int kColShift = 6, kColBuckets = 32;   // 64-px columns; x >= 1984 shares the last column
 constexpr int kStereoCells = kRowBuckets * kColBuckets;
@@ -52,6 +52,7 @@ __device__ __forceinline__ int col_bucket(float x) {
 // thr_y / thr_dx: the largest floats <= y_threshold / max_dx, so that for a float d the reference's double
 // comparison (double)d > T is exactly d > thr (no float lies strictly between thr and T).  reach_y / reach_dx:
 // |float(a - b)| <= T implies |a - b| < T + 1 for coordinates < 2^13, which bounds the buckets worth visiting.
+template <int kStereoPerThread>
 __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_keypoint *__restrict__ kl,
                                                            const uint8_t *__restrict__ dl, const int32_t *__restrict__ nl,
                                                            const sfe_keypoint *__restrict__ kr,
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_l = min(nl[f], cap), n_r = min(nr[f], cap);
     const size_t base = (size_t)f * cap;
+    constexpr int kStereoPerCta = 256 * kStereoPerThread;
     const int i0 = blockIdx.x * kStereoPerCta;
     uint32_t k0[kStereoPerThread], k1[kStereoPerThread];
 #pragma unroll
@@ -177,8 +179,12 @@ void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoin
                          double ratio, int32_t *out_idx, int32_t *out_dist) {
     // rows a candidate can sit in: |float(ly - ry)| <= y_thr implies |ly - ry| < y_thr + 1 for coordinates < 2^13
     const float reach = (float)(std::max(y_thr, 0.0) + 1.0), reach_dx = (float)(std::max(max_dx, 0.0) + 1.0);
-    stereo_match_kernel<<<dim3(div_up(cap, kStereoPerCta), frames), 256, 0, st>>>(
-        cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
+    if (frames * div_up(cap, 512) < 64)
+        stereo_match_kernel<1><<<dim3(div_up(cap, 256), frames), 256, 0, st>>>(
+            cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
+    else
+        stereo_match_kernel<kStereoPerThreadMax><<<dim3(div_up(cap, 256 * kStereoPerThreadMax), frames), 256, 0, st>>>(
+            cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2116,6 +2122,7 @@ int sfe_knn2_sharded(sfe_matcher *m, sfe_comm *c, const sfe_db *shard, const uin
     SFE_REQUIRE(shard->device == m->device, SFE_ERR_BAD_ARG, "database shard lives on another device");
     DeviceGuard g(m->device);
     SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
+    if (c->world == 1) return knn_partial(m, shard, queries_dev, q, nullptr, out_dev);  // nothing to exchange
     c->epoch++;
     const CommView V = comm_view(c);
     if ((rc = knn_partial(m, shard, queries_dev, q, nullptr, nullptr, &V)) != SFE_OK) return rc;

@@ -94,3 +94,18 @@ def test_adapter_results_equal_oracle(tmp_path, oracle):
     assert int(got["proj"]) > 0.5 * (si >= 0).sum() and int(got["self"]) > 0.9 * int(got["proj"])
     # sfe_comm_create_local + sfe_knn2_sharded + sfe_projection_match_sharded called from C++ on every visible GPU
     assert int(got["sharded_gpus"]) >= 1 and got["sharded_knn"] == "ok" and got["sharded_proj"] == "ok"
+
+
+@pytest.mark.gpu
+def test_adapter_fused_stereo_call_and_graph_replay(tmp_path):
+    """ORBextractor::extractStereo (one round trip) returns the bytes of extract + extract + StereoMatch; both run their
+    kernels as replayed CUDA graphs from the third call on (tests/cpp/adapter_latency.cpp compares them after 320 calls)."""
+    _build()
+    L, R = synth.stereo_pair(3)
+    L.tofile(tmp_path / "l.raw")
+    R.tofile(tmp_path / "r.raw")
+    p = subprocess.run([os.path.join(ROOT, "tests", "cpp", "adapter_latency"), str(tmp_path / "l.raw"), str(tmp_path / "r.raw"),
+                        str(L.shape[1]), str(L.shape[0]), "50"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    got = dict(kv.split("=") for kv in p.stdout.split())
+    assert got["same"] == "1" and int(got["nl"]) > 1900

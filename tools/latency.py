@@ -46,3 +46,11 @@ for _ in range(n): f.ProjectionMatch(xw, mpd, None, np.eye(3, 4), 50.0)
 t4 = time.perf_counter()
 print(f"StereoMatch(2000 x 2000): {1e6*(t1-t0)/n:.0f} us/call   ProjectionMatch(1500 points, frame uploaded per call): "
       f"{1e6*(t2-t1)/n:.0f} us/call   against a resident frame: {1e6*(t4-t3)/n:.0f} us/call")
+
+# the same through the C++ adapter (include/sfe_adapter.hpp), no Python in the loop
+import subprocess
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+subprocess.check_call(["make", "-C", os.path.join(root, "tests", "cpp")], stdout=subprocess.DEVNULL)
+L.tofile("/tmp/lat_l.raw"); R.tofile("/tmp/lat_r.raw")
+print("C++ adapter:", subprocess.run([os.path.join(root, "tests", "cpp", "adapter_latency"), "/tmp/lat_l.raw", "/tmp/lat_r.raw",
+                                      str(L.shape[1]), str(L.shape[0]), "500"], capture_output=True, text=True).stdout.strip())
