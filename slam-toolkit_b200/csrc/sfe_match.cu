@@ -1296,7 +1296,8 @@ static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, i
     const int qgroups = by_rows ? 1 : div_up(q, kKnnThreads);
     int chunks = std::max(1, (8 * m->sm_count) / qgroups);  // 8 CTAs of 256 threads per SM: the XOR-CSA-POPC chain needs the warps to hide its latency
     int64_t chunk_rows = std::max<int64_t>((db->rows + chunks - 1) / chunks, 1);
-    chunk_rows = (chunk_rows + 511) / 512 * 512;
+    const int64_t grain = by_rows ? 512 : kKnnTile;  // the streaming kernel walks 8 warps x 64 rows per step, the other one tiles of 256
+    chunk_rows = (chunk_rows + grain - 1) / grain * grain;
     SFE_REQUIRE(chunk_rows <= (1 << 22), SFE_ERR_UNSUPPORTED, "database shard larger than 2^22 rows per chunk");
     chunks = (int)std::max<int64_t>((db->rows + chunk_rows - 1) / chunk_rows, 1);
     SFE_CUDA(m->d_part.ensure((size_t)chunks * q * 2));
