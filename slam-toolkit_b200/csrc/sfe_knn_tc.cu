@@ -1,0 +1,305 @@
+// Brute-force Hamming top-2 for MANY queries on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+// For 256-bit descriptors a, b:  hamming(a, b) = |a| + |b| - 2 <a, b>  with <a, b> the dot product of the two bit
+// vectors.  With the bits unpacked to int8 {0, 1} the Q x M dot products are an int8 GEMM with K = 256 whose int32
+// accumulators are exact, so the distances -- and the lexicographic (distance, row) top-2 the matchers of the reference
+// keep (src/matcher.cpp:114-123) -- are bit-identical to the XOR / POPC kernels (knn2_partial_kernel), at a fraction of
+// their integer-pipe cost: the pair loop shrinks from 16 LOP3 + 4 POPC + 3 min/max per pair to ~3.5 ALU operations of the
+// epilogue (BASELINE config 4: 2000 queries x 10 M rows).
+//
+// One persistent CTA per SM works on one (query group of 512, chunk of database rows) item:
+//   * the group's 4 x 128 queries are unpacked once into shared memory as four A tiles (K-major, no swizzle: 8-row x 16-byte
+//     core matrices, LBO = 128 B between K chunks, SBO = 2048 B between 8-row groups);
+//   * 4 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same
+//     layout, with a per-row base key ((|b| + 512) << 22 | row-in-chunk);
+//   * one elected thread issues tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32, 8 per tile pair) into TMEM: two stages of
+//     two 128-column accumulators each fill the 512 columns;
+//   * 8 epilogue warps drain a stage with tcgen05.ld (thread = query row, 32 columns at a time), turn every dot product
+//     into the key  base[row] - (dot << 23)  and keep the two smallest keys per query in registers;
+//   * mbarriers carry the B-tile full / empty and TMEM full / empty hand-offs; tcgen05.commit arrives on them.
+// Output = the same per-(chunk, query) pair of 64-bit keys (distance << 32 | global row) the other partial kernels
+// write, so knn2_merge_kernel / knn2_merge_push_kernel finish the job.
+#include <algorithm>
+
+#include "sfe_common.cuh"
+#include "sfe_tma.cuh"
+
+namespace sfe {
+
+namespace {
+
+constexpr int kTcThreads = 13 * 32;          // warp 0: MMA issuer, warps 1-4: producers, warps 5-12: epilogue
+constexpr int kGroupQ = 512;                 // queries per work item: 4 M-tiles of 128
+constexpr int kTileN = 128;                  // database rows per B tile
+constexpr int kTileBytes = 128 * 256;        // one operand tile: 128 rows x 256 int8
+constexpr uint32_t kSBO = 2048, kLBO = 128;  // bytes: between 8-row groups / between 16-byte K chunks
+constexpr uint32_t kKeyOffset = 512;         // keeps |b| - 2 dot non-negative (>= -256)
+constexpr uint32_t kNoKey32 = 0xFFFFFFFFu;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// tcgen05.commit: the barrier gets one arrival once every MMA issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 |
+// SBO >> 4 << 32 | version 1 << 46
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | (uint64_t)(kLBO >> 4) << 16 | (uint64_t)(kSBO >> 4) << 32 | 1ull << 46;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = unsigned 8-bit, both K-major, N >> 3, M >> 4
+constexpr uint32_t kIdesc = (2u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, bool accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"((uint32_t)accumulate), "r"(0u)
+        : "memory");
+}
+// 32 lanes x 32 consecutive columns of 32 bits -> 32 registers per thread (lane = TMEM lane of the warp's quadrant)
+__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// 16 descriptor bits -> 16 bytes of {0, 1}: bit k of the half-word goes to byte k (any fixed order works: both operands use it)
+__device__ __forceinline__ uint4 unpack16(uint32_t bits) {
+    uint4 o;
+    o.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
+    o.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+    o.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+    o.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    return o;
+}
+// byte offset of (row, 16-byte K chunk) inside an operand tile
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row >> 3) * kSBO + (uint32_t)chunk * kLBO + (uint32_t)(row & 7) * 16; }
+
+// the two smallest of {k0 <= k1, x, y}
+__device__ __forceinline__ void top2_pair(uint32_t &k0, uint32_t &k1, uint32_t x, uint32_t y) {
+    const uint32_t lo = min(x, y), hi = max(x, y);
+    k1 = min(min(k1, hi), max(k0, lo));
+    k0 = min(k0, lo);
+}
+
+struct TcSmem {
+    uint8_t a[4][kTileBytes];      // query tiles of the group
+    uint8_t b[2][kTileBytes];      // database tiles, double buffered
+    uint32_t base[4][kTileN];      // per database row of the tile: (|b| + 512) << 22 | row in chunk  (0xFFFFFFFF past the end).  Four slots:
+                                   // a B buffer is free once its MMAs are done, but the epilogue may still be reading that tile's keys
+    uint64_t b_full[2], b_empty[2], d_full[2], d_empty[2];
+    uint32_t tmem_base;
+    uint32_t merge[4][128][2];     // epilogue warps 4-7 hand their pairs to warps 0-3
+};
+
+}  // namespace
+
+// part[(chunk * q + query) * 2 + r] = r-th smallest (distance << 32 | global row) of the chunk, ~0 when there is none
+__global__ void __launch_bounds__(kTcThreads, 1)
+knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_base, int chunk_rows, int chunks, const uint8_t *__restrict__ queries,
+               int q, unsigned long long *__restrict__ part) {
+    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
+    TcSmem &S = *(TcSmem *)tc_smem_raw;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int groups = (q + kGroupQ - 1) / kGroupQ;
+    if (warp == 0) {  // TMEM: all 512 columns (one CTA per SM: the shared memory footprint sees to that)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&S.b_full[i], 4);   // one arrival per producer warp
+            mbar_init(&S.b_empty[i], 1);  // tcgen05.commit
+            mbar_init(&S.d_full[i], 1);   // tcgen05.commit
+            mbar_init(&S.d_empty[i], 8);  // one arrival per epilogue warp
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+    uint32_t ph_b_full = 0, ph_b_empty = 0, ph_d_full = 0, ph_d_empty = 0;  // bit i = parity of the next wait on barrier i
+
+    for (int item = blockIdx.x; item < groups * chunks; item += gridDim.x) {
+        const int g = item / chunks, chunk = item % chunks;
+        const long long r0 = (long long)chunk * chunk_rows, r1 = min(r0 + (long long)chunk_rows, rows);
+        const int q0 = g * kGroupQ, ntiles = r1 > r0 ? (int)((r1 - r0 + kTileN - 1) / kTileN) : 0;
+        // ---- A tiles: the group's queries, unpacked by every thread (queries past q are zero rows) ----------------------
+        __syncthreads();  // the previous item's MMAs no longer read the A tiles (its epilogue has drained every accumulator)
+        for (int u = tid; u < kGroupQ * 16; u += kTcThreads) {
+            const int row = u >> 4, chunk16 = u & 15, qi = q0 + row;
+            const uint32_t bits = qi < q ? __ldg((const uint16_t *)(queries + (size_t)qi * 32) + chunk16) : 0u;
+            *(uint4 *)(S.a[row >> 7] + tile_off(row & 127, chunk16)) = unpack16(bits);
+        }
+        fence_async_smem();
+        __syncthreads();
+
+        if (warp == 0) {
+            // ===== MMA issuer ========================================================================================
+            for (int n = 0; n < ntiles; n++) {
+                const int bi = n & 1;
+                mbar_wait(&S.b_full[bi], (ph_b_full >> bi) & 1);
+                ph_b_full ^= 1u << bi;
+                tc_fence_after();
+                for (int h = 0; h < 2; h++) {       // two M-tile pairs per B tile, alternating TMEM stages
+                    const int st = h;               // stage h: columns [256 h, 256 h + 256)
+                    mbar_wait(&S.d_empty[st], ((ph_d_empty >> st) & 1) ^ 1);  // first use passes: the barrier starts in phase 0
+                    ph_d_empty ^= 1u << st;
+                    tc_fence_after();
+                    if (lane == 0) {
+                        for (int t = 0; t < 2; t++) {
+                            const uint32_t a_addr = smem_u32(S.a[2 * h + t]), b_addr = smem_u32(S.b[bi]);
+                            const uint32_t d = tmem + (uint32_t)(st * 256 + t * 128);
+#pragma unroll
+                            for (int k = 0; k < 8; k++)  // K = 32 per instruction: two 16-byte chunks
+                                mma_i8(d, smem_desc(a_addr + k * 2 * kLBO), smem_desc(b_addr + k * 2 * kLBO), k > 0);
+                        }
+                        tc_commit(&S.d_full[st]);
+                        if (h == 1) tc_commit(&S.b_empty[bi]);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (warp <= 4) {
+            // ===== producers: database rows -> B tile + base keys ====================================================
+            const int pw = warp - 1, pt = pw * 32 + lane;  // 128 producer threads
+            for (int n = 0; n < ntiles; n++) {
+                const int bi = n & 1;
+                mbar_wait(&S.b_empty[bi], ((ph_b_empty >> bi) & 1) ^ 1);
+                ph_b_empty ^= 1u << bi;
+                const long long t0 = r0 + (long long)n * kTileN;
+                // thread = (row, half): 16 threads x 8 passes cover 128 rows x 16 chunks with 16-byte stores that a warp lays
+                // down as 8 rows x 4 chunks = 512 contiguous bytes
+                for (int pass = 0; pass < 16; pass++) {
+                    const int row = (pt & 7) + 8 * ((pt >> 5) + 4 * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
+                    const long long gr = t0 + row;
+                    const uint32_t bits = gr < r1 ? __ldg((const uint16_t *)(db + (size_t)gr * 32) + chunk16) : 0u;
+                    *(uint4 *)(S.b[bi] + tile_off(row, chunk16)) = unpack16(bits);
+                }
+                {   // base key of row pt
+                    const long long gr = t0 + pt;
+                    uint32_t key = kNoKey32;
+                    if (gr < r1) {
+                        const uint4 *p = (const uint4 *)(db + (size_t)gr * 32);
+                        const uint4 u = __ldg(p), v = __ldg(p + 1);
+                        const int pc = __popc(u.x) + __popc(u.y) + __popc(u.z) + __popc(u.w) + __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+                        key = ((uint32_t)pc + kKeyOffset) << 22 | (uint32_t)(gr - r0);
+                    }
+                    S.base[n & 3][pt] = key;
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.b_full[bi]);
+            }
+        } else {
+            // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
+            const int ew = warp - 5, quad = warp & 3, half = ew >> 2;  // a warp reads the TMEM lanes of quadrant warp % 4
+            const int row = quad * 32 + lane;                           // query row inside each M-tile
+            uint32_t k0[4], k1[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) k0[t] = k1[t] = kNoKey32;
+            for (int n = 0; n < ntiles; n++) {
+                for (int h = 0; h < 2; h++) {
+                    const int st = h;
+                    mbar_wait(&S.d_full[st], (ph_d_full >> st) & 1);
+                    ph_d_full ^= 1u << st;
+                    tc_fence_after();
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        // this warp's half of the tile's 128 columns: two loads of 32 columns
+#pragma unroll
+                        for (int c = 0; c < 2; c++) {
+                            const int col = half * 64 + c * 32;
+                            uint32_t v[32];
+                            tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * 256 + t * 128 + col), v);
+                            const uint4 *bk = (const uint4 *)&S.base[n & 3][col];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const uint4 b4 = bk[j];  // broadcast read: every lane takes the same four base keys
+                                // rows past the end carry base 0xFFFFFFFF and a zero dot product: they stay 0xFFFFFFFF
+                                top2_pair(k0[2 * h + t], k1[2 * h + t], b4.x - (v[4 * j] << 23), b4.y - (v[4 * j + 1] << 23));
+                                top2_pair(k0[2 * h + t], k1[2 * h + t], b4.z - (v[4 * j + 2] << 23), b4.w - (v[4 * j + 3] << 23));
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.d_empty[st]);
+                }
+            }
+            // the two warps of a quadrant hold disjoint columns: merge through shared memory, then write the chunk's keys
+            if (half == 1) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    S.merge[t][row][0] = k0[t];
+                    S.merge[t][row][1] = k1[t];
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+            if (half == 0) {
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    top2_pair(k0[t], k1[t], S.merge[t][row][0], S.merge[t][row][1]);
+                    const int qi = q0 + t * 128 + row;
+                    if (qi < q) {
+                        const uint4 *p = (const uint4 *)(queries + (size_t)qi * 32);
+                        const uint4 u = __ldg(p), w = __ldg(p + 1);
+                        const int pa = __popc(u.x) + __popc(u.y) + __popc(u.z) + __popc(u.w) + __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+                        unsigned long long o[2];
+                        const uint32_t kk[2] = {k0[t], k1[t]};
+#pragma unroll
+                        for (int r = 0; r < 2; r++) {
+                            if (kk[r] == kNoKey32) { o[r] = ~0ull; continue; }
+                            const unsigned long long dist = (unsigned long long)((kk[r] >> 22) - kKeyOffset + (uint32_t)pa);
+                            o[r] = dist << 32 | (unsigned long long)(idx_base + r0 + (long long)(kk[r] & 0x3FFFFFu));
+                        }
+                        unsigned long long *dst = part + ((size_t)chunk * q + qi) * 2;
+                        dst[0] = o[0];
+                        dst[1] = o[1];
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // merge[] is free for the next item
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+size_t knn2_tc_smem_bytes() { return sizeof(TcSmem) + 1024; }
+
+// chunks x q x 2 keys into `part`; chunk_rows must be a multiple of 128 and at most 2^22
+cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, long long rows, long long idx_base, int chunk_rows, int chunks,
+                           const uint8_t *queries, int q, unsigned long long *part) {
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = knn2_tc_smem_bytes();
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = true;
+    }
+    const int groups = (q + kGroupQ - 1) / kGroupQ;
+    const int grid = std::min(sm_count, groups * chunks);
+    knn2_tc_kernel<<<grid, kTcThreads, smem, st>>>(db, rows, idx_base, chunk_rows, chunks, queries, q, part);
+    return cudaGetLastError();
+}
+
+}  // namespace sfe

@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint8_t
 // g*32 + j in lane j.  A row only enters the reduction when it beats that query's current second best --
 // after the first few thousand rows almost never -- so the steady state is XOR + POPC + one vote per pair.
 constexpr int kRowsQMax = 128;
+constexpr int kKnnTcMinQ = 256;  // from here on the tensor-core kernel wins (it always works on groups of 512 queries)
 
 template <int QPL>  // queries per lane: q <= 32 * QPL
 __global__ void __launch_bounds__(256) knn2_rows_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_base,
@@ -1181,6 +1182,7 @@ struct sfe_matcher {
     int sm_count = 148;
     int64_t launches = 0;
     bool async_dev = false;  // _dev entry points return after enqueueing (sfe_matcher_wait)
+    bool knn_tc = true;      // SFE_KNN_TC=0: brute-force top-2 with many queries stays on the XOR / POPC kernel
     DevBuf<sfe_keypoint> d_kl, d_kr;
     DevBuf<uint8_t> d_dl, d_dr, d_skip;
     DevBuf<int32_t> d_n, d_idx, d_dist;
@@ -1289,9 +1291,33 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
     return SFE_OK;
 }
 
+namespace sfe {
+cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, long long rows, long long idx_base, int chunk_rows, int chunks,
+                           const uint8_t *queries, int q, unsigned long long *part);  // sfe_knn_tc.cu
+}
+
 static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, int q, unsigned long long *keys_dev,
                        int32_t *quad_dev, const CommView *push = nullptr) {
     cudaStream_t st = m->stream;
+    if (m->knn_tc && q >= kKnnTcMinQ && db->rows >= 1) {
+        // many queries: the pair distances are an int8 GEMM on the tensor cores (sfe_knn_tc.cu), one (512-query group, chunk)
+        // item per SM; the chunk partials are merged as usual
+        const int groups = div_up(q, 512);
+        int chunks = std::max(1, m->sm_count / groups);
+        int64_t chunk_rows = std::max<int64_t>((db->rows + chunks - 1) / chunks, 1);
+        chunk_rows = (chunk_rows + 127) / 128 * 128;
+        SFE_REQUIRE(chunk_rows <= (1 << 22), SFE_ERR_UNSUPPORTED, "database shard larger than 2^22 rows per chunk");
+        chunks = (int)std::max<int64_t>((db->rows + chunk_rows - 1) / chunk_rows, 1);
+        SFE_CUDA(m->d_part.ensure((size_t)chunks * q * 2));
+        SFE_CUDA(launch_knn2_tc(st, m->sm_count, db->rows_dev, db->rows, db->idx_base, (int)chunk_rows, chunks, q_dev, q, m->d_part.p));
+        if (push)
+            knn2_merge_push_kernel<<<div_up(q, 4), 128, 0, st>>>(*push, m->d_part.p, chunks, q);
+        else
+            knn2_merge_kernel<<<div_up(q, 4), 128, 0, st>>>(m->d_part.p, chunks, q, keys_dev, quad_dev);
+        m->launches += 2;
+        SFE_CUDA(cudaGetLastError());
+        return SFE_OK;
+    }
     const bool by_rows = q <= kRowsQMax;  // thread = row (streaming) for few queries, thread = query otherwise
     const int qgroups = by_rows ? 1 : div_up(q, kKnnThreads);
     int chunks = std::max(1, (8 * m->sm_count) / qgroups);  // 8 CTAs of 256 threads per SM: the XOR-CSA-POPC chain needs the warps to hide its latency
@@ -1341,6 +1367,7 @@ int sfe_matcher_create(int device, sfe_matcher **out) {
         return SFE_ERR_CUDA;
     }
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (const char *env = getenv("SFE_KNN_TC")) m->knn_tc = atoi(env) != 0;
     *out = m;
     return SFE_OK;
 }
