@@ -1,21 +1,22 @@
 // Brute-force Hamming top-2 for MANY queries on the 5th-generation tensor cores (tcgen05, sm_100a).
 //
-// For 256-bit descriptors a, b:  hamming(a, b) = |a| + |b| - 2 <a, b>  with <a, b> the dot product of the two bit
-// vectors.  With the bits unpacked to int8 {0, 1} the Q x M dot products are an int8 GEMM with K = 256 whose int32
-// accumulators are exact, so the distances -- and the lexicographic (distance, row) top-2 the matchers of the reference
-// keep (src/matcher.cpp:114-123) -- are bit-identical to the XOR / POPC kernels (knn2_partial_kernel), at a fraction of
-// their integer-pipe cost: the pair loop shrinks from 16 LOP3 + 4 POPC + 3 min/max per pair to ~3.5 ALU operations of the
-// epilogue (BASELINE config 4: 2000 queries x 10 M rows).
+// For 256-bit descriptors a, b:  hamming(a, b) = |a| + |b| - 2 <a, b> = |a| + sum_k b_k (1 - 2 a_k).  With the query bits
+// unpacked to int8 {+1, -1} (= 1 - 2 a_k) and the database bits to int8 {0, 1}, the Q x M values  D' = hamming - |a|  are an
+// int8 GEMM with K = 256 whose int32 accumulators are exact, so the distances -- and the lexicographic (distance, row) top-2
+// the matchers of the reference keep (src/matcher.cpp:114-123) -- are bit-identical to the XOR / POPC kernels
+// (knn2_partial_kernel), at a fraction of their integer-pipe cost: the pair loop shrinks from 16 LOP3 + 4 POPC + 3 min/max
+// per pair to half a min per pair in the epilogue, which only looks closer at the rare accumulator that can still enter a
+// query's top-2 (BASELINE config 4: 2000 queries x 10 M rows).
 //
 // One persistent CTA per SM works on one (query group of 512, chunk of database rows) item:
 //   * the group's 4 x 128 queries are unpacked once into shared memory as four A tiles (K-major, no swizzle: 8-row x 16-byte
 //     core matrices, LBO = 128 B between K chunks, SBO = 2048 B between 8-row groups);
-//   * 4 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same
-//     layout, with a per-row base key ((|b| + 512) << 22 | row-in-chunk);
+//   * 4 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same layout;
 //   * one elected thread issues tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32, 8 per tile pair) into TMEM: two stages of
 //     two 128-column accumulators each fill the 512 columns;
-//   * 8 epilogue warps drain a stage with tcgen05.ld (thread = query row, 32 columns at a time), turn every dot product
-//     into the key  base[row] - (dot << 23)  and keep the two smallest keys per query in registers;
+//   * 8 epilogue warps drain a stage with tcgen05.ld (thread = query row, 32 columns at a time, the next load in flight
+//     while the current one is examined): the minimum of 8 accumulators is compared with the query's current second-best
+//     D'; only a group that can still matter is turned into keys ((D' + 512) << 22 | row in chunk) and inserted;
 //   * mbarriers carry the B-tile full / empty and TMEM full / empty hand-offs; tcgen05.commit arrives on them.
 // Output = the same per-(chunk, query) pair of 64-bit keys (distance << 32 | global row) the other partial kernels
 // write, so knn2_merge_kernel / knn2_merge_push_kernel finish the job.
@@ -28,13 +29,25 @@ namespace sfe {
 
 namespace {
 
-constexpr int kTcThreads = 13 * 32;          // warp 0: MMA issuer, warps 1-4: producers, warps 5-12: epilogue
+#ifndef SFE_TC_EPI_WARPS
+#define SFE_TC_EPI_WARPS 16
+#endif
+#ifndef SFE_TC_NOINLINE
+#define SFE_TC_NOINLINE 0
+#endif
+constexpr int kEpiWarps = SFE_TC_EPI_WARPS;  // 4 * kParts: kParts warps per TMEM lane quadrant, each on 128 / kParts columns of a tile
+constexpr int kParts = kEpiWarps / 4, kColsPerWarp = 128 / kParts, kLoadsPerTile = kColsPerWarp / 32;
+constexpr int kTcThreads = (5 + kEpiWarps) * 32;  // warp 0: MMA issuer, warps 1-4: producers, warps 5-20: epilogue
 constexpr int kGroupQ = 512;                 // queries per work item: 4 M-tiles of 128
 constexpr int kTileN = 128;                  // database rows per B tile
 constexpr int kTileBytes = 128 * 256;        // one operand tile: 128 rows x 256 int8
 constexpr uint32_t kSBO = 2048, kLBO = 128;  // bytes: between 8-row groups / between 16-byte K chunks
-constexpr uint32_t kKeyOffset = 512;         // keeps |b| - 2 dot non-negative (>= -256)
+constexpr int kKeyOffset = 512;              // keeps D' = |b| - 2 dot non-negative in the key (D' >= -256)
 constexpr uint32_t kNoKey32 = 0xFFFFFFFFu;
+#ifndef SFE_TC_PREFETCH
+#define SFE_TC_PREFETCH 0
+#endif
+constexpr bool kPrefetchB = SFE_TC_PREFETCH != 0;  // fetch the next tile's bits before writing this one (measured: slower)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -52,8 +65,8 @@ __device__ __forceinline__ void tc_commit(uint64_t *bar) {
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | (uint64_t)(kLBO >> 4) << 16 | (uint64_t)(kSBO >> 4) << 32 | 1ull << 46;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = unsigned 8-bit, both K-major, N >> 3, M >> 4
-constexpr uint32_t kIdesc = (2u << 4) | ((uint32_t)(kTileN >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed 8-bit, both K-major, N >> 3, M >> 4
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((128u >> 4) << 24);
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, bool accumulate) {
     asm volatile(
         "{\n"
@@ -64,8 +77,13 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
         "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"((uint32_t)accumulate), "r"(0u)
         : "memory");
 }
-// 32 lanes x 32 consecutive columns of 32 bits -> 32 registers per thread (lane = TMEM lane of the warp's quadrant)
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
+// 32 lanes x 32 consecutive columns of 32 bits -> 32 registers per thread (lane = TMEM lane of the warp's quadrant).
+// The load is asynchronous: tmem_ld_wait makes the registers valid (they are operands of the wait so that no use moves above it).
+#define SFE_R32(v) "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), \
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),   \
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),   \
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, int (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
         "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -75,16 +93,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
           "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(addr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait(int (&v)[32]) { asm volatile("tcgen05.wait::ld.sync.aligned;" : SFE_R32(v)::"memory"); }
 
-// 16 descriptor bits -> 16 bytes of {0, 1}: bit k of the half-word goes to byte k (any fixed order works: both operands use it)
+// 16 descriptor bits -> 16 bytes of {0, 1}: bit k of the half-word goes to byte k (any fixed order works: both operands use it);
+// unpack16_pm turns them into {+1, -1} = 1 - 2 bit
 __device__ __forceinline__ uint4 unpack16(uint32_t bits) {
     uint4 o;
     o.x = ((bits & 0xFu) * 0x00204081u) & 0x01010101u;
     o.y = (((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
     o.z = (((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
     o.w = (((bits >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+    return o;
+}
+__device__ __forceinline__ uint4 unpack16_pm(uint32_t bits) {
+    uint4 o = unpack16(bits);
+    o.x = 0x01010101u | (o.x * 0xFEu);  // byte 0 -> 0x01, byte 1 -> 0xFF; no carry crosses a byte
+    o.y = 0x01010101u | (o.y * 0xFEu);
+    o.z = 0x01010101u | (o.z * 0xFEu);
+    o.w = 0x01010101u | (o.w * 0xFEu);
     return o;
 }
 // byte offset of (row, 16-byte K chunk) inside an operand tile
@@ -96,15 +123,47 @@ __device__ __forceinline__ void top2_pair(uint32_t &k0, uint32_t &k1, uint32_t x
     k1 = min(min(k1, hi), max(k0, lo));
     k0 = min(k0, lo);
 }
+__device__ __forceinline__ void top2_one(uint32_t &k0, uint32_t &k1, uint32_t x) {
+    k1 = min(k1, max(k0, x));
+    k0 = min(k0, x);
+}
+
+// 8 accumulators of which at least one can still enter the query's top-2: key and insert the valid ones.  Out of line: it
+// runs for a few percent of the groups, and inlining its 8 copies 16 times over made the epilogue miss the instruction cache
+// (44 % of its stall samples).
+#if SFE_TC_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+void insert8(int v0, int v1, int v2, int v3, int v4, int v5, int v6, int v7, uint32_t idx, uint32_t chunk_n,
+                                     uint32_t &k0, uint32_t &k1, int &thr) {
+    const int v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
+#pragma unroll
+    for (int e = 0; e < 8; e++)
+        if (v[e] <= thr && idx + e < chunk_n) top2_one(k0, k1, (uint32_t)(v[e] + kKeyOffset) << 22 | (idx + e));
+    thr = (int)(k1 >> 22) - kKeyOffset;  // 511 while fewer than two rows have been seen: everything passes
+}
+
+// 32 accumulators D' of one query (columns idx0 .. idx0 + 31 of the chunk): groups of 8 whose minimum cannot beat the
+// query's second-best distance are dropped after 4 min3 / min
+__device__ __forceinline__ void examine32(const int (&v)[32], uint32_t &k0, uint32_t &k1, int &thr, uint32_t idx0, uint32_t chunk_n) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int m = __vimin3_s32(__vimin3_s32(v[8 * j], v[8 * j + 1], v[8 * j + 2]), __vimin3_s32(v[8 * j + 3], v[8 * j + 4], v[8 * j + 5]),
+                                   min(v[8 * j + 6], v[8 * j + 7]));
+        if (m <= thr)
+            insert8(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7], idx0 + 8 * j,
+                    chunk_n, k0, k1, thr);
+    }
+}
 
 struct TcSmem {
     uint8_t a[4][kTileBytes];      // query tiles of the group
     uint8_t b[2][kTileBytes];      // database tiles, double buffered
-    uint32_t base[4][kTileN];      // per database row of the tile: (|b| + 512) << 22 | row in chunk  (0xFFFFFFFF past the end).  Four slots:
-                                   // a B buffer is free once its MMAs are done, but the epilogue may still be reading that tile's keys
     uint64_t b_full[2], b_empty[2], d_full[2], d_empty[2];
     uint32_t tmem_base;
-    uint32_t merge[4][128][2];     // epilogue warps 4-7 hand their pairs to warps 0-3
+    uint32_t merge[kParts > 1 ? kParts - 1 : 1][4][128][2];  // the epilogue warps of column parts 1.. hand their pairs to the warp of part 0
 };
 
 }  // namespace
@@ -112,7 +171,7 @@ struct TcSmem {
 // part[(chunk * q + query) * 2 + r] = r-th smallest (distance << 32 | global row) of the chunk, ~0 when there is none
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_base, int chunk_rows, int chunks, const uint8_t *__restrict__ queries,
-               int q, unsigned long long *__restrict__ part) {
+               int q, unsigned long long *__restrict__ part_out) {
     extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
     TcSmem &S = *(TcSmem *)tc_smem_raw;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -126,7 +185,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
             mbar_init(&S.b_full[i], 4);   // one arrival per producer warp
             mbar_init(&S.b_empty[i], 1);  // tcgen05.commit
             mbar_init(&S.d_full[i], 1);   // tcgen05.commit
-            mbar_init(&S.d_empty[i], 8);  // one arrival per epilogue warp
+            mbar_init(&S.d_empty[i], kEpiWarps);  // one arrival per epilogue warp
         }
     }
     tc_fence_before();
@@ -139,12 +198,12 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         const int g = item / chunks, chunk = item % chunks;
         const long long r0 = (long long)chunk * chunk_rows, r1 = min(r0 + (long long)chunk_rows, rows);
         const int q0 = g * kGroupQ, ntiles = r1 > r0 ? (int)((r1 - r0 + kTileN - 1) / kTileN) : 0;
-        // ---- A tiles: the group's queries, unpacked by every thread (queries past q are zero rows) ----------------------
+        // ---- A tiles: the group's queries as +1 / -1, unpacked by every thread (rows past q are ignored later) -----------
         __syncthreads();  // the previous item's MMAs no longer read the A tiles (its epilogue has drained every accumulator)
         for (int u = tid; u < kGroupQ * 16; u += kTcThreads) {
             const int row = u >> 4, chunk16 = u & 15, qi = q0 + row;
             const uint32_t bits = qi < q ? __ldg((const uint16_t *)(queries + (size_t)qi * 32) + chunk16) : 0u;
-            *(uint4 *)(S.a[row >> 7] + tile_off(row & 127, chunk16)) = unpack16(bits);
+            *(uint4 *)(S.a[row >> 7] + tile_off(row & 127, chunk16)) = unpack16_pm(bits);
         }
         fence_async_smem();
         __syncthreads();
@@ -176,85 +235,92 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 }
             }
         } else if (warp <= 4) {
-            // ===== producers: database rows -> B tile + base keys ====================================================
+            // ===== producers: database rows -> B tile ================================================================
             const int pw = warp - 1, pt = pw * 32 + lane;  // 128 producer threads
+            // thread = 4 rows x 4 chunks of a tile: 16 passes of one 16-byte store each, which a warp lays down as 8 rows x 4 chunks =
+            // 512 contiguous bytes.  The descriptor bits of the NEXT tile are fetched before this one is written, so the global
+            // latency never sits between "buffer free" and "buffer full".
+            uint32_t bits[16];
+            auto fetch = [&](int n) {
+                const long long t0 = r0 + (long long)n * kTileN;
+#pragma unroll
+                for (int pass = 0; pass < 16; pass++) {
+                    const int row = (pt & 7) + 8 * ((pt >> 5) + 4 * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
+                    const long long gr = t0 + row;
+                    bits[pass] = gr < r1 ? __ldg((const uint16_t *)(db + (size_t)gr * 32) + chunk16) : 0u;
+                }
+            };
+            if (kPrefetchB && ntiles > 0) fetch(0);
             for (int n = 0; n < ntiles; n++) {
                 const int bi = n & 1;
                 mbar_wait(&S.b_empty[bi], ((ph_b_empty >> bi) & 1) ^ 1);
                 ph_b_empty ^= 1u << bi;
-                const long long t0 = r0 + (long long)n * kTileN;
-                // thread = (row, half): 16 threads x 8 passes cover 128 rows x 16 chunks with 16-byte stores that a warp lays
-                // down as 8 rows x 4 chunks = 512 contiguous bytes
+                if (!kPrefetchB) fetch(n);
+#pragma unroll
                 for (int pass = 0; pass < 16; pass++) {
                     const int row = (pt & 7) + 8 * ((pt >> 5) + 4 * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
-                    const long long gr = t0 + row;
-                    const uint32_t bits = gr < r1 ? __ldg((const uint16_t *)(db + (size_t)gr * 32) + chunk16) : 0u;
-                    *(uint4 *)(S.b[bi] + tile_off(row, chunk16)) = unpack16(bits);
-                }
-                {   // base key of row pt
-                    const long long gr = t0 + pt;
-                    uint32_t key = kNoKey32;
-                    if (gr < r1) {
-                        const uint4 *p = (const uint4 *)(db + (size_t)gr * 32);
-                        const uint4 u = __ldg(p), v = __ldg(p + 1);
-                        const int pc = __popc(u.x) + __popc(u.y) + __popc(u.z) + __popc(u.w) + __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
-                        key = ((uint32_t)pc + kKeyOffset) << 22 | (uint32_t)(gr - r0);
-                    }
-                    S.base[n & 3][pt] = key;
+                    *(uint4 *)(S.b[bi] + tile_off(row, chunk16)) = unpack16(bits[pass]);
                 }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.b_full[bi]);
+                if (kPrefetchB && n + 1 < ntiles) fetch(n + 1);
             }
         } else {
             // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
-            const int ew = warp - 5, quad = warp & 3, half = ew >> 2;  // a warp reads the TMEM lanes of quadrant warp % 4
+            const int ew = warp - 5, quad = warp & 3, part = ew >> 2;  // a warp reads the TMEM lanes of quadrant warp % 4
             const int row = quad * 32 + lane;                           // query row inside each M-tile
             uint32_t k0[4], k1[4];
+            int thr[4];
 #pragma unroll
-            for (int t = 0; t < 4; t++) k0[t] = k1[t] = kNoKey32;
+            for (int t = 0; t < 4; t++) {
+                k0[t] = k1[t] = kNoKey32;
+                thr[t] = (int)(kNoKey32 >> 22) - kKeyOffset;
+            }
+            const uint32_t chunk_n = (uint32_t)(r1 - r0), lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * kColsPerWarp);
             for (int n = 0; n < ntiles; n++) {
+                const uint32_t idx0 = (uint32_t)n * kTileN + (uint32_t)(part * kColsPerWarp);
+#pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const int st = h;
                     mbar_wait(&S.d_full[st], (ph_d_full >> st) & 1);
                     ph_d_full ^= 1u << st;
                     tc_fence_after();
+                    // this warp's columns of the stage's two tiles, 32 at a time, the next load in flight while one is examined; the
+                    // stage goes back to the MMA issuer as soon as the last load has landed
+                    constexpr int L = 2 * kLoadsPerTile;
+                    int buf[2][32];
+                    tmem_ld32_issue(lane_addr + (uint32_t)(st * 256), buf[0]);
 #pragma unroll
-                    for (int t = 0; t < 2; t++) {
-                        // this warp's half of the tile's 128 columns: two loads of 32 columns
-#pragma unroll
-                        for (int c = 0; c < 2; c++) {
-                            const int col = half * 64 + c * 32;
-                            uint32_t v[32];
-                            tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * 256 + t * 128 + col), v);
-                            const uint4 *bk = (const uint4 *)&S.base[n & 3][col];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const uint4 b4 = bk[j];  // broadcast read: every lane takes the same four base keys
-                                // rows past the end carry base 0xFFFFFFFF and a zero dot product: they stay 0xFFFFFFFF
-                                top2_pair(k0[2 * h + t], k1[2 * h + t], b4.x - (v[4 * j] << 23), b4.y - (v[4 * j + 1] << 23));
-                                top2_pair(k0[2 * h + t], k1[2 * h + t], b4.z - (v[4 * j + 2] << 23), b4.w - (v[4 * j + 3] << 23));
-                            }
+                    for (int i = 0; i < L; i++) {
+                        const int t = i / kLoadsPerTile, c = i % kLoadsPerTile;
+                        tmem_ld_wait(buf[i & 1]);
+                        if (i + 1 < L) {
+                            const int t2 = (i + 1) / kLoadsPerTile, c2 = (i + 1) % kLoadsPerTile;
+                            tmem_ld32_issue(lane_addr + (uint32_t)(st * 256 + t2 * 128 + c2 * 32), buf[(i + 1) & 1]);
+                        } else {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&S.d_empty[st]);
                         }
+                        examine32(buf[i & 1], k0[2 * h + t], k1[2 * h + t], thr[2 * h + t], idx0 + 32 * c, chunk_n);
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&S.d_empty[st]);
                 }
             }
-            // the two warps of a quadrant hold disjoint columns: merge through shared memory, then write the chunk's keys
-            if (half == 1) {
+            // the four warps of a quadrant hold disjoint columns: merge through shared memory, then write the chunk's keys
+            if (part > 0) {
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    S.merge[t][row][0] = k0[t];
-                    S.merge[t][row][1] = k1[t];
+                    S.merge[part - 1][t][row][0] = k0[t];
+                    S.merge[part - 1][t][row][1] = k1[t];
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-            if (half == 0) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the epilogue warps only
+            if (part == 0) {
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    top2_pair(k0[t], k1[t], S.merge[t][row][0], S.merge[t][row][1]);
+#pragma unroll
+                    for (int p2 = 0; p2 + 1 < kParts; p2++) top2_pair(k0[t], k1[t], S.merge[p2][t][row][0], S.merge[p2][t][row][1]);
                     const int qi = q0 + t * 128 + row;
                     if (qi < q) {
                         const uint4 *p = (const uint4 *)(queries + (size_t)qi * 32);
@@ -265,16 +331,16 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
 #pragma unroll
                         for (int r = 0; r < 2; r++) {
                             if (kk[r] == kNoKey32) { o[r] = ~0ull; continue; }
-                            const unsigned long long dist = (unsigned long long)((kk[r] >> 22) - kKeyOffset + (uint32_t)pa);
+                            const unsigned long long dist = (unsigned long long)((int)(kk[r] >> 22) - kKeyOffset + pa);  // D' + |a|
                             o[r] = dist << 32 | (unsigned long long)(idx_base + r0 + (long long)(kk[r] & 0x3FFFFFu));
                         }
-                        unsigned long long *dst = part + ((size_t)chunk * q + qi) * 2;
+                        unsigned long long *dst = part_out + ((size_t)chunk * q + qi) * 2;
                         dst[0] = o[0];
                         dst[1] = o[1];
                     }
                 }
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");  // merge[] is free for the next item
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // merge[] is free for the next item
         }
     }
     tc_fence_before();
