@@ -713,6 +713,26 @@ def test_knn2_vs_oracle_and_sharded_merge(gpu, oracle):
         assert np.array_equal(out.download((Q, 4), np.int32), ref), bounds
 
 
+@pytest.mark.parametrize("rows,q", [(1000, 300), (128, 256), (50_001, 512), (50_001, 700), (200_003, 2000), (33, 1300), (3, 257)])
+def test_knn2_tensor_core_kernel_equals_popc_kernel_and_oracle(gpu, oracle, monkeypatch, rows, q):
+    """From 256 queries on, the pair distances come from tcgen05.mma kind::i8 on unpacked descriptor bits (sfe_knn_tc.cu);
+    SFE_KNN_TC=0 keeps the XOR / POPC kernel.  Both must return the oracle's {idx0, dist0, idx1, dist1}: partial query
+    groups, partial row tiles, fewer rows than two, duplicated rows (ties broken by index)."""
+    db = synth.knn_database(rows, seed=11)
+    qs, _ = synth.knn_queries(db, q, seed=12, hard_fraction=0.2)
+    if rows > 300:
+        db[rows - 1] = db[7]
+        qs[1] = db[7]
+    ref = oracle.knn2(qs, db, nthreads=os.cpu_count() or 4)
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SFE_KNN_TC", mode)
+        m = api.Matcher()
+        got = m.knn2(m.create_db(db), qs)
+        assert np.array_equal(got, ref), f"SFE_KNN_TC={mode}: {(got != ref).any(1).sum()} of {q} queries differ"
+    if rows > 300:
+        assert ref[1].tolist() == [7, 0, rows - 1, 0]
+
+
 def test_knn2_baseline_config4_full_size_bit_exact(gpu, oracle):
     """BASELINE config 4 exactly as SURVEY §8d states it: 10 M x 32 B map from default_rng(1234), 2000 queries = map rows
     picked by default_rng(5678) with bit flips (a fifth of them flipped hard enough to FAIL the ratio test), every
