@@ -14,7 +14,7 @@
 //   * 4 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same layout;
 //   * one elected thread issues tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32, 8 per tile pair) into TMEM: two stages of
 //     two 128-column accumulators each fill the 512 columns;
-//   * 8 epilogue warps drain a stage with tcgen05.ld (thread = query row, 32 columns at a time, the next load in flight
+//   * 16 epilogue warps, 8 per TMEM stage, drain their stage with tcgen05.ld (thread = query row, 32 columns at a time, the next load in flight
 //     while the current one is examined): the minimum of 8 accumulators is compared with the query's current second-best
 //     D'; only a group that can still matter is turned into keys ((D' + 512) << 22 | row in chunk) and inserted;
 //   * mbarriers carry the B-tile full / empty and TMEM full / empty hand-offs; tcgen05.commit arrives on them.
@@ -35,8 +35,9 @@ namespace {
 #ifndef SFE_TC_NOINLINE
 #define SFE_TC_NOINLINE 0
 #endif
-constexpr int kEpiWarps = SFE_TC_EPI_WARPS;  // 4 * kParts: kParts warps per TMEM lane quadrant, each on 128 / kParts columns of a tile
-constexpr int kParts = kEpiWarps / 4, kColsPerWarp = 128 / kParts, kLoadsPerTile = kColsPerWarp / 32;
+constexpr int kEpiWarps = SFE_TC_EPI_WARPS;  // half of them drain TMEM stage 0 (query tiles 0, 1), the other half stage 1 (tiles 2, 3):
+                                             // a stage's warps examine their registers while the other stage's warps wait for theirs
+constexpr int kParts = kEpiWarps / 8, kColsPerWarp = 128 / kParts, kLoadsPerTile = kColsPerWarp / 32;  // kParts warps per quadrant and stage
 constexpr int kTcThreads = (5 + kEpiWarps) * 32;  // warp 0: MMA issuer, warps 1-4: producers, warps 5-20: epilogue
 constexpr int kGroupQ = 512;                 // queries per work item: 4 M-tiles of 128
 constexpr int kTileN = 128;                  // database rows per B tile
@@ -163,7 +164,7 @@ struct TcSmem {
     uint8_t b[2][kTileBytes];      // database tiles, double buffered
     uint64_t b_full[2], b_empty[2], d_full[2], d_empty[2];
     uint32_t tmem_base;
-    uint32_t merge[kParts > 1 ? kParts - 1 : 1][4][128][2];  // the epilogue warps of column parts 1.. hand their pairs to the warp of part 0
+    uint32_t merge[kParts > 1 ? kParts - 1 : 1][4][128][2];  // the epilogue warps of column parts 1.. hand their pairs to the warp of part 0 (per query tile)
 };
 
 }  // namespace
@@ -185,7 +186,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
             mbar_init(&S.b_full[i], 4);   // one arrival per producer warp
             mbar_init(&S.b_empty[i], 1);  // tcgen05.commit
             mbar_init(&S.d_full[i], 1);   // tcgen05.commit
-            mbar_init(&S.d_empty[i], kEpiWarps);  // one arrival per epilogue warp
+            mbar_init(&S.d_empty[i], kEpiWarps / 2);  // one arrival per epilogue warp of the stage
         }
     }
     tc_fence_before();
@@ -268,60 +269,61 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
             }
         } else {
             // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
-            const int ew = warp - 5, quad = warp & 3, part = ew >> 2;  // a warp reads the TMEM lanes of quadrant warp % 4
-            const int row = quad * 32 + lane;                           // query row inside each M-tile
-            uint32_t k0[4], k1[4];
-            int thr[4];
+            const int ew = warp - 5, quad = warp & 3;  // a warp reads the TMEM lanes of quadrant warp % 4
+            const int st = ew / (kEpiWarps / 2);        // the stage this warp serves = the pair of query tiles 2 st, 2 st + 1
+            const int part = (ew % (kEpiWarps / 2)) >> 2;
+            const int row = quad * 32 + lane;           // query row inside each M-tile
+            uint32_t k0[2], k1[2];
+            int thr[2];
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
+            for (int t = 0; t < 2; t++) {
                 k0[t] = k1[t] = kNoKey32;
                 thr[t] = (int)(kNoKey32 >> 22) - kKeyOffset;
             }
-            const uint32_t chunk_n = (uint32_t)(r1 - r0), lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * kColsPerWarp);
+            const uint32_t chunk_n = (uint32_t)(r1 - r0);
+            const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * 256 + part * kColsPerWarp);
+            uint32_t ph_full = (ph_d_full >> st) & 1;
             for (int n = 0; n < ntiles; n++) {
                 const uint32_t idx0 = (uint32_t)n * kTileN + (uint32_t)(part * kColsPerWarp);
+                mbar_wait(&S.d_full[st], ph_full);
+                ph_full ^= 1;
+                tc_fence_after();
+                // this warp's columns of the stage's two tiles, 32 at a time, the next load in flight while one is examined; the
+                // stage goes back to the MMA issuer as soon as the last load has landed
+                constexpr int L = 2 * kLoadsPerTile;
+                int buf[2][32];
+                tmem_ld32_issue(lane_addr, buf[0]);
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const int st = h;
-                    mbar_wait(&S.d_full[st], (ph_d_full >> st) & 1);
-                    ph_d_full ^= 1u << st;
-                    tc_fence_after();
-                    // this warp's columns of the stage's two tiles, 32 at a time, the next load in flight while one is examined; the
-                    // stage goes back to the MMA issuer as soon as the last load has landed
-                    constexpr int L = 2 * kLoadsPerTile;
-                    int buf[2][32];
-                    tmem_ld32_issue(lane_addr + (uint32_t)(st * 256), buf[0]);
-#pragma unroll
-                    for (int i = 0; i < L; i++) {
-                        const int t = i / kLoadsPerTile, c = i % kLoadsPerTile;
-                        tmem_ld_wait(buf[i & 1]);
-                        if (i + 1 < L) {
-                            const int t2 = (i + 1) / kLoadsPerTile, c2 = (i + 1) % kLoadsPerTile;
-                            tmem_ld32_issue(lane_addr + (uint32_t)(st * 256 + t2 * 128 + c2 * 32), buf[(i + 1) & 1]);
-                        } else {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&S.d_empty[st]);
-                        }
-                        examine32(buf[i & 1], k0[2 * h + t], k1[2 * h + t], thr[2 * h + t], idx0 + 32 * c, chunk_n);
+                for (int i = 0; i < L; i++) {
+                    const int t = i / kLoadsPerTile, c = i % kLoadsPerTile;
+                    tmem_ld_wait(buf[i & 1]);
+                    if (i + 1 < L) {
+                        const int t2 = (i + 1) / kLoadsPerTile, c2 = (i + 1) % kLoadsPerTile;
+                        tmem_ld32_issue(lane_addr + (uint32_t)(t2 * 128 + c2 * 32), buf[(i + 1) & 1]);
+                    } else {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&S.d_empty[st]);
                     }
+                    examine32(buf[i & 1], k0[t], k1[t], thr[t], idx0 + 32 * c, chunk_n);
                 }
             }
-            // the four warps of a quadrant hold disjoint columns: merge through shared memory, then write the chunk's keys
+            ph_d_full = (ph_d_full & ~(1u << st)) | ph_full << st;
+            // the warps of a quadrant and stage hold disjoint columns: merge through shared memory, then write the chunk's keys
             if (part > 0) {
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    S.merge[part - 1][t][row][0] = k0[t];
-                    S.merge[part - 1][t][row][1] = k1[t];
+                for (int t = 0; t < 2; t++) {
+                    S.merge[part - 1][2 * st + t][row][0] = k0[t];
+                    S.merge[part - 1][2 * st + t][row][1] = k1[t];
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the epilogue warps only
             if (part == 0) {
 #pragma unroll
-                for (int t = 0; t < 4; t++) {
+                for (int t = 0; t < 2; t++) {
 #pragma unroll
-                    for (int p2 = 0; p2 + 1 < kParts; p2++) top2_pair(k0[t], k1[t], S.merge[p2][t][row][0], S.merge[p2][t][row][1]);
-                    const int qi = q0 + t * 128 + row;
+                    for (int p2 = 0; p2 + 1 < kParts; p2++) top2_pair(k0[t], k1[t], S.merge[p2][2 * st + t][row][0], S.merge[p2][2 * st + t][row][1]);
+                    const int qi = q0 + (2 * st + t) * 128 + row;
                     if (qi < q) {
                         const uint4 *p = (const uint4 *)(queries + (size_t)qi * 32);
                         const uint4 u = __ldg(p), w = __ldg(p + 1);
