@@ -778,11 +778,11 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
 // this is the plain launch, with fewer CTAs (SFE_OCTREE_CTAS) the kernel is persistent and leaves shared memory to a
 // kernel running beside it.
 template <bool kWide>
-__global__ void __launch_bounds__(1024) octree_kernel(ImgSet S, int count, int smem_cand, int max_cand, int max_nodes,
+__global__ void __launch_bounds__(1024) octree_kernel(ImgSet S, int count, int level0, int level_n, int smem_cand, int max_cand, int max_nodes,
                                                      uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
-    const int items = S.nlevels * count;
+    const int items = level_n * count;  // levels [level0, level0 + level_n)
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
-        octree_item<kWide>(S, w / count, w % count, smem_cand, max_cand, max_nodes, scratch, scratch_slots, scratch_next);
+        octree_item<kWide>(S, level0 + w / count, w % count, smem_cand, max_cand, max_nodes, scratch, scratch_slots, scratch_next);
         __syncthreads();  // the next item reuses the shared arrays
     }
 }
@@ -1209,8 +1209,11 @@ struct sfe_extractor {
     cudaStream_t extra[kComputeStreams - 1] = {};   // further compute streams: sub-batch c runs on stream c % n_compute, so the
                                                     // kernels of one sub-batch fill the tail waves / latency-bound stages of others
     int n_compute = 3;                              // SFE_COMPUTE_STREAMS
-    cudaStream_t aux[2] = {nullptr, nullptr};       // per compute stream: the blur runs beside FAST + quadtree
-    cudaEvent_t ev_fork[2] = {}, ev_join[2] = {};
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // [0] the blur beside FAST + quadtree, [1] the matchers of an asynchronous call beside the next
+                                                        // call, [2] FAST + quadtree of levels 0-1 of a few-image call beside the rest of the pyramid
+    cudaEvent_t ev_fork[3] = {}, ev_join[3] = {};
+    bool split_small = false;                       // SFE_SPLIT_SMALL=1: few-image calls run FAST + quadtree of levels 0-1 beside the pyramid tail
+                                                    // (measured: no gain, 195 vs 198 us per stereo pair)
     int octree_ctas = 0;    // SFE_OCTREE_CTAS: > 0 = persistent quadtree kernel with that many CTAs
     int sm_count = 148;
     bool piped_now = false; // a pipelined host call is enqueueing its sub-batches
@@ -1244,6 +1247,7 @@ struct sfe_extractor {
     size_t l0_geom[4] = {0, 0, 0, 0};
     int pitch0 = 0;       // row pitch of the host-path staging buffer
     std::vector<SegRec> segs;
+    int seg_level_start[kMaxLevels + 1] = {};  // segments are stored level by level: level l = [start[l], start[l + 1])
     DevBuf<SegRec> d_segs;
     size_t fast_smem = 0, pyr_smem = 0;
     int pyr_wide_h[kMaxLevels] = {};
@@ -1415,6 +1419,7 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
             }
         }
         ex->fast.n_cells += n_level_cells;
+        ex->seg_level_start[l + 1] = (int)ex->segs.size();
         // quadtree roots
         L.n_ini = 1;
         L.hx = 1.f;
@@ -1644,8 +1649,11 @@ static void prepare_l0_maps(sfe_extractor *ex, const uint8_t *a, const uint8_t *
 
 constexpr bool kFastTma = true;
 
-static int launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count) {
-    const dim3 grid((unsigned)ex->fast.n_segs, count);
+static int launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count, int level0 = 0, int level1 = kMaxLevels) {
+    level1 = std::min(level1, ex->prm.nlevels);
+    const int seg0 = ex->seg_level_start[level0], nseg = ex->seg_level_start[level1] - seg0;  // the segments of levels [level0, level1)
+    if (nseg <= 0) return SFE_OK;
+    const dim3 grid((unsigned)nseg, count);
     if (ex->fast_smem > 48 * 1024) {  // the opt-in shared-memory limit is a per-function attribute: only ever raise it
         static std::mutex mu;
         static size_t granted[64] = {};
@@ -1664,11 +1672,13 @@ static int launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int 
         });
     }
     if (ex->tma_now && kFastTma)
-        fast_segments_kernel<true><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p, ex->fast_maps);
+        fast_segments_kernel<true><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p + seg0, ex->fast_maps);
     else
-        fast_segments_kernel<false><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p, ex->fast_maps);
+        fast_segments_kernel<false><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p + seg0, ex->fast_maps);
     return SFE_OK;
 }
+
+constexpr int kSplitMaxImages = 4;  // calls with at most this many images run levels 0-1 beside the rest of the pyramid
 
 // Order the handle's main stream behind a matching tail still running on the side stream.
 static int join_tail(sfe_extractor *ex) {
@@ -1682,7 +1692,7 @@ static int join_tail(sfe_extractor *ex) {
 static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int count, const OutSet &O) {
     const int nl = ex->prm.nlevels;
     prof_mark(ex, 0);
-    for (int l = 1; l < nl; l++) {
+    auto launch_pyr = [&](int l) {  // level l from level l - 1
         const LevelPlan &D = ex->lv[l], &Q = ex->lv[l - 1];
         const PyrStep P{D.w, D.h, D.pitch, D.plane_off, Q.w, l == 1 ? S.in_pitch : Q.pitch, Q.plane_off, l == 1, D.xtab_off, D.ytab_off,
                         l - 1, ex->pyr_box_w, ex->pyr_box_h, ex->pyr_wide_h[l]};
@@ -1692,66 +1702,111 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         else
             pyr_resize_kernel<false><<<grid, 256, ex->pyr_smem, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p, ex->pyr_maps);
         ex->launches++;
+    };
+    const bool has_cells = ex->fast.n_cells > 0;
+    {   // every kernel of the sequence asks for the same (largest) shared-memory carve-out as FAST: kernels that want different
+        // L1 / shared splits cannot share an SM, which serialised the branches of a few-image call
+        static std::once_flag once[64];
+        std::call_once(once[ex->device & 63], [] {
+            const void *fns[] = {(const void *)pyr_resize_kernel<true>, (const void *)pyr_resize_kernel<false>, (const void *)blur_kernel<true>,
+                                 (const void *)blur_kernel<false>, (const void *)octree_kernel<true>, (const void *)octree_kernel<false>,
+                                 (const void *)orient_describe_kernel<true>, (const void *)orient_describe_kernel<false>,
+                                 (const void *)realign_kernel};
+            for (const void *f : fns) cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        });
     }
-    prof_mark(ex, 1);
-    if (ex->fast.n_cells > 0) {
-        // The blur only needs the pyramid, so it runs on a side stream beside the quadtree (which is latency-bound: 35 %
-        // issue-active) and joins before the descriptors.  Serial when stages are timed and on the pipelined host path,
-        // whose sub-batches already overlap across compute streams.
-        const int si = 0;
-        const bool fork = ex->overlap_blur && !ex->profiling && !ex->piped_now && st == ex->stream, late = ex->overlap_blur == 2;
-        cudaStream_t sb = fork ? ex->aux[si] : st;
-        auto launch_blur = [&]() {
-            if (ex->tma_now)
-                blur_kernel<true><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
-            else
-                blur_kernel<false><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
-        };
-        auto fork_blur = [&]() -> int {
-            SFE_CUDA(cudaEventRecord(ex->ev_fork[si], st));
-            SFE_CUDA(cudaStreamWaitEvent(sb, ex->ev_fork[si], 0));
-            launch_blur();
-            SFE_CUDA(cudaEventRecord(ex->ev_join[si], sb));
-            return SFE_OK;
-        };
-        if (fork && !late)
-            if (int rc = fork_blur()) return rc;
-        if (int rc = launch_fast(ex, st, S, count)) return rc;
-        prof_mark(ex, 2);
-        if (fork && late)
-            if (int rc = fork_blur()) return rc;
-        {   // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
-            static std::mutex mu;
-            static size_t granted[64] = {};
-            std::lock_guard<std::mutex> lock(mu);
-            if (ex->octree_smem > granted[ex->device & 63]) {
-                SFE_CUDA(cudaFuncSetAttribute(octree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
-                SFE_CUDA(cudaFuncSetAttribute(octree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
-                granted[ex->device & 63] = ex->octree_smem;
-            }
+    if (has_cells) {  // the opt-in shared-memory limit is a per-function (not per-handle) attribute: only ever raise it
+        static std::mutex mu;
+        static size_t granted[64] = {};
+        std::lock_guard<std::mutex> lock(mu);
+        if (ex->octree_smem > granted[ex->device & 63]) {
+            SFE_CUDA(cudaFuncSetAttribute(octree_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
+            SFE_CUDA(cudaFuncSetAttribute(octree_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ex->octree_smem));
+            granted[ex->device & 63] = ex->octree_smem;
         }
-        // beside the forked blur the quadtree runs persistent with 2 CTAs per SM: its ~60 KB of shared memory per CTA would
-        // otherwise leave the blur one CTA per SM (measured: 2.12 -> 2.06 ms per 128-frame step; alone, fewer CTAs are slower)
-        const int oct_items = nl * count;
-        const int oct_ctas = ex->octree_ctas > 0 ? ex->octree_ctas : (fork && late ? 2 * ex->sm_count : 0);
-        const int oct_grid = oct_ctas > 0 ? std::min(oct_items, oct_ctas) : oct_items;
-        int *scratch_next = ex->d_counts.p + (size_t)ex->max_images * nl * 2;
+    }
+    int *scratch_next = ex->d_counts.p + (size_t)ex->max_images * nl * 2;
+    auto launch_octree = [&](cudaStream_t so, int level0, int level_n, int ctas) {
+        const int items = level_n * count;
+        const int grid = ctas > 0 ? std::min(items, ctas) : items;
         // a call with few images cannot fill the machine with (level, image) items: their latency is what counts, and a
-        // 1024-thread CTA walks a level's candidates in a quarter of the iterations (38.6 -> measured in DESIGN.md §6)
-        const int oct_threads = oct_items <= ex->sm_count / 2 ? 1024 : 256;
+        // 1024-thread CTA walks a level's candidates in a quarter of the iterations
+        const int threads = nl * count <= ex->sm_count / 2 ? 1024 : 256;
         if (ex->octree_wide)
-            octree_kernel<true><<<oct_grid, oct_threads, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
-                                                                               ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
+            octree_kernel<true><<<grid, threads, ex->octree_smem, so>>>(S, count, level0, level_n, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
+                                                                       ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
         else
-            octree_kernel<false><<<oct_grid, oct_threads, ex->octree_smem, st>>>(S, count, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
-                                                                                ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
-        prof_mark(ex, 3);
-        if (fork) SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[si], 0));
-        else launch_blur();
-        prof_mark(ex, 4);
+            octree_kernel<false><<<grid, threads, ex->octree_smem, so>>>(S, count, level0, level_n, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
+                                                                        ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
+        ex->launches++;
+    };
+    const bool fork_ok = !ex->profiling && !ex->piped_now && st == ex->stream;
+    // Few images (the reference-shaped single call): the chain pyramid -> FAST -> quadtree is pure latency, and its longest link is
+    // the quadtree of level 0.  Levels 0 and 1 only need the first pyramid launch, so their FAST + quadtree run on a side stream
+    // beside the rest of the pyramid, the FAST + quadtree of the small levels and the blur.
+    const bool split = fork_ok && has_cells && ex->split_small && count <= kSplitMaxImages && nl >= 3;
+    if (split) {
+        launch_pyr(1);
+        cudaStream_t sa = ex->aux[2];
+        SFE_CUDA(cudaEventRecord(ex->ev_fork[2], st));
+        SFE_CUDA(cudaStreamWaitEvent(sa, ex->ev_fork[2], 0));
+        if (int rc = launch_fast(ex, sa, S, count, 0, 2)) return rc;
+        launch_octree(sa, 0, 2, 0);
+        SFE_CUDA(cudaEventRecord(ex->ev_join[2], sa));
+        for (int l = 2; l < nl; l++) launch_pyr(l);
+        cudaStream_t sb = ex->aux[0];
+        SFE_CUDA(cudaEventRecord(ex->ev_fork[0], st));
+        SFE_CUDA(cudaStreamWaitEvent(sb, ex->ev_fork[0], 0));
+        if (ex->tma_now)
+            blur_kernel<true><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
+        else
+            blur_kernel<false><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
+        SFE_CUDA(cudaEventRecord(ex->ev_join[0], sb));
+        if (int rc = launch_fast(ex, st, S, count, 2, nl)) return rc;
+        launch_octree(st, 2, nl - 2, 0);
+        SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[2], 0));
+        SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[0], 0));
         ex->launches += 3;
     } else {
-        prof_mark(ex, 2); prof_mark(ex, 3); prof_mark(ex, 4);
+        for (int l = 1; l < nl; l++) launch_pyr(l);
+        prof_mark(ex, 1);
+        if (has_cells) {
+            // The blur only needs the pyramid, so it runs on a side stream beside the quadtree (which is latency-bound: 35 %
+            // issue-active) and joins before the descriptors.  Serial when stages are timed and on the pipelined host path,
+            // whose sub-batches already overlap across compute streams.
+            const int si = 0;
+            const bool fork = ex->overlap_blur && fork_ok, late = ex->overlap_blur == 2;
+            cudaStream_t sb = fork ? ex->aux[si] : st;
+            auto launch_blur = [&]() {
+                if (ex->tma_now)
+                    blur_kernel<true><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
+                else
+                    blur_kernel<false><<<dim3((unsigned)ex->tiles.size(), count), 256, 0, sb>>>(S, ex->d_tiles.p, ex->blur_maps);
+            };
+            auto fork_blur = [&]() -> int {
+                SFE_CUDA(cudaEventRecord(ex->ev_fork[si], st));
+                SFE_CUDA(cudaStreamWaitEvent(sb, ex->ev_fork[si], 0));
+                launch_blur();
+                SFE_CUDA(cudaEventRecord(ex->ev_join[si], sb));
+                return SFE_OK;
+            };
+            if (fork && !late)
+                if (int rc = fork_blur()) return rc;
+            if (int rc = launch_fast(ex, st, S, count)) return rc;
+            prof_mark(ex, 2);
+            if (fork && late)
+                if (int rc = fork_blur()) return rc;
+            // beside the forked blur the quadtree runs persistent with 2 CTAs per SM: its ~60 KB of shared memory per CTA would
+            // otherwise leave the blur one CTA per SM (measured: 2.12 -> 2.06 ms per 128-frame step; alone, fewer CTAs are slower)
+            launch_octree(st, 0, nl, ex->octree_ctas > 0 ? ex->octree_ctas : (fork && late ? 2 * ex->sm_count : 0));
+            prof_mark(ex, 3);
+            if (fork) SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[si], 0));
+            else launch_blur();
+            prof_mark(ex, 4);
+            ex->launches += 2;
+        } else {
+            prof_mark(ex, 2); prof_mark(ex, 3); prof_mark(ex, 4);
+        }
     }
     if (st == ex->stream) {  // the previous call's matchers may still be reading the output arrays this kernel writes
         if (int rc = join_tail(ex)) return rc;
@@ -2128,7 +2183,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
               cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ex->ev_start, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < kComputeStreams - 1 && ok; i++) ok = cudaStreamCreateWithFlags(&ex->extra[i], cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; i < 2 && ok; i++)
+    for (int i = 0; i < 3 && ok; i++)
         ok = cudaStreamCreateWithFlags(&ex->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&ex->ev_fork[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ex->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
@@ -2154,6 +2209,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_OCTREE_SMEM_CAND")) ex->octree_cand_override = atoi(env);
     if (const char *env = getenv("SFE_CAND_CAP")) ex->cand_cap_override = std::max(8, atoi(env));
     if (const char *env = getenv("SFE_GRAPHS")) ex->use_graphs = atoi(env) != 0;
+    if (const char *env = getenv("SFE_SPLIT_SMALL")) ex->split_small = atoi(env) != 0;
     build_tables(ex);
     *out = ex;
     return SFE_OK;
@@ -2178,7 +2234,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     }
     for (auto &e : ex->tr_ev)
         if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 3; i++) {
         if (ex->ev_fork[i]) cudaEventDestroy(ex->ev_fork[i]);
         if (ex->ev_join[i]) cudaEventDestroy(ex->ev_join[i]);
         if (ex->aux[i]) cudaStreamDestroy(ex->aux[i]);
