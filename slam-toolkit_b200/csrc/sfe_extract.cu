@@ -1212,6 +1212,7 @@ struct sfe_extractor {
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // [0] the blur beside FAST + quadtree, [1] the matchers of an asynchronous call beside the next
                                                         // call, [2] FAST + quadtree of levels 0-1 of a few-image call beside the rest of the pyramid
     cudaEvent_t ev_fork[3] = {}, ev_join[3] = {};
+    int dev_split = 1;                              // SFE_DEV_SPLIT=n: a resident stereo batch runs as n sub-batches on n streams
     bool split_small = false;                       // SFE_SPLIT_SMALL=1: few-image calls run FAST + quadtree of levels 0-1 beside the pyramid tail
                                                     // (measured: no gain, 195 vs 198 us per stereo pair)
     int octree_ctas = 0;    // SFE_OCTREE_CTAS: > 0 = persistent quadtree kernel with that many CTAs
@@ -2210,6 +2211,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_CAND_CAP")) ex->cand_cap_override = std::max(8, atoi(env));
     if (const char *env = getenv("SFE_GRAPHS")) ex->use_graphs = atoi(env) != 0;
     if (const char *env = getenv("SFE_SPLIT_SMALL")) ex->split_small = atoi(env) != 0;
+    if (const char *env = getenv("SFE_DEV_SPLIT")) ex->dev_split = std::max(1, std::min(atoi(env), kComputeStreams));
     build_tables(ex);
     *out = ex;
     return SFE_OK;
@@ -2360,7 +2362,22 @@ static int stereo_frames_dev_once(sfe_extractor *ex, const uint8_t *left_dev, co
     const ImgSet S = make_imgset(ex, left_dev, right_dev, frames, image_stride, stride);
     prepare_l0_maps(ex, left_dev, right_dev, frames, frames, image_stride, stride);
     if ((rc = reset_counters(ex)) != SFE_OK) return rc;
-    if ((rc = enqueue_extract(ex, ex->stream, S, 2 * frames, O)) != SFE_OK) return rc;
+    const int nsplit = !ex->profiling && frames >= 16 * ex->dev_split ? std::min(ex->dev_split, ex->n_compute) : 1;
+    if (nsplit <= 1) {
+        if ((rc = enqueue_extract(ex, ex->stream, S, 2 * frames, O)) != SFE_OK) return rc;
+    } else {
+        // A large resident batch runs as nsplit sub-batches on as many streams: while one is in a latency-bound stage (quadtree,
+        // the tail of a launch) the issue slots it leaves idle go to the FAST / blur / descriptor kernels of another.
+        SFE_CUDA(cudaEventRecord(ex->ev_start, ex->stream));  // the counter reset precedes every sub-batch
+        for (int c = 1; c < nsplit; c++) SFE_CUDA(cudaStreamWaitEvent(ex->extra[c - 1], ex->ev_start, 0));
+        for (int c = 0; c < nsplit; c++) {
+            const int f0 = (int)((long long)frames * c / nsplit), f1 = (int)((long long)frames * (c + 1) / nsplit);
+            cudaStream_t sc = c == 0 ? ex->stream : ex->extra[c - 1];
+            if ((rc = enqueue_extract(ex, sc, chunk_of(S, f0, f1, true), 2 * (f1 - f0), chunk_of(O, f0))) != SFE_OK) return rc;
+            if (c > 0) SFE_CUDA(cudaEventRecord(ex->ev_done[c], sc));
+        }
+        for (int c = 1; c < nsplit; c++) SFE_CUDA(cudaStreamWaitEvent(ex->stream, ex->ev_done[c], 0));
+    }
     // asynchronous calls: the matchers are small latency-bound kernels, so they go to a side stream and run beside the
     // next call's pyramid and FAST kernels
     const bool tail = ex->async_dev && ex->overlap_tail && !ex->profiling;

@@ -899,3 +899,17 @@ def test_bow_transform_vs_oracle(gpu, oracle, kitti_ex):
         assert abs(vals.sum() - 1.0) < 1e-12 and sorted(fv) == list(fv)
         assert sum(len(v) for v in fv.values()) == int((rw > 0).sum())
     assert voc.transform_features(feats[:0])[0].shape == (0,)
+
+
+def test_copy_probe_and_write_combined_pages(gpu):
+    """sfe_copy_probe (the e2e ceiling bench.py prints) and sfe_host_alloc_ex: sane rates, and a write-combined input buffer
+    feeds the host entry point with the same results as an ordinary pinned one"""
+    up, down = api.copy_probe(0, 8 << 20, 2 << 20, chunks=4, seconds=0.05)
+    assert 1.0 < up < 200.0 and 0.5 < down < 200.0
+    L, R = synth.stereo_pair(6)
+    ex = api.ORBextractor(max_images=2)
+    a, b = api.PinnedArray(L.shape, np.uint8), api.PinnedArray(L.shape, np.uint8, write_combined=True)
+    a.array[:], b.array[:] = L, L
+    k0, d0 = ex.extract(a.array)
+    k1, d1 = ex.extract(b.array)
+    assert np.array_equal(k0, k1) and np.array_equal(d0, d1) and len(k0) > 1900
