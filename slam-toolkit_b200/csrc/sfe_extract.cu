@@ -1006,7 +1006,10 @@ constexpr bool pattern_within_patch() {
     return true;
 }
 static_assert(pattern_within_patch(), "a rotated pattern point could round outside the staged window");
-constexpr int kKpPerWarp = 4;  // keypoints one warp handles in turn: the pattern / disc table set-up is paid once
+#ifndef SFE_KP_PER_WARP
+#define SFE_KP_PER_WARP 8
+#endif
+constexpr int kKpPerWarp = SFE_KP_PER_WARP;  // keypoints one warp handles in turn: the pattern / disc table set-up is paid once
 
 // kTma: both windows of a keypoint -- the 31 rows x 48 bytes of the unblurred level around it for IC_Angle and the 37 rows x
 // 64 bytes of the blurred level for rBRIEF, each starting on the 16-byte grid of its row -- arrive by two TMA boxes issued by
@@ -1020,7 +1023,7 @@ struct OrientMaps {
 
 template <bool kTma>
 __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSet O, const __grid_constant__ OrientMaps M) {
-    __shared__ __half2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane` (|x|, |y| <= 13: exact in fp16)
+    __shared__ float2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane` (floats: no conversion in the loop)
     __shared__ __align__(128) uint8_t win_all[8][kTma ? kWinBytes : kPatchRows * kPatchWords * 4];  // per warp: the windows
     __shared__ uint64_t bars[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y, slot = slot_of(S, img);
@@ -1029,7 +1032,7 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
     if (kTma && lane == 0) mbar_init(&bars[warp], 1);
     for (int i = tid; i < 512; i += 256) {
         const int byte = i >> 4, s = i & 15;
-        pat[s * 32 + byte] = __floats2half2_rn((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
+        pat[s * 32 + byte] = make_float2((float)g_pattern[2 * i], (float)g_pattern[2 * i + 1]);
     }
     // IC_Angle: the 31 x 32-byte window is 31 rows x 8 words; lane = word (lane & 7) of the rows ic_row(t), t = 0..7: step t
     // covers rows b, b + 2, b + 4, b + 6 with b = 8 (t / 2) + t % 2, so one warp-wide load touches 4 rows (4-8 cache
@@ -1163,7 +1166,7 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
             int tv[2];
 #pragma unroll
             for (int s = 0; s < 2; s++) {
-                const float2 pp = __half22float2(pat[(2 * k + s) * 32 + lane]);
+                const float2 pp = pat[(2 * k + s) * 32 + lane];
                 const int ry = __float2int_rn(__fadd_rn(__fmul_rn(pp.x, b), __fmul_rn(pp.y, a)));
                 const int rx = __float2int_rn(__fsub_rn(__fmul_rn(pp.x, a), __fmul_rn(pp.y, b)));
                 tv[s] = pc[ry * wpitch + rx];
