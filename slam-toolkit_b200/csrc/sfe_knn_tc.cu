@@ -29,19 +29,16 @@ namespace sfe {
 
 namespace {
 
-#ifndef SFE_TC_EPI_WARPS
-#define SFE_TC_EPI_WARPS 16
+#ifndef SFE_TC_N
+#define SFE_TC_N 128
 #endif
-#ifndef SFE_TC_NOINLINE
-#define SFE_TC_NOINLINE 0
-#endif
-constexpr int kEpiWarps = SFE_TC_EPI_WARPS;  // half of them drain TMEM stage 0 (query tiles 0, 1), the other half stage 1 (tiles 2, 3):
-                                             // a stage's warps examine their registers while the other stage's warps wait for theirs
-constexpr int kParts = kEpiWarps / 8, kColsPerWarp = 128 / kParts, kLoadsPerTile = kColsPerWarp / 32;  // kParts warps per quadrant and stage
+constexpr int kTileN = SFE_TC_N;              // database rows per B tile = N of one MMA: 128 or 256
+constexpr int kTilesPerStage = 256 / kTileN;  // a TMEM stage is 256 columns: two 128-column accumulators or one of 256
+constexpr int kGroupTiles = 2 * kTilesPerStage, kGroupQ = 128 * kGroupTiles;  // query tiles / queries per work item: 4 / 512 or 2 / 256
+constexpr int kEpiWarps = 16;  // 8 per TMEM stage: one per (lane quadrant, half of the stage's 256 columns); a stage's warps examine
+                               // their registers while the other stage's warps wait for theirs
 constexpr int kTcThreads = (5 + kEpiWarps) * 32;  // warp 0: MMA issuer, warps 1-4: producers, warps 5-20: epilogue
-constexpr int kGroupQ = 512;                 // queries per work item: 4 M-tiles of 128
-constexpr int kTileN = 128;                  // database rows per B tile
-constexpr int kTileBytes = 128 * 256;        // one operand tile: 128 rows x 256 int8
+constexpr int kATileBytes = 128 * 256, kBTileBytes = kTileN * 256;  // operand tiles: rows x 256 int8
 constexpr uint32_t kSBO = 2048, kLBO = 128;  // bytes: between 8-row groups / between 16-byte K chunks
 constexpr int kKeyOffset = 512;              // keeps D' = |b| - 2 dot non-negative in the key (D' >= -256)
 constexpr uint32_t kNoKey32 = 0xFFFFFFFFu;
@@ -67,7 +64,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     return (uint64_t)((addr & 0x3FFFF) >> 4) | (uint64_t)(kLBO >> 4) << 16 | (uint64_t)(kSBO >> 4) << 32 | 1ull << 46;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32, A = B = signed 8-bit, both K-major, N >> 3, M >> 4
-constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTileN >> 3) << 17) | ((128u >> 4) << 24);  // M = 128, N = kTileN
 __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, bool accumulate) {
     asm volatile(
         "{\n"
@@ -129,15 +126,9 @@ __device__ __forceinline__ void top2_one(uint32_t &k0, uint32_t &k1, uint32_t x)
     k0 = min(k0, x);
 }
 
-// 8 accumulators of which at least one can still enter the query's top-2: key and insert the valid ones.  Out of line: it
-// runs for a few percent of the groups, and inlining its 8 copies 16 times over made the epilogue miss the instruction cache
-// (44 % of its stall samples).
-#if SFE_TC_NOINLINE
-__device__ __noinline__
-#else
-__device__ __forceinline__
-#endif
-void insert8(int v0, int v1, int v2, int v3, int v4, int v5, int v6, int v7, uint32_t idx, uint32_t chunk_n,
+// 8 accumulators of which at least one can still enter the query's top-2: key and insert the valid ones (a few percent of
+// the groups; kept inline: out of line, the running top-2 would live in local memory around every call)
+__device__ __forceinline__ void insert8(int v0, int v1, int v2, int v3, int v4, int v5, int v6, int v7, uint32_t idx, uint32_t chunk_n,
                                      uint32_t &k0, uint32_t &k1, int &thr) {
     const int v[8] = {v0, v1, v2, v3, v4, v5, v6, v7};
 #pragma unroll
@@ -160,11 +151,11 @@ __device__ __forceinline__ void examine32(const int (&v)[32], uint32_t &k0, uint
 }
 
 struct TcSmem {
-    uint8_t a[4][kTileBytes];      // query tiles of the group
-    uint8_t b[2][kTileBytes];      // database tiles, double buffered
+    uint8_t a[kGroupTiles][kATileBytes];  // query tiles of the group
+    uint8_t b[2][kBTileBytes];            // database tiles, double buffered
     uint64_t b_full[2], b_empty[2], d_full[2], d_empty[2];
     uint32_t tmem_base;
-    uint32_t merge[kParts > 1 ? kParts - 1 : 1][4][128][2];  // the epilogue warps of column parts 1.. hand their pairs to the warp of part 0 (per query tile)
+    uint32_t merge[2][128][2];            // N = 256: the warp of a tile's upper 128 columns hands its pair to the warp of the lower ones
 };
 
 }  // namespace
@@ -216,15 +207,15 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 mbar_wait(&S.b_full[bi], (ph_b_full >> bi) & 1);
                 ph_b_full ^= 1u << bi;
                 tc_fence_after();
-                for (int h = 0; h < 2; h++) {       // two M-tile pairs per B tile, alternating TMEM stages
+                for (int h = 0; h < 2; h++) {       // the group's query tiles against this B tile, half of them per TMEM stage
                     const int st = h;               // stage h: columns [256 h, 256 h + 256)
                     mbar_wait(&S.d_empty[st], ((ph_d_empty >> st) & 1) ^ 1);  // first use passes: the barrier starts in phase 0
                     ph_d_empty ^= 1u << st;
                     tc_fence_after();
                     if (lane == 0) {
-                        for (int t = 0; t < 2; t++) {
-                            const uint32_t a_addr = smem_u32(S.a[2 * h + t]), b_addr = smem_u32(S.b[bi]);
-                            const uint32_t d = tmem + (uint32_t)(st * 256 + t * 128);
+                        for (int t = 0; t < kTilesPerStage; t++) {
+                            const uint32_t a_addr = smem_u32(S.a[kTilesPerStage * h + t]), b_addr = smem_u32(S.b[bi]);
+                            const uint32_t d = tmem + (uint32_t)(st * 256 + t * kTileN);
 #pragma unroll
                             for (int k = 0; k < 8; k++)  // K = 32 per instruction: two 16-byte chunks
                                 mma_i8(d, smem_desc(a_addr + k * 2 * kLBO), smem_desc(b_addr + k * 2 * kLBO), k > 0);
@@ -238,14 +229,15 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         } else if (warp <= 4) {
             // ===== producers: database rows -> B tile ================================================================
             const int pw = warp - 1, pt = pw * 32 + lane;  // 128 producer threads
-            // thread = 4 rows x 4 chunks of a tile: 16 passes of one 16-byte store each, which a warp lays down as 8 rows x 4 chunks =
+            // thread = kPasses (row, chunk) cells of a tile, one 16-byte store each, which a warp lays down as 8 rows x 4 chunks =
             // 512 contiguous bytes.  The descriptor bits of the NEXT tile are fetched before this one is written, so the global
             // latency never sits between "buffer free" and "buffer full".
-            uint32_t bits[16];
+            constexpr int kPasses = kTileN * 16 / 128;  // 16-byte stores per producer thread and tile
+            uint32_t bits[kPasses];
             auto fetch = [&](int n) {
                 const long long t0 = r0 + (long long)n * kTileN;
 #pragma unroll
-                for (int pass = 0; pass < 16; pass++) {
+                for (int pass = 0; pass < kPasses; pass++) {
                     const int row = (pt & 7) + 8 * ((pt >> 5) + 4 * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
                     const long long gr = t0 + row;
                     bits[pass] = gr < r1 ? __ldg((const uint16_t *)(db + (size_t)gr * 32) + chunk16) : 0u;
@@ -258,7 +250,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 ph_b_empty ^= 1u << bi;
                 if (!kPrefetchB) fetch(n);
 #pragma unroll
-                for (int pass = 0; pass < 16; pass++) {
+                for (int pass = 0; pass < kPasses; pass++) {
                     const int row = (pt & 7) + 8 * ((pt >> 5) + 4 * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
                     *(uint4 *)(S.b[bi] + tile_off(row, chunk16)) = unpack16(bits[pass]);
                 }
@@ -270,76 +262,63 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         } else {
             // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
             const int ew = warp - 5, quad = warp & 3;  // a warp reads the TMEM lanes of quadrant warp % 4
-            const int st = ew / (kEpiWarps / 2);        // the stage this warp serves = the pair of query tiles 2 st, 2 st + 1
-            const int part = (ew % (kEpiWarps / 2)) >> 2;
-            const int row = quad * 32 + lane;           // query row inside each M-tile
-            uint32_t k0[2], k1[2];
-            int thr[2];
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-                k0[t] = k1[t] = kNoKey32;
-                thr[t] = (int)(kNoKey32 >> 22) - kKeyOffset;
-            }
+            const int st = ew >> 3;                     // the stage this warp serves
+            const int half = (ew >> 2) & 1;             // ... and which 128 of its 256 columns
+            const int tile = kTilesPerStage * st + (half * 128) / kTileN;  // the query tile those columns belong to
+            const int col0 = (half * 128) % kTileN;                        // and their first database row inside a B tile
+            const int row = quad * 32 + lane;           // query row inside the tile
+            uint32_t k0 = kNoKey32, k1 = kNoKey32;
+            int thr = (int)(kNoKey32 >> 22) - kKeyOffset;
             const uint32_t chunk_n = (uint32_t)(r1 - r0);
-            const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * 256 + part * kColsPerWarp);
+            const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * 256 + half * 128);
             uint32_t ph_full = (ph_d_full >> st) & 1;
             for (int n = 0; n < ntiles; n++) {
-                const uint32_t idx0 = (uint32_t)n * kTileN + (uint32_t)(part * kColsPerWarp);
+                const uint32_t idx0 = (uint32_t)n * kTileN + (uint32_t)col0;
                 mbar_wait(&S.d_full[st], ph_full);
                 ph_full ^= 1;
                 tc_fence_after();
-                // this warp's columns of the stage's two tiles, 32 at a time, the next load in flight while one is examined; the
-                // stage goes back to the MMA issuer as soon as the last load has landed
-                constexpr int L = 2 * kLoadsPerTile;
+                // 128 columns, 32 at a time, the next load in flight while one is examined; the stage goes back to the MMA
+                // issuer as soon as the last load has landed
                 int buf[2][32];
                 tmem_ld32_issue(lane_addr, buf[0]);
 #pragma unroll
-                for (int i = 0; i < L; i++) {
-                    const int t = i / kLoadsPerTile, c = i % kLoadsPerTile;
+                for (int i = 0; i < 4; i++) {
                     tmem_ld_wait(buf[i & 1]);
-                    if (i + 1 < L) {
-                        const int t2 = (i + 1) / kLoadsPerTile, c2 = (i + 1) % kLoadsPerTile;
-                        tmem_ld32_issue(lane_addr + (uint32_t)(t2 * 128 + c2 * 32), buf[(i + 1) & 1]);
+                    if (i + 1 < 4) {
+                        tmem_ld32_issue(lane_addr + (uint32_t)((i + 1) * 32), buf[(i + 1) & 1]);
                     } else {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&S.d_empty[st]);
                     }
-                    examine32(buf[i & 1], k0[t], k1[t], thr[t], idx0 + 32 * c, chunk_n);
+                    examine32(buf[i & 1], k0, k1, thr, idx0 + 32 * i, chunk_n);
                 }
             }
             ph_d_full = (ph_d_full & ~(1u << st)) | ph_full << st;
-            // the warps of a quadrant and stage hold disjoint columns: merge through shared memory, then write the chunk's keys
-            if (part > 0) {
-#pragma unroll
-                for (int t = 0; t < 2; t++) {
-                    S.merge[part - 1][2 * st + t][row][0] = k0[t];
-                    S.merge[part - 1][2 * st + t][row][1] = k1[t];
-                }
+            // N = 256: two warps hold the halves of one query tile's columns: merge through shared memory
+            if (kTileN == 256 && half == 1) {
+                S.merge[st][row][0] = k0;
+                S.merge[st][row][1] = k1;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the epilogue warps only
-            if (part == 0) {
+            if (kTileN == 128 || half == 0) {
+                if (kTileN == 256) top2_pair(k0, k1, S.merge[st][row][0], S.merge[st][row][1]);
+                const int qi = q0 + tile * 128 + row;
+                if (qi < q) {
+                    const uint4 *p = (const uint4 *)(queries + (size_t)qi * 32);
+                    const uint4 u = __ldg(p), w = __ldg(p + 1);
+                    const int pa = __popc(u.x) + __popc(u.y) + __popc(u.z) + __popc(u.w) + __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+                    unsigned long long o[2];
+                    const uint32_t kk[2] = {k0, k1};
 #pragma unroll
-                for (int t = 0; t < 2; t++) {
-#pragma unroll
-                    for (int p2 = 0; p2 + 1 < kParts; p2++) top2_pair(k0[t], k1[t], S.merge[p2][2 * st + t][row][0], S.merge[p2][2 * st + t][row][1]);
-                    const int qi = q0 + (2 * st + t) * 128 + row;
-                    if (qi < q) {
-                        const uint4 *p = (const uint4 *)(queries + (size_t)qi * 32);
-                        const uint4 u = __ldg(p), w = __ldg(p + 1);
-                        const int pa = __popc(u.x) + __popc(u.y) + __popc(u.z) + __popc(u.w) + __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-                        unsigned long long o[2];
-                        const uint32_t kk[2] = {k0[t], k1[t]};
-#pragma unroll
-                        for (int r = 0; r < 2; r++) {
-                            if (kk[r] == kNoKey32) { o[r] = ~0ull; continue; }
-                            const unsigned long long dist = (unsigned long long)((int)(kk[r] >> 22) - kKeyOffset + pa);  // D' + |a|
-                            o[r] = dist << 32 | (unsigned long long)(idx_base + r0 + (long long)(kk[r] & 0x3FFFFFu));
-                        }
-                        unsigned long long *dst = part_out + ((size_t)chunk * q + qi) * 2;
-                        dst[0] = o[0];
-                        dst[1] = o[1];
+                    for (int r = 0; r < 2; r++) {
+                        if (kk[r] == kNoKey32) { o[r] = ~0ull; continue; }
+                        const unsigned long long dist = (unsigned long long)((int)(kk[r] >> 22) - kKeyOffset + pa);  // D' + |a|
+                        o[r] = dist << 32 | (unsigned long long)(idx_base + r0 + (long long)(kk[r] & 0x3FFFFFu));
                     }
+                    unsigned long long *dst = part_out + ((size_t)chunk * q + qi) * 2;
+                    dst[0] = o[0];
+                    dst[1] = o[1];
                 }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // merge[] is free for the next item
@@ -351,6 +330,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
 }
 
 size_t knn2_tc_smem_bytes() { return sizeof(TcSmem) + 1024; }
+int knn2_tc_group_queries() { return kGroupQ; }  // queries per work item: the caller sizes its chunks with it
 
 // chunks x q x 2 keys into `part`; chunk_rows must be a multiple of 128 and at most 2^22
 cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, long long rows, long long idx_base, int chunk_rows, int chunks,

@@ -1294,6 +1294,7 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
 namespace sfe {
 cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, long long rows, long long idx_base, int chunk_rows, int chunks,
                            const uint8_t *queries, int q, unsigned long long *part);  // sfe_knn_tc.cu
+int knn2_tc_group_queries();
 }
 
 static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, int q, unsigned long long *keys_dev,
@@ -1302,10 +1303,10 @@ static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, i
     if (m->knn_tc && q >= kKnnTcMinQ && db->rows >= 1) {
         // many queries: the pair distances are an int8 GEMM on the tensor cores (sfe_knn_tc.cu), one (512-query group, chunk)
         // item per SM; the chunk partials are merged as usual
-        const int groups = div_up(q, 512);
+        const int groups = div_up(q, knn2_tc_group_queries());
         int chunks = std::max(1, m->sm_count / groups);
         int64_t chunk_rows = std::max<int64_t>((db->rows + chunks - 1) / chunks, 1);
-        chunk_rows = (chunk_rows + 127) / 128 * 128;
+        chunk_rows = (chunk_rows + 255) / 256 * 256;
         SFE_REQUIRE(chunk_rows <= (1 << 22), SFE_ERR_UNSUPPORTED, "database shard larger than 2^22 rows per chunk");
         chunks = (int)std::max<int64_t>((db->rows + chunk_rows - 1) / chunk_rows, 1);
         SFE_CUDA(m->d_part.ensure((size_t)chunks * q * 2));
