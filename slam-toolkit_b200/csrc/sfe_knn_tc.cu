@@ -12,8 +12,8 @@
 //   * the group's 4 x 128 queries are unpacked once into shared memory as four A tiles (K-major, no swizzle: 8-row x 16-byte
 //     core matrices, LBO = 128 B between K chunks, SBO = 2048 B between 8-row groups);
 //   * 4 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same layout;
-//   * one elected thread issues tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32, 8 per tile pair) into TMEM: two stages of
-//     two 128-column accumulators each fill the 512 columns;
+//   * two issuer warps, one per TMEM stage (an elected lane each), issue tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32, 8 per
+//     tile pair) into TMEM: two stages of two 128-column accumulators each fill the 512 columns;
 //   * 16 epilogue warps, 8 per TMEM stage, drain their stage with tcgen05.ld (thread = query row, 32 columns at a time, the next load in flight
 //     while the current one is examined): the minimum of 8 accumulators is compared with the query's current second-best
 //     D'; only a group that can still matter is turned into keys ((D' + 512) << 22 | row in chunk) and inserted;
@@ -37,7 +37,7 @@ constexpr int kTilesPerStage = 256 / kTileN;  // a TMEM stage is 256 columns: tw
 constexpr int kGroupTiles = 2 * kTilesPerStage, kGroupQ = 128 * kGroupTiles;  // query tiles / queries per work item: 4 / 512 or 2 / 256
 constexpr int kEpiWarps = 16;  // 8 per TMEM stage: one per (lane quadrant, half of the stage's 256 columns); a stage's warps examine
                                // their registers while the other stage's warps wait for theirs
-constexpr int kTcThreads = (5 + kEpiWarps) * 32;  // warp 0: MMA issuer, warps 1-4: producers, warps 5-20: epilogue
+constexpr int kTcThreads = (6 + kEpiWarps) * 32;  // warps 0-1: MMA issuers (one per TMEM stage), warps 2-5: producers, warps 6-21: epilogue
 constexpr int kATileBytes = 128 * 256, kBTileBytes = kTileN * 256;  // operand tiles: rows x 256 int8
 constexpr uint32_t kSBO = 2048, kLBO = 128;  // bytes: between 8-row groups / between 16-byte K chunks
 constexpr int kKeyOffset = 512;              // keeps D' = |b| - 2 dot non-negative in the key (D' >= -256)
@@ -172,10 +172,10 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (tid == 32) {
+    if (tid == 64) {
         for (int i = 0; i < 2; i++) {
             mbar_init(&S.b_full[i], 4);   // one arrival per producer warp
-            mbar_init(&S.b_empty[i], 1);  // tcgen05.commit
+            mbar_init(&S.b_empty[i], 2);  // tcgen05.commit of either MMA issuer
             mbar_init(&S.d_full[i], 1);   // tcgen05.commit
             mbar_init(&S.d_empty[i], kEpiWarps / 2);  // one arrival per epilogue warp of the stage
         }
@@ -200,35 +200,33 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         fence_async_smem();
         __syncthreads();
 
-        if (warp == 0) {
-            // ===== MMA issuer ========================================================================================
+        if (warp <= 1) {
+            // ===== MMA issuers: warp h feeds TMEM stage h (query tiles kTilesPerStage h ..), so the wait -> issue -> commit chains
+            // of the two stages run side by side ==========================================================================
+            const int h = warp, st = warp;  // stage h: columns [256 h, 256 h + 256)
             for (int n = 0; n < ntiles; n++) {
                 const int bi = n & 1;
                 mbar_wait(&S.b_full[bi], (ph_b_full >> bi) & 1);
                 ph_b_full ^= 1u << bi;
+                mbar_wait(&S.d_empty[st], ((ph_d_empty >> st) & 1) ^ 1);  // first use passes: the barrier starts in phase 0
+                ph_d_empty ^= 1u << st;
                 tc_fence_after();
-                for (int h = 0; h < 2; h++) {       // the group's query tiles against this B tile, half of them per TMEM stage
-                    const int st = h;               // stage h: columns [256 h, 256 h + 256)
-                    mbar_wait(&S.d_empty[st], ((ph_d_empty >> st) & 1) ^ 1);  // first use passes: the barrier starts in phase 0
-                    ph_d_empty ^= 1u << st;
-                    tc_fence_after();
-                    if (lane == 0) {
-                        for (int t = 0; t < kTilesPerStage; t++) {
-                            const uint32_t a_addr = smem_u32(S.a[kTilesPerStage * h + t]), b_addr = smem_u32(S.b[bi]);
-                            const uint32_t d = tmem + (uint32_t)(st * 256 + t * kTileN);
+                if (lane == 0) {
+                    for (int t = 0; t < kTilesPerStage; t++) {
+                        const uint32_t a_addr = smem_u32(S.a[kTilesPerStage * h + t]), b_addr = smem_u32(S.b[bi]);
+                        const uint32_t d = tmem + (uint32_t)(st * 256 + t * kTileN);
 #pragma unroll
-                            for (int k = 0; k < 8; k++)  // K = 32 per instruction: two 16-byte chunks
-                                mma_i8(d, smem_desc(a_addr + k * 2 * kLBO), smem_desc(b_addr + k * 2 * kLBO), k > 0);
-                        }
-                        tc_commit(&S.d_full[st]);
-                        if (h == 1) tc_commit(&S.b_empty[bi]);
+                        for (int k = 0; k < 8; k++)  // K = 32 per instruction: two 16-byte chunks
+                            mma_i8(d, smem_desc(a_addr + k * 2 * kLBO), smem_desc(b_addr + k * 2 * kLBO), k > 0);
                     }
-                    __syncwarp();
+                    tc_commit(&S.d_full[st]);
+                    tc_commit(&S.b_empty[bi]);
                 }
+                __syncwarp();
             }
-        } else if (warp <= 4) {
+        } else if (warp <= 5) {
             // ===== producers: database rows -> B tile ================================================================
-            const int pw = warp - 1, pt = pw * 32 + lane;  // 128 producer threads
+            const int pw = warp - 2, pt = pw * 32 + lane;  // 128 producer threads
             // thread = kPasses (row, chunk) cells of a tile, one 16-byte store each, which a warp lays down as 8 rows x 4 chunks =
             // 512 contiguous bytes.  The descriptor bits of the NEXT tile are fetched before this one is written, so the global
             // latency never sits between "buffer free" and "buffer full".
@@ -261,7 +259,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
             }
         } else {
             // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
-            const int ew = warp - 5, quad = warp & 3;  // a warp reads the TMEM lanes of quadrant warp % 4
+            const int ew = warp - 6, quad = warp & 3;  // a warp reads the TMEM lanes of quadrant warp % 4
             const int st = ew >> 3;                     // the stage this warp serves
             const int half = (ew >> 2) & 1;             // ... and which 128 of its 256 columns
             const int tile = kTilesPerStage * st + (half * 128) / kTileN;  // the query tile those columns belong to
