@@ -11,7 +11,7 @@
 // One persistent CTA per SM works on one (query group of 512, chunk of database rows) item:
 //   * the group's 4 x 128 queries are unpacked once into shared memory as four A tiles (K-major, no swizzle: 8-row x 16-byte
 //     core matrices, LBO = 128 B between K chunks, SBO = 2048 B between 8-row groups);
-//   * 4 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same layout;
+//   * 2 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same layout;
 //   * two issuer warps, one per TMEM stage (an elected lane each), issue tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32, 8 per
 //     tile pair) into TMEM: two stages of two 128-column accumulators each fill the 512 columns;
 //   * 16 epilogue warps, 8 per TMEM stage, drain their stage with tcgen05.ld (thread = query row, 32 columns at a time, the next load in flight
@@ -37,7 +37,11 @@ constexpr int kTilesPerStage = 256 / kTileN;  // a TMEM stage is 256 columns: tw
 constexpr int kGroupTiles = 2 * kTilesPerStage, kGroupQ = 128 * kGroupTiles;  // query tiles / queries per work item: 4 / 512 or 2 / 256
 constexpr int kEpiWarps = 16;  // 8 per TMEM stage: one per (lane quadrant, half of the stage's 256 columns); a stage's warps examine
                                // their registers while the other stage's warps wait for theirs
-constexpr int kTcThreads = (6 + kEpiWarps) * 32;  // warps 0-1: MMA issuers (one per TMEM stage), warps 2-5: producers, warps 6-21: epilogue
+#ifndef SFE_TC_PRODUCERS
+#define SFE_TC_PRODUCERS 2
+#endif
+constexpr int kProdWarps = SFE_TC_PRODUCERS;           // 2: 20 warps in all = 640 threads, which leaves 96 registers per thread
+constexpr int kTcThreads = (2 + kProdWarps + kEpiWarps) * 32;  // warps 0-1: MMA issuers (one per TMEM stage), then the producers, then the epilogue
 constexpr int kATileBytes = 128 * 256, kBTileBytes = kTileN * 256;  // operand tiles: rows x 256 int8
 constexpr uint32_t kSBO = 2048, kLBO = 128;  // bytes: between 8-row groups / between 16-byte K chunks
 constexpr int kKeyOffset = 512;              // keeps D' = |b| - 2 dot non-negative in the key (D' >= -256)
@@ -137,16 +141,20 @@ __device__ __forceinline__ void insert8(int v0, int v1, int v2, int v3, int v4, 
     thr = (int)(k1 >> 22) - kKeyOffset;  // 511 while fewer than two rows have been seen: everything passes
 }
 
-// 32 accumulators D' of one query (columns idx0 .. idx0 + 31 of the chunk): groups of 8 whose minimum cannot beat the
-// query's second-best distance are dropped after 4 min3 / min
+// 32 accumulators D' of one query (rows idx0 .. idx0 + 31 of the chunk): one test of their minimum against the query's
+// second-best distance drops them all; otherwise the groups of 8 whose own minimum passes are keyed and inserted
 __device__ __forceinline__ void examine32(const int (&v)[32], uint32_t &k0, uint32_t &k1, int &thr, uint32_t idx0, uint32_t chunk_n) {
+    int g[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int m = __vimin3_s32(__vimin3_s32(v[8 * j], v[8 * j + 1], v[8 * j + 2]), __vimin3_s32(v[8 * j + 3], v[8 * j + 4], v[8 * j + 5]),
-                                   min(v[8 * j + 6], v[8 * j + 7]));
-        if (m <= thr)
-            insert8(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7], idx0 + 8 * j,
-                    chunk_n, k0, k1, thr);
+    for (int j = 0; j < 4; j++)
+        g[j] = __vimin3_s32(__vimin3_s32(v[8 * j], v[8 * j + 1], v[8 * j + 2]), __vimin3_s32(v[8 * j + 3], v[8 * j + 4], v[8 * j + 5]),
+                            min(v[8 * j + 6], v[8 * j + 7]));
+    if (min(__vimin3_s32(g[0], g[1], g[2]), g[3]) <= thr) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (g[j] <= thr)
+                insert8(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7], idx0 + 8 * j,
+                        chunk_n, k0, k1, thr);
     }
 }
 
@@ -174,7 +182,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
     }
     if (tid == 64) {
         for (int i = 0; i < 2; i++) {
-            mbar_init(&S.b_full[i], 4);   // one arrival per producer warp
+            mbar_init(&S.b_full[i], kProdWarps);  // one arrival per producer warp
             mbar_init(&S.b_empty[i], 2);  // tcgen05.commit of either MMA issuer
             mbar_init(&S.d_full[i], 1);   // tcgen05.commit
             mbar_init(&S.d_empty[i], kEpiWarps / 2);  // one arrival per epilogue warp of the stage
@@ -224,19 +232,19 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 }
                 __syncwarp();
             }
-        } else if (warp <= 5) {
+        } else if (warp < 2 + kProdWarps) {
             // ===== producers: database rows -> B tile ================================================================
-            const int pw = warp - 2, pt = pw * 32 + lane;  // 128 producer threads
+            const int pw = warp - 2, pt = pw * 32 + lane;  // producer thread
             // thread = kPasses (row, chunk) cells of a tile, one 16-byte store each, which a warp lays down as 8 rows x 4 chunks =
             // 512 contiguous bytes.  The descriptor bits of the NEXT tile are fetched before this one is written, so the global
             // latency never sits between "buffer free" and "buffer full".
-            constexpr int kPasses = kTileN * 16 / 128;  // 16-byte stores per producer thread and tile
+            constexpr int kPasses = kTileN * 16 / (kProdWarps * 32);  // 16-byte stores per producer thread and tile
             uint32_t bits[kPasses];
             auto fetch = [&](int n) {
                 const long long t0 = r0 + (long long)n * kTileN;
 #pragma unroll
                 for (int pass = 0; pass < kPasses; pass++) {
-                    const int row = (pt & 7) + 8 * ((pt >> 5) + 4 * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
+                    const int row = (pt & 7) + 8 * ((pt >> 5) + kProdWarps * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
                     const long long gr = t0 + row;
                     bits[pass] = gr < r1 ? __ldg((const uint16_t *)(db + (size_t)gr * 32) + chunk16) : 0u;
                 }
@@ -249,7 +257,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 if (!kPrefetchB) fetch(n);
 #pragma unroll
                 for (int pass = 0; pass < kPasses; pass++) {
-                    const int row = (pt & 7) + 8 * ((pt >> 5) + 4 * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
+                    const int row = (pt & 7) + 8 * ((pt >> 5) + kProdWarps * (pass >> 2)), chunk16 = ((pt >> 3) & 3) + 4 * (pass & 3);
                     *(uint4 *)(S.b[bi] + tile_off(row, chunk16)) = unpack16(bits[pass]);
                 }
                 fence_async_smem();
@@ -259,7 +267,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
             }
         } else {
             // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
-            const int ew = warp - 6, quad = warp & 3;  // a warp reads the TMEM lanes of quadrant warp % 4
+            const int ew = warp - 2 - kProdWarps, quad = warp & 3;  // a warp reads the TMEM lanes of quadrant warp % 4
             const int st = ew >> 3;                     // the stage this warp serves
             const int half = (ew >> 2) & 1;             // ... and which 128 of its 256 columns
             const int tile = kTilesPerStage * st + (half * 128) / kTileN;  // the query tile those columns belong to
