@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(kKnnThreads) knn2_partial_kernel(const uint8_t
 // g*32 + j in lane j.  A row only enters the reduction when it beats that query's current second best --
 // after the first few thousand rows almost never -- so the steady state is XOR + POPC + one vote per pair.
 constexpr int kRowsQMax = 128;
-constexpr int kKnnTcMinQ = 256;  // from here on the tensor-core kernel wins (it always works on groups of 512 queries)
+constexpr int kKnnTcMinQ = 64;  // from here on the tensor-core kernel wins on a large map (10 M rows: 0.91 ms vs 1.04 ms at 64 queries, 0.91 vs 3.0 at 129); it always works on groups of 512 queries
 
 template <int QPL>  // queries per lane: q <= 32 * QPL
 __global__ void __launch_bounds__(256) knn2_rows_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_base,
@@ -1183,6 +1183,7 @@ struct sfe_matcher {
     int64_t launches = 0;
     bool async_dev = false;  // _dev entry points return after enqueueing (sfe_matcher_wait)
     bool knn_tc = true;      // SFE_KNN_TC=0: brute-force top-2 with many queries stays on the XOR / POPC kernel
+    int knn_tc_min_q = kKnnTcMinQ;  // SFE_KNN_TC_MINQ: query count from which the tensor-core kernel is used
     DevBuf<sfe_keypoint> d_kl, d_kr;
     DevBuf<uint8_t> d_dl, d_dr, d_skip;
     DevBuf<int32_t> d_n, d_idx, d_dist;
@@ -1300,7 +1301,8 @@ int knn2_tc_group_queries();
 static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, int q, unsigned long long *keys_dev,
                        int32_t *quad_dev, const CommView *push = nullptr) {
     cudaStream_t st = m->stream;
-    if (m->knn_tc && q >= kKnnTcMinQ && db->rows >= 1) {
+    // Below 256 queries the group of 512 is mostly padding: worth it only when the map is large enough to hide the set-up.
+    if (m->knn_tc && q >= m->knn_tc_min_q && db->rows >= 1 && (q >= 256 || db->rows >= 65536)) {
         // many queries: the pair distances are an int8 GEMM on the tensor cores (sfe_knn_tc.cu), one (512-query group, chunk)
         // item per SM; the chunk partials are merged as usual
         const int groups = div_up(q, knn2_tc_group_queries());
@@ -1369,6 +1371,7 @@ int sfe_matcher_create(int device, sfe_matcher **out) {
     }
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *env = getenv("SFE_KNN_TC")) m->knn_tc = atoi(env) != 0;
+    if (const char *env = getenv("SFE_KNN_TC_MINQ")) m->knn_tc_min_q = std::max(1, atoi(env));
     *out = m;
     return SFE_OK;
 }

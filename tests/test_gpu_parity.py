@@ -713,9 +713,9 @@ def test_knn2_vs_oracle_and_sharded_merge(gpu, oracle):
         assert np.array_equal(out.download((Q, 4), np.int32), ref), bounds
 
 
-@pytest.mark.parametrize("rows,q", [(1000, 300), (128, 256), (50_001, 512), (50_001, 700), (200_003, 2000), (33, 1300), (3, 257)])
+@pytest.mark.parametrize("rows,q", [(1000, 300), (128, 256), (50_001, 512), (50_001, 700), (200_003, 2000), (33, 1300), (3, 257), (70_001, 64), (70_001, 130), (65_536, 255)])
 def test_knn2_tensor_core_kernel_equals_popc_kernel_and_oracle(gpu, oracle, monkeypatch, rows, q):
-    """From 256 queries on, the pair distances come from tcgen05.mma kind::i8 on unpacked descriptor bits (sfe_knn_tc.cu);
+    """From 256 queries on (64 on a large map), the pair distances come from tcgen05.mma kind::i8 on unpacked descriptor bits (sfe_knn_tc.cu);
     SFE_KNN_TC=0 keeps the XOR / POPC kernel.  Both must return the oracle's {idx0, dist0, idx1, dist1}: partial query
     groups, partial row tiles, fewer rows than two, duplicated rows (ties broken by index)."""
     db = synth.knn_database(rows, seed=11)
