@@ -623,5 +623,30 @@ def main():
         sys.exit(1)
 
 
+def _only_the_json_line_on_stdout(fn):
+    """Libraries (NCCL prints its version banner on stdout at the first communicator) must not share stdout with the one
+    JSON line: fd 1 points at stderr while the bench runs and is restored for the final print."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_print = print
+
+    def emit(*a, **k):
+        if k.get("file") in (None, sys.stdout):
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            real_print(*a, **k)
+            sys.stdout.flush()
+            os.dup2(2, 1)
+        else:
+            real_print(*a, **k)
+    globals()["print"] = emit
+    try:
+        fn()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+
+
 if __name__ == "__main__":
-    main()
+    _only_the_json_line_on_stdout(main)
