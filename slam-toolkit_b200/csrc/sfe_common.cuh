@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sfe.h"
@@ -76,7 +77,32 @@ struct DevBuf {
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// Programmatic dependent launch: a kernel launched with `pdl` may be scheduled while its predecessor on the stream is still
+// running (its CTAs then sit in pdl_enter() until the predecessor has completed and flushed), which hides the launch latency
+// between the small dependent kernels of a one-image / one-pair call.  Every kernel launched this way calls pdl_enter() first.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
 }  // namespace sfe
+
+// First statement of every kernel that may be launched with programmatic stream serialization: let the successor be scheduled
+// as soon as all CTAs of this grid are running, then wait for the predecessor grid's completion (no-ops otherwise).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 struct sfe_event {
     int device;

@@ -44,6 +44,7 @@ __device__ __forceinline__ uint32_t dp2a_hi(uint32_t a, uint32_t b, uint32_t c) 
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) realign_kernel(const uint8_t *__restrict__ src, size_t src_stride, int src_pitch,
                                                       uint8_t *__restrict__ dst, size_t dst_stride, int dst_pitch, int w, int h) {
+    pdl_enter();
     const int x = (blockIdx.x * 32 + threadIdx.x) * 16, y = blockIdx.y * 8 + threadIdx.y, img = blockIdx.z;
     if (x >= dst_pitch || y >= h) return;
     const uint8_t *p = src + (size_t)img * src_stride + (size_t)y * src_pitch + x;
@@ -83,6 +84,7 @@ struct PyrStep {            // geometry of one resize launch, in the kernel para
 template <bool kTma>
 __global__ void __launch_bounds__(256) pyr_resize_kernel(ImgSet S, PyrStep P, const uint2 *__restrict__ xtab,
                                                          const uint2 *__restrict__ ytab, const __grid_constant__ TmaMaps M) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t pyr_smem[];
     uint16_t *pyr_u = (uint16_t *)(pyr_smem + (kTma ? P.box_w * P.box_h : 0));  // [source row][kPyrTileW]
     __shared__ uint64_t bar;
@@ -227,6 +229,7 @@ template <bool kTma>
 __global__ void __launch_bounds__(kFastThreads, kFastCtasPerSm) fast_segments_kernel(ImgSet S, FastPlan P, const SegRec *__restrict__ segs,
                                                                      const __grid_constant__ TmaMaps M) {
     constexpr int TP = kFastTilePitch, TW = TP / 4, SP = kFastScorePitch, T = kFastThreads;
+    pdl_enter();
     extern __shared__ __align__(128) uint32_t fast_smem[];
     uint32_t *tile32 = fast_smem;                              // tile_rows x TW
     uint8_t *score = (uint8_t *)(tile32 + P.tile_rows * TW);   // score_rows x SP
@@ -780,6 +783,7 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
 template <bool kWide>
 __global__ void __launch_bounds__(1024) octree_kernel(ImgSet S, int count, int level0, int level_n, int smem_cand, int max_cand, int max_nodes,
                                                      uint8_t *__restrict__ scratch, int scratch_slots, int *scratch_next) {
+    pdl_enter();
     const int items = level_n * count;  // levels [level0, level0 + level_n)
     for (int w = blockIdx.x; w < items; w += gridDim.x) {
         octree_item<kWide>(S, level0 + w / count, w % count, smem_cand, max_cand, max_nodes, scratch, scratch_slots, scratch_next);
@@ -810,6 +814,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 template <bool kTma>
 __global__ void __launch_bounds__(256) blur_kernel(ImgSet S, const TilePlan *__restrict__ tiles,
                                                    const __grid_constant__ TmaMaps M) {
+    pdl_enter();
     constexpr int IH = kBlurTileH + 6, IWW = kBlurInWords;
     static_assert(IH % 2 == 0 && kBlurTileW == 128 && kBlurTileH == 32, "the blur passes pair rows and map 32 x 8 threads onto the tile");
     __shared__ __align__(128) uint32_t in32[IH * IWW];
@@ -1026,6 +1031,7 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
     __shared__ float2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane` (floats: no conversion in the loop)
     __shared__ __align__(128) uint8_t win_all[8][kTma ? kWinBytes : kPatchRows * kPatchWords * 4];  // per warp: the windows
     __shared__ uint64_t bars[8];
+    pdl_enter();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, img = blockIdx.y, slot = slot_of(S, img);
     uint32_t *patch = (uint32_t *)win_all[warp];
     uint32_t phase = 0;
@@ -1274,6 +1280,8 @@ struct sfe_extractor {
     std::vector<GraphEntry> graphs;
     uint64_t plan_gen = 0, graph_clock = 0;
     bool use_graphs = true;           // SFE_GRAPHS=0 turns it off
+    bool use_pdl = true;              // SFE_PDL=0: no programmatic dependent launches in small host calls
+    bool pdl_now = false;             // this call's kernels are launched with programmatic stream serialization
     bool octree_wide = false;         // some level's candidate buffer exceeds 16-bit positions: the quadtree runs its 32-bit instance
     int cand_floor[kMaxLevels] = {};  // per-level candidate capacity learnt from an overflow (the reference's list is unbounded,
                                       // src/orb_extractor.cpp:778-779: a call that overflows is re-run with room for what it counted)
@@ -1287,6 +1295,8 @@ struct sfe_extractor {
     DevBuf<sfe_keypoint> d_kps;
     DevBuf<int32_t> d_nout, d_sidx, d_sdist, d_tidx, d_tdist;
     std::vector<int> h_flags;
+    int *h_flags_pinned = nullptr;    // kGraphMaxImages flags written by copy_out_kernel
+    bool use_copy_kernel = true;      // SFE_COPY_KERNEL=0: small host calls download with cudaMemcpyAsync like large ones
     int64_t launches = 0;
     // optional per-stage CUDA-event timing on the handle's own stream (bench roofline)
     bool profiling = false;
@@ -1619,6 +1629,36 @@ static OutSet chunk_of(const OutSet &O, int f0) {
     return C;
 }
 
+// Results of a small host call whose output arrays are pinned (device-mapped) host memory: one kernel stores every array
+// straight into the caller's buffers over PCIe -- one launch instead of nine DMA copies of 4 - 80 KB each, which cost the
+// one-pair call 43 us of its 200.
+constexpr int kMaxCopySegs = 12;
+struct CopySeg { const void *src; void *dst; uint32_t bytes; };
+struct CopyPlan { CopySeg seg[kMaxCopySegs]; int n; };
+__global__ void __launch_bounds__(256) copy_out_kernel(const __grid_constant__ CopyPlan P) {
+    pdl_enter();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, T = gridDim.x * blockDim.x;
+    for (int s = 0; s < P.n; s++) {
+        const CopySeg &g = P.seg[s];
+        if ((((uintptr_t)g.src | (uintptr_t)g.dst | g.bytes) & 15) == 0) {
+            const uint4 *a = (const uint4 *)g.src;
+            uint4 *b = (uint4 *)g.dst;
+            for (uint32_t i = t; i < g.bytes / 16; i += T) b[i] = a[i];
+        } else {  // every array here is made of 4-byte items
+            const uint32_t *a = (const uint32_t *)g.src;
+            uint32_t *b = (uint32_t *)g.dst;
+            for (uint32_t i = t; i < g.bytes / 4; i += T) b[i] = a[i];
+        }
+    }
+}
+
+// device address of a host pointer a kernel may store to (pinned or registered memory), or nullptr
+static void *mapped_host_pointer(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 static int reset_counters(sfe_extractor *ex) {
     // layout: cand_count | kp_count | scratch_next | flags.  An asynchronous handle keeps the error flags until sfe_extractor_wait.
     const size_t n = (size_t)ex->max_images * (2 * ex->prm.nlevels + (ex->async_dev ? 0 : 1)) + 1;
@@ -1676,9 +1716,9 @@ static int launch_fast(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, int 
         });
     }
     if (ex->tma_now && kFastTma)
-        fast_segments_kernel<true><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p + seg0, ex->fast_maps);
+        launch_k(fast_segments_kernel<true>, grid, kFastThreads, ex->fast_smem, st, ex->pdl_now, S, ex->fast, ex->d_segs.p + seg0, ex->fast_maps);
     else
-        fast_segments_kernel<false><<<grid, kFastThreads, ex->fast_smem, st>>>(S, ex->fast, ex->d_segs.p + seg0, ex->fast_maps);
+        launch_k(fast_segments_kernel<false>, grid, kFastThreads, ex->fast_smem, st, ex->pdl_now, S, ex->fast, ex->d_segs.p + seg0, ex->fast_maps);
     return SFE_OK;
 }
 
@@ -1702,9 +1742,10 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
                         l - 1, ex->pyr_box_w, ex->pyr_box_h, ex->pyr_wide_h[l]};
         dim3 grid(div_up(D.w, kPyrTileW), div_up(D.h, kPyrTileH), count);
         if (ex->tma_now)
-            pyr_resize_kernel<true><<<grid, 256, ex->pyr_smem + (size_t)ex->pyr_box_w * ex->pyr_box_h, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p, ex->pyr_maps);
+            launch_k(pyr_resize_kernel<true>, grid, 256, ex->pyr_smem + (size_t)ex->pyr_box_w * ex->pyr_box_h, st, ex->pdl_now, S, P, ex->d_xtab.p,
+                     ex->d_ytab.p, ex->pyr_maps);
         else
-            pyr_resize_kernel<false><<<grid, 256, ex->pyr_smem, st>>>(S, P, ex->d_xtab.p, ex->d_ytab.p, ex->pyr_maps);
+            launch_k(pyr_resize_kernel<false>, grid, 256, ex->pyr_smem, st, ex->pdl_now, S, P, ex->d_xtab.p, ex->d_ytab.p, ex->pyr_maps);
         ex->launches++;
     };
     const bool has_cells = ex->fast.n_cells > 0;
@@ -1737,11 +1778,11 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         // 1024-thread CTA walks a level's candidates in a quarter of the iterations
         const int threads = nl * count <= ex->sm_count / 2 ? 1024 : 256;
         if (ex->octree_wide)
-            octree_kernel<true><<<grid, threads, ex->octree_smem, so>>>(S, count, level0, level_n, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
-                                                                       ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
+            launch_k(octree_kernel<true>, grid, threads, ex->octree_smem, so, ex->pdl_now, S, count, level0, level_n, ex->octree_smem_cand,
+                     ex->max_cand, ex->max_nodes, ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
         else
-            octree_kernel<false><<<grid, threads, ex->octree_smem, so>>>(S, count, level0, level_n, ex->octree_smem_cand, ex->max_cand, ex->max_nodes,
-                                                                        ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
+            launch_k(octree_kernel<false>, grid, threads, ex->octree_smem, so, ex->pdl_now, S, count, level0, level_n, ex->octree_smem_cand,
+                     ex->max_cand, ex->max_nodes, ex->d_octree_scratch.p, ex->octree_slots, scratch_next);
         ex->launches++;
     };
     const bool fork_ok = !ex->profiling && !ex->piped_now && st == ex->stream;
@@ -1818,9 +1859,9 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
         SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[1], 0));
     }
     if (ex->tma_now && ex->orient_tma)
-        orient_describe_kernel<true><<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O, ex->orient_maps);
+        launch_k(orient_describe_kernel<true>, dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st, ex->pdl_now, S, O, ex->orient_maps);
     else
-        orient_describe_kernel<false><<<dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st>>>(S, O, ex->orient_maps);
+        launch_k(orient_describe_kernel<false>, dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st, ex->pdl_now, S, O, ex->orient_maps);
     prof_mark(ex, 5);
     ex->prof_pending = ex->profiling;
     ex->prof_has_stereo = ex->prof_has_track = false;
@@ -1866,10 +1907,12 @@ static int grow_candidate_buffers(sfe_extractor *ex, int count) {
     return kStatusRerun;
 }
 
-static int check_flags(sfe_extractor *ex, cudaStream_t st, int count) {
+// flags_here: the flags of this call already sit in ex->h_flags_pinned behind `st` (copy_out_kernel)
+static int check_flags(sfe_extractor *ex, cudaStream_t st, int count, bool flags_here = false) {
     ex->h_flags.resize(count);
-    SFE_CUDA(cudaMemcpyAsync(ex->h_flags.data(), ex->last.flags, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+    if (!flags_here) SFE_CUDA(cudaMemcpyAsync(ex->h_flags.data(), ex->last.flags, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
     SFE_CUDA(cudaStreamSynchronize(st));
+    if (flags_here) memcpy(ex->h_flags.data(), ex->h_flags_pinned, sizeof(int) * count);
     if (ex->prof_pending) {
         const int ns = ex->prof_has_track ? kNumStages : ex->prof_has_stereo ? kNumStages - 1 : kNumStages - 2;
         for (int i = 0; i < ns; i++) {
@@ -1926,8 +1969,8 @@ static int upload_images(sfe_extractor *ex, cudaStream_t st, const uint8_t *imag
 // tight staging slots [first, first + count) -> pitched level-0 planes (same slots) on stream st
 static void realign_images(sfe_extractor *ex, cudaStream_t st, int first, int count, int w, int h) {
     const size_t p0 = ex->pitch0;
-    realign_kernel<<<dim3(div_up((int)p0 / 16, 32), div_up(h, 8), count), dim3(32, 8), 0, st>>>(
-        ex->d_in.p + (size_t)first * w * h, (size_t)w * h, w, ex->d_l0.p + (size_t)first * p0 * h, p0 * h, (int)p0, w, h);
+    launch_k(realign_kernel, dim3(div_up((int)p0 / 16, 32), div_up(h, 8), count), dim3(32, 8), 0, st, false,
+             (const uint8_t *)(ex->d_in.p + (size_t)first * w * h), (size_t)w * h, w, ex->d_l0.p + (size_t)first * p0 * h, p0 * h, (int)p0, w, h);
     ex->launches++;
 }
 
@@ -1995,9 +2038,11 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
     const bool prof = ex->profiling;
     struct Restore {  // every exit puts the handle's mode switches back
         sfe_extractor *ex; bool prof;
-        ~Restore() { ex->profiling = prof; ex->piped_now = false; }
+        ~Restore() { ex->profiling = prof; ex->piped_now = false; ex->pdl_now = false; }
     } restore{ex, prof};
     ex->piped_now = piped;
+    // a one-image / one-pair call is a chain of small dependent kernels: let each be scheduled under its predecessor's tail
+    ex->pdl_now = ex->use_pdl && !piped && images <= kGraphMaxImages && !prof;
     if (piped) {
         ex->profiling = false;  // per-stage events describe one unpipelined batch
         SFE_CUDA(cudaEventRecord(ex->ev_start, ex->stream));  // the counter reset precedes every sub-batch
@@ -2006,6 +2051,18 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
     int bound[kMaxChunks + 1];  // sub-batch boundaries (an uneven split -- small first sub-batch -- measured slower)
     for (int c = 0; c <= nch; c++) bound[c] = (int)((long long)frames * c / nch);
     if (ex->trace) cudaEventRecord(ex->tr_ev[3 * kMaxChunks], sin);
+    // small calls: arrays in pinned host memory are stored by one kernel (with the counts and the flags) instead of DMA copies
+    const bool small_out = ex->use_copy_kernel && !piped && images <= kGraphMaxImages && !(tp && stereo);
+    CopyPlan out_plan;
+    out_plan.n = 0;
+    if (small_out && !ex->h_flags_pinned && cudaHostAlloc((void **)&ex->h_flags_pinned, sizeof(int) * kGraphMaxImages, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        ex->h_flags_pinned = nullptr;
+    }
+    static const bool trs = getenv("SFE_TRACE_SMALL") != nullptr;
+    static double tr_acc[6]; static int tr_n;
+    auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+    double tr_t[6] = {now_us()};
     for (int c = 0; c < nch && rc == SFE_OK; c++) {
         const int f0 = bound[c], f1 = bound[c + 1], fc = f1 - f0;
         if (fc <= 0) continue;
@@ -2015,18 +2072,23 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
                                           frames + f0)) != SFE_OK)
             break;
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c], sin);
+        if (trs) { tr_t[1] = now_us(); cudaStreamSynchronize(sin); tr_t[2] = now_us(); }
         if (piped) {
             SFE_CUDA_BREAK(cudaEventRecord(ex->ev_in[c], sin));
             SFE_CUDA_BREAK(cudaStreamWaitEvent(sc, ex->ev_in[c], 0));
         }
         auto compute = [&]() -> int {  // the kernels of this sub-batch, on stream sc
-            realign_images(ex, sc, f0, fc, w, h);
-            if (stereo) realign_images(ex, sc, frames + f0, fc, w, h);
+            if (stereo && fc == frames) {  // the whole call in one sub-batch: left and right slots are adjacent
+                realign_images(ex, sc, 0, 2 * fc, w, h);
+            } else {
+                realign_images(ex, sc, f0, fc, w, h);
+                if (stereo) realign_images(ex, sc, frames + f0, fc, w, h);
+            }
             const OutSet Oc = chunk_of(O, f0);
             if (int r = enqueue_extract(ex, sc, chunk_of(B, f0, f1, stereo), stereo ? 2 * fc : fc, Oc)) return r;
             if (stereo) {
                 launch_stereo_match(sc, fc, cap, Oc.kps_a, Oc.desc_a, Oc.n_a, Oc.kps_b, Oc.desc_b, Oc.n_b, sp->y_threshold, sp->max_dx,
-                                    sp->best12_threshold, ex->d_sidx.p + (size_t)f0 * cap, ex->d_sdist.p + (size_t)f0 * cap);
+                                    sp->best12_threshold, ex->d_sidx.p + (size_t)f0 * cap, ex->d_sdist.p + (size_t)f0 * cap, ex->pdl_now);
                 if (!piped) prof_mark(ex, 6);
                 ex->prof_has_stereo = true;
                 ex->launches++;
@@ -2088,20 +2150,30 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
             if (ge) ge->seen = 1;
         }
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 1], sc);
+        if (trs) { tr_t[3] = now_us(); cudaStreamSynchronize(sc); tr_t[4] = now_us(); }
         if (piped) {
             SFE_CUDA_BREAK(cudaEventRecord(ex->ev_done[c], sc));
             SFE_CUDA_BREAK(cudaStreamWaitEvent(sout, ex->ev_done[c], 0));
         }
         const size_t o = (size_t)f0 * cap, nk = (size_t)fc * cap;
-        SFE_CUDA_BREAK(cudaMemcpyAsync(kps_l + o, kl + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
-        SFE_CUDA_BREAK(cudaMemcpyAsync(desc_l + o * 32, dl + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
-        if (stereo) {
-            SFE_CUDA_BREAK(cudaMemcpyAsync(kps_r + o, kr + o, sizeof(sfe_keypoint) * nk, cudaMemcpyDeviceToHost, sout));
-            SFE_CUDA_BREAK(cudaMemcpyAsync(desc_r + o * 32, dr + o * 32, nk * 32, cudaMemcpyDeviceToHost, sout));
-            SFE_CUDA_BREAK(cudaMemcpyAsync(stereo_idx + o, ex->d_sidx.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
-            if (stereo_dist)
-                SFE_CUDA_BREAK(cudaMemcpyAsync(stereo_dist + o, ex->d_sdist.p + o, sizeof(int32_t) * nk, cudaMemcpyDeviceToHost, sout));
+        struct Out { const void *src; void *dst; size_t bytes; };
+        const Out outs[6] = {{kl + o, kps_l + o, sizeof(sfe_keypoint) * nk},
+                             {dl + o * 32, desc_l + o * 32, nk * 32},
+                             {kr + o, stereo ? kps_r + o : nullptr, sizeof(sfe_keypoint) * nk},
+                             {dr + o * 32, stereo ? desc_r + o * 32 : nullptr, nk * 32},
+                             {ex->d_sidx.p + o, stereo ? stereo_idx + o : nullptr, sizeof(int32_t) * nk},
+                             {ex->d_sdist.p + o, stereo && stereo_dist ? stereo_dist + o : nullptr, sizeof(int32_t) * nk}};
+        for (const Out &g : outs) {
+            if (!g.dst) continue;
+            void *mapped = small_out ? mapped_host_pointer(g.dst) : nullptr;
+            if (mapped && g.bytes < (1u << 31) && out_plan.n < kMaxCopySegs - 3) {
+                out_plan.seg[out_plan.n++] = CopySeg{g.src, mapped, (uint32_t)g.bytes};
+            } else {
+                cudaError_t e_ = cudaMemcpyAsync(g.dst, g.src, g.bytes, cudaMemcpyDeviceToHost, sout);
+                if (e_ != cudaSuccess) { set_error("download: %s", cudaGetErrorString(e_)); rc = SFE_ERR_CUDA; break; }
+            }
         }
+        if (rc != SFE_OK) break;
         if (ex->trace) cudaEventRecord(ex->tr_ev[3 * c + 2], sout);
     }
     ex->profiling = prof;
@@ -2125,12 +2197,34 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
         SFE_CUDA_DRAIN(cudaMemcpyAsync(track_idx, ex->d_tidx.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
         if (track_dist) SFE_CUDA_DRAIN(cudaMemcpyAsync(track_dist, ex->d_tdist.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
     }
-    SFE_CUDA_DRAIN(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
-    if (stereo) SFE_CUDA_DRAIN(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
+    void *map_nl = small_out ? mapped_host_pointer(n_l) : nullptr, *map_nr = small_out && stereo ? mapped_host_pointer(n_r) : nullptr;
+    if (map_nl) out_plan.seg[out_plan.n++] = CopySeg{nl, map_nl, (uint32_t)(sizeof(int32_t) * F)};
+    else SFE_CUDA_DRAIN(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
+    if (stereo) {
+        if (map_nr) out_plan.seg[out_plan.n++] = CopySeg{nr, map_nr, (uint32_t)(sizeof(int32_t) * F)};
+        else SFE_CUDA_DRAIN(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
+    }
+    const bool flags_here = small_out && ex->h_flags_pinned && out_plan.n > 0;
+    if (flags_here) out_plan.seg[out_plan.n++] = CopySeg{B.flags, ex->h_flags_pinned, (uint32_t)(sizeof(int) * images)};
+    if (out_plan.n > 0) {
+        SFE_CUDA_DRAIN(launch_k(copy_out_kernel, dim3(64), dim3(256), 0, sout, ex->pdl_now, out_plan));
+        ex->launches++;
+    }
     ex->last = B;
     if (!stereo) ex->last.split = images;  // one set: every image reads in_a
     ex->last_count = images;
-    rc = check_flags(ex, sout, images);  // sout is behind every sub-batch
+    if (trs) tr_t[5] = now_us();
+    rc = check_flags(ex, sout, images, flags_here);  // sout is behind every sub-batch
+    if (trs) {
+        const double e = now_us();
+        const double d[6] = {tr_t[1] - tr_t[0], tr_t[2] - tr_t[1], tr_t[3] - tr_t[2], tr_t[4] - tr_t[3], tr_t[5] - tr_t[4], e - tr_t[5]};
+        for (int i = 0; i < 6; i++) tr_acc[i] += d[i];
+        if (++tr_n % 100 == 0) {
+            fprintf(stderr, "sfe small-call trace (us, mean of 100): enqueue upload %.1f | upload done %.1f | enqueue kernels %.1f | kernels done %.1f | enqueue downloads %.1f | downloads done %.1f\n",
+                    tr_acc[0] / 100, tr_acc[1] / 100, tr_acc[2] / 100, tr_acc[3] / 100, tr_acc[4] / 100, tr_acc[5] / 100);
+            for (double &a : tr_acc) a = 0;
+        }
+    }
     if (ex->trace) {
         fprintf(stderr, "sfe trace: %d frames in %d sub-batches (ms since the first upload was queued)\n", frames, nch);
         for (int c = 0; c < nch; c++) {
@@ -2213,6 +2307,8 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_OCTREE_SMEM_CAND")) ex->octree_cand_override = atoi(env);
     if (const char *env = getenv("SFE_CAND_CAP")) ex->cand_cap_override = std::max(8, atoi(env));
     if (const char *env = getenv("SFE_GRAPHS")) ex->use_graphs = atoi(env) != 0;
+    if (const char *env = getenv("SFE_PDL")) ex->use_pdl = atoi(env) != 0;
+    if (const char *env = getenv("SFE_COPY_KERNEL")) ex->use_copy_kernel = atoi(env) != 0;
     if (const char *env = getenv("SFE_SPLIT_SMALL")) ex->split_small = atoi(env) != 0;
     if (const char *env = getenv("SFE_DEV_SPLIT")) ex->dev_split = std::max(1, std::min(atoi(env), kComputeStreams));
     build_tables(ex);
@@ -2223,6 +2319,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
 int sfe_extractor_destroy(sfe_extractor *ex) {
     if (!ex) return SFE_OK;
     drop_graphs(ex);
+    if (ex->h_flags_pinned) cudaFreeHost(ex->h_flags_pinned);
     DeviceGuard g(ex->device);
     SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStreamSynchronize(ex->stream);

@@ -134,7 +134,7 @@ __device__ __forceinline__ const uint8_t *level_pixels(const ImgSet &S, int l, i
 void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoint *kl,
                          const uint8_t *dl, const int32_t *nl, const sfe_keypoint *kr,
                          const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
-                         double ratio, int32_t *out_idx, int32_t *out_dist);
+                         double ratio, int32_t *out_idx, int32_t *out_dist, bool pdl = false);
 
 // sequence tracking launch (sfe_match.cu), used by sfe_stereo_sequence on the extractor's stream: per-frame bucket grids,
 // GetDepth + ProjectionMatch of frame f-1's stereo points into frame f, decode.  3 launches.

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
                                                            const uint8_t *__restrict__ dr, const int32_t *__restrict__ nr,
                                                            float thr_y, float thr_dx, float reach_y, float reach_dx, double ratio,
                                                            int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist) {
+    pdl_enter();
     __shared__ float2 rxy[kStereoChunk];            // right keypoints of the chunk, in bucket order
     __shared__ uint16_t order[kStereoChunk];        // their indices inside the chunk
     __shared__ uint16_t start[kStereoCells + 1];    // bucket c = positions start[c] .. start[c + 1]
@@ -176,15 +177,15 @@ static float float_at_most(double v) {  // largest float <= v
 
 void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoint *kl, const uint8_t *dl, const int32_t *nl,
                          const sfe_keypoint *kr, const uint8_t *dr, const int32_t *nr, double y_thr, double max_dx,
-                         double ratio, int32_t *out_idx, int32_t *out_dist) {
+                         double ratio, int32_t *out_idx, int32_t *out_dist, bool pdl) {
     // rows a candidate can sit in: |float(ly - ry)| <= y_thr implies |ly - ry| < y_thr + 1 for coordinates < 2^13
     const float reach = (float)(std::max(y_thr, 0.0) + 1.0), reach_dx = (float)(std::max(max_dx, 0.0) + 1.0);
     if (frames * div_up(cap, 512) < 64)
-        stereo_match_kernel<1><<<dim3(div_up(cap, 256), frames), 256, 0, st>>>(
-            cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
+        launch_k(stereo_match_kernel<1>, dim3(div_up(cap, 256), frames), 256, 0, st, pdl, cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr),
+                 float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
     else
-        stereo_match_kernel<kStereoPerThreadMax><<<dim3(div_up(cap, 256 * kStereoPerThreadMax), frames), 256, 0, st>>>(
-            cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
+        launch_k(stereo_match_kernel<kStereoPerThreadMax>, dim3(div_up(cap, 256 * kStereoPerThreadMax), frames), 256, 0, st, pdl, cap, kl, dl,
+                 nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
 }
 
 // ---------------------------------------------------------------------------------------------
