@@ -460,6 +460,101 @@ __device__ int block_excl_scan(int *a, int n, int *warp_sums) {
     return carry;
 }
 
+// Exclusive scan of one packed 64-bit value per thread (fields that never carry into each other), chunk by chunk over n items:
+// scan_chunk() returns the exclusive prefix of the thread's value inside the chunk plus the running carry.  Two barriers a chunk.
+__device__ __forceinline__ unsigned long long block_excl_scan64(unsigned long long v, unsigned long long *ws, unsigned long long &carry) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) ws[warp] = inc;
+    __syncthreads();
+    // every warp scans the warp totals itself (lane w holds warp w's)
+    unsigned long long x = lane < nwarps ? ws[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long u = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += u;
+    }
+    const unsigned long long tot = __shfl_sync(0xffffffffu, x, 31);
+    const unsigned long long upto = __shfl_sync(0xffffffffu, x, max(warp - 1, 0));
+    const unsigned long long woff = warp > 0 ? upto : 0ull;
+    const unsigned long long r = carry + woff + inc - v;
+    carry += tot;
+    __syncthreads();  // ws is reused by the next chunk
+    return r;
+}
+
+// Second half of a pass: write the next node list and move the points.  M.tord[i] = processing index of a split node or -1;
+// M.arr_b[by_order ? tord[i] : i] = exclusive prefix (non-empty children | expandable children << 16) over the processing order;
+// M.arr_a[i] = rank of an unsplit node among the unsplit ones.  C = number of children.  Returns the new list size.
+template <bool kWide>
+__device__ int octree_emit(OctSmemT<kWide> &M, int cur, int n, int nL, int C, int n_unsplit, bool by_order) {
+    typedef ONodeT<kWide> ONode;
+    typedef typename ONode::pos_t pos_t;
+    const int tid = threadIdx.x, T = blockDim.x, nxt = cur ^ 1;
+    const ONode *nd = M.nd[cur];
+    for (int i = tid; i < nL; i += T) {
+        const int t = M.tord[i];
+        const ONode o = nd[i];
+        if (t >= 0) {
+            const int pe = M.arr_b[by_order ? t : i], pp = pe & 0xFFFF, ep = pe >> 16;
+            const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
+            uint32_t cc[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) cc[q] = M.child[i * 4 + q];
+            int k = 0, ke = 0, off = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                M.child[i * 4 + q] = o.start + off;  // from now on: start position of child q
+                if (cc[q] > 0) {
+                    const int pos = C - 1 - (pp + k);  // push_front order reversed (:606-662)
+                    ONode c;
+                    c.x0 = (q & 1) ? mx : o.x0;
+                    c.x1 = (q & 1) ? o.x1 : mx;
+                    c.y0 = (q & 2) ? my : o.y0;
+                    c.y1 = (q & 2) ? o.y1 : my;
+                    c.start = (pos_t)(o.start + off);
+                    c.cnt = (pos_t)cc[q];
+                    M.nd[nxt][pos] = c;
+                    M.eidx[nxt][pos] = (uint16_t)(cc[q] > 1 ? ep + ke : 0);
+                    M.childpos[i * 4 + q] = (uint16_t)pos;
+                    k++;
+                    ke += cc[q] > 1;
+                }
+                off += cc[q];
+            }
+        } else {
+            const int pos = C + M.arr_a[i];
+            M.nd[nxt][pos] = o;
+            M.eidx[nxt][pos] = M.eidx[cur][i];
+            M.childpos[i * 4] = (uint16_t)pos;
+        }
+    }
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const int i = M.own[cur][p];
+        if (M.tord[i] >= 0) {
+            const ONode o = nd[i];
+            const uint32_t v = M.pk[cur][p];
+            const int x = v & 0xFFF, y = (v >> 12) & 0xFFF;
+            const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
+            const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);  // as in the counting loop above
+            const int np = M.child[i * 4 + q] + M.qs[p];
+            M.pk[nxt][np] = v;
+            M.own[nxt][np] = M.childpos[i * 4 + q];
+        } else {
+            M.pk[nxt][p] = M.pk[cur][p];
+            M.own[nxt][p] = M.childpos[i * 4];
+        }
+    }
+    __syncthreads();
+    return C + n_unsplit;
+}
+
 // One pass over the node list.  careful == false: split every expandable node in list order
 // (:594-665).  careful == true: split expandable nodes in descending (count, creation order)
 // until the list reaches n_want (:673-738).  Returns new list size; *n_expand = new |E|.
@@ -487,11 +582,32 @@ __device__ int octree_pass(OctSmemT<kWide> &M, int cur, int n, int nL, int n_wan
     // processing order of expandable nodes
     int n_split;
     if (!careful) {
-        for (int i = tid; i < nL; i += T) M.arr_a[i] = nd[i].cnt > 1 ? 1 : 0;
+        // list order is processing order: one scan of (expandable, non-empty children, expandable children) per node gives the
+        // processing index, the position of the children in the next list and their creation order
+        __shared__ unsigned long long ws64[32];
+        unsigned long long carry = 0;
+        for (int base = 0; base < nL; base += T) {
+            const int i = base + tid;
+            unsigned long long v = 0;
+            if (i < nL && nd[i].cnt > 1) {
+                const uint32_t *c = &M.child[i * 4];
+                const unsigned long long nz = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+                const unsigned long long ne = (c[0] > 1) + (c[1] > 1) + (c[2] > 1) + (c[3] > 1);
+                v = 1ull | nz << 16 | ne << 32;
+            }
+            const unsigned long long ex = block_excl_scan64(v, ws64, carry);
+            if (i < nL) {
+                const int e = (int)(ex & 0xFFFF);
+                M.tord[i] = v ? e : -1;
+                M.arr_b[i] = (int)((ex >> 16) & 0xFFFF) | (int)((ex >> 32) & 0xFFFF) << 16;
+                M.arr_a[i] = i - e;  // unsplit nodes keep their relative order behind the children
+            }
+        }
+        n_split = (int)(carry & 0xFFFF);
+        const int C = (int)((carry >> 16) & 0xFFFF);
+        *n_expand = (int)((carry >> 32) & 0xFFFF);
         __syncthreads();
-        n_split = block_excl_scan(M.arr_a, nL, M.warp_sums);
-        for (int i = tid; i < nL; i += T) M.tord[i] = nd[i].cnt > 1 ? M.arr_a[i] : -1;
-        __syncthreads();
+        return octree_emit<kWide>(M, cur, n, nL, C, nL - n_split, false);
     } else {
         // rank by (count, creation order) descending (0 = not expandable)
         int n_e_local = 0;
@@ -570,64 +686,8 @@ __device__ int octree_pass(OctSmemT<kWide> &M, int cur, int n, int nL, int n_wan
     __syncthreads();
     const int tot = block_excl_scan(M.arr_b, n_split, M.warp_sums);
     const int n_unsplit = block_excl_scan(M.arr_a, nL, M.warp_sums);
-    const int C = tot & 0xFFFF;
     *n_expand = tot >> 16;
-    for (int i = tid; i < nL; i += T) {
-        const int t = M.tord[i];
-        const ONode o = nd[i];
-        if (t >= 0) {
-            const int pp = M.arr_b[t] & 0xFFFF, ep = M.arr_b[t] >> 16;
-            const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
-            uint32_t cc[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) cc[q] = M.child[i * 4 + q];
-            int k = 0, ke = 0, off = 0;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                M.child[i * 4 + q] = o.start + off;  // from now on: start position of child q
-                if (cc[q] > 0) {
-                    const int pos = C - 1 - (pp + k);  // push_front order reversed (:606-662)
-                    ONode c;
-                    c.x0 = (q & 1) ? mx : o.x0;
-                    c.x1 = (q & 1) ? o.x1 : mx;
-                    c.y0 = (q & 2) ? my : o.y0;
-                    c.y1 = (q & 2) ? o.y1 : my;
-                    c.start = (pos_t)(o.start + off);
-                    c.cnt = (pos_t)cc[q];
-                    M.nd[nxt][pos] = c;
-                    M.eidx[nxt][pos] = (uint16_t)(cc[q] > 1 ? ep + ke : 0);
-                    M.childpos[i * 4 + q] = (uint16_t)pos;
-                    k++;
-                    ke += cc[q] > 1;
-                }
-                off += cc[q];
-            }
-        } else {
-            const int pos = C + M.arr_a[i];
-            M.nd[nxt][pos] = o;
-            M.eidx[nxt][pos] = M.eidx[cur][i];
-            M.childpos[i * 4] = (uint16_t)pos;
-        }
-    }
-    __syncthreads();
-    for (int p = tid; p < n; p += T) {
-        const int i = M.own[cur][p];
-        if (M.tord[i] >= 0) {
-            const ONode o = nd[i];
-            const uint32_t v = M.pk[cur][p];
-            const int x = v & 0xFFF, y = (v >> 12) & 0xFFF;
-            const int mx = o.x0 + ((o.x1 - o.x0 + 1) >> 1), my = o.y0 + ((o.y1 - o.y0 + 1) >> 1);
-            const int q = (x < mx ? 0 : 1) + (y < my ? 0 : 2);  // as in the counting loop above
-            const int np = M.child[i * 4 + q] + M.qs[p];
-            M.pk[nxt][np] = v;
-            M.own[nxt][np] = M.childpos[i * 4 + q];
-        } else {
-            M.pk[nxt][p] = M.pk[cur][p];
-            M.own[nxt][p] = M.childpos[i * 4];
-        }
-    }
-    __syncthreads();
-    return C + n_unsplit;
+    return octree_emit<kWide>(M, cur, n, nL, tot & 0xFFFF, n_unsplit, true);
 }
 
 // Candidate-sized arrays (14 B per candidate) live in shared memory when the level has at most smem_cand
@@ -700,13 +760,33 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
         M.qs[p] = (pos_t)atomicAdd(&M.child[r], 1u);
     }
     __syncthreads();
-    for (int i = tid; i < n_ini; i += T) {
-        M.arr_a[i] = M.child[i];
-        M.arr_b[i] = M.child[i] > 0;
+    int nL;
+    if (n_ini <= 32) {  // the usual handful of roots: one warp scans them
+        if (tid < 32) {
+            const int c = tid < n_ini ? (int)M.child[tid] : 0;
+            int a = c, b = c > 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ua = __shfl_up_sync(0xffffffffu, a, o), ub = __shfl_up_sync(0xffffffffu, b, o);
+                if (tid >= o) { a += ua; b += ub; }
+            }
+            if (tid < n_ini) {
+                M.arr_a[tid] = a - c;
+                M.arr_b[tid] = b - (c > 0);
+            }
+            if (tid == 31) sh_misc[1] = b;
+        }
+        __syncthreads();
+        nL = sh_misc[1];
+    } else {
+        for (int i = tid; i < n_ini; i += T) {
+            M.arr_a[i] = M.child[i];
+            M.arr_b[i] = M.child[i] > 0;
+        }
+        __syncthreads();
+        block_excl_scan(M.arr_a, n_ini, M.warp_sums);
+        nL = block_excl_scan(M.arr_b, n_ini, M.warp_sums);
     }
-    __syncthreads();
-    block_excl_scan(M.arr_a, n_ini, M.warp_sums);
-    int nL = block_excl_scan(M.arr_b, n_ini, M.warp_sums);
     for (int i = tid; i < n_ini; i += T) {
         const int c = M.child[i];
         if (c > 0) {

@@ -52,7 +52,10 @@ __device__ __forceinline__ int col_bucket(float x) {
 // thr_y / thr_dx: the largest floats <= y_threshold / max_dx, so that for a float d the reference's double
 // comparison (double)d > T is exactly d > thr (no float lies strictly between thr and T).  reach_y / reach_dx:
 // |float(a - b)| <= T implies |a - b| < T + 1 for coordinates < 2^13, which bounds the buckets worth visiting.
-template <int kStereoPerThread>
+// kLanes lanes share one left keypoint (candidate positions t = lane, lane + kLanes, ... of every bucket range, merged by
+// shuffles): a one-pair call is bound by the longest walk in each warp, and four lanes per keypoint cut that walk fourfold
+// and spread the frame over four times as many CTAs.
+template <int kStereoPerThread, int kLanes>
 __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_keypoint *__restrict__ kl,
                                                            const uint8_t *__restrict__ dl, const int32_t *__restrict__ nl,
                                                            const sfe_keypoint *__restrict__ kr,
@@ -68,8 +71,8 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
     const int f = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_l = min(nl[f], cap), n_r = min(nr[f], cap);
     const size_t base = (size_t)f * cap;
-    constexpr int kStereoPerCta = 256 * kStereoPerThread;
-    const int i0 = blockIdx.x * kStereoPerCta;
+    constexpr int kSlots = 256 / kLanes, kStereoPerCta = kSlots * kStereoPerThread;
+    const int i0 = blockIdx.x * kStereoPerCta, sub = tid % kLanes, slot = tid / kLanes;
     uint32_t k0[kStereoPerThread], k1[kStereoPerThread];
 #pragma unroll
     for (int k = 0; k < kStereoPerThread; k++) k0[k] = k1[k] = kNoKey;
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < kStereoPerThread; k++) {
-            const int i = i0 + k * 256 + tid;
+            const int i = i0 + k * kSlots + slot;
             if (i >= n_l) continue;
             const float lx = kl[base + i].x, ly = kl[base + i].y;
             uint32_t a[8];
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
             uint32_t q0 = k0[k], q1 = k1[k];
             for (int yb = yb0; yb <= yb1; yb++) {
                 const int t1 = start[yb * kColBuckets + xb1 + 1];
-                for (int t = start[yb * kColBuckets + xb0]; t < t1; t++) {
+                for (int t = start[yb * kColBuckets + xb0] + sub; t < t1; t += kLanes) {
                     const float2 r = rxy[t];
                     const float dx = __fsub_rn(lx, r.x), dy = __fsub_rn(ly, r.y);  // float subtraction, as in the reference
                     if (fabsf(dy) > thr_y || dx < 0.f || dx > thr_dx) continue;   // :103-110
@@ -153,9 +156,15 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
     }
 #pragma unroll
     for (int k = 0; k < kStereoPerThread; k++) {
-        const int i = i0 + k * 256 + tid;
-        if (i >= cap) continue;
-        const uint32_t q0 = k0[k], q1 = k1[k];
+        const int i = i0 + k * kSlots + slot;
+        uint32_t q0 = k0[k], q1 = k1[k];
+#pragma unroll
+        for (int o = 1; o < kLanes; o <<= 1) {  // the lanes of a keypoint hold disjoint candidates: merge their top-2 (kNoKey never enters)
+            const uint32_t u0 = __shfl_xor_sync(0xffffffffu, q0, o), u1 = __shfl_xor_sync(0xffffffffu, q1, o);
+            top2_insert(q0, q1, u0);
+            top2_insert(q0, q1, u1);
+        }
+        if (i >= cap || sub != 0) continue;
         int idx = -1, dist = -1;
         if (i < n_l && q0 != kNoKey) {
             const double d0 = (double)(q0 >> 16), d1 = q1 == kNoKey ? 999999999. : (double)(q1 >> 16);
@@ -180,11 +189,14 @@ void launch_stereo_match(cudaStream_t st, int frames, int cap, const sfe_keypoin
                          double ratio, int32_t *out_idx, int32_t *out_dist, bool pdl) {
     // rows a candidate can sit in: |float(ly - ry)| <= y_thr implies |ly - ry| < y_thr + 1 for coordinates < 2^13
     const float reach = (float)(std::max(y_thr, 0.0) + 1.0), reach_dx = (float)(std::max(max_dx, 0.0) + 1.0);
-    if (frames * div_up(cap, 512) < 64)
-        launch_k(stereo_match_kernel<1>, dim3(div_up(cap, 256), frames), 256, 0, st, pdl, cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr),
+    if (frames * div_up(cap, 64) <= 2 * 148)  // a few frames (two CTAs per SM of a B200 at most): four lanes per keypoint, 64 keypoints per CTA
+        launch_k(stereo_match_kernel<1, 4>, dim3(div_up(cap, 64), frames), 256, 0, st, pdl, cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr),
+                 float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
+    else if (frames * div_up(cap, 512) < 64)
+        launch_k(stereo_match_kernel<1, 1>, dim3(div_up(cap, 256), frames), 256, 0, st, pdl, cap, kl, dl, nl, kr, dr, nr, float_at_most(y_thr),
                  float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
     else
-        launch_k(stereo_match_kernel<kStereoPerThreadMax>, dim3(div_up(cap, 256 * kStereoPerThreadMax), frames), 256, 0, st, pdl, cap, kl, dl,
+        launch_k(stereo_match_kernel<kStereoPerThreadMax, 1>, dim3(div_up(cap, 256 * kStereoPerThreadMax), frames), 256, 0, st, pdl, cap, kl, dl,
                  nl, kr, dr, nr, float_at_most(y_thr), float_at_most(max_dx), reach, reach_dx, ratio, out_idx, out_dist);
 }
 
