@@ -690,6 +690,128 @@ __device__ int octree_pass(OctSmemT<kWide> &M, int cur, int n, int nL, int n_wan
     return octree_emit<kWide>(M, cur, n, nL, tot & 0xFFFF, n_unsplit, true);
 }
 
+// The node list after `d0` full passes, written directly (tools/octree_model.py: fast_forward).  With 4 * n_ini * 4^d0 <= quota
+// those passes cannot end the reference's loop through its size tests (|list| <= n_ini * 4^d, |list| + 3 |E| <= 4 |list|), and
+// node boundaries do not depend on the data: the list holds the non-empty cells of the depth-d0 grid -- a cell with a single
+// point stopped splitting at the depth f where it became single and sits behind every deeper node -- in the order the
+// push_front passes leave: per depth f, digit i of the cell's path (root = digit 0) runs descending when the list was reversed
+// an odd number of times since that digit was appended (root: f odd; q_i: f - i even).  A pass that does not grow the list
+// ends the loop (:665): then the list of that depth is final (*finished).  Returns the list size; list 0 is written.
+template <bool kWide>
+__device__ int octree_build_at_depth(OctSmemT<kWide> &M, const uint32_t *__restrict__ cand, int n, int n_ini, float hx, int win_h, int d0,
+                                     bool *finished) {
+    typedef ONodeT<kWide> ONode;
+    typedef typename ONode::pos_t pos_t;
+    __shared__ unsigned long long ws64[32];
+    __shared__ int sizes[8];
+    const int tid = threadIdx.x, T = blockDim.x;
+    uint32_t *cntp = M.child;  // counts of every cell of depths 0 .. d0: cell c of depth f at off(f) + c
+    auto off = [n_ini](int f) { return n_ini * (((1 << (2 * f)) - 1) / 3); };
+    auto cells = [n_ini](int f) { return n_ini << (2 * f); };
+    const int tot = off(d0 + 1);
+    for (int i = tid; i < tot; i += T) cntp[i] = 0;
+    if (tid < 8) sizes[tid] = 0;
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const uint32_t v = cand[p];
+        const int x = v & 0xFFF, y = (v >> 12) & 0xFFF;
+        int r = (int)__fdiv_rn((float)x, hx);
+        r = min(r, n_ini - 1);
+        int x0 = (int)__fmul_rn(hx, (float)r), x1 = (int)__fmul_rn(hx, (float)(r + 1)), y0 = 0, y1 = win_h, cell = r;
+        for (int f = 0; f < d0; f++) {
+            const int mx = x0 + ((x1 - x0 + 1) >> 1), my = y0 + ((y1 - y0 + 1) >> 1);
+            const bool right = x >= mx, low = y >= my;
+            x0 = right ? mx : x0; x1 = right ? x1 : mx;
+            y0 = low ? my : y0;   y1 = low ? y1 : my;
+            cell = cell * 4 + (right ? 1 : 0) + (low ? 2 : 0);
+        }
+        M.own[1][p] = (uint16_t)cell;  // < quota / 4
+        atomicAdd(&cntp[off(d0) + cell], 1u);
+    }
+    __syncthreads();
+    for (int f = d0 - 1; f >= 0; f--) {
+        for (int c = tid; c < cells(f); c += T) {
+            const uint32_t *k = &cntp[off(f + 1) + 4 * c];
+            cntp[off(f) + c] = k[0] + k[1] + k[2] + k[3];
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < tot; i += T) {
+        if (cntp[i] == 0) continue;
+        int f = 0;
+        while (i >= off(f + 1)) f++;
+        atomicAdd(&sizes[f], 1);
+    }
+    __syncthreads();
+    int d_build = d0;
+    *finished = false;
+    for (int f = 1; f <= d0; f++)
+        if (sizes[f] == sizes[f - 1]) { d_build = f; *finished = true; break; }
+    // list order: the nodes of depth d_build, then the single-point nodes of depth d_build - 1, ..., 0
+    const int totb = off(d_build + 1);
+    unsigned long long carry = 0;
+    for (int base = 0; base < totb; base += T) {
+        const int k = base + tid;
+        unsigned long long v = 0;
+        int f = d_build, cell = 0;
+        uint32_t here = 0;
+        if (k < totb) {
+            int e = k;
+            while (e >= cells(f)) { e -= cells(f); f--; }
+            const int re = e >> (2 * f);
+            cell = (f & 1) ? n_ini - 1 - re : re;
+            for (int i = 1; i <= f; i++) {
+                const int q = (e >> (2 * (f - i))) & 3;
+                cell = cell * 4 + (((f - i) & 1) == 0 ? 3 - q : q);
+            }
+            here = cntp[off(f) + cell];
+            const uint32_t parent = f > 0 ? cntp[off(f - 1) + (cell >> 2)] : 2u;
+            const bool node = parent > 1 && (f == d_build ? here > 0 : here == 1);
+            if (node) v = 1ull | (unsigned long long)here << 32;
+        }
+        const unsigned long long ex = block_excl_scan64(v, ws64, carry);
+        if (v) {
+            const int pos = (int)(ex & 0xFFFF);
+            int x0 = 0, x1 = 0, y0 = 0, y1 = win_h;
+            {
+                const int r = cell >> (2 * f);
+                x0 = (int)__fmul_rn(hx, (float)r);
+                x1 = (int)__fmul_rn(hx, (float)(r + 1));
+                for (int i = 1; i <= f; i++) {
+                    const int q = (cell >> (2 * (f - i))) & 3;
+                    const int mx = x0 + ((x1 - x0 + 1) >> 1), my = y0 + ((y1 - y0 + 1) >> 1);
+                    x0 = (q & 1) ? mx : x0; x1 = (q & 1) ? x1 : mx;
+                    y0 = (q & 2) ? my : y0; y1 = (q & 2) ? y1 : my;
+                }
+            }
+            ONode o;
+            o.x0 = (short)x0; o.x1 = (short)x1; o.y0 = (short)y0; o.y1 = (short)y1;
+            o.start = (pos_t)(ex >> 32);
+            o.cnt = (pos_t)here;
+            M.nd[0][pos] = o;
+            M.eidx[0][pos] = 0;  // the next pass is a full one: it numbers its children itself
+            M.arr_a[off(f) + cell] = pos;
+            M.arr_b[pos] = 0;    // fill cursor of the node's segment
+        }
+    }
+    const int nL = (int)(carry & 0xFFFF);
+    __syncthreads();
+    for (int p = tid; p < n; p += T) {
+        const int fine = M.own[1][p];
+        int f = 0, c = 0;
+        for (; f <= d_build; f++) {
+            c = fine >> (2 * (d0 - f));
+            if (f == d_build || cntp[off(f) + c] == 1) break;
+        }
+        const int pos = M.arr_a[off(f) + c];
+        const int np = (int)M.nd[0][pos].start + atomicAdd(&M.arr_b[pos], 1);
+        M.pk[0][np] = cand[p];
+        M.own[0][np] = (uint16_t)pos;
+    }
+    __syncthreads();
+    return nL;
+}
+
 // Candidate-sized arrays (14 B per candidate) live in shared memory when the level has at most smem_cand
 // candidates -- sized for the common case so that several CTAs fit an SM -- and otherwise in one of the
 // handle's global scratch slots (same code, generic pointers; L2-resident).
@@ -749,6 +871,11 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
     const uint32_t *cand = S.cand + (size_t)img * S.cand_stride + L.cand_off;
     const int n_ini = L.n_ini, n_want = L.quota;
     const float hx = L.hx;
+    int nL;
+    bool finished = false;
+    if (L.ff_depth > 0) {
+        nL = octree_build_at_depth<kWide>(M, cand, n, n_ini, hx, L.win_h, L.ff_depth, &finished);
+    } else {
     // roots (:543-585): point -> root (int)(x / hX); empty roots are dropped
     for (int i = tid; i < n_ini; i += T) M.child[i] = 0;
     __syncthreads();
@@ -760,7 +887,6 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
         M.qs[p] = (pos_t)atomicAdd(&M.child[r], 1u);
     }
     __syncthreads();
-    int nL;
     if (n_ini <= 32) {  // the usual handful of roots: one warp scans them
         if (tid < 32) {
             const int c = tid < n_ini ? (int)M.child[tid] : 0;
@@ -809,10 +935,11 @@ __device__ __forceinline__ void octree_item(const ImgSet &S, int l, int image, i
         M.own[0][np] = (uint16_t)M.arr_b[r];
     }
     __syncthreads();
+    }
     // main loop (:587-739)
     int cur = 0;
     const bool overflow = false;
-    for (;;) {
+    while (!finished) {
         // a full pass is only entered with nL <= n_ini or nL + 3 * nExpand <= quota, so the next
         // list always fits max_nodes >= max(quota + 8, 4 * n_ini + 5)
         const int prev = nL;
@@ -1361,6 +1488,7 @@ struct sfe_extractor {
     uint64_t plan_gen = 0, graph_clock = 0;
     bool use_graphs = true;           // SFE_GRAPHS=0 turns it off
     bool use_pdl = true;              // SFE_PDL=0: no programmatic dependent launches in small host calls
+    bool octree_ff = true;            // SFE_OCTREE_FF=0: the quadtree starts from its roots and makes every pass
     bool pdl_now = false;             // this call's kernels are launched with programmatic stream serialization
     bool octree_wide = false;         // some level's candidate buffer exceeds 16-bit positions: the quadtree runs its 32-bit instance
     int cand_floor[kMaxLevels] = {};  // per-level candidate capacity learnt from an overflow (the reference's list is unbounded,
@@ -1523,6 +1651,9 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
                         "portrait level (W/H < 0.5): the reference divides by nIni == 0");
             L.hx = (float)L.win_w / (float)L.n_ini;
         }
+        // 4 * n_ini * 4^d <= quota: the first d full passes cannot end through the list-size tests (see octree_build_at_depth)
+        L.ff_depth = 0;
+        while (ex->octree_ff && L.ff_depth < 6 && 4ll * L.n_ini * (1ll << (2 * (L.ff_depth + 1))) <= L.quota) L.ff_depth++;
         // NMS'd FAST corners reach ~1 per 30 px on the small pyramid levels of textured frames
         // first guess: one corner per 12 tested pixels, within the quadtree's 16-bit instance; a level that really holds more
         // teaches the handle its floor (grow_candidate_buffers)
@@ -2388,6 +2519,7 @@ int sfe_extractor_create(const sfe_extractor_params *p, int device, int max_imag
     if (const char *env = getenv("SFE_CAND_CAP")) ex->cand_cap_override = std::max(8, atoi(env));
     if (const char *env = getenv("SFE_GRAPHS")) ex->use_graphs = atoi(env) != 0;
     if (const char *env = getenv("SFE_PDL")) ex->use_pdl = atoi(env) != 0;
+    if (const char *env = getenv("SFE_OCTREE_FF")) ex->octree_ff = atoi(env) != 0;
     if (const char *env = getenv("SFE_COPY_KERNEL")) ex->use_copy_kernel = atoi(env) != 0;
     if (const char *env = getenv("SFE_SPLIT_SMALL")) ex->split_small = atoi(env) != 0;
     if (const char *env = getenv("SFE_DEV_SPLIT")) ex->dev_split = std::max(1, std::min(atoi(env), kComputeStreams));

@@ -30,6 +30,7 @@ struct LevelPlan {
     int quota;              // mnFeaturesPerLevel, :435-446
     int n_ini;              // quadtree roots, :543
     float hx;               // root width, :545
+    int ff_depth;           // quadtree passes whose outcome is written directly (octree_build_at_depth); 0 = start from the roots
     int cand_cap, cand_off; // FAST candidate slots of this level inside one image's array
     int kp_cap, kp_off;     // quadtree survivor slots
     int xtab_off, ytab_off; // resize tables that PRODUCE this level from level-1

@@ -498,7 +498,7 @@ def test_execution_variants_of_the_resident_path_agree(gpu, monkeypatch):
             "stereo_idx": (4, np.int32, (F, cap)), "stereo_dist": (4, np.int32, (F, cap)), "track_idx": (4, np.int32, (F, cap)),
             "track_dist": (4, np.int32, (F, cap))}
     for env in ({}, {"SFE_OVERLAP_BLUR": "0"}, {"SFE_OVERLAP_BLUR": "1"}, {"SFE_ORIENT_TMA": "0"}, {"SFE_OVERLAP_TAIL": "0"},
-                {"SFE_OCTREE_CTAS": "7"}, {"SFE_NO_TMA": "1", "SFE_OVERLAP_BLUR": "2"}):
+                {"SFE_OCTREE_CTAS": "7"}, {"SFE_NO_TMA": "1", "SFE_OVERLAP_BLUR": "2"}, {"SFE_OCTREE_FF": "0"}):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         ex = api.ORBextractor(max_images=2 * F)
@@ -514,6 +514,39 @@ def test_execution_variants_of_the_resident_path_agree(gpu, monkeypatch):
             assert np.array_equal(got["track_idx"][f, :n], base["track_idx"][f, :n]), env
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_one_pair_host_call_variants_agree(gpu, oracle, monkeypatch):
+    """The reference-shaped call (one stereo pair, host buffers) replays a CUDA graph of kernels launched with programmatic
+    stream serialization, starts the quadtree from a directly written depth-d list and stores its results into pinned output
+    arrays with one kernel: each of these switched off, pageable instead of pinned buffers, and the oracle must all agree."""
+    L, R = synth.stereo_pair(7)
+    base = None
+    for env in ({}, {"SFE_PDL": "0"}, {"SFE_COPY_KERNEL": "0"}, {"SFE_GRAPHS": "0"}, {"SFE_OCTREE_FF": "0"},
+                {"SFE_PDL": "0", "SFE_GRAPHS": "0", "SFE_COPY_KERNEL": "0", "SFE_OCTREE_FF": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ex = api.ORBextractor(max_images=2)
+        for pinned in (True, False):
+            out = ex.alloc_stereo_out(1, pinned=pinned)
+            if pinned:
+                pl, pr = api.PinnedArray(L.shape, np.uint8), api.PinnedArray(R.shape, np.uint8)
+                pl.array[:], pr.array[:] = L, R
+                a, b = pl.array[None], pr.array[None]
+            else:
+                a, b = L[None], R[None]
+            for _ in range(3):  # eager, capture, replay
+                got = ex.stereo_frames(a, b, out)
+                got = {k: np.array(v, copy=True) for k, v in got.items()}
+                if base is None:
+                    base = got
+                _stereo_equal(got, base, 1)
+        for k in env:
+            monkeypatch.delenv(k)
+    kl, dl = oracle.Extractor().extract(L)
+    n = int(base["n_l"][0])
+    assert n == len(kl) and np.array_equal(base["desc_l"][0, :n], dl)
+    assert np.array_equal(base["kps_l"][0, :n].view(np.uint8).reshape(n, 28), np.ascontiguousarray(kl).view(np.uint8).reshape(n, 28))
 
 
 def test_pipelined_sub_batches_and_load_paths_agree(gpu, oracle, monkeypatch):

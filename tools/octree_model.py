@@ -19,7 +19,7 @@ def order_key(x, y, w_cell, h_cell):
     return ((ci * 4096 + cj) * 4096 + y) * 4096 + x
 
 
-def distribute(xs, ys, resp, W, H, n_want, w_cell, h_cell):
+def distribute(xs, ys, resp, W, H, n_want, w_cell, h_cell, fast_forward=True):
     """xs, ys: window-relative integer coords; returns indices of kept candidates in list order."""
     n = len(xs)
     if n == 0:
@@ -27,33 +27,117 @@ def distribute(xs, ys, resp, W, H, n_want, w_cell, h_cell):
     f32 = np.float32
     n_ini = int(np.floor(f32(W) / f32(H) + f32(0.5)))
     hx = f32(f32(W) / f32(n_ini))
-    # roots
+    # Fast-forward: with 4 * n_ini * 4^d <= n_want the first d full passes cannot end the loop through the size tests
+    # (|list| <= n_ini * 4^d, |list| + 3 |E| <= 4 |list|), and node boundaries do not depend on the data, so the list after
+    # those d passes is written directly: its nodes are the non-empty cells of the depth-d grid (a cell holding one point
+    # stopped splitting at the depth where it became single), in the order the push_front passes produce.
+    d0 = 0
+    while fast_forward and 4 * n_ini * 4 ** (d0 + 1) <= n_want:
+        d0 += 1
     root = [int(f32(f32(xs[p]) / hx)) for p in range(n)]
-    cnt = [0] * n_ini
-    for r in root:
-        cnt[r] += 1
-    nodes = []  # list order; node = [x0,x1,y0,y1,start,cnt,eidx]
-    start = 0
-    starts = []
-    for i in range(n_ini):
-        starts.append(start)
-        if cnt[i] > 0:
-            nodes.append([int(f32(hx * f32(i))), int(f32(hx * f32(i + 1))), 0, H, start, cnt[i], 0])
-        start += cnt[i]
-    fill = [0] * n_ini
-    perm = [0] * n
-    for p in range(n):
-        perm[starts[root[p]] + fill[root[p]]] = p
-        fill[root[p]] += 1
-    owner = [0] * n
-    for li, nd in enumerate(nodes):
-        for p in range(nd[4], nd[4] + nd[5]):
-            owner[p] = li
-    e = 0
-    for nd in nodes:  # E order for roots is irrelevant (first pass is always a full pass)
-        if nd[5] > 1:
-            nd[6] = e
-            e += 1
+
+    def descend(r, x, y, depth):
+        """cell index (root, q1..q_depth in base 4) and bounds of the depth-`depth` cell holding (x, y)"""
+        x0, x1, y0, y1 = int(f32(hx * f32(r))), int(f32(hx * f32(r + 1))), 0, H
+        cell = r
+        for _ in range(depth):
+            mx, my = x0 + ((x1 - x0 + 1) >> 1), y0 + ((y1 - y0 + 1) >> 1)
+            q = (0 if x < mx else 1) + (0 if y < my else 2)
+            x0, x1 = (x0, mx) if x < mx else (mx, x1)
+            y0, y1 = (y0, my) if y < my else (my, y1)
+            cell = cell * 4 + q
+        return cell, (x0, x1, y0, y1)
+
+    def cell_bounds(cell, depth):
+        digits = []
+        for _ in range(depth):
+            digits.append(cell & 3)
+            cell >>= 2
+        x0, x1, y0, y1 = int(f32(hx * f32(cell))), int(f32(hx * f32(cell + 1))), 0, H
+        for q in reversed(digits):
+            mx, my = x0 + ((x1 - x0 + 1) >> 1), y0 + ((y1 - y0 + 1) >> 1)
+            x0, x1 = (mx, x1) if q & 1 else (x0, mx)
+            y0, y1 = (my, y1) if q & 2 else (y0, my)
+        return x0, x1, y0, y1
+
+    def list_order_to_cell(e, depth):
+        """e-th cell of the depth-`depth` grid in list order: digit i (root = 0) runs descending when the list was reversed
+        an odd number of times since that digit was appended -- root: depth odd; q_i: depth - i even."""
+        digits = []
+        for _ in range(depth):
+            digits.append(e & 3)
+            e >>= 2
+        r = (n_ini - 1 - e) if depth & 1 else e
+        cell = r
+        for k, q in enumerate(reversed(digits)):  # k = 0 is q_1
+            i = k + 1
+            cell = cell * 4 + ((3 - q) if (depth - i) % 2 == 0 else q)
+        return cell
+
+    finished = False
+    if d0 > 0:
+        fine = [descend(root[p], int(xs[p]), int(ys[p]), d0)[0] for p in range(n)]
+        cnt = [None] * (d0 + 1)
+        cnt[d0] = [0] * (n_ini * 4 ** d0)
+        for c in fine:
+            cnt[d0][c] += 1
+        for f in range(d0 - 1, -1, -1):
+            cnt[f] = [sum(cnt[f + 1][4 * c:4 * c + 4]) for c in range(n_ini * 4 ** f)]
+        size = [sum(1 for c in cnt[f] if c > 0) for f in range(d0 + 1)]
+        d_build = d0
+        for f in range(1, d0 + 1):
+            if size[f] == size[f - 1]:  # a pass that did not grow the list ends the reference's loop (:665)
+                d_build, finished = f, True
+                break
+        nodes, nodepos = [], {}
+        start = 0
+        for f in range(d_build, -1, -1):
+            for e in range(n_ini * 4 ** f):
+                c = list_order_to_cell(e, f)
+                parent = cnt[f - 1][c >> 2] if f > 0 else 2
+                here = cnt[f][c]
+                is_node = parent > 1 and (here > 0 if f == d_build else here == 1)
+                if is_node:
+                    nodepos[(f, c)] = len(nodes)
+                    nodes.append([*cell_bounds(c, f), start, here, 0])
+                    start += here
+        fill = [0] * len(nodes)
+        perm, owner = [0] * n, [0] * n
+        for p in range(n):
+            for f in range(d_build + 1):
+                c = fine[p] >> (2 * (d0 - f))
+                if cnt[f][c] == 1 or f == d_build:
+                    break
+            li = nodepos[(f, c)]
+            perm[nodes[li][4] + fill[li]] = p
+            owner[nodes[li][4] + fill[li]] = li
+            fill[li] += 1
+    else:
+        cnt = [0] * n_ini
+        for r in root:
+            cnt[r] += 1
+        nodes = []  # list order; node = [x0,x1,y0,y1,start,cnt,eidx]
+        start = 0
+        starts = []
+        for i in range(n_ini):
+            starts.append(start)
+            if cnt[i] > 0:
+                nodes.append([int(f32(hx * f32(i))), int(f32(hx * f32(i + 1))), 0, H, start, cnt[i], 0])
+            start += cnt[i]
+        fill = [0] * n_ini
+        perm = [0] * n
+        for p in range(n):
+            perm[starts[root[p]] + fill[root[p]]] = p
+            fill[root[p]] += 1
+        owner = [0] * n
+        for li, nd in enumerate(nodes):
+            for p in range(nd[4], nd[4] + nd[5]):
+                owner[p] = li
+        e = 0
+        for nd in nodes:  # E order for roots is irrelevant (first pass is always a full pass)
+            if nd[5] > 1:
+                nd[6] = e
+                e += 1
 
     def split_pass(careful):
         nonlocal nodes, perm, owner
@@ -137,7 +221,7 @@ def distribute(xs, ys, resp, W, H, n_want, w_cell, h_cell):
         nodes, perm, owner = new_nodes, new_perm, new_owner
         return acc_e
 
-    while True:
+    while not finished:
         prev = len(nodes)
         n_expand = split_pass(False)
         if len(nodes) >= n_want or len(nodes) == prev:
