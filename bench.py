@@ -227,6 +227,34 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def latency_leg(api, dev, left, right, calls=400):
+    """The reference-shaped call: ONE stereo pair per call, host buffers in and out, synchronous (what Frame::Frame +
+    ExtractRightKeypoints + StereoMatch cost a caller that does not batch; src/frame.cpp:47,388, src/pipeline.cpp:248).
+    Median and mean wall time per call of sfe_stereo_frames(1 pair) with pinned and with pageable buffers, rank 0 only."""
+    out = {}
+    ex = api.ORBextractor(2000, 1.2, 8, 20, 7, device=dev, max_images=2)
+    for kind in ("pinned", "pageable"):
+        if kind == "pinned":
+            pl, pr = api.PinnedArray(left.shape, np.uint8), api.PinnedArray(right.shape, np.uint8)
+            pl.array[:], pr.array[:] = left, right
+            a, b = pl.array[None], pr.array[None]
+        else:
+            a, b = left[None].copy(), right[None].copy()
+        res = ex.alloc_stereo_out(1, pinned=kind == "pinned")
+        for _ in range(20):
+            ex.stereo_frames(a, b, res)
+        ts = np.empty(calls)
+        for i in range(calls):
+            t0 = time.perf_counter()
+            ex.stereo_frames(a, b, res)
+            ts[i] = time.perf_counter() - t0
+        out[f"stereo_pair_{kind}_median"] = float(np.median(ts) * 1e6)
+        out[f"stereo_pair_{kind}_mean"] = float(ts.mean() * 1e6)
+    out["what"] = ("sfe_stereo_frames(1 pair): upload 2 x 1241x376, extract L + R, StereoMatch, download, synchronous; CUDA graph of "
+                   "programmatically serialized kernels, results stored into pinned arrays by one kernel")
+    return out
+
+
 def _max_over_ranks(dist, dev, values):
     if dist is None:
         return list(values)
@@ -597,6 +625,7 @@ def main():
     if projection is not None:
         projection["frac_of_hbm_peak"] = projection["algorithmic_gbs"] / hbm_peak
         line["projection_match"] = projection
+    line["latency_us"] = latency_leg(api, dev, L[0], R[0])
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         impl = cpu_impl()

@@ -58,6 +58,32 @@ inline sfe_matcher *thread_matcher(int device = 0) {
 
 }  // namespace sfe_adapter
 
+namespace sfe_adapter {
+// Staging array in pinned host memory (sfe_host_alloc): a one-image / one-pair call then has its results stored straight into
+// it by one kernel instead of several DMA copies.  Grows, never shrinks; contents are not preserved.
+template <typename T>
+class PinnedArray {
+public:
+    PinnedArray() = default;
+    ~PinnedArray() { if (p_) sfe_host_free(p_); }
+    PinnedArray(const PinnedArray &) = delete;
+    PinnedArray &operator=(const PinnedArray &) = delete;
+    void resize(size_t n) {
+        if (n <= cap_) return;
+        if (p_) sfe_host_free(p_);
+        p_ = nullptr; cap_ = 0;
+        void *q = nullptr;
+        check(sfe_host_alloc(&q, n * sizeof(T)), "sfe_host_alloc");
+        p_ = static_cast<T *>(q); cap_ = n;
+    }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+private:
+    T *p_ = nullptr;
+    size_t cap_ = 0;
+};
+}  // namespace sfe_adapter
+
 namespace ORB_SLAM2 {
 
 class ORBextractor {
@@ -89,9 +115,11 @@ public:
         sfe_adapter::check(sfe_extractor_max_keypoints_for(ex_, image.cols, image.rows, &need), "sfe_extractor_max_keypoints_for");
         if (need > cap_) { cap_ = need; kps_.resize(cap_); }
         desc_.resize((size_t)cap_ * 32);
-        int n = 0;
-        sfe_adapter::check(sfe_extract(ex_, image.data, image.cols, image.rows, (int)image.step, kps_.data(), desc_.data(),
-                                       cap_, &n), "sfe_extract");
+        counts_.resize(2);
+        int32_t &n = counts_.data()[0];
+        n = 0;
+        sfe_adapter::check(sfe_extract_batch(ex_, image.data, (size_t)image.step * image.rows, 1, image.cols, image.rows, (int)image.step,
+                                             kps_.data(), desc_.data(), cap_, &n), "sfe_extract");
         if (n == 0) {
             _descriptors.release();
         } else {
@@ -134,13 +162,14 @@ public:
         if (need > cap_) { cap_ = need; kps_.resize(cap_); }
         desc_.resize((size_t)cap_ * 32);
         kps_r_.resize(cap_); desc_r_.resize((size_t)cap_ * 32); sidx_.resize(cap_);
-        int32_t nl = 0, nr = 0;
+        counts_.resize(2);
+        int32_t *nl = counts_.data(), *nr = counts_.data() + 1;
         sfe_adapter::check(sfe_stereo_frames(ex_, L.data, R.data, (size_t)L.step * L.rows, 1, L.cols, L.rows, (int)L.step, nullptr,
-                                             kps_.data(), desc_.data(), &nl, kps_r_.data(), desc_r_.data(), &nr, sidx_.data(), nullptr,
+                                             kps_.data(), desc_.data(), nl, kps_r_.data(), desc_r_.data(), nr, sidx_.data(), nullptr,
                                              cap_), "sfe_stereo_frames");
-        fill(kps_, desc_, nl, kps_l, _desc_l);
-        fill(kps_r_, desc_r_, nr, kps_r, _desc_r);
-        stereo_indices.assign(sidx_.begin(), sidx_.begin() + nl);
+        fill(kps_, desc_, *nl, kps_l, _desc_l);
+        fill(kps_r_, desc_r_, *nr, kps_r, _desc_r);
+        stereo_indices.assign(sidx_.data(), sidx_.data() + *nl);
     }
 
 protected:
@@ -150,8 +179,8 @@ protected:
     std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
 
 private:
-    static void fill(const std::vector<sfe_keypoint> &k, const std::vector<uint8_t> &d, int n, std::vector<cv::KeyPoint> &kps,
-                     cv::OutputArray desc) {
+    static void fill(const sfe_adapter::PinnedArray<sfe_keypoint> &k, const sfe_adapter::PinnedArray<uint8_t> &d, int n,
+                     std::vector<cv::KeyPoint> &kps, cv::OutputArray desc) {
         if (n == 0) {
             desc.release();
         } else {
@@ -164,9 +193,9 @@ private:
     }
     sfe_extractor *ex_ = nullptr;
     int cap_ = 0;
-    std::vector<sfe_keypoint> kps_, kps_r_;
-    std::vector<uint8_t> desc_, desc_r_;
-    std::vector<int32_t> sidx_;
+    sfe_adapter::PinnedArray<sfe_keypoint> kps_, kps_r_;
+    sfe_adapter::PinnedArray<uint8_t> desc_, desc_r_;
+    sfe_adapter::PinnedArray<int32_t> sidx_, counts_;
 };
 
 }  // namespace ORB_SLAM2

@@ -646,48 +646,41 @@ __device__ int octree_pass(OctSmemT<kWide> &M, int cur, int n, int nL, int n_wan
         if (tid == 0) { sh_misc[0] = 0; sh_misc[1] = 0x7fffffff; }
         __syncthreads();
         if (n_e_local) atomicAdd(&sh_misc[0], n_e_local);
-        // growth of the list per split, in processing order
+        // per expandable node, in processing order: non-empty children | children with > 1 points << 16.  One scan serves the
+        // list growth (a split adds its non-empty children minus itself), the children's positions and their creation order.
         for (int i = tid; i < nL; i += T) {
             const int t = M.tord[i];
             if (t >= 0) {
                 const uint32_t *c = &M.child[i * 4];
-                M.arr_b[t] = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
+                const int nz = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+                const int ne = (c[0] > 1) + (c[1] > 1) + (c[2] > 1) + (c[3] > 1);
+                M.arr_b[t] = nz | ne << 16;
             }
         }
         __syncthreads();
         const int n_e = sh_misc[0];
-        block_excl_scan(M.arr_b, n_e, M.warp_sums);  // exclusive; inclusive = excl + own growth
+        const int tot = block_excl_scan(M.arr_b, n_e, M.warp_sums);
         for (int i = tid; i < nL; i += T) {
             const int t = M.tord[i];
             if (t >= 0) {
                 const uint32_t *c = &M.child[i * 4];
-                const int g = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0) - 1;
-                if (nL + M.arr_b[t] + g >= n_want) atomicMin(&sh_misc[1], t + 1);  // break after this split (:730)
+                const int nz = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
+                if (nL + (M.arr_b[t] & 0xFFFF) - t + nz - 1 >= n_want) atomicMin(&sh_misc[1], t + 1);  // break after this split (:730)
             }
         }
         __syncthreads();
         n_split = min(sh_misc[1], n_e);
-        __syncthreads();
-        for (int i = tid; i < nL; i += T)
-            if (M.tord[i] >= n_split) M.tord[i] = -1;
-        __syncthreads();
-    }
-    // per split node, in processing order: non-empty children | children with > 1 points << 16
-    for (int i = tid; i < nL; i += T) {
-        const int t = M.tord[i];
-        if (t >= 0) {
-            const uint32_t *c = &M.child[i * 4];
-            const int nz = (c[0] > 0) + (c[1] > 0) + (c[2] > 0) + (c[3] > 0);
-            const int ne = (c[0] > 1) + (c[1] > 1) + (c[2] > 1) + (c[3] > 1);
-            M.arr_b[t] = nz | ne << 16;
+        const int upto = n_split < n_e ? M.arr_b[n_split] : tot;  // totals over the nodes that are split
+        for (int i = tid; i < nL; i += T) {
+            int t = M.tord[i];
+            if (t >= n_split) M.tord[i] = t = -1;
+            M.arr_a[i] = t < 0 ? 1 : 0;  // unsplit nodes keep their relative order behind the children
         }
-        M.arr_a[i] = t < 0 ? 1 : 0;  // unsplit nodes keep their relative order behind the children
+        __syncthreads();
+        const int n_unsplit = block_excl_scan(M.arr_a, nL, M.warp_sums);
+        *n_expand = upto >> 16;
+        return octree_emit<kWide>(M, cur, n, nL, upto & 0xFFFF, n_unsplit, true);
     }
-    __syncthreads();
-    const int tot = block_excl_scan(M.arr_b, n_split, M.warp_sums);
-    const int n_unsplit = block_excl_scan(M.arr_a, nL, M.warp_sums);
-    *n_expand = tot >> 16;
-    return octree_emit<kWide>(M, cur, n, nL, tot & 0xFFFF, n_unsplit, true);
 }
 
 // The node list after `d0` full passes, written directly (tools/octree_model.py: fast_forward).  With 4 * n_ini * 4^d0 <= quota
