@@ -1497,6 +1497,8 @@ struct sfe_extractor {
     DevBuf<int32_t> d_nout, d_sidx, d_sdist, d_tidx, d_tdist;
     std::vector<int> h_flags;
     int *h_flags_pinned = nullptr;    // kGraphMaxImages flags written by copy_out_kernel
+    uint8_t *h_stage = nullptr;       // pinned staging for the results of small calls whose output arrays are pageable
+    size_t h_stage_bytes = 0;
     bool use_copy_kernel = true;      // SFE_COPY_KERNEL=0: small host calls download with cudaMemcpyAsync like large ones
     int64_t launches = 0;
     // optional per-stage CUDA-event timing on the handle's own stream (bench roofline)
@@ -2259,6 +2261,34 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
     const bool small_out = ex->use_copy_kernel && !piped && images <= kGraphMaxImages && !(tp && stereo);
     CopyPlan out_plan;
     out_plan.n = 0;
+    struct Staged { void *dst; size_t off, bytes; };  // pageable destinations: stored into ex->h_stage, copied out after the wait
+    Staged staged[kMaxCopySegs];
+    int n_staged = 0;
+    size_t stage_used = 0;
+    if (small_out) {  // room for every array of the call (grow-only)
+        const size_t need = (size_t)images * cap * (sizeof(sfe_keypoint) + 32 + 2 * sizeof(int32_t)) + 16 * kMaxCopySegs + sizeof(int32_t) * 2 * F;
+        if (need > ex->h_stage_bytes) {
+            if (ex->h_stage) cudaFreeHost(ex->h_stage);
+            ex->h_stage = nullptr;
+            ex->h_stage_bytes = 0;
+            if (cudaHostAlloc((void **)&ex->h_stage, need, cudaHostAllocDefault) == cudaSuccess) ex->h_stage_bytes = need;
+            else cudaGetLastError();
+        }
+    }
+    // destination of one result array inside the copy kernel's plan: the caller's pages when they are pinned, else the staging buffer
+    auto plan_out = [&](const void *src, void *dst, size_t bytes) -> bool {
+        if (!small_out || bytes >= (1u << 31) || out_plan.n >= kMaxCopySegs - 1) return false;
+        void *target = mapped_host_pointer(dst);
+        if (!target) {
+            const size_t room = (bytes + 15) & ~(size_t)15;
+            if (!ex->h_stage || stage_used + room > ex->h_stage_bytes) return false;
+            target = ex->h_stage + stage_used;
+            staged[n_staged++] = Staged{dst, stage_used, bytes};
+            stage_used += room;
+        }
+        out_plan.seg[out_plan.n++] = CopySeg{src, target, (uint32_t)bytes};
+        return true;
+    };
     if (small_out && !ex->h_flags_pinned && cudaHostAlloc((void **)&ex->h_flags_pinned, sizeof(int) * kGraphMaxImages, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         ex->h_flags_pinned = nullptr;
@@ -2369,10 +2399,7 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
                              {ex->d_sdist.p + o, stereo && stereo_dist ? stereo_dist + o : nullptr, sizeof(int32_t) * nk}};
         for (const Out &g : outs) {
             if (!g.dst) continue;
-            void *mapped = small_out ? mapped_host_pointer(g.dst) : nullptr;
-            if (mapped && g.bytes < (1u << 31) && out_plan.n < kMaxCopySegs - 3) {
-                out_plan.seg[out_plan.n++] = CopySeg{g.src, mapped, (uint32_t)g.bytes};
-            } else {
+            if (!plan_out(g.src, g.dst, g.bytes)) {
                 cudaError_t e_ = cudaMemcpyAsync(g.dst, g.src, g.bytes, cudaMemcpyDeviceToHost, sout);
                 if (e_ != cudaSuccess) { set_error("download: %s", cudaGetErrorString(e_)); rc = SFE_ERR_CUDA; break; }
             }
@@ -2401,13 +2428,10 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
         SFE_CUDA_DRAIN(cudaMemcpyAsync(track_idx, ex->d_tidx.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
         if (track_dist) SFE_CUDA_DRAIN(cudaMemcpyAsync(track_dist, ex->d_tdist.p, sizeof(int32_t) * F * cap, cudaMemcpyDeviceToHost, sout));
     }
-    void *map_nl = small_out ? mapped_host_pointer(n_l) : nullptr, *map_nr = small_out && stereo ? mapped_host_pointer(n_r) : nullptr;
-    if (map_nl) out_plan.seg[out_plan.n++] = CopySeg{nl, map_nl, (uint32_t)(sizeof(int32_t) * F)};
-    else SFE_CUDA_DRAIN(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
-    if (stereo) {
-        if (map_nr) out_plan.seg[out_plan.n++] = CopySeg{nr, map_nr, (uint32_t)(sizeof(int32_t) * F)};
-        else SFE_CUDA_DRAIN(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
-    }
+    if (!plan_out(nl, n_l, sizeof(int32_t) * F))
+        SFE_CUDA_DRAIN(cudaMemcpyAsync(n_l, nl, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));  // after the last sub-batch
+    if (stereo && !plan_out(nr, n_r, sizeof(int32_t) * F))
+        SFE_CUDA_DRAIN(cudaMemcpyAsync(n_r, nr, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, sout));
     const bool flags_here = small_out && ex->h_flags_pinned && out_plan.n > 0;
     if (flags_here) out_plan.seg[out_plan.n++] = CopySeg{B.flags, ex->h_flags_pinned, (uint32_t)(sizeof(int) * images)};
     if (out_plan.n > 0) {
@@ -2419,6 +2443,7 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
     ex->last_count = images;
     if (trs) tr_t[5] = now_us();
     rc = check_flags(ex, sout, images, flags_here);  // sout is behind every sub-batch
+    for (int i = 0; i < n_staged; i++) memcpy(staged[i].dst, ex->h_stage + staged[i].off, staged[i].bytes);
     if (trs) {
         const double e = now_us();
         const double d[6] = {tr_t[1] - tr_t[0], tr_t[2] - tr_t[1], tr_t[3] - tr_t[2], tr_t[4] - tr_t[3], tr_t[5] - tr_t[4], e - tr_t[5]};
@@ -2525,6 +2550,7 @@ int sfe_extractor_destroy(sfe_extractor *ex) {
     if (!ex) return SFE_OK;
     drop_graphs(ex);
     if (ex->h_flags_pinned) cudaFreeHost(ex->h_flags_pinned);
+    if (ex->h_stage) cudaFreeHost(ex->h_stage);
     DeviceGuard g(ex->device);
     SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaStreamSynchronize(ex->stream);
