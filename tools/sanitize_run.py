@@ -15,6 +15,12 @@ for no_tma in ("0", "1"):
         L, R = synth.stereo_pair(7, w, h)
         ex = api.ORBextractor(nf, 1.2, nl, 20, 7, max_images=4)
         out = ex.stereo_frames(np.stack([L, R]), np.stack([R, L]))
+        if w == 320:  # the one-pair call: eager, graph capture, replay; pinned arrays (stored by the copy kernel) and pageable ones (staged)
+            for pinned in (True, False):
+                res = ex.alloc_stereo_out(1, pinned=pinned)
+                for _ in range(3):
+                    one = ex.stereo_frames(L[None], R[None], res)
+                assert int(one["n_l"][0]) == int(out["n_l"][0]), (one["n_l"], out["n_l"])
         k, d = ex.extract(L)
         print(no_tma, w, h, int(out["n_l"].sum()), len(k), flush=True)
 m = api.Matcher(0)
