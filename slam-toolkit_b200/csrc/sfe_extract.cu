@@ -2293,6 +2293,8 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
         cudaGetLastError();
         ex->h_flags_pinned = nullptr;
     }
+    // SFE_TRACE_SMALL=1 (diagnostic, one thread): wait after the upload, the kernels and the downloads of an unpipelined call and
+    // print the mean host time of each phase every 100 calls
     static const bool trs = getenv("SFE_TRACE_SMALL") != nullptr;
     static double tr_acc[6]; static int tr_n;
     auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
