@@ -2437,7 +2437,8 @@ static int run_host_batch_once(sfe_extractor *ex, const uint8_t *left, const uin
     const bool flags_here = small_out && ex->h_flags_pinned && out_plan.n > 0;
     if (flags_here) out_plan.seg[out_plan.n++] = CopySeg{B.flags, ex->h_flags_pinned, (uint32_t)(sizeof(int) * images)};
     if (out_plan.n > 0) {
-        SFE_CUDA_DRAIN(launch_k(copy_out_kernel, dim3(64), dim3(256), 0, sout, ex->pdl_now, out_plan));
+        // (an ordinary launch: what precedes it on the stream is a graph launch, not a kernel it could be serialized under)
+        SFE_CUDA_DRAIN(launch_k(copy_out_kernel, dim3(64), dim3(256), 0, sout, false, out_plan));
         ex->launches++;
     }
     ex->last = B;
