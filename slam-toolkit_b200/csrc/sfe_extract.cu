@@ -1227,7 +1227,7 @@ struct OrientMaps {
 };
 
 template <bool kTma>
-__global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSet O, const __grid_constant__ OrientMaps M) {
+__global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSet O, int kp_per_warp, const __grid_constant__ OrientMaps M) {
     __shared__ float2 pat[16 * 32];  // pat[s * 32 + lane] = sample s of descriptor byte `lane` (floats: no conversion in the loop)
     __shared__ __align__(128) uint8_t win_all[8][kTma ? kWinBytes : kPatchRows * kPatchWords * 4];  // per warp: the windows
     __shared__ uint64_t bars[8];
@@ -1268,8 +1268,8 @@ __global__ void __launch_bounds__(256, 5) orient_describe_kernel(ImgSet S, OutSe
         (set_a ? O.n_a : O.n_b)[oi] = min(total, O.cap);
         if (total > O.cap) atomicOr(&S.flags[slot], kFlagOutOverflow);
     }
-    const int g0 = (blockIdx.x * 8 + warp) * kKpPerWarp;
-    for (int g = g0; g < g0 + kKpPerWarp; g++) {
+    const int g0 = (blockIdx.x * 8 + warp) * kp_per_warp;
+    for (int g = g0; g < g0 + kp_per_warp; g++) {
         if (g >= total || g >= O.cap) return;
         const int l = __popc(__ballot_sync(0xffffffffu, lane < S.nlevels && inc <= g));  // first level whose prefix exceeds g
         const int local = g - __shfl_sync(0xffffffffu, inc - cnt, min(l, 31));
@@ -2064,10 +2064,13 @@ static int enqueue_extract(sfe_extractor *ex, cudaStream_t st, const ImgSet &S, 
     } else if (ex->tail_pending) {
         SFE_CUDA(cudaStreamWaitEvent(st, ex->ev_join[1], 0));
     }
+    // keypoints per warp: kKpPerWarp amortises the table set-up of a CTA in a batch; a call with few images instead spreads its
+    // keypoints over every warp the machine holds (5 CTAs x 8 warps per SM) -- one pair: one keypoint per warp, 21 -> 9 us
+    const int kpw = std::max(1, std::min(kKpPerWarp, div_up(O.cap * count, ex->sm_count * 5 * 8)));
     if (ex->tma_now && ex->orient_tma)
-        launch_k(orient_describe_kernel<true>, dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st, ex->pdl_now, S, O, ex->orient_maps);
+        launch_k(orient_describe_kernel<true>, dim3(div_up(O.cap, 8 * kpw), count), 256, 0, st, ex->pdl_now, S, O, kpw, ex->orient_maps);
     else
-        launch_k(orient_describe_kernel<false>, dim3(div_up(O.cap, 8 * kKpPerWarp), count), 256, 0, st, ex->pdl_now, S, O, ex->orient_maps);
+        launch_k(orient_describe_kernel<false>, dim3(div_up(O.cap, 8 * kpw), count), 256, 0, st, ex->pdl_now, S, O, kpw, ex->orient_maps);
     prof_mark(ex, 5);
     ex->prof_pending = ex->profiling;
     ex->prof_has_stereo = ex->prof_has_track = false;
