@@ -84,10 +84,23 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
         __syncthreads();
         // count: the shared-memory atomics work on 32-bit words, two 16-bit counters per word
         uint32_t *fill32 = (uint32_t *)fill;
-        for (int j = tid; j < cn; j += 256) {
-            const sfe_keypoint &q = kr[base + c0 + j];
-            const int c = row_bucket(q.y) * kColBuckets + col_bucket(q.x);
-            atomicAdd(&fill32[c >> 1], 1u << (16 * (c & 1)));
+        // the thread's right keypoints of this chunk: loaded once, all loads in flight together, used by the count and the scatter
+        constexpr int kPerThread = kStereoChunk / 256;
+        float2 rk[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            const int j = tid + 256 * k;
+            if (j < cn) {
+                const sfe_keypoint &q = kr[base + c0 + j];
+                rk[k] = make_float2(q.x, q.y);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            if (tid + 256 * k < cn) {
+                const int c = row_bucket(rk[k].y) * kColBuckets + col_bucket(rk[k].x);
+                atomicAdd(&fill32[c >> 1], 1u << (16 * (c & 1)));
+            }
         }
         __syncthreads();
         {   // exclusive scan of the bucket counts: 16 consecutive buckets per thread
@@ -118,14 +131,17 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(int cap, const sfe_ke
             if (tid == 255) start[kStereoCells] = (uint16_t)run;
         }
         __syncthreads();
-        for (int j = tid; j < cn; j += 256) {
-            const sfe_keypoint &q = kr[base + c0 + j];
-            const float x = q.x, y = q.y;
-            const int c = row_bucket(y) * kColBuckets + col_bucket(x);
-            const uint32_t old = atomicAdd(&fill32[c >> 1], 1u << (16 * (c & 1)));
-            const int t = (old >> (16 * (c & 1))) & 0xFFFF;
-            order[t] = (uint16_t)j;
-            rxy[t] = make_float2(x, y);
+#pragma unroll
+        for (int k = 0; k < kPerThread; k++) {
+            const int j = tid + 256 * k;
+            if (j < cn) {
+                const float x = rk[k].x, y = rk[k].y;
+                const int c = row_bucket(y) * kColBuckets + col_bucket(x);
+                const uint32_t old = atomicAdd(&fill32[c >> 1], 1u << (16 * (c & 1)));
+                const int t = (old >> (16 * (c & 1))) & 0xFFFF;
+                order[t] = (uint16_t)j;
+                rxy[t] = make_float2(x, y);
+            }
         }
         __syncthreads();
 #pragma unroll
