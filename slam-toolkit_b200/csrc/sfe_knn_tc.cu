@@ -97,6 +97,10 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, int (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait(int (&v)[32]) { asm volatile("tcgen05.wait::ld.sync.aligned;" : SFE_R32(v)::"memory"); }
+__device__ __forceinline__ void tmem_ld_wait2(int (&v)[32], int (&w)[32]) {  // two loads in flight: both register sets hang on the wait
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : SFE_R32(v)::"memory");
+    asm volatile("" : SFE_R32(w)::"memory");
+}
 
 // 16 descriptor bits -> 16 bytes of {0, 1}: bit k of the half-word goes to byte k (any fixed order works: both operands use it);
 // unpack16_pm turns them into {+1, -1} = 1 - 2 bit
@@ -285,20 +289,22 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 tc_fence_after();
                 // 128 columns, 32 at a time, the next load in flight while one is examined; the stage goes back to the MMA
                 // issuer as soon as the last load has landed
+                // 128 columns in two rounds of two loads in flight together: the stage goes back to its issuer two load latencies
+                // (not four) after the commit
                 int buf[2][32];
                 tmem_ld32_issue(lane_addr, buf[0]);
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    tmem_ld_wait(buf[i & 1]);
-                    if (i + 1 < 4) {
-                        tmem_ld32_issue(lane_addr + (uint32_t)((i + 1) * 32), buf[(i + 1) & 1]);
-                    } else {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.d_empty[st]);
-                    }
-                    examine32(buf[i & 1], k0, k1, thr, idx0 + 32 * i, chunk_n);
-                }
+                tmem_ld32_issue(lane_addr + 32u, buf[1]);
+                tmem_ld_wait2(buf[0], buf[1]);
+                examine32(buf[0], k0, k1, thr, idx0, chunk_n);
+                tmem_ld32_issue(lane_addr + 64u, buf[0]);
+                examine32(buf[1], k0, k1, thr, idx0 + 32, chunk_n);
+                tmem_ld32_issue(lane_addr + 96u, buf[1]);
+                tmem_ld_wait2(buf[0], buf[1]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.d_empty[st]);
+                examine32(buf[0], k0, k1, thr, idx0 + 64, chunk_n);
+                examine32(buf[1], k0, k1, thr, idx0 + 96, chunk_n);
             }
             ph_d_full = (ph_d_full & ~(1u << st)) | ph_full << st;
             // N = 256: two warps hold the halves of one query tile's columns: merge through shared memory
