@@ -46,6 +46,9 @@ constexpr int kATileBytes = 128 * 256, kBTileBytes = kTileN * 256;  // operand t
 constexpr uint32_t kSBO = 2048, kLBO = 128;  // bytes: between 8-row groups / between 16-byte K chunks
 constexpr int kKeyOffset = 512;              // keeps D' = |b| - 2 dot non-negative in the key (D' >= -256)
 constexpr uint32_t kNoKey32 = 0xFFFFFFFFu;
+#ifndef SFE_TC_ABLATE
+#define SFE_TC_ABLATE 0  // experiments: 1 = the epilogue releases a stage without reading it, 2 = reads it without examining
+#endif
 #ifndef SFE_TC_PREFETCH
 #define SFE_TC_PREFETCH 0
 #endif
@@ -100,6 +103,21 @@ __device__ __forceinline__ void tmem_ld_wait(int (&v)[32]) { asm volatile("tcgen
 __device__ __forceinline__ void tmem_ld_wait2(int (&v)[32], int (&w)[32]) {  // two loads in flight: both register sets hang on the wait
     asm volatile("tcgen05.wait::ld.sync.aligned;" : SFE_R32(v)::"memory");
     asm volatile("" : SFE_R32(w)::"memory");
+}
+
+// The same load with .pack::16b: 64 consecutive columns, the low halves of columns 2 i and 2 i + 1 in register i (the accumulators
+// D' lie in [-256, 256]: their low 16 bits are the value).  Half the bytes cross from tensor memory to the register file, and the
+// epilogue's minima work on two accumulators per instruction (tools/tc_pack_probe.cu, tools/tc_tmem_ld_rate.cu).
+__device__ __forceinline__ void tmem_ld64p_issue(uint32_t addr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, "
+        "%18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr)
+        : "memory");
 }
 
 // 16 descriptor bits -> 16 bytes of {0, 1}: bit k of the half-word goes to byte k (any fixed order works: both operands use it);
@@ -162,22 +180,56 @@ __device__ __forceinline__ void examine32(const int (&v)[32], uint32_t &k0, uint
     }
 }
 
-struct TcSmem {
+// 64 accumulators of one query as 32 packed pairs (rows idx0 .. idx0 + 63 of the chunk; register i = rows 2 i, 2 i + 1): one
+// test of their minimum against the query's second-best distance drops them all; otherwise the groups of 8 whose own minimum
+// passes are unpacked, keyed and inserted
+__device__ __forceinline__ void examine64p(const int (&v)[32], uint32_t &k0, uint32_t &k1, int &thr, uint32_t idx0, uint32_t chunk_n) {
+    uint32_t g[8];  // packed minima of 4 registers = 8 accumulators
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        g[j] = __vmins2(__vimin3_s16x2((uint32_t)v[4 * j], (uint32_t)v[4 * j + 1], (uint32_t)v[4 * j + 2]), (uint32_t)v[4 * j + 3]);
+    const uint32_t m = __vimin3_s16x2(__vimin3_s16x2(g[0], g[1], g[2]), __vimin3_s16x2(g[3], g[4], g[5]), __vmins2(g[6], g[7]));
+    if (min((int)(short)(m & 0xFFFF), (int)(short)(m >> 16)) <= thr) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            if (min((int)(short)(g[j] & 0xFFFF), (int)(short)(g[j] >> 16)) <= thr)
+                insert8((short)(v[4 * j] & 0xFFFF), (short)((uint32_t)v[4 * j] >> 16), (short)(v[4 * j + 1] & 0xFFFF),
+                        (short)((uint32_t)v[4 * j + 1] >> 16), (short)(v[4 * j + 2] & 0xFFFF), (short)((uint32_t)v[4 * j + 2] >> 16),
+                        (short)(v[4 * j + 3] & 0xFFFF), (short)((uint32_t)v[4 * j + 3] >> 16), idx0 + 8 * j, chunk_n, k0, k1, thr);
+    }
+}
+
+// kBStages database tiles in flight: 2 when the producer warps unpack them, 3 when they arrive ready-made by bulk copies (whose
+// latency is longer than the microsecond a tile lasts)
+template <int kBStages>
+struct TcSmemT {
     uint8_t a[kGroupTiles][kATileBytes];  // query tiles of the group
-    uint8_t b[2][kBTileBytes];            // database tiles, double buffered
-    uint64_t b_full[2], b_empty[2], d_full[2], d_empty[2];
+    uint8_t b[kBStages][kBTileBytes];     // database tiles
+    uint64_t b_full[kBStages], b_empty[kBStages], d_full[2], d_empty[2];
     uint32_t tmem_base;
-    uint32_t merge[2][128][2];            // N = 256: the warp of a tile's upper 128 columns hands its pair to the warp of the lower ones
+    uint32_t merge[kTileN == 256 ? 2 : 1][kTileN == 256 ? 128 : 1][2];  // N = 256: the warp of a tile's upper 128 columns hands its pair to the warp of the lower ones
 };
+constexpr int kBulkStages = kTileN == 128 ? 3 : 2;
+
+// 1-D bulk copy global -> shared memory, completion in bytes on an mbarrier (TMA engine, no tensor map)
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 }  // namespace
 
 // part[(chunk * q + query) * 2 + r] = r-th smallest (distance << 32 | global row) of the chunk, ~0 when there is none
+// kBulk: `db` holds the rows already unpacked, one 32 KB operand tile per 128 rows (knn2_unpack_tiles_kernel): a database
+// tile is one bulk copy issued by one thread instead of 2048 unpack + store steps of the producer warps.
+template <bool kBulk>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_base, int chunk_rows, int chunks, const uint8_t *__restrict__ queries,
                int q, unsigned long long *__restrict__ part_out) {
-    extern __shared__ __align__(1024) uint8_t tc_smem_raw[];
-    TcSmem &S = *(TcSmem *)tc_smem_raw;
+    constexpr int kBStages = kBulk ? kBulkStages : 2;
+    extern __shared__ __align__(128) uint8_t tc_smem_raw[];
+    TcSmemT<kBStages> &S = *(TcSmemT<kBStages> *)tc_smem_raw;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int groups = (q + kGroupQ - 1) / kGroupQ;
     if (warp == 0) {  // TMEM: all 512 columns (one CTA per SM: the shared memory footprint sees to that)
@@ -185,9 +237,11 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 64) {
-        for (int i = 0; i < 2; i++) {
-            mbar_init(&S.b_full[i], kProdWarps);  // one arrival per producer warp
+        for (int i = 0; i < kBStages; i++) {
+            mbar_init(&S.b_full[i], kBulk ? 1 : kProdWarps);  // one arrival per producer warp / the expect_tx of the bulk copy
             mbar_init(&S.b_empty[i], 2);  // tcgen05.commit of either MMA issuer
+        }
+        for (int i = 0; i < 2; i++) {
             mbar_init(&S.d_full[i], 1);   // tcgen05.commit
             mbar_init(&S.d_empty[i], kEpiWarps / 2);  // one arrival per epilogue warp of the stage
         }
@@ -196,7 +250,8 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
-    uint32_t ph_b_full = 0, ph_b_empty = 0, ph_d_full = 0, ph_d_empty = 0;  // bit i = parity of the next wait on barrier i
+    uint32_t ph_d_full = 0, ph_d_empty = 0;  // bit i = parity of the next wait on barrier i
+    uint32_t tb = 0;  // database tiles this thread's role has gone through so far: tile tb uses buffer tb % kBStages in phase tb / kBStages
 
     for (int item = blockIdx.x; item < groups * chunks; item += gridDim.x) {
         const int g = item / chunks, chunk = item % chunks;
@@ -216,10 +271,9 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
             // ===== MMA issuers: warp h feeds TMEM stage h (query tiles kTilesPerStage h ..), so the wait -> issue -> commit chains
             // of the two stages run side by side ==========================================================================
             const int h = warp, st = warp;  // stage h: columns [256 h, 256 h + 256)
-            for (int n = 0; n < ntiles; n++) {
-                const int bi = n & 1;
-                mbar_wait(&S.b_full[bi], (ph_b_full >> bi) & 1);
-                ph_b_full ^= 1u << bi;
+            for (int n = 0; n < ntiles; n++, tb++) {
+                const int bi = (int)(tb % kBStages);
+                mbar_wait(&S.b_full[bi], (tb / kBStages) & 1);
                 mbar_wait(&S.d_empty[st], ((ph_d_empty >> st) & 1) ^ 1);  // first use passes: the barrier starts in phase 0
                 ph_d_empty ^= 1u << st;
                 tc_fence_after();
@@ -253,11 +307,22 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                     bits[pass] = gr < r1 ? __ldg((const uint16_t *)(db + (size_t)gr * 32) + chunk16) : 0u;
                 }
             };
+            if (kBulk) {
+                // the tiles are ready-made in global memory: one elected thread keeps kBStages bulk copies in flight
+                if (pw == 0 && lane == 0) {
+                    const uint8_t *src = db + (size_t)(r0 / kTileN) * kBTileBytes;
+                    for (int n = 0; n < ntiles; n++, tb++) {
+                        const int bi = (int)(tb % kBStages);
+                        mbar_wait(&S.b_empty[bi], ((tb / kBStages) & 1) ^ 1);
+                        mbar_expect_tx(&S.b_full[bi], kBTileBytes);
+                        bulk_load(S.b[bi], src + (size_t)n * kBTileBytes, kBTileBytes, &S.b_full[bi]);
+                    }
+                }
+            } else {
             if (kPrefetchB && ntiles > 0) fetch(0);
-            for (int n = 0; n < ntiles; n++) {
-                const int bi = n & 1;
-                mbar_wait(&S.b_empty[bi], ((ph_b_empty >> bi) & 1) ^ 1);
-                ph_b_empty ^= 1u << bi;
+            for (int n = 0; n < ntiles; n++, tb++) {
+                const int bi = (int)(tb % kBStages);
+                mbar_wait(&S.b_empty[bi], ((tb / kBStages) & 1) ^ 1);
                 if (!kPrefetchB) fetch(n);
 #pragma unroll
                 for (int pass = 0; pass < kPasses; pass++) {
@@ -268,6 +333,7 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.b_full[bi]);
                 if (kPrefetchB && n + 1 < ntiles) fetch(n + 1);
+            }
             }
         } else {
             // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
@@ -289,22 +355,23 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 tc_fence_after();
                 // 128 columns, 32 at a time, the next load in flight while one is examined; the stage goes back to the MMA
                 // issuer as soon as the last load has landed
-                // 128 columns in two rounds of two loads in flight together: the stage goes back to its issuer two load latencies
-                // (not four) after the commit
+                // 128 columns as two packed loads of 64, both in flight: the stage goes back to its issuer one load latency after
+                // the commit
                 int buf[2][32];
-                tmem_ld32_issue(lane_addr, buf[0]);
-                tmem_ld32_issue(lane_addr + 32u, buf[1]);
+#if SFE_TC_ABLATE != 1
+                tmem_ld64p_issue(lane_addr, buf[0]);
+                tmem_ld64p_issue(lane_addr + 64u, buf[1]);
                 tmem_ld_wait2(buf[0], buf[1]);
-                examine32(buf[0], k0, k1, thr, idx0, chunk_n);
-                tmem_ld32_issue(lane_addr + 64u, buf[0]);
-                examine32(buf[1], k0, k1, thr, idx0 + 32, chunk_n);
-                tmem_ld32_issue(lane_addr + 96u, buf[1]);
-                tmem_ld_wait2(buf[0], buf[1]);
+#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.d_empty[st]);
-                examine32(buf[0], k0, k1, thr, idx0 + 64, chunk_n);
-                examine32(buf[1], k0, k1, thr, idx0 + 96, chunk_n);
+#if SFE_TC_ABLATE == 0
+                examine64p(buf[0], k0, k1, thr, idx0, chunk_n);
+                examine64p(buf[1], k0, k1, thr, idx0 + 64, chunk_n);
+#elif SFE_TC_ABLATE == 2
+                k0 ^= (uint32_t)(buf[0][0] + buf[1][31] + buf[0][17]);
+#endif
             }
             ph_d_full = (ph_d_full & ~(1u << st)) | ph_full << st;
             // N = 256: two warps hold the halves of one query tile's columns: merge through shared memory
@@ -341,24 +408,49 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
-size_t knn2_tc_smem_bytes() { return sizeof(TcSmem) + 1024; }
-int knn2_tc_group_queries() { return kGroupQ; }  // queries per work item: the caller sizes its chunks with it
+// Database rows -> ready-made operand tiles: tile t = rows 128 t .. 128 t + 127 as int8 {0, 1} in the K-major core-matrix layout
+// the MMA reads (32 KB per tile, 256 B per row: 8 x the packed map; rows past the end are zeros, which the epilogue never keys).
+__global__ void __launch_bounds__(256) knn2_unpack_tiles_kernel(const uint8_t *__restrict__ db, long long rows, uint8_t *__restrict__ tiles) {
+    const long long t0 = (long long)blockIdx.x * kTileN;
+    uint8_t *dst = tiles + (size_t)blockIdx.x * kBTileBytes;
+    for (int u = threadIdx.x; u < kTileN * 16; u += 256) {
+        const int row = u >> 4, chunk16 = u & 15;
+        const long long gr = t0 + row;
+        const uint32_t bits = gr < rows ? __ldg((const uint16_t *)(db + (size_t)gr * 32) + chunk16) : 0u;
+        *(uint4 *)(dst + tile_off(row, chunk16)) = unpack16(bits);
+    }
+}
 
-// chunks x q x 2 keys into `part`; chunk_rows must be a multiple of 128 and at most 2^22
-cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, long long rows, long long idx_base, int chunk_rows, int chunks,
-                           const uint8_t *queries, int q, unsigned long long *part) {
+size_t knn2_tc_smem_bytes() { return sizeof(TcSmemT<2>) + 128; }
+int knn2_tc_group_queries() { return kGroupQ; }  // queries per work item: the caller sizes its chunks with it
+size_t knn2_tc_tiles_bytes(long long rows) { return (size_t)((rows + kTileN - 1) / kTileN) * kBTileBytes; }
+
+cudaError_t launch_knn2_unpack_tiles(cudaStream_t st, const uint8_t *db, long long rows, uint8_t *tiles) {
+    const long long n = (rows + kTileN - 1) / kTileN;
+    if (n > 0) knn2_unpack_tiles_kernel<<<(unsigned)n, 256, 0, st>>>(db, rows, tiles);
+    return cudaGetLastError();
+}
+
+// chunks x q x 2 keys into `part`; chunk_rows must be a multiple of 128 and at most 2^22.  tiles != nullptr: the map's
+// ready-made operand tiles (launch_knn2_unpack_tiles), fetched by bulk copies instead of being unpacked by the producer warps.
+cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, const uint8_t *tiles, long long rows, long long idx_base,
+                           int chunk_rows, int chunks, const uint8_t *queries, int q, unsigned long long *part) {
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const size_t smem = knn2_tc_smem_bytes();
+    const size_t smem = knn2_tc_smem_bytes(), smem_bulk = sizeof(TcSmemT<kBulkStages>) + 128;
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(knn2_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(knn2_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bulk);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
     const int groups = (q + kGroupQ - 1) / kGroupQ;
     const int grid = std::min(sm_count, groups * chunks);
-    knn2_tc_kernel<<<grid, kTcThreads, smem, st>>>(db, rows, idx_base, chunk_rows, chunks, queries, q, part);
+    if (tiles)
+        knn2_tc_kernel<true><<<grid, kTcThreads, smem_bulk, st>>>(tiles, rows, idx_base, chunk_rows, chunks, queries, q, part);
+    else
+        knn2_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(db, rows, idx_base, chunk_rows, chunks, queries, q, part);
     return cudaGetLastError();
 }
 

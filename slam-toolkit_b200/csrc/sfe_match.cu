@@ -1213,6 +1213,7 @@ struct sfe_matcher {
     bool async_dev = false;  // _dev entry points return after enqueueing (sfe_matcher_wait)
     bool knn_tc = true;      // SFE_KNN_TC=0: brute-force top-2 with many queries stays on the XOR / POPC kernel
     int knn_tc_min_q = kKnnTcMinQ;  // SFE_KNN_TC_MINQ: query count from which the tensor-core kernel is used
+    size_t knn_tiles_max_bytes = (size_t)16 << 30;  // SFE_KNN_TILES_MAX_GB: largest unpacked copy of a map (0: never unpack)
     DevBuf<sfe_keypoint> d_kl, d_kr;
     DevBuf<uint8_t> d_dl, d_dr, d_skip;
     DevBuf<int32_t> d_n, d_idx, d_dist;
@@ -1229,6 +1230,10 @@ struct sfe_db {
     int device = 0;
     uint8_t *rows_dev = nullptr;
     int64_t rows = 0, idx_base = 0;
+    // the rows as ready-made int8 operand tiles of the tensor-core kernel (8 x the packed size), built at the first
+    // many-query search when the policy (knn_tiles_max_bytes) allows; tiles_tried: do not try again
+    mutable uint8_t *tiles_dev = nullptr;
+    mutable bool tiles_tried = false;
 };
 
 // keys_out != nullptr: leave the per-keypoint (dist << 32 | ~global query) keys there (one shard's contribution to a
@@ -1322,8 +1327,10 @@ static int projection_impl(sfe_matcher *m, const double *xw, const uint8_t *mp_d
 }
 
 namespace sfe {
-cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, long long rows, long long idx_base, int chunk_rows, int chunks,
-                           const uint8_t *queries, int q, unsigned long long *part);  // sfe_knn_tc.cu
+cudaError_t launch_knn2_tc(cudaStream_t st, int sm_count, const uint8_t *db, const uint8_t *tiles, long long rows, long long idx_base,
+                           int chunk_rows, int chunks, const uint8_t *queries, int q, unsigned long long *part);
+cudaError_t launch_knn2_unpack_tiles(cudaStream_t st, const uint8_t *db, long long rows, uint8_t *tiles);
+size_t knn2_tc_tiles_bytes(long long rows);
 int knn2_tc_group_queries();
 }
 
@@ -1341,7 +1348,25 @@ static int knn_partial(sfe_matcher *m, const sfe_db *db, const uint8_t *q_dev, i
         SFE_REQUIRE(chunk_rows <= (1 << 22), SFE_ERR_UNSUPPORTED, "database shard larger than 2^22 rows per chunk");
         chunks = (int)std::max<int64_t>((db->rows + chunk_rows - 1) / chunk_rows, 1);
         SFE_CUDA(m->d_part.ensure((size_t)chunks * q * 2));
-        SFE_CUDA(launch_knn2_tc(st, m->sm_count, db->rows_dev, db->rows, db->idx_base, (int)chunk_rows, chunks, q_dev, q, m->d_part.p));
+        // A map that is searched with many queries keeps its rows unpacked in HBM (256 B per row instead of 32): the kernel's
+        // producers then move tiles with bulk copies instead of unpacking 10 M rows once per query group.  Built on first use,
+        // when it fits the budget (SFE_KNN_TILES_MAX_GB, default 16 GB and a quarter of the free memory).
+        if (!db->tiles_dev && !db->tiles_tried && q >= 256 && db->rows >= 65536) {
+            db->tiles_tried = true;
+            const size_t need = knn2_tc_tiles_bytes(db->rows);
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && need <= m->knn_tiles_max_bytes && need <= free_b / 4) {
+                if (cudaMalloc((void **)&db->tiles_dev, need) == cudaSuccess) {
+                    SFE_CUDA(launch_knn2_unpack_tiles(st, db->rows_dev, db->rows, db->tiles_dev));
+                    m->launches++;
+                } else {
+                    cudaGetLastError();
+                    db->tiles_dev = nullptr;
+                }
+            }
+        }
+        SFE_CUDA(launch_knn2_tc(st, m->sm_count, db->rows_dev, db->tiles_dev, db->rows, db->idx_base, (int)chunk_rows, chunks, q_dev, q,
+                                m->d_part.p));
         if (push)
             knn2_merge_push_kernel<<<div_up(q, 4), 128, 0, st>>>(*push, m->d_part.p, chunks, q);
         else
@@ -1401,6 +1426,7 @@ int sfe_matcher_create(int device, sfe_matcher **out) {
     cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (const char *env = getenv("SFE_KNN_TC")) m->knn_tc = atoi(env) != 0;
     if (const char *env = getenv("SFE_KNN_TC_MINQ")) m->knn_tc_min_q = std::max(1, atoi(env));
+    if (const char *env = getenv("SFE_KNN_TILES_MAX_GB")) m->knn_tiles_max_bytes = (size_t)(std::max(0.0, atof(env)) * (double)(1ull << 30));
     *out = m;
     return SFE_OK;
 }
@@ -1985,6 +2011,7 @@ int sfe_db_destroy(sfe_db *db) {
     DeviceGuard g(db->device);
     SFE_REQUIRE(g.ok, SFE_ERR_NO_DEVICE, "cannot select the handle's device");
     cudaFree(db->rows_dev);
+    if (db->tiles_dev) cudaFree(db->tiles_dev);
     delete db;
     return SFE_OK;
 }
