@@ -11,12 +11,15 @@
 // One persistent CTA per SM works on one (query group of 512, chunk of database rows) item:
 //   * the group's 4 x 128 queries are unpacked once into shared memory as four A tiles (K-major, no swizzle: 8-row x 16-byte
 //     core matrices, LBO = 128 B between K chunks, SBO = 2048 B between 8-row groups);
-//   * 2 producer warps stream the chunk: 128 database rows at a time are unpacked into one of two B tiles of the same layout;
+//   * the chunk's database rows arrive 128 at a time as B tiles of the same layout: ready-made from HBM by one bulk copy per
+//     tile (cp.async.bulk, three in flight) when the map keeps an unpacked copy (256 B per row, built at the first many-query
+//     search if it fits the budget), else unpacked by 2 producer warps into one of two B tiles;
 //   * two issuer warps, one per TMEM stage (an elected lane each), issue tcgen05.mma.kind::i8 (M = 128, N = 128, K = 32, 8 per
 //     tile pair) into TMEM: two stages of two 128-column accumulators each fill the 512 columns;
-//   * 16 epilogue warps, 8 per TMEM stage, drain their stage with tcgen05.ld (thread = query row, 32 columns at a time, the next load in flight
-//     while the current one is examined): the minimum of 8 accumulators is compared with the query's current second-best
-//     D'; only a group that can still matter is turned into keys ((D' + 512) << 22 | row in chunk) and inserted;
+//   * 16 epilogue warps, 8 per TMEM stage, drain their stage with tcgen05.ld.pack::16b (thread = query row; the accumulators lie
+//     in [-256, 256], so two of them travel in one register: 128 columns = two loads of 32 registers, both in flight) and give
+//     the stage back before looking at the values: packed 16x2 minima are compared with the query's current second-best D';
+//     only a group of 8 that can still matter is turned into keys ((D' + 512) << 22 | row in chunk) and inserted;
 //   * mbarriers carry the B-tile full / empty and TMEM full / empty hand-offs; tcgen05.commit arrives on them.
 // Output = the same per-(chunk, query) pair of 64-bit keys (distance << 32 | global row) the other partial kernels
 // write, so knn2_merge_kernel / knn2_merge_push_kernel finish the job.
@@ -46,9 +49,6 @@ constexpr int kATileBytes = 128 * 256, kBTileBytes = kTileN * 256;  // operand t
 constexpr uint32_t kSBO = 2048, kLBO = 128;  // bytes: between 8-row groups / between 16-byte K chunks
 constexpr int kKeyOffset = 512;              // keeps D' = |b| - 2 dot non-negative in the key (D' >= -256)
 constexpr uint32_t kNoKey32 = 0xFFFFFFFFu;
-#ifndef SFE_TC_ABLATE
-#define SFE_TC_ABLATE 0  // experiments: 1 = the epilogue releases a stage without reading it, 2 = reads it without examining
-#endif
 #ifndef SFE_TC_PREFETCH
 #define SFE_TC_PREFETCH 0
 #endif
@@ -82,24 +82,11 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
         "l"(a_desc), "l"(b_desc), "r"(kIdesc), "r"((uint32_t)accumulate), "r"(0u)
         : "memory");
 }
-// 32 lanes x 32 consecutive columns of 32 bits -> 32 registers per thread (lane = TMEM lane of the warp's quadrant).
-// The load is asynchronous: tmem_ld_wait makes the registers valid (they are operands of the wait so that no use moves above it).
+// TMEM loads are asynchronous: tmem_ld_wait2 makes the registers valid (they are operands of the wait so that no use moves above it).
 #define SFE_R32(v) "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), \
                    "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),   \
                    "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),   \
                    "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
-__device__ __forceinline__ void tmem_ld32_issue(uint32_t addr, int (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(addr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait(int (&v)[32]) { asm volatile("tcgen05.wait::ld.sync.aligned;" : SFE_R32(v)::"memory"); }
 __device__ __forceinline__ void tmem_ld_wait2(int (&v)[32], int (&w)[32]) {  // two loads in flight: both register sets hang on the wait
     asm volatile("tcgen05.wait::ld.sync.aligned;" : SFE_R32(v)::"memory");
     asm volatile("" : SFE_R32(w)::"memory");
@@ -161,23 +148,6 @@ __device__ __forceinline__ void insert8(int v0, int v1, int v2, int v3, int v4, 
     for (int e = 0; e < 8; e++)
         if (v[e] <= thr && idx + e < chunk_n) top2_one(k0, k1, (uint32_t)(v[e] + kKeyOffset) << 22 | (idx + e));
     thr = (int)(k1 >> 22) - kKeyOffset;  // 511 while fewer than two rows have been seen: everything passes
-}
-
-// 32 accumulators D' of one query (rows idx0 .. idx0 + 31 of the chunk): one test of their minimum against the query's
-// second-best distance drops them all; otherwise the groups of 8 whose own minimum passes are keyed and inserted
-__device__ __forceinline__ void examine32(const int (&v)[32], uint32_t &k0, uint32_t &k1, int &thr, uint32_t idx0, uint32_t chunk_n) {
-    int g[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-        g[j] = __vimin3_s32(__vimin3_s32(v[8 * j], v[8 * j + 1], v[8 * j + 2]), __vimin3_s32(v[8 * j + 3], v[8 * j + 4], v[8 * j + 5]),
-                            min(v[8 * j + 6], v[8 * j + 7]));
-    if (min(__vimin3_s32(g[0], g[1], g[2]), g[3]) <= thr) {
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-            if (g[j] <= thr)
-                insert8(v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5], v[8 * j + 6], v[8 * j + 7], idx0 + 8 * j,
-                        chunk_n, k0, k1, thr);
-    }
 }
 
 // 64 accumulators of one query as 32 packed pairs (rows idx0 .. idx0 + 63 of the chunk; register i = rows 2 i, 2 i + 1): one
@@ -358,20 +328,14 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                 // 128 columns as two packed loads of 64, both in flight: the stage goes back to its issuer one load latency after
                 // the commit
                 int buf[2][32];
-#if SFE_TC_ABLATE != 1
                 tmem_ld64p_issue(lane_addr, buf[0]);
                 tmem_ld64p_issue(lane_addr + 64u, buf[1]);
                 tmem_ld_wait2(buf[0], buf[1]);
-#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&S.d_empty[st]);
-#if SFE_TC_ABLATE == 0
                 examine64p(buf[0], k0, k1, thr, idx0, chunk_n);
                 examine64p(buf[1], k0, k1, thr, idx0 + 64, chunk_n);
-#elif SFE_TC_ABLATE == 2
-                k0 ^= (uint32_t)(buf[0][0] + buf[1][31] + buf[0][17]);
-#endif
             }
             ph_d_full = (ph_d_full & ~(1u << st)) | ph_full << st;
             // N = 256: two warps hold the halves of one query tile's columns: merge through shared memory
