@@ -32,12 +32,8 @@ namespace sfe {
 
 namespace {
 
-#ifndef SFE_TC_N
-#define SFE_TC_N 128
-#endif
-constexpr int kTileN = SFE_TC_N;              // database rows per B tile = N of one MMA: 128 or 256
-constexpr int kTilesPerStage = 256 / kTileN;  // a TMEM stage is 256 columns: two 128-column accumulators or one of 256
-constexpr int kGroupTiles = 2 * kTilesPerStage, kGroupQ = 128 * kGroupTiles;  // query tiles / queries per work item: 4 / 512 or 2 / 256
+constexpr int kTileN = 128;                   // database rows per B tile = N of one MMA (N = 256 tiles measured slower)
+constexpr int kGroupTiles = 4, kGroupQ = 128 * kGroupTiles;  // query tiles / queries per work item: one 128-column accumulator each
 constexpr int kEpiWarps = 16;  // 8 per TMEM stage: one per (lane quadrant, half of the stage's 256 columns); a stage's warps examine
                                // their registers while the other stage's warps wait for theirs
 #ifndef SFE_TC_PRODUCERS
@@ -175,11 +171,10 @@ template <int kBStages>
 struct TcSmemT {
     uint8_t a[kGroupTiles][kATileBytes];  // query tiles of the group
     uint8_t b[kBStages][kBTileBytes];     // database tiles
-    uint64_t b_full[kBStages], b_empty[kBStages], d_full[2], d_empty[2];
+    uint64_t b_full[kBStages], b_empty[kBStages], d_full[kGroupTiles], d_empty[kGroupTiles];  // one hand-off per accumulator
     uint32_t tmem_base;
-    uint32_t merge[kTileN == 256 ? 2 : 1][kTileN == 256 ? 128 : 1][2];  // N = 256: the warp of a tile's upper 128 columns hands its pair to the warp of the lower ones
 };
-constexpr int kBulkStages = kTileN == 128 ? 3 : 2;
+constexpr int kBulkStages = 3;
 
 // 1-D bulk copy global -> shared memory, completion in bytes on an mbarrier (TMA engine, no tensor map)
 __device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -211,17 +206,17 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
             mbar_init(&S.b_full[i], kBulk ? 1 : kProdWarps);  // one arrival per producer warp / the expect_tx of the bulk copy
             mbar_init(&S.b_empty[i], 2);  // tcgen05.commit of either MMA issuer
         }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kGroupTiles; i++) {
             mbar_init(&S.d_full[i], 1);   // tcgen05.commit
-            mbar_init(&S.d_empty[i], kEpiWarps / 2);  // one arrival per epilogue warp of the stage
+            mbar_init(&S.d_empty[i], kEpiWarps / kGroupTiles);  // one arrival per epilogue warp of the accumulator
         }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = S.tmem_base;
-    uint32_t ph_d_full = 0, ph_d_empty = 0;  // bit i = parity of the next wait on barrier i
-    uint32_t tb = 0;  // database tiles this thread's role has gone through so far: tile tb uses buffer tb % kBStages in phase tb / kBStages
+    uint32_t tb = 0;  // database tiles this thread's role has gone through so far: tile tb uses buffer tb % kBStages in phase
+                      // tb / kBStages, and every accumulator hand-off is in phase tb & 1
 
     for (int item = blockIdx.x; item < groups * chunks; item += gridDim.x) {
         const int g = item / chunks, chunk = item % chunks;
@@ -240,24 +235,25 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         if (warp <= 1) {
             // ===== MMA issuers: warp h feeds TMEM stage h (query tiles kTilesPerStage h ..), so the wait -> issue -> commit chains
             // of the two stages run side by side ==========================================================================
-            const int h = warp, st = warp;  // stage h: columns [256 h, 256 h + 256)
+            const int h = warp;  // accumulators 2 h and 2 h + 1: columns [256 h, 256 h + 256)
             for (int n = 0; n < ntiles; n++, tb++) {
                 const int bi = (int)(tb % kBStages);
                 mbar_wait(&S.b_full[bi], (tb / kBStages) & 1);
-                mbar_wait(&S.d_empty[st], ((ph_d_empty >> st) & 1) ^ 1);  // first use passes: the barrier starts in phase 0
-                ph_d_empty ^= 1u << st;
-                tc_fence_after();
-                if (lane == 0) {
-                    for (int t = 0; t < kTilesPerStage; t++) {
-                        const uint32_t a_addr = smem_u32(S.a[kTilesPerStage * h + t]), b_addr = smem_u32(S.b[bi]);
-                        const uint32_t d = tmem + (uint32_t)(st * 256 + t * kTileN);
+                const uint32_t b_addr = smem_u32(S.b[bi]);
+                for (int t = 0; t < 2; t++) {  // each accumulator is handed over on its own: its warps start after 8 MMAs, not 16
+                    const int acc = 2 * h + t;
+                    mbar_wait(&S.d_empty[acc], (tb & 1) ^ 1);  // first use passes: the barrier starts in phase 0
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_addr = smem_u32(S.a[acc]), d = tmem + (uint32_t)(128 * acc);
 #pragma unroll
                         for (int k = 0; k < 8; k++)  // K = 32 per instruction: two 16-byte chunks
                             mma_i8(d, smem_desc(a_addr + k * 2 * kLBO), smem_desc(b_addr + k * 2 * kLBO), k > 0);
+                        tc_commit(&S.d_full[acc]);
                     }
-                    tc_commit(&S.d_full[st]);
-                    tc_commit(&S.b_empty[bi]);
+                    __syncwarp();
                 }
+                if (lane == 0) tc_commit(&S.b_empty[bi]);
                 __syncwarp();
             }
         } else if (warp < 2 + kProdWarps) {
@@ -308,44 +304,29 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
         } else {
             // ===== epilogue: TMEM -> keys -> running top-2 per query ====================================================
             const int ew = warp - 2 - kProdWarps, quad = warp & 3;  // a warp reads the TMEM lanes of quadrant warp % 4
-            const int st = ew >> 3;                     // the stage this warp serves
-            const int half = (ew >> 2) & 1;             // ... and which 128 of its 256 columns
-            const int tile = kTilesPerStage * st + (half * 128) / kTileN;  // the query tile those columns belong to
-            const int col0 = (half * 128) % kTileN;                        // and their first database row inside a B tile
+            const int tile = ew >> 2;                   // the query tile = accumulator this warp serves (4 warps each: one per quadrant)
             const int row = quad * 32 + lane;           // query row inside the tile
             uint32_t k0 = kNoKey32, k1 = kNoKey32;
             int thr = (int)(kNoKey32 >> 22) - kKeyOffset;
             const uint32_t chunk_n = (uint32_t)(r1 - r0);
-            const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(st * 256 + half * 128);
-            uint32_t ph_full = (ph_d_full >> st) & 1;
-            for (int n = 0; n < ntiles; n++) {
-                const uint32_t idx0 = (uint32_t)n * kTileN + (uint32_t)col0;
-                mbar_wait(&S.d_full[st], ph_full);
-                ph_full ^= 1;
+            const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(128 * tile);
+            for (int n = 0; n < ntiles; n++, tb++) {
+                const uint32_t idx0 = (uint32_t)n * kTileN;
+                mbar_wait(&S.d_full[tile], tb & 1);
                 tc_fence_after();
-                // 128 columns, 32 at a time, the next load in flight while one is examined; the stage goes back to the MMA
-                // issuer as soon as the last load has landed
-                // 128 columns as two packed loads of 64, both in flight: the stage goes back to its issuer one load latency after
-                // the commit
+                // 128 columns as two packed loads of 64, both in flight: the accumulator goes back to its issuer one load latency
+                // after the commit
                 int buf[2][32];
                 tmem_ld64p_issue(lane_addr, buf[0]);
                 tmem_ld64p_issue(lane_addr + 64u, buf[1]);
                 tmem_ld_wait2(buf[0], buf[1]);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&S.d_empty[st]);
+                if (lane == 0) mbar_arrive(&S.d_empty[tile]);
                 examine64p(buf[0], k0, k1, thr, idx0, chunk_n);
                 examine64p(buf[1], k0, k1, thr, idx0 + 64, chunk_n);
             }
-            ph_d_full = (ph_d_full & ~(1u << st)) | ph_full << st;
-            // N = 256: two warps hold the halves of one query tile's columns: merge through shared memory
-            if (kTileN == 256 && half == 1) {
-                S.merge[st][row][0] = k0;
-                S.merge[st][row][1] = k1;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // the epilogue warps only
-            if (kTileN == 128 || half == 0) {
-                if (kTileN == 256) top2_pair(k0, k1, S.merge[st][row][0], S.merge[st][row][1]);
+            {
                 const int qi = q0 + tile * 128 + row;
                 if (qi < q) {
                     const uint4 *p = (const uint4 *)(queries + (size_t)qi * 32);
@@ -364,7 +345,6 @@ knn2_tc_kernel(const uint8_t *__restrict__ db, long long rows, long long idx_bas
                     dst[1] = o[1];
                 }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");  // merge[] is free for the next item
         }
     }
     tc_fence_before();
