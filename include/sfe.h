@@ -362,7 +362,11 @@ int sfe_projection_merge_dev(sfe_matcher *m, const uint64_t *keys_dev, int shard
                              int32_t *kp_to_query_dev, int32_t *kp_dist_dev);
 
 /* Brute-force top-2 over a resident descriptor database shard.
- * idx_base = global index of the shard's first row (multi-GPU sharding). */
+ * idx_base = global index of the shard's first row (multi-GPU sharding).
+ * Device memory: 32 B per row; a shard of >= 65536 rows that is searched with >= 256 queries at a time
+ * additionally keeps its rows as int8 operand tiles of the tensor-core kernel (256 B per row, built at
+ * the first such search when that fits SFE_KNN_TILES_MAX_GB -- default 16 -- and a quarter of the free
+ * memory; 0 disables it). */
 int sfe_db_create(sfe_matcher *m, const uint8_t *desc_host, int64_t rows, int64_t idx_base,
                   sfe_db **out);
 int sfe_db_destroy(sfe_db *db);
