@@ -757,11 +757,19 @@ def test_knn2_tensor_core_kernel_equals_popc_kernel_and_oracle(gpu, oracle, monk
         db[rows - 1] = db[7]
         qs[1] = db[7]
     ref = oracle.knn2(qs, db, nthreads=os.cpu_count() or 4)
-    for mode in ("1", "0"):
+    # tensor cores with the map's rows kept as ready-made operand tiles (bulk copies; maps of >= 65536 rows searched with >= 256
+    # queries), tensor cores with the producer warps unpacking the rows, and the XOR / POPC kernels
+    for mode, tiles_gb in (("1", None), ("1", "0"), ("0", None)):
         monkeypatch.setenv("SFE_KNN_TC", mode)
+        if tiles_gb is not None:
+            monkeypatch.setenv("SFE_KNN_TILES_MAX_GB", tiles_gb)
         m = api.Matcher()
-        got = m.knn2(m.create_db(db), qs)
-        assert np.array_equal(got, ref), f"SFE_KNN_TC={mode}: {(got != ref).any(1).sum()} of {q} queries differ"
+        h = m.create_db(db)
+        for _ in range(2):  # the second search finds the tiles already built
+            got = m.knn2(h, qs)
+            assert np.array_equal(got, ref), f"SFE_KNN_TC={mode} tiles={tiles_gb}: {(got != ref).any(1).sum()} of {q} queries differ"
+        if tiles_gb is not None:
+            monkeypatch.delenv("SFE_KNN_TILES_MAX_GB")
     if rows > 300:
         assert ref[1].tolist() == [7, 0, rows - 1, 0]
 
