@@ -1421,7 +1421,7 @@ struct sfe_extractor {
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // [0] the blur beside FAST + quadtree, [1] the matchers of an asynchronous call beside the next
                                                         // call, [2] FAST + quadtree of levels 0-1 of a few-image call beside the rest of the pyramid
     cudaEvent_t ev_fork[3] = {}, ev_join[3] = {};
-    int dev_split = 1;                              // SFE_DEV_SPLIT=n: a resident stereo batch runs as n sub-batches on n streams
+    int dev_split = 3;                              // SFE_DEV_SPLIT=n: a resident stereo batch runs as n sub-batches on n streams
     bool split_small = false;                       // SFE_SPLIT_SMALL=1: few-image calls run FAST + quadtree of levels 0-1 beside the pyramid tail
                                                     // (measured: no gain, 195 vs 198 us per stereo pair)
     int octree_ctas = 0;    // SFE_OCTREE_CTAS: > 0 = persistent quadtree kernel with that many CTAs
@@ -1747,6 +1747,9 @@ static int build_plan(sfe_extractor *ex, int w, int h) {
     SFE_CUDA(ex->d_cand.ensure((size_t)ex->cand_stride * n));
     SFE_CUDA(ex->d_kpst.ensure((size_t)ex->kpst_stride * n));
     SFE_CUDA(ex->d_counts.ensure((size_t)n * (2 * nl + 1) + 1));  // cand_count | kp_count | scratch_next | flags
+    // (an asynchronous handle only clears its error flags at sfe_extractor_wait: they must not start as whatever the
+    // allocation held)
+    SFE_CUDA(cudaMemsetAsync(ex->d_counts.p, 0, sizeof(int) * ex->d_counts.n, ex->stream));
     SFE_CUDA(ex->d_tiles.ensure(std::max<size_t>(ex->tiles.size(), 1)));
     SFE_CUDA(ex->d_segs.ensure(std::max<size_t>(ex->segs.size(), 1)));
     if (!ex->segs.empty())
@@ -2707,7 +2710,9 @@ static int stereo_frames_dev_once(sfe_extractor *ex, const uint8_t *left_dev, co
         // the tail of a launch) the issue slots it leaves idle go to the FAST / blur / descriptor kernels of another.
         SFE_CUDA(cudaEventRecord(ex->ev_start, ex->stream));  // the counter reset precedes every sub-batch
         for (int c = 1; c < nsplit; c++) SFE_CUDA(cudaStreamWaitEvent(ex->extra[c - 1], ex->ev_start, 0));
-        for (int c = 0; c < nsplit; c++) {
+        // (the side streams first: while a previous asynchronous call's matchers are still pending, each of them waits for that
+        // tail before its descriptor kernel overwrites the arrays the matchers read; the main stream's join clears the flag)
+        for (int c = nsplit - 1; c >= 0; c--) {
             const int f0 = (int)((long long)frames * c / nsplit), f1 = (int)((long long)frames * (c + 1) / nsplit);
             cudaStream_t sc = c == 0 ? ex->stream : ex->extra[c - 1];
             if ((rc = enqueue_extract(ex, sc, chunk_of(S, f0, f1, true), 2 * (f1 - f0), chunk_of(O, f0))) != SFE_OK) return rc;

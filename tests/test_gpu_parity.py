@@ -478,6 +478,43 @@ def test_async_queue_with_matchers_on_the_side_stream(gpu):
     ex.set_async(False)
 
 
+def test_resident_batch_split_over_streams(gpu, monkeypatch):
+    """A resident batch of >= 48 stereo frames runs as three sub-batches on three streams (SFE_DEV_SPLIT, default 3), also when
+    asynchronous calls queue back to back onto the SAME output arrays while the previous call's matchers are still running on
+    the side stream: the bytes must equal the unsplit, synchronous run."""
+    F, w, h = 48, 320, 200
+    def long_sequence(seed):  # three 16-frame sequences back to back
+        parts = [synth.stereo_sequence(seed + 10 * k, 16, 4, w, h) for k in range(F // 16)]
+        return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+    seqs = [long_sequence(s) for s in (5, 6)]
+    cam = api.Camera.make(300.0, 300.0, w / 2.0, h / 2.0, (0, 0, 0, 0), w, h)
+    tp = api.TrackParams.make(cam, 0.5, None, 30.0)
+    monkeypatch.setenv("SFE_DEV_SPLIT", "1")
+    ref_ex = api.ORBextractor(600, 1.2, 4, 20, 7, max_images=2 * F)
+    cap = ref_ex.cap
+    sync = [ref_ex.stereo_sequence(L, R, tp) for L, R in seqs]
+    monkeypatch.delenv("SFE_DEV_SPLIT")
+    ex = api.ORBextractor(600, 1.2, 4, 20, 7, max_images=2 * F)
+    assert ex.cap == cap
+    spec = {"kps_l": (28, api.KP_DTYPE, (F, cap)), "desc_l": (32, np.uint8, (F, cap, 32)), "n_l": (0, np.int32, (F,)),
+            "kps_r": (28, api.KP_DTYPE, (F, cap)), "desc_r": (32, np.uint8, (F, cap, 32)), "n_r": (0, np.int32, (F,)),
+            "stereo_idx": (4, np.int32, (F, cap)), "stereo_dist": (4, np.int32, (F, cap)), "track_idx": (4, np.int32, (F, cap)),
+            "track_dist": (4, np.int32, (F, cap))}
+    imgs = [(api.DeviceBuffer(L.nbytes).upload(L), api.DeviceBuffer(R.nbytes).upload(R)) for L, R in seqs]
+    bufs = {k: api.DeviceBuffer(max(b * cap * F, 4 * F)) for k, (b, _, _) in spec.items()}
+    ex.set_async(True)
+    for i in (0, 1, 0, 1, 1, 0):  # the last call must win, untouched by the tails of the earlier ones
+        ex.stereo_sequence_dev(imgs[i][0].ptr, imgs[i][1].ptr, F, w, h, {k: b.ptr for k, b in bufs.items()}, tp)
+    ex.wait()
+    got = {k: bufs[k].download(shape, dt) for k, (_, dt, shape) in spec.items()}
+    _stereo_equal(got, sync[0], F)
+    for f in range(F):
+        n = sync[0]["n_l"][f]
+        assert np.array_equal(got["track_idx"][f, :n], sync[0]["track_idx"][f, :n])
+        assert np.array_equal(got["track_dist"][f, :n], sync[0]["track_dist"][f, :n])
+    ex.set_async(False)
+
+
 def test_execution_variants_of_the_resident_path_agree(gpu, monkeypatch):
     """Blur forked beside a persistent quadtree or serial, TMA or lane-staged windows in the descriptor kernel, matchers on
     the side stream or not: every switch of DESIGN.md §10 leaves the bytes unchanged."""
