@@ -2647,7 +2647,20 @@ static int extract_batch_dev_once(sfe_extractor *ex, const uint8_t *images_dev, 
     const ImgSet S = make_imgset(ex, images_dev, images_dev, count, image_stride, stride);
     prepare_l0_maps(ex, images_dev, images_dev, count, count, image_stride, stride);
     if ((rc = reset_counters(ex)) != SFE_OK) return rc;
-    if ((rc = enqueue_extract(ex, ex->stream, S, count, O)) != SFE_OK) return rc;
+    const int nsplit = !ex->profiling && count >= 32 * ex->dev_split ? std::min(ex->dev_split, ex->n_compute) : 1;
+    if (nsplit <= 1) {
+        if ((rc = enqueue_extract(ex, ex->stream, S, count, O)) != SFE_OK) return rc;
+    } else {  // sub-batches on as many streams, as in stereo_frames_dev_once
+        SFE_CUDA(cudaEventRecord(ex->ev_start, ex->stream));
+        for (int c = 1; c < nsplit; c++) SFE_CUDA(cudaStreamWaitEvent(ex->extra[c - 1], ex->ev_start, 0));
+        for (int c = nsplit - 1; c >= 0; c--) {
+            const int f0 = (int)((long long)count * c / nsplit), f1 = (int)((long long)count * (c + 1) / nsplit);
+            cudaStream_t sc = c == 0 ? ex->stream : ex->extra[c - 1];
+            if ((rc = enqueue_extract(ex, sc, chunk_of(S, f0, f1, false), f1 - f0, chunk_of(O, f0))) != SFE_OK) return rc;
+            if (c > 0) SFE_CUDA(cudaEventRecord(ex->ev_done[c], sc));
+        }
+        for (int c = 1; c < nsplit; c++) SFE_CUDA(cudaStreamWaitEvent(ex->stream, ex->ev_done[c], 0));
+    }
     ex->last = S;
     ex->last_count = count;
     return finish_dev(ex, count);

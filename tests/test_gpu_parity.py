@@ -513,6 +513,17 @@ def test_resident_batch_split_over_streams(gpu, monkeypatch):
         assert np.array_equal(got["track_idx"][f, :n], sync[0]["track_idx"][f, :n])
         assert np.array_equal(got["track_dist"][f, :n], sync[0]["track_dist"][f, :n])
     ex.set_async(False)
+    # the same for the image-only entry point: 96 resident images = three sub-batches of 32
+    both = np.concatenate([seqs[0][0], seqs[0][1]])
+    dimg = api.DeviceBuffer(both.nbytes).upload(both)
+    dk, dd, dn = api.DeviceBuffer(28 * cap * 2 * F), api.DeviceBuffer(32 * cap * 2 * F), api.DeviceBuffer(4 * 2 * F)
+    ex.extract_batch_dev(dimg.ptr, 2 * F, w, h, dk.ptr, dd.ptr, dn.ptr)
+    n = dn.download((2 * F,), np.int32)
+    k, d = dk.download((2 * F, cap), api.KP_DTYPE), dd.download((2 * F, cap, 32), np.uint8)
+    for f in range(F):
+        for side, key_n, key_k, key_d in ((f, "n_l", "kps_l", "desc_l"), (F + f, "n_r", "kps_r", "desc_r")):
+            m = sync[0][key_n][f]
+            assert n[side] == m and np.array_equal(k[side, :m], sync[0][key_k][f, :m]) and np.array_equal(d[side, :m], sync[0][key_d][f, :m])
 
 
 def test_execution_variants_of_the_resident_path_agree(gpu, monkeypatch):
